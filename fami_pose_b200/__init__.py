@@ -1,0 +1,60 @@
+"""fami_pose_b200 -- B200 (sm_100a) implementation of the FAMI-Pose forward/backward hot path.
+
+Python mirror of the reference's operator interface (posetimation/layers, posetimation/backbones,
+posetimation/zoo/Alignment, posetimation/loss, torchvision DeformConv2d, kornia warp_affine) over
+the C ABI in include/fami_b200.h.  There is no CPU / PyTorch fallback: ops raise if the CUDA library
+is missing or if they are given CPU tensors.
+"""
+from . import _lib, ops  # noqa: F401
+from .backbones import HighResolutionModule, HRNet, HRNetPlus  # noqa: F401
+from .decode import argmax_indices, get_max_preds  # noqa: F401
+from .layers import (BasicBlock, Bottleneck, ChainOfBasicBlocks, DeformConv2d, Interpolate,  # noqa: F401
+                     conv_bn_relu)
+from .loss import JointMSELoss, combine_losses  # noqa: F401
+from .ops import get_precision, set_precision  # noqa: F401
+from .zoo import Alignment_V15  # noqa: F401
+
+__all__ = ["Alignment_V15", "HRNetPlus", "HRNet", "HighResolutionModule", "BasicBlock", "Bottleneck",
+           "ChainOfBasicBlocks", "Interpolate", "conv_bn_relu", "DeformConv2d", "JointMSELoss",
+           "combine_losses", "get_max_preds", "argmax_indices", "set_precision", "get_precision",
+           "patch_reference"]
+
+
+def patch_reference():
+    """Rebinds the names the reference resolves at import time to the fami modules, so
+    the reference's own model definitions / engine call the B200 kernels unchanged.  Call after the
+    reference packages are importable and before models are constructed.  Returns the patched names."""
+    import importlib
+    import sys
+    import types
+    from . import kornia_shim
+    patched = []
+
+    def rebind(modname, **names):
+        try:
+            mod = importlib.import_module(modname)
+        except Exception:
+            return
+        for k, v in names.items():
+            setattr(mod, k, v)
+            patched.append("%s.%s" % (modname, k))
+
+    layer_names = dict(BasicBlock=BasicBlock, Bottleneck=Bottleneck, Interpolate=Interpolate,
+                       ChainOfBasicBlocks=ChainOfBasicBlocks)
+    rebind("posetimation.layers.basic_model", **layer_names)
+    rebind("posetimation.layers.basic_layer", conv_bn_relu=conv_bn_relu)
+    rebind("posetimation.layers", conv_bn_relu=conv_bn_relu, **layer_names)
+    rebind("posetimation.backbones.hrnet", BasicBlock=BasicBlock, Bottleneck=Bottleneck, Interpolate=Interpolate,
+           HighResolutionModule=HighResolutionModule, HRNetPlus=HRNetPlus, HRNet=HRNet,
+           blocks_dict={'BASIC': BasicBlock, 'BOTTLENECK': Bottleneck})
+    rebind("posetimation.loss.mse_loss", JointMSELoss=JointMSELoss)
+    if "kornia" not in sys.modules:
+        k = types.ModuleType("kornia")
+        k.geometry = types.ModuleType("kornia.geometry")
+        sys.modules["kornia"] = k
+        sys.modules["kornia.geometry"] = k.geometry
+    sys.modules["kornia"].geometry.warp_affine = kornia_shim.warp_affine
+    patched.append("kornia.geometry.warp_affine")
+    rebind("posetimation.zoo.Alignment.Alignment_V15", conv_bn_relu=conv_bn_relu,
+           ChainOfBasicBlocks=ChainOfBasicBlocks, HRNetPlus=HRNetPlus, DeformConv2d=DeformConv2d)
+    return patched

@@ -1,0 +1,264 @@
+// extern "C" surface of libfami_b200.so (see include/fami_b200.h).  Argument validation lives
+// here; kernels live in conv_simt.cu / conv_tc.cu / dcn.cu / misc.cu.
+#include <atomic>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace fami {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// kernels implemented in other translation units
+int conv_f32_launch(const fami_conv_desc* d, const float* x, const float* w, const float* scale,
+                    const float* shift, const float* res, float* y, double* stats, cudaStream_t st);
+int pack_w_f32_launch(const float* w, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t st);
+int dcn_f32_simt_launch(const fami_dcn_desc* d, const float* x, const float* off, const float* mask,
+                        const float* w, const float* bias, float* out, cudaStream_t st);
+int conv_bf16_tc_supported(const fami_conv_desc* d);
+int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale,
+                        const float* shift, const void* res, void* y, double* stats, cudaStream_t st);
+int64_t pack_w_bf16_elems(int Cout, int Cin, int kh, int kw);
+int pack_w_bf16_launch(const float* w, void* out, int Cout, int Cin, int kh, int kw, cudaStream_t st);
+int dcn_bwd_launch(const fami_dcn_desc* d, const float* x, const float* off, const float* mask, const float* w,
+                   const float* go, float* gx, float* goff, float* gmask, float* gw, float* gb, cudaStream_t st);
+int warp_translate_bwd_launch(const float* src, int sp, const float* txy, const float* go, int gop, float* gs,
+                              int gsp, float* gtxy, int B, int H, int W, int C, cudaStream_t st);
+int nchw_to_nhwc_launch(const float*, int64_t, void*, int, int, int, int, int, int, cudaStream_t);
+int nhwc_to_nchw_launch(const void*, int, int, float*, int, int, int, int, cudaStream_t);
+int warp_translate_fwd_launch(const void*, int, const float*, void*, int, int, int, int, int, int, cudaStream_t);
+int sub_bcast_launch(const void*, const void*, void*, int, int64_t, int, cudaStream_t);
+int linear_fwd_launch(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
+int copy2d_launch(const void*, int, void*, int, int, int64_t, int, cudaStream_t);
+int bn_finalize_launch(const double*, const float*, const float*, float*, float*, float*, float*, float*, float*, int,
+                       int64_t, float, float, cudaStream_t);
+int bn_apply_act_launch(const void*, int, const float*, const float*, const void*, int, void*, int, int, int, int, int,
+                        int, int, int, cudaStream_t);
+int joint_mse_launch(const void*, int, int, const float*, const float*, float*, float*, float, int, int, int, int,
+                     cudaStream_t);
+int softmax_pkl_launch(const void*, int, const void*, int, int, float*, int, int, int, float, cudaStream_t);
+int argmax_hw_launch(const void*, int, int, int32_t*, float*, int, int, int, cudaStream_t);
+
+}  // namespace fami
+
+using namespace fami;
+
+static inline bool valid_dtype(int dt) { return dt == FAMI_F32 || dt == FAMI_BF16; }
+static inline size_t esize(int dt) { return dt == FAMI_F32 ? 4 : 2; }
+static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+extern "C" {
+
+const char* fami_last_error(void) { return g_err; }
+int fami_abi_version(void) { return FAMI_ABI_VERSION; }
+int64_t fami_launch_count(void) { return g_launches.load(); }
+
+int fami_nchw_to_nhwc(const float* src, int64_t src_n_stride, void* dst, int dst_dtype, int N, int C, int H, int W,
+                      int dst_pitch, void* stream) {
+  FAMI_CHECK_ARG(src && dst, "fami_nchw_to_nhwc: null pointer");
+  FAMI_CHECK_ARG(valid_dtype(dst_dtype), "fami_nchw_to_nhwc: bad dtype %d", dst_dtype);
+  FAMI_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && dst_pitch >= C, "fami_nchw_to_nhwc: bad shape");
+  return nchw_to_nhwc_launch(src, src_n_stride, dst, dst_dtype, N, C, H, W, dst_pitch, (cudaStream_t)stream);
+}
+
+int fami_nhwc_to_nchw(const void* src, int src_dtype, int src_pitch, float* dst, int N, int C, int H, int W,
+                      void* stream) {
+  FAMI_CHECK_ARG(src && dst, "fami_nhwc_to_nchw: null pointer");
+  FAMI_CHECK_ARG(valid_dtype(src_dtype), "fami_nhwc_to_nchw: bad dtype %d", src_dtype);
+  FAMI_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && src_pitch >= C, "fami_nhwc_to_nchw: bad shape");
+  return nhwc_to_nchw_launch(src, src_dtype, src_pitch, dst, N, C, H, W, (cudaStream_t)stream);
+}
+
+int fami_conv_cout_pad(int Cout) { return ((Cout + 15) / 16) * 16; }
+
+int64_t fami_packed_weight_elems(int Cout, int Cin, int kh, int kw, int dtype) {
+  if (dtype == FAMI_BF16) return pack_w_bf16_elems(Cout, Cin, kh, kw);
+  int64_t kpad = ((int64_t)kh * kw * Cin + 15) / 16 * 16;
+  return kpad * fami_conv_cout_pad(Cout);
+}
+
+int fami_pack_conv_weight(const float* w_oihw, void* w_packed, int Cout, int Cin, int kh, int kw, int dtype,
+                          void* stream) {
+  FAMI_CHECK_ARG(w_oihw && w_packed, "fami_pack_conv_weight: null pointer");
+  FAMI_CHECK_ARG(valid_dtype(dtype), "fami_pack_conv_weight: bad dtype %d", dtype);
+  FAMI_CHECK_ARG(Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "fami_pack_conv_weight: bad shape");
+  if (dtype == FAMI_BF16) return pack_w_bf16_launch(w_oihw, w_packed, Cout, Cin, kh, kw, (cudaStream_t)stream);
+  return pack_w_f32_launch(w_oihw, (float*)w_packed, Cout, Cin, kh, kw, (cudaStream_t)stream);
+}
+
+int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w_packed, const float* scale,
+                           const float* shift, const void* residual, void* y, double* stats_out, void* stream) {
+  FAMI_CHECK_ARG(d && x && w_packed && y, "fami_conv2d_bn_act_fwd: null pointer");
+  FAMI_CHECK_ARG(valid_dtype(d->dtype), "fami_conv2d_bn_act_fwd: bad dtype %d", d->dtype);
+  FAMI_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "fami_conv2d_bn_act_fwd: bad shape");
+  FAMI_CHECK_ARG(d->kh == d->kw && (d->kh == 1 || d->kh == 3), "fami_conv2d_bn_act_fwd: kernel %dx%d unsupported",
+                 d->kh, d->kw);
+  FAMI_CHECK_ARG(d->stride >= 1 && d->dil >= 1 && d->pad >= 0, "fami_conv2d_bn_act_fwd: bad stride/dil/pad");
+  int Ho = (d->H + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
+  int Wo = (d->W + 2 * d->pad - d->dil * (d->kw - 1) - 1) / d->stride + 1;
+  FAMI_CHECK_ARG(Ho == d->Ho && Wo == d->Wo, "fami_conv2d_bn_act_fwd: Ho/Wo (%d,%d) inconsistent, expected (%d,%d)",
+                 d->Ho, d->Wo, Ho, Wo);
+  FAMI_CHECK_ARG(d->up == 1 || d->up == 2 || d->up == 4 || d->up == 8, "fami_conv2d_bn_act_fwd: up=%d", d->up);
+  FAMI_CHECK_ARG(d->in_pitch >= d->Cin && d->out_pitch >= d->Cout, "fami_conv2d_bn_act_fwd: pitch < channels");
+  FAMI_CHECK_ARG(!residual || d->res_pitch >= d->Cout, "fami_conv2d_bn_act_fwd: res_pitch < Cout");
+  FAMI_CHECK_ARG(!d->stats || stats_out, "fami_conv2d_bn_act_fwd: stats requested without stats_out");
+  FAMI_CHECK_ARG((int64_t)d->N * d->Ho * d->Wo < (1ll << 31), "fami_conv2d_bn_act_fwd: too many output pixels");
+  if (d->dtype == FAMI_BF16) {
+    FAMI_CHECK_ARG(conv_bf16_tc_supported(d), "fami_conv2d_bn_act_fwd: shape not supported by the bf16 tensor path");
+    return conv_bf16_tc_launch(d, x, w_packed, scale, shift, residual, y, stats_out, (cudaStream_t)stream);
+  }
+  return conv_f32_launch(d, (const float*)x, (const float*)w_packed, scale, shift, (const float*)residual, (float*)y,
+                         stats_out, (cudaStream_t)stream);
+}
+
+int fami_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float* scale, float* shift, float* save_mean, float* save_invstd, int C,
+                     int64_t count, float eps, float momentum, void* stream) {
+  FAMI_CHECK_ARG(stats && scale && shift && C > 0 && count > 0, "fami_bn_finalize: bad arguments");
+  return bn_finalize_launch(stats, gamma, beta, running_mean, running_var, scale, shift, save_mean, save_invstd, C,
+                            count, eps, momentum, (cudaStream_t)stream);
+}
+
+int fami_bn_apply_act(const void* x, int x_pitch, const float* scale, const float* shift, const void* residual,
+                      int res_pitch, void* y, int y_pitch, int dtype, int N, int Ho, int Wo, int C, int up, int relu,
+                      void* stream) {
+  FAMI_CHECK_ARG(x && scale && shift && y, "fami_bn_apply_act: null pointer");
+  FAMI_CHECK_ARG(valid_dtype(dtype), "fami_bn_apply_act: bad dtype");
+  FAMI_CHECK_ARG(up == 1 || up == 2 || up == 4 || up == 8, "fami_bn_apply_act: up=%d", up);
+  return bn_apply_act_launch(x, x_pitch, scale, shift, residual, res_pitch, y, y_pitch, dtype, N, Ho, Wo, C, up, relu,
+                             (cudaStream_t)stream);
+}
+
+static int check_dcn(const fami_dcn_desc* d, const char* who) {
+  FAMI_CHECK_ARG(d, "%s: null desc", who);
+  FAMI_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->Cout > 0 && d->G > 0, "%s: bad shape", who);
+  FAMI_CHECK_ARG(d->kh == 3 && d->kw == 3 && d->stride == 1, "%s: only 3x3 stride-1 deformable kernels", who);
+  FAMI_CHECK_ARG(d->pad == d->dil, "%s: pad (%d) must equal dilation (%d) (same-size output)", who, d->pad, d->dil);
+  /* torchvision raises for channels not divisible by groups (deform_conv.py:129-132) */
+  FAMI_CHECK_ARG(d->C % d->G == 0, "%s: in_channels %d not divisible by offset groups %d", who, d->C, d->G);
+  FAMI_CHECK_ARG((d->C / d->G) % 4 == 0 && d->C % 16 == 0,
+                 "%s: channels per offset group must be a multiple of 4 and C a multiple of 16 (C=%d G=%d)", who,
+                 d->C, d->G);
+  FAMI_CHECK_ARG(d->x_pitch >= d->C && d->off_pitch >= 18 * d->G && d->mask_pitch >= 9 * d->G &&
+                     d->out_pitch >= d->Cout,
+                 "%s: pitch too small", who);
+  FAMI_CHECK_ARG((int64_t)d->B * d->H * d->W < (1ll << 31), "%s: too many pixels", who);
+  return 0;
+}
+
+int fami_dcn_fwd(const fami_dcn_desc* d, const void* x, const void* offset, const void* mask, const void* w_packed,
+                 const float* bias, void* out, void* stream) {
+  if (int e = check_dcn(d, "fami_dcn_fwd")) return e;
+  FAMI_CHECK_ARG(x && offset && mask && w_packed && out, "fami_dcn_fwd: null pointer");
+  FAMI_CHECK_ARG(d->dtype == FAMI_F32, "fami_dcn_fwd: dtype %d not supported yet", d->dtype);
+  FAMI_CHECK_ARG(aligned(x, 16) && d->x_pitch % 4 == 0, "fami_dcn_fwd: x must be 16B aligned with pitch %% 4 == 0");
+  FAMI_CHECK_ARG(aligned(offset, 8) && d->off_pitch % 2 == 0, "fami_dcn_fwd: offset must be 8B aligned, even pitch");
+  return dcn_f32_simt_launch(d, (const float*)x, (const float*)offset, (const float*)mask, (const float*)w_packed,
+                             bias, (float*)out, (cudaStream_t)stream);
+}
+
+int fami_dcn_bwd(const fami_dcn_desc* d, const float* x, const float* offset, const float* mask,
+                 const float* w_packed, const float* grad_out, float* grad_x, float* grad_offset, float* grad_mask,
+                 float* grad_w_packed, float* grad_bias, void* stream) {
+  if (int e = check_dcn(d, "fami_dcn_bwd")) return e;
+  FAMI_CHECK_ARG(x && offset && mask && w_packed && grad_out, "fami_dcn_bwd: null pointer");
+  FAMI_CHECK_ARG(d->dtype == FAMI_F32, "fami_dcn_bwd: fp32 storage only");
+  return dcn_bwd_launch(d, x, offset, mask, w_packed, grad_out, grad_x, grad_offset, grad_mask, grad_w_packed,
+                        grad_bias, (cudaStream_t)stream);
+}
+
+int fami_warp_translate_fwd(const void* src, int src_pitch, const float* txy, void* out, int out_pitch, int dtype,
+                            int B, int H, int W, int C, void* stream) {
+  FAMI_CHECK_ARG(src && txy && out, "fami_warp_translate_fwd: null pointer");
+  FAMI_CHECK_ARG(valid_dtype(dtype), "fami_warp_translate_fwd: bad dtype");
+  FAMI_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "fami_warp_translate_fwd: C must be a multiple of 4");
+  FAMI_CHECK_ARG(src_pitch % 4 == 0 && out_pitch % 4 == 0 && src_pitch >= C && out_pitch >= C,
+                 "fami_warp_translate_fwd: pitches must be multiples of 4 and >= C");
+  FAMI_CHECK_ARG(aligned(src, 4 * esize(dtype)) && aligned(out, 4 * esize(dtype)),
+                 "fami_warp_translate_fwd: pointers must be aligned to 4 elements");
+  return warp_translate_fwd_launch(src, src_pitch, txy, out, out_pitch, dtype, B, H, W, C, (cudaStream_t)stream);
+}
+
+int fami_warp_translate_bwd(const float* src, int src_pitch, const float* txy, const float* grad_out, int go_pitch,
+                            float* grad_src, int gs_pitch, float* grad_txy, int B, int H, int W, int C,
+                            void* stream) {
+  FAMI_CHECK_ARG(src && txy && grad_out, "fami_warp_translate_bwd: null pointer");
+  FAMI_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0, "fami_warp_translate_bwd: bad shape");
+  return warp_translate_bwd_launch(src, src_pitch, txy, grad_out, go_pitch, grad_src, gs_pitch, grad_txy, B, H, W, C,
+                                   (cudaStream_t)stream);
+}
+
+int fami_sub_bcast(const void* a, const void* b, void* out, int dtype, int64_t n, int rep, void* stream) {
+  FAMI_CHECK_ARG(a && b && out, "fami_sub_bcast: null pointer");
+  FAMI_CHECK_ARG(valid_dtype(dtype), "fami_sub_bcast: bad dtype");
+  FAMI_CHECK_ARG(n > 0 && n % 4 == 0 && rep > 0, "fami_sub_bcast: n must be a positive multiple of 4");
+  FAMI_CHECK_ARG(aligned(a, 4 * esize(dtype)) && aligned(b, 4 * esize(dtype)) && aligned(out, 4 * esize(dtype)),
+                 "fami_sub_bcast: pointers must be aligned to 4 elements");
+  return sub_bcast_launch(a, b, out, dtype, n, rep, (cudaStream_t)stream);
+}
+
+int fami_copy2d(const void* src, int src_pitch, void* dst, int dst_pitch, int dtype, int64_t rows, int cols,
+                void* stream) {
+  FAMI_CHECK_ARG(src && dst, "fami_copy2d: null pointer");
+  FAMI_CHECK_ARG(valid_dtype(dtype), "fami_copy2d: bad dtype");
+  FAMI_CHECK_ARG(rows > 0 && cols > 0 && cols % 4 == 0 && src_pitch % 4 == 0 && dst_pitch % 4 == 0 &&
+                     src_pitch >= cols && dst_pitch >= cols,
+                 "fami_copy2d: cols and pitches must be multiples of 4");
+  FAMI_CHECK_ARG(aligned(src, 4 * esize(dtype)) && aligned(dst, 4 * esize(dtype)),
+                 "fami_copy2d: pointers must be aligned to 4 elements");
+  return copy2d_launch(src, src_pitch, dst, dst_pitch, dtype, rows, cols, (cudaStream_t)stream);
+}
+
+int fami_linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int K, int N, void* stream) {
+  FAMI_CHECK_ARG(x && w && y && M > 0 && K > 0 && N > 0, "fami_linear_fwd: bad arguments");
+  return linear_fwd_launch(x, w, b, y, M, K, N, (cudaStream_t)stream);
+}
+
+int fami_joint_mse_fwd_bwd(const void* pred, int pred_dtype, int pred_pitch, const float* target_nchw,
+                           const float* weight, float* loss_out, float* grad_pred, float grad_scale, int B, int J,
+                           int H, int W, void* stream) {
+  FAMI_CHECK_ARG(pred && target_nchw && loss_out, "fami_joint_mse_fwd_bwd: null pointer");
+  FAMI_CHECK_ARG(valid_dtype(pred_dtype), "fami_joint_mse_fwd_bwd: bad dtype");
+  FAMI_CHECK_ARG(B > 0 && J > 0 && H > 0 && W > 0 && pred_pitch >= J, "fami_joint_mse_fwd_bwd: bad shape");
+  return joint_mse_launch(pred, pred_dtype, pred_pitch, target_nchw, weight, loss_out, grad_pred, grad_scale, B, J, H,
+                          W, (cudaStream_t)stream);
+}
+
+int fami_softmax_pkl_fwd(const void* a, int a_pitch, const void* b, int b_pitch, int dtype, float* out, int B, int HW,
+                         int C, float temperature, void* stream) {
+  FAMI_CHECK_ARG(a && b && out, "fami_softmax_pkl_fwd: null pointer");
+  FAMI_CHECK_ARG(valid_dtype(dtype), "fami_softmax_pkl_fwd: bad dtype");
+  FAMI_CHECK_ARG(B > 0 && HW > 0 && C > 0 && C <= 1024 && a_pitch >= C && b_pitch >= C && temperature > 0.f,
+                 "fami_softmax_pkl_fwd: bad shape");
+  return softmax_pkl_launch(a, a_pitch, b, b_pitch, dtype, out, B, HW, C, temperature, (cudaStream_t)stream);
+}
+
+int fami_argmax_hw(const void* hm, int dtype, int pitch, int32_t* idx_out, float* maxval_out, int B, int HW, int J,
+                   void* stream) {
+  FAMI_CHECK_ARG(hm && idx_out && maxval_out, "fami_argmax_hw: null pointer");
+  FAMI_CHECK_ARG(valid_dtype(dtype), "fami_argmax_hw: bad dtype");
+  FAMI_CHECK_ARG(B > 0 && HW > 0 && J > 0 && J <= 1024 && pitch >= J, "fami_argmax_hw: bad shape");
+  return argmax_hw_launch(hm, dtype, pitch, idx_out, maxval_out, B, HW, J, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,375 @@
+// fp32 implicit-GEMM convolution with fused (folded-BN scale/shift | bias) + residual + ReLU
+// + nearest-upsample-on-write epilogue.  Exact fp32 FMA arithmetic: this is the "fp32 parity"
+// arm of fami_conv2d_bn_act_fwd and the fallback for shapes the tcgen05 path does not take.
+//
+// Replaces (reference): nn.Conv2d/BatchNorm2d/ReLU chains in posetimation/layers/basic_model.py:44-63,
+// :83-113, basic_layer.py:55-73 and posetimation/backbones/hrnet.py:89-172,651-680.
+//
+// GEMM view: M = N*Ho*Wo output pixels, N = Cout, K = kh*kw*Cin.  NHWC activations make each
+// (pixel, tap) a contiguous run of Cin floats, so the A tile is gathered with 16-byte cp.async
+// (zero-filled at the padding halo) straight into shared memory; weights are pre-packed
+// [K][CoutPad] so the B tile is a plain 2-D copy.  3-stage cp.async pipeline, 8x4 register tile.
+#include "common.cuh"
+
+namespace fami {
+
+struct ConvParams {
+  const float* x;
+  const float* w;
+  const float* scale;
+  const float* shift;
+  const float* res;
+  float* y;
+  double* stats;
+  int N, H, W, Cin, Cout, CoutPad, kh, kw, stride, pad, dil, Ho, Wo, up, relu;
+  int in_pitch, out_pitch, res_pitch;
+  int M;       // N*Ho*Wo
+  int Ktot;    // kh*kw*Cin
+  int ksteps;  // ceil(Ktot/16)
+  int vec_store;  // y / residual pointers and pitches allow 16B accesses
+  // DCN mode (MODE_DCN): x is sampled bilinearly at offset positions and modulated by mask
+  const float* off;
+  const float* mask;
+  int off_pitch, mask_pitch, cpg;
+};
+
+enum { MODE_VEC = 0, MODE_SCALAR = 1, MODE_DCN = 2 };
+
+template <int WM, int WN, int MODE>
+__global__ void __launch_bounds__(WM * WN * 32) conv_f32_kernel(const ConvParams p) {
+  constexpr int BM = WM * 64, BN = WN * 16, KC = 16, NT = WM * WN * 32, AS = KC + 4, STAGES = 3;
+  constexpr int A_CH = (BM * 4 + NT - 1) / NT;        // 16B chunks of the A tile per thread
+  constexpr int B_CH = (KC * BN / 4 + NT - 1) / NT;   // 16B chunks of the B tile per thread
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                         // [STAGES][BM][AS]
+  float* Bs = smem + STAGES * BM * AS;      // [STAGES][KC][BN]
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wm = warp / WN, wn = warp % WN;
+  const int lm = lane >> 2, ln = lane & 3;
+  const int m_blk = blockIdx.x * BM;
+  const int n_blk = blockIdx.y * BN;
+  const int HoWo = p.Ho * p.Wo;
+
+  // ---- per-thread gather metadata for its A chunks (fixed over the K loop) ------------------
+  int a_iy0[A_CH], a_ix0[A_CH];
+  int64_t a_img[A_CH];
+  bool a_ok[A_CH];
+#pragma unroll
+  for (int i = 0; i < A_CH; ++i) {
+    int c = tid + i * NT;
+    int m = m_blk + (c >> 2);
+    bool ok = (c < BM * 4) && (m < p.M);
+    int mm = ok ? m : 0;
+    int n = mm / HoWo;
+    int r = mm - n * HoWo;
+    int yo = r / p.Wo, xo = r - yo * p.Wo;
+    a_iy0[i] = yo * p.stride - p.pad;
+    a_ix0[i] = xo * p.stride - p.pad;
+    a_img[i] = (int64_t)n * p.H * p.W;
+    a_ok[i] = ok;
+  }
+  const int cpt = p.Cin >> 4;  // 16-channel chunks per tap (VEC path)
+
+  auto load_stage = [&](int s, int ks) {
+    float* as = As + s * BM * AS;
+    float* bs = Bs + s * KC * BN;
+    if (MODE == MODE_DCN) {
+      // modulated deformable gather (torchvision deform_conv2d semantics):
+      // 16 channels (4 quads) of one tap per k-step; stride 1 so the output pixel index is m.
+      int tap = ks / cpt;
+      int c0 = (ks - tap * cpt) << 4;
+      int r = tap / p.kw, sx = tap - r * p.kw;
+      int dy = r * p.dil, dx = sx * p.dil;
+#pragma unroll
+      for (int i = 0; i < A_CH; ++i) {
+        int c = tid + i * NT;
+        if (c < BM * 4) {
+          float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a_ok[i]) {
+            int ch = c0 + ((c & 3) << 2);
+            int g = ch / p.cpg;
+            int64_t pix = (int64_t)m_blk + (c >> 2);
+            const float* op = p.off + pix * p.off_pitch + g * 2 * p.kh * p.kw + 2 * tap;
+            float ody = __ldg(op), odx = __ldg(op + 1);
+            float mk = __ldg(p.mask + pix * p.mask_pitch + g * p.kh * p.kw + tap);
+            float py = (float)(a_iy0[i] + dy) + ody;
+            float px = (float)(a_ix0[i] + dx) + odx;
+            if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
+              int y0 = (int)floorf(py), x0 = (int)floorf(px);
+              float ly = py - (float)y0, lx = px - (float)x0;
+              float hy = 1.f - ly, hx = 1.f - lx;
+              const float* xb = p.x + a_img[i] * p.in_pitch + ch;
+              const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+              bool y0ok = y0 >= 0, y1ok = y0 + 1 <= p.H - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= p.W - 1;
+              float4 v1 = (y0ok && x0ok) ? ld4(xb + ((int64_t)y0 * p.W + x0) * p.in_pitch) : z;
+              float4 v2 = (y0ok && x1ok) ? ld4(xb + ((int64_t)y0 * p.W + x0 + 1) * p.in_pitch) : z;
+              float4 v3 = (y1ok && x0ok) ? ld4(xb + ((int64_t)(y0 + 1) * p.W + x0) * p.in_pitch) : z;
+              float4 v4 = (y1ok && x1ok) ? ld4(xb + ((int64_t)(y0 + 1) * p.W + x0 + 1) * p.in_pitch) : z;
+              float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+              val.x = mk * (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x);
+              val.y = mk * (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y);
+              val.z = mk * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z);
+              val.w = mk * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w);
+            }
+          }
+          *reinterpret_cast<float4*>(as + (c >> 2) * AS + ((c & 3) << 2)) = val;
+        }
+      }
+    } else if (MODE == MODE_VEC) {
+      int tap = ks / cpt;
+      int c0 = (ks - tap * cpt) << 4;
+      int r = tap / p.kw, sx = tap - r * p.kw;
+      int dy = r * p.dil, dx = sx * p.dil;
+#pragma unroll
+      for (int i = 0; i < A_CH; ++i) {
+        int c = tid + i * NT;
+        if (c < BM * 4) {
+          int iy = a_iy0[i] + dy, ix = a_ix0[i] + dx;
+          bool ok = a_ok[i] && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+          const float* src = ok ? p.x + (a_img[i] + (int64_t)iy * p.W + ix) * p.in_pitch + c0 + ((c & 3) << 2) : p.x;
+          cp_async16(as + (c >> 2) * AS + ((c & 3) << 2), src, ok);
+        }
+      }
+    } else {
+      // generic scalar gather over the flattened K axis (stem conv, Cin = 3)
+      for (int e = tid; e < BM * KC; e += NT) {
+        int ml = e >> 4, kk = e & 15;
+        int m = m_blk + ml;
+        int k = ks * KC + kk;
+        float v = 0.f;
+        if (m < p.M && k < p.Ktot) {
+          int tap = k / p.Cin, ci = k - tap * p.Cin;
+          int r = tap / p.kw, sx = tap - r * p.kw;
+          int n = m / HoWo, rr = m - n * HoWo;
+          int yo = rr / p.Wo, xo = rr - yo * p.Wo;
+          int iy = yo * p.stride - p.pad + r * p.dil, ix = xo * p.stride - p.pad + sx * p.dil;
+          if ((unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W)
+            v = __ldg(p.x + ((int64_t)(n * p.H + iy) * p.W + ix) * p.in_pitch + ci);
+        }
+        as[ml * AS + kk] = v;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < B_CH; ++i) {
+      int c = tid + i * NT;
+      if (c < KC * BN / 4) {
+        int row = c / (BN / 4), col = (c - row * (BN / 4)) << 2;
+        const float* src = p.w + (int64_t)(ks * KC + row) * p.CoutPad + n_blk + col;
+        cp_async16(bs + row * BN + col, src, true);
+      }
+    }
+  };
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  // prologue
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < p.ksteps) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  const int a_row0 = wm * 64 + lm * 4;  // rows a_row0..+3 and a_row0+32..+35
+  const int b_col = wn * 16 + ln * 4;
+
+  for (int ks = 0; ks < p.ksteps; ++ks) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      int nk = ks + STAGES - 1;
+      if (nk < p.ksteps) load_stage(nk % STAGES, nk);
+      cp_async_commit();
+    }
+    const float* as = As + (ks % STAGES) * BM * AS;
+    const float* bs = Bs + (ks % STAGES) * KC * BN;
+#pragma unroll
+    for (int kq = 0; kq < 4; ++kq) {
+      float4 a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] = *reinterpret_cast<const float4*>(as + (a_row0 + i) * AS + kq * 4);
+        a[i + 4] = *reinterpret_cast<const float4*>(as + (a_row0 + 32 + i) * AS + kq * 4);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(bs + (kq * 4 + j) * BN + b_col);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] = fmaf(a[i].x, b[0].x, acc[i][0]); acc[i][1] = fmaf(a[i].x, b[0].y, acc[i][1]);
+        acc[i][2] = fmaf(a[i].x, b[0].z, acc[i][2]); acc[i][3] = fmaf(a[i].x, b[0].w, acc[i][3]);
+        acc[i][0] = fmaf(a[i].y, b[1].x, acc[i][0]); acc[i][1] = fmaf(a[i].y, b[1].y, acc[i][1]);
+        acc[i][2] = fmaf(a[i].y, b[1].z, acc[i][2]); acc[i][3] = fmaf(a[i].y, b[1].w, acc[i][3]);
+        acc[i][0] = fmaf(a[i].z, b[2].x, acc[i][0]); acc[i][1] = fmaf(a[i].z, b[2].y, acc[i][1]);
+        acc[i][2] = fmaf(a[i].z, b[2].z, acc[i][2]); acc[i][3] = fmaf(a[i].z, b[2].w, acc[i][3]);
+        acc[i][0] = fmaf(a[i].w, b[3].x, acc[i][0]); acc[i][1] = fmaf(a[i].w, b[3].y, acc[i][1]);
+        acc[i][2] = fmaf(a[i].w, b[3].z, acc[i][2]); acc[i][3] = fmaf(a[i].w, b[3].w, acc[i][3]);
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue ------------------------------------------------------------------------------
+  const int n0 = n_blk + b_col;
+  float sc[4], sh[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int o = n0 + j;
+    sc[j] = (p.scale && o < p.Cout) ? __ldg(p.scale + o) : 1.f;
+    sh[j] = (p.shift && o < p.Cout) ? __ldg(p.shift + o) : 0.f;
+  }
+  const bool vec_out = (n0 + 3 < p.Cout) && p.vec_store;
+  const int Hout = p.Ho * p.up, Wout = p.Wo * p.up;
+  float ssum[4] = {0, 0, 0, 0}, ssq[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int m = m_blk + a_row0 + (i & 3) + ((i >> 2) << 5);
+    if (m >= p.M) continue;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fmaf(acc[i][j], sc[j], sh[j]);
+    if (p.stats) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { ssum[j] += v[j]; ssq[j] += v[j] * v[j]; }
+    }
+    int n = m / HoWo, r = m - n * HoWo;
+    int yo = r / p.Wo, xo = r - yo * p.Wo;
+    for (int dy = 0; dy < p.up; ++dy)
+      for (int dx = 0; dx < p.up; ++dx) {
+        int64_t pix = ((int64_t)n * Hout + yo * p.up + dy) * Wout + xo * p.up + dx;
+        float* yp = p.y + pix * p.out_pitch + n0;
+        if (vec_out) {
+          float4 o = make_float4(v[0], v[1], v[2], v[3]);
+          if (p.res) {
+            float4 rr = *reinterpret_cast<const float4*>(p.res + pix * p.res_pitch + n0);
+            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+          }
+          if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          *reinterpret_cast<float4*>(yp) = o;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n0 + j < p.Cout) {
+              float o = v[j];
+              if (p.res) o += p.res[pix * p.res_pitch + n0 + j];
+              if (p.relu) o = fmaxf(o, 0.f);
+              yp[j] = o;
+            }
+          }
+        }
+      }
+  }
+  if (p.stats) {
+    // reduce over the 8 lanes sharing ln (lane bits 2..4), then one double atomic per channel per warp
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], o);
+        ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], o);
+      }
+    }
+    if (lm == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n0 + j < p.Cout) {
+          atomicAdd(p.stats + n0 + j, (double)ssum[j]);
+          atomicAdd(p.stats + p.Cout + n0 + j, (double)ssq[j]);
+        }
+    }
+  }
+}
+
+template <int WM, int WN, int MODE>
+static int launch_cfg(const ConvParams& p, cudaStream_t st) {
+  constexpr int BM = WM * 64, BN = WN * 16;
+  constexpr size_t smem = (size_t)3 * (BM * 20 + 16 * BN) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(conv_f32_kernel<WM, WN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  dim3 grid(cdiv(p.M, BM), p.CoutPad / BN);
+  conv_f32_kernel<WM, WN, MODE><<<grid, WM * WN * 32, smem, st>>>(p);
+  FAMI_CHECK_LAUNCH("conv_f32_kernel");
+  return 0;
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int MODE>
+static int dispatch_tile(const ConvParams& p, cudaStream_t st) {
+  const int cp = p.CoutPad;
+  if (cp % 64 == 0) return launch_cfg<2, 4, MODE>(p, st);
+  if (cp % 48 == 0) return launch_cfg<2, 3, MODE>(p, st);
+  if (cp % 32 == 0) return launch_cfg<4, 2, MODE>(p, st);
+  return launch_cfg<4, 1, MODE>(p, st);
+}
+
+int conv_f32_launch(const fami_conv_desc* d, const float* x, const float* w, const float* scale,
+                    const float* shift, const float* res, float* y, double* stats, cudaStream_t st) {
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.res = res; p.y = y; p.stats = d->stats ? stats : nullptr;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+  p.CoutPad = fami_conv_cout_pad(d->Cout);
+  p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad; p.dil = d->dil;
+  p.Ho = d->Ho; p.Wo = d->Wo; p.up = d->up; p.relu = d->relu;
+  p.in_pitch = d->in_pitch; p.out_pitch = d->out_pitch; p.res_pitch = d->res_pitch;
+  p.M = d->N * d->Ho * d->Wo;
+  p.Ktot = d->kh * d->kw * d->Cin;
+  p.ksteps = (p.Ktot + 15) / 16;
+  p.vec_store = al16(y) && (d->out_pitch % 4 == 0) && (!res || (al16(res) && d->res_pitch % 4 == 0));
+  const bool vec = (d->Cin % 16 == 0) && (d->in_pitch % 4 == 0) && al16(x);
+  return vec ? dispatch_tile<MODE_VEC>(p, st) : dispatch_tile<MODE_SCALAR>(p, st);
+}
+
+// v1 DCN forward: same mainloop/epilogue as the conv, A tile produced by the deformable gather.
+int dcn_f32_simt_launch(const fami_dcn_desc* d, const float* x, const float* off, const float* mask,
+                        const float* w, const float* bias, float* out, cudaStream_t st) {
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.w = w; p.scale = nullptr; p.shift = bias; p.res = nullptr; p.y = out; p.stats = nullptr;
+  p.N = d->B; p.H = d->H; p.W = d->W; p.Cin = d->C; p.Cout = d->Cout;
+  p.CoutPad = fami_conv_cout_pad(d->Cout);
+  p.kh = d->kh; p.kw = d->kw; p.stride = 1; p.pad = d->pad; p.dil = d->dil;
+  p.Ho = d->H + 2 * d->pad - d->dil * (d->kh - 1); p.Wo = d->W + 2 * d->pad - d->dil * (d->kw - 1);
+  p.up = 1; p.relu = 0;
+  p.in_pitch = d->x_pitch; p.out_pitch = d->out_pitch; p.res_pitch = 0;
+  p.M = d->B * p.Ho * p.Wo;
+  p.Ktot = d->kh * d->kw * d->C;
+  p.ksteps = p.Ktot / 16;
+  p.vec_store = al16(out) && (d->out_pitch % 4 == 0);
+  p.off = off; p.mask = mask; p.off_pitch = d->off_pitch; p.mask_pitch = d->mask_pitch;
+  p.cpg = d->C / d->G;
+  return dispatch_tile<MODE_DCN>(p, st);
+}
+
+// ---- weight packing: OIHW float -> [kh*kw*Cin (padded to 16)][CoutPad] float ------------------
+__global__ void pack_w_f32_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin,
+                                  int taps, int Kpad, int CoutPad) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t tot = (int64_t)Kpad * CoutPad;
+  if (i >= tot) return;
+  int k = (int)(i / CoutPad), o = (int)(i - (int64_t)k * CoutPad);
+  float v = 0.f;
+  if (k < taps * Cin && o < Cout) {
+    int tap = k / Cin, c = k - tap * Cin;
+    v = w[((int64_t)o * Cin + c) * taps + tap];
+  }
+  out[i] = v;
+}
+
+int pack_w_f32_launch(const float* w, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t st) {
+  int taps = kh * kw, Kpad = ((taps * Cin + 15) / 16) * 16, CoutPad = fami_conv_cout_pad(Cout);
+  int64_t tot = (int64_t)Kpad * CoutPad;
+  pack_w_f32_kernel<<<cdiv(tot, 256), 256, 0, st>>>(w, out, Cout, Cin, taps, Kpad, CoutPad);
+  FAMI_CHECK_LAUNCH("pack_w_f32_kernel");
+  return 0;
+}
+
+}  // namespace fami

@@ -1,0 +1,386 @@
+// Bandwidth-bound pieces of the FAMI-Pose hot path: layout conversion, global translation warp,
+// frame difference, tiny linear head, train-mode BN finalize/apply, losses, keypoint argmax.
+// Reference call sites are cited at each launcher (paths relative to the reference tree).
+#include "common.cuh"
+
+namespace fami {
+
+// ---------------------------------------------------------------------------------------------
+// NCHW fp32 <-> NHWC {fp32,bf16}
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int64_t src_n_stride, T* __restrict__ dst,
+                                    int N, int C, int HW, int pitch) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // pixel index over N*HW
+  if (i >= (int64_t)N * HW) return;
+  int n = (int)(i / HW);
+  int pix = (int)(i - (int64_t)n * HW);
+  const float* s = src + n * src_n_stride + pix;
+  T* d = dst + i * pitch;
+  for (int c = 0; c < C; ++c) d[c] = from_f<T>(__ldg(s + (int64_t)c * HW));
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, int pitch, float* __restrict__ dst, int N, int C,
+                                    int HW) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)N * HW) return;
+  int n = (int)(i / HW);
+  int pix = (int)(i - (int64_t)n * HW);
+  const T* s = src + i * pitch;
+  float* d = dst + (int64_t)n * C * HW + pix;
+  for (int c = 0; c < C; ++c) d[(int64_t)c * HW] = to_f<T>(s[c]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// translation warp: out[b,y,x,:] = bilinear_zero_pad(src[b], y - ty, x - tx)
+// (kornia.geometry.warp_affine with M=[[1,0,tx],[0,1,ty]], Alignment_V15.py:133-135)
+// one thread per (pixel, channel quad)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void warp_translate_fwd_kernel(const T* __restrict__ src, int src_pitch, const float* __restrict__ txy,
+                                          T* __restrict__ out, int out_pitch, int B, int H, int W, int C4) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t tot = (int64_t)B * H * W * C4;
+  if (i >= tot) return;
+  int q = (int)(i % C4);
+  int64_t pix = i / C4;
+  int x = (int)(pix % W);
+  int64_t t = pix / W;
+  int y = (int)(t % H);
+  int b = (int)(t / H);
+  float tx = __ldg(txy + 2 * b), ty = __ldg(txy + 2 * b + 1);
+  float px = (float)x - tx, py = (float)y - ty;
+  float fx = floorf(px), fy = floorf(py);
+  float lx = px - fx, ly = py - fy;
+  // clamp before the int conversion so absurd translations cannot overflow
+  fx = fminf(fmaxf(fx, -2.f), (float)W);
+  fy = fminf(fmaxf(fy, -2.f), (float)H);
+  int x0 = (int)fx, y0 = (int)fy;
+  const T* sb = src + (int64_t)b * H * W * src_pitch + q * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int yy = y0 + (k >> 1), xx = x0 + (k & 1);
+    float w = ((k >> 1) ? ly : 1.f - ly) * ((k & 1) ? lx : 1.f - lx);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      float4 v = ld4<T>(sb + ((int64_t)yy * W + xx) * src_pitch);
+      acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+    }
+  }
+  st4<T>(out + pix * out_pitch + q * 4, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[r*n + i] = a[r*n + i] - b[i]   (Alignment_V15.py:132, all supporting frames at once)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void sub_bcast_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t n4,
+                                 int rep) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4 * rep) return;
+  int64_t j = i % n4;
+  float4 va = ld4<T>(a + i * 4), vb = ld4<T>(b + j * 4);
+  st4<T>(out + i * 4, make_float4(va.x - vb.x, va.y - vb.y, va.z - vb.z, va.w - vb.w));
+}
+
+// rows x cols strided copy (channel-slice writes of the reference's torch.cat along dim=1)
+template <typename T>
+__global__ void copy2d_kernel(const T* __restrict__ src, int sp, T* __restrict__ dst, int dp, int64_t rows, int c4) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * c4) return;
+  int64_t r = i / c4;
+  int q = (int)(i - r * c4);
+  st4<T>(dst + r * dp + q * 4, ld4<T>(src + r * sp + q * 4));
+}
+
+// ---------------------------------------------------------------------------------------------
+// y[M,N] = x[M,K] w[N,K]^T + b   (nn.Linear, Alignment_V15.py:69-71); one warp per output
+// ---------------------------------------------------------------------------------------------
+__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                  const float* __restrict__ b, float* __restrict__ y, int M, int K, int N) {
+  int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (gw >= M * N) return;
+  int m = gw / N, n = gw - m * N;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s = fmaf(__ldg(x + (int64_t)m * K + k), __ldg(w + (int64_t)n * K + k), s);
+  s = warp_sum(s);
+  if (lane == 0) y[gw] = s + (b ? __ldg(b + n) : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// train-mode BN
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean, float* running_var,
+                                   float* scale, float* shift, float* save_mean, float* save_invstd, int C,
+                                   double count, float eps, float momentum) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double mean = stats[c] / count;
+  double var = stats[C + c] / count - mean * mean;
+  if (var < 0) var = 0;
+  float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  float g = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+  scale[c] = g * invstd;
+  shift[c] = be - (float)mean * g * invstd;
+  if (save_mean) save_mean[c] = (float)mean;
+  if (save_invstd) save_invstd[c] = invstd;
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+  if (running_var) {
+    double unb = count > 1 ? var * count / (count - 1.0) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  }
+}
+
+template <typename T>
+__global__ void bn_apply_act_kernel(const T* __restrict__ x, int x_pitch, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, const T* __restrict__ res, int res_pitch,
+                                    T* __restrict__ y, int y_pitch, int N, int Ho, int Wo, int C, int up, int relu) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t tot = (int64_t)N * Ho * Wo * C;
+  if (i >= tot) return;
+  int c = (int)(i % C);
+  int64_t pix = i / C;
+  float v = to_f<T>(x[pix * x_pitch + c]) * __ldg(scale + c) + __ldg(shift + c);
+  int xo = (int)(pix % Wo);
+  int64_t t = pix / Wo;
+  int yo = (int)(t % Ho);
+  int n = (int)(t / Ho);
+  int Hout = Ho * up, Wout = Wo * up;
+  for (int dy = 0; dy < up; ++dy)
+    for (int dx = 0; dx < up; ++dx) {
+      int64_t op = ((int64_t)n * Hout + yo * up + dy) * Wout + xo * up + dx;
+      float o = v;
+      if (res) o += to_f<T>(res[op * res_pitch + c]);
+      if (relu) o = fmaxf(o, 0.f);
+      y[op * y_pitch + c] = from_f<T>(o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// JointMSELoss (mse_loss.py:21-40): loss = 1/(J*B*HW) sum_{b,j,p} w_bj^2 (pred - gt)^2
+// pred NHWC, target NCHW.  one thread per (b, pixel), loop over joints.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void joint_mse_kernel(const T* __restrict__ pred, int pitch, const float* __restrict__ target,
+                                 const float* __restrict__ weight, float* loss_out, float* grad_pred,
+                                 float grad_scale, int B, int J, int HW, float inv_count) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float s = 0.f;
+  if (i < (int64_t)B * HW) {
+    int b = (int)(i / HW);
+    int pix = (int)(i - (int64_t)b * HW);
+    for (int j = 0; j < J; ++j) {
+      float w = weight ? __ldg(weight + b * J + j) : 1.f;
+      float p = to_f<T>(pred[i * pitch + j]);
+      float g = __ldg(target + ((int64_t)b * J + j) * HW + pix);
+      float d = p * w - g * w;
+      s = fmaf(d, d, s);
+      if (grad_pred) grad_pred[i * J + j] = 2.f * d * w * inv_count * grad_scale;
+    }
+  }
+  s = warp_sum(s);
+  __shared__ float red[32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) red[wid] = s;
+  __syncthreads();
+  if (wid == 0) {
+    s = lane < (blockDim.x >> 5) ? red[lane] : 0.f;
+    s = warp_sum(s);
+    if (lane == 0) atomicAdd(loss_out, s * inv_count);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MI estimator core (Alignment_V15.py:250-277): per row r=(b,c) over L=HW positions
+//   t = softmax(b/T), p = softmax(a/T);  value = mean_{r,l} t*(log t - p)   [reference quirk]
+// One block per image; thread (rg, c): channel c = tid % C, row-group rg = tid / C strides over
+// pixels.  Pass 1 column maxima, pass 2 partition sums (data re-read from L2).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024) softmax_pkl_kernel(const T* __restrict__ a, int a_pitch,
+                                                           const T* __restrict__ bsrc, int b_pitch, float* out,
+                                                           int HW, int C, float inv_temp, float inv_count) {
+  extern __shared__ float sm[];  // [6][RG*C] scratch
+  const int RG = blockDim.x / C;
+  const int tid = threadIdx.x;
+  const int c = tid % C, rg = tid / C;
+  const bool active = rg < RG;
+  const T* ab = a + (int64_t)blockIdx.x * HW * a_pitch;
+  const T* bb = bsrc + (int64_t)blockIdx.x * HW * b_pitch;
+  float ma = -INFINITY, mb = -INFINITY;
+  if (active)
+    for (int l = rg; l < HW; l += RG) {
+      ma = fmaxf(ma, to_f<T>(ab[(int64_t)l * a_pitch + c]) * inv_temp);
+      mb = fmaxf(mb, to_f<T>(bb[(int64_t)l * b_pitch + c]) * inv_temp);
+    }
+  float* s_ma = sm;
+  float* s_mb = sm + RG * C;
+  if (active) { s_ma[rg * C + c] = ma; s_mb[rg * C + c] = mb; }
+  __syncthreads();
+  if (active) {
+    for (int r = 0; r < RG; ++r) { ma = fmaxf(ma, s_ma[r * C + c]); mb = fmaxf(mb, s_mb[r * C + c]); }
+  }
+  __syncthreads();
+  float za = 0.f, zb = 0.f, sb = 0.f, xab = 0.f;
+  if (active)
+    for (int l = rg; l < HW; l += RG) {
+      float va = to_f<T>(ab[(int64_t)l * a_pitch + c]) * inv_temp - ma;
+      float vb = to_f<T>(bb[(int64_t)l * b_pitch + c]) * inv_temp - mb;
+      float ea = expf(va), eb = expf(vb);
+      za += ea; zb += eb; sb = fmaf(eb, vb, sb); xab = fmaf(ea, eb, xab);
+    }
+  float* s0 = sm; float* s1 = sm + RG * C; float* s2 = sm + 2 * RG * C; float* s3 = sm + 3 * RG * C;
+  if (active) { s0[rg * C + c] = za; s1[rg * C + c] = zb; s2[rg * C + c] = sb; s3[rg * C + c] = xab; }
+  __syncthreads();
+  float val = 0.f;
+  if (tid < C) {
+    za = zb = sb = xab = 0.f;
+    for (int r = 0; r < RG; ++r) { za += s0[r * C + tid]; zb += s1[r * C + tid]; sb += s2[r * C + tid]; xab += s3[r * C + tid]; }
+    // sum_l t*(log t - p) = sb/zb - log zb - xab/(za*zb)
+    val = sb / zb - logf(zb) - xab / (za * zb);
+  }
+  __syncthreads();
+  // block reduce val over the first C threads
+  val = warp_sum(val);
+  if ((tid & 31) == 0) sm[tid >> 5] = val;
+  __syncthreads();
+  if (tid < 32) {
+    float v = tid < (blockDim.x >> 5) ? sm[tid] : 0.f;
+    v = warp_sum(v);
+    if (tid == 0) atomicAdd(out, v * inv_count);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// get_max_preds (heatmaps_process.py:16-44): flat argmax per (b,j), first maximum wins
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024) argmax_hw_kernel(const T* __restrict__ hm, int pitch, int32_t* idx_out,
+                                                         float* maxval_out, int HW, int J) {
+  extern __shared__ float sm[];
+  const int RG = blockDim.x / J;
+  float* s_v = sm;
+  int* s_i = reinterpret_cast<int*>(sm + RG * J);
+  const int tid = threadIdx.x;
+  const int j = tid % J, rg = tid / J;
+  const T* hb = hm + (int64_t)blockIdx.x * HW * pitch;
+  if (rg < RG) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int l = rg; l < HW; l += RG) {
+      float v = to_f<T>(hb[(int64_t)l * pitch + j]);
+      if (v > best || bi == 0x7fffffff) { best = v; bi = l; }
+    }
+    s_v[rg * J + j] = best;
+    s_i[rg * J + j] = bi;
+  }
+  __syncthreads();
+  if (tid < J) {
+    float best = s_v[tid];
+    int bi = s_i[tid];
+    for (int r = 1; r < RG; ++r) {
+      float v = s_v[r * J + tid];
+      int ii = s_i[r * J + tid];
+      if (ii != 0x7fffffff && (v > best || (v == best && ii < bi))) { best = v; bi = ii; }
+    }
+    idx_out[blockIdx.x * J + tid] = bi;
+    maxval_out[blockIdx.x * J + tid] = best;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+#define DISPATCH_T(dtype, ...)                         \
+  if ((dtype) == FAMI_F32) { using T = float; __VA_ARGS__ } else { using T = __nv_bfloat16; __VA_ARGS__ }
+
+int nchw_to_nhwc_launch(const float* src, int64_t sns, void* dst, int dt, int N, int C, int H, int W, int pitch,
+                        cudaStream_t st) {
+  int64_t tot = (int64_t)N * H * W;
+  DISPATCH_T(dt, nchw_to_nhwc_kernel<T><<<cdiv(tot, 256), 256, 0, st>>>(src, sns, (T*)dst, N, C, H * W, pitch);)
+  FAMI_CHECK_LAUNCH("nchw_to_nhwc");
+  return 0;
+}
+int nhwc_to_nchw_launch(const void* src, int dt, int pitch, float* dst, int N, int C, int H, int W, cudaStream_t st) {
+  int64_t tot = (int64_t)N * H * W;
+  DISPATCH_T(dt, nhwc_to_nchw_kernel<T><<<cdiv(tot, 256), 256, 0, st>>>((const T*)src, pitch, dst, N, C, H * W);)
+  FAMI_CHECK_LAUNCH("nhwc_to_nchw");
+  return 0;
+}
+int warp_translate_fwd_launch(const void* src, int sp, const float* txy, void* out, int op, int dt, int B, int H,
+                              int W, int C, cudaStream_t st) {
+  int64_t tot = (int64_t)B * H * W * (C / 4);
+  DISPATCH_T(dt, warp_translate_fwd_kernel<T><<<cdiv(tot, 256), 256, 0, st>>>((const T*)src, sp, txy, (T*)out, op, B,
+                                                                               H, W, C / 4);)
+  FAMI_CHECK_LAUNCH("warp_translate_fwd");
+  return 0;
+}
+int sub_bcast_launch(const void* a, const void* b, void* out, int dt, int64_t n, int rep, cudaStream_t st) {
+  int64_t n4 = n / 4;
+  DISPATCH_T(dt, sub_bcast_kernel<T><<<cdiv(n4 * rep, 256), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n4, rep);)
+  FAMI_CHECK_LAUNCH("sub_bcast");
+  return 0;
+}
+int copy2d_launch(const void* src, int sp, void* dst, int dp, int dt, int64_t rows, int cols, cudaStream_t st) {
+  int c4 = cols / 4;
+  DISPATCH_T(dt, copy2d_kernel<T><<<cdiv(rows * c4, 256), 256, 0, st>>>((const T*)src, sp, (T*)dst, dp, rows, c4);)
+  FAMI_CHECK_LAUNCH("copy2d");
+  return 0;
+}
+int linear_fwd_launch(const float* x, const float* w, const float* b, float* y, int M, int K, int N, cudaStream_t st) {
+  int64_t threads = (int64_t)M * N * 32;
+  linear_fwd_kernel<<<cdiv(threads, 256), 256, 0, st>>>(x, w, b, y, M, K, N);
+  FAMI_CHECK_LAUNCH("linear_fwd");
+  return 0;
+}
+int bn_finalize_launch(const double* stats, const float* gamma, const float* beta, float* rm, float* rv, float* scale,
+                       float* shift, float* save_mean, float* save_invstd, int C, int64_t count, float eps,
+                       float momentum, cudaStream_t st) {
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(stats, gamma, beta, rm, rv, scale, shift, save_mean, save_invstd, C,
+                                                   (double)count, eps, momentum);
+  FAMI_CHECK_LAUNCH("bn_finalize");
+  return 0;
+}
+int bn_apply_act_launch(const void* x, int xp, const float* scale, const float* shift, const void* res, int rp, void* y,
+                        int yp, int dt, int N, int Ho, int Wo, int C, int up, int relu, cudaStream_t st) {
+  int64_t tot = (int64_t)N * Ho * Wo * C;
+  DISPATCH_T(dt, bn_apply_act_kernel<T><<<cdiv(tot, 256), 256, 0, st>>>((const T*)x, xp, scale, shift, (const T*)res,
+                                                                         rp, (T*)y, yp, N, Ho, Wo, C, up, relu);)
+  FAMI_CHECK_LAUNCH("bn_apply_act");
+  return 0;
+}
+int joint_mse_launch(const void* pred, int dt, int pitch, const float* target, const float* weight, float* loss,
+                     float* grad, float gscale, int B, int J, int H, int W, cudaStream_t st) {
+  int64_t tot = (int64_t)B * H * W;
+  float inv = 1.f / ((float)J * (float)B * (float)(H * W));
+  DISPATCH_T(dt, joint_mse_kernel<T><<<cdiv(tot, 256), 256, 0, st>>>((const T*)pred, pitch, target, weight, loss, grad,
+                                                                      gscale, B, J, H * W, inv);)
+  FAMI_CHECK_LAUNCH("joint_mse");
+  return 0;
+}
+int softmax_pkl_launch(const void* a, int ap, const void* b, int bp, int dt, float* out, int B, int HW, int C,
+                       float temperature, cudaStream_t st) {
+  int threads = 1024;
+  int RG = threads / C;
+  size_t smem = (size_t)4 * RG * C * sizeof(float);
+  if (smem < 32 * sizeof(float)) smem = 32 * sizeof(float);
+  float inv_count = 1.f / ((float)B * (float)C * (float)HW);
+  DISPATCH_T(dt, softmax_pkl_kernel<T><<<B, threads, smem, st>>>((const T*)a, ap, (const T*)b, bp, out, HW, C,
+                                                                 1.f / temperature, inv_count);)
+  FAMI_CHECK_LAUNCH("softmax_pkl");
+  return 0;
+}
+int argmax_hw_launch(const void* hm, int dt, int pitch, int32_t* idx, float* maxv, int B, int HW, int J,
+                     cudaStream_t st) {
+  int threads = 1024;
+  int RG = threads / J;
+  size_t smem = (size_t)2 * RG * J * sizeof(float);
+  DISPATCH_T(dt, argmax_hw_kernel<T><<<B, threads, smem, st>>>((const T*)hm, pitch, idx, maxv, HW, J);)
+  FAMI_CHECK_LAUNCH("argmax_hw");
+  return 0;
+}
+
+}  // namespace fami

@@ -1,0 +1,400 @@
+"""Functional ops over libfami_b200.so.
+
+Activations travel between ops as torch tensors with LOGICAL shape [N,C,H,W] and channels-last
+strides (element (n,c,y,x) at ((n*H+y)*W+x)*pitch + c).  `pitch` may exceed C: a channel slice of a
+wider buffer is a valid operand, which is how the reference's torch.cat(dim=1) calls are executed
+without copies.  torch is used for memory, streams and parameter bookkeeping only; every FLOP on
+activations is issued through the C ABI.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, ConvDesc, DcnDesc
+
+_PRECISION = "fp32"
+
+
+def set_precision(p):
+    """'fp32' (exact-fp32 SIMT kernels, 1e-3 parity arm) or 'bf16' (tcgen05 tensor-core arm)."""
+    global _PRECISION
+    if p not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _PRECISION = p
+
+
+def get_precision():
+    return _PRECISION
+
+
+def act_dtype():
+    return torch.float32 if _PRECISION == "fp32" else torch.bfloat16
+
+
+def _code(dtype):
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise TypeError("unsupported activation dtype %s" % dtype)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("fami_pose_b200 ops need CUDA tensors (no CPU fallback); got device %s" % t.device)
+
+
+def empty_nhwc(N, C, H, W, dtype, device, pitch=None):
+    p = C if pitch is None else pitch
+    return torch.empty_strided((N, C, H, W), (H * W * p, 1, W * p, p), dtype=dtype, device=device)
+
+
+def meta(t):
+    """(N, C, H, W, pitch) of a channels-last operand; raises if the strides are not NHWC-with-pitch."""
+    if t.dim() != 4:
+        raise ValueError("expected a 4-D activation, got shape %s" % (tuple(t.shape),))
+    N, C, H, W = t.shape
+    s = t.stride()
+    if W > 1:
+        p = s[3]
+    elif H > 1:
+        p = s[2]
+    elif N > 1:
+        p = s[0]
+    else:
+        p = C
+    ok = (C == 1 or s[1] == 1) and (W == 1 or s[3] == p) and (H == 1 or s[2] == W * p) and (N == 1 or s[0] == H * W * p) and p >= C
+    if not ok:
+        raise ValueError("activation is not channels-last with a uniform pixel pitch: shape %s strides %s"
+                         % (tuple(t.shape), s))
+    return N, C, H, W, p
+
+
+def is_nhwc(t):
+    try:
+        meta(t)
+        return True
+    except ValueError:
+        return False
+
+
+def to_nhwc(x, dtype=None):
+    """Boundary conversion from the reference's NCHW fp32 tensors (fami_nchw_to_nhwc).
+
+    Tensors that already carry channels-last strides (outputs of other fami ops) pass through."""
+    _need_cuda(x)
+    dtype = dtype or act_dtype()
+    if x.dim() == 4 and is_nhwc(x):
+        if x.dtype != dtype:
+            raise TypeError("activation dtype %s does not match the active precision %s" % (x.dtype, dtype))
+        return x
+    if x.dtype != torch.float32:
+        raise TypeError("boundary tensors must be float32 NCHW, got %s" % x.dtype)
+    x = x.contiguous()
+    N, C, H, W = x.shape
+    out = empty_nhwc(N, C, H, W, dtype, x.device)
+    _lib.call("fami_nchw_to_nhwc", _ptr(x), C * H * W, _ptr(out), _code(dtype), N, C, H, W, C, _stream())
+    return out
+
+
+def frames_to_nhwc(kf_x, sup_x, dtype=None):
+    """Alignment_V15.py:115-119: [B,3,H,W] + [B,3*ns,H,W] -> frame-major [(1+ns)*B,H,W,3]."""
+    _need_cuda(kf_x, sup_x)
+    dtype = dtype or act_dtype()
+    kf_x = kf_x.contiguous()
+    sup_x = sup_x.contiguous()
+    B, _, H, W = kf_x.shape
+    ns = sup_x.shape[1] // 3
+    out = empty_nhwc((1 + ns) * B, 3, H, W, dtype, kf_x.device)
+    _lib.call("fami_nchw_to_nhwc", _ptr(kf_x), 3 * H * W, _ptr(out[:B]), _code(dtype), B, 3, H, W, 3, _stream())
+    for i in range(ns):
+        src = sup_x[:, 3 * i:3 * i + 3]
+        _lib.call("fami_nchw_to_nhwc", ctypes.c_void_p(src.data_ptr()), 3 * ns * H * W,
+                  _ptr(out[(1 + i) * B:(2 + i) * B]), _code(dtype), B, 3, H, W, 3, _stream())
+    return out
+
+
+def to_nchw(t):
+    """NHWC(+pitch) activation -> contiguous float32 NCHW (fami_nhwc_to_nchw)."""
+    _need_cuda(t)
+    N, C, H, W, p = meta(t)
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=t.device)
+    _lib.call("fami_nhwc_to_nchw", _ptr(t), _code(t.dtype), p, _ptr(out), N, C, H, W, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter caches (packed weights, folded BN)
+# ------------------------------------------------------------------------------------------------
+
+def _ver(*ts):
+    return tuple((t._version, t.data_ptr()) if t is not None else None for t in ts)
+
+
+def packed_weight(owner, weight, dtype):
+    """[kh*kw*Cin][CoutPad] packing of an OIHW weight (fami_pack_conv_weight), cached per version."""
+    key = ("w", _code(dtype))
+    cache = owner.__dict__.setdefault("_fami_cache", {})
+    ver = _ver(weight)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    Cout, Cin, kh, kw = weight.shape
+    n = _lib.load().fami_packed_weight_elems(Cout, Cin, kh, kw, _code(dtype))
+    out = torch.empty(n, dtype=dtype, device=weight.device)
+    w = weight.detach().contiguous().float()
+    _lib.call("fami_pack_conv_weight", _ptr(w), _ptr(out), Cout, Cin, kh, kw, _code(dtype), _stream())
+    cache[key] = (ver, out)
+    return out
+
+
+def folded_affine(conv_bias, bn):
+    """Per-channel (scale, shift) of eval-mode BatchNorm folded with the conv bias."""
+    owner = bn if bn is not None else None
+    if bn is None:
+        return None, (conv_bias.detach().float() if conv_bias is not None else None)
+    cache = owner.__dict__.setdefault("_fami_cache", {})
+    ver = _ver(bn.weight, bn.bias, bn.running_mean, bn.running_var, conv_bias)
+    hit = cache.get("affine")
+    if hit is not None and hit[0] == ver:
+        return hit[1], hit[2]
+    with torch.no_grad():
+        var = bn.running_var.double()
+        g = bn.weight.double() if bn.weight is not None else torch.ones_like(var)
+        b = bn.bias.double() if bn.bias is not None else torch.zeros_like(var)
+        s = g / torch.sqrt(var + bn.eps)
+        mu = bn.running_mean.double()
+        if conv_bias is not None:
+            mu = mu - conv_bias.double()
+        scale = s.float().contiguous()
+        shift = (b - mu * s).float().contiguous()
+    cache["affine"] = (ver, scale, shift)
+    return scale, shift
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution (+BN +residual +ReLU +upsample-on-write)
+# ------------------------------------------------------------------------------------------------
+
+def _conv_raw(x, w_packed, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, out, stats):
+    N, Cin, H, W, ip = meta(x)
+    Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    if out is None:
+        out = empty_nhwc(N, Cout, Ho * up, Wo * up, x.dtype, x.device)
+    oN, oC, oH, oW, op = meta(out)
+    if (oN, oC, oH, oW) != (N, Cout, Ho * up, Wo * up) or out.dtype != x.dtype:
+        raise ValueError("conv output buffer has shape %s, expected %s" % (tuple(out.shape), (N, Cout, Ho * up, Wo * up)))
+    rp = 0
+    if residual is not None:
+        rN, rC, rH, rW, rp = meta(residual)
+        if (rN, rC, rH, rW) != (N, Cout, Ho * up, Wo * up) or residual.dtype != x.dtype:
+            raise ValueError("residual shape %s does not match conv output %s"
+                             % (tuple(residual.shape), (N, Cout, Ho * up, Wo * up)))
+    d = ConvDesc(N, H, W, Cin, Cout, k, k, stride, pad, dil, Ho, Wo, up, int(bool(relu)), ip, op, rp,
+                 _code(x.dtype), int(stats is not None))
+    _lib.call("fami_conv2d_bn_act_fwd", ctypes.byref(d), _ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift),
+              _ptr(residual), _ptr(out), _ptr(stats), _stream())
+    return out
+
+
+def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None):
+    """conv -> [BatchNorm] -> [+residual] -> [ReLU] -> [nearest x`up`] in one launch (eval-mode BN)
+    or conv(+stats) -> finalize -> apply (train-mode BN, batch statistics).
+
+    conv: nn.Conv2d used as a parameter container (square kernel 1/3, groups=1); bn: nn.BatchNorm2d.
+    Reference chains: basic_model.py:44-63,83-113; basic_layer.py:55-73; hrnet.py:89-172.
+    """
+    _need_cuda(x)
+    if conv.groups != 1:
+        raise NotImplementedError("grouped convolutions are not on the FAMI-Pose hot path")
+    k = conv.kernel_size[0]
+    stride, pad, dil = conv.stride[0], conv.padding[0], conv.dilation[0]
+    w = packed_weight(conv, conv.weight, x.dtype)
+    Cout = conv.out_channels
+    if bn is not None and bn.training:
+        # batch statistics: raw conv (+bias) with fused per-channel sum / sum-of-squares
+        bias = conv.bias.detach().float() if conv.bias is not None else None
+        stats = torch.zeros(2 * Cout, dtype=torch.float64, device=x.device)
+        raw = _conv_raw(x, w, Cout, k, stride, pad, dil, None, bias, None, False, 1, None, stats)
+        N, _, Ho, Wo, rawp = meta(raw)
+        scale = torch.empty(Cout, dtype=torch.float32, device=x.device)
+        shift = torch.empty_like(scale)
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        track = bn.track_running_stats and bn.running_mean is not None
+        _lib.call("fami_bn_finalize", _ptr(stats), _ptr(bn.weight), _ptr(bn.bias),
+                  _ptr(bn.running_mean if track else None), _ptr(bn.running_var if track else None),
+                  _ptr(scale), _ptr(shift), None, None, Cout, N * Ho * Wo, float(bn.eps), float(mom), _stream())
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        if out is None:
+            out = empty_nhwc(N, Cout, Ho * up, Wo * up, x.dtype, x.device)
+        op = meta(out)[4]
+        rp = meta(residual)[4] if residual is not None else 0
+        _lib.call("fami_bn_apply_act", _ptr(raw), rawp, _ptr(scale), _ptr(shift), _ptr(residual), rp, _ptr(out), op,
+                  _code(x.dtype), N, Ho, Wo, Cout, up, int(bool(relu)), _stream())
+        return out
+    scale, shift = folded_affine(conv.bias, bn)
+    return _conv_raw(x, w, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, out, None)
+
+
+def upsample_nearest(x, factor):
+    """F.interpolate(scale_factor=factor, mode='nearest') (basic_model.py:116-125) as the
+    replicate-on-write epilogue with an identity affine."""
+    _need_cuda(x)
+    if factor not in (1, 2, 4, 8):
+        raise NotImplementedError("nearest upsample factor must be 1, 2, 4 or 8")
+    N, C, H, W, p = meta(x)
+    out = empty_nhwc(N, C, H * factor, W * factor, x.dtype, x.device)
+    one = torch.ones(C, dtype=torch.float32, device=x.device)
+    zero = torch.zeros(C, dtype=torch.float32, device=x.device)
+    _lib.call("fami_bn_apply_act", _ptr(x), p, _ptr(one), _ptr(zero), None, 0, _ptr(out), C, _code(x.dtype), N, H, W,
+              C, factor, 0, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# deformable convolution
+# ------------------------------------------------------------------------------------------------
+
+def dcn_fwd(x, offset, mask, weight, bias, owner, pad=3, dil=3, out=None):
+    """torchvision.ops.deform_conv2d(x, offset, weight, bias, stride=1, padding=pad, dilation=dil, mask=mask)
+    on NHWC operands (Alignment_V15.py:146,150,154,158)."""
+    _need_cuda(x, offset, mask)
+    B, C, H, W, xp = meta(x)
+    Cout, Cin, kh, kw = weight.shape
+    oB, OC, oH, oW, offp = meta(offset)
+    if OC % (2 * kh * kw) != 0:
+        # torchvision raises RuntimeError for a bad offset channel count (deform_conv.py:85-90)
+        raise RuntimeError("offset channels %d not a multiple of 2*kh*kw=%d" % (OC, 2 * kh * kw))
+    G = OC // (2 * kh * kw)
+    if C % G != 0 or Cin != C:
+        raise ValueError("in_channels %d must be divisible by offset groups %d and match the weight (%d)" % (C, G, Cin))
+    mB, MC, mH, mW, mp = meta(mask)
+    if MC != G * kh * kw or (oB, oH, oW) != (B, H, W) or (mB, mH, mW) != (B, H, W):
+        raise RuntimeError("offset/mask shapes %s %s inconsistent with input %s"
+                           % (tuple(offset.shape), tuple(mask.shape), tuple(x.shape)))
+    if out is None:
+        out = empty_nhwc(B, Cout, H, W, x.dtype, x.device)
+    outp = meta(out)[4]
+    w = packed_weight(owner, weight, x.dtype)
+    d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, offp, mp, outp, _code(x.dtype))
+    b = bias.detach().float() if bias is not None else None
+    _lib.call("fami_dcn_fwd", ctypes.byref(d), _ptr(x), _ptr(offset), _ptr(mask), _ptr(w), _ptr(b), _ptr(out),
+              _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# warp / small ops
+# ------------------------------------------------------------------------------------------------
+
+def warp_translate(src, txy, out=None):
+    """kornia.geometry.warp_affine(src, [[1,0,tx],[0,1,ty]], dsize=(H,W)) (Alignment_V15.py:133-135)."""
+    _need_cuda(src, txy)
+    B, C, H, W, sp = meta(src)
+    txy = txy.detach().float().contiguous()
+    if tuple(txy.shape) != (B, 2):
+        raise ValueError("txy must be [B,2]")
+    if out is None:
+        out = empty_nhwc(B, C, H, W, src.dtype, src.device)
+    op = meta(out)[4]
+    _lib.call("fami_warp_translate_fwd", _ptr(src), sp, _ptr(txy), _ptr(out), op, _code(src.dtype), B, H, W, C,
+              _stream())
+    return out
+
+
+def sub_bcast(a, b, rep):
+    """out[r] = a[r] - b for r < rep, a = rep stacked blocks shaped like b (dense NHWC)."""
+    _need_cuda(a, b)
+    Na, C, H, W, pa = meta(a)
+    Nb, Cb, Hb, Wb, pb = meta(b)
+    if pa != C or pb != Cb or (Nb * rep, Cb, Hb, Wb) != (Na, C, H, W):
+        raise ValueError("sub_bcast needs dense NHWC operands with a = rep x b")
+    out = empty_nhwc(Na, C, H, W, a.dtype, a.device)
+    _lib.call("fami_sub_bcast", _ptr(a), _ptr(b), _ptr(out), _code(a.dtype), Nb * C * H * W, rep, _stream())
+    return out
+
+
+def copy_into(src, dst):
+    """dst[:] = src for NHWC operands with independent pitches (one operand of a channel concat)."""
+    _need_cuda(src, dst)
+    N, C, H, W, sp = meta(src)
+    dN, dC, dH, dW, dp = meta(dst)
+    if (N, C, H, W) != (dN, dC, dH, dW) or src.dtype != dst.dtype:
+        raise ValueError("copy_into shape/dtype mismatch")
+    _lib.call("fami_copy2d", _ptr(src), sp, _ptr(dst), dp, _code(src.dtype), N * H * W, C, _stream())
+    return dst
+
+
+def flatten_nchw_order(x):
+    """nn.Flatten() of a (small) NHWC activation in the reference's C,H,W order -> float32 [N, C*H*W]."""
+    return to_nchw(x).reshape(x.shape[0], -1)
+
+
+def linear(x, weight, bias):
+    """nn.Linear forward on float32 [M,K] (Alignment_V15.py:69-71)."""
+    _need_cuda(x)
+    x = x.contiguous()
+    M, K = x.shape
+    N = weight.shape[0]
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    w = weight.detach().float().contiguous()
+    b = bias.detach().float().contiguous() if bias is not None else None
+    _lib.call("fami_linear_fwd", _ptr(x), _ptr(w), _ptr(b), _ptr(y), M, K, N, _stream())
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# losses / decode
+# ------------------------------------------------------------------------------------------------
+
+def joint_mse(pred, target, target_weight, want_grad=False, grad_scale=1.0):
+    """JointMSELoss (mse_loss.py:21-40).  pred: NHWC activation or NCHW fp32; target NCHW fp32."""
+    _need_cuda(pred, target)
+    if not is_nhwc(pred):
+        pred = to_nhwc(pred.float(), torch.float32)
+    B, J, H, W, pp = meta(pred)
+    target = target.float().contiguous()
+    w = target_weight.float().reshape(B, J).contiguous() if target_weight is not None else None
+    loss = torch.zeros((), dtype=torch.float32, device=pred.device)
+    grad = torch.empty((B, H, W, J), dtype=torch.float32, device=pred.device) if want_grad else None
+    _lib.call("fami_joint_mse_fwd_bwd", _ptr(pred), _code(pred.dtype), pp, _ptr(target), _ptr(w), _ptr(loss),
+              _ptr(grad), float(grad_scale), B, J, H, W, _stream())
+    return (loss, grad) if want_grad else loss
+
+
+def softmax_pkl(a, b, temperature=0.05):
+    """kl_div(input=softmax(a/T), target=softmax(b/T), 'mean') with the reference's quirk
+    (Alignment_V15.py:250-277); a, b NHWC activations [B,C,H,W]."""
+    _need_cuda(a, b)
+    B, C, H, W, ap = meta(a)
+    B2, C2, H2, W2, bp = meta(b)
+    if (B, C, H, W) != (B2, C2, H2, W2) or a.dtype != b.dtype:
+        raise ValueError("softmax_pkl operand mismatch")
+    out = torch.zeros((), dtype=torch.float32, device=a.device)
+    _lib.call("fami_softmax_pkl_fwd", _ptr(a), ap, _ptr(b), bp, _code(a.dtype), _ptr(out), B, H * W, C,
+              float(temperature), _stream())
+    return out
+
+
+def argmax_hw(hm):
+    """get_max_preds core (heatmaps_process.py:29-30): flat argmax + max per (b,j).  hm NHWC or NCHW."""
+    _need_cuda(hm)
+    if not is_nhwc(hm):
+        hm = to_nhwc(hm.float(), torch.float32)
+    B, J, H, W, p = meta(hm)
+    idx = torch.empty((B, J), dtype=torch.int32, device=hm.device)
+    mx = torch.empty((B, J), dtype=torch.float32, device=hm.device)
+    _lib.call("fami_argmax_hw", _ptr(hm), _code(hm.dtype), p, _ptr(idx), _ptr(mx), B, H * W, J, _stream())
+    return idx, mx

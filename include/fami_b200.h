@@ -1,0 +1,165 @@
+/*
+ * fami_b200.h -- C ABI of libfami_b200.so: the B200 (sm_100a) implementation of the FAMI-Pose
+ * forward/backward hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: its hot path
+ * is Python nn.Modules that bottom out in ATen / cuDNN / torchvision's _C.so.  Each entry point
+ * below names the reference call (file:line, relative to the reference tree) whose arithmetic it
+ * replaces; the Python shim in fami_pose_b200/ binds these symbols with ctypes and re-exposes them
+ * as nn.Module / autograd.Function objects with the reference's own names and signatures
+ * (INTEGRATION.md shows the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; fami_last_error() gives the text
+ *     (thread-local).  No entry point allocates device memory or synchronises the host.
+ *   - pointers are DEVICE pointers unless the name ends in _host.  `stream` is a cudaStream_t
+ *     passed as void* (0 = legacy default stream).
+ *   - activations are NHWC ("channels-last": element (n,y,x,c) at ((n*H+y)*W+x)*pitch + c) where
+ *     `pitch` >= C is the per-pixel element pitch, so channel slices of a wider buffer (the
+ *     reference's torch.cat along dim=1) can be read/written in place.
+ *   - dtype: FAMI_F32 activations are float; FAMI_BF16 activations are __nv_bfloat16 (tensor-core
+ *     path).  Per-channel scale/shift vectors, biases, loss outputs are always float.
+ */
+#ifndef FAMI_B200_H_
+#define FAMI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FAMI_ABI_VERSION 1
+
+enum { FAMI_F32 = 0, FAMI_BF16 = 1 };
+
+/* error text of the last failing call on this thread ("" if none) */
+const char* fami_last_error(void);
+int fami_abi_version(void);
+/* number of kernel launches issued through this library since load (bench.py gpu_launches) */
+int64_t fami_launch_count(void);
+
+/* ---- layout -------------------------------------------------------------------------------
+ * The reference keeps NCHW fp32 tensors (SURVEY.md 8b "Tensors").  These convert at the boundary.
+ * nchw_to_nhwc also performs the frame re-batching of Alignment_V15.py:117-119 when called per
+ * frame slice (src_n_stride lets sup_x[B,12,H,W] be read as 4 frame-major [B,3,H,W] slabs). */
+int fami_nchw_to_nhwc(const float* src, int64_t src_n_stride, void* dst, int dst_dtype, int N, int C,
+                      int H, int W, int dst_pitch, void* stream);
+int fami_nhwc_to_nchw(const void* src, int src_dtype, int src_pitch, float* dst, int N, int C, int H,
+                      int W, void* stream);
+
+/* ---- convolution + folded BN + residual + activation (+ nearest upsample on write) ---------
+ * Replaces nn.Conv2d -> nn.BatchNorm2d(eval) -> [+residual] -> nn.ReLU chains:
+ *   BasicBlock.forward   posetimation/layers/basic_model.py:44-63
+ *   Bottleneck.forward   posetimation/layers/basic_model.py:83-113
+ *   conv_bn_relu.forward posetimation/layers/basic_layer.py:55-73
+ *   HighResolutionModule fuse layers posetimation/backbones/hrnet.py:89-146,151-172
+ *   (conv1x1+BN+Interpolate(nearest x2^k) is `up` = 2^k; the running sum is `residual`)
+ *   HRNetPlus stem/transition/final_layer posetimation/backbones/hrnet.py:651-680
+ *   y[n, yo*up+dy, xo*up+dx, o] = act( scale[o]*conv(x)[n,yo,xo,o] + shift[o] + residual[same] )
+ * Weights are pre-packed by fami_pack_conv_weight to [kh*kw][Cin][CoutPad] (CoutPad = Cout rounded
+ * up to 16), float for the F32 path, bf16 UMMA-tiled for the BF16 tensor-core path.              */
+typedef struct fami_conv_desc {
+  int32_t N, H, W, Cin;          /* input  [N,H,W,Cin], pitch in_pitch          */
+  int32_t Cout, kh, kw;          /* square kernels 1 or 3                        */
+  int32_t stride, pad, dil;
+  int32_t Ho, Wo;                /* conv output size (before `up`)               */
+  int32_t up;                    /* 1,2,4,8: nearest-neighbour replication on write */
+  int32_t relu;                  /* 0/1                                          */
+  int32_t in_pitch, out_pitch, res_pitch;
+  int32_t dtype;                 /* FAMI_F32 or FAMI_BF16 (x, y, residual, w)    */
+  int32_t stats;                 /* 1: also accumulate per-channel sum / sum-of-squares of the RAW
+                                    (post scale/shift, pre residual/act) output into the double
+                                    array stats_out[2*Cout], which the caller zeroes (train-mode BN) */
+} fami_conv_desc;
+
+int fami_conv_cout_pad(int Cout);
+int64_t fami_packed_weight_elems(int Cout, int Cin, int kh, int kw, int dtype);
+int fami_pack_conv_weight(const float* w_oihw, void* w_packed, int Cout, int Cin, int kh, int kw,
+                          int dtype, void* stream);
+int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w_packed,
+                           const float* scale, const float* shift, const void* residual, void* y,
+                           double* stats_out, void* stream);
+
+/* train-mode BatchNorm (batch statistics over N*H*W, biased variance, eps, momentum update):
+ * nn.BatchNorm2d(momentum=0.1) as used at basic_model.py:29,39 and hrnet.py:53,106,124,137.
+ * fami_bn_finalize turns (sum, sumsq) into scale/shift and updates running stats;
+ * fami_bn_apply_act is y = act(scale*x + shift + residual) with the same `up` write semantics.  */
+int fami_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float* scale, float* shift, float* save_mean,
+                     float* save_invstd, int C, int64_t count, float eps, float momentum, void* stream);
+int fami_bn_apply_act(const void* x, int x_pitch, const float* scale, const float* shift,
+                      const void* residual, int res_pitch, void* y, int y_pitch, int dtype, int N, int Ho,
+                      int Wo, int C, int up, int relu, void* stream);
+
+/* ---- modulated deformable convolution v2 (the north-star kernel) ---------------------------
+ * Replaces torchvision.ops.deform_conv2d as constructed/called at
+ * posetimation/zoo/Alignment/Alignment_V15.py:83,89,95,101 / :146,150,154,158
+ * (DeformConv2d(C,Cout,3,padding=3,dilation=3), offset groups G = offset_channels/18, mask raw).
+ * x [B,H,W,C]; offset [B,H,W,18G] (channel g*18+2t = dy, +1 = dx); mask [B,H,W,9G];
+ * w_packed [9][C][CoutPad]; out [B,H,W,Cout].  Fused gather -> on-chip columns -> contraction; the
+ * [C*9, B*H*W] im2col buffer of the reference never exists in HBM.                              */
+typedef struct fami_dcn_desc {
+  int32_t B, H, W, C, Cout, G;
+  int32_t kh, kw, stride, pad, dil; /* 3,3,1,3,3 in the reference; stride must be 1 */
+  int32_t x_pitch, off_pitch, mask_pitch, out_pitch;
+  int32_t dtype;                    /* storage of x/offset/mask/out: FAMI_F32 or FAMI_BF16 */
+} fami_dcn_desc;
+
+int fami_dcn_fwd(const fami_dcn_desc* d, const void* x, const void* offset, const void* mask,
+                 const void* w_packed, const float* bias, void* out, void* stream);
+/* backward (fp32 storage): grad wrt input (scatter), offset+mask, weight+bias.
+ * torchvision: deformable_col2im / deformable_col2im_coord + GEMMs.              */
+int fami_dcn_bwd(const fami_dcn_desc* d, const float* x, const float* offset, const float* mask,
+                 const float* w_packed, const float* grad_out, float* grad_x, float* grad_offset,
+                 float* grad_mask, float* grad_w_packed, float* grad_bias, void* stream);
+
+/* ---- global translation warp ---------------------------------------------------------------
+ * Replaces kornia.geometry.warp_affine(src, [[1,0,tx],[0,1,ty]], dsize=(H,W)) at
+ * Alignment_V15.py:133-135: out[b,y,x,c] = bilinear_zero_pad(src[b], y - ty_b, x - tx_b).
+ * txy [B,2] = (tx, ty).  out may be a channel slice of the 4-frame concat buffer (:139).        */
+int fami_warp_translate_fwd(const void* src, int src_pitch, const float* txy, void* out, int out_pitch,
+                            int dtype, int B, int H, int W, int C, void* stream);
+int fami_warp_translate_bwd(const float* src, int src_pitch, const float* txy, const float* grad_out,
+                            int go_pitch, float* grad_src, int gs_pitch, float* grad_txy, int B, int H,
+                            int W, int C, void* stream);
+
+/* ---- small dense pieces --------------------------------------------------------------------
+ * a - b (Alignment_V15.py:132 `sup_bb_feat - kf_bb_feat`), b broadcast over `rep` groups of the
+ * leading dimension: out[r*n + i] = a[r*n + i] - b[i].                                          */
+int fami_sub_bcast(const void* a, const void* b, void* out, int dtype, int64_t n, int rep, void* stream);
+/* dst[r, 0:cols] = src[r, 0:cols] for r < rows with independent row pitches: writes one operand of
+ * the reference's torch.cat(dim=1) (Alignment_V15.py:143,160) into its channel slice.           */
+int fami_copy2d(const void* src, int src_pitch, void* dst, int dst_pitch, int dtype, int64_t rows, int cols,
+                void* stream);
+/* nn.Linear chain of feat_global_offset_layers[7..9] (Alignment_V15.py:69-71): y = x W^T + b.
+ * x [M,K] float, w [N,K] float (torch layout), y [M,N].                                         */
+int fami_linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int K, int N,
+                    void* stream);
+
+/* ---- losses --------------------------------------------------------------------------------
+ * JointMSELoss.forward, posetimation/loss/mse_loss.py:21-40 (use_target_weight, divided by J):
+ * loss = 1/(J*B*HW) * sum w_bj^2 (pred-gt)^2 ; pred NHWC [B,H,W,J] (pitch), target NCHW fp32
+ * [B,J,H,W] as the reference's loader produces it, weight [B,J].  grad_pred (NHWC float, may be
+ * NULL) = d loss / d pred * grad_scale.  loss_out is a single float accumulated with atomics:
+ * caller zeroes it.                                                                             */
+int fami_joint_mse_fwd_bwd(const void* pred, int pred_dtype, int pred_pitch, const float* target_nchw,
+                           const float* weight, float* loss_out, float* grad_pred, float grad_scale,
+                           int B, int J, int H, int W, void* stream);
+/* MI estimator core, Alignment_V15.py:250-277: kl_div(input=softmax(a/T), target=softmax(b/T),
+ * reduction='mean') with the reference's quirk (probabilities passed as log-probs), i.e.
+ * mean_{r,l}( t*(log t - p) ), rows r = (sample, channel), l over H*W.  a, b NHWC [B,HW,C].
+ * out: single float accumulated with atomics (caller zeroes).                                   */
+int fami_softmax_pkl_fwd(const void* a, int a_pitch, const void* b, int b_pitch, int dtype, float* out,
+                         int B, int HW, int C, float temperature, void* stream);
+
+/* ---- keypoint argmax -----------------------------------------------------------------------
+ * get_max_preds, datasets/process/heatmaps_process.py:16-44: flat argmax over H*W per (b,j),
+ * first maximum wins; idx_out [B,J] int32, maxval_out [B,J] float.  hm NHWC.                    */
+int fami_argmax_hw(const void* hm, int dtype, int pitch, int32_t* idx_out, float* maxval_out, int B,
+                   int HW, int J, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAMI_B200_H_ */

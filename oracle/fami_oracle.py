@@ -1,0 +1,592 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the FAMI-Pose hot path (the parity oracle).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product path (fami_pose_b200) never does and fails loudly without its CUDA
+library.
+
+Every function cites the reference file:line it restates (paths relative to /root/reference, or
+the third-party call the reference makes).  Pinning status (see DESIGN.md "Oracle"):
+the reference ships NO golden vectors/tests for this path, so the restatement
+is pinned against outputs of the reference itself run in the build container
+(tests/golden/make_golden.py -> tests/golden/*.npz) and against torchvision's CPU deform_conv2d
+(the un-vendored dependency the reference calls, Alignment_V15.py:11,83,146).
+
+Third-party arithmetic restated here:
+  * torchvision.ops.deform_conv2d (reference does not pin a version; container has 0.26.0):
+    modulated deformable convolution v2 -- dcn_fwd / dcn_bwd below.
+  * kornia.geometry.warp_affine (unpinned, not installed): restated with kornia>=0.6 semantics
+    (normalised homography, affine_grid/grid_sample align_corners=True, bilinear, zeros) --
+    warp_affine_kornia; and its closed form for pure translations -- warp_translate.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------------
+# Modulated deformable convolution (torchvision.ops.deform_conv2d as called at
+# posetimation/zoo/Alignment/Alignment_V15.py:83,146,150,154,158; spec: SURVEY.md Appendix B)
+# --------------------------------------------------------------------------------------------
+
+
+def _bilinear_parts(py, px, H, W):
+    """Corner indices, weights and validity for sample positions (numpy arrays, any shape).
+
+    torchvision semantics: the sample is 0 if py<=-1 or py>=H or px<=-1 or px>=W; each of the four
+    corners contributes only when it lies inside [0,H-1]x[0,W-1].
+    """
+    inside = (py > -1) & (py < H) & (px > -1) & (px < W)
+    y0 = np.floor(py)
+    x0 = np.floor(px)
+    ly = py - y0
+    lx = px - x0
+    hy = 1.0 - ly
+    hx = 1.0 - lx
+    y0 = y0.astype(np.int64)
+    x0 = x0.astype(np.int64)
+    y1 = y0 + 1
+    x1 = x0 + 1
+    v00 = inside & (y0 >= 0) & (x0 >= 0)
+    v01 = inside & (y0 >= 0) & (x1 <= W - 1)
+    v10 = inside & (y1 <= H - 1) & (x0 >= 0)
+    v11 = inside & (y1 <= H - 1) & (x1 <= W - 1)
+    return (y0, x0, y1, x1), (ly, lx, hy, hx), (v00, v01, v10, v11)
+
+
+def _gather(xb, yy, xx, valid, H, W):
+    """xb [C,H,W]; yy/xx/valid [...]; returns [C, ...] with zeros where invalid."""
+    yc = np.clip(yy, 0, H - 1)
+    xc = np.clip(xx, 0, W - 1)
+    v = xb[:, yc, xc]
+    return v * valid[None].astype(xb.dtype)
+
+
+def dcn_columns(x, offset, mask, kh=3, kw=3, stride=1, pad=3, dil=3):
+    """Sampled, modulated columns col[B, C, kh*kw, Ho, Wo] (numpy).  SURVEY.md Appendix B."""
+    x = np.asarray(x)
+    offset = np.asarray(offset)
+    B, C, H, W = x.shape
+    K = kh * kw
+    G = offset.shape[1] // (2 * K)
+    assert offset.shape[1] == 2 * K * G and C % G == 0
+    cpg = C // G
+    Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+    assert offset.shape[2:] == (Ho, Wo)
+    col = np.zeros((B, C, K, Ho, Wo), dtype=x.dtype)
+    ys = (np.arange(Ho) * stride - pad)[:, None].astype(x.dtype)
+    xs = (np.arange(Wo) * stride - pad)[None, :].astype(x.dtype)
+    for b in range(B):
+        for g in range(G):
+            xb = x[b, g * cpg:(g + 1) * cpg]
+            for t in range(K):
+                i, j = divmod(t, kw)
+                py = ys + i * dil + offset[b, g * 2 * K + 2 * t]
+                px = xs + j * dil + offset[b, g * 2 * K + 2 * t + 1]
+                (y0, x0, y1, x1), (ly, lx, hy, hx), (v00, v01, v10, v11) = _bilinear_parts(py, px, H, W)
+                val = (hy * hx)[None] * _gather(xb, y0, x0, v00, H, W) \
+                    + (hy * lx)[None] * _gather(xb, y0, x1, v01, H, W) \
+                    + (ly * hx)[None] * _gather(xb, y1, x0, v10, H, W) \
+                    + (ly * lx)[None] * _gather(xb, y1, x1, v11, H, W)
+                if mask is not None:
+                    val = val * np.asarray(mask)[b, g * K + t][None]
+                col[b, g * cpg:(g + 1) * cpg, t] = val
+    return col
+
+
+def dcn_fwd(x, offset, mask, weight, bias=None, stride=1, pad=3, dil=3):
+    """out[b,o,y,x] = bias[o] + sum_{c,t} W[o,c,t] * col[b,c,t,y,x]   (weight groups = 1)."""
+    weight = np.asarray(weight)
+    Co, C, kh, kw = weight.shape
+    col = dcn_columns(x, offset, mask, kh, kw, stride, pad, dil)
+    out = np.einsum("oct,bctyx->boyx", weight.reshape(Co, C, kh * kw), col, optimize=True)
+    if bias is not None:
+        out = out + np.asarray(bias)[None, :, None, None]
+    return out.astype(np.asarray(x).dtype)
+
+
+def dcn_bwd(x, offset, mask, weight, grad_out, stride=1, pad=3, dil=3):
+    """Analytic gradients (g_x, g_offset, g_mask, g_weight, g_bias); SURVEY.md Appendix B backward.
+
+    Follows torchvision's deformable_col2im / col2im_coord definitions: floor() is treated as
+    locally constant, out-of-range corners contribute 0 to both value and coordinate derivative.
+    """
+    x = np.asarray(x)
+    offset = np.asarray(offset)
+    mask = np.asarray(mask)
+    weight = np.asarray(weight)
+    grad_out = np.asarray(grad_out)
+    B, C, H, W = x.shape
+    Co, _, kh, kw = weight.shape
+    K = kh * kw
+    G = offset.shape[1] // (2 * K)
+    cpg = C // G
+    Ho, Wo = grad_out.shape[2:]
+    g_col = np.einsum("oct,boyx->bctyx", weight.reshape(Co, C, K), grad_out, optimize=True)
+    g_x = np.zeros_like(x)
+    g_off = np.zeros_like(offset)
+    g_mask = np.zeros_like(mask)
+    ys = (np.arange(Ho) * stride - pad)[:, None].astype(x.dtype)
+    xs = (np.arange(Wo) * stride - pad)[None, :].astype(x.dtype)
+    col_unmod = np.zeros((B, C, K, Ho, Wo), dtype=x.dtype)
+    for b in range(B):
+        for g in range(G):
+            cs = slice(g * cpg, (g + 1) * cpg)
+            xb = x[b, cs]
+            for t in range(K):
+                i, j = divmod(t, kw)
+                py = ys + i * dil + offset[b, g * 2 * K + 2 * t]
+                px = xs + j * dil + offset[b, g * 2 * K + 2 * t + 1]
+                (y0, x0, y1, x1), (ly, lx, hy, hx), (v00, v01, v10, v11) = _bilinear_parts(py, px, H, W)
+                a00 = _gather(xb, y0, x0, v00, H, W)
+                a01 = _gather(xb, y0, x1, v01, H, W)
+                a10 = _gather(xb, y1, x0, v10, H, W)
+                a11 = _gather(xb, y1, x1, v11, H, W)
+                val = (hy * hx)[None] * a00 + (hy * lx)[None] * a01 + (ly * hx)[None] * a10 + (ly * lx)[None] * a11
+                col_unmod[b, cs, t] = val
+                m = mask[b, g * K + t]
+                gc = g_col[b, cs, t]                           # [cpg,Ho,Wo]
+                g_mask[b, g * K + t] = (gc * val).sum(0)
+                dval_dy = hx[None] * (a10 - a00) + lx[None] * (a11 - a01)
+                dval_dx = hy[None] * (a01 - a00) + ly[None] * (a11 - a10)
+                g_off[b, g * 2 * K + 2 * t] = (gc * dval_dy).sum(0) * m
+                g_off[b, g * 2 * K + 2 * t + 1] = (gc * dval_dx).sum(0) * m
+                gm = gc * m[None]
+                for (yy, xx, wgt, vv) in ((y0, x0, hy * hx, v00), (y0, x1, hy * lx, v01),
+                                          (y1, x0, ly * hx, v10), (y1, x1, ly * lx, v11)):
+                    yc = np.clip(yy, 0, H - 1)
+                    xc = np.clip(xx, 0, W - 1)
+                    contrib = gm * (wgt * vv)[None]
+                    for c in range(cpg):
+                        np.add.at(g_x[b, g * cpg + c], (yc, xc), contrib[c])
+    col = col_unmod * np.repeat(mask.reshape(B, G, K, Ho, Wo), cpg, axis=1)
+    g_w = np.einsum("boyx,bctyx->oct", grad_out, col, optimize=True).reshape(weight.shape)
+    g_b = grad_out.sum((0, 2, 3))
+    return g_x, g_off, g_mask, g_w, g_b
+
+
+# --------------------------------------------------------------------------------------------
+# Global translation warp (kornia.geometry.warp_affine as called at Alignment_V15.py:133-135)
+# --------------------------------------------------------------------------------------------
+
+
+def _normal_transform_pixel(h, w, dtype):
+    """kornia.geometry.conversions.normal_transform_pixel: pixel -> [-1,1] (align_corners=True)."""
+    n = torch.tensor([[1.0, 0.0, -1.0], [0.0, 1.0, -1.0], [0.0, 0.0, 1.0]], dtype=dtype)
+    n[0, 0] = n[0, 0] * 2.0 / max(w - 1, 1e-14)
+    n[1, 1] = n[1, 1] * 2.0 / max(h - 1, 1e-14)
+    return n
+
+
+def warp_affine_kornia(src, M, dsize, mode="bilinear", padding_mode="zeros", align_corners=True):
+    """Restatement of kornia>=0.6 `warp_affine(src[B,C,H,W], M[B,2,3], dsize=(H,W))`.
+
+    M3 = [M; 0 0 1]; theta = inverse(N_dst @ M3 @ inverse(N_src))[:, :2];
+    grid = affine_grid(theta, align_corners=True); grid_sample(bilinear, zeros, align_corners=True).
+    """
+    B, C, H, W = src.shape
+    M3 = torch.zeros(B, 3, 3, dtype=src.dtype, device=src.device)
+    M3[:, :2] = M
+    M3[:, 2, 2] = 1.0
+    n_src = _normal_transform_pixel(H, W, src.dtype).to(src.device)
+    n_dst = _normal_transform_pixel(dsize[0], dsize[1], src.dtype).to(src.device)
+    dst_norm_trans_src_norm = n_dst @ M3 @ torch.inverse(n_src)
+    src_norm_trans_dst_norm = torch.inverse(dst_norm_trans_src_norm)
+    grid = F.affine_grid(src_norm_trans_dst_norm[:, :2, :], [B, C, dsize[0], dsize[1]],
+                         align_corners=align_corners)
+    return F.grid_sample(src, grid, mode=mode, padding_mode=padding_mode, align_corners=align_corners)
+
+
+def warp_translate(src, txy):
+    """Closed form of the above for M=[[1,0,tx],[0,1,ty]]: out[b,c,y,x] = bilinear_zeropad(src, y-ty, x-tx).
+
+    grid_sample(zeros) semantics: each corner contributes iff inside the image (no (-1,H) cut-off
+    subtlety: a corner outside contributes 0, which is the same thing).  numpy, float64/32.
+    """
+    src = np.asarray(src)
+    txy = np.asarray(txy)
+    B, C, H, W = src.shape
+    out = np.zeros_like(src)
+    for b in range(B):
+        py = np.arange(H, dtype=src.dtype)[:, None] - txy[b, 1] + np.zeros((1, W), src.dtype)
+        px = np.arange(W, dtype=src.dtype)[None, :] - txy[b, 0] + np.zeros((H, 1), src.dtype)
+        y0 = np.floor(py)
+        x0 = np.floor(px)
+        ly, lx = py - y0, px - x0
+        y0 = y0.astype(np.int64)
+        x0 = x0.astype(np.int64)
+        for (yy, xx, wgt) in ((y0, x0, (1 - ly) * (1 - lx)), (y0, x0 + 1, (1 - ly) * lx),
+                              (y0 + 1, x0, ly * (1 - lx)), (y0 + 1, x0 + 1, ly * lx)):
+            valid = (yy >= 0) & (yy <= H - 1) & (xx >= 0) & (xx <= W - 1)
+            out[b] += _gather(src[b], yy, xx, valid, H, W) * wgt[None]
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# Losses (posetimation/loss/mse_loss.py:21-40; Alignment_V15.py:250-277)
+# --------------------------------------------------------------------------------------------
+
+
+def joint_mse(output, target, target_weight, use_target_weight=True, divided_num_joints=True):
+    """JointMSELoss.forward: sum_j mean_{b,p}((pred_j*w_bj - gt_j*w_bj)^2) [/ J]."""
+    output = np.asarray(output, dtype=np.float64)
+    target = np.asarray(target, dtype=np.float64)
+    B, J = output.shape[:2]
+    p = output.reshape(B, J, -1)
+    t = target.reshape(B, J, -1)
+    if use_target_weight:
+        w = np.asarray(target_weight, dtype=np.float64).reshape(B, J, 1)
+        p = p * w
+        t = t * w
+    loss = ((p - t) ** 2).mean(axis=(0, 2)).sum()
+    if divided_num_joints:
+        loss = loss / J
+    return loss
+
+
+def softmax_pkl(inp_rows, tgt_rows, temperature=0.05):
+    """The reference's MI estimator core: kl_div(input=softmax(a/T), target=softmax(b/T), 'mean').
+
+    QUIRK reproduced on purpose: F.kl_div expects log-probabilities as `input`
+    but the reference passes probabilities, so the value is mean_{all elems}( t*(log t - p) ).
+    Rows: [R, L]; softmax over L (dim=1).  float64 numpy.
+    """
+    a = np.asarray(inp_rows, dtype=np.float64) / temperature
+    b = np.asarray(tgt_rows, dtype=np.float64) / temperature
+    a = a - a.max(1, keepdims=True)
+    b = b - b.max(1, keepdims=True)
+    p = np.exp(a)
+    p /= p.sum(1, keepdims=True)
+    logt = b - np.log(np.exp(b).sum(1, keepdims=True))
+    t = np.exp(logt)
+    # torch xlogy semantics: t==0 -> 0
+    term = np.where(t > 0, t * logt, 0.0) - t * p
+    return term.mean()
+
+
+def get_max_preds(batch_heatmaps):
+    """datasets/process/heatmaps_process.py:16-44: flat argmax (first max wins) -> (x,y), maxvals;
+    coordinates zeroed where maxval <= 0.  Returns (preds[B,J,2] float32, maxvals[B,J,1], idx[B,J])."""
+    hm = np.asarray(batch_heatmaps)
+    B, J, H, W = hm.shape
+    r = hm.reshape(B, J, -1)
+    idx = np.argmax(r, 2)
+    maxvals = np.amax(r, 2).reshape(B, J, 1)
+    preds = np.zeros((B, J, 2), np.float32)
+    preds[:, :, 0] = idx % W
+    preds[:, :, 1] = np.floor(idx / W)
+    preds *= (maxvals > 0.0).astype(np.float32)
+    return preds, maxvals, idx
+
+
+def refine_quarter_pixel(batch_heatmaps, coords):
+    """heatmaps_process.py:47-62 (the +-0.25 px shift toward the higher neighbour), before the
+    inverse affine.  coords modified copy returned."""
+    hm = np.asarray(batch_heatmaps)
+    coords = np.array(coords, copy=True)
+    B, J, H, W = hm.shape
+    for n in range(B):
+        for p in range(J):
+            px = int(math.floor(coords[n][p][0] + 0.5))
+            py = int(math.floor(coords[n][p][1] + 0.5))
+            if 1 < px < W - 1 and 1 < py < H - 1:
+                diff = np.array([hm[n][p][py][px + 1] - hm[n][p][py][px - 1],
+                                 hm[n][p][py + 1][px] - hm[n][p][py - 1][px]])
+                coords[n][p] += np.sign(diff) * .25
+    return coords
+
+
+# --------------------------------------------------------------------------------------------
+# Whole-model functional restatement over a state_dict (torch CPU fp32/fp64).
+# Keys are the reference's state_dict keys (SURVEY.md section 5 "Checkpoint").
+# --------------------------------------------------------------------------------------------
+
+
+class FunctionalFami:
+    """Functional forward of HRNetPlus / HRNet / Alignment_V15 over a reference-keyed state_dict.
+
+    bn_train=False: BatchNorm uses running stats (module.eval()); True: batch statistics (biased
+    variance, eps 1e-5), which is what the reference's default training does even with frozen
+    HRNet weights (Alignment_V15.py:110-111, hrnet.py:686-690 only clear requires_grad).
+    """
+
+    def __init__(self, sd, width=48, num_joints=17, num_sup=4, offset_groups=12, bn_train=False,
+                 conv_hook=None):
+        self.sd = sd
+        self.C = width
+        self.J = num_joints
+        self.num_sup = num_sup
+        self.G = offset_groups
+        self.bn_train = bn_train
+        self.conv_hook = conv_hook  # optional fn(x, w) -> (x, w), e.g. to emulate tf32/bf16 operands
+
+    # -- primitives ---------------------------------------------------------------------------
+    def conv(self, x, name, stride=1, pad=0, dil=1):
+        w = self.sd[name + ".weight"]
+        b = self.sd.get(name + ".bias")
+        if self.conv_hook is not None:
+            x, w = self.conv_hook(x, w)
+        return F.conv2d(x, w, b, stride=stride, padding=pad, dilation=dil)
+
+    def bn(self, x, name):
+        sd = self.sd
+        if self.bn_train:
+            return F.batch_norm(x, None, None, sd[name + ".weight"], sd[name + ".bias"], True, 0.1, 1e-5)
+        return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"],
+                            sd[name + ".weight"], sd[name + ".bias"], False, 0.1, 1e-5)
+
+    def basic_block(self, x, p):
+        """posetimation/layers/basic_model.py:44-63"""
+        out = F.relu(self.bn(self.conv(x, p + "conv1", 1, 1), p + "bn1"))
+        out = self.bn(self.conv(out, p + "conv2", 1, 1), p + "bn2")
+        if (p + "downsample.0.weight") in self.sd:
+            res = self.bn(self.conv(x, p + "downsample.0"), p + "downsample.1")
+        else:
+            res = x
+        return F.relu(out + res)
+
+    def bottleneck(self, x, p):
+        """basic_model.py:83-113"""
+        out = F.relu(self.bn(self.conv(x, p + "conv1"), p + "bn1"))
+        out = F.relu(self.bn(self.conv(out, p + "conv2", 1, 1), p + "bn2"))
+        out = self.bn(self.conv(out, p + "conv3"), p + "bn3")
+        if (p + "downsample.0.weight") in self.sd:
+            res = self.bn(self.conv(x, p + "downsample.0"), p + "downsample.1")
+        else:
+            res = x
+        return F.relu(out + res)
+
+    def chain(self, x, p, n):
+        """ChainOfBasicBlocks, basic_model.py:128-148"""
+        for i in range(n):
+            x = self.basic_block(x, "%slayers.%d." % (p, i))
+        return x
+
+    def cbr(self, x, p, stride, pad, dil, has_bn=True, has_relu=True):
+        """conv_bn_relu, basic_layer.py:13-73"""
+        x = self.conv(x, p + "conv", stride, pad, dil)
+        if has_bn:
+            x = self.bn(x, p + "bn")
+        if has_relu:
+            x = F.relu(x)
+        return x
+
+    # -- HRNet --------------------------------------------------------------------------------
+    def hr_module(self, xs, p, nb, multi_scale_output=True):
+        """HighResolutionModule.forward, hrnet.py:151-172 (+ _make_fuse_layers :89-146)."""
+        xs = [self._branch(xs[i], "%sbranches.%d." % (p, i)) for i in range(nb)]
+        outs = []
+        for i in range(nb if multi_scale_output else 1):
+            y = None
+            for j in range(nb):
+                if j == i:
+                    t = xs[j]
+                elif j > i:
+                    q = "%sfuse_layers.%d.%d." % (p, i, j)
+                    t = self.bn(self.conv(xs[j], q + "0"), q + "1")
+                    t = F.interpolate(t, scale_factor=2 ** (j - i), mode="nearest")
+                else:
+                    t = xs[j]
+                    for k in range(i - j):
+                        q = "%sfuse_layers.%d.%d.%d." % (p, i, j, k)
+                        t = self.bn(self.conv(t, q + "0", 2, 1), q + "1")
+                        if k != i - j - 1:
+                            t = F.relu(t)
+                y = t if y is None else y + t
+            outs.append(F.relu(y))
+        return outs
+
+    def _branch(self, x, p):
+        for b in range(4):
+            x = self.basic_block(x, "%s%d." % (p, b))
+        return x
+
+    def hrnet_trunk(self, x, p):
+        """HRNetPlus.forward, hrnet.py:651-680 (identical trunk in HRNet.forward :302-333)."""
+        x = F.relu(self.bn(self.conv(x, p + "conv1", 2, 1), p + "bn1"))
+        x = F.relu(self.bn(self.conv(x, p + "conv2", 2, 1), p + "bn2"))
+        for i in range(4):
+            x = self.bottleneck(x, "%slayer1.%d." % (p, i))
+        xs = [F.relu(self.bn(self.conv(x, p + "transition1.0.0", 1, 1), p + "transition1.0.1")),
+              F.relu(self.bn(self.conv(x, p + "transition1.1.0.0", 2, 1), p + "transition1.1.0.1"))]
+        xs = self.hr_module(xs, p + "stage2.0.", 2)
+        xs = xs + [F.relu(self.bn(self.conv(xs[-1], p + "transition2.2.0.0", 2, 1), p + "transition2.2.0.1"))]
+        for m in range(4):
+            xs = self.hr_module(xs, "%sstage3.%d." % (p, m), 3)
+        xs = xs + [F.relu(self.bn(self.conv(xs[-1], p + "transition3.3.0.0", 2, 1), p + "transition3.3.0.1"))]
+        for m in range(3):
+            xs = self.hr_module(xs, "%sstage4.%d." % (p, m), 4, multi_scale_output=(m != 2))
+        feat = xs[0]
+        hm = self.conv(feat, p + "final_layer")
+        return hm, feat
+
+    # -- Alignment_V15 ------------------------------------------------------------------------
+    def global_offset(self, d):
+        """feat_global_offset_layers, Alignment_V15.py:61-72."""
+        p = "feat_global_offset_layers."
+        x = self.chain(d, p + "0.", 1)
+        for i in range(1, 6):
+            x = self.cbr(x, "%s%d." % (p, i), 2, 1, 1)
+        x = x.flatten(1)
+        for i in (7, 8, 9):
+            x = F.linear(x, self.sd["%s%d.weight" % (p, i)], self.sd["%s%d.bias" % (p, i)])
+        return x
+
+    def dcn(self, x, off, msk, name):
+        import torchvision
+        return torchvision.ops.deform_conv2d(x, off, self.sd[name + ".weight"], self.sd[name + ".bias"],
+                                             stride=1, padding=3, dilation=3, mask=msk)
+
+    def mi_feat_label(self, feat, y):
+        """Alignment_V15.py:250-263"""
+        B = feat.shape[0]
+        pred = self.conv(feat, "hrnet.final_layer").reshape(B * self.J, -1)
+        yy = y.reshape(B * self.J, -1)
+        return F.kl_div(input=F.softmax(pred.detach() / 0.05, dim=1), target=F.softmax(yy / 0.05, dim=1),
+                        reduction="mean")
+
+    def mi_feat_feat(self, f1, f2):
+        """Alignment_V15.py:265-277"""
+        B, C = f1.shape[:2]
+        a = f1.reshape(B * C, -1)
+        b = f2.reshape(B * C, -1)
+        return F.kl_div(input=F.softmax(a.detach() / 0.05, dim=1), target=F.softmax(b / 0.05, dim=1),
+                        reduction="mean")
+
+    def alignment(self, kf_x, sup_x, with_mi=False, return_intermediates=False):
+        """Alignment_V15.forward, Alignment_V15.py:113-183."""
+        B = kf_x.shape[0]
+        ns = sup_x.shape[1] // 3
+        sup = torch.cat(torch.chunk(sup_x, ns, dim=1), dim=0)
+        x = torch.cat([kf_x, sup], dim=0)
+        hm_all, feat_all = self.hrnet_trunk(x, "hrnet.")
+        kf_hm = hm_all[:B]
+        feats = torch.chunk(feat_all, ns + 1, dim=0)
+        kf_feat = feats[0]
+        H, W = kf_feat.shape[2:]
+        warped = []
+        txys = []
+        for i in range(ns):
+            sf = feats[1 + i]
+            txy = self.global_offset(sf - kf_feat)
+            txys.append(txy)
+            M = torch.eye(3, dtype=sf.dtype)[0:2].view(1, 2, 3).repeat(B, 1, 1)
+            M[:, 0, 2], M[:, 1, 2] = txy[:, 0], txy[:, 1]
+            warped.append(warp_affine_kornia(sf, M, (H, W)))
+        agg = self.chain(torch.cat(warped, dim=1), "sup_agg_block.", 2)
+        comb = self.chain(torch.cat([agg, kf_feat], dim=1), "combined_feat_layers.", 1)
+        inter = {"kf_feat": kf_feat, "txy": torch.stack(txys, 0), "agg_sup_feat": agg, "combined0": comb}
+        cur = comb
+        src = [None, None, agg, None]
+        for k in range(1, 5):
+            off = self.cbr(cur, "dcn_offset_%d." % k, 1, 3, 3, False, False)
+            msk = self.cbr(cur, "dcn_mask_%d." % k, 1, 3, 3, False, False)
+            inp = cur if src[k - 1] is None else src[k - 1]
+            cur = self.dcn(inp, off, msk, "dcn_%d" % k)
+            inter["dcn%d" % k] = cur
+        allf = self.chain(torch.cat([kf_feat, cur], dim=1), "init_feature_agg_block.", 3)
+        final = self.conv(allf, "agg_final_layer", 1, 1)
+        inter["all_agg"] = allf
+        out = [final, kf_hm]
+        if with_mi:
+            mi = [self.mi_feat_label(allf, final), self.mi_feat_feat(kf_feat, allf),
+                  self.mi_feat_label(agg, final), self.mi_feat_feat(agg, allf),
+                  self.mi_feat_label(kf_feat, final), self.mi_feat_feat(kf_feat, allf)]
+            out.append(mi)
+        if return_intermediates:
+            out.append(inter)
+        return tuple(out)
+
+
+def combine_losses(mse, mi, w_mse=1.0, alpha=0.5, beta=0.1):
+    """engine/core/functions/alignment_mi_function_term6_1.py:119-148:
+    loss = MSE*w + alpha*( -beta*mi1 + beta*mi2 + mi3 - mi4 + mi5 - mi6 )."""
+    return mse * w_mse + alpha * (-beta * mi[0] + beta * mi[1] + mi[2] - mi[3] + mi[4] - mi[5])
+
+
+# --------------------------------------------------------------------------------------------
+# Seeded O(1)-scale initialisation (SURVEY.md 8c caveat (i)): the reference's own init gives
+# |heatmap| ~ 1e-4 which would make a 1e-3 parity check vacuous.
+# --------------------------------------------------------------------------------------------
+
+
+def _key_seed(key, seed):
+    h = 1469598103934665603
+    for ch in key.encode():
+        h = ((h ^ ch) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return (h ^ (seed * 0x9E3779B97F4A7C15)) & 0x7FFFFFFFFFFFFFFF
+
+
+def seeded_state_dict(shapes, seed=19970808, dtype=torch.float32):
+    """shapes: {key: shape} with reference state_dict keys.  Deterministic per key (order
+    independent).  Conv/Linear/DCN weights: N(0, gain^2/fan_in); biases N(0,0.05^2);
+    BN gamma U(0.5,1.5), beta N(0,0.1^2), running_mean N(0,0.1^2), running_var U(0.5,1.5).
+    dcn_offset_* convs are scaled so raw offsets are ~N(0, 1.5 px) and dcn_mask_* ~N(0.5,0.5)."""
+    out = {}
+    for key, shape in shapes.items():
+        g = torch.Generator().manual_seed(_key_seed(key, seed))
+        shape = tuple(shape)
+        leaf = key.rsplit(".", 1)[-1]
+        if leaf == "num_batches_tracked":
+            out[key] = torch.zeros(shape, dtype=torch.long)
+        elif leaf == "running_var":
+            out[key] = (torch.rand(shape, generator=g) + 0.5).to(dtype)
+        elif leaf == "running_mean":
+            out[key] = (0.1 * torch.randn(shape, generator=g)).to(dtype)
+        elif leaf == "weight" and len(shape) == 1:
+            t = torch.rand(shape, generator=g) * 0.5 + 0.5
+            if _is_block_last_bn(key):
+                t = t * 0.4          # keep residual branches modest so 100+ stacked blocks stay O(1)
+            out[key] = t.to(dtype)
+        elif leaf == "bias":
+            t = 0.1 * torch.randn(shape, generator=g) if _is_bn_bias(key, shapes) else 0.05 * torch.randn(shape, generator=g)
+            if "dcn_mask_" in key:
+                t = t + 0.5
+            out[key] = t.to(dtype)
+        elif leaf == "weight":
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            gain = 1.0
+            if "dcn_offset_" in key:
+                gain = 1.5
+            elif "dcn_mask_" in key:
+                gain = 0.5
+            elif "feat_global_offset_layers.9" in key:
+                gain = 3.0
+            elif len(shape) == 2 or "final_layer" in key or key.startswith("dcn_"):
+                gain = 1.0
+            out[key] = (gain / math.sqrt(fan_in) * torch.randn(shape, generator=g)).to(dtype)
+        else:
+            raise KeyError(key)
+    return out
+
+
+def _is_block_last_bn(key):
+    """bn2 of a BasicBlock / bn3 of a Bottleneck / BN of a fuse or downsample path."""
+    mod = key.rsplit(".", 1)[0]
+    last = mod.rsplit(".", 1)[-1]
+    if "layer1." in key:
+        return last in ("bn3", "1") and "downsample" in key or last == "bn3"
+    return last == "bn2" or "fuse_layers" in key or "downsample" in key
+
+
+def _is_bn_bias(key, shapes):
+    return (key.rsplit(".", 1)[0] + ".running_mean") in shapes
+
+
+def synthetic_clip(B, H=384, W=288, num_sup=4, J=17, seed=19970808):
+    """SURVEY.md 8(d) synthetic inputs: N(0,1) frames; sigma=3 gaussian targets at random joint
+    centres (datasets/process/heatmaps_process.py:146-203); Bernoulli(0.85) target weights."""
+    g = torch.Generator().manual_seed(seed)
+    kf = torch.randn(B, 3, H, W, generator=g)
+    sup = torch.randn(B, 3 * num_sup, H, W, generator=g)
+    hh, ww = H // 4, W // 4
+    cx = torch.rand(B, J, generator=g) * (ww - 1)
+    cy = torch.rand(B, J, generator=g) * (hh - 1)
+    ys = torch.arange(hh).view(1, 1, hh, 1).float()
+    xs = torch.arange(ww).view(1, 1, 1, ww).float()
+    tgt = torch.exp(-((xs - cx.round().view(B, J, 1, 1)) ** 2 + (ys - cy.round().view(B, J, 1, 1)) ** 2) / (2 * 3.0 ** 2))
+    tw = (torch.rand(B, J, 1, generator=g) < 0.85).float()
+    return kf, sup, tgt, tw

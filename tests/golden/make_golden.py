@@ -1,0 +1,119 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference,
+build container only) and torchvision's CPU deform_conv2d on seeded inputs.
+
+    python tests/golden/make_golden.py
+
+The reference ships no golden vectors of its own; these files are the pins.
+Inputs/weights are not stored: they are regenerated from the seeds by oracle.fami_oracle
+(seeded_state_dict / synthetic_clip, CPU torch.Generator), only outputs are stored.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torchvision
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import fami_oracle as fo  # noqa: E402
+from oracle import ref_harness as rh  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+SEED = 19970808  # the reference's seed, tools/run.py:32-34
+
+
+def dcn_cases():
+    """(name, B, C, Cout, G, H, W, offset sigma) -- includes out-of-bounds offsets and G=1."""
+    return [("c48g12", 2, 48, 48, 12, 12, 9, 3.0), ("c32g8", 1, 32, 32, 8, 10, 7, 2.0),
+            ("c16g1_oob", 1, 16, 32, 1, 6, 5, 8.0), ("c64g16", 1, 64, 48, 16, 8, 8, 1.0)]
+
+
+def dcn_inputs(name, B, C, Cout, G, H, W, sig, dtype=torch.float32):
+    g = torch.Generator().manual_seed(SEED + sum(map(ord, name)))
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64).to(dtype)
+    off = (sig * torch.randn(B, 18 * G, H, W, generator=g, dtype=torch.float64)).to(dtype)
+    msk = torch.randn(B, 9 * G, H, W, generator=g, dtype=torch.float64).to(dtype)
+    w = (0.05 * torch.randn(Cout, C, 3, 3, generator=g, dtype=torch.float64)).to(dtype)
+    b = (0.1 * torch.randn(Cout, generator=g, dtype=torch.float64)).to(dtype)
+    go = torch.randn(B, Cout, H, W, generator=g, dtype=torch.float64).to(dtype)
+    return x, off, msk, w, b, go
+
+
+def make_dcn():
+    out = {}
+    for case in dcn_cases():
+        name = case[0]
+        for dt, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+            x, off, msk, w, b, go = dcn_inputs(*case, dtype=dt)
+            x.requires_grad_(True); off.requires_grad_(True); msk.requires_grad_(True)
+            w.requires_grad_(True); b.requires_grad_(True)
+            y = torchvision.ops.deform_conv2d(x, off, w, b, stride=1, padding=3, dilation=3, mask=msk)
+            y.backward(go)
+            out["%s_%s_out" % (name, tag)] = y.detach().numpy()
+            if tag == "f64":
+                for nm, t in (("gx", x), ("goff", off), ("gmask", msk), ("gw", w), ("gb", b)):
+                    out["%s_%s_%s" % (name, tag, nm)] = t.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "dcn_torchvision.npz"), **out)
+    print("dcn_torchvision.npz", len(out))
+
+
+def make_model():
+    ref = rh.load_reference()
+    out = {}
+    # config 2 shape at B=1: Alignment_V15 W48 384x288, 5 frames, 17 joints -- eval-mode BN
+    cfg = rh.make_cfg(48, 17)
+    m = ref.Alignment_V15(cfg, 'validate').eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = fo.seeded_state_dict(shapes, SEED)
+    m.load_state_dict(sd, strict=True)
+    kf, sup, tgt, tw = fo.synthetic_clip(1, seed=SEED)
+    with torch.no_grad():
+        hm, kfhm = m(kf, sup)
+    out["v15_eval_final_hm"] = hm.numpy()
+    out["v15_eval_kf_hm"] = kfhm.numpy()
+    out["v15_eval_final_argmax"] = hm.flatten(2).argmax(2).numpy().astype(np.int32)
+    out["v15_eval_kf_argmax"] = kfhm.flatten(2).argmax(2).numpy().astype(np.int32)
+    out["v15_eval_mse"] = np.float64(ref.JointMSELoss()(hm, tgt, tw).item())
+
+    # train-phase model (3-tuple incl. the six MI terms), BN in eval mode for determinism, B=2
+    mt = ref.Alignment_V15(cfg, 'train').eval()
+    mt.load_state_dict(sd, strict=True)
+    kf2, sup2, tgt2, tw2 = fo.synthetic_clip(2, seed=SEED + 1)
+    with torch.no_grad():
+        hm2, kfhm2, mi = mt(kf2, sup2)
+    out["v15_train_final_hm"] = hm2.numpy()
+    out["v15_train_mi"] = np.array([float(v) for v in mi], dtype=np.float64)
+    out["v15_train_mse"] = np.float64(ref.JointMSELoss()(hm2, tgt2, tw2).item())
+
+    # train-mode BatchNorm (batch statistics over the 5B frames), B=1
+    mb = ref.Alignment_V15(cfg, 'train').train()
+    mb.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        hm3, kfhm3, mi3 = mb(kf, sup)
+    out["v15_bntrain_final_hm"] = hm3.numpy()
+    out["v15_bntrain_kf_hm"] = kfhm3.numpy()
+    out["v15_bntrain_mi"] = np.array([float(v) for v in mi3], dtype=np.float64)
+    out["v15_bntrain_hrnet_bn1_running_mean"] = mb.state_dict()["hrnet.bn1.running_mean"].numpy()
+    out["v15_bntrain_hrnet_bn1_running_var"] = mb.state_dict()["hrnet.bn1.running_var"].numpy()
+
+    # config 1: HRNet-W32 256x192 single-frame forward, batch 1
+    cfg32 = rh.make_cfg(32, 17)
+    h = ref.HRNet(cfg32, False).eval()
+    shapes32 = {k: tuple(v.shape) for k, v in h.state_dict().items()}
+    sd32 = fo.seeded_state_dict(shapes32, SEED)
+    h.load_state_dict(sd32, strict=True)
+    g = torch.Generator().manual_seed(SEED)
+    x = torch.randn(1, 3, 256, 192, generator=g)
+    with torch.no_grad():
+        hm32, _ = h(x)
+    out["hrnet_w32_hm"] = hm32.numpy()
+    out["hrnet_w32_argmax"] = hm32.flatten(2).argmax(2).numpy().astype(np.int32)
+    np.savez_compressed(os.path.join(OUT, "model_reference.npz"), **out)
+    print("model_reference.npz", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    make_dcn()
+    make_model()

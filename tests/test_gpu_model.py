@@ -1,0 +1,164 @@
+"""Whole-model GPU parity: fami_pose_b200.Alignment_V15 / HRNet against (a) the committed goldens
+produced by the unmodified reference (tests/golden/make_golden.py) and (b) the CPU oracle run on
+the same seeded inputs.  fp32 tolerance from BASELINE.json north_star: 1e-3 max-abs on heatmaps,
+argmax indices identical wherever the reference's own top-1/top-2 margin exceeds that tolerance."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import fami_oracle as fo  # noqa: E402  (checker only)
+from oracle import ref_harness as rh  # noqa: E402  (cfg helper only; the reference itself is not on the GPU box)
+
+DEV = "cuda"
+SEED = 19970808
+TOL = 1e-3
+
+
+def _argmax_check(got, ref, tol=TOL):
+    """bit-exact argmax where the reference margin > tol; otherwise the chosen pixel must be a
+    near-tie (within tol of the reference maximum)."""
+    B, J = ref.shape[:2]
+    r = ref.reshape(B, J, -1)
+    g = got.reshape(B, J, -1)
+    ri, gi = r.argmax(2), g.argmax(2)
+    srt = np.sort(r, 2)
+    margin = srt[:, :, -1] - srt[:, :, -2]
+    strict = margin > tol
+    assert np.array_equal(ri[strict], gi[strict])
+    near = np.take_along_axis(r, gi[..., None], 2)[..., 0]
+    assert np.all(r.max(2) - near <= tol)
+    return int(strict.sum()), int(strict.size)
+
+
+def _build(phase, sd_cache={}):
+    import fami_pose_b200 as fp
+    fp.set_precision("fp32")
+    cfg = rh.make_cfg(48, 17)
+    m = fp.Alignment_V15(cfg, phase)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    if "sd" not in sd_cache:
+        sd_cache["sd"] = fo.seeded_state_dict(shapes, SEED)
+    m.load_state_dict(sd_cache["sd"], strict=True)
+    return m.to(DEV), sd_cache["sd"]
+
+
+def test_alignment_v15_eval_vs_reference_golden(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "model_reference.npz"))
+    m, sd = _build("validate")
+    m.eval()
+    kf, sup, tgt, tw = fo.synthetic_clip(1, seed=SEED)
+    with torch.no_grad():
+        hm, kfhm = m(kf.to(DEV), sup.to(DEV))
+    assert hm.shape == (1, 17, 96, 72) and hm.dtype == torch.float32 and hm.is_contiguous()
+    e1 = float(np.abs(hm.cpu().numpy() - gold["v15_eval_final_hm"]).max())
+    e2 = float(np.abs(kfhm.cpu().numpy() - gold["v15_eval_kf_hm"]).max())
+    print("max-abs err final %.3e kf %.3e" % (e1, e2))
+    assert e1 <= TOL and e2 <= TOL
+    _argmax_check(hm.cpu().numpy(), gold["v15_eval_final_hm"])
+    _argmax_check(kfhm.cpu().numpy(), gold["v15_eval_kf_hm"])
+    # device argmax agrees with numpy argmax of our own output (bit-exact index path)
+    import fami_pose_b200 as fp
+    idx = fp.argmax_indices(hm).cpu().numpy()
+    assert np.array_equal(idx, hm.cpu().numpy().reshape(1, 17, -1).argmax(2).astype(np.int32))
+    # loss
+    mse = float(fp.JointMSELoss()(hm, tgt.to(DEV), tw.to(DEV)))
+    assert abs(mse - float(gold["v15_eval_mse"])) <= 1e-4 * abs(float(gold["v15_eval_mse"])) + 1e-6
+
+
+def test_alignment_v15_train_phase_mi_vs_reference_golden(golden_dir):
+    """3-tuple output incl. six MI terms (BN in eval mode), B=2."""
+    import fami_pose_b200 as fp
+    gold = np.load(os.path.join(golden_dir, "model_reference.npz"))
+    m, sd = _build("train")
+    m.eval()
+    kf, sup, tgt, tw = fo.synthetic_clip(2, seed=SEED + 1)
+    with torch.no_grad():
+        hm, kfhm, mi = m(kf.to(DEV), sup.to(DEV))
+    assert len(mi) == 6
+    assert float(np.abs(hm.cpu().numpy() - gold["v15_train_final_hm"]).max()) <= TOL
+    got = np.array([float(v) for v in mi])
+    ref = gold["v15_train_mi"]
+    print("mi", got, ref)
+    assert np.all(np.abs(got - ref) <= 1e-6 + 1e-3 * np.abs(ref))
+    mse = float(fp.JointMSELoss()(hm, tgt.to(DEV), tw.to(DEV)))
+    assert abs(mse - float(gold["v15_train_mse"])) <= 1e-4 * abs(float(gold["v15_train_mse"])) + 1e-6
+    total = fp.combine_losses(torch.tensor(mse), [torch.tensor(v) for v in got])
+    assert abs(float(total) - float(fo.combine_losses(mse, list(ref)))) <= 1e-5
+
+
+def test_alignment_v15_batchnorm_train_mode_vs_reference_golden(golden_dir):
+    """train-mode BatchNorm (batch statistics over the 5B frames; running stats updated), B=1.
+    Batch-stat BN amplifies fp32 reordering noise less than 1e-3 here; tolerance 2e-3."""
+    gold = np.load(os.path.join(golden_dir, "model_reference.npz"))
+    m, sd = _build("train")
+    m.train()
+    kf, sup, tgt, tw = fo.synthetic_clip(1, seed=SEED)
+    with torch.no_grad():
+        hm, kfhm, mi = m(kf.to(DEV), sup.to(DEV))
+    e1 = float(np.abs(hm.cpu().numpy() - gold["v15_bntrain_final_hm"]).max())
+    e2 = float(np.abs(kfhm.cpu().numpy() - gold["v15_bntrain_kf_hm"]).max())
+    print("bn-train max-abs err final %.3e kf %.3e" % (e1, e2))
+    assert e1 <= 2e-3 and e2 <= 2e-3
+    rm = m.state_dict()["hrnet.bn1.running_mean"].cpu().numpy()
+    rv = m.state_dict()["hrnet.bn1.running_var"].cpu().numpy()
+    assert np.abs(rm - gold["v15_bntrain_hrnet_bn1_running_mean"]).max() <= 1e-5
+    assert np.abs(rv - gold["v15_bntrain_hrnet_bn1_running_var"]).max() <= 1e-5
+
+
+def test_hrnet_w32_config1_vs_reference_golden(golden_dir):
+    """BASELINE config 1: HRNet-W32 256x192 single-frame forward, batch 1."""
+    import fami_pose_b200 as fp
+    fp.set_precision("fp32")
+    gold = np.load(os.path.join(golden_dir, "model_reference.npz"))
+    cfg = rh.make_cfg(32, 17)
+    h = fp.HRNet(cfg, False)
+    shapes = {k: tuple(v.shape) for k, v in h.state_dict().items()}
+    h.load_state_dict(fo.seeded_state_dict(shapes, SEED), strict=True)
+    h = h.to(DEV).eval()
+    g = torch.Generator().manual_seed(SEED)
+    x = torch.randn(1, 3, 256, 192, generator=g)
+    with torch.no_grad():
+        hm, feats = h(x.to(DEV))
+    from fami_pose_b200 import ops
+    got = ops.to_nchw(hm).cpu().numpy()
+    e = float(np.abs(got - gold["hrnet_w32_hm"]).max())
+    print("hrnet w32 max-abs err %.3e" % e)
+    assert e <= TOL
+    _argmax_check(got, gold["hrnet_w32_hm"])
+    assert len(feats) == 4
+
+
+def test_alignment_v15_vs_oracle_other_seed_and_batch():
+    """CUDA path vs the CPU oracle on a different seed at B=2 (not a stored golden)."""
+    m, sd = _build("validate")
+    m.eval()
+    kf, sup, _, _ = fo.synthetic_clip(2, seed=4242)
+    with torch.no_grad():
+        hm, kfhm = m(kf.to(DEV), sup.to(DEV))
+        rhm, rkf = fo.FunctionalFami(sd).alignment(kf, sup)
+    assert float((hm.cpu() - rhm).abs().max()) <= TOL
+    assert float((kfhm.cpu() - rkf).abs().max()) <= TOL
+
+
+def test_full_size_properties_config2():
+    """Size-independent properties at BASELINE config 2's full size (B=32, 160 HRNet images), where the
+    CPU oracle would take minutes: (i) clips are independent -> the first clips of a B=32 batch equal
+    the same clips run at B=2 (bit-exact: same kernels, same per-pixel arithmetic); (ii) outputs finite;
+    (iii) device argmax == numpy argmax of the output."""
+    import fami_pose_b200 as fp
+    m, sd = _build("validate")
+    m.eval()
+    kf, sup, _, _ = fo.synthetic_clip(32, seed=99)
+    kf, sup = kf.to(DEV), sup.to(DEV)
+    with torch.no_grad():
+        hm, kfhm = m(kf, sup)
+        hm2, kfhm2 = m(kf[:2].contiguous(), sup[:2].contiguous())
+    assert torch.isfinite(hm).all() and torch.isfinite(kfhm).all()
+    assert float((hm[:2] - hm2).abs().max()) <= 1e-6
+    assert float((kfhm[:2] - kfhm2).abs().max()) <= 1e-6
+    idx = fp.argmax_indices(hm).cpu().numpy()
+    assert np.array_equal(idx, hm.cpu().numpy().reshape(32, 17, -1).argmax(2).astype(np.int32))

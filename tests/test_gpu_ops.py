@@ -1,0 +1,301 @@
+"""GPU parity of each C-ABI op against the CPU oracle (oracle/fami_oracle.py) and the committed
+torchvision/reference goldens.  Tolerances are stated per test; index results are bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import fami_oracle as fo  # noqa: E402  (checker only)
+
+DEV = "cuda"
+
+
+def fp():
+    import fami_pose_b200 as m
+    m.set_precision("fp32")
+    return m
+
+
+def nhwc(t):
+    """NCHW cpu tensor -> channels-last activation on the GPU via the library's own converter."""
+    from fami_pose_b200 import ops
+    return ops.to_nhwc(t.to(DEV).float().contiguous(), torch.float32)
+
+
+def back(t):
+    from fami_pose_b200 import ops
+    return ops.to_nchw(t).cpu()
+
+
+def test_layout_roundtrip():
+    fp()
+    g = torch.Generator().manual_seed(1)
+    for shape in [(2, 3, 17, 13), (1, 48, 9, 7), (3, 17, 5, 4), (1, 1, 4, 4)]:
+        x = torch.randn(*shape, generator=g)
+        y = back(nhwc(x))
+        assert torch.equal(x, y), shape
+
+
+CONV_CASES = [
+    # Cin, Cout, k, stride, pad, dil, H, W, bias, bn, relu, res, up
+    (3, 64, 3, 2, 1, 1, 20, 14, False, True, True, False, 1),     # stem (scalar gather path)
+    (64, 64, 3, 2, 1, 1, 19, 13, False, True, True, False, 1),
+    (64, 256, 1, 1, 0, 1, 9, 7, False, True, False, True, 1),     # bottleneck conv3 + residual
+    (48, 48, 3, 1, 1, 1, 24, 18, False, True, True, True, 1),     # BasicBlock conv2
+    (96, 48, 1, 1, 0, 1, 6, 5, False, True, True, True, 2),       # fuse up x2
+    (384, 48, 1, 1, 0, 1, 3, 3, False, True, False, True, 8),     # fuse up x8
+    (48, 96, 3, 2, 1, 1, 24, 18, False, True, False, True, 1),    # fuse down + running sum
+    (48, 324, 3, 1, 3, 3, 12, 9, True, False, False, False, 1),   # offset|mask conv, dilation 3
+    (48, 17, 3, 1, 1, 1, 12, 9, True, False, False, False, 1),    # agg_final_layer (Cout=17 scalar store)
+    (48, 17, 1, 1, 0, 1, 12, 9, True, False, False, False, 1),    # hrnet.final_layer
+    (16, 16, 3, 2, 1, 1, 6, 5, True, True, True, False, 1),       # conv_bn_relu with bias + BN
+    (192, 192, 3, 1, 1, 1, 6, 5, False, True, True, True, 1),
+    (384, 384, 3, 1, 1, 1, 5, 4, False, True, True, True, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_bn_act_eval(case):
+    """fami_conv2d_bn_act_fwd vs torch CPU fp32 conv2d -> batch_norm(eval) -> +res -> relu -> nearest up.
+    Tolerance 2e-5 * max|ref| + 1e-5 (fp32, differing summation order only)."""
+    m = fp()
+    from fami_pose_b200 import ops
+    Cin, Cout, k, s, p, d, H, W, bias, bn, relu, res, up = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    N = 3
+    x = torch.randn(N, Cin, H, W, generator=g)
+    conv = torch.nn.Conv2d(Cin, Cout, k, s, p, d, bias=bias)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (Cin * k * k) ** 0.5)
+        if bias:
+            conv.bias.copy_(torch.randn(Cout, generator=g))
+    bnm = None
+    if bn:
+        bnm = torch.nn.BatchNorm2d(Cout).eval()
+        with torch.no_grad():
+            bnm.weight.copy_(torch.rand(Cout, generator=g) + 0.5)
+            bnm.bias.copy_(torch.randn(Cout, generator=g) * 0.2)
+            bnm.running_mean.copy_(torch.randn(Cout, generator=g) * 0.2)
+            bnm.running_var.copy_(torch.rand(Cout, generator=g) + 0.5)
+    with torch.no_grad():
+        y = conv(x)
+        if bn:
+            y = bnm(y)
+        if up > 1:
+            y = F.interpolate(y, scale_factor=up, mode="nearest")
+        r = torch.randn(y.shape, generator=g) if res else None
+        if res:
+            y = y + r
+        if relu:
+            y = F.relu(y)
+    conv_d = conv.to(DEV)
+    bn_d = bnm.to(DEV) if bn else None
+    out = ops.conv_bn_act(nhwc(x), conv_d, bn_d, relu=relu, residual=nhwc(r) if res else None, up=up)
+    got = back(out)
+    tol = 2e-5 * float(y.abs().max()) + 1e-5
+    assert float((got - y).abs().max()) <= tol
+
+
+def test_conv_bn_train_mode():
+    """train-mode BatchNorm (batch statistics + running-stat update) vs torch; tol 1e-4."""
+    fp()
+    from fami_pose_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(4, 48, 12, 9, generator=g)
+    conv = torch.nn.Conv2d(48, 96, 3, 2, 1, bias=False)
+    bn = torch.nn.BatchNorm2d(96, momentum=0.1).train()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(96, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(96, generator=g) * 0.1)
+    import copy
+    conv_d, bn_d = copy.deepcopy(conv).to(DEV), copy.deepcopy(bn).to(DEV)
+    with torch.no_grad():
+        y = F.relu(bn(conv(x)))
+    out = back(ops.conv_bn_act(nhwc(x), conv_d, bn_d, relu=True))
+    assert float((out - y).abs().max()) <= 1e-4
+    assert float((bn_d.running_mean.cpu() - bn.running_mean).abs().max()) <= 1e-5
+    assert float((bn_d.running_var.cpu() - bn.running_var).abs().max()) <= 1e-5
+    assert int(bn_d.num_batches_tracked) == 1
+
+
+
+
+def _golden_inputs(name):
+    # same generator recipe as tests/golden/make_golden.py::dcn_inputs (kept in sync by test_oracle.py)
+    from tests_support import dcn_cases, dcn_inputs
+    for case in dcn_cases():
+        if case[0] == name:
+            return case, dcn_inputs(*case)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["c48g12", "c32g8", "c16g1_oob", "c64g16"])
+def test_dcn_fwd_vs_torchvision_golden(name, golden_dir):
+    """fami_dcn_fwd vs torchvision CPU deform_conv2d (committed golden, fp64 reference values);
+    tolerance 1e-5 abs."""
+    fp()
+    from fami_pose_b200 import layers
+    gold = np.load(os.path.join(golden_dir, "dcn_torchvision.npz"))
+    case, (x, off, msk, w, b, go) = _golden_inputs(name)
+    _, B, C, Cout, G, H, W, sig = case
+    mod = layers.DeformConv2d(C, Cout, 3, padding=3, dilation=3).to(DEV)
+    with torch.no_grad():
+        mod.weight.copy_(w.to(DEV))
+        mod.bias.copy_(b.to(DEV))
+    out = back(mod(nhwc(x), nhwc(off), nhwc(msk)))
+    ref = torch.from_numpy(gold["%s_f64_out" % name]).float()
+    assert float((out - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+
+
+def test_dcn_fwd_vs_oracle_larger():
+    """config-2 DCN shape at B=2 vs the numpy oracle; tol 2e-5."""
+    fp()
+    from fami_pose_b200 import layers
+    g = torch.Generator().manual_seed(3)
+    B, C, G, H, W = 2, 48, 12, 96, 72
+    x = torch.randn(B, C, H, W, generator=g)
+    off = 2.0 * torch.randn(B, 18 * G, H, W, generator=g)
+    msk = torch.randn(B, 9 * G, H, W, generator=g)
+    w = 0.05 * torch.randn(C, C, 3, 3, generator=g)
+    b = 0.1 * torch.randn(C, generator=g)
+    ref = torch.from_numpy(fo.dcn_fwd(x.numpy(), off.numpy(), msk.numpy(), w.numpy(), b.numpy()))
+    mod = layers.DeformConv2d(C, C, 3, padding=3, dilation=3).to(DEV)
+    with torch.no_grad():
+        mod.weight.copy_(w.to(DEV))
+        mod.bias.copy_(b.to(DEV))
+    out = back(mod(nhwc(x), nhwc(off), nhwc(msk)))
+    assert float((out - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+def test_dcn_zero_offset_equals_dilated_conv():
+    """Property (size independent): zero offsets + unit mask == ordinary dilated convolution."""
+    fp()
+    from fami_pose_b200 import layers, ops
+    g = torch.Generator().manual_seed(5)
+    B, C, G, H, W = 4, 48, 12, 96, 72
+    x = torch.randn(B, C, H, W, generator=g)
+    mod = layers.DeformConv2d(C, C, 3, padding=3, dilation=3).to(DEV)
+    conv = torch.nn.Conv2d(C, C, 3, 1, 3, 3).to(DEV)
+    with torch.no_grad():
+        conv.weight.copy_(mod.weight)
+        conv.bias.copy_(mod.bias)
+    xd = nhwc(x)
+    off = ops.empty_nhwc(B, 18 * G, H, W, torch.float32, DEV).zero_()
+    msk = ops.empty_nhwc(B, 9 * G, H, W, torch.float32, DEV).fill_(1.0)
+    a = back(mod(xd, off, msk))
+    b = back(ops.conv_bn_act(xd, conv, None))
+    assert float((a - b).abs().max()) <= 1e-5
+
+
+def test_dcn_bad_offset_channels_raises():
+    fp()
+    from fami_pose_b200 import layers, ops
+    mod = layers.DeformConv2d(48, 48, 3, padding=3, dilation=3).to(DEV)
+    x = ops.empty_nhwc(1, 48, 8, 8, torch.float32, DEV).zero_()
+    off = ops.empty_nhwc(1, 20, 8, 8, torch.float32, DEV).zero_()
+    msk = ops.empty_nhwc(1, 9, 8, 8, torch.float32, DEV).zero_()
+    with pytest.raises(RuntimeError):
+        mod(x, off, msk)
+
+
+def test_warp_translate_vs_kornia_restatement():
+    """fami_warp_translate_fwd vs the kornia>=0.6 warp_affine restatement; tol 1e-5 (incl. shifts
+    that push the whole image out of view)."""
+    fp()
+    from fami_pose_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    B, C, H, W = 5, 48, 24, 18
+    src = torch.randn(B, C, H, W, generator=g)
+    txy = torch.tensor([[0.0, 0.0], [1.25, -2.5], [-3.75, 0.5], [40.0, 3.0], [0.999, 17.2]])
+    M = torch.eye(3)[0:2].view(1, 2, 3).repeat(B, 1, 1)
+    M[:, 0, 2], M[:, 1, 2] = txy[:, 0], txy[:, 1]
+    ref = fo.warp_affine_kornia(src, M, (H, W))
+    out = back(ops.warp_translate(nhwc(src), txy.to(DEV)))
+    assert float((out - ref).abs().max()) <= 1e-5
+    ref2 = torch.from_numpy(fo.warp_translate(src.numpy(), txy.numpy()))
+    assert float((out - ref2).abs().max()) <= 1e-5
+
+
+def test_sub_copy_linear():
+    fp()
+    from fami_pose_b200 import ops
+    g = torch.Generator().manual_seed(13)
+    a = torch.randn(6, 16, 5, 4, generator=g)
+    b = torch.randn(2, 16, 5, 4, generator=g)
+    out = back(ops.sub_bcast(nhwc(a), nhwc(b), 3))
+    assert torch.equal(out, a - b.repeat(3, 1, 1, 1))
+    dst = ops.empty_nhwc(2, 32, 5, 4, torch.float32, DEV).zero_()
+    ops.copy_into(nhwc(b), dst[:, 16:])
+    full = back(dst)
+    assert torch.equal(full[:, 16:], b) and float(full[:, :16].abs().max()) == 0.0
+    x = torch.randn(8, 144, generator=g)
+    w = torch.randn(64, 144, generator=g) / 12
+    bias = torch.randn(64, generator=g)
+    y = ops.linear(x.to(DEV), w.to(DEV), bias.to(DEV)).cpu()
+    assert float((y - F.linear(x, w, bias)).abs().max()) <= 1e-5
+
+
+def test_joint_mse_vs_oracle():
+    """fami_joint_mse_fwd_bwd vs oracle.joint_mse (float64) rel 1e-5, and vs autograd for the gradient."""
+    fp()
+    from fami_pose_b200 import ops
+    g = torch.Generator().manual_seed(17)
+    B, J, H, W = 3, 17, 24, 18
+    pred = torch.randn(B, J, H, W, generator=g)
+    tgt = torch.rand(B, J, H, W, generator=g)
+    tw = (torch.rand(B, J, 1, generator=g) < 0.85).float()
+    ref = fo.joint_mse(pred.numpy(), tgt.numpy(), tw.numpy())
+    loss, grad = ops.joint_mse(pred.to(DEV), tgt.to(DEV), tw.to(DEV), want_grad=True)
+    assert abs(float(loss) - ref) <= 1e-5 * abs(ref)
+    p = pred.clone().requires_grad_(True)
+    l2 = (((p - tgt) * tw.view(B, J, 1, 1)) ** 2).mean(dim=(0, 2, 3)).sum() / J
+    l2.backward()
+    assert float((grad.permute(0, 3, 1, 2).cpu() - p.grad).abs().max()) <= 1e-8 + 1e-5 * float(p.grad.abs().max())
+
+
+def test_softmax_pkl_vs_oracle_and_torch():
+    """fami_softmax_pkl_fwd vs oracle.softmax_pkl (float64) and torch's own F.kl_div call as the
+    reference makes it (Alignment_V15.py:260,275); tol 1e-6 abs + 1e-4 rel."""
+    fp()
+    from fami_pose_b200 import ops
+    g = torch.Generator().manual_seed(19)
+    for C in (17, 48):
+        B, H, W = 2, 96, 72
+        a = torch.randn(B, C, H, W, generator=g) * 0.3
+        b = torch.randn(B, C, H, W, generator=g) * 0.3
+        ref = fo.softmax_pkl(a.reshape(B * C, -1).numpy(), b.reshape(B * C, -1).numpy(), 0.05)
+        tref = F.kl_div(input=F.softmax(a.reshape(B * C, -1) / 0.05, dim=1),
+                        target=F.softmax(b.reshape(B * C, -1) / 0.05, dim=1), reduction="mean")
+        got = float(ops.softmax_pkl(nhwc(a), nhwc(b), 0.05))
+        assert abs(ref - float(tref)) <= 1e-6 + 1e-4 * abs(ref)
+        assert abs(got - ref) <= 1e-6 + 1e-4 * abs(ref)
+
+
+def test_argmax_bit_exact_with_ties():
+    """fami_argmax_hw == numpy argmax (first maximum wins), including planted ties."""
+    fp()
+    import fami_pose_b200 as m
+    g = torch.Generator().manual_seed(23)
+    B, J, H, W = 4, 17, 96, 72
+    hm = torch.randn(B, J, H, W, generator=g)
+    hm[0, 0].fill_(0.0)                      # all equal -> index 0
+    hm[1, 3, 10, 5] = 9.0
+    hm[1, 3, 50, 60] = 9.0                   # tie -> lower flat index
+    hm[2, 5] = -hm[2, 5].abs() - 1.0         # all negative -> coords masked to 0
+    preds_ref, maxv_ref, idx_ref = fo.get_max_preds(hm.numpy())
+    idx = m.argmax_indices(hm.to(DEV)).cpu().numpy()
+    assert np.array_equal(idx, idx_ref.astype(np.int32))
+    preds, maxv = m.get_max_preds(hm.to(DEV))
+    assert np.array_equal(preds.cpu().numpy(), preds_ref)
+    assert np.array_equal(maxv.cpu().numpy(), maxv_ref)
+
+
+def test_cpu_tensors_fail_loudly():
+    fp()
+    from fami_pose_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.to_nhwc(torch.zeros(1, 3, 4, 4))
