@@ -18,7 +18,7 @@ BF16 = 1
 class ConvDesc(Structure):
     _fields_ = [(n, c_int32) for n in (
         "N", "H", "W", "Cin", "Cout", "kh", "kw", "stride", "pad", "dil", "Ho", "Wo", "up", "relu",
-        "in_pitch", "out_pitch", "res_pitch", "dtype", "stats")]
+        "in_pitch", "out_pitch", "res_pitch", "dtype", "out_dtype", "stats")]
 
 
 class DcnDesc(Structure):

@@ -123,6 +123,8 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
   FAMI_CHECK_ARG(!residual || d->res_pitch >= d->Cout, "fami_conv2d_bn_act_fwd: res_pitch < Cout");
   FAMI_CHECK_ARG(!d->stats || stats_out, "fami_conv2d_bn_act_fwd: stats requested without stats_out");
   FAMI_CHECK_ARG((int64_t)d->N * d->Ho * d->Wo < (1ll << 31), "fami_conv2d_bn_act_fwd: too many output pixels");
+  FAMI_CHECK_ARG(d->out_dtype == d->dtype || (d->dtype == FAMI_BF16 && d->out_dtype == FAMI_F32),
+                 "fami_conv2d_bn_act_fwd: unsupported (dtype, out_dtype) = (%d, %d)", d->dtype, d->out_dtype);
   if (d->dtype == FAMI_BF16) {
     FAMI_CHECK_ARG(conv_bf16_tc_supported(d), "fami_conv2d_bn_act_fwd: shape not supported by the bf16 tensor path");
     return conv_bf16_tc_launch(d, x, w_packed, scale, shift, residual, y, stats_out, (cudaStream_t)stream);

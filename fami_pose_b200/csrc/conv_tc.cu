@@ -1,19 +1,473 @@
-// bf16 tcgen05 implicit-GEMM convolution (tensor-core arm of fami_conv2d_bn_act_fwd).
-// Placeholder until the UMMA/TMA kernel lands: reports "unsupported" so callers get a loud error.
+// bf16 implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), fed by TMA.
+// Tensor-core arm of fami_conv2d_bn_act_fwd (reference chains: basic_model.py:44-63,83-113;
+// basic_layer.py:55-73; hrnet.py:89-172,651-680).
+//
+// GEMM view: D[M=128 pixels][N=BN couts] += A[128][64 ch] * B[BN][64 ch]^T per (tap, 64-channel chunk).
+//   A: TMA *im2col* load straight from the NHWC bf16 activation: 128 consecutive output pixels
+//      (linearised n,yo,xo), 64 channels of filter tap (r,s); the padding halo and the channel tail
+//      (Cin % 64) are zero-filled by the TMA unit; stride-2 convs use the traversal stride.
+//   B: TMA tiled load from weights pre-packed [CoutPad][taps*chunks*64] (K-major, zero padded).
+//   Both land in 128-byte-swizzled K-major shared-memory tiles that tcgen05.mma reads through
+//   shared-memory descriptors; the fp32 accumulator lives in TMEM (double buffered, 2 x 256 cols).
+// Warp roles (192 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = TMEM owner +
+// single-thread MMA issuer, warps 2-5 = epilogue (tcgen05.ld -> scale/shift (+residual) (+ReLU) ->
+// bf16/fp32 NHWC stores with optional nearest-upsample replication).
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace fami {
 
-int conv_bf16_tc_supported(const fami_conv_desc*) { return 0; }
-int conv_bf16_tc_launch(const fami_conv_desc*, const void*, const void*, const float*, const float*, const void*,
-                        void*, double*, cudaStream_t) {
-  set_error("bf16 tensor-core convolution not built");
-  return 3;
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kKC = 64;                 // channels per K chunk (128 B of bf16 = one swizzle row)
+constexpr int kABytes = kBM * kKC * 2;  // 16 KB
+constexpr int kThreads = 192;
+constexpr int kAccCols = 256;           // TMEM columns per accumulator buffer
+
+struct TcParams {
+  int M, Ho, Wo, HoWo;
+  int stride, pad, dil, kw, taps;
+  int cchunks, last_kk;
+  int Cout, BN, n_tiles, m_tiles;
+  int up, relu;
+  int out_pitch, res_pitch;
+  int out_f32, vec_ok;
+  int stages;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* res;
+  void* y;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-int64_t pack_w_bf16_elems(int, int, int, int) { return 0; }
-int pack_w_bf16_launch(const float*, void*, int, int, int, int, cudaStream_t) {
-  set_error("bf16 tensor-core convolution not built");
-  return 3;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_im2col_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w, int h,
+                                              int n, uint16_t offw, uint16_t offh) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(offw), "h"(offh)
+      : "memory");
+}
+__device__ __forceinline__ void tma_tiled_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row swizzle atoms 1024 B apart.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address  [0,14)
+  d |= (uint64_t)1 << 16;                    // LBO (unused for swizzled K-major) [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;          // SBO = 1024 B [32,46)
+  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stages = p.stages;
+  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  const uint32_t bar0 = smem_u32(bars);
+  // barrier i at bar0 + 8*i: full[0..S), empty[S..2S), tfull[2S..2S+2), tempty[2S+2..2S+4)
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (stages + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * stages + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * stages + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int ksteps = p.taps * p.cchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        const int m0 = mt * kBM;
+        const int n = m0 / p.HoWo, r = m0 - n * p.HoWo;
+        const int yo = r / p.Wo, xo = r - yo * p.Wo;
+        const int cw = xo * p.stride - p.pad, ch = yo * p.stride - p.pad;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int fr = tap / p.kw, fs = tap - fr * p.kw;
+          for (int cc = 0; cc < p.cchunks; ++cc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+            const uint32_t a_dst = smem_u32(smem + (size_t)stage * stage_bytes);
+            tma_im2col_4d(a_dst, &tmA, full_bar(stage), cc * kKC, cw, ch, n, (uint16_t)(fs * p.dil),
+                          (uint16_t)(fr * p.dil));
+            tma_tiled_2d(a_dst + kABytes, &tmB, full_bar(stage), (tap * p.cchunks + cc) * kKC, nt * p.BN);
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t adesc = make_sw128_desc(a_addr);
+          const uint64_t bdesc = make_sw128_desc(a_addr + kABytes);
+          const int cc = ks % p.cchunks;
+          const int nk = (cc == p.cchunks - 1) ? p.last_kk : 4;
+          for (int k = 0; k < nk; ++k) {
+            // advance 16 bf16 (32 B) along K inside the swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));   // frees the smem slot once the MMAs above have read it
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));       // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    int it = 0;
+    const int Hout = p.Ho * p.up, Wout = p.Wo * p.up;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int m = mt * kBM + row;
+      const bool valid = m < p.M;
+      int64_t pix0 = 0;
+      if (valid) {
+        if (p.up == 1) {
+          pix0 = m;
+        } else {
+          const int n = m / p.HoWo, r = m - n * p.HoWo;
+          const int yo = r / p.Wo, xo = r - yo * p.Wo;
+          pix0 = ((int64_t)n * Hout + (int64_t)yo * p.up) * Wout + (int64_t)xo * p.up;
+        }
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)(quarter * 32) << 16);
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_addr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        const int ch0 = nt * p.BN + c0;
+        if (!valid || ch0 >= p.Cout) continue;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int c = ch0 + j;
+          const float sc = (p.scale && c < p.Cout) ? __ldg(p.scale + c) : 1.f;
+          const float sh = (p.shift && c < p.Cout) ? __ldg(p.shift + c) : 0.f;
+          f[j] = fmaf(__uint_as_float(v[j]), sc, sh);
+        }
+        const bool full16 = (ch0 + 16 <= p.Cout) && p.vec_ok;
+        for (int dy = 0; dy < p.up; ++dy)
+          for (int dx = 0; dx < p.up; ++dx) {
+            const int64_t pix = pix0 + (int64_t)dy * Wout + dx;
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = f[j];
+            if (p.res) {
+              const __nv_bfloat16* rp = p.res + pix * p.res_pitch + ch0;
+              if (full16) {
+                const uint4 r0 = *reinterpret_cast<const uint4*>(rp);
+                const uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
+                const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[j]));
+                  o[2 * j] += t.x;
+                  o[2 * j + 1] += t.y;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (ch0 + j < p.Cout) o[j] += __bfloat162float(rp[j]);
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+            }
+            if (p.out_f32) {
+              float* yp = reinterpret_cast<float*>(p.y) + pix * p.out_pitch + ch0;
+              if (full16) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  *reinterpret_cast<float4*>(yp + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (ch0 + j < p.Cout) yp[j] = o[j];
+              }
+            } else {
+              __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.out_pitch + ch0;
+              if (full16) {
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  __nv_bfloat162 t = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+                  w[j] = *reinterpret_cast<uint32_t*>(&t);
+                }
+                *reinterpret_cast<uint4*>(yp) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(yp + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (ch0 + j < p.Cout) yp[j] = __float2bfloat16_rn(o[j]);
+              }
+            }
+          }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeIm2colFn g_encode_im2col = nullptr;
+EncodeTiledFn g_encode_tiled = nullptr;
+
+bool load_driver_fns() {
+  if (g_encode_im2col && g_encode_tiled) return true;
+  void* f1 = nullptr;
+  void* f2 = nullptr;
+  cudaDriverEntryPointQueryResult q1, q2;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f1, cudaEnableDefault, &q1) != cudaSuccess ||
+      q1 != cudaDriverEntryPointSuccess)
+    return false;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f2, cudaEnableDefault, &q2) != cudaSuccess ||
+      q2 != cudaDriverEntryPointSuccess)
+    return false;
+  g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(f1);
+  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(f2);
+  return true;
+}
+
+struct TileCfg {
+  int BN, n_tiles, CoutPad, cchunks, Kp;
+};
+
+TileCfg tile_cfg(int Cout, int Cin, int kh, int kw) {
+  TileCfg t;
+  t.n_tiles = (Cout + 255) / 256;
+  int per = (Cout + t.n_tiles - 1) / t.n_tiles;
+  t.BN = ((per + 15) / 16) * 16;
+  t.CoutPad = t.BN * t.n_tiles;
+  t.cchunks = (Cin + kKC - 1) / kKC;
+  t.Kp = kh * kw * t.cchunks * kKC;
+  return t;
+}
+
+}  // namespace
+
+int conv_bf16_tc_supported(const fami_conv_desc* d) {
+  if (d->Cin % 16 != 0 || d->in_pitch % 8 != 0) return 0;
+  if (d->kh != d->kw || (d->kh != 1 && d->kh != 3)) return 0;
+  if (d->stride < 1 || d->stride > 8) return 0;
+  if (d->pad > 127 || (d->kh - 1) * d->dil - d->pad > 128) return 0;
+  return 1;
+}
+
+int64_t pack_w_bf16_elems(int Cout, int Cin, int kh, int kw) {
+  TileCfg t = tile_cfg(Cout, Cin, kh, kw);
+  return (int64_t)t.CoutPad * t.Kp;
+}
+
+// OIHW float -> [CoutPad][taps][cchunks*64] bf16, zero padded
+__global__ void pack_w_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin,
+                                   int taps, int cchunks, int CoutPad) {
+  const int Kp = taps * cchunks * kKC;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)CoutPad * Kp) return;
+  int o = (int)(i / Kp), k = (int)(i - (int64_t)o * Kp);
+  int tap = k / (cchunks * kKC), c = k - tap * cchunks * kKC;
+  float v = 0.f;
+  if (o < Cout && c < Cin) v = w[((int64_t)o * Cin + c) * taps + tap];
+  out[i] = __float2bfloat16_rn(v);
+}
+
+int pack_w_bf16_launch(const float* w, void* out, int Cout, int Cin, int kh, int kw, cudaStream_t st) {
+  TileCfg t = tile_cfg(Cout, Cin, kh, kw);
+  int64_t tot = (int64_t)t.CoutPad * t.Kp;
+  pack_w_bf16_kernel<<<cdiv(tot, 256), 256, 0, st>>>(w, (__nv_bfloat16*)out, Cout, Cin, kh * kw, t.cchunks, t.CoutPad);
+  FAMI_CHECK_LAUNCH("pack_w_bf16_kernel");
+  return 0;
+}
+
+// x, residual: bf16 NHWC; y: bf16 or fp32 (d->out_dtype)
+int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
+                        const void* res, void* y, double* stats, cudaStream_t st) {
+  (void)stats;
+  FAMI_CHECK_ARG(!d->stats, "bf16 tensor-core conv: fused BN statistics are not supported (use fami_bn_stats)");
+  FAMI_CHECK_ARG(load_driver_fns(), "cuTensorMapEncode* driver entry points unavailable");
+  FAMI_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+                 "bf16 tensor-core conv: x / w must be 16-byte aligned");
+  const int out_f32 = d->out_dtype == FAMI_F32;
+  TileCfg t = tile_cfg(d->Cout, d->Cin, d->kh, d->kw);
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_pitch * 2, (cuuint64_t)d->W * d->in_pitch * 2,
+                             (cuuint64_t)d->H * d->W * d->in_pitch * 2};
+    int lower[2] = {-d->pad, -d->pad};
+    int upper[2] = {d->pad - (d->kw - 1) * d->dil, d->pad - (d->kh - 1) * d->dil};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    CUresult r = g_encode_im2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower,
+                                 upper, kKC, kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FAMI_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed (%d)", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)t.Kp, (cuuint64_t)t.CoutPad};
+    cuuint64_t strides[1] = {(cuuint64_t)t.Kp * 2};
+    cuuint32_t box[2] = {kKC, (cuuint32_t)t.BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FAMI_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  }
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = d->N * d->Ho * d->Wo;
+  p.Ho = d->Ho; p.Wo = d->Wo; p.HoWo = d->Ho * d->Wo;
+  p.stride = d->stride; p.pad = d->pad; p.dil = d->dil; p.kw = d->kw; p.taps = d->kh * d->kw;
+  p.cchunks = t.cchunks;
+  p.last_kk = (d->Cin - (t.cchunks - 1) * kKC) / 16;
+  p.Cout = d->Cout; p.BN = t.BN; p.n_tiles = t.n_tiles; p.m_tiles = (p.M + kBM - 1) / kBM;
+  p.up = d->up; p.relu = d->relu;
+  p.out_pitch = d->out_pitch; p.res_pitch = d->res_pitch;
+  p.out_f32 = out_f32;
+  const size_t osz = out_f32 ? 4 : 2;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((d->out_pitch * osz) % 16 == 0) &&
+             (!res || (((reinterpret_cast<uintptr_t>(res) & 15) == 0) && (d->res_pitch % 8 == 0)));
+  p.scale = scale; p.shift = shift; p.res = (const __nv_bfloat16*)res; p.y = y;
+
+  const int stage_bytes = kABytes + t.BN * 128;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 4) * 8 + 16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_done = true;
+  }
+  int grid = p.m_tiles * p.n_tiles;
+  const int sms = num_sms();
+  if (grid > sms) grid = sms;
+  conv_tc_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  FAMI_CHECK_LAUNCH("conv_tc_kernel");
+  return 0;
 }
 
 }  // namespace fami

@@ -186,14 +186,15 @@ def folded_affine(conv_bias, bn):
 # convolution (+BN +residual +ReLU +upsample-on-write)
 # ------------------------------------------------------------------------------------------------
 
-def _conv_raw(x, w_packed, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, out, stats):
+def _conv_raw(x, w_packed, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, out, stats, out_dtype=None):
     N, Cin, H, W, ip = meta(x)
     Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
     Wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    out_dtype = out_dtype or (out.dtype if out is not None else x.dtype)
     if out is None:
-        out = empty_nhwc(N, Cout, Ho * up, Wo * up, x.dtype, x.device)
+        out = empty_nhwc(N, Cout, Ho * up, Wo * up, out_dtype, x.device)
     oN, oC, oH, oW, op = meta(out)
-    if (oN, oC, oH, oW) != (N, Cout, Ho * up, Wo * up) or out.dtype != x.dtype:
+    if (oN, oC, oH, oW) != (N, Cout, Ho * up, Wo * up) or out.dtype != out_dtype:
         raise ValueError("conv output buffer has shape %s, expected %s" % (tuple(out.shape), (N, Cout, Ho * up, Wo * up)))
     rp = 0
     if residual is not None:
@@ -202,13 +203,13 @@ def _conv_raw(x, w_packed, Cout, k, stride, pad, dil, scale, shift, residual, re
             raise ValueError("residual shape %s does not match conv output %s"
                              % (tuple(residual.shape), (N, Cout, Ho * up, Wo * up)))
     d = ConvDesc(N, H, W, Cin, Cout, k, k, stride, pad, dil, Ho, Wo, up, int(bool(relu)), ip, op, rp,
-                 _code(x.dtype), int(stats is not None))
+                 _code(x.dtype), _code(out_dtype), int(stats is not None))
     _lib.call("fami_conv2d_bn_act_fwd", ctypes.byref(d), _ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift),
               _ptr(residual), _ptr(out), _ptr(stats), _stream())
     return out
 
 
-def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None):
+def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None, out_dtype=None):
     """conv -> [BatchNorm] -> [+residual] -> [ReLU] -> [nearest x`up`] in one launch (eval-mode BN)
     or conv(+stats) -> finalize -> apply (train-mode BN, batch statistics).
 
@@ -245,7 +246,7 @@ def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None):
                   _code(x.dtype), N, Ho, Wo, Cout, up, int(bool(relu)), _stream())
         return out
     scale, shift = folded_affine(conv.bias, bn)
-    return _conv_raw(x, w, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, out, None)
+    return _conv_raw(x, w, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, out, None, out_dtype)
 
 
 def upsample_nearest(x, factor):

@@ -67,7 +67,9 @@ typedef struct fami_conv_desc {
   int32_t up;                    /* 1,2,4,8: nearest-neighbour replication on write */
   int32_t relu;                  /* 0/1                                          */
   int32_t in_pitch, out_pitch, res_pitch;
-  int32_t dtype;                 /* FAMI_F32 or FAMI_BF16 (x, y, residual, w)    */
+  int32_t dtype;                 /* FAMI_F32 or FAMI_BF16 (x, residual, w)       */
+  int32_t out_dtype;             /* dtype of y: equal to dtype, or FAMI_F32 with dtype FAMI_BF16
+                                    (offset/mask and heatmap convs keep fp32 outputs)            */
   int32_t stats;                 /* 1: also accumulate per-channel sum / sum-of-squares of the RAW
                                     (post scale/shift, pre residual/act) output into the double
                                     array stats_out[2*Cout], which the caller zeroes (train-mode BN) */

@@ -299,3 +299,76 @@ def test_cpu_tensors_fail_loudly():
     from fami_pose_b200 import ops
     with pytest.raises(RuntimeError):
         ops.to_nhwc(torch.zeros(1, 3, 4, 4))
+
+
+# ---------------------------------------------------------------------------------------------
+# bf16 tensor-core (tcgen05) convolution
+# ---------------------------------------------------------------------------------------------
+TC_CASES = [
+    # Cin, Cout, k, stride, pad, dil, H, W, N, bias, bn, relu, res, up, out_f32
+    (48, 48, 3, 1, 1, 1, 24, 18, 3, False, True, True, True, 1, False),
+    (64, 64, 1, 1, 0, 1, 16, 8, 1, False, False, False, False, 1, False),   # plain GEMM, M = 128
+    (64, 64, 3, 1, 1, 1, 16, 8, 2, False, True, True, False, 1, False),
+    (96, 96, 3, 1, 1, 1, 12, 9, 5, False, True, True, True, 1, False),      # 2 chunks, partial last chunk
+    (192, 192, 3, 1, 1, 1, 6, 5, 7, False, True, True, True, 1, False),
+    (384, 384, 3, 1, 1, 1, 5, 4, 9, False, True, True, True, 1, False),     # 2 N tiles
+    (48, 96, 3, 2, 1, 1, 24, 18, 3, False, True, False, True, 1, False),    # stride 2 + running sum
+    (64, 64, 3, 2, 1, 1, 19, 13, 2, False, True, True, False, 1, False),    # stride 2, odd size
+    (96, 48, 1, 1, 0, 1, 6, 5, 4, False, True, True, True, 2, False),       # fuse up x2
+    (384, 48, 1, 1, 0, 1, 3, 3, 5, False, True, False, True, 8, False),     # fuse up x8
+    (48, 324, 3, 1, 3, 3, 12, 9, 2, True, False, False, False, 1, True),    # offset|mask conv, fp32 out
+    (48, 17, 3, 1, 1, 1, 12, 9, 2, True, False, False, False, 1, True),     # heatmap conv, fp32 out
+    (16, 16, 3, 2, 1, 1, 6, 5, 8, True, True, True, False, 1, False),
+    (256, 64, 1, 1, 0, 1, 9, 7, 3, False, True, True, False, 1, False),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc_bf16(case):
+    """tcgen05 bf16 conv vs torch CPU fp32 conv on the SAME bf16-rounded operands (so only the
+    accumulation order and the bf16 output rounding differ): tol 1e-2*max|ref| for bf16 outputs
+    (2^-8 rounding), 2e-3*max|ref| for fp32 outputs."""
+    import fami_pose_b200 as m
+    from fami_pose_b200 import ops
+    m.set_precision("bf16")
+    try:
+        Cin, Cout, k, s, p, d, H, W, N, bias, bn, relu, res, up, out_f32 = case
+        g = torch.Generator().manual_seed(abs(hash(case)) % (2 ** 31))
+        rb = lambda t: t.bfloat16().float()
+        x = rb(torch.randn(N, Cin, H, W, generator=g))
+        conv = torch.nn.Conv2d(Cin, Cout, k, s, p, d, bias=bias)
+        with torch.no_grad():
+            conv.weight.copy_(rb(torch.randn(conv.weight.shape, generator=g) / (Cin * k * k) ** 0.5))
+            if bias:
+                conv.bias.copy_(torch.randn(Cout, generator=g))
+        bnm = None
+        if bn:
+            bnm = torch.nn.BatchNorm2d(Cout).eval()
+            with torch.no_grad():
+                bnm.weight.copy_(torch.rand(Cout, generator=g) + 0.5)
+                bnm.bias.copy_(torch.randn(Cout, generator=g) * 0.2)
+                bnm.running_mean.copy_(torch.randn(Cout, generator=g) * 0.2)
+                bnm.running_var.copy_(torch.rand(Cout, generator=g) + 0.5)
+        with torch.no_grad():
+            y = conv(x)
+            if bn:
+                y = bnm(y)
+            if up > 1:
+                y = F.interpolate(y, scale_factor=up, mode="nearest")
+            r = rb(torch.randn(y.shape, generator=g)) if res else None
+            if res:
+                y = y + r
+            if relu:
+                y = F.relu(y)
+        xd = ops.to_nhwc(x.to(DEV), torch.bfloat16)
+        rd = ops.to_nhwc(r.to(DEV), torch.bfloat16) if res else None
+        out = ops.conv_bn_act(xd, conv.to(DEV), bnm.to(DEV) if bn else None, relu=relu, residual=rd, up=up,
+                              out_dtype=torch.float32 if out_f32 else None)
+        assert out.dtype == (torch.float32 if out_f32 else torch.bfloat16)
+        got = ops.to_nchw(out).cpu()
+        tol = (2e-3 if out_f32 else 1e-2) * float(y.abs().max()) + 1e-3
+        err = float((got - y).abs().max())
+        print("tc conv", case, "err", err, "tol", tol)
+        assert err <= tol
+    finally:
+        m.set_precision("fp32")
