@@ -6,6 +6,7 @@ state_dict keys are identical ('stage3.1.branches.2.3.conv2.weight', 'transition
 every fuse-layer term is a convolution whose epilogue adds the running sum, applies the final ReLU
 and replicates on write for the nearest upsample (hrnet.py:89-146,151-172).
 """
+import torch
 import torch.nn as nn
 
 from . import ops
@@ -250,11 +251,11 @@ class HRNetPlus(_HRNetTrunk):
     def forward(self, x, **kwargs):
         if kwargs.get("similar", False):
             raise NotImplementedError("HRNetPlus(similar=True) is not used by any registered model")
-        x = ops.to_nhwc(x)
+        x = ops.to_nhwc(x, torch.float32)   # the stem reads fp32 pixels in both precisions
         ys, _ = self._trunk(x)
         if kwargs.get("heatmap", True) is False:
             return ys[0]
-        hm = ops.conv_bn_act(ys[0], self.final_layer, None, relu=False)
+        hm = ops.conv_bn_act(ys[0], self.final_layer, None, relu=False, out_dtype=torch.float32)
         return hm, ys
 
 
@@ -269,9 +270,9 @@ class HRNet(_HRNetTrunk):
         return None
 
     def forward(self, x):
-        x = ops.to_nhwc(x)
+        x = ops.to_nhwc(x, torch.float32)
         ys, x3_list = self._trunk(x)
-        hm = ops.conv_bn_act(ys[0], self.final_layer, None, relu=False)
+        hm = ops.conv_bn_act(ys[0], self.final_layer, None, relu=False, out_dtype=torch.float32)
         if self.use_deconv or self.use_prediction:
             return x3_list[0], hm
         return hm, x3_list

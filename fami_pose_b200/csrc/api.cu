@@ -31,10 +31,10 @@ int num_sms() {
 
 // kernels implemented in other translation units
 int conv_f32_launch(const fami_conv_desc* d, const float* x, const float* w, const float* scale,
-                    const float* shift, const float* res, float* y, double* stats, cudaStream_t st);
+                    const float* shift, const void* res, void* y, double* stats, cudaStream_t st);
 int pack_w_f32_launch(const float* w, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t st);
-int dcn_f32_simt_launch(const fami_dcn_desc* d, const float* x, const float* off, const float* mask,
-                        const float* w, const float* bias, float* out, cudaStream_t st);
+int dcn_simt_launch(const fami_dcn_desc* d, const void* x, const float* off, const float* mask,
+                    const float* w, const float* bias, void* out, cudaStream_t st);
 int conv_bf16_tc_supported(const fami_conv_desc* d);
 int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale,
                         const float* shift, const void* res, void* y, double* stats, cudaStream_t st);
@@ -52,8 +52,9 @@ int linear_fwd_launch(const float*, const float*, const float*, float*, int, int
 int copy2d_launch(const void*, int, void*, int, int, int64_t, int, cudaStream_t);
 int bn_finalize_launch(const double*, const float*, const float*, float*, float*, float*, float*, float*, float*, int,
                        int64_t, float, float, cudaStream_t);
-int bn_apply_act_launch(const void*, int, const float*, const float*, const void*, int, void*, int, int, int, int, int,
-                        int, int, int, cudaStream_t);
+int bn_apply_act_launch(const void*, int, int, const float*, const float*, const void*, int, void*, int, int, int, int,
+                        int, int, int, int, cudaStream_t);
+int bn_stats_launch(const void*, int, int, int64_t, int, double*, cudaStream_t);
 int joint_mse_launch(const void*, int, int, const float*, const float*, float*, float*, float, int, int, int, int,
                      cudaStream_t);
 int softmax_pkl_launch(const void*, int, const void*, int, int, float*, int, int, int, float, cudaStream_t);
@@ -123,14 +124,16 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
   FAMI_CHECK_ARG(!residual || d->res_pitch >= d->Cout, "fami_conv2d_bn_act_fwd: res_pitch < Cout");
   FAMI_CHECK_ARG(!d->stats || stats_out, "fami_conv2d_bn_act_fwd: stats requested without stats_out");
   FAMI_CHECK_ARG((int64_t)d->N * d->Ho * d->Wo < (1ll << 31), "fami_conv2d_bn_act_fwd: too many output pixels");
-  FAMI_CHECK_ARG(d->out_dtype == d->dtype || (d->dtype == FAMI_BF16 && d->out_dtype == FAMI_F32),
-                 "fami_conv2d_bn_act_fwd: unsupported (dtype, out_dtype) = (%d, %d)", d->dtype, d->out_dtype);
+  FAMI_CHECK_ARG(valid_dtype(d->out_dtype), "fami_conv2d_bn_act_fwd: bad out_dtype %d", d->out_dtype);
+  /* fp32 input with bf16 output: only the stem (Cin not a multiple of 16), which runs the SIMT kernel */
+  FAMI_CHECK_ARG(!(d->dtype == FAMI_F32 && d->out_dtype == FAMI_BF16) || (d->Cin % 16 != 0 && !d->stats),
+                 "fami_conv2d_bn_act_fwd: fp32-in/bf16-out is only supported for the stem convolution");
   if (d->dtype == FAMI_BF16) {
     FAMI_CHECK_ARG(conv_bf16_tc_supported(d), "fami_conv2d_bn_act_fwd: shape not supported by the bf16 tensor path");
     return conv_bf16_tc_launch(d, x, w_packed, scale, shift, residual, y, stats_out, (cudaStream_t)stream);
   }
-  return conv_f32_launch(d, (const float*)x, (const float*)w_packed, scale, shift, (const float*)residual, (float*)y,
-                         stats_out, (cudaStream_t)stream);
+  return conv_f32_launch(d, (const float*)x, (const float*)w_packed, scale, shift, residual, y, stats_out,
+                         (cudaStream_t)stream);
 }
 
 int fami_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
@@ -141,14 +144,21 @@ int fami_bn_finalize(const double* stats, const float* gamma, const float* beta,
                             count, eps, momentum, (cudaStream_t)stream);
 }
 
-int fami_bn_apply_act(const void* x, int x_pitch, const float* scale, const float* shift, const void* residual,
-                      int res_pitch, void* y, int y_pitch, int dtype, int N, int Ho, int Wo, int C, int up, int relu,
-                      void* stream) {
+int fami_bn_apply_act(const void* x, int x_dtype, int x_pitch, const float* scale, const float* shift,
+                      const void* residual, int res_pitch, void* y, int y_pitch, int dtype, int N, int Ho, int Wo, int C,
+                      int up, int relu, void* stream) {
   FAMI_CHECK_ARG(x && scale && shift && y, "fami_bn_apply_act: null pointer");
-  FAMI_CHECK_ARG(valid_dtype(dtype), "fami_bn_apply_act: bad dtype");
+  FAMI_CHECK_ARG(valid_dtype(dtype) && valid_dtype(x_dtype), "fami_bn_apply_act: bad dtype");
   FAMI_CHECK_ARG(up == 1 || up == 2 || up == 4 || up == 8, "fami_bn_apply_act: up=%d", up);
-  return bn_apply_act_launch(x, x_pitch, scale, shift, residual, res_pitch, y, y_pitch, dtype, N, Ho, Wo, C, up, relu,
-                             (cudaStream_t)stream);
+  return bn_apply_act_launch(x, x_dtype, x_pitch, scale, shift, residual, res_pitch, y, y_pitch, dtype, N, Ho, Wo, C, up,
+                             relu, (cudaStream_t)stream);
+}
+
+int fami_bn_stats(const void* x, int dtype, int pitch, int64_t rows, int C, double* stats, void* stream) {
+  FAMI_CHECK_ARG(x && stats, "fami_bn_stats: null pointer");
+  FAMI_CHECK_ARG(valid_dtype(dtype), "fami_bn_stats: bad dtype");
+  FAMI_CHECK_ARG(rows > 0 && C > 0 && C <= 1024 && pitch >= C, "fami_bn_stats: bad shape");
+  return bn_stats_launch(x, dtype, pitch, rows, C, stats, (cudaStream_t)stream);
 }
 
 static int check_dcn(const fami_dcn_desc* d, const char* who) {
@@ -172,11 +182,11 @@ int fami_dcn_fwd(const fami_dcn_desc* d, const void* x, const void* offset, cons
                  const float* bias, void* out, void* stream) {
   if (int e = check_dcn(d, "fami_dcn_fwd")) return e;
   FAMI_CHECK_ARG(x && offset && mask && w_packed && out, "fami_dcn_fwd: null pointer");
-  FAMI_CHECK_ARG(d->dtype == FAMI_F32, "fami_dcn_fwd: dtype %d not supported yet", d->dtype);
-  FAMI_CHECK_ARG(aligned(x, 16) && d->x_pitch % 4 == 0, "fami_dcn_fwd: x must be 16B aligned with pitch %% 4 == 0");
-  FAMI_CHECK_ARG(aligned(offset, 8) && d->off_pitch % 2 == 0, "fami_dcn_fwd: offset must be 8B aligned, even pitch");
-  return dcn_f32_simt_launch(d, (const float*)x, (const float*)offset, (const float*)mask, (const float*)w_packed,
-                             bias, (float*)out, (cudaStream_t)stream);
+  FAMI_CHECK_ARG(valid_dtype(d->dtype), "fami_dcn_fwd: bad dtype %d", d->dtype);
+  FAMI_CHECK_ARG(aligned(x, 4 * esize(d->dtype)) && d->x_pitch % 4 == 0,
+                 "fami_dcn_fwd: x must be aligned to 4 elements with pitch %% 4 == 0");
+  return dcn_simt_launch(d, x, (const float*)offset, (const float*)mask, (const float*)w_packed, bias, out,
+                         (cudaStream_t)stream);
 }
 
 int fami_dcn_bwd(const fami_dcn_desc* d, const float* x, const float* offset, const float* mask,

@@ -14,12 +14,12 @@
 namespace fami {
 
 struct ConvParams {
-  const float* x;
+  const void* x;      // float (conv modes) or TX (DCN mode)
   const float* w;
   const float* scale;
   const float* shift;
-  const float* res;
-  float* y;
+  const void* res;    // TO
+  void* y;            // TO
   double* stats;
   int N, H, W, Cin, Cout, CoutPad, kh, kw, stride, pad, dil, Ho, Wo, up, relu;
   int in_pitch, out_pitch, res_pitch;
@@ -35,8 +35,12 @@ struct ConvParams {
 
 enum { MODE_VEC = 0, MODE_SCALAR = 1, MODE_DCN = 2 };
 
-template <int WM, int WN, int MODE>
+template <int WM, int WN, int MODE, typename TX, typename TO>
 __global__ void __launch_bounds__(WM * WN * 32) conv_f32_kernel(const ConvParams p) {
+  const TX* __restrict__ xptr = reinterpret_cast<const TX*>(p.x);
+  const float* __restrict__ xptrf = reinterpret_cast<const float*>(p.x);
+  const TO* __restrict__ rptr = reinterpret_cast<const TO*>(p.res);
+  TO* __restrict__ yptr = reinterpret_cast<TO*>(p.y);
   constexpr int BM = WM * 64, BN = WN * 16, KC = 16, NT = WM * WN * 32, AS = KC + 4, STAGES = 3;
   constexpr int A_CH = (BM * 4 + NT - 1) / NT;        // 16B chunks of the A tile per thread
   constexpr int B_CH = (KC * BN / 4 + NT - 1) / NT;   // 16B chunks of the B tile per thread
@@ -100,13 +104,13 @@ __global__ void __launch_bounds__(WM * WN * 32) conv_f32_kernel(const ConvParams
               int y0 = (int)floorf(py), x0 = (int)floorf(px);
               float ly = py - (float)y0, lx = px - (float)x0;
               float hy = 1.f - ly, hx = 1.f - lx;
-              const float* xb = p.x + a_img[i] * p.in_pitch + ch;
+              const TX* xb = xptr + a_img[i] * p.in_pitch + ch;
               const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
               bool y0ok = y0 >= 0, y1ok = y0 + 1 <= p.H - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= p.W - 1;
-              float4 v1 = (y0ok && x0ok) ? ld4(xb + ((int64_t)y0 * p.W + x0) * p.in_pitch) : z;
-              float4 v2 = (y0ok && x1ok) ? ld4(xb + ((int64_t)y0 * p.W + x0 + 1) * p.in_pitch) : z;
-              float4 v3 = (y1ok && x0ok) ? ld4(xb + ((int64_t)(y0 + 1) * p.W + x0) * p.in_pitch) : z;
-              float4 v4 = (y1ok && x1ok) ? ld4(xb + ((int64_t)(y0 + 1) * p.W + x0 + 1) * p.in_pitch) : z;
+              float4 v1 = (y0ok && x0ok) ? ld4<TX>(xb + ((int64_t)y0 * p.W + x0) * p.in_pitch) : z;
+              float4 v2 = (y0ok && x1ok) ? ld4<TX>(xb + ((int64_t)y0 * p.W + x0 + 1) * p.in_pitch) : z;
+              float4 v3 = (y1ok && x0ok) ? ld4<TX>(xb + ((int64_t)(y0 + 1) * p.W + x0) * p.in_pitch) : z;
+              float4 v4 = (y1ok && x1ok) ? ld4<TX>(xb + ((int64_t)(y0 + 1) * p.W + x0 + 1) * p.in_pitch) : z;
               float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
               val.x = mk * (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x);
               val.y = mk * (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y);
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(WM * WN * 32) conv_f32_kernel(const ConvParams
         if (c < BM * 4) {
           int iy = a_iy0[i] + dy, ix = a_ix0[i] + dx;
           bool ok = a_ok[i] && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
-          const float* src = ok ? p.x + (a_img[i] + (int64_t)iy * p.W + ix) * p.in_pitch + c0 + ((c & 3) << 2) : p.x;
+          const float* src = ok ? xptrf + (a_img[i] + (int64_t)iy * p.W + ix) * p.in_pitch + c0 + ((c & 3) << 2) : xptrf;
           cp_async16(as + (c >> 2) * AS + ((c & 3) << 2), src, ok);
         }
       }
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(WM * WN * 32) conv_f32_kernel(const ConvParams
           int yo = rr / p.Wo, xo = rr - yo * p.Wo;
           int iy = yo * p.stride - p.pad + r * p.dil, ix = xo * p.stride - p.pad + sx * p.dil;
           if ((unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W)
-            v = __ldg(p.x + ((int64_t)(n * p.H + iy) * p.W + ix) * p.in_pitch + ci);
+            v = __ldg(xptrf + ((int64_t)(n * p.H + iy) * p.W + ix) * p.in_pitch + ci);
         }
         as[ml * AS + kk] = v;
       }
@@ -241,23 +245,23 @@ __global__ void __launch_bounds__(WM * WN * 32) conv_f32_kernel(const ConvParams
     for (int dy = 0; dy < p.up; ++dy)
       for (int dx = 0; dx < p.up; ++dx) {
         int64_t pix = ((int64_t)n * Hout + yo * p.up + dy) * Wout + xo * p.up + dx;
-        float* yp = p.y + pix * p.out_pitch + n0;
+        TO* yp = yptr + pix * p.out_pitch + n0;
         if (vec_out) {
           float4 o = make_float4(v[0], v[1], v[2], v[3]);
-          if (p.res) {
-            float4 rr = *reinterpret_cast<const float4*>(p.res + pix * p.res_pitch + n0);
+          if (rptr) {
+            float4 rr = ld4<TO>(rptr + pix * p.res_pitch + n0);
             o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
           }
           if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          *reinterpret_cast<float4*>(yp) = o;
+          st4<TO>(yp, o);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (n0 + j < p.Cout) {
               float o = v[j];
-              if (p.res) o += p.res[pix * p.res_pitch + n0 + j];
+              if (rptr) o += to_f<TO>(rptr[pix * p.res_pitch + n0 + j]);
               if (p.relu) o = fmaxf(o, 0.f);
-              yp[j] = o;
+              yp[j] = from_f<TO>(o);
             }
           }
         }
@@ -284,36 +288,39 @@ __global__ void __launch_bounds__(WM * WN * 32) conv_f32_kernel(const ConvParams
   }
 }
 
-template <int WM, int WN, int MODE>
+template <int WM, int WN, int MODE, typename TX, typename TO>
 static int launch_cfg(const ConvParams& p, cudaStream_t st) {
   constexpr int BM = WM * 64, BN = WN * 16;
   constexpr size_t smem = (size_t)3 * (BM * 20 + 16 * BN) * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(conv_f32_kernel<WM, WN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(conv_f32_kernel<WM, WN, MODE, TX, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
   dim3 grid(cdiv(p.M, BM), p.CoutPad / BN);
-  conv_f32_kernel<WM, WN, MODE><<<grid, WM * WN * 32, smem, st>>>(p);
+  conv_f32_kernel<WM, WN, MODE, TX, TO><<<grid, WM * WN * 32, smem, st>>>(p);
   FAMI_CHECK_LAUNCH("conv_f32_kernel");
   return 0;
 }
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int MODE>
+template <int MODE, typename TX, typename TO>
 static int dispatch_tile(const ConvParams& p, cudaStream_t st) {
   const int cp = p.CoutPad;
-  if (cp % 64 == 0) return launch_cfg<2, 4, MODE>(p, st);
-  if (cp % 48 == 0) return launch_cfg<2, 3, MODE>(p, st);
-  if (cp % 32 == 0) return launch_cfg<4, 2, MODE>(p, st);
-  return launch_cfg<4, 1, MODE>(p, st);
+  if (cp % 64 == 0) return launch_cfg<2, 4, MODE, TX, TO>(p, st);
+  if (cp % 48 == 0) return launch_cfg<2, 3, MODE, TX, TO>(p, st);
+  if (cp % 32 == 0) return launch_cfg<4, 2, MODE, TX, TO>(p, st);
+  return launch_cfg<4, 1, MODE, TX, TO>(p, st);
 }
 
+// x: float NHWC.  y/residual: float (out_bf16 = 0) or bf16 (out_bf16 = 1, scalar-gather stem path only).
 int conv_f32_launch(const fami_conv_desc* d, const float* x, const float* w, const float* scale,
-                    const float* shift, const float* res, float* y, double* stats, cudaStream_t st) {
+                    const float* shift, const void* res, void* y, double* stats, cudaStream_t st) {
   ConvParams p;
   memset(&p, 0, sizeof(p));
+  const bool out_bf16 = d->out_dtype == FAMI_BF16;
+  const size_t osz = out_bf16 ? 2 : 4;
   p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.res = res; p.y = y; p.stats = d->stats ? stats : nullptr;
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
   p.CoutPad = fami_conv_cout_pad(d->Cout);
@@ -323,16 +330,21 @@ int conv_f32_launch(const fami_conv_desc* d, const float* x, const float* w, con
   p.M = d->N * d->Ho * d->Wo;
   p.Ktot = d->kh * d->kw * d->Cin;
   p.ksteps = (p.Ktot + 15) / 16;
-  p.vec_store = al16(y) && (d->out_pitch % 4 == 0) && (!res || (al16(res) && d->res_pitch % 4 == 0));
+  const size_t va = 4 * osz;  // bytes of a 4-channel vector access
+  p.vec_store = (reinterpret_cast<uintptr_t>(y) % va == 0) && (d->out_pitch % 4 == 0) &&
+                (!res || ((reinterpret_cast<uintptr_t>(res) % va == 0) && d->res_pitch % 4 == 0));
   const bool vec = (d->Cin % 16 == 0) && (d->in_pitch % 4 == 0) && al16(x);
-  return vec ? dispatch_tile<MODE_VEC>(p, st) : dispatch_tile<MODE_SCALAR>(p, st);
+  if (out_bf16) return dispatch_tile<MODE_SCALAR, float, __nv_bfloat16>(p, st);
+  return vec ? dispatch_tile<MODE_VEC, float, float>(p, st) : dispatch_tile<MODE_SCALAR, float, float>(p, st);
 }
 
 // v1 DCN forward: same mainloop/epilogue as the conv, A tile produced by the deformable gather.
-int dcn_f32_simt_launch(const fami_dcn_desc* d, const float* x, const float* off, const float* mask,
-                        const float* w, const float* bias, float* out, cudaStream_t st) {
+// x/out: float or bf16 (d->dtype); offset/mask/weights/bias: float.
+int dcn_simt_launch(const fami_dcn_desc* d, const void* x, const float* off, const float* mask,
+                    const float* w, const float* bias, void* out, cudaStream_t st) {
   ConvParams p;
   memset(&p, 0, sizeof(p));
+  const bool bf = d->dtype == FAMI_BF16;
   p.x = x; p.w = w; p.scale = nullptr; p.shift = bias; p.res = nullptr; p.y = out; p.stats = nullptr;
   p.N = d->B; p.H = d->H; p.W = d->W; p.Cin = d->C; p.Cout = d->Cout;
   p.CoutPad = fami_conv_cout_pad(d->Cout);
@@ -343,10 +355,11 @@ int dcn_f32_simt_launch(const fami_dcn_desc* d, const float* x, const float* off
   p.M = d->B * p.Ho * p.Wo;
   p.Ktot = d->kh * d->kw * d->C;
   p.ksteps = p.Ktot / 16;
-  p.vec_store = al16(out) && (d->out_pitch % 4 == 0);
+  p.vec_store = (reinterpret_cast<uintptr_t>(out) % (bf ? 8 : 16) == 0) && (d->out_pitch % 4 == 0);
   p.off = off; p.mask = mask; p.off_pitch = d->off_pitch; p.mask_pitch = d->mask_pitch;
   p.cpg = d->C / d->G;
-  return dispatch_tile<MODE_DCN>(p, st);
+  if (bf) return dispatch_tile<MODE_DCN, __nv_bfloat16, __nv_bfloat16>(p, st);
+  return dispatch_tile<MODE_DCN, float, float>(p, st);
 }
 
 // ---- weight packing: OIHW float -> [kh*kw*Cin (padded to 16)][CoutPad] float ------------------

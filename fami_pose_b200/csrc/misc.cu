@@ -134,8 +134,34 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float
   }
 }
 
+// per-channel sum / sum-of-squares over rows of an NHWC activation (train-mode BN on the tensor-core path)
 template <typename T>
-__global__ void bn_apply_act_kernel(const T* __restrict__ x, int x_pitch, const float* __restrict__ scale,
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, int pitch, int64_t rows, int C,
+                                                        double* __restrict__ stats, int rows_per_block) {
+  extern __shared__ float sm[];
+  const int RG = blockDim.x / C;
+  const int tid = threadIdx.x, c = tid % C, rg = tid / C;
+  int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float s = 0.f, q = 0.f;
+  if (rg < RG)
+    for (int64_t r = r0 + rg; r < r1; r += RG) {
+      float v = to_f<T>(x[r * pitch + c]);
+      s += v;
+      q = fmaf(v, v, q);
+    }
+  if (rg < RG) { sm[rg * C + c] = s; sm[(RG + rg) * C + c] = q; }
+  __syncthreads();
+  if (tid < C) {
+    double ds = 0, dq = 0;
+    for (int r = 0; r < RG; ++r) { ds += sm[r * C + tid]; dq += sm[(RG + r) * C + tid]; }
+    atomicAdd(stats + tid, ds);
+    atomicAdd(stats + C + tid, dq);
+  }
+}
+
+template <typename TI, typename T>
+__global__ void bn_apply_act_kernel(const TI* __restrict__ x, int x_pitch, const float* __restrict__ scale,
                                     const float* __restrict__ shift, const T* __restrict__ res, int res_pitch,
                                     T* __restrict__ y, int y_pitch, int N, int Ho, int Wo, int C, int up, int relu) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,7 +169,7 @@ __global__ void bn_apply_act_kernel(const T* __restrict__ x, int x_pitch, const 
   if (i >= tot) return;
   int c = (int)(i % C);
   int64_t pix = i / C;
-  float v = to_f<T>(x[pix * x_pitch + c]) * __ldg(scale + c) + __ldg(shift + c);
+  float v = to_f<TI>(x[pix * x_pitch + c]) * __ldg(scale + c) + __ldg(shift + c);
   int xo = (int)(pix % Wo);
   int64_t t = pix / Wo;
   int yo = (int)(t % Ho);
@@ -344,12 +370,28 @@ int bn_finalize_launch(const double* stats, const float* gamma, const float* bet
   FAMI_CHECK_LAUNCH("bn_finalize");
   return 0;
 }
-int bn_apply_act_launch(const void* x, int xp, const float* scale, const float* shift, const void* res, int rp, void* y,
-                        int yp, int dt, int N, int Ho, int Wo, int C, int up, int relu, cudaStream_t st) {
+int bn_apply_act_launch(const void* x, int xdt, int xp, const float* scale, const float* shift, const void* res, int rp,
+                        void* y, int yp, int dt, int N, int Ho, int Wo, int C, int up, int relu, cudaStream_t st) {
   int64_t tot = (int64_t)N * Ho * Wo * C;
-  DISPATCH_T(dt, bn_apply_act_kernel<T><<<cdiv(tot, 256), 256, 0, st>>>((const T*)x, xp, scale, shift, (const T*)res,
-                                                                         rp, (T*)y, yp, N, Ho, Wo, C, up, relu);)
+  if (xdt == FAMI_F32) {
+    DISPATCH_T(dt, bn_apply_act_kernel<float, T><<<cdiv(tot, 256), 256, 0, st>>>(
+                       (const float*)x, xp, scale, shift, (const T*)res, rp, (T*)y, yp, N, Ho, Wo, C, up, relu);)
+  } else {
+    DISPATCH_T(dt, bn_apply_act_kernel<__nv_bfloat16, T><<<cdiv(tot, 256), 256, 0, st>>>(
+                       (const __nv_bfloat16*)x, xp, scale, shift, (const T*)res, rp, (T*)y, yp, N, Ho, Wo, C, up, relu);)
+  }
   FAMI_CHECK_LAUNCH("bn_apply_act");
+  return 0;
+}
+int bn_stats_launch(const void* x, int dt, int pitch, int64_t rows, int C, double* stats, cudaStream_t st) {
+  int threads = 256;
+  if (C > threads) threads = ((C + 31) / 32) * 32;
+  int RG = threads / C;
+  int rows_per_block = 2048;
+  size_t smem = (size_t)2 * RG * C * sizeof(float);
+  DISPATCH_T(dt, bn_stats_kernel<T><<<cdiv(rows, rows_per_block), threads, smem, st>>>((const T*)x, pitch, rows, C, stats,
+                                                                                       rows_per_block);)
+  FAMI_CHECK_LAUNCH("bn_stats");
   return 0;
 }
 int joint_mse_launch(const void* pred, int dt, int pitch, const float* target, const float* weight, float* loss,

@@ -188,9 +188,9 @@ class DeformConv2d(nn.Module):
 
     def forward(self, input, offset, mask=None, out=None):
         x = ops.to_nhwc(input)
-        off = ops.to_nhwc(offset)
+        off = ops.to_nhwc(offset, torch.float32)
         if mask is None:
             raise NotImplementedError("FAMI-Pose always passes a modulation mask (DCNv2)")
-        msk = ops.to_nhwc(mask)
+        msk = ops.to_nhwc(mask, torch.float32)
         return ops.dcn_fwd(x, off, msk, self.weight, self.bias, self, pad=self.padding[0], dil=self.dilation[0],
                            out=out)

@@ -94,9 +94,7 @@ def to_nhwc(x, dtype=None):
     Tensors that already carry channels-last strides (outputs of other fami ops) pass through."""
     _need_cuda(x)
     dtype = dtype or act_dtype()
-    if x.dim() == 4 and is_nhwc(x):
-        if x.dtype != dtype:
-            raise TypeError("activation dtype %s does not match the active precision %s" % (x.dtype, dtype))
+    if x.dim() == 4 and is_nhwc(x) and x.dtype in (torch.float32, torch.bfloat16):
         return x
     if x.dtype != torch.float32:
         raise TypeError("boundary tensors must be float32 NCHW, got %s" % x.dtype)
@@ -107,10 +105,10 @@ def to_nhwc(x, dtype=None):
     return out
 
 
-def frames_to_nhwc(kf_x, sup_x, dtype=None):
-    """Alignment_V15.py:115-119: [B,3,H,W] + [B,3*ns,H,W] -> frame-major [(1+ns)*B,H,W,3]."""
+def frames_to_nhwc(kf_x, sup_x, dtype=torch.float32):
+    """Alignment_V15.py:115-119: [B,3,H,W] + [B,3*ns,H,W] -> frame-major [(1+ns)*B,H,W,3] (float32: the
+    stem convolution reads fp32 pixels in both precisions)."""
     _need_cuda(kf_x, sup_x)
-    dtype = dtype or act_dtype()
     kf_x = kf_x.contiguous()
     sup_x = sup_x.contiguous()
     B, _, H, W = kf_x.shape
@@ -190,7 +188,7 @@ def _conv_raw(x, w_packed, Cout, k, stride, pad, dil, scale, shift, residual, re
     N, Cin, H, W, ip = meta(x)
     Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
     Wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
-    out_dtype = out_dtype or (out.dtype if out is not None else x.dtype)
+    out_dtype = out_dtype or (out.dtype if out is not None else act_dtype())
     if out is None:
         out = empty_nhwc(N, Cout, Ho * up, Wo * up, out_dtype, x.device)
     oN, oC, oH, oW, op = meta(out)
@@ -227,8 +225,14 @@ def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None, out
         # batch statistics: raw conv (+bias) with fused per-channel sum / sum-of-squares
         bias = conv.bias.detach().float() if conv.bias is not None else None
         stats = torch.zeros(2 * Cout, dtype=torch.float64, device=x.device)
-        raw = _conv_raw(x, w, Cout, k, stride, pad, dil, None, bias, None, False, 1, None, stats)
-        N, _, Ho, Wo, rawp = meta(raw)
+        if x.dtype == torch.float32:
+            raw = _conv_raw(x, w, Cout, k, stride, pad, dil, None, bias, None, False, 1, None, stats, torch.float32)
+            N, _, Ho, Wo, rawp = meta(raw)
+        else:
+            # tensor-core arm: raw conv output kept in fp32, statistics by a separate column reduction
+            raw = _conv_raw(x, w, Cout, k, stride, pad, dil, None, bias, None, False, 1, None, None, torch.float32)
+            N, _, Ho, Wo, rawp = meta(raw)
+            _lib.call("fami_bn_stats", _ptr(raw), F32, rawp, N * Ho * Wo, Cout, _ptr(stats), _stream())
         scale = torch.empty(Cout, dtype=torch.float32, device=x.device)
         shift = torch.empty_like(scale)
         mom = bn.momentum if bn.momentum is not None else 0.1
@@ -239,11 +243,11 @@ def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None, out
         if track and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
         if out is None:
-            out = empty_nhwc(N, Cout, Ho * up, Wo * up, x.dtype, x.device)
+            out = empty_nhwc(N, Cout, Ho * up, Wo * up, out_dtype or act_dtype(), x.device)
         op = meta(out)[4]
         rp = meta(residual)[4] if residual is not None else 0
-        _lib.call("fami_bn_apply_act", _ptr(raw), rawp, _ptr(scale), _ptr(shift), _ptr(residual), rp, _ptr(out), op,
-                  _code(x.dtype), N, Ho, Wo, Cout, up, int(bool(relu)), _stream())
+        _lib.call("fami_bn_apply_act", _ptr(raw), _code(raw.dtype), rawp, _ptr(scale), _ptr(shift), _ptr(residual), rp,
+                  _ptr(out), op, _code(out.dtype), N, Ho, Wo, Cout, up, int(bool(relu)), _stream())
         return out
     scale, shift = folded_affine(conv.bias, bn)
     return _conv_raw(x, w, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, out, None, out_dtype)
@@ -259,8 +263,8 @@ def upsample_nearest(x, factor):
     out = empty_nhwc(N, C, H * factor, W * factor, x.dtype, x.device)
     one = torch.ones(C, dtype=torch.float32, device=x.device)
     zero = torch.zeros(C, dtype=torch.float32, device=x.device)
-    _lib.call("fami_bn_apply_act", _ptr(x), p, _ptr(one), _ptr(zero), None, 0, _ptr(out), C, _code(x.dtype), N, H, W,
-              C, factor, 0, _stream())
+    _lib.call("fami_bn_apply_act", _ptr(x), _code(x.dtype), p, _ptr(one), _ptr(zero), None, 0, _ptr(out), C,
+              _code(x.dtype), N, H, W, C, factor, 0, _stream())
     return out
 
 
@@ -282,13 +286,15 @@ def dcn_fwd(x, offset, mask, weight, bias, owner, pad=3, dil=3, out=None):
     if C % G != 0 or Cin != C:
         raise ValueError("in_channels %d must be divisible by offset groups %d and match the weight (%d)" % (C, G, Cin))
     mB, MC, mH, mW, mp = meta(mask)
+    if offset.dtype != torch.float32 or mask.dtype != torch.float32:
+        raise TypeError("deformable offsets and masks are float32 in both precisions")
     if MC != G * kh * kw or (oB, oH, oW) != (B, H, W) or (mB, mH, mW) != (B, H, W):
         raise RuntimeError("offset/mask shapes %s %s inconsistent with input %s"
                            % (tuple(offset.shape), tuple(mask.shape), tuple(x.shape)))
     if out is None:
         out = empty_nhwc(B, Cout, H, W, x.dtype, x.device)
     outp = meta(out)[4]
-    w = packed_weight(owner, weight, x.dtype)
+    w = packed_weight(owner, weight, torch.float32)   # SIMT contraction: fp32 [K][CoutPad] packing
     d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, offp, mp, outp, _code(x.dtype))
     b = bias.detach().float() if bias is not None else None
     _lib.call("fami_dcn_fwd", ctypes.byref(d), _ptr(x), _ptr(offset), _ptr(mask), _ptr(w), _ptr(b), _ptr(out),

@@ -156,7 +156,7 @@ class Alignment_V15(nn.Module):
     def _offset_mask(self, k, x):
         off_m, msk_m = getattr(self, "dcn_offset_%d" % k), getattr(self, "dcn_mask_%d" % k)
         conv = self._offmask[k - 1].get(off_m.conv, msk_m.conv)
-        buf = ops.conv_bn_act(x, conv, None, relu=False)
+        buf = ops.conv_bn_act(x, conv, None, relu=False, out_dtype=torch.float32)   # sub-pixel offsets stay fp32
         n_off = off_m.conv.out_channels
         return buf[:, :n_off], buf[:, n_off:]
 
@@ -198,7 +198,7 @@ class Alignment_V15(nn.Module):
         ops.copy_into(kf_feat, cat2[:, :C])
         self.dcn_4(aligned, off, msk, out=cat2[:, C:])
         all_agg = self.init_feature_agg_block(cat2)                                # :161
-        final_hm = ops.conv_bn_act(all_agg, self.agg_final_layer, None, relu=False)  # :163
+        final_hm = ops.conv_bn_act(all_agg, self.agg_final_layer, None, relu=False, out_dtype=torch.float32)  # :163
 
         final_out, kf_out = ops.to_nchw(final_hm), ops.to_nchw(kf_bb_hm)
         self._last = {"final_hm_nhwc": final_hm, "txy": txy}
@@ -215,7 +215,7 @@ class Alignment_V15(nn.Module):
 
     def feat_label_mi_estimation(self, Feat, Y):
         """Alignment_V15.py:250-263."""
-        pred_Y = ops.conv_bn_act(ops.to_nhwc(Feat), self.hrnet.final_layer, None, relu=False)
+        pred_Y = ops.conv_bn_act(ops.to_nhwc(Feat), self.hrnet.final_layer, None, relu=False, out_dtype=torch.float32)
         return ops.softmax_pkl(pred_Y, ops.to_nhwc(Y), 0.05)
 
     def feat_feat_mi_estimation(self, F1, F2):

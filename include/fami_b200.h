@@ -68,8 +68,9 @@ typedef struct fami_conv_desc {
   int32_t relu;                  /* 0/1                                          */
   int32_t in_pitch, out_pitch, res_pitch;
   int32_t dtype;                 /* FAMI_F32 or FAMI_BF16 (x, residual, w)       */
-  int32_t out_dtype;             /* dtype of y: equal to dtype, or FAMI_F32 with dtype FAMI_BF16
-                                    (offset/mask and heatmap convs keep fp32 outputs)            */
+  int32_t out_dtype;             /* dtype of y (and residual): equal to dtype; or FAMI_F32 with dtype
+                                    FAMI_BF16 (offset/mask and heatmap convs keep fp32 outputs, no
+                                    residual); or FAMI_BF16 with dtype FAMI_F32 (stem conv only)   */
   int32_t stats;                 /* 1: also accumulate per-channel sum / sum-of-squares of the RAW
                                     (post scale/shift, pre residual/act) output into the double
                                     array stats_out[2*Cout], which the caller zeroes (train-mode BN) */
@@ -90,9 +91,13 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
 int fami_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
                      float* running_var, float* scale, float* shift, float* save_mean,
                      float* save_invstd, int C, int64_t count, float eps, float momentum, void* stream);
-int fami_bn_apply_act(const void* x, int x_pitch, const float* scale, const float* shift,
+int fami_bn_apply_act(const void* x, int x_dtype, int x_pitch, const float* scale, const float* shift,
                       const void* residual, int res_pitch, void* y, int y_pitch, int dtype, int N, int Ho,
                       int Wo, int C, int up, int relu, void* stream);
+/* per-channel (sum, sum of squares) of an NHWC activation [rows, C] accumulated into the double array
+ * stats[2*C] (caller zeroes): batch statistics for the tensor-core conv path, whose epilogue does not
+ * fuse them.                                                                                      */
+int fami_bn_stats(const void* x, int dtype, int pitch, int64_t rows, int C, double* stats, void* stream);
 
 /* ---- modulated deformable convolution v2 (the north-star kernel) ---------------------------
  * Replaces torchvision.ops.deform_conv2d as constructed/called at
@@ -105,7 +110,8 @@ typedef struct fami_dcn_desc {
   int32_t B, H, W, C, Cout, G;
   int32_t kh, kw, stride, pad, dil; /* 3,3,1,3,3 in the reference; stride must be 1 */
   int32_t x_pitch, off_pitch, mask_pitch, out_pitch;
-  int32_t dtype;                    /* storage of x/offset/mask/out: FAMI_F32 or FAMI_BF16 */
+  int32_t dtype;                    /* storage of x/out: FAMI_F32 or FAMI_BF16; offset, mask, packed
+                                       weights and bias are always float (sub-pixel precision)        */
 } fami_dcn_desc;
 
 int fami_dcn_fwd(const fami_dcn_desc* d, const void* x, const void* offset, const void* mask,

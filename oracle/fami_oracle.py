@@ -555,6 +555,8 @@ def seeded_state_dict(shapes, seed=19970808, dtype=torch.float32):
                 gain = 0.5
             elif "feat_global_offset_layers.9" in key:
                 gain = 3.0
+            elif "hrnet.final_layer" in key or key.startswith("final_layer"):
+                gain = 0.3   # rough heatmaps with |max| ~ 1
             elif len(shape) == 2 or "final_layer" in key or key.startswith("dcn_"):
                 gain = 1.0
             out[key] = (gain / math.sqrt(fan_in) * torch.randn(shape, generator=g)).to(dtype)
