@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libfami_b200.so")
 
 F32 = 0
 BF16 = 1
+F16 = 2
 
 
 class ConvDesc(Structure):

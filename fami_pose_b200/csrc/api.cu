@@ -39,7 +39,7 @@ int conv_bf16_tc_supported(const fami_conv_desc* d);
 int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale,
                         const float* shift, const void* res, void* y, double* stats, cudaStream_t st);
 int64_t pack_w_bf16_elems(int Cout, int Cin, int kh, int kw);
-int pack_w_bf16_launch(const float* w, void* out, int Cout, int Cin, int kh, int kw, cudaStream_t st);
+int pack_w_bf16_launch(const float* w, void* out, int Cout, int Cin, int kh, int kw, int dtype, cudaStream_t st);
 int dcn_bwd_launch(const fami_dcn_desc* d, const float* x, const float* off, const float* mask, const float* w,
                    const float* go, float* gx, float* goff, float* gmask, float* gw, float* gb, cudaStream_t st);
 int warp_translate_bwd_launch(const float* src, int sp, const float* txy, const float* go, int gop, float* gs,
@@ -64,7 +64,7 @@ int argmax_hw_launch(const void*, int, int, int32_t*, float*, int, int, int, cud
 
 using namespace fami;
 
-static inline bool valid_dtype(int dt) { return dt == FAMI_F32 || dt == FAMI_BF16; }
+static inline bool valid_dtype(int dt) { return dt == FAMI_F32 || dt == FAMI_BF16 || dt == FAMI_F16; }
 static inline size_t esize(int dt) { return dt == FAMI_F32 ? 4 : 2; }
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
@@ -93,7 +93,7 @@ int fami_nhwc_to_nchw(const void* src, int src_dtype, int src_pitch, float* dst,
 int fami_conv_cout_pad(int Cout) { return ((Cout + 15) / 16) * 16; }
 
 int64_t fami_packed_weight_elems(int Cout, int Cin, int kh, int kw, int dtype) {
-  if (dtype == FAMI_BF16) return pack_w_bf16_elems(Cout, Cin, kh, kw);
+  if (is_half_dtype(dtype)) return pack_w_bf16_elems(Cout, Cin, kh, kw);
   int64_t kpad = ((int64_t)kh * kw * Cin + 15) / 16 * 16;
   return kpad * fami_conv_cout_pad(Cout);
 }
@@ -103,7 +103,7 @@ int fami_pack_conv_weight(const float* w_oihw, void* w_packed, int Cout, int Cin
   FAMI_CHECK_ARG(w_oihw && w_packed, "fami_pack_conv_weight: null pointer");
   FAMI_CHECK_ARG(valid_dtype(dtype), "fami_pack_conv_weight: bad dtype %d", dtype);
   FAMI_CHECK_ARG(Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "fami_pack_conv_weight: bad shape");
-  if (dtype == FAMI_BF16) return pack_w_bf16_launch(w_oihw, w_packed, Cout, Cin, kh, kw, (cudaStream_t)stream);
+  if (is_half_dtype(dtype)) return pack_w_bf16_launch(w_oihw, w_packed, Cout, Cin, kh, kw, dtype, (cudaStream_t)stream);
   return pack_w_f32_launch(w_oihw, (float*)w_packed, Cout, Cin, kh, kw, (cudaStream_t)stream);
 }
 
@@ -126,9 +126,11 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
   FAMI_CHECK_ARG((int64_t)d->N * d->Ho * d->Wo < (1ll << 31), "fami_conv2d_bn_act_fwd: too many output pixels");
   FAMI_CHECK_ARG(valid_dtype(d->out_dtype), "fami_conv2d_bn_act_fwd: bad out_dtype %d", d->out_dtype);
   /* fp32 input with bf16 output: only the stem (Cin not a multiple of 16), which runs the SIMT kernel */
-  FAMI_CHECK_ARG(!(d->dtype == FAMI_F32 && d->out_dtype == FAMI_BF16) || (d->Cin % 16 != 0 && !d->stats),
+  FAMI_CHECK_ARG(!(d->dtype == FAMI_F32 && is_half_dtype(d->out_dtype)) || (d->Cin % 16 != 0 && !d->stats),
                  "fami_conv2d_bn_act_fwd: fp32-in/bf16-out is only supported for the stem convolution");
-  if (d->dtype == FAMI_BF16) {
+  if (is_half_dtype(d->dtype)) {
+    FAMI_CHECK_ARG(d->out_dtype == d->dtype || d->out_dtype == FAMI_F32,
+                   "fami_conv2d_bn_act_fwd: half-precision conv output must be the same half type or fp32");
     FAMI_CHECK_ARG(conv_bf16_tc_supported(d), "fami_conv2d_bn_act_fwd: shape not supported by the bf16 tensor path");
     return conv_bf16_tc_launch(d, x, w_packed, scale, shift, residual, y, stats_out, (cudaStream_t)stream);
   }

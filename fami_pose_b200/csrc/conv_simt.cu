@@ -319,8 +319,8 @@ int conv_f32_launch(const fami_conv_desc* d, const float* x, const float* w, con
                     const float* shift, const void* res, void* y, double* stats, cudaStream_t st) {
   ConvParams p;
   memset(&p, 0, sizeof(p));
-  const bool out_bf16 = d->out_dtype == FAMI_BF16;
-  const size_t osz = out_bf16 ? 2 : 4;
+  const bool out_half = is_half_dtype(d->out_dtype);
+  const size_t osz = out_half ? 2 : 4;
   p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.res = res; p.y = y; p.stats = d->stats ? stats : nullptr;
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
   p.CoutPad = fami_conv_cout_pad(d->Cout);
@@ -334,7 +334,8 @@ int conv_f32_launch(const fami_conv_desc* d, const float* x, const float* w, con
   p.vec_store = (reinterpret_cast<uintptr_t>(y) % va == 0) && (d->out_pitch % 4 == 0) &&
                 (!res || ((reinterpret_cast<uintptr_t>(res) % va == 0) && d->res_pitch % 4 == 0));
   const bool vec = (d->Cin % 16 == 0) && (d->in_pitch % 4 == 0) && al16(x);
-  if (out_bf16) return dispatch_tile<MODE_SCALAR, float, __nv_bfloat16>(p, st);
+  if (d->out_dtype == FAMI_BF16) return dispatch_tile<MODE_SCALAR, float, __nv_bfloat16>(p, st);
+  if (d->out_dtype == FAMI_F16) return dispatch_tile<MODE_SCALAR, float, __half>(p, st);
   return vec ? dispatch_tile<MODE_VEC, float, float>(p, st) : dispatch_tile<MODE_SCALAR, float, float>(p, st);
 }
 
@@ -344,7 +345,7 @@ int dcn_simt_launch(const fami_dcn_desc* d, const void* x, const float* off, con
                     const float* w, const float* bias, void* out, cudaStream_t st) {
   ConvParams p;
   memset(&p, 0, sizeof(p));
-  const bool bf = d->dtype == FAMI_BF16;
+  const bool bf = is_half_dtype(d->dtype);
   p.x = x; p.w = w; p.scale = nullptr; p.shift = bias; p.res = nullptr; p.y = out; p.stats = nullptr;
   p.N = d->B; p.H = d->H; p.W = d->W; p.Cin = d->C; p.Cout = d->Cout;
   p.CoutPad = fami_conv_cout_pad(d->Cout);
@@ -358,7 +359,8 @@ int dcn_simt_launch(const fami_dcn_desc* d, const void* x, const float* off, con
   p.vec_store = (reinterpret_cast<uintptr_t>(out) % (bf ? 8 : 16) == 0) && (d->out_pitch % 4 == 0);
   p.off = off; p.mask = mask; p.off_pitch = d->off_pitch; p.mask_pitch = d->mask_pitch;
   p.cpg = d->C / d->G;
-  if (bf) return dispatch_tile<MODE_DCN, __nv_bfloat16, __nv_bfloat16>(p, st);
+  if (d->dtype == FAMI_BF16) return dispatch_tile<MODE_DCN, __nv_bfloat16, __nv_bfloat16>(p, st);
+  if (d->dtype == FAMI_F16) return dispatch_tile<MODE_DCN, __half, __half>(p, st);
   return dispatch_tile<MODE_DCN, float, float>(p, st);
 }
 

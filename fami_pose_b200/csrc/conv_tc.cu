@@ -37,9 +37,27 @@ struct TcParams {
   int stages;
   const float* scale;
   const float* shift;
-  const __nv_bfloat16* res;
+  const void* res;   // TH
   void* y;
+  uint32_t ab_format;  // instruction-descriptor operand format: 0 = F16, 1 = BF16
 };
+
+template <typename TH> __device__ __forceinline__ float2 h2_to_f2(uint32_t w);
+template <> __device__ __forceinline__ float2 h2_to_f2<__nv_bfloat16>(uint32_t w) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+}
+template <> __device__ __forceinline__ float2 h2_to_f2<__half>(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+template <typename TH> __device__ __forceinline__ uint32_t f2_to_h2(float a, float b);
+template <> __device__ __forceinline__ uint32_t f2_to_h2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+template <> __device__ __forceinline__ uint32_t f2_to_h2<__half>(float a, float b) {
+  __half2 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -114,6 +132,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+template <typename TH>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -181,8 +200,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+      // instruction descriptor: D=f32, A=B=f16|bf16, both K-major, M=128, N=BN
+      const uint32_t idesc = (1u << 4) | (p.ab_format << 7) | (p.ab_format << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -257,21 +276,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 16; ++j) o[j] = f[j];
             if (p.res) {
-              const __nv_bfloat16* rp = p.res + pix * p.res_pitch + ch0;
+              const TH* rp = reinterpret_cast<const TH*>(p.res) + pix * p.res_pitch + ch0;
               if (full16) {
                 const uint4 r0 = *reinterpret_cast<const uint4*>(rp);
                 const uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
                 const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[j]));
+                  const float2 t = h2_to_f2<TH>(rw[j]);
                   o[2 * j] += t.x;
                   o[2 * j + 1] += t.y;
                 }
               } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                  if (ch0 + j < p.Cout) o[j] += __bfloat162float(rp[j]);
+                  if (ch0 + j < p.Cout) o[j] += to_f<TH>(rp[j]);
               }
             }
             if (p.relu) {
@@ -290,20 +309,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   if (ch0 + j < p.Cout) yp[j] = o[j];
               }
             } else {
-              __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.out_pitch + ch0;
+              TH* yp = reinterpret_cast<TH*>(p.y) + pix * p.out_pitch + ch0;
               if (full16) {
                 uint32_t w[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  __nv_bfloat162 t = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
-                  w[j] = *reinterpret_cast<uint32_t*>(&t);
-                }
+                for (int j = 0; j < 8; ++j) w[j] = f2_to_h2<TH>(o[2 * j], o[2 * j + 1]);
                 *reinterpret_cast<uint4*>(yp) = make_uint4(w[0], w[1], w[2], w[3]);
                 *reinterpret_cast<uint4*>(yp + 8) = make_uint4(w[4], w[5], w[6], w[7]);
               } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                  if (ch0 + j < p.Cout) yp[j] = __float2bfloat16_rn(o[j]);
+                  if (ch0 + j < p.Cout) yp[j] = from_f<TH>(o[j]);
               }
             }
           }
@@ -379,8 +395,9 @@ int64_t pack_w_bf16_elems(int Cout, int Cin, int kh, int kw) {
   return (int64_t)t.CoutPad * t.Kp;
 }
 
-// OIHW float -> [CoutPad][taps][cchunks*64] bf16, zero padded
-__global__ void pack_w_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin,
+// OIHW float -> [CoutPad][taps][cchunks*64] half (f16 or bf16), zero padded
+template <typename TH>
+__global__ void pack_w_bf16_kernel(const float* __restrict__ w, TH* __restrict__ out, int Cout, int Cin,
                                    int taps, int cchunks, int CoutPad) {
   const int Kp = taps * cchunks * kKC;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -389,13 +406,16 @@ __global__ void pack_w_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* _
   int tap = k / (cchunks * kKC), c = k - tap * cchunks * kKC;
   float v = 0.f;
   if (o < Cout && c < Cin) v = w[((int64_t)o * Cin + c) * taps + tap];
-  out[i] = __float2bfloat16_rn(v);
+  out[i] = from_f<TH>(v);
 }
 
-int pack_w_bf16_launch(const float* w, void* out, int Cout, int Cin, int kh, int kw, cudaStream_t st) {
+int pack_w_bf16_launch(const float* w, void* out, int Cout, int Cin, int kh, int kw, int dtype, cudaStream_t st) {
   TileCfg t = tile_cfg(Cout, Cin, kh, kw);
   int64_t tot = (int64_t)t.CoutPad * t.Kp;
-  pack_w_bf16_kernel<<<cdiv(tot, 256), 256, 0, st>>>(w, (__nv_bfloat16*)out, Cout, Cin, kh * kw, t.cchunks, t.CoutPad);
+  if (dtype == FAMI_F16)
+    pack_w_bf16_kernel<__half><<<cdiv(tot, 256), 256, 0, st>>>(w, (__half*)out, Cout, Cin, kh * kw, t.cchunks, t.CoutPad);
+  else
+    pack_w_bf16_kernel<__nv_bfloat16><<<cdiv(tot, 256), 256, 0, st>>>(w, (__nv_bfloat16*)out, Cout, Cin, kh * kw, t.cchunks, t.CoutPad);
   FAMI_CHECK_LAUNCH("pack_w_bf16_kernel");
   return 0;
 }
@@ -412,6 +432,7 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   TileCfg t = tile_cfg(d->Cout, d->Cin, d->kh, d->kw);
 
   CUtensorMap tmA, tmB;
+  const CUtensorMapDataType tm_dtype = d->dtype == FAMI_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
     cuuint64_t strides[3] = {(cuuint64_t)d->in_pitch * 2, (cuuint64_t)d->W * d->in_pitch * 2,
@@ -419,7 +440,7 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
     int lower[2] = {-d->pad, -d->pad};
     int upper[2] = {d->pad - (d->kw - 1) * d->dil, d->pad - (d->kh - 1) * d->dil};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
-    CUresult r = g_encode_im2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower,
+    CUresult r = g_encode_im2col(&tmA, tm_dtype, 4, const_cast<void*>(x), dims, strides, lower,
                                  upper, kKC, kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FAMI_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed (%d)", (int)r);
@@ -429,7 +450,7 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
     cuuint64_t strides[1] = {(cuuint64_t)t.Kp * 2};
     cuuint32_t box[2] = {kKC, (cuuint32_t)t.BN};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box,
+    CUresult r = g_encode_tiled(&tmB, tm_dtype, 2, const_cast<void*>(w), dims, strides, box,
                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FAMI_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -449,7 +470,8 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   const size_t osz = out_f32 ? 4 : 2;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((d->out_pitch * osz) % 16 == 0) &&
              (!res || (((reinterpret_cast<uintptr_t>(res) & 15) == 0) && (d->res_pitch % 8 == 0)));
-  p.scale = scale; p.shift = shift; p.res = (const __nv_bfloat16*)res; p.y = y;
+  p.scale = scale; p.shift = shift; p.res = res; p.y = y;
+  p.ab_format = d->dtype == FAMI_F16 ? 0u : 1u;
 
   const int stage_bytes = kABytes + t.BN * 128;
   int stages = (200 * 1024) / stage_bytes;
@@ -459,13 +481,17 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 4) * 8 + 16;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_done = true;
   }
   int grid = p.m_tiles * p.n_tiles;
   const int sms = num_sms();
   if (grid > sms) grid = sms;
-  conv_tc_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  if (d->dtype == FAMI_F16)
+    conv_tc_kernel<__half><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  else
+    conv_tc_kernel<__nv_bfloat16><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   FAMI_CHECK_LAUNCH("conv_tc_kernel");
   return 0;
 }

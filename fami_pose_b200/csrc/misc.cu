@@ -136,7 +136,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float
 
 // per-channel sum / sum-of-squares over rows of an NHWC activation (train-mode BN on the tensor-core path)
 template <typename T>
-__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, int pitch, int64_t rows, int C,
+__global__ void __launch_bounds__(1024) bn_stats_kernel(const T* __restrict__ x, int pitch, int64_t rows, int C,
                                                         double* __restrict__ stats, int rows_per_block) {
   extern __shared__ float sm[];
   const int RG = blockDim.x / C;
@@ -320,8 +320,10 @@ __global__ void __launch_bounds__(1024) argmax_hw_kernel(const T* __restrict__ h
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-#define DISPATCH_T(dtype, ...)                         \
-  if ((dtype) == FAMI_F32) { using T = float; __VA_ARGS__ } else { using T = __nv_bfloat16; __VA_ARGS__ }
+#define DISPATCH_T(dtype, ...)                                                 \
+  if ((dtype) == FAMI_F32) { using T = float; __VA_ARGS__ }                    \
+  else if ((dtype) == FAMI_F16) { using T = __half; __VA_ARGS__ }              \
+  else { using T = __nv_bfloat16; __VA_ARGS__ }
 
 int nchw_to_nhwc_launch(const float* src, int64_t sns, void* dst, int dt, int N, int C, int H, int W, int pitch,
                         cudaStream_t st) {
@@ -376,6 +378,9 @@ int bn_apply_act_launch(const void* x, int xdt, int xp, const float* scale, cons
   if (xdt == FAMI_F32) {
     DISPATCH_T(dt, bn_apply_act_kernel<float, T><<<cdiv(tot, 256), 256, 0, st>>>(
                        (const float*)x, xp, scale, shift, (const T*)res, rp, (T*)y, yp, N, Ho, Wo, C, up, relu);)
+  } else if (xdt == FAMI_F16) {
+    DISPATCH_T(dt, bn_apply_act_kernel<__half, T><<<cdiv(tot, 256), 256, 0, st>>>(
+                       (const __half*)x, xp, scale, shift, (const T*)res, rp, (T*)y, yp, N, Ho, Wo, C, up, relu);)
   } else {
     DISPATCH_T(dt, bn_apply_act_kernel<__nv_bfloat16, T><<<cdiv(tot, 256), 256, 0, st>>>(
                        (const __nv_bfloat16*)x, xp, scale, shift, (const T*)res, rp, (T*)y, yp, N, Ho, Wo, C, up, relu);)

@@ -11,16 +11,21 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, ConvDesc, DcnDesc
+from ._lib import BF16, F16, F32, ConvDesc, DcnDesc
 
 _PRECISION = "fp32"
 
 
+_DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
+
+
 def set_precision(p):
-    """'fp32' (exact-fp32 SIMT kernels, 1e-3 parity arm) or 'bf16' (tcgen05 tensor-core arm)."""
+    """'fp32': exact-fp32 SIMT kernels (1e-3 parity arm).  'fp16' / 'bf16': tcgen05 tensor-core arm
+    with 16-bit activations (fp32 accumulation, fp32 offsets/masks/heatmaps); fp16 carries 3 more
+    mantissa bits than bf16 at the same tensor-core rate and is the default tensor arm."""
     global _PRECISION
-    if p not in ("fp32", "bf16"):
-        raise ValueError("precision must be 'fp32' or 'bf16'")
+    if p not in _DTYPES:
+        raise ValueError("precision must be one of %s" % sorted(_DTYPES))
     _PRECISION = p
 
 
@@ -29,7 +34,7 @@ def get_precision():
 
 
 def act_dtype():
-    return torch.float32 if _PRECISION == "fp32" else torch.bfloat16
+    return _DTYPES[_PRECISION]
 
 
 def _code(dtype):
@@ -37,6 +42,8 @@ def _code(dtype):
         return F32
     if dtype == torch.bfloat16:
         return BF16
+    if dtype == torch.float16:
+        return F16
     raise TypeError("unsupported activation dtype %s" % dtype)
 
 
@@ -94,7 +101,7 @@ def to_nhwc(x, dtype=None):
     Tensors that already carry channels-last strides (outputs of other fami ops) pass through."""
     _need_cuda(x)
     dtype = dtype or act_dtype()
-    if x.dim() == 4 and is_nhwc(x) and x.dtype in (torch.float32, torch.bfloat16):
+    if x.dim() == 4 and is_nhwc(x) and x.dtype in (torch.float32, torch.bfloat16, torch.float16):
         return x
     if x.dtype != torch.float32:
         raise TypeError("boundary tensors must be float32 NCHW, got %s" % x.dtype)

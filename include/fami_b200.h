@@ -17,8 +17,9 @@
  *   - activations are NHWC ("channels-last": element (n,y,x,c) at ((n*H+y)*W+x)*pitch + c) where
  *     `pitch` >= C is the per-pixel element pitch, so channel slices of a wider buffer (the
  *     reference's torch.cat along dim=1) can be read/written in place.
- *   - dtype: FAMI_F32 activations are float; FAMI_BF16 activations are __nv_bfloat16 (tensor-core
- *     path).  Per-channel scale/shift vectors, biases, loss outputs are always float.
+ *   - dtype: FAMI_F32 activations are float (exact-fp32 SIMT arm); FAMI_F16 / FAMI_BF16 activations
+ *     are __half / __nv_bfloat16 (tcgen05 tensor-core arm; "half" below means either 16-bit type).
+ *     Per-channel scale/shift vectors, biases, loss outputs are always float.
  */
 #ifndef FAMI_B200_H_
 #define FAMI_B200_H_
@@ -31,7 +32,7 @@ extern "C" {
 
 #define FAMI_ABI_VERSION 1
 
-enum { FAMI_F32 = 0, FAMI_BF16 = 1 };
+enum { FAMI_F32 = 0, FAMI_BF16 = 1, FAMI_F16 = 2 };
 
 /* error text of the last failing call on this thread ("" if none) */
 const char* fami_last_error(void);

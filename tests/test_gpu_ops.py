@@ -323,18 +323,20 @@ TC_CASES = [
 ]
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
 @pytest.mark.parametrize("case", TC_CASES)
-def test_conv_tc_bf16(case):
-    """tcgen05 bf16 conv vs torch CPU fp32 conv on the SAME bf16-rounded operands (so only the
-    accumulation order and the bf16 output rounding differ): tol 1e-2*max|ref| for bf16 outputs
-    (2^-8 rounding), 2e-3*max|ref| for fp32 outputs."""
+def test_conv_tc_half(case, prec):
+    """tcgen05 16-bit conv vs torch CPU fp32 conv on the SAME rounded operands (so only the
+    accumulation order and the output rounding differ): tol 1e-2*max|ref| for bf16 outputs
+    (2^-8 rounding), 2e-3*max|ref| for fp16 / fp32 outputs."""
     import fami_pose_b200 as m
     from fami_pose_b200 import ops
-    m.set_precision("bf16")
+    m.set_precision(prec)
+    hdt = ops.act_dtype()
     try:
         Cin, Cout, k, s, p, d, H, W, N, bias, bn, relu, res, up, out_f32 = case
         g = torch.Generator().manual_seed(abs(hash(case)) % (2 ** 31))
-        rb = lambda t: t.bfloat16().float()
+        rb = lambda t: t.to(hdt).float()
         x = rb(torch.randn(N, Cin, H, W, generator=g))
         conv = torch.nn.Conv2d(Cin, Cout, k, s, p, d, bias=bias)
         with torch.no_grad():
@@ -360,15 +362,15 @@ def test_conv_tc_bf16(case):
                 y = y + r
             if relu:
                 y = F.relu(y)
-        xd = ops.to_nhwc(x.to(DEV), torch.bfloat16)
-        rd = ops.to_nhwc(r.to(DEV), torch.bfloat16) if res else None
+        xd = ops.to_nhwc(x.to(DEV), hdt)
+        rd = ops.to_nhwc(r.to(DEV), hdt) if res else None
         out = ops.conv_bn_act(xd, conv.to(DEV), bnm.to(DEV) if bn else None, relu=relu, residual=rd, up=up,
                               out_dtype=torch.float32 if out_f32 else None)
-        assert out.dtype == (torch.float32 if out_f32 else torch.bfloat16)
+        assert out.dtype == (torch.float32 if out_f32 else hdt)
         got = ops.to_nchw(out).cpu()
-        tol = (2e-3 if out_f32 else 1e-2) * float(y.abs().max()) + 1e-3
+        tol = (2e-3 if (out_f32 or prec == 'fp16') else 1e-2) * float(y.abs().max()) + 1e-3
         err = float((got - y).abs().max())
-        print("tc conv", case, "err", err, "tol", tol)
+        print("tc conv", prec, case, "err", err, "tol", tol)
         assert err <= tol
     finally:
         m.set_precision("fp32")
