@@ -130,10 +130,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fami", choices=["fami", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
-    ap.add_argument("--precision", default=os.environ.get("FAMI_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("FAMI_PRECISION", "fp16"), choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--ref-batch", type=int, default=2)
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run ONE eager step between cudaProfilerStart/Stop (ncu --profile-from-start off) and exit")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 5:
@@ -181,6 +183,16 @@ def main():
         return loss, idx
 
     stream = torch.cuda.Stream(device=dev)
+    if args.profile_step:
+        with torch.no_grad(), torch.cuda.stream(stream):
+            for _ in range(2):
+                step_fn(kf_d, sup_d, tgt_d, tw_d)
+            stream.synchronize()
+            torch.cuda.profiler.start()
+            step_fn(kf_d, sup_d, tgt_d, tw_d)
+            stream.synchronize()
+            torch.cuda.profiler.stop()
+        return
     graph = None
     with torch.no_grad(), torch.cuda.stream(stream):
         step_fn(kf_d, sup_d, tgt_d, tw_d)           # builds packed-weight / folded-BN caches
@@ -254,7 +266,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.precision], "data": "synthetic",
             "config": {"workload": "BASELINE config 2: Alignment_V15 HRNet-W48 384x288, 5-frame window, 17 joints, "
                                    "batch 32 per GPU; forward (eval-mode BN) + JointsMSE + keypoint argmax",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d (clips shard by batch)" % world,

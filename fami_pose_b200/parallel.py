@@ -1,0 +1,95 @@
+"""Data-parallel plumbing: one process per GPU, clips shard by batch, per-replica
+BatchNorm (the reference's DataParallel semantics, engine/defaults/trainer.py:58), and ONE bucketed
+gradient all-reduce per step over NCCL (NVLink 5 / NVSwitch).  Forward/eval needs no collective.
+
+torch.distributed is plumbing here: NCCL on GPUs, gloo on CPU for the world_size-2 host-logic tests.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend=None):
+    """Initialises the default process group from RANK / WORLD_SIZE / MASTER_* (torchrun).  Returns
+    (rank, world, local_rank).  No-op for a single process."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend, **kw)
+    return rank, world, local
+
+
+def shard_range(global_batch, rank, world):
+    """[start, stop) of this rank's clips: global batch = per-GPU batch x #GPUs
+    (datasets/zoo/build.py:40 semantics); remainders go to the lowest ranks."""
+    base, rem = divmod(global_batch, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def rank_seed(base_seed, rank):
+    """Per-rank synthetic-data seed (seed = base + rank)."""
+    return int(base_seed) + int(rank)
+
+
+class GradBuckets:
+    """Flat gradient buckets: grads of the trainable parameters are views into a few contiguous
+    buffers so that the whole exchange is `len(buckets)` all-reduce calls (reference default: only
+    the 1.06 M alignment-head parameters are trainable -> one 4.2 MB bucket)."""
+
+    def __init__(self, params, bucket_bytes=64 << 20):
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets = []
+        cur, cur_bytes = [], 0
+        for p in self.params:
+            nb = p.numel() * p.element_size()
+            if cur and cur_bytes + nb > bucket_bytes:
+                self.buckets.append(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nb
+        if cur:
+            self.buckets.append(cur)
+        self.flat = []
+        for b in self.buckets:
+            n = sum(p.numel() for p in b)
+            buf = torch.zeros(n, dtype=b[0].dtype, device=b[0].device)
+            off = 0
+            for p in b:
+                p.grad = buf[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            self.flat.append(buf)
+
+    def zero(self):
+        for f in self.flat:
+            f.zero_()
+
+    def allreduce_mean(self, async_op=False):
+        """sum over ranks / world, in place, one collective per bucket."""
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return []
+        world = dist.get_world_size()
+        works = []
+        for f in self.flat:
+            f.div_(world)
+            w = dist.all_reduce(f, op=dist.ReduceOp.SUM, async_op=async_op)
+            if async_op:
+                works.append(w)
+        return works
+
+
+def max_over_ranks(value, device):
+    """Timing helper: the max over ranks of a python float (device-side all-reduce)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
