@@ -2,6 +2,7 @@
 // here; kernels live in conv_simt.cu / conv_tc.cu / dcn.cu / misc.cu.
 #include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -39,6 +40,9 @@ int conv_bf16_tc_supported(const fami_conv_desc* d);
 int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale,
                         const float* shift, const void* res, void* y, double* stats, cudaStream_t st);
 int64_t pack_w_bf16_elems(int Cout, int Cin, int kh, int kw);
+int conv_halo_supported(const fami_conv_desc* d);
+int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
+                     const void* res, void* y, cudaStream_t st);
 int pack_w_bf16_launch(const float* w, void* out, int Cout, int Cin, int kh, int kw, int dtype, cudaStream_t st);
 int dcn_bwd_launch(const fami_dcn_desc* d, const float* x, const float* off, const float* mask, const float* w,
                    const float* go, float* gx, float* goff, float* gmask, float* gw, float* gb, cudaStream_t st);
@@ -59,6 +63,7 @@ int joint_mse_launch(const void*, int, int, const float*, const float*, float*, 
                      cudaStream_t);
 int softmax_pkl_launch(const void*, int, const void*, int, int, float*, int, int, int, float, cudaStream_t);
 int argmax_hw_launch(const void*, int, int, int32_t*, float*, int, int, int, cudaStream_t);
+int debug_umma_rowshift_launch(const void*, const void*, float*, int, int, int, cudaStream_t);
 
 }  // namespace fami
 
@@ -132,6 +137,9 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
     FAMI_CHECK_ARG(d->out_dtype == d->dtype || d->out_dtype == FAMI_F32,
                    "fami_conv2d_bn_act_fwd: half-precision conv output must be the same half type or fp32");
     FAMI_CHECK_ARG(conv_bf16_tc_supported(d), "fami_conv2d_bn_act_fwd: shape not supported by the bf16 tensor path");
+    static const bool halo_off = getenv("FAMI_DISABLE_HALO") != nullptr;
+    if (!halo_off && !d->stats && conv_halo_supported(d))
+      return conv_halo_launch(d, x, w_packed, scale, shift, residual, y, (cudaStream_t)stream);
     return conv_bf16_tc_launch(d, x, w_packed, scale, shift, residual, y, stats_out, (cudaStream_t)stream);
   }
   return conv_f32_launch(d, (const float*)x, (const float*)w_packed, scale, shift, residual, y, stats_out,
@@ -273,6 +281,13 @@ int fami_argmax_hw(const void* hm, int dtype, int pitch, int32_t* idx_out, float
   FAMI_CHECK_ARG(valid_dtype(dtype), "fami_argmax_hw: bad dtype");
   FAMI_CHECK_ARG(B > 0 && HW > 0 && J > 0 && J <= 1024 && pitch >= J, "fami_argmax_hw: bad shape");
   return argmax_hw_launch(hm, dtype, pitch, idx_out, maxval_out, B, HW, J, (cudaStream_t)stream);
+}
+
+/* hardware probe used by tools/probe_umma.py (not part of the product path) */
+int fami_debug_umma_rowshift(const void* x_f16, const void* w_f16, float* out, int R, int shift, int mode,
+                             void* stream) {
+  FAMI_CHECK_ARG(x_f16 && w_f16 && out, "fami_debug_umma_rowshift: null pointer");
+  return debug_umma_rowshift_launch(x_f16, w_f16, out, R, shift, mode, (cudaStream_t)stream);
 }
 
 }  // extern "C"

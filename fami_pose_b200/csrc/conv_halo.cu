@@ -1,0 +1,430 @@
+// 3x3 stride-1 "same" convolution (pad == dil) on tcgen05 with the input tile staged ONCE in shared
+// memory (halo form).  This is the kernel for the HRNet BasicBlock convs (84 % of the model's FLOPs)
+// and the dilated offset/mask convs of the alignment head.
+//
+// Why: the TMA-im2col form (conv_tc.cu) fetches every activation byte 9x from L2 and re-streams the
+// weights for every 128-pixel tile; measured, it saturates the L2->SM fabric (~25 B/clk/SM) at 12-32 %
+// tensor utilisation.  Here one TMA *tiled* box load brings (BH+2d) x (W+2d) pixels x 64 channels
+// (zero-filled outside the image / beyond Cin) into a 128B-swizzled tile whose rows are the
+// flattened, width-padded pixel positions.  With that layout filter tap (r,s) of output position q is
+// simply row  q + (r*Wp + s)*d : the nine taps are nine UMMA A-descriptors with shifted start
+// addresses into the SAME tile (the hardware applies the 128B swizzle on absolute address bits, so
+// any 128-byte row shift is legal -- established by tools/probe_umma.py).  Outputs are computed for
+// all Wp = W+2d columns of BH rows (NM = ceil(BH*Wp/128) UMMA M-tiles sharing every B tile); the 2d
+// padded columns per row are discarded by the epilogue.  Weights are either resident in shared
+// memory for the whole kernel (narrow convs) or streamed once per CTA tile and shared by the NM
+// M-tiles.
+//
+// Warp roles (320 threads, persistent): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
+// warps 2-9 epilogue (two warps per TMEM lane quarter, alternating M-tiles).
+#include "tc_common.cuh"
+
+namespace fami {
+
+namespace {
+
+constexpr int kHThreads = 320;
+constexpr int kEpiThreads = 256;
+
+struct HaloParams {
+  int N, H, W, Wp, d;        // image count/size, padded width W+2d, dilation (= padding)
+  int BH, NM, HR;            // rows per CTA tile, M-tiles per CTA tile, smem rows per A stage
+  int tiles_per_img, n_tiles, total_tiles;
+  int cchunks, last_kk;
+  int Cout, BN;
+  int relu, out_f32, vec_ok;
+  int out_pitch, res_pitch;
+  int sA, sB, b_resident, acc_bufs;
+  uint32_t a_stage_bytes, b_tile_bytes, a_box_bytes;
+  uint32_t ab_format;
+  const float* scale;
+  const float* shift;
+  const void* res;
+  void* y;
+};
+
+template <typename TH>
+__global__ void __launch_bounds__(kHThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int ksteps = 9 * p.cchunks;
+  const int nB = p.b_resident ? ksteps : p.sB;
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + (size_t)p.sA * p.a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + (size_t)nB * p.b_tile_bytes);
+  const uint32_t bar0 = smem_u32(bars);
+  // barriers: fullA[sA] emptyA[sA] fullB[nBbar] emptyB[nBbar] tfull[2] tempty[2]
+  const int nBbar = p.b_resident ? 1 : p.sB;
+  auto fullA = [&](int s) { return bar0 + 8u * s; };
+  auto emptyA = [&](int s) { return bar0 + 8u * (p.sA + s); };
+  auto fullB = [&](int s) { return bar0 + 8u * (2 * p.sA + s); };
+  auto emptyB = [&](int s) { return bar0 + 8u * (2 * p.sA + nBbar + s); };
+  auto tfull = [&](int a) { return bar0 + 8u * (2 * p.sA + 2 * nBbar + a); };
+  auto tempty = [&](int a) { return bar0 + 8u * (2 * p.sA + 2 * nBbar + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.sA + 2 * nBbar + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.sA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < nBbar; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), kEpiThreads); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int acc_cols = p.NM * p.BN;     // TMEM columns of one accumulator set
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      if (p.b_resident) {
+        // all weights of this conv (single N tile) stay in shared memory for the whole kernel
+        mbar_arrive_expect_tx(fullB(0), (uint32_t)ksteps * p.b_tile_bytes);
+        for (int ks = 0; ks < ksteps; ++ks)
+          tma_tiled_2d(smem_u32(smemB + (size_t)ks * p.b_tile_bytes), &tmB, fullB(0), ks * 64, 0);
+      }
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int t2 = tile / p.n_tiles;
+        const int ty = t2 % p.tiles_per_img, img = t2 / p.tiles_per_img;
+        const int y0 = ty * p.BH;
+        for (int cc = 0; cc < p.cchunks; ++cc) {
+          mbar_wait(emptyA(sa), pa ^ 1u);
+          mbar_arrive_expect_tx(fullA(sa), p.a_box_bytes);
+          tma_tiled_4d(smem_u32(smemA + (size_t)sa * p.a_stage_bytes), &tmA, fullA(sa), cc * 64, -p.d, y0 - p.d, img);
+          if (++sa == p.sA) { sa = 0; pa ^= 1u; }
+          if (!p.b_resident) {
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(emptyB(sb), pb ^ 1u);
+              mbar_arrive_expect_tx(fullB(sb), p.b_tile_bytes);
+              tma_tiled_2d(smem_u32(smemB + (size_t)sb * p.b_tile_bytes), &tmB, fullB(sb), (tap * p.cchunks + cc) * 64,
+                           nt * p.BN);
+              if (++sb == p.sB) { sb = 0; pb ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (p.ab_format << 7) | (p.ab_format << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      if (p.b_resident) { mbar_wait(fullB(0), 0); tc_fence_after(); }
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int acc = (p.acc_bufs == 2) ? (it & 1) : 0;
+        const uint32_t acc_phase = (p.acc_bufs == 2) ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
+        mbar_wait(tempty(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
+        for (int cc = 0; cc < p.cchunks; ++cc) {
+          mbar_wait(fullA(sa), pa);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smemA + (size_t)sa * p.a_stage_bytes);
+          const int nk = (cc == p.cchunks - 1) ? p.last_kk : 4;
+          for (int tap = 0; tap < 9; ++tap) {
+            uint32_t b_addr;
+            if (p.b_resident) {
+              b_addr = smem_u32(smemB + (size_t)(tap * p.cchunks + cc) * p.b_tile_bytes);
+            } else {
+              mbar_wait(fullB(sb), pb);
+              tc_fence_after();
+              b_addr = smem_u32(smemB + (size_t)sb * p.b_tile_bytes);
+            }
+            const uint64_t bdesc = make_sw128_desc(b_addr);
+            const int fr = tap / 3, fs = tap - fr * 3;
+            const uint32_t row_shift = (uint32_t)((fr * p.Wp + fs) * p.d);
+            for (int m = 0; m < p.NM; ++m) {
+              const uint64_t adesc = make_sw128_desc(a_base + ((uint32_t)(m * 128) + row_shift) * 128u);
+              for (int k = 0; k < nk; ++k)
+                umma_bf16(d_tmem + (uint32_t)(m * p.BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                          (cc | tap | k) ? 1u : 0u);
+            }
+            if (!p.b_resident) {
+              umma_commit(emptyB(sb));
+              if (++sb == p.sB) { sb = 0; pb ^= 1u; }
+            }
+          }
+          umma_commit(emptyA(sa));
+          if (++sa == p.sA) { sa = 0; pa ^= 1u; }
+        }
+        umma_commit(tfull(acc));
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    const int e = warp - 2;
+    const int quarter = warp & 3;
+    const int half = e >> 2;
+    const int row = quarter * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = (p.acc_bufs == 2) ? (it & 1) : 0;
+      const uint32_t acc_phase = (p.acc_bufs == 2) ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
+      const int nt = tile % p.n_tiles;
+      const int t2 = tile / p.n_tiles;
+      const int ty = t2 % p.tiles_per_img, img = t2 / p.tiles_per_img;
+      const int y0 = ty * p.BH;
+      mbar_wait(tfull(acc), acc_phase);
+      tc_fence_after();
+      for (int m = half; m < p.NM; m += 2) {
+        const int q = m * 128 + row;
+        const int yy = q / p.Wp, xx = q - yy * p.Wp;
+        const bool valid = (yy < p.BH) && (xx < p.W) && (y0 + yy < p.H);
+        const int64_t pix = ((int64_t)img * p.H + (y0 + yy)) * p.W + xx;
+        const uint32_t t_addr = tmem_base + (uint32_t)(acc * acc_cols + m * p.BN) + ((uint32_t)(quarter * 32) << 16);
+        for (int g0 = 0; g0 < p.BN; g0 += 64) {
+          const int gcols = (p.BN - g0 < 64) ? (p.BN - g0) : 64;
+          // prefetch the residual of this column group (independent of the accumulator)
+          uint4 rpre[8];
+          const int chg = nt * p.BN + g0;
+          const bool grp_vec = valid && p.res && p.vec_ok && (chg + gcols <= p.Cout);
+          if (grp_vec) {
+            const TH* rp = reinterpret_cast<const TH*>(p.res) + pix * p.res_pitch + chg;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j * 8 < gcols) rpre[j] = __ldg(reinterpret_cast<const uint4*>(rp + j * 8));
+          }
+#pragma unroll
+          for (int cj = 0; cj < 4; ++cj) {
+            const int c0 = g0 + cj * 16;
+            if (c0 >= p.BN) break;
+            uint32_t v[16];
+            tmem_ld16(t_addr + (uint32_t)c0, v);
+            tmem_ld_wait();
+            const int ch0 = nt * p.BN + c0;
+            if (!valid || ch0 >= p.Cout) continue;
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = ch0 + j;
+              const float sc = (p.scale && c < p.Cout) ? __ldg(p.scale + c) : 1.f;
+              const float sh = (p.shift && c < p.Cout) ? __ldg(p.shift + c) : 0.f;
+              o[j] = fmaf(__uint_as_float(v[j]), sc, sh);
+            }
+            const bool full16 = (ch0 + 16 <= p.Cout) && p.vec_ok;
+            if (p.res) {
+              if (grp_vec) {
+                const uint4 r0 = rpre[2 * cj], r1 = rpre[2 * cj + 1];
+                const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float2 t = h2_to_f2<TH>(rw[j]);
+                  o[2 * j] += t.x;
+                  o[2 * j + 1] += t.y;
+                }
+              } else {
+                const TH* rp = reinterpret_cast<const TH*>(p.res) + pix * p.res_pitch + ch0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (ch0 + j < p.Cout) o[j] += to_f<TH>(rp[j]);
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+            }
+            if (p.out_f32) {
+              float* yp = reinterpret_cast<float*>(p.y) + pix * p.out_pitch + ch0;
+              if (full16) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  *reinterpret_cast<float4*>(yp + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (ch0 + j < p.Cout) yp[j] = o[j];
+              }
+            } else {
+              TH* yp = reinterpret_cast<TH*>(p.y) + pix * p.out_pitch + ch0;
+              if (full16) {
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] = f2_to_h2<TH>(o[2 * j], o[2 * j + 1]);
+                *reinterpret_cast<uint4*>(yp) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(yp + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (ch0 + j < p.Cout) yp[j] = from_f<TH>(o[j]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+struct HaloCfg {
+  int BN, n_tiles, CoutPad, cchunks;
+  int BH, NM, HR, sA, sB, b_resident, acc_bufs;
+  size_t smem;
+  bool ok;
+};
+
+constexpr size_t kSmemBudget = 220 * 1024;
+
+// Chooses the CTA tile: BH image rows (NM = ceil(BH*Wp/128) M-tiles).  Preference: double-buffered
+// accumulators, high fraction of useful MMA rows, weights resident if they fit.
+HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d) {
+  HaloCfg best;
+  best.ok = false;
+  const int Wp = W + 2 * d;
+  if (Wp > 256) return best;
+  int n_tiles = (Cout + 255) / 256;
+  int per = (Cout + n_tiles - 1) / n_tiles;
+  int BN = ((per + 15) / 16) * 16;
+  const int cchunks = (Cin + 63) / 64;
+  const int ksteps = 9 * cchunks;
+  double best_score = -1;
+  for (int NM = 1; NM <= 8; ++NM) {
+    if (NM * BN > 512) break;
+    int BH = (NM * 128) / Wp;
+    if (BH < 1) continue;
+    if (BH > H) BH = H;
+    if (BH + 2 * d > 256) continue;
+    const int nm = (BH * Wp + 127) / 128;   // actual M-tiles needed for BH rows
+    const int acc_bufs = (2 * nm * BN <= 512) ? 2 : 1;
+    int HR = nm * 128 + (2 * Wp + 2) * d;
+    const int box_rows = (BH + 2 * d) * Wp;
+    if (HR < box_rows) HR = box_rows;
+    HR = ((HR + 7) / 8) * 8;
+    const size_t a_stage = (size_t)HR * 128;
+    const size_t b_tile = (size_t)BN * 128;
+    const size_t b_all = b_tile * ksteps;
+    for (int resident = 1; resident >= 0; --resident) {
+      if (resident && n_tiles != 1) continue;
+      size_t bbytes;
+      int sB;
+      if (resident) { bbytes = b_all; sB = 0; }
+      else { sB = 4; bbytes = b_tile * sB; }
+      for (int sA = 2; sA >= 1; --sA) {
+        size_t smem = a_stage * sA + bbytes + 1024 + 256;
+        if (smem > kSmemBudget) continue;
+        const int tiles_per_img = (H + BH - 1) / BH;
+        const double eff = (double)H * W / ((double)tiles_per_img * nm * 128);
+        if (eff < 0.7) continue;   // small maps waste too many MMA rows here: the im2col kernel takes them
+        // feed cost model (bytes per useful output pixel), lower is better
+        const double a_bytes = (double)box_rows * 128.0 * cchunks;
+        const double b_bytes = resident ? 0.0 : (double)b_all;
+        const double feed = (a_bytes + b_bytes) / ((double)BH * W);
+        double score = eff / feed * (acc_bufs == 2 ? 1.0 : 0.8) * (sA == 2 ? 1.0 : 0.85);
+        if (score > best_score) {
+          best_score = score;
+          best.ok = true;
+          best.BN = BN; best.n_tiles = n_tiles; best.CoutPad = BN * n_tiles; best.cchunks = cchunks;
+          best.BH = BH; best.NM = nm; best.HR = HR; best.sA = sA; best.sB = resident ? 1 : sB;
+          best.b_resident = resident; best.acc_bufs = acc_bufs; best.smem = smem;
+        }
+        break;  // largest sA that fits for this (NM, resident)
+      }
+    }
+  }
+  return best;
+}
+
+}  // namespace
+
+int conv_halo_supported(const fami_conv_desc* d) {
+  if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != d->dil || d->up != 1) return 0;
+  if (d->Cin % 16 != 0 || d->in_pitch % 8 != 0) return 0;
+  if (d->dil < 1 || d->dil > 8) return 0;
+  return halo_cfg(d->H, d->W, d->Cin, d->Cout, d->dil).ok ? 1 : 0;
+}
+
+int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
+                     const void* res, void* y, cudaStream_t st) {
+  FAMI_CHECK_ARG(load_driver_fns(), "cuTensorMapEncode* driver entry points unavailable");
+  HaloCfg c = halo_cfg(d->H, d->W, d->Cin, d->Cout, d->dil);
+  FAMI_CHECK_ARG(c.ok, "conv_halo: no tile configuration fits");
+  const CUtensorMapDataType tm_dtype = d->dtype == FAMI_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const int dl = d->dil, Wp = d->W + 2 * dl;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_pitch * 2, (cuuint64_t)d->W * d->in_pitch * 2,
+                             (cuuint64_t)d->H * d->W * d->in_pitch * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)Wp, (cuuint32_t)(c.BH + 2 * dl), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode_tiled(&tmA, tm_dtype, 4, const_cast<void*>(x), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FAMI_CHECK_ARG(r == CUDA_SUCCESS, "conv_halo: cuTensorMapEncodeTiled(A) failed (%d)", (int)r);
+  }
+  const int Kp = 9 * c.cchunks * 64;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)c.CoutPad};
+    cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)c.BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(&tmB, tm_dtype, 2, const_cast<void*>(w), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FAMI_CHECK_ARG(r == CUDA_SUCCESS, "conv_halo: cuTensorMapEncodeTiled(B) failed (%d)", (int)r);
+  }
+  HaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Wp = Wp; p.d = dl;
+  p.BH = c.BH; p.NM = c.NM; p.HR = c.HR;
+  p.tiles_per_img = (d->H + c.BH - 1) / c.BH;
+  p.n_tiles = c.n_tiles;
+  p.total_tiles = d->N * p.tiles_per_img * c.n_tiles;
+  p.cchunks = c.cchunks;
+  p.last_kk = (d->Cin - (c.cchunks - 1) * 64) / 16;
+  p.Cout = d->Cout; p.BN = c.BN;
+  p.relu = d->relu; p.out_f32 = d->out_dtype == FAMI_F32;
+  const size_t osz = p.out_f32 ? 4 : 2;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((d->out_pitch * osz) % 16 == 0) &&
+             (!res || (((reinterpret_cast<uintptr_t>(res) & 15) == 0) && (d->res_pitch % 8 == 0)));
+  p.out_pitch = d->out_pitch; p.res_pitch = d->res_pitch;
+  p.sA = c.sA; p.sB = c.sB; p.b_resident = c.b_resident; p.acc_bufs = c.acc_bufs;
+  p.a_stage_bytes = (uint32_t)c.HR * 128u;
+  p.b_tile_bytes = (uint32_t)c.BN * 128u;
+  p.a_box_bytes = (uint32_t)((c.BH + 2 * dl) * Wp) * 128u;
+  p.ab_format = d->dtype == FAMI_F16 ? 0u : 1u;
+  p.scale = scale; p.shift = shift; p.res = res; p.y = y;
+
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(conv_halo_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_done = true;
+  }
+  int grid = p.total_tiles;
+  const int sms = num_sms();
+  if (grid > sms) grid = sms;
+  if (d->dtype == FAMI_F16)
+    conv_halo_kernel<__half><<<grid, kHThreads, c.smem, st>>>(tmA, tmB, p);
+  else
+    conv_halo_kernel<__nv_bfloat16><<<grid, kHThreads, c.smem, st>>>(tmA, tmB, p);
+  FAMI_CHECK_LAUNCH("conv_halo_kernel");
+  return 0;
+}
+
+}  // namespace fami

@@ -12,9 +12,7 @@
 // Warp roles (192 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = TMEM owner +
 // single-thread MMA issuer, warps 2-5 = epilogue (tcgen05.ld -> scale/shift (+residual) (+ReLU) ->
 // bf16/fp32 NHWC stores with optional nearest-upsample replication).
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace fami {
 
@@ -41,96 +39,6 @@ struct TcParams {
   void* y;
   uint32_t ab_format;  // instruction-descriptor operand format: 0 = F16, 1 = BF16
 };
-
-template <typename TH> __device__ __forceinline__ float2 h2_to_f2(uint32_t w);
-template <> __device__ __forceinline__ float2 h2_to_f2<__nv_bfloat16>(uint32_t w) {
-  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-}
-template <> __device__ __forceinline__ float2 h2_to_f2<__half>(uint32_t w) {
-  return __half22float2(*reinterpret_cast<const __half2*>(&w));
-}
-template <typename TH> __device__ __forceinline__ uint32_t f2_to_h2(float a, float b);
-template <> __device__ __forceinline__ uint32_t f2_to_h2<__nv_bfloat16>(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-template <> __device__ __forceinline__ uint32_t f2_to_h2<__half>(float a, float b) {
-  __half2 t = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_im2col_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w, int h,
-                                              int n, uint16_t offw, uint16_t offh) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(offw), "h"(offh)
-      : "memory");
-}
-__device__ __forceinline__ void tma_tiled_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row swizzle atoms 1024 B apart.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address  [0,14)
-  d |= (uint64_t)1 << 16;                    // LBO (unused for swizzled K-major) [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;          // SBO = 1024 B [32,46)
-  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <typename TH>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -338,33 +246,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
-                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeIm2colFn g_encode_im2col = nullptr;
-EncodeTiledFn g_encode_tiled = nullptr;
-
-bool load_driver_fns() {
-  if (g_encode_im2col && g_encode_tiled) return true;
-  void* f1 = nullptr;
-  void* f2 = nullptr;
-  cudaDriverEntryPointQueryResult q1, q2;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f1, cudaEnableDefault, &q1) != cudaSuccess ||
-      q1 != cudaDriverEntryPointSuccess)
-    return false;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f2, cudaEnableDefault, &q2) != cudaSuccess ||
-      q2 != cudaDriverEntryPointSuccess)
-    return false;
-  g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(f1);
-  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(f2);
-  return true;
-}
-
 struct TileCfg {
   int BN, n_tiles, CoutPad, cchunks, Kp;
 };
@@ -493,6 +374,100 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   else
     conv_tc_kernel<__nv_bfloat16><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   FAMI_CHECK_LAUNCH("conv_tc_kernel");
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Hardware probe (test infrastructure): does a K-major SWIZZLE_128B UMMA descriptor whose start
+// address is shifted by `shift` 128-byte rows inside a TMA-written tile address rows
+// [shift, shift+128)?  mode 0: base_offset field = 0; mode 1: base_offset = (addr >> 7) & 7.
+// x: f16 [R][64], w: f16 [16][64], out: f32 [128][16] = x[shift:shift+128] @ w^T.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(128, 1)
+umma_rowshift_probe(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, float* out,
+                    int R, int shift, int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sX = smem;                    // R rows x 128 B (R multiple of 8)
+  uint8_t* sW = smem + (size_t)R * 128;  // 16 rows x 128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 16 * 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const uint32_t bar_load = smem_u32(bars), bar_mma = smem_u32(bars + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_load, (uint32_t)(R * 128 + 16 * 128));
+    for (int r0 = 0; r0 < R; r0 += 8) tma_tiled_2d(smem_u32(sX + (size_t)r0 * 128), &tmX, bar_load, 0, r0);
+    tma_tiled_2d(smem_u32(sW), &tmW, bar_load, 0, 0);
+    mbar_wait(bar_load, 0);
+    tc_fence_after();
+    const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a_addr = smem_u32(sX) + (uint32_t)shift * 128u;
+    uint64_t adesc = make_sw128_desc(a_addr);
+    if (mode == 1) adesc |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+    const uint64_t bdesc = make_sw128_desc(smem_u32(sW));
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k ? 1u : 0u);
+    umma_commit(bar_mma);
+  }
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+  uint32_t v[16];
+  tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+  tmem_ld_wait();
+  const int row = warp * 32 + lane;
+  for (int j = 0; j < 16; ++j) out[row * 16 + j] = __uint_as_float(v[j]);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");
+  }
+}
+}  // namespace
+
+int debug_umma_rowshift_launch(const void* x, const void* w, float* out, int R, int shift, int mode, cudaStream_t st) {
+  FAMI_CHECK_ARG(load_driver_fns(), "driver entry points unavailable");
+  FAMI_CHECK_ARG(R % 8 == 0 && R >= 128 + shift + 8 && R <= 1024, "bad R");
+  CUtensorMap tmX, tmW;
+  {
+    cuuint64_t dims[2] = {64, (cuuint64_t)R};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, 8};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FAMI_CHECK_ARG(r == CUDA_SUCCESS, "encode X failed %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {64, 16};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, 16};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FAMI_CHECK_ARG(r == CUDA_SUCCESS, "encode W failed %d", (int)r);
+  }
+  size_t smem = (size_t)R * 128 + 16 * 128 + 1024 + 64;
+  cudaFuncSetAttribute(umma_rowshift_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  umma_rowshift_probe<<<1, 128, smem, st>>>(tmX, tmW, out, R, shift, mode);
+  FAMI_CHECK_LAUNCH("umma_rowshift_probe");
   return 0;
 }
 

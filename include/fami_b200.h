@@ -168,6 +168,13 @@ int fami_softmax_pkl_fwd(const void* a, int a_pitch, const void* b, int b_pitch,
 int fami_argmax_hw(const void* hm, int dtype, int pitch, int32_t* idx_out, float* maxval_out, int B,
                    int HW, int J, void* stream);
 
+/* ---- hardware probe (test infrastructure, tools/probe_umma.py) -------------------------------
+ * out[128][16] = x[shift:shift+128][64] @ w[16][64]^T through one tcgen05 tile whose A descriptor
+ * starts `shift` 128-byte rows into a TMA-written SWIZZLE_128B tile (mode 0: base_offset 0,
+ * mode 1: base_offset = (addr >> 7) & 7).  Establishes the row-shift rule the halo conv relies on. */
+int fami_debug_umma_rowshift(const void* x_f16, const void* w_f16, float* out, int R, int shift, int mode,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

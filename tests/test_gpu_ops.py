@@ -323,8 +323,23 @@ TC_CASES = [
 ]
 
 
+# shapes that take the halo kernel (3x3, stride 1, pad == dil, feature maps large enough)
+HALO_CASES = [
+    (48, 48, 3, 1, 1, 1, 96, 72, 2, False, True, True, True, 1, False),     # stage-4 branch 0 (weights resident)
+    (96, 96, 3, 1, 1, 1, 48, 36, 2, False, True, True, True, 1, False),     # branch 1 (2 chunks, streamed B)
+    (192, 192, 3, 1, 1, 1, 24, 18, 3, False, True, True, True, 1, False),   # branch 2
+    (64, 64, 3, 1, 1, 1, 96, 72, 1, False, True, True, False, 1, False),    # layer1 bottleneck conv2
+    (256, 48, 3, 1, 1, 1, 96, 72, 1, False, True, True, False, 1, False),   # transition1 (4 chunks)
+    (192, 48, 3, 1, 1, 1, 96, 72, 1, False, True, True, False, 1, False),   # sup_agg_block conv1
+    (48, 324, 3, 1, 3, 3, 96, 72, 1, True, False, False, False, 1, True),   # offset|mask conv: dilation 3, 3 N tiles, fp32 out
+    (48, 17, 3, 1, 1, 1, 96, 72, 2, True, False, False, False, 1, True),    # agg_final_layer, fp32 out, Cout 17
+    (48, 48, 3, 1, 1, 1, 50, 37, 3, False, True, True, True, 1, False),     # ragged size (partial last row tile)
+    (32, 32, 3, 1, 1, 1, 80, 60, 2, False, True, True, True, 1, False),     # W32 variant
+]
+
+
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
-@pytest.mark.parametrize("case", TC_CASES)
+@pytest.mark.parametrize("case", TC_CASES + HALO_CASES)
 def test_conv_tc_half(case, prec):
     """tcgen05 16-bit conv vs torch CPU fp32 conv on the SAME rounded operands (so only the
     accumulation order and the output rounding differ): tol 1e-2*max|ref| for bf16 outputs
