@@ -59,6 +59,8 @@ SIGNATURES = {
                                        c_int, c_int, c_int, c_int, c_void_p]),
     "fami_softmax_pkl_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                      c_float, c_void_p]),
+    "fami_debug_read_trace": (c_int, [c_void_p, c_int]),
+    "fami_debug_umma_rate": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "fami_debug_umma_rowshift": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "fami_argmax_hw": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
 }

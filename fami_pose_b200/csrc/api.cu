@@ -63,6 +63,8 @@ int joint_mse_launch(const void*, int, int, const float*, const float*, float*, 
                      cudaStream_t);
 int softmax_pkl_launch(const void*, int, const void*, int, int, float*, int, int, int, float, cudaStream_t);
 int argmax_hw_launch(const void*, int, int, int32_t*, float*, int, int, int, cudaStream_t);
+int debug_read_trace(unsigned long long* host_out, int n);
+int debug_umma_rate_launch(long long* out, int N, int iters, int variant, cudaStream_t st);
 int debug_umma_rowshift_launch(const void*, const void*, float*, int, int, int, cudaStream_t);
 
 }  // namespace fami
@@ -128,7 +130,8 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
   FAMI_CHECK_ARG(d->in_pitch >= d->Cin && d->out_pitch >= d->Cout, "fami_conv2d_bn_act_fwd: pitch < channels");
   FAMI_CHECK_ARG(!residual || d->res_pitch >= d->Cout, "fami_conv2d_bn_act_fwd: res_pitch < Cout");
   FAMI_CHECK_ARG(!d->stats || stats_out, "fami_conv2d_bn_act_fwd: stats requested without stats_out");
-  FAMI_CHECK_ARG((int64_t)d->N * d->Ho * d->Wo < (1ll << 31), "fami_conv2d_bn_act_fwd: too many output pixels");
+  FAMI_CHECK_ARG((int64_t)d->N * d->Ho * d->Wo * d->up * d->up < (1ll << 31),
+                 "fami_conv2d_bn_act_fwd: too many output pixels");
   FAMI_CHECK_ARG(valid_dtype(d->out_dtype), "fami_conv2d_bn_act_fwd: bad out_dtype %d", d->out_dtype);
   /* fp32 input with bf16 output: only the stem (Cin not a multiple of 16), which runs the SIMT kernel */
   FAMI_CHECK_ARG(!(d->dtype == FAMI_F32 && is_half_dtype(d->out_dtype)) || (d->Cin % 16 != 0 && !d->stats),
@@ -281,6 +284,18 @@ int fami_argmax_hw(const void* hm, int dtype, int pitch, int32_t* idx_out, float
   FAMI_CHECK_ARG(valid_dtype(dtype), "fami_argmax_hw: bad dtype");
   FAMI_CHECK_ARG(B > 0 && HW > 0 && J > 0 && J <= 1024 && pitch >= J, "fami_argmax_hw: bad shape");
   return argmax_hw_launch(hm, dtype, pitch, idx_out, maxval_out, B, HW, J, (cudaStream_t)stream);
+}
+
+/* per-role timeline of CTA 0 of the last halo conv launched with FAMI_HALO_TRACE=1 (tools/trace_halo.py) */
+int fami_debug_read_trace(uint64_t* host_out, int n) {
+  FAMI_CHECK_ARG(host_out && n > 0, "fami_debug_read_trace: bad arguments");
+  return debug_read_trace(reinterpret_cast<unsigned long long*>(host_out), n);
+}
+
+/* hardware probe: tcgen05.mma issue/execution rate (tools/probe_umma.py) */
+int fami_debug_umma_rate(int64_t* out, int N, int iters, int variant, void* stream) {
+  FAMI_CHECK_ARG(out, "fami_debug_umma_rate: null pointer");
+  return debug_umma_rate_launch(reinterpret_cast<long long*>(out), N, iters, variant, (cudaStream_t)stream);
 }
 
 /* hardware probe used by tools/probe_umma.py (not part of the product path) */

@@ -15,16 +15,34 @@
 // memory for the whole kernel (narrow convs) or streamed once per CTA tile and shared by the NM
 // M-tiles.
 //
-// Warp roles (320 threads, persistent): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
-// warps 2-9 epilogue (two warps per TMEM lane quarter, alternating M-tiles).
+// Warp roles (512 threads, persistent): warp 0 TMA producer; warps 1-3 MMA issuers, issuer j owning the
+// M-tiles m = j (mod n_iss) -- the per-MMA issue cost of a single thread (~150 clk measured) exceeds the
+// tensor-pipe time of an N=48 MMA (~44 clk), so the M-tiles of a CTA tile are issued from separate warps
+// into separate accumulators; warps 4-15 epilogue (3 column groups x 4 TMEM lane quarters, coalesced
+// through shared-memory staging).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace fami {
 
+// optional per-role timeline of CTA 0 (p.trace != 0; read back with fami_debug_read_trace)
+__device__ unsigned long long g_trace[8192];   // [4 slots][64 tiles][8 events]
+
 namespace {
 
-constexpr int kHThreads = 320;
-constexpr int kEpiThreads = 256;
+__device__ __forceinline__ void trace(int on, int slot, int it, int ev) {
+  if (on && blockIdx.x == 0 && it < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_trace[(slot * 64 + it) * 8 + ev] = t;
+  }
+}
+
+constexpr int kMmaWarps = 3;                       // MMA issuer warps (one per M-tile, see below)
+constexpr int kEpiWarp0 = 1 + kMmaWarps;           // first epilogue warp
+constexpr int kHThreads = 32 * (1 + kMmaWarps + kEpiWarps);
+constexpr int kEpiThreads = 32 * kEpiWarps;
 
 struct HaloParams {
   int N, H, W, Wp, d;        // image count/size, padded width W+2d, dilation (= padding)
@@ -34,9 +52,10 @@ struct HaloParams {
   int Cout, BN;
   int relu, out_f32, vec_ok;
   int out_pitch, res_pitch;
-  int sA, sB, b_resident, acc_bufs;
+  int sA, sB, b_resident, acc_bufs, n_iss;
   uint32_t a_stage_bytes, b_tile_bytes, a_box_bytes;
   uint32_t ab_format;
+  int trace;
   const float* scale;
   const float* shift;
   const void* res;
@@ -63,12 +82,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto tfull = [&](int a) { return bar0 + 8u * (2 * p.sA + 2 * nBbar + a); };
   auto tempty = [&](int a) { return bar0 + 8u * (2 * p.sA + 2 * nBbar + 2 + a); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.sA + 2 * nBbar + 4);
+  float* s_scale = reinterpret_cast<float*>(bars + 2 * p.sA + 2 * nBbar + 6);
+  float* s_shift = s_scale + p.n_tiles * p.BN;
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_shift + p.n_tiles * p.BN) + 15) & ~(uintptr_t)15);
+  fill_scale_shift(s_scale, s_shift, p.scale, p.shift, p.Cout, p.n_tiles * p.BN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.sA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
-    for (int s = 0; s < nBbar; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), kEpiThreads); }
+    for (int s = 0; s < p.sA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), p.n_iss); }
+    for (int s = 0; s < nBbar; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), p.n_iss); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), p.n_iss); mbar_init(tempty(a), kEpiThreads); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
   }
@@ -84,15 +107,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int acc_cols = p.NM * p.BN;     // TMEM columns of one accumulator set
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====
+    {
+      const bool leader = elect_one();
+      if (leader) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      }
       if (p.b_resident) {
         // all weights of this conv (single N tile) stay in shared memory for the whole kernel
-        mbar_arrive_expect_tx(fullB(0), (uint32_t)ksteps * p.b_tile_bytes);
+        if (leader) mbar_arrive_expect_tx(fullB(0), (uint32_t)ksteps * p.b_tile_bytes);
         for (int ks = 0; ks < ksteps; ++ks)
-          tma_tiled_2d(smem_u32(smemB + (size_t)ks * p.b_tile_bytes), &tmB, fullB(0), ks * 64, 0);
+          if (leader) tma_tiled_2d(smem_u32(smemB + (size_t)ks * p.b_tile_bytes), &tmB, fullB(0), ks * 64, 0);
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
@@ -103,24 +129,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int y0 = ty * p.BH;
         for (int cc = 0; cc < p.cchunks; ++cc) {
           mbar_wait(emptyA(sa), pa ^ 1u);
-          mbar_arrive_expect_tx(fullA(sa), p.a_box_bytes);
-          tma_tiled_4d(smem_u32(smemA + (size_t)sa * p.a_stage_bytes), &tmA, fullA(sa), cc * 64, -p.d, y0 - p.d, img);
+          if (leader) {
+            trace(p.trace, 0, (tile - blockIdx.x) / gridDim.x, 0);
+            mbar_arrive_expect_tx(fullA(sa), p.a_box_bytes);
+            tma_tiled_4d(smem_u32(smemA + (size_t)sa * p.a_stage_bytes), &tmA, fullA(sa), cc * 64, -p.d, y0 - p.d, img);
+          }
           if (++sa == p.sA) { sa = 0; pa ^= 1u; }
           if (!p.b_resident) {
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(emptyB(sb), pb ^ 1u);
-              mbar_arrive_expect_tx(fullB(sb), p.b_tile_bytes);
-              tma_tiled_2d(smem_u32(smemB + (size_t)sb * p.b_tile_bytes), &tmB, fullB(sb), (tap * p.cchunks + cc) * 64,
-                           nt * p.BN);
+              if (leader) {
+                mbar_arrive_expect_tx(fullB(sb), p.b_tile_bytes);
+                tma_tiled_2d(smem_u32(smemB + (size_t)sb * p.b_tile_bytes), &tmB, fullB(sb), (tap * p.cchunks + cc) * 64,
+                             nt * p.BN);
+              }
               if (++sb == p.sB) { sb = 0; pb ^= 1u; }
             }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp <= kMmaWarps) {
+   if (warp - 1 < p.n_iss) {
+    const int issuer = warp - 1;
+    // ===================== MMA issuers (warp-uniform control flow, one elected lane issues) ======
+    // Operands of tcgen05.mma live in uniform registers: keeping the whole warp converged lets the
+    // compiler keep descriptors there; issuing from divergent code (if lane == 0) costs 2-3x per MMA.
+    {
+      const bool leader = elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = (1u << 4) | (p.ab_format << 7) | (p.ab_format << 10) | ((uint32_t)(p.BN >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
       int sa = 0, sb = 0;
@@ -130,49 +167,67 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int acc = (p.acc_bufs == 2) ? (it & 1) : 0;
         const uint32_t acc_phase = (p.acc_bufs == 2) ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
+        if (leader && issuer == 0) trace(p.trace, 1, it, 3);
         mbar_wait(tempty(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
+        if (leader && issuer == 0) trace(p.trace, 1, it, 0);
+        const uint32_t d_tmem = tmem_u + (uint32_t)(acc * acc_cols);
         for (int cc = 0; cc < p.cchunks; ++cc) {
           mbar_wait(fullA(sa), pa);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smemA + (size_t)sa * p.a_stage_bytes);
+          if (cc == 0 && leader && issuer == 0) trace(p.trace, 1, it, 1);
+          const uint32_t a_lo0 = sw128_desc_lo(smem_u32(smemA + (size_t)sa * p.a_stage_bytes));
           const int nk = (cc == p.cchunks - 1) ? p.last_kk : 4;
-          for (int tap = 0; tap < 9; ++tap) {
-            uint32_t b_addr;
-            if (p.b_resident) {
-              b_addr = smem_u32(smemB + (size_t)(tap * p.cchunks + cc) * p.b_tile_bytes);
-            } else {
-              mbar_wait(fullB(sb), pb);
-              tc_fence_after();
-              b_addr = smem_u32(smemB + (size_t)sb * p.b_tile_bytes);
-            }
-            const uint64_t bdesc = make_sw128_desc(b_addr);
-            const int fr = tap / 3, fs = tap - fr * 3;
-            const uint32_t row_shift = (uint32_t)((fr * p.Wp + fs) * p.d);
-            for (int m = 0; m < p.NM; ++m) {
-              const uint64_t adesc = make_sw128_desc(a_base + ((uint32_t)(m * 128) + row_shift) * 128u);
-              for (int k = 0; k < nk; ++k)
-                umma_bf16(d_tmem + (uint32_t)(m * p.BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                          (cc | tap | k) ? 1u : 0u);
-            }
-            if (!p.b_resident) {
-              umma_commit(emptyB(sb));
-              if (++sb == p.sB) { sb = 0; pb ^= 1u; }
+          const uint32_t b_step = p.b_tile_bytes >> 4;                      // one B tile, in 16-byte units
+          uint32_t b_res_lo = sw128_desc_lo(smem_u32(smemB)) + (uint32_t)cc * b_step;   // resident: tile (tap*cchunks + cc)
+          const uint32_t b_res_inc = (uint32_t)p.cchunks * b_step;
+          const uint32_t wp8 = (uint32_t)(p.Wp * p.d) * 8u, d8 = (uint32_t)p.d * 8u;    // row shifts in 16-byte units
+          int tap = 0;
+          for (int fr = 0; fr < 3; ++fr) {
+            uint32_t a_tap = a_lo0 + (uint32_t)fr * wp8;
+            for (int fs = 0; fs < 3; ++fs, ++tap, a_tap += d8) {
+              uint32_t b_lo;
+              if (p.b_resident) {
+                b_lo = b_res_lo;
+                b_res_lo += b_res_inc;
+              } else {
+                mbar_wait(fullB(sb), pb);
+                tc_fence_after();
+                b_lo = sw128_desc_lo(smem_u32(smemB + (size_t)sb * p.b_tile_bytes));
+              }
+              const bool acc_first = (cc | tap) != 0;
+              uint32_t a_lo = a_tap + (uint32_t)issuer * 1024u, dcol = d_tmem + (uint32_t)(issuer * p.BN);
+              const uint32_t a_inc = (uint32_t)p.n_iss * 1024u, d_inc = (uint32_t)(p.n_iss * p.BN);
+              for (int m = issuer; m < p.NM; m += p.n_iss, a_lo += a_inc, dcol += d_inc)
+                umma_ksteps_n(nk, leader, dcol, a_lo, b_lo, idesc, acc_first);
+              if (leader && tap < 8 && issuer == 0) trace(p.trace, 3, it, tap);
+              if (!p.b_resident) {
+                if (leader) umma_commit(emptyB(sb));
+                if (++sb == p.sB) { sb = 0; pb ^= 1u; }
+              }
             }
           }
-          umma_commit(emptyA(sa));
+          if (leader) umma_commit(emptyA(sa));
           if (++sa == p.sA) { sa = 0; pa ^= 1u; }
         }
-        umma_commit(tfull(acc));
+        if (leader) umma_commit(tfull(acc));
+        if (leader && issuer == 0) trace(p.trace, 1, it, 2);
+        if (leader && issuer == 0 && p.trace && blockIdx.x == 0 && it < 64) g_trace[(1 * 64 + it) * 8 + 5] = (unsigned long long)clock64();
       }
     }
+   }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
-    const int e = warp - 2;
+    // ===================== epilogue (warps 4..15) =====================
     const int quarter = warp & 3;
-    const int half = e >> 2;
     const int row = quarter * 32 + lane;
+    int col_begin, col_end;
+    epi_col_range(p.BN, (warp - kEpiWarp0) >> 2, col_begin, col_end);
+    EpiArgs ea;
+    ea.spitch = epi_stage_pitch(p.BN, p.out_f32);
+    uint8_t* stage = stage_base + (warp - kEpiWarp0) * 32 * ea.spitch;
+    ea.s_scale = s_scale; ea.s_shift = s_shift; ea.res = p.res; ea.y = p.y;
+    ea.Cout = p.Cout; ea.BN = p.BN; ea.out_pitch = p.out_pitch; ea.res_pitch = p.res_pitch;
+    ea.out_f32 = p.out_f32; ea.relu = p.relu; ea.vec_ok = p.vec_ok; ea.up = 1; ea.Wout = p.W;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = (p.acc_bufs == 2) ? (it & 1) : 0;
@@ -181,95 +236,30 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int t2 = tile / p.n_tiles;
       const int ty = t2 % p.tiles_per_img, img = t2 / p.tiles_per_img;
       const int y0 = ty * p.BH;
-      mbar_wait(tfull(acc), acc_phase);
-      tc_fence_after();
-      for (int m = half; m < p.NM; m += 2) {
+      ea.ch_base = nt * p.BN;
+      if (warp == kEpiWarp0 && lane == 0) trace(p.trace, 2, it, 2);
+      // row -> pixel for M-tile m of this CTA tile
+      auto row_pix = [&](int m, bool& valid) -> int {
         const int q = m * 128 + row;
         const int yy = q / p.Wp, xx = q - yy * p.Wp;
-        const bool valid = (yy < p.BH) && (xx < p.W) && (y0 + yy < p.H);
-        const int64_t pix = ((int64_t)img * p.H + (y0 + yy)) * p.W + xx;
+        valid = (yy < p.BH) && (xx < p.W) && (y0 + yy < p.H);
+        return valid ? (img * p.H + (y0 + yy)) * p.W + xx : 0;
+      };
+      // (a register prefetch of the residual one M-tile ahead was tried and measured SLOWER -- 207 vs
+      //  173 us on the 48->48 conv -- because of the extra live registers; kept simple.)
+      uint4 no_pre[kPre];
+      mbar_wait(tfull(acc), acc_phase);
+      tc_fence_after();
+      if (warp == kEpiWarp0 && lane == 0) trace(p.trace, 2, it, 0);
+      for (int m = 0; m < p.NM; ++m) {
+        bool valid;
+        const int pix = row_pix(m, valid);
         const uint32_t t_addr = tmem_base + (uint32_t)(acc * acc_cols + m * p.BN) + ((uint32_t)(quarter * 32) << 16);
-        for (int g0 = 0; g0 < p.BN; g0 += 64) {
-          const int gcols = (p.BN - g0 < 64) ? (p.BN - g0) : 64;
-          // prefetch the residual of this column group (independent of the accumulator)
-          uint4 rpre[8];
-          const int chg = nt * p.BN + g0;
-          const bool grp_vec = valid && p.res && p.vec_ok && (chg + gcols <= p.Cout);
-          if (grp_vec) {
-            const TH* rp = reinterpret_cast<const TH*>(p.res) + pix * p.res_pitch + chg;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j * 8 < gcols) rpre[j] = __ldg(reinterpret_cast<const uint4*>(rp + j * 8));
-          }
-#pragma unroll
-          for (int cj = 0; cj < 4; ++cj) {
-            const int c0 = g0 + cj * 16;
-            if (c0 >= p.BN) break;
-            uint32_t v[16];
-            tmem_ld16(t_addr + (uint32_t)c0, v);
-            tmem_ld_wait();
-            const int ch0 = nt * p.BN + c0;
-            if (!valid || ch0 >= p.Cout) continue;
-            float o[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c = ch0 + j;
-              const float sc = (p.scale && c < p.Cout) ? __ldg(p.scale + c) : 1.f;
-              const float sh = (p.shift && c < p.Cout) ? __ldg(p.shift + c) : 0.f;
-              o[j] = fmaf(__uint_as_float(v[j]), sc, sh);
-            }
-            const bool full16 = (ch0 + 16 <= p.Cout) && p.vec_ok;
-            if (p.res) {
-              if (grp_vec) {
-                const uint4 r0 = rpre[2 * cj], r1 = rpre[2 * cj + 1];
-                const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float2 t = h2_to_f2<TH>(rw[j]);
-                  o[2 * j] += t.x;
-                  o[2 * j + 1] += t.y;
-                }
-              } else {
-                const TH* rp = reinterpret_cast<const TH*>(p.res) + pix * p.res_pitch + ch0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (ch0 + j < p.Cout) o[j] += to_f<TH>(rp[j]);
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
-            }
-            if (p.out_f32) {
-              float* yp = reinterpret_cast<float*>(p.y) + pix * p.out_pitch + ch0;
-              if (full16) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  *reinterpret_cast<float4*>(yp + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (ch0 + j < p.Cout) yp[j] = o[j];
-              }
-            } else {
-              TH* yp = reinterpret_cast<TH*>(p.y) + pix * p.out_pitch + ch0;
-              if (full16) {
-                uint32_t w[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) w[j] = f2_to_h2<TH>(o[2 * j], o[2 * j + 1]);
-                *reinterpret_cast<uint4*>(yp) = make_uint4(w[0], w[1], w[2], w[3]);
-                *reinterpret_cast<uint4*>(yp + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (ch0 + j < p.Cout) yp[j] = from_f<TH>(o[j]);
-              }
-            }
-          }
-        }
+        if (!(p.trace & 2)) epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix, stage, lane, false, no_pre);
       }
       tc_fence_before();
       mbar_arrive(tempty(acc));
+      if (warp == kEpiWarp0 && lane == 0) trace(p.trace, 2, it, 1);
     }
   }
 
@@ -325,7 +315,7 @@ HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d) {
       if (resident) { bbytes = b_all; sB = 0; }
       else { sB = 4; bbytes = b_tile * sB; }
       for (int sA = 2; sA >= 1; --sA) {
-        size_t smem = a_stage * sA + bbytes + 1024 + 256;
+        size_t smem = a_stage * sA + bbytes + 1024 + 256 + (size_t)kEpiWarps * 32 * (128 + 16) + (size_t)BN * n_tiles * 8;
         if (smem > kSmemBudget) continue;
         const int tiles_per_img = (H + BH - 1) / BH;
         const double eff = (double)H * W / ((double)tiles_per_img * nm * 128);
@@ -355,7 +345,11 @@ int conv_halo_supported(const fami_conv_desc* d) {
   if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != d->dil || d->up != 1) return 0;
   if (d->Cin % 16 != 0 || d->in_pitch % 8 != 0) return 0;
   if (d->dil < 1 || d->dil > 8) return 0;
-  return halo_cfg(d->H, d->W, d->Cin, d->Cout, d->dil).ok ? 1 : 0;
+  // Measured (tools/prof_conv.py, N=160 fp16): the halo form wins when the weights stay resident in
+  // shared memory (Cin <= 64: 48->48 160 us vs 225 us im2col) and loses when they must be re-streamed
+  // per CTA tile (96->96: 146 vs 110 us, 192->192: 109 vs 74 us), so only resident-B shapes come here.
+  HaloCfg c = halo_cfg(d->H, d->W, d->Cin, d->Cout, d->dil);
+  return (c.ok && (c.b_resident || c.n_tiles > 1)) ? 1 : 0;
 }
 
 int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
@@ -404,11 +398,14 @@ int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, cons
              (!res || (((reinterpret_cast<uintptr_t>(res) & 15) == 0) && (d->res_pitch % 8 == 0)));
   p.out_pitch = d->out_pitch; p.res_pitch = d->res_pitch;
   p.sA = c.sA; p.sB = c.sB; p.b_resident = c.b_resident; p.acc_bufs = c.acc_bufs;
+  p.n_iss = c.NM < kMmaWarps ? c.NM : kMmaWarps;
   p.a_stage_bytes = (uint32_t)c.HR * 128u;
   p.b_tile_bytes = (uint32_t)c.BN * 128u;
   p.a_box_bytes = (uint32_t)((c.BH + 2 * dl) * Wp) * 128u;
   p.ab_format = d->dtype == FAMI_F16 ? 0u : 1u;
   p.scale = scale; p.shift = shift; p.res = res; p.y = y;
+  static const bool trace_on = getenv("FAMI_HALO_TRACE") != nullptr;
+  p.trace = trace_on ? atoi(getenv("FAMI_HALO_TRACE")) : 0;
 
   static bool attr_done = false;
   if (!attr_done) {
@@ -425,6 +422,12 @@ int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, cons
     conv_halo_kernel<__nv_bfloat16><<<grid, kHThreads, c.smem, st>>>(tmA, tmB, p);
   FAMI_CHECK_LAUNCH("conv_halo_kernel");
   return 0;
+}
+
+int debug_read_trace(unsigned long long* host_out, int n) {
+  if (n > 8192) n = 8192;
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host_out, g_trace, (size_t)n * sizeof(unsigned long long)) == cudaSuccess ? 0 : 1;
 }
 
 }  // namespace fami

@@ -21,7 +21,7 @@ namespace {
 constexpr int kBM = 128;
 constexpr int kKC = 64;                 // channels per K chunk (128 B of bf16 = one swizzle row)
 constexpr int kABytes = kBM * kKC * 2;  // 16 KB
-constexpr int kThreads = 192;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kAccCols = 256;           // TMEM columns per accumulator buffer
 
 struct TcParams {
@@ -56,11 +56,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * stages + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * stages + 2 + a); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+  float* s_scale = reinterpret_cast<float*>(bars + 2 * stages + 6);
+  float* s_shift = s_scale + p.n_tiles * p.BN;
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_shift + p.n_tiles * p.BN) + 15) & ~(uintptr_t)15);
+  fill_scale_shift(s_scale, s_shift, p.scale, p.shift, p.Cout, p.n_tiles * p.BN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 32 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
   }
@@ -79,10 +83,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int ksteps = p.taps * p.cchunks;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====
+    {
+      const bool leader = elect_one();
+      if (leader) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -95,19 +102,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int fr = tap / p.kw, fs = tap - fr * p.kw;
           for (int cc = 0; cc < p.cchunks; ++cc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
-            const uint32_t a_dst = smem_u32(smem + (size_t)stage * stage_bytes);
-            tma_im2col_4d(a_dst, &tmA, full_bar(stage), cc * kKC, cw, ch, n, (uint16_t)(fs * p.dil),
-                          (uint16_t)(fr * p.dil));
-            tma_tiled_2d(a_dst + kABytes, &tmB, full_bar(stage), (tap * p.cchunks + cc) * kKC, nt * p.BN);
+            if (leader) {
+              mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+              const uint32_t a_dst = smem_u32(smem + (size_t)stage * stage_bytes);
+              tma_im2col_4d(a_dst, &tmA, full_bar(stage), cc * kKC, cw, ch, n, (uint16_t)(fs * p.dil),
+                            (uint16_t)(fr * p.dil));
+              tma_tiled_2d(a_dst + kABytes, &tmB, full_bar(stage), (tap * p.cchunks + cc) * kKC, nt * p.BN);
+            }
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =======
+    {
+      const bool leader = elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       // instruction descriptor: D=f32, A=B=f16|bf16, both K-major, M=128, N=BN
       const uint32_t idesc = (1u << 4) | (p.ab_format << 7) | (p.ab_format << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
       int stage = 0;
@@ -118,120 +129,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
+        const uint32_t d_tmem = tmem_u + (uint32_t)acc * kAccCols;
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t adesc = make_sw128_desc(a_addr);
-          const uint64_t bdesc = make_sw128_desc(a_addr + kABytes);
           const int cc = ks % p.cchunks;
           const int nk = (cc == p.cchunks - 1) ? p.last_kk : 4;
-          for (int k = 0; k < nk; ++k) {
-            // advance 16 bf16 (32 B) along K inside the swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks | k) ? 1u : 0u);
-          }
-          umma_commit(empty_bar(stage));   // frees the smem slot once the MMAs above have read it
+          umma_ksteps_n(nk, leader, d_tmem, sw128_desc_lo(a_addr), sw128_desc_lo(a_addr + kABytes), idesc, ks != 0);
+          if (leader) umma_commit(empty_bar(stage));   // frees the smem slot once the MMAs above have read it
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));       // accumulator complete -> epilogue
+        if (leader) umma_commit(tfull_bar(acc));       // accumulator complete -> epilogue
       }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
-    int it = 0;
+    int col_begin, col_end;
+    epi_col_range(p.BN, (warp - 2) >> 2, col_begin, col_end);
     const int Hout = p.Ho * p.up, Wout = p.Wo * p.up;
+    EpiArgs ea;
+    ea.spitch = epi_stage_pitch(p.BN, p.out_f32);
+    uint8_t* stage = stage_base + (warp - 2) * 32 * ea.spitch;
+    ea.s_scale = s_scale; ea.s_shift = s_shift; ea.res = p.res; ea.y = p.y;
+    ea.Cout = p.Cout; ea.BN = p.BN; ea.out_pitch = p.out_pitch; ea.res_pitch = p.res_pitch;
+    ea.out_f32 = p.out_f32; ea.relu = p.relu; ea.vec_ok = p.vec_ok; ea.up = p.up; ea.Wout = Wout;
+    int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
       const int m = mt * kBM + row;
       const bool valid = m < p.M;
-      int64_t pix0 = 0;
+      int pix0 = 0;
       if (valid) {
         if (p.up == 1) {
           pix0 = m;
         } else {
           const int n = m / p.HoWo, r = m - n * p.HoWo;
           const int yo = r / p.Wo, xo = r - yo * p.Wo;
-          pix0 = ((int64_t)n * Hout + (int64_t)yo * p.up) * Wout + (int64_t)xo * p.up;
+          pix0 = (n * Hout + yo * p.up) * Wout + xo * p.up;
         }
       }
+      ea.ch_base = nt * p.BN;
+      uint4 pre[kPre];
+      const bool have_pre = false;   // register prefetch of the residual measured slower (register pressure)
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)(quarter * 32) << 16);
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_addr + (uint32_t)c0, v);
-        tmem_ld_wait();
-        const int ch0 = nt * p.BN + c0;
-        if (!valid || ch0 >= p.Cout) continue;
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int c = ch0 + j;
-          const float sc = (p.scale && c < p.Cout) ? __ldg(p.scale + c) : 1.f;
-          const float sh = (p.shift && c < p.Cout) ? __ldg(p.shift + c) : 0.f;
-          f[j] = fmaf(__uint_as_float(v[j]), sc, sh);
-        }
-        const bool full16 = (ch0 + 16 <= p.Cout) && p.vec_ok;
-        for (int dy = 0; dy < p.up; ++dy)
-          for (int dx = 0; dx < p.up; ++dx) {
-            const int64_t pix = pix0 + (int64_t)dy * Wout + dx;
-            float o[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = f[j];
-            if (p.res) {
-              const TH* rp = reinterpret_cast<const TH*>(p.res) + pix * p.res_pitch + ch0;
-              if (full16) {
-                const uint4 r0 = *reinterpret_cast<const uint4*>(rp);
-                const uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
-                const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float2 t = h2_to_f2<TH>(rw[j]);
-                  o[2 * j] += t.x;
-                  o[2 * j + 1] += t.y;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (ch0 + j < p.Cout) o[j] += to_f<TH>(rp[j]);
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
-            }
-            if (p.out_f32) {
-              float* yp = reinterpret_cast<float*>(p.y) + pix * p.out_pitch + ch0;
-              if (full16) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  *reinterpret_cast<float4*>(yp + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (ch0 + j < p.Cout) yp[j] = o[j];
-              }
-            } else {
-              TH* yp = reinterpret_cast<TH*>(p.y) + pix * p.out_pitch + ch0;
-              if (full16) {
-                uint32_t w[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) w[j] = f2_to_h2<TH>(o[2 * j], o[2 * j + 1]);
-                *reinterpret_cast<uint4*>(yp) = make_uint4(w[0], w[1], w[2], w[3]);
-                *reinterpret_cast<uint4*>(yp + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (ch0 + j < p.Cout) yp[j] = from_f<TH>(o[j]);
-              }
-            }
-          }
-      }
+      epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix0, stage, lane, have_pre, pre);
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
     }
@@ -355,11 +303,12 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   p.ab_format = d->dtype == FAMI_F16 ? 0u : 1u;
 
   const int stage_bytes = kABytes + t.BN * 128;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (150 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 4) * 8 + 16;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 4) * 8 + 64 +
+                      (size_t)t.CoutPad * 8 + (size_t)kEpiWarps * 32 * (128 + 16);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -468,6 +417,109 @@ int debug_umma_rowshift_launch(const void* x, const void* w, float* out, int R, 
   cudaFuncSetAttribute(umma_rowshift_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   umma_rowshift_probe<<<1, 128, smem, st>>>(tmX, tmW, out, R, shift, mode);
   FAMI_CHECK_LAUNCH("umma_rowshift_probe");
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Hardware probe: back-to-back tcgen05.mma throughput (M=128, K=16, f16) as a function of N and of
+// how the issuing thread builds its descriptors.  out[0] = clock cycles for `iters` MMAs (clock64 around
+// issue + final commit wait), out[1] = cycles for the issue loop alone.
+// variant 0: constant descriptors; 1: descriptors recomputed per MMA from a rotating row shift (as
+// the halo conv does); 2: as 0 but 4 different accumulator column offsets round-robin.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(128, 1) umma_rate_probe(long long* out, int N, int iters, int variant) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                  // 1024 rows x 128 B
+  uint8_t* sB = smem + 1024 * 128;     // 256 rows x 128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 256 * 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const uint32_t bar_mma = smem_u32(bars);
+  for (int i = threadIdx.x; i < (1024 + 256) * 128 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // 1.0h
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {
+    // warp-uniform control flow; a single elected lane issues (variant >= 3) or lane 0 in divergent code
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+    const uint64_t adesc0 = make_sw128_desc(a0), bdesc0 = make_sw128_desc(b0);
+    long long t0 = clock64(), t1 = 0;
+    if (variant >= 3) {
+      const bool leader = elect_one();
+      for (int i = 0; i < iters; ++i) {
+        uint64_t ad = adesc0, bd = bdesc0;
+        uint32_t dt = tm;
+        if (variant >= 6) {
+          // mimic the halo conv issue pattern: tap -> m (3 accumulators) -> k (3 K-steps)
+          const int k = i % 3, m = (i / 3) % 3, tap = (i / 9) % 9;
+          const int fr = tap / 3, fs = tap - fr * 3;
+          ad = make_sw128_desc(a0 + (uint32_t)(m * 128 + fr * 74 + fs) * 128u) + (uint64_t)(2 * k);
+          bd = make_sw128_desc(b0 + (uint32_t)(variant == 8 ? 0 : tap) * (uint32_t)N * 128u % (256u * 128u)) + (uint64_t)(2 * k);
+          dt = tm + (uint32_t)(m * (variant == 7 ? 64 : N));
+        }
+        if (variant == 4) {
+          const uint32_t shift = (uint32_t)((i * 37) & 511);
+          ad = make_sw128_desc(a0 + shift * 128u) + (uint64_t)(2 * (i & 3));
+          bd = bdesc0 + (uint64_t)(2 * (i & 3));
+        }
+        if (variant == 5) dt = tm + (uint32_t)((i & 1) * 256);
+        if (leader) umma_bf16(dt, ad, bd, idesc, i > 1 ? 1u : 0u);
+      }
+      t1 = clock64();
+      if (leader) umma_commit(bar_mma);
+    } else if (threadIdx.x == 0) {
+      for (int i = 0; i < iters; ++i) {
+        if (variant == 1) {
+          const uint32_t shift = (uint32_t)((i * 37) & 511);
+          const uint64_t ad = make_sw128_desc(a0 + shift * 128u) + (uint64_t)(2 * (i & 3));
+          umma_bf16(tmem_base, ad, bdesc0 + (uint64_t)(2 * (i & 3)), idesc, i ? 1u : 0u);
+        } else if (variant == 2) {
+          umma_bf16(tmem_base + (uint32_t)((i & 1) * 256), adesc0, bdesc0, idesc, i > 1 ? 1u : 0u);
+        } else {
+          umma_bf16(tmem_base, adesc0, bdesc0, idesc, i ? 1u : 0u);
+        }
+      }
+      t1 = clock64();
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(bar_mma, 0);
+    long long t2 = clock64();
+    if (threadIdx.x == 0) {
+      out[0] = t2 - t0;
+      out[1] = t1 - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+}  // namespace
+
+int debug_umma_rate_launch(long long* out, int N, int iters, int variant, cudaStream_t st) {
+  FAMI_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && iters > 0, "bad N/iters");
+  size_t smem = (size_t)(1024 + 256) * 128 + 1024 + 64;
+  cudaFuncSetAttribute(umma_rate_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  umma_rate_probe<<<1, 128, smem, st>>>(out, N, iters, variant);
+  FAMI_CHECK_LAUNCH("umma_rate_probe");
   return 0;
 }
 

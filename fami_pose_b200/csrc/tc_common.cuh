@@ -67,6 +67,58 @@ __device__ __forceinline__ void tma_tiled_4d(uint32_t dst, const CUtensorMap* tm
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// ---- lean MMA issue ---------------------------------------------------------------------------
+// Measured on B200 (tools/probe_umma_rate.py): a tcgen05.mma of M=128,K=16 costs max(N/2, ~44) clk in
+// the tensor pipe, but the ISSUE side is easily slower: every uniform-datapath instruction between two
+// MMAs adds to the per-MMA cost (a loop that rebuilds 64-bit descriptors measured 110-190 clk/MMA).
+// So descriptors are kept as (constant high word, 32-bit low word) and only the low word is advanced.
+constexpr uint32_t kSw128DescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO=1024, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t sw128_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool accumulate) {
+  const uint64_t ad = ((uint64_t)kSw128DescHi << 32) | a_lo;
+  const uint64_t bd = ((uint64_t)kSw128DescHi << 32) | b_lo;
+  if (accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc) : "memory");
+  } else {
+    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc) : "memory");
+  }
+}
+// NK K-steps (16 elements = 32 B = +2 in the descriptor address field each) of one (A rows, B tile) pair
+template <int NK>
+__device__ __forceinline__ void umma_ksteps(bool leader, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                            bool first_accumulates) {
+  if (leader) {
+    if (first_accumulates) umma_f16_lo(tmem_d, a_lo, b_lo, idesc, true);
+    else umma_f16_lo(tmem_d, a_lo, b_lo, idesc, false);
+#pragma unroll
+    for (int k = 1; k < NK; ++k) umma_f16_lo(tmem_d, a_lo + 2u * k, b_lo + 2u * k, idesc, true);
+  }
+}
+__device__ __forceinline__ void umma_ksteps_n(int nk, bool leader, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                              uint32_t idesc, bool first_accumulates) {
+  switch (nk) {
+    case 1: umma_ksteps<1>(leader, tmem_d, a_lo, b_lo, idesc, first_accumulates); break;
+    case 2: umma_ksteps<2>(leader, tmem_d, a_lo, b_lo, idesc, first_accumulates); break;
+    case 3: umma_ksteps<3>(leader, tmem_d, a_lo, b_lo, idesc, first_accumulates); break;
+    default: umma_ksteps<4>(leader, tmem_d, a_lo, b_lo, idesc, first_accumulates); break;
+  }
+}
+
+// true in exactly one lane of a fully converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -103,6 +155,220 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+
+// ------------------------------------------------------------------------------------------------
+// Shared epilogue: one warp drains its 32 accumulator rows (TMEM lane quarter) of a 128 x BN tile.
+//   y[pix(row) (+ replica), ch] = act(scale*acc + shift + residual)
+// Direct per-lane global accesses would touch 32 different cache lines per instruction (each lane
+// owns one pixel row), which measured as the bottleneck of both conv kernels.  Instead every column
+// group (64 x 16-bit or 32 x fp32 = 128 B per row) goes through a per-warp shared-memory staging
+// tile with an odd 16-byte row pitch (conflict-free): residual is fetched and the result is written
+// with fully coalesced 16-byte pieces (consecutive lanes -> consecutive addresses).
+// ------------------------------------------------------------------------------------------------
+constexpr int kEpiGroups = 3;                       // epilogue warp groups (column ranges), 4 warps each
+constexpr int kEpiWarps = 4 * kEpiGroups;
+
+// staging row pitch (bytes) for a conv with BN output columns per tile: payload of the widest column
+// range handled by one epilogue group (<= 128 B) + 16 (odd multiple of 16 -> conflict-free rows)
+__host__ __device__ inline int epi_stage_pitch(int BN, int out_f32) {
+  const int chunks = BN >> 4;
+  const int widest = ((chunks + kEpiGroups - 1) / kEpiGroups) << 4;   // columns
+  int bytes = widest * (out_f32 ? 4 : 2);
+  if (bytes > 128) bytes = 128;
+  return bytes + 16;
+}
+
+// fills the per-CTA scale/shift tables (defaults 1 / 0 beyond Cout or when the pointer is null)
+__device__ __forceinline__ void fill_scale_shift(float* s_scale, float* s_shift, const float* scale, const float* shift,
+                                                 int Cout, int CoutPad) {
+  for (int c = threadIdx.x; c < CoutPad; c += blockDim.x) {
+    s_scale[c] = (scale && c < Cout) ? scale[c] : 1.f;
+    s_shift[c] = (shift && c < Cout) ? shift[c] : 0.f;
+  }
+}
+
+// column range [begin,end) of epilogue group g (multiples of 16, as even as possible)
+__device__ __forceinline__ void epi_col_range(int BN, int g, int& begin, int& end) {
+  const int chunks = BN >> 4;
+  const int base = chunks / kEpiGroups, rem = chunks - base * kEpiGroups;
+  const int b = g * base + (g < rem ? g : rem);
+  begin = b << 4;
+  end = (b + base + (g < rem ? 1 : 0)) << 4;
+}
+
+struct EpiArgs {
+  const float* s_scale;   // shared memory, indexed by output channel (CoutPad entries; 1/0 defaults)
+  const float* s_shift;
+  const void* res;        // TH, may be null
+  void* y;                // TH or float
+  int Cout, BN, ch_base;  // ch_base = first output channel of this N tile
+  int out_pitch, res_pitch;
+  int out_f32, relu, vec_ok;
+  int up, Wout;           // nearest-upsample replication (1 = none); Wout = output row width in pixels
+  int spitch;             // staging row pitch in bytes (epi_stage_pitch)
+};
+
+// One warp drains columns [col_begin, col_end) of its 32 accumulator rows.  pix0 = pixel index of this
+// lane's row (first replica); valid = row maps to a real output pixel.
+// Residual prefetch for the FIRST column group of a warp's range (replica 0): issues the coalesced
+// 16-byte loads into registers so their latency overlaps whatever the caller does next (waiting for
+// the accumulator, draining the previous M-tile).  Returns false if this (range, args) combination
+// does not use the vector path -- epilogue_rows then loads the residual itself.
+constexpr int kPre = 4;   // prefetch registers (uint4) per lane: column ranges up to 32 x 16-bit columns
+template <typename TH>
+__device__ __forceinline__ bool epi_prefetch(const EpiArgs& a, int col_begin, int col_end, bool valid, int pix0, int lane,
+                                             uint4 (&rreg)[kPre]) {
+  if (col_begin >= col_end || !a.res) return false;
+  const int gmax = a.out_f32 ? 32 : 64;
+  const int gc = (col_end - col_begin < gmax) ? (col_end - col_begin) : gmax;
+  const int chg = a.ch_base + col_begin;
+  if (!(a.vec_ok && (chg + gc <= a.Cout) && !a.out_f32)) return false;
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  const int ppr = (gc * 2) >> 4;
+  const int lg = ppr <= 2 ? 1 : (ppr <= 4 ? 2 : 3);
+  const int lpr = 1 << lg, rpi = 32 >> lg;
+  if (lpr > kPre) return false;   // wide ranges: no register prefetch
+  const int sub_r = lane >> lg, sub_c = lane & (lpr - 1);
+  const bool lane_on = sub_c < ppr;
+#pragma unroll
+  for (int it = 0; it < kPre; ++it) {
+    if (it < lpr) {
+      const int r = it * rpi + sub_r;
+      const int pr = __shfl_sync(0xffffffffu, pix0, r);
+      rreg[it] = make_uint4(0, 0, 0, 0);
+      if (lane_on && ((vmask >> r) & 1u))
+        rreg[it] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const TH*>(a.res) + (int64_t)pr * a.res_pitch + chg) + sub_c);
+    }
+  }
+  return true;
+}
+
+template <typename TH>
+__device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr, int col_begin, int col_end, bool valid,
+                                              int pix0, uint8_t* stage, int lane, bool have_pre, uint4 (&pre)[kPre]) {
+  if (col_begin >= col_end) return;   // warp-uniform
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  const int esz = a.out_f32 ? 4 : 2;
+  const int gmax = a.out_f32 ? 32 : 64;   // columns per staged group (128 B per row)
+  uint8_t* my_row = stage + lane * a.spitch;
+  for (int g0 = col_begin; g0 < col_end; g0 += gmax) {
+    const int gc = (col_end - g0 < gmax) ? (col_end - g0) : gmax;
+    const int chg = a.ch_base + g0;
+    if (chg >= a.Cout) break;   // warp-uniform
+    const bool grp_vec = a.vec_ok && (chg + gc <= a.Cout) && !(a.res && a.out_f32);
+    // 16-byte pieces per row, mapped with power-of-two lanes per row (no divisions)
+    const int ppr = (gc * esz) >> 4;
+    const int lg = ppr <= 2 ? 1 : (ppr <= 4 ? 2 : 3);
+    const int lpr = 1 << lg;                 // lanes per row
+    const int rpi = 32 >> lg;                // rows per iteration
+    const int sub_r = lane >> lg, sub_c = lane & (lpr - 1);
+    const bool lane_on = sub_c < ppr;
+    for (int dy = 0; dy < a.up; ++dy)
+      for (int dx = 0; dx < a.up; ++dx) {
+        const int pix = pix0 + dy * a.Wout + dx;
+        // ---- 1. residual: coalesced global -> staging ------------------------------------------
+        if (a.res && grp_vec) {
+          uint4 rreg[8];
+          const bool use_pre = have_pre && g0 == col_begin && dy == 0 && dx == 0;   // warp-uniform
+          if (!use_pre) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              if (it < lpr) {
+                const int r = it * rpi + sub_r;
+                const int pr = __shfl_sync(0xffffffffu, pix, r);
+                rreg[it] = make_uint4(0, 0, 0, 0);
+                if (lane_on && ((vmask >> r) & 1u))
+                  rreg[it] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const TH*>(a.res) + (int64_t)pr * a.res_pitch + chg) + sub_c);
+              }
+            }
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            if (it < lpr) {
+              const int r = it * rpi + sub_r;
+              if (lane_on) *reinterpret_cast<uint4*>(stage + r * a.spitch + sub_c * 16) = (use_pre && it < kPre) ? pre[it < kPre ? it : 0] : rreg[it];
+            }
+          }
+          __syncwarp();
+        }
+        // ---- 2. accumulator chunks: TMEM -> registers -> (+res) -> staging (or direct scalar) -----
+        for (int c0 = 0; c0 < gc; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_addr + (uint32_t)(g0 + c0), v);
+          tmem_ld_wait();
+          const int ch0 = chg + c0;
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 sc = *reinterpret_cast<const float4*>(a.s_scale + ch0 + 4 * j);
+            const float4 sh = *reinterpret_cast<const float4*>(a.s_shift + ch0 + 4 * j);
+            o[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
+            o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
+            o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
+            o[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
+          }
+          if (grp_vec) {
+            if (a.res) {
+              const uint4 r0 = *reinterpret_cast<const uint4*>(my_row + c0 * 2);
+              const uint4 r1 = *reinterpret_cast<const uint4*>(my_row + c0 * 2 + 16);
+              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 t = h2_to_f2<TH>(rw[j]);
+                o[2 * j] += t.x;
+                o[2 * j + 1] += t.y;
+              }
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+            }
+            if (a.out_f32) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(my_row + c0 * 4 + 16 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            } else {
+              uint32_t w[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) w[j] = f2_to_h2<TH>(o[2 * j], o[2 * j + 1]);
+              *reinterpret_cast<uint4*>(my_row + c0 * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<uint4*>(my_row + c0 * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+          } else if (valid) {
+            // ragged tail (Cout not a multiple of the vector width, odd pitches): per-lane scalar path
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = ch0 + j;
+              if (c < a.Cout) {
+                float t = o[j];
+                if (a.res) t += to_f<TH>(reinterpret_cast<const TH*>(a.res)[(int64_t)pix * a.res_pitch + c]);
+                if (a.relu) t = fmaxf(t, 0.f);
+                if (a.out_f32) reinterpret_cast<float*>(a.y)[(int64_t)pix * a.out_pitch + c] = t;
+                else reinterpret_cast<TH*>(a.y)[(int64_t)pix * a.out_pitch + c] = from_f<TH>(t);
+              }
+            }
+          }
+        }
+        // ---- 3. staging -> global, coalesced ----------------------------------------------------
+        if (grp_vec) {
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            if (it < lpr) {
+              const int r = it * rpi + sub_r;
+              const int pr = __shfl_sync(0xffffffffu, pix, r);
+              if (lane_on && ((vmask >> r) & 1u)) {
+                const uint4 val = *reinterpret_cast<const uint4*>(stage + r * a.spitch + sub_c * 16);
+                uint8_t* dst = reinterpret_cast<uint8_t*>(a.y) + ((int64_t)pr * a.out_pitch + chg) * esz + sub_c * 16;
+                *reinterpret_cast<uint4*>(dst) = val;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+  }
+}
 
 // ---- driver entry points for tensor-map encoding (resolved at run time, no -lcuda) ------------
 typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

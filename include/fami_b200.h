@@ -172,6 +172,12 @@ int fami_argmax_hw(const void* hm, int dtype, int pitch, int32_t* idx_out, float
  * out[128][16] = x[shift:shift+128][64] @ w[16][64]^T through one tcgen05 tile whose A descriptor
  * starts `shift` 128-byte rows into a TMA-written SWIZZLE_128B tile (mode 0: base_offset 0,
  * mode 1: base_offset = (addr >> 7) & 7).  Establishes the row-shift rule the halo conv relies on. */
+/* globaltimer timeline (ns) of CTA 0 of the last halo conv launched with FAMI_HALO_TRACE=1:
+ * [role 0..2][tile iteration 0..63][event 0..7] (tools/trace_halo.py).  Synchronises the device.   */
+int fami_debug_read_trace(uint64_t* host_out, int n);
+/* out[0] = SM clocks for `iters` back-to-back M=128,K=16 f16 tcgen05.mma of width N (issue + drain),
+ * out[1] = clocks of the issue loop alone (tools/probe_umma.py).                                   */
+int fami_debug_umma_rate(int64_t* out, int N, int iters, int variant, void* stream);
 int fami_debug_umma_rowshift(const void* x_f16, const void* w_f16, float* out, int R, int shift, int mode,
                              void* stream);
 

@@ -1,0 +1,12 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from fami_pose_b200 import _lib, ops
+out = torch.zeros(2, dtype=torch.int64, device="cuda")
+for variant in (3, 4, 6, 7, 8):
+    for N in (48, 96):
+        for iters in (81, 810):
+            _lib.call("fami_debug_umma_rate", ops._ptr(out), N, iters, variant, ops._stream())
+            torch.cuda.synchronize()
+            tot, iss = out.tolist()
+            print("variant %d N=%3d iters=%4d: %7.1f clk/MMA total, %7.1f clk/MMA issue  (ideal %.0f)" % (variant, N, iters, tot / iters, iss / iters, 128 * N / 256))
