@@ -1,0 +1,354 @@
+// Modulated deformable convolution v2 on B200 -- the north-star kernel (fami_dcn_fwd, 16-bit arm).
+// Replaces torchvision.ops.deform_conv2d as called at posetimation/zoo/Alignment/Alignment_V15.py:146-158.
+//
+// Structure (persistent CTAs, one 16x8-pixel tile at a time, 672 threads):
+//   * the x neighbourhood of the tile ((16+2R) x (8+2R) pixels x 64 channel slots) is brought ONCE into
+//     shared memory by a TMA tiled box load (128B-swizzled rows; out-of-image pixels zero-filled, which
+//     is exactly torchvision's "corner outside the image contributes 0" rule);
+//   * 16 gather warps walk the taps: thread (pixel, offset group) reads its (dy, dx, mask) -- streamed
+//     from HBM exactly once, in the tap-major layout the fused offset|mask conv writes -- forms the four
+//     bilinear corners from shared memory (8-byte loads, swizzle keeps them nearly conflict free), and
+//     stores 4 modulated fp16 columns into the UMMA A tile of that tap (128B-swizzled K-major);
+//     samples that fall outside the staged window take a bounds-checked global path;
+//   * one warp issues tcgen05.mma (M=128, N=Cout, K=C per tap) against the weights resident in shared
+//     memory, accumulating the nine taps in TMEM (double buffered across tiles);
+//   * 4 epilogue warps add the bias and store the tile (coalesced, through shared-memory staging).
+// The [C*9, B*H*W] column buffer of the reference never exists; HBM traffic is the algorithmic minimum:
+// offsets+masks (4*27*G B/pixel) + x (~once, via L2) + out.
+#include "tc_common.cuh"
+
+namespace fami {
+
+namespace {
+
+constexpr int kTH = 16, kTW = 8;            // output tile (pixels): 128 = one UMMA M tile
+constexpr int kGatherWarps = 16;
+constexpr int kGatherThreads = 32 * kGatherWarps;
+constexpr int kDcnEpiWarps = 4;
+constexpr int kDcnThreads = kGatherThreads + 32 + 32 * kDcnEpiWarps;   // 672
+constexpr int kAStages = 3;
+constexpr int kATile = 128 * 128;          // bytes per A stage
+
+struct DcnTcParams {
+  int B, H, W, C, Cout, G, d, R;
+  int WH, WW;                       // staged window (pixels)
+  int tiles_x, tiles_y, total_tiles;
+  int nk, BN;
+  int om_pitch, x_pitch, out_pitch, vec_ok;
+  uint32_t win_bytes, w_tile_bytes, ab_format;
+  const float* om;                  // [B*H*W][om_pitch], per pixel [9 taps][dy(G) | dx(G) | mask(G)]
+  const void* x;                    // TH NHWC (global fallback path)
+  const float* bias;
+  void* out;
+};
+
+template <typename TH> __device__ __forceinline__ float4 ld4h(const TH* p);   // 4 consecutive 16-bit values (8 B)
+template <> __device__ __forceinline__ float4 ld4h<__half>(const __half* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <> __device__ __forceinline__ float4 ld4h<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <typename TH>
+__global__ void __launch_bounds__(kDcnThreads, 1)
+dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const DcnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_win = smem;                                   // WH*WW rows x 128 B
+  uint8_t* s_a = s_win + p.win_bytes;                      // kAStages x 16 KB
+  uint8_t* s_w = s_a + kAStages * kATile;                  // 9 x BN x 128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + 9 * p.w_tile_bytes);
+  const uint32_t bar0 = smem_u32(bars);
+  // barriers: win_full, win_free, w_full, a_full[3], a_empty[3], tfull[2], tempty[2]
+  const uint32_t win_full = bar0, win_free = bar0 + 8, w_full = bar0 + 16;
+  auto a_full = [&](int s) { return bar0 + 8u * (3 + s); };
+  auto a_empty = [&](int s) { return bar0 + 8u * (3 + kAStages + s); };
+  auto tfull = [&](int a) { return bar0 + 8u * (3 + 2 * kAStages + a); };
+  auto tempty = [&](int a) { return bar0 + 8u * (5 + 2 * kAStages + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 + 2 * kAStages);
+  float* s_scale = reinterpret_cast<float*>(bars + 9 + 2 * kAStages);
+  float* s_shift = s_scale + p.BN;
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_shift + p.BN) + 15) & ~(uintptr_t)15);
+  fill_scale_shift(s_scale, s_shift, nullptr, p.bias, p.Cout, p.BN);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(win_full, 1);
+    mbar_init(win_free, kGatherThreads);
+    mbar_init(w_full, 1);
+    for (int s = 0; s < kAStages; ++s) { mbar_init(a_full(s), kGatherThreads); mbar_init(a_empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 32 * kDcnEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  if (warp == kGatherWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_origin = [&](int tile, int& b, int& y0, int& x0) {
+    const int per_img = p.tiles_x * p.tiles_y;
+    b = tile / per_img;
+    const int t = tile - b * per_img;
+    const int ty = t / p.tiles_x;
+    y0 = ty * kTH;
+    x0 = (t - ty * p.tiles_x) * kTW;
+  };
+
+  if (warp < kGatherWarps) {
+    // ===================== gather warps =====================
+    const TH* xg = reinterpret_cast<const TH*>(p.x);
+    const int G = p.G;
+    const int npairs = 128 * G;
+    int stage = 0;
+    uint32_t aph = 0, wph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int b, y0, x0;
+      tile_origin(tile, b, y0, x0);
+      const float wy_org = (float)(y0 - p.R), wx_org = (float)(x0 - p.R);
+      mbar_wait(win_full, wph);
+      wph ^= 1u;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int fr = tap / 3, fs = tap - fr * 3;
+        mbar_wait(a_empty(stage), aph ^ 1u);
+        uint8_t* a_st = s_a + stage * kATile;
+        const float* om_tap = p.om + tap * 3 * G;
+        for (int pair = threadIdx.x; pair < npairs; pair += kGatherThreads) {
+          const int r = pair / G, g = pair - r * G;
+          const int ty = r >> 3, tx = r & 7;
+          const int y = y0 + ty, x = x0 + tx;
+          float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (y < p.H && x < p.W) {
+            const float* o = om_tap + ((int64_t)(b * p.H + y) * p.W + x) * p.om_pitch + g;
+            const float ody = __ldg(o), odx = __ldg(o + G), mk = __ldg(o + 2 * G);
+            const float py = (float)(y - p.d + fr * p.d) + ody;
+            const float px = (float)(x - p.d + fs * p.d) + odx;
+            const float wy = py - wy_org, wx = px - wx_org;
+            if (wy >= 0.f && wy < (float)(p.WH - 1) && wx >= 0.f && wx < (float)(p.WW - 1)) {
+              // all four corners inside the staged (zero-padded) window
+              const float fy = floorf(wy), fx = floorf(wx);
+              const float ly = wy - fy, lx = wx - fx, hy = 1.f - ly, hx = 1.f - lx;
+              const int row00 = (int)fy * p.WW + (int)fx;
+              const int row10 = row00 + p.WW;
+              const uint32_t gsel = (uint32_t)(g >> 1), gofs = (uint32_t)(g & 1) << 3;
+              const float4 v1 = ld4h<TH>(reinterpret_cast<const TH*>(s_win + row00 * 128 + (((gsel ^ (uint32_t)(row00 & 7))) << 4) + gofs));
+              const float4 v2 = ld4h<TH>(reinterpret_cast<const TH*>(s_win + (row00 + 1) * 128 + (((gsel ^ (uint32_t)((row00 + 1) & 7))) << 4) + gofs));
+              const float4 v3 = ld4h<TH>(reinterpret_cast<const TH*>(s_win + row10 * 128 + (((gsel ^ (uint32_t)(row10 & 7))) << 4) + gofs));
+              const float4 v4 = ld4h<TH>(reinterpret_cast<const TH*>(s_win + (row10 + 1) * 128 + (((gsel ^ (uint32_t)((row10 + 1) & 7))) << 4) + gofs));
+              const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+              val.x = mk * (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x);
+              val.y = mk * (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y);
+              val.z = mk * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z);
+              val.w = mk * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w);
+            } else if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
+              // large offset: sample lies outside the staged window -> bounds-checked global corners
+              const int iy0 = (int)floorf(py), ix0 = (int)floorf(px);
+              const float ly = py - (float)iy0, lx = px - (float)ix0, hy = 1.f - ly, hx = 1.f - lx;
+              const TH* xb = xg + (int64_t)b * p.H * p.W * p.x_pitch + g * 4;
+              const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+              const bool y0ok = iy0 >= 0, y1ok = iy0 + 1 <= p.H - 1, x0ok = ix0 >= 0, x1ok = ix0 + 1 <= p.W - 1;
+              const float4 v1 = (y0ok && x0ok) ? ld4h<TH>(xb + ((int64_t)iy0 * p.W + ix0) * p.x_pitch) : z;
+              const float4 v2 = (y0ok && x1ok) ? ld4h<TH>(xb + ((int64_t)iy0 * p.W + ix0 + 1) * p.x_pitch) : z;
+              const float4 v3 = (y1ok && x0ok) ? ld4h<TH>(xb + ((int64_t)(iy0 + 1) * p.W + ix0) * p.x_pitch) : z;
+              const float4 v4 = (y1ok && x1ok) ? ld4h<TH>(xb + ((int64_t)(iy0 + 1) * p.W + ix0 + 1) * p.x_pitch) : z;
+              const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+              val.x = mk * (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x);
+              val.y = mk * (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y);
+              val.z = mk * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z);
+              val.w = mk * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w);
+            }
+          }
+          uint2 pk;
+          pk.x = f2_to_h2<TH>(val.x, val.y);
+          pk.y = f2_to_h2<TH>(val.z, val.w);
+          *reinterpret_cast<uint2*>(a_st + r * 128 + ((((uint32_t)(g >> 1)) ^ (uint32_t)(r & 7)) << 4) + ((g & 1) << 3)) = pk;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
+        mbar_arrive(a_full(stage));
+        if (++stage == kAStages) { stage = 0; aph ^= 1u; }
+      }
+      mbar_arrive(win_free);   // this thread no longer reads the window of this tile
+    }
+  } else if (warp == kGatherWarps) {
+    // ===================== TMA + MMA issuer (warp-uniform control flow, elected lane issues) =====
+    const bool leader = elect_one();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t idesc = (1u << 4) | (p.ab_format << 7) | (p.ab_format << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    if (leader) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+      mbar_arrive_expect_tx(w_full, 9u * p.w_tile_bytes);
+      for (int t = 0; t < 9; ++t) tma_tiled_2d(smem_u32(s_w + t * p.w_tile_bytes), &tmW, w_full, t * 64, 0);
+    }
+    {
+      int b, y0, x0;
+      if ((int)blockIdx.x < p.total_tiles) {
+        tile_origin(blockIdx.x, b, y0, x0);
+        if (leader) {
+          mbar_arrive_expect_tx(win_full, p.win_bytes);
+          tma_tiled_4d(smem_u32(s_win), &tmX, win_full, 0, x0 - p.R, y0 - p.R, b);
+        }
+      }
+    }
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    const uint32_t w_lo0 = sw128_desc_lo(smem_u32(s_w));
+    const uint32_t w_step = p.w_tile_bytes >> 4;
+    int stage = 0;
+    uint32_t aph = 0, fph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tempty(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_u + (uint32_t)(acc * p.BN);
+      uint32_t w_lo = w_lo0;
+      for (int tap = 0; tap < 9; ++tap, w_lo += w_step) {
+        mbar_wait(a_full(stage), aph);
+        tc_fence_after();
+        const uint32_t a_lo = sw128_desc_lo(smem_u32(s_a + stage * kATile));
+        umma_ksteps_n(p.nk, leader, d_tmem, a_lo, w_lo, idesc, tap != 0);
+        if (leader) umma_commit(a_empty(stage));
+        if (++stage == kAStages) { stage = 0; aph ^= 1u; }
+      }
+      if (leader) umma_commit(tfull(acc));
+      // all gathers of this tile are done (the last a_full completed): refill the window for the next tile
+      const int next = tile + gridDim.x;
+      mbar_wait(win_free, fph);
+      fph ^= 1u;
+      if (next < p.total_tiles) {
+        int b, y0, x0;
+        tile_origin(next, b, y0, x0);
+        if (leader) {
+          mbar_arrive_expect_tx(win_full, p.win_bytes);
+          tma_tiled_4d(smem_u32(s_win), &tmX, win_full, 0, x0 - p.R, y0 - p.R, b);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    EpiArgs ea;
+    ea.s_scale = s_scale; ea.s_shift = s_shift; ea.res = nullptr; ea.y = p.out;
+    ea.Cout = p.Cout; ea.BN = p.BN; ea.ch_base = 0; ea.out_pitch = p.out_pitch; ea.res_pitch = 0;
+    ea.out_f32 = 0; ea.relu = 0; ea.vec_ok = p.vec_ok; ea.up = 1; ea.Wout = p.W;
+    ea.spitch = 128 + 16;
+    uint8_t* stage = stage_base + (warp - kGatherWarps - 1) * 32 * ea.spitch;
+    uint4 no_pre[kPre];
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      int b, y0, x0;
+      tile_origin(tile, b, y0, x0);
+      const int y = y0 + (row >> 3), x = x0 + (row & 7);
+      const bool valid = y < p.H && x < p.W;
+      const int pix = valid ? (b * p.H + y) * p.W + x : 0;
+      mbar_wait(tfull(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(quarter * 32) << 16);
+      epilogue_rows<TH>(ea, t_addr, 0, p.BN, valid, pix, stage, lane, false, no_pre);
+      tc_fence_before();
+      mbar_arrive(tempty(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kGatherWarps) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace
+
+int dcn_tc_supported(const fami_dcn_desc* d) {
+  if (!is_half_dtype(d->dtype) || d->om_layout != 1) return 0;
+  if (d->C % 16 != 0 || d->C > 64 || d->C / d->G != 4) return 0;
+  if (d->Cout > 256 || d->x_pitch % 8 != 0) return 0;
+  if (d->kh != 3 || d->kw != 3 || d->pad != d->dil || d->dil > 4) return 0;
+  return 1;
+}
+
+int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const void* w, const float* bias, void* out,
+                  cudaStream_t st) {
+  FAMI_CHECK_ARG(load_driver_fns(), "cuTensorMapEncode* driver entry points unavailable");
+  FAMI_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+                 "dcn_tc: x / w must be 16-byte aligned");
+  DcnTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = d->B; p.H = d->H; p.W = d->W; p.C = d->C; p.Cout = d->Cout; p.G = d->G; p.d = d->dil;
+  p.R = d->dil + 5;   // dilation reach + 5 px of offset (2.5 sigma of the sigma = 2 px regime); beyond -> global path
+  p.WH = kTH + 2 * p.R; p.WW = kTW + 2 * p.R;
+  p.tiles_x = (d->W + kTW - 1) / kTW; p.tiles_y = (d->H + kTH - 1) / kTH;
+  p.total_tiles = d->B * p.tiles_x * p.tiles_y;
+  p.nk = d->C / 16;
+  p.BN = ((d->Cout + 15) / 16) * 16;
+  p.om_pitch = d->off_pitch; p.x_pitch = d->x_pitch; p.out_pitch = d->out_pitch;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (d->out_pitch % 8 == 0);
+  p.win_bytes = (uint32_t)(p.WH * p.WW) * 128u;
+  p.w_tile_bytes = (uint32_t)p.BN * 128u;
+  p.ab_format = d->dtype == FAMI_F16 ? 0u : 1u;
+  p.om = om; p.x = x; p.bias = bias; p.out = out;
+
+  const CUtensorMapDataType tm_dtype = d->dtype == FAMI_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap tmX, tmW;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->x_pitch * 2, (cuuint64_t)d->W * d->x_pitch * 2,
+                             (cuuint64_t)d->H * d->W * d->x_pitch * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.WW, (cuuint32_t)p.WH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode_tiled(&tmX, tm_dtype, 4, const_cast<void*>(x), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FAMI_CHECK_ARG(r == CUDA_SUCCESS, "dcn_tc: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
+  }
+  {
+    // weights packed by fami_pack_conv_weight(half): [CoutPad][9 taps][64] (Cin <= 64 -> one chunk per tap)
+    cuuint64_t dims[2] = {(cuuint64_t)9 * 64, (cuuint64_t)p.BN};
+    cuuint64_t strides[1] = {(cuuint64_t)9 * 64 * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)p.BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(&tmW, tm_dtype, 2, const_cast<void*>(w), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FAMI_CHECK_ARG(r == CUDA_SUCCESS, "dcn_tc: cuTensorMapEncodeTiled(w) failed (%d)", (int)r);
+  }
+  const size_t smem = (size_t)p.win_bytes + kAStages * kATile + 9 * (size_t)p.w_tile_bytes + 1024 + 256 +
+                      (size_t)p.BN * 8 + (size_t)kDcnEpiWarps * 32 * (128 + 16);
+  FAMI_CHECK_ARG(smem <= 227 * 1024, "dcn_tc: shared memory budget exceeded (%zu B)", smem);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(dcn_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(dcn_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_done = true;
+  }
+  int grid = p.total_tiles;
+  const int sms = num_sms();
+  if (grid > sms) grid = sms;
+  if (d->dtype == FAMI_F16)
+    dcn_tc_kernel<__half><<<grid, kDcnThreads, smem, st>>>(tmX, tmW, p);
+  else
+    dcn_tc_kernel<__nv_bfloat16><<<grid, kDcnThreads, smem, st>>>(tmX, tmW, p);
+  FAMI_CHECK_LAUNCH("dcn_tc_kernel");
+  return 0;
+}
+
+}  // namespace fami

@@ -186,8 +186,12 @@ class DeformConv2d(nn.Module):
             bound = 1 / math.sqrt(fan_in)
             nn.init.uniform_(self.bias, -bound, bound)
 
-    def forward(self, input, offset, mask=None, out=None):
+    def forward(self, input, offset, mask=None, out=None, fused_om=None):
         x = ops.to_nhwc(input)
+        if fused_om is not None:
+            # fami extension: one tap-major [offset|mask] buffer from the fused producer conv (ops.tap_major_perm)
+            return ops.dcn_fwd(x, None, None, self.weight, self.bias, self, pad=self.padding[0], dil=self.dilation[0],
+                               out=out, fused_om=fused_om)
         off = ops.to_nhwc(offset, torch.float32)
         if mask is None:
             raise NotImplementedError("FAMI-Pose always passes a modulation mask (DCNv2)")

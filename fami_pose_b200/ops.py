@@ -279,12 +279,45 @@ def upsample_nearest(x, factor):
 # deformable convolution
 # ------------------------------------------------------------------------------------------------
 
-def dcn_fwd(x, offset, mask, weight, bias, owner, pad=3, dil=3, out=None):
+def dcn_fused_supported(C, G, dtype):
+    """True if the 16-bit tensor-core DCN kernel (fused tap-major offsets) takes this shape."""
+    return dtype in (torch.float16, torch.bfloat16) and C % 16 == 0 and C <= 64 and C % G == 0 and C // G == 4
+
+
+def tap_major_perm(G, k=3):
+    """Channel permutation that turns the concatenated [offset(18G) | mask(9G)] torchvision layout into
+    the fused tap-major layout [tap][dy(G) | dx(G) | mask(G)]: new[n] = old[perm[n]]."""
+    K = k * k
+    perm = []
+    for t in range(K):
+        perm += [g * 2 * K + 2 * t for g in range(G)]
+        perm += [g * 2 * K + 2 * t + 1 for g in range(G)]
+        perm += [2 * K * G + g * K + t for g in range(G)]
+    return perm
+
+
+def dcn_fwd(x, offset, mask, weight, bias, owner, pad=3, dil=3, out=None, fused_om=None):
     """torchvision.ops.deform_conv2d(x, offset, weight, bias, stride=1, padding=pad, dilation=dil, mask=mask)
-    on NHWC operands (Alignment_V15.py:146,150,154,158)."""
-    _need_cuda(x, offset, mask)
+    on NHWC operands (Alignment_V15.py:146,150,154,158).  fused_om: ONE float32 buffer [B, 27G, H, W]
+    in tap-major layout (see tap_major_perm) instead of (offset, mask) -- the 16-bit tensor-core kernel."""
+    _need_cuda(x, offset, mask, fused_om)
     B, C, H, W, xp = meta(x)
     Cout, Cin, kh, kw = weight.shape
+    if out is None:
+        out = empty_nhwc(B, Cout, H, W, x.dtype, x.device)
+    outp = meta(out)[4]
+    b = bias.detach().float() if bias is not None else None
+    if fused_om is not None:
+        fB, FC, fH, fW, fp_ = meta(fused_om)
+        if FC % (3 * kh * kw) != 0 or (fB, fH, fW) != (B, H, W) or fused_om.dtype != torch.float32:
+            raise RuntimeError("fused offset|mask buffer %s inconsistent with input %s" % (tuple(fused_om.shape), tuple(x.shape)))
+        G = FC // (3 * kh * kw)
+        if Cin != C or not dcn_fused_supported(C, G, x.dtype):
+            raise ValueError("fused tap-major DCN needs 16-bit x, C <= 64 and 4 channels per offset group")
+        w = packed_weight(owner, weight, x.dtype)      # UMMA B operand: [CoutPad][9][64] half
+        d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, fp_, 0, outp, 1, _code(x.dtype))
+        _lib.call("fami_dcn_fwd", ctypes.byref(d), _ptr(x), _ptr(fused_om), None, _ptr(w), _ptr(b), _ptr(out), _stream())
+        return out
     oB, OC, oH, oW, offp = meta(offset)
     if OC % (2 * kh * kw) != 0:
         # torchvision raises RuntimeError for a bad offset channel count (deform_conv.py:85-90)
@@ -298,12 +331,8 @@ def dcn_fwd(x, offset, mask, weight, bias, owner, pad=3, dil=3, out=None):
     if MC != G * kh * kw or (oB, oH, oW) != (B, H, W) or (mB, mH, mW) != (B, H, W):
         raise RuntimeError("offset/mask shapes %s %s inconsistent with input %s"
                            % (tuple(offset.shape), tuple(mask.shape), tuple(x.shape)))
-    if out is None:
-        out = empty_nhwc(B, Cout, H, W, x.dtype, x.device)
-    outp = meta(out)[4]
     w = packed_weight(owner, weight, torch.float32)   # SIMT contraction: fp32 [K][CoutPad] packing
-    d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, offp, mp, outp, _code(x.dtype))
-    b = bias.detach().float() if bias is not None else None
+    d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, offp, mp, outp, 0, _code(x.dtype))
     _lib.call("fami_dcn_fwd", ctypes.byref(d), _ptr(x), _ptr(offset), _ptr(mask), _ptr(w), _ptr(b), _ptr(out),
               _stream())
     return out

@@ -27,16 +27,22 @@ class _CatConv:
         self._ver = None
         self.conv = None
 
-    def get(self, a, b):
-        ver = ops._ver(a.weight, a.bias, b.weight, b.bias)
+    def get(self, a, b, perm=None):
+        ver = (ops._ver(a.weight, a.bias, b.weight, b.bias), perm is not None)
         if self.conv is None or ver != self._ver:
             ca, cb = a.out_channels, b.out_channels
             conv = nn.Conv2d(a.in_channels, ca + cb, a.kernel_size, a.stride, a.padding, a.dilation,
                              bias=a.bias is not None).to(a.weight.device)
             with torch.no_grad():
-                conv.weight.copy_(torch.cat([a.weight, b.weight], 0))
-                if a.bias is not None:
-                    conv.bias.copy_(torch.cat([a.bias, b.bias], 0))
+                wcat = torch.cat([a.weight, b.weight], 0)
+                bcat = torch.cat([a.bias, b.bias], 0) if a.bias is not None else None
+                if perm is not None:   # tap-major output-channel order for the tensor-core DCN kernel
+                    idx = torch.tensor(perm, device=wcat.device)
+                    wcat = wcat[idx]
+                    bcat = bcat[idx] if bcat is not None else None
+                conv.weight.copy_(wcat)
+                if bcat is not None:
+                    conv.bias.copy_(bcat)
             for p in conv.parameters():
                 p.requires_grad = False
             self.conv = conv
@@ -153,12 +159,19 @@ class Alignment_V15(nn.Module):
             v = ops.linear(v, L[i].weight, L[i].bias)
         return v
 
-    def _offset_mask(self, k, x):
+    def _dcn(self, k, feat_for_offsets, x, out=None):
+        """dcn_offset_k + dcn_mask_k (one fused conv, Alignment_V15.py:144-145) then dcn_k (:146).  On the
+        16-bit arm the fused conv writes the tap-major layout the tensor-core DCN kernel streams."""
         off_m, msk_m = getattr(self, "dcn_offset_%d" % k), getattr(self, "dcn_mask_%d" % k)
-        conv = self._offmask[k - 1].get(off_m.conv, msk_m.conv)
-        buf = ops.conv_bn_act(x, conv, None, relu=False, out_dtype=torch.float32)   # sub-pixel offsets stay fp32
+        dcn = getattr(self, "dcn_%d" % k)
+        fused = ops.dcn_fused_supported(self.width, self.offset_groups, feat_for_offsets.dtype)
+        perm = ops.tap_major_perm(self.offset_groups) if fused else None
+        conv = self._offmask[k - 1].get(off_m.conv, msk_m.conv, perm)
+        buf = ops.conv_bn_act(feat_for_offsets, conv, None, relu=False, out_dtype=torch.float32)   # sub-pixel offsets stay fp32
+        if fused:
+            return dcn(x, None, None, out=out, fused_om=buf)
         n_off = off_m.conv.out_channels
-        return buf[:, :n_off], buf[:, n_off:]
+        return dcn(x, buf[:, :n_off], buf[:, n_off:], out=out)
 
     def forward(self, kf_x, sup_x, **kwargs):
         B, ns = kf_x.shape[0], sup_x.shape[1] // 3
@@ -187,16 +200,12 @@ class Alignment_V15(nn.Module):
         ops.copy_into(kf_feat, cat1[:, C:])
         combined = self.combined_feat_layers(cat1)                                 # :143
 
-        off, msk = self._offset_mask(1, combined)                                  # :144-146
-        combined = self.dcn_1(combined, off, msk)
-        off, msk = self._offset_mask(2, combined)                                  # :148-150
-        combined = self.dcn_2(combined, off, msk)
-        off, msk = self._offset_mask(3, combined)                                  # :152-154
-        aligned = self.dcn_3(agg_sup_feat, off, msk)
-        off, msk = self._offset_mask(4, aligned)                                   # :156-158
+        combined = self._dcn(1, combined, combined)                                # :144-146
+        combined = self._dcn(2, combined, combined)                                # :148-150
+        aligned = self._dcn(3, combined, agg_sup_feat)                             # :152-154 (offsets from the refined stream)
         cat2 = ops.empty_nhwc(B, 2 * C, H, W, kf_feat.dtype, kf_feat.device)       # [kf_feat | aligned] :160
         ops.copy_into(kf_feat, cat2[:, :C])
-        self.dcn_4(aligned, off, msk, out=cat2[:, C:])
+        self._dcn(4, aligned, aligned, out=cat2[:, C:])                            # :156-158
         all_agg = self.init_feature_agg_block(cat2)                                # :161
         final_hm = ops.conv_bn_act(all_agg, self.agg_final_layer, None, relu=False, out_dtype=torch.float32)  # :163
 

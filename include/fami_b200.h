@@ -105,12 +105,19 @@ int fami_bn_stats(const void* x, int dtype, int pitch, int64_t rows, int C, doub
  * posetimation/zoo/Alignment/Alignment_V15.py:83,89,95,101 / :146,150,154,158
  * (DeformConv2d(C,Cout,3,padding=3,dilation=3), offset groups G = offset_channels/18, mask raw).
  * x [B,H,W,C]; offset [B,H,W,18G] (channel g*18+2t = dy, +1 = dx); mask [B,H,W,9G];
- * w_packed [9][C][CoutPad]; out [B,H,W,Cout].  Fused gather -> on-chip columns -> contraction; the
- * [C*9, B*H*W] im2col buffer of the reference never exists in HBM.                              */
+ * w_packed: fami_pack_conv_weight(dtype FAMI_F32) for fp32 x, or (half dtype) for the 16-bit kernel;
+ * out [B,H,W,Cout].  Fused gather -> on-chip columns -> contraction; the [C*9, B*H*W] im2col buffer
+ * of the reference never exists in HBM.                                                          */
 typedef struct fami_dcn_desc {
   int32_t B, H, W, C, Cout, G;
   int32_t kh, kw, stride, pad, dil; /* 3,3,1,3,3 in the reference; stride must be 1 */
   int32_t x_pitch, off_pitch, mask_pitch, out_pitch;
+  int32_t om_layout;                /* 0: torchvision layout -- `offset` [.,18G] (channel g*18+2t = dy, +1 = dx)
+                                       and `mask` [.,9G] (channel g*9+t) are separate operands;
+                                       1: fused tap-major -- `offset` points at ONE buffer holding, per pixel,
+                                       [9 taps][dy(G) | dx(G) | mask(G)] (off_pitch >= 27G), `mask` is ignored.
+                                       The alignment head's fused offset|mask convolution writes layout 1 so the
+                                       16-bit tensor-core kernel streams each tap's 3G floats contiguously.      */
   int32_t dtype;                    /* storage of x/out: FAMI_F32 or FAMI_BF16; offset, mask, packed
                                        weights and bias are always float (sub-pixel precision)        */
 } fami_dcn_desc;

@@ -389,3 +389,71 @@ def test_conv_tc_half(case, prec):
         assert err <= tol
     finally:
         m.set_precision("fp32")
+
+
+# ---------------------------------------------------------------------------------------------
+# 16-bit tensor-core DCN (fused tap-major offsets)
+# ---------------------------------------------------------------------------------------------
+def _to_tap_major(off, msk, G):
+    from fami_pose_b200 import ops
+    cat = torch.cat([off, msk], 1)
+    return cat[:, ops.tap_major_perm(G)].contiguous()
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 48, 48, 12, 12, 9, 3.0), (1, 32, 32, 8, 10, 7, 2.0), (1, 64, 48, 16, 8, 8, 1.0),
+                                   (2, 48, 48, 12, 96, 72, 2.0), (1, 48, 48, 12, 40, 30, 14.0), (1, 48, 17, 12, 33, 21, 2.0)])
+def test_dcn_tc_fused_vs_oracle(shape, prec):
+    """tensor-core DCN (x/weights/columns in 16 bit, fp32 accumulate, fp32 offsets) vs the numpy oracle run
+    on the SAME 16-bit-rounded x and weights; sigma=14 px exercises the out-of-window global path.
+    Tolerance: 4e-3*max|ref| (fp16) / 2e-2*max|ref| (bf16) -- column + output rounding only."""
+    import fami_pose_b200 as m
+    from fami_pose_b200 import layers, ops
+    B, C, Cout, G, H, W, sig = shape
+    m.set_precision(prec)
+    hdt = ops.act_dtype()
+    try:
+        g = torch.Generator().manual_seed(B * 1000 + C + H)
+        x = torch.randn(B, C, H, W, generator=g).to(hdt).float()
+        off = sig * torch.randn(B, 18 * G, H, W, generator=g)
+        msk = torch.randn(B, 9 * G, H, W, generator=g)
+        w = (0.05 * torch.randn(Cout, C, 3, 3, generator=g)).to(hdt).float()
+        b = 0.1 * torch.randn(Cout, generator=g)
+        ref = torch.from_numpy(fo.dcn_fwd(x.numpy(), off.numpy(), msk.numpy(), w.numpy(), b.numpy()))
+        mod = layers.DeformConv2d(C, Cout, 3, padding=3, dilation=3).to(DEV)
+        with torch.no_grad():
+            mod.weight.copy_(w.to(DEV))
+            mod.bias.copy_(b.to(DEV))
+        om = ops.to_nhwc(_to_tap_major(off, msk, G).to(DEV), torch.float32)
+        out = mod(ops.to_nhwc(x.to(DEV), hdt), None, None, fused_om=om)
+        assert out.dtype == hdt
+        got = ops.to_nchw(out).cpu()
+        tol = (4e-3 if prec == "fp16" else 2e-2) * float(ref.abs().max()) + 1e-3
+        err = float((got - ref).abs().max())
+        print("dcn tc", prec, shape, "err", err, "tol", tol)
+        assert err <= tol
+    finally:
+        m.set_precision("fp32")
+
+
+def test_dcn_tc_zero_offset_equals_dilated_conv_full_size():
+    """Property at config-2 size (B=32): zero offsets + unit mask == the tensor-core dilated conv."""
+    import fami_pose_b200 as m
+    from fami_pose_b200 import layers, ops
+    m.set_precision("fp16")
+    try:
+        g = torch.Generator().manual_seed(5)
+        B, C, G, H, W = 32, 48, 12, 96, 72
+        xd = ops.empty_nhwc(B, C, H, W, torch.float16, DEV).normal_()
+        mod = layers.DeformConv2d(C, C, 3, padding=3, dilation=3).to(DEV)
+        conv = torch.nn.Conv2d(C, C, 3, 1, 3, 3).to(DEV)
+        with torch.no_grad():
+            conv.weight.copy_(mod.weight)
+            conv.bias.copy_(mod.bias)
+        om = ops.empty_nhwc(B, 27 * G, H, W, torch.float32, DEV).zero_()
+        om.view(B, 9, 3, G, H, W)[:, :, 2] = 1.0    # logical channel order [tap][dy|dx|mask][g]
+        a = ops.to_nchw(mod(xd, None, None, fused_om=om)).cpu()
+        b = ops.to_nchw(ops.conv_bn_act(xd, conv, None)).cpu()
+        assert float((a - b).abs().max()) <= 4e-3 * float(b.abs().max()) + 1e-3
+    finally:
+        m.set_precision("fp32")
