@@ -288,16 +288,25 @@ def main():
 
 
 def dcn_roofline(fp, ops, dev, stream, B, pk):
-    """The north-star kernel timed alone at the config-2 shape (x [B,48,96,72], G=12, fp32):
-    algorithmic bytes = 4*B*H*W*(Cin+Cout+27G) + 4*(9*Cin*Cout+Cout)."""
+    """The north-star kernel timed alone at the config-2 shape (x [B,48,96,72], G=12) in the active
+    precision.  Algorithmic bytes: B*H*W*(s_x*(Cin+Cout) + 4*27*G) + weights, with
+    s_x = 4 (fp32 arm) or 2 (16-bit arm; offsets and masks are fp32 in both)."""
     import torch
     C, G, H, W = 48, 12, 96, 72
+    dt = ops.act_dtype()
+    half = dt != torch.float32
     g = torch.Generator(device="cpu").manual_seed(1)
-    x = ops.to_nhwc(torch.randn(B, C, H, W, generator=g).to(dev), torch.float32)
-    off = ops.to_nhwc((2 * torch.randn(B, 18 * G, H, W, generator=g)).to(dev), torch.float32)
-    msk = ops.to_nhwc(torch.randn(B, 9 * G, H, W, generator=g).to(dev), torch.float32)
+    x = ops.to_nhwc(torch.randn(B, C, H, W, generator=g).to(dev), dt)
+    off = (2 * torch.randn(B, 18 * G, H, W, generator=g)).to(dev)     # sigma = 2 px (SURVEY.md 8d)
+    msk = torch.randn(B, 9 * G, H, W, generator=g).to(dev)
     dcn = fp.DeformConv2d(C, C, 3, padding=3, dilation=3).to(dev)
-    out = ops.empty_nhwc(B, C, H, W, torch.float32, dev)
+    out = ops.empty_nhwc(B, C, H, W, dt, dev)
+    if half:   # fused tap-major [offset|mask] buffer, as the alignment head's producer conv writes it
+        om = ops.to_nhwc(torch.cat([off, msk], 1)[:, ops.tap_major_perm(G)].contiguous(), torch.float32)
+        run = lambda: dcn(x, None, None, out=out, fused_om=om)
+    else:
+        offn, mskn = ops.to_nhwc(off, torch.float32), ops.to_nhwc(msk, torch.float32)
+        run = lambda: dcn(x, offn, mskn, out=out)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     times = []
     with torch.no_grad(), torch.cuda.stream(stream):
@@ -305,17 +314,18 @@ def dcn_roofline(fp, ops, dev, stream, B, pk):
             flush.zero_()  # evict L2 between launches (inputs alone exceed L2 at B=32, flushed anyway)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            dcn(x, off, msk, out=out)
+            run()
             e1.record(stream)
             stream.synchronize()
             if i >= 3:
                 times.append(e0.elapsed_time(e1))
     t = sorted(times)[len(times) // 2] / 1000.0
-    alg = 4 * B * H * W * (C + C + 27 * G) + 4 * (9 * C * C + C)
+    sx = 2 if half else 4
+    alg = B * H * W * (sx * (C + C) + 4 * 27 * G) + sx * 9 * C * C + 4 * C
     ach = alg / t / 1e9
-    return {"kernel": "fami_dcn_fwd (modulated deformable conv, C=48 G=12 96x72 B=%d fp32)" % B, "bound": "hbm",
-            "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
-            "algorithmic_bytes": alg, "us_per_launch": t * 1e6}
+    return {"kernel": "fami_dcn_fwd (modulated deformable conv, C=48 G=12 96x72 B=%d, x/out %s, offsets fp32)" % (B, str(dt).replace("torch.", "")),
+            "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+            "traffic": None, "algorithmic_bytes": alg, "us_per_launch": t * 1e6}
 
 
 def conv_roofline(fp, ops, dev, stream, B, pk, precision):

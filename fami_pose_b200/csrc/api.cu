@@ -67,6 +67,7 @@ int joint_mse_launch(const void*, int, int, const float*, const float*, float*, 
 int softmax_pkl_launch(const void*, int, const void*, int, int, float*, int, int, int, float, cudaStream_t);
 int argmax_hw_launch(const void*, int, int, int32_t*, float*, int, int, int, cudaStream_t);
 int debug_read_trace(unsigned long long* host_out, int n);
+int debug_read_dcn_trace(unsigned long long* host_out, int n);
 int debug_umma_rate_launch(long long* out, int N, int iters, int variant, cudaStream_t st);
 int debug_umma_rowshift_launch(const void*, const void*, float*, int, int, int, cudaStream_t);
 
@@ -297,7 +298,8 @@ int fami_argmax_hw(const void* hm, int dtype, int pitch, int32_t* idx_out, float
 
 /* per-role timeline of CTA 0 of the last halo conv launched with FAMI_HALO_TRACE=1 (tools/trace_halo.py) */
 int fami_debug_read_trace(uint64_t* host_out, int n) {
-  FAMI_CHECK_ARG(host_out && n > 0, "fami_debug_read_trace: bad arguments");
+  FAMI_CHECK_ARG(host_out && n != 0, "fami_debug_read_trace: bad arguments");
+  if (n < 0) return debug_read_dcn_trace(reinterpret_cast<unsigned long long*>(host_out), -n);   /* n < 0: DCN kernel trace */
   return debug_read_trace(reinterpret_cast<unsigned long long*>(host_out), n);
 }
 

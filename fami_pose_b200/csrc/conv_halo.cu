@@ -91,7 +91,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.sA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), p.n_iss); }
     for (int s = 0; s < nBbar; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), p.n_iss); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), p.n_iss); mbar_init(tempty(a), kEpiThreads); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), p.n_iss); mbar_init(tempty(a), kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
   }
@@ -258,7 +258,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (!(p.trace & 2)) epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix, stage, lane, false, no_pre);
       }
       tc_fence_before();
-      mbar_arrive(tempty(acc));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(acc));   // one arrival per warp
       if (warp == kEpiWarp0 && lane == 0) trace(p.trace, 2, it, 1);
     }
   }

@@ -15,11 +15,23 @@
 //   * 4 epilogue warps add the bias and store the tile (coalesced, through shared-memory staging).
 // The [C*9, B*H*W] column buffer of the reference never exists; HBM traffic is the algorithmic minimum:
 // offsets+masks (4*27*G B/pixel) + x (~once, via L2) + out.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace fami {
 
+__device__ unsigned long long g_dcn_trace[4096];   // [tile it < 16][16 events] of CTA 0, FAMI_DCN_TRACE=1
+
 namespace {
+
+__device__ __forceinline__ void dtrace(int on, int it, int ev) {
+  if (on && blockIdx.x == 0 && it < 16) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_dcn_trace[it * 16 + ev] = t;
+  }
+}
 
 constexpr int kTH = 16, kTW = 8;            // output tile (pixels): 128 = one UMMA M tile
 constexpr int kGatherWarps = 16;
@@ -36,6 +48,7 @@ struct DcnTcParams {
   int nk, BN;
   int om_pitch, x_pitch, out_pitch, vec_ok;
   uint32_t win_bytes, w_tile_bytes, ab_format;
+  int trace;
   const float* om;                  // [B*H*W][om_pitch], per pixel [9 taps][dy(G) | dx(G) | mask(G)]
   const void* x;                    // TH NHWC (global fallback path)
   const float* bias;
@@ -56,6 +69,21 @@ template <> __device__ __forceinline__ float4 ld4h<__nv_bfloat16>(const __nv_bfl
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// packed 16-bit arithmetic for the bilinear blend: acc += w * v on two channels at once
+template <typename TH> struct H2;
+template <> struct H2<__half> {
+  typedef __half2 t;
+  static __device__ __forceinline__ t bcast(float w) { return __float2half2_rn(w); }
+  static __device__ __forceinline__ t fma(t a, t b, t c) { return __hfma2(a, b, c); }
+  static __device__ __forceinline__ t mul(t a, t b) { return __hmul2(a, b); }
+};
+template <> struct H2<__nv_bfloat16> {
+  typedef __nv_bfloat162 t;
+  static __device__ __forceinline__ t bcast(float w) { return __float2bfloat162_rn(w); }
+  static __device__ __forceinline__ t fma(t a, t b, t c) { return __hfma2(a, b, c); }
+  static __device__ __forceinline__ t mul(t a, t b) { return __hmul2(a, b); }
+};
+
 template <typename TH>
 __global__ void __launch_bounds__(kDcnThreads, 1)
 dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const DcnTcParams p) {
@@ -73,7 +101,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   auto tfull = [&](int a) { return bar0 + 8u * (3 + 2 * kAStages + a); };
   auto tempty = [&](int a) { return bar0 + 8u * (5 + 2 * kAStages + a); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 + 2 * kAStages);
-  float* s_scale = reinterpret_cast<float*>(bars + 9 + 2 * kAStages);
+  float* s_scale = reinterpret_cast<float*>(bars + 10 + 2 * kAStages);   // 16-byte aligned (float4 reads)
   float* s_shift = s_scale + p.BN;
   uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_shift + p.BN) + 15) & ~(uintptr_t)15);
   fill_scale_shift(s_scale, s_shift, nullptr, p.bias, p.Cout, p.BN);
@@ -81,10 +109,10 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(win_full, 1);
-    mbar_init(win_free, kGatherThreads);
+    mbar_init(win_free, kGatherWarps);
     mbar_init(w_full, 1);
-    for (int s = 0; s < kAStages; ++s) { mbar_init(a_full(s), kGatherThreads); mbar_init(a_empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 32 * kDcnEpiWarps); }
+    for (int s = 0; s < kAStages; ++s) { mbar_init(a_full(s), kGatherWarps); mbar_init(a_empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), kDcnEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
   }
@@ -112,74 +140,127 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const TH* xg = reinterpret_cast<const TH*>(p.x);
     const int G = p.G;
     const int npairs = 128 * G;
+    typedef typename H2<TH>::t h2;
+    constexpr int kPairs = (128 * 16 + kGatherThreads - 1) / kGatherThreads;   // (pixel, group) pairs per thread, G <= 16
     int stage = 0;
     uint32_t aph = 0, wph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int git = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++git) {
       int b, y0, x0;
       tile_origin(tile, b, y0, x0);
-      const float wy_org = (float)(y0 - p.R), wx_org = (float)(x0 - p.R);
+      if (threadIdx.x == 0) dtrace(p.trace, git, 0);
+      // this thread's pairs are the same for all nine taps: resolve them once per tile
+      int pr_rg[kPairs];                    // r | g << 8, or -1
+      const float* pr_o[kPairs];            // &om[pixel][tap 0][dy][g]; nullptr if the pixel is outside the image
+#pragma unroll
+      for (int j = 0; j < kPairs; ++j) {
+        const int pair = threadIdx.x + j * kGatherThreads;
+        pr_o[j] = nullptr;
+        pr_rg[j] = -1;
+        if (pair < npairs) {
+          const int r = pair / G, g = pair - r * G;
+          const int y = y0 + (r >> 3), x = x0 + (r & 7);
+          pr_rg[j] = r | (g << 8);
+          if (y < p.H && x < p.W) pr_o[j] = p.om + ((int64_t)(b * p.H + y) * p.W + x) * p.om_pitch + g;
+        }
+      }
+      // software pipeline: the (dy, dx, mask) triples of tap t+1 are in flight while tap t is gathered
+      float c_dy[kPairs], c_dx[kPairs], c_mk[kPairs], n_dy[kPairs], n_dx[kPairs], n_mk[kPairs];
+#pragma unroll
+      for (int j = 0; j < kPairs; ++j) {
+        c_dy[j] = c_dx[j] = c_mk[j] = 0.f;
+        if (pr_o[j]) { c_dy[j] = __ldg(pr_o[j]); c_dx[j] = __ldg(pr_o[j] + G); c_mk[j] = __ldg(pr_o[j] + 2 * G); }
+      }
       mbar_wait(win_full, wph);
       wph ^= 1u;
+      if (threadIdx.x == 0) dtrace(p.trace, git, 1);
       for (int tap = 0; tap < 9; ++tap) {
         const int fr = tap / 3, fs = tap - fr * 3;
+        if (tap + 1 < 9) {
+#pragma unroll
+          for (int j = 0; j < kPairs; ++j) {
+            n_dy[j] = n_dx[j] = n_mk[j] = 0.f;
+            if (pr_o[j] && !(p.trace & 2)) {
+              const float* o = pr_o[j] + (tap + 1) * 3 * G;
+              n_dy[j] = __ldg(o); n_dx[j] = __ldg(o + G); n_mk[j] = __ldg(o + 2 * G);
+            }
+          }
+        }
         mbar_wait(a_empty(stage), aph ^ 1u);
         uint8_t* a_st = s_a + stage * kATile;
-        const float* om_tap = p.om + tap * 3 * G;
-        for (int pair = threadIdx.x; pair < npairs; pair += kGatherThreads) {
-          const int r = pair / G, g = pair - r * G;
-          const int ty = r >> 3, tx = r & 7;
-          const int y = y0 + ty, x = x0 + tx;
-          float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (y < p.H && x < p.W) {
-            const float* o = om_tap + ((int64_t)(b * p.H + y) * p.W + x) * p.om_pitch + g;
-            const float ody = __ldg(o), odx = __ldg(o + G), mk = __ldg(o + 2 * G);
-            const float py = (float)(y - p.d + fr * p.d) + ody;
-            const float px = (float)(x - p.d + fs * p.d) + odx;
-            const float wy = py - wy_org, wx = px - wx_org;
-            if (wy >= 0.f && wy < (float)(p.WH - 1) && wx >= 0.f && wx < (float)(p.WW - 1)) {
-              // all four corners inside the staged (zero-padded) window
+        const float tap_y = (float)(fr * p.d + p.R - p.d), tap_x = (float)(fs * p.d + p.R - p.d);
+#pragma unroll
+        for (int j = 0; j < kPairs; ++j) {
+          if (pr_rg[j] < 0) continue;
+          const int r = pr_rg[j] & 255, g = pr_rg[j] >> 8;
+          uint2 pk = make_uint2(0u, 0u);
+          if (pr_o[j]) {
+            // window coordinates: integer shifts of the image-space sample position, so the fractional
+            // parts are exactly those of py / px
+            const float wy = (float)(r >> 3) + tap_y + c_dy[j];
+            const float wx = (float)(r & 7) + tap_x + c_dx[j];
+            if (p.trace & 8) {
+              pk.x = __float_as_uint(wy); pk.y = __float_as_uint(wx);   // experiment: no window loads / blend
+            } else if (wy >= 0.f && wy < (float)(p.WH - 1) && wx >= 0.f && wx < (float)(p.WW - 1)) {
+              // all four corners inside the staged (zero-padded) window: 8-byte shared-memory loads,
+              // blend in packed 16-bit arithmetic (the column is rounded to 16 bit for the MMA anyway)
               const float fy = floorf(wy), fx = floorf(wx);
               const float ly = wy - fy, lx = wx - fx, hy = 1.f - ly, hx = 1.f - lx;
               const int row00 = (int)fy * p.WW + (int)fx;
               const int row10 = row00 + p.WW;
               const uint32_t gsel = (uint32_t)(g >> 1), gofs = (uint32_t)(g & 1) << 3;
-              const float4 v1 = ld4h<TH>(reinterpret_cast<const TH*>(s_win + row00 * 128 + (((gsel ^ (uint32_t)(row00 & 7))) << 4) + gofs));
-              const float4 v2 = ld4h<TH>(reinterpret_cast<const TH*>(s_win + (row00 + 1) * 128 + (((gsel ^ (uint32_t)((row00 + 1) & 7))) << 4) + gofs));
-              const float4 v3 = ld4h<TH>(reinterpret_cast<const TH*>(s_win + row10 * 128 + (((gsel ^ (uint32_t)(row10 & 7))) << 4) + gofs));
-              const float4 v4 = ld4h<TH>(reinterpret_cast<const TH*>(s_win + (row10 + 1) * 128 + (((gsel ^ (uint32_t)((row10 + 1) & 7))) << 4) + gofs));
-              const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-              val.x = mk * (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x);
-              val.y = mk * (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y);
-              val.z = mk * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z);
-              val.w = mk * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w);
-            } else if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
-              // large offset: sample lies outside the staged window -> bounds-checked global corners
-              const int iy0 = (int)floorf(py), ix0 = (int)floorf(px);
-              const float ly = py - (float)iy0, lx = px - (float)ix0, hy = 1.f - ly, hx = 1.f - lx;
-              const TH* xb = xg + (int64_t)b * p.H * p.W * p.x_pitch + g * 4;
-              const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-              const bool y0ok = iy0 >= 0, y1ok = iy0 + 1 <= p.H - 1, x0ok = ix0 >= 0, x1ok = ix0 + 1 <= p.W - 1;
-              const float4 v1 = (y0ok && x0ok) ? ld4h<TH>(xb + ((int64_t)iy0 * p.W + ix0) * p.x_pitch) : z;
-              const float4 v2 = (y0ok && x1ok) ? ld4h<TH>(xb + ((int64_t)iy0 * p.W + ix0 + 1) * p.x_pitch) : z;
-              const float4 v3 = (y1ok && x0ok) ? ld4h<TH>(xb + ((int64_t)(iy0 + 1) * p.W + ix0) * p.x_pitch) : z;
-              const float4 v4 = (y1ok && x1ok) ? ld4h<TH>(xb + ((int64_t)(iy0 + 1) * p.W + ix0 + 1) * p.x_pitch) : z;
-              const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-              val.x = mk * (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x);
-              val.y = mk * (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y);
-              val.z = mk * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z);
-              val.w = mk * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w);
+              const uint2 u1 = *reinterpret_cast<const uint2*>(s_win + row00 * 128 + ((gsel ^ (uint32_t)(row00 & 7)) << 4) + gofs);
+              const uint2 u2 = *reinterpret_cast<const uint2*>(s_win + (row00 + 1) * 128 + ((gsel ^ (uint32_t)((row00 + 1) & 7)) << 4) + gofs);
+              const uint2 u3 = *reinterpret_cast<const uint2*>(s_win + row10 * 128 + ((gsel ^ (uint32_t)(row10 & 7)) << 4) + gofs);
+              const uint2 u4 = *reinterpret_cast<const uint2*>(s_win + (row10 + 1) * 128 + ((gsel ^ (uint32_t)((row10 + 1) & 7)) << 4) + gofs);
+              const float mk = c_mk[j];
+              const h2 w1 = H2<TH>::bcast(mk * hy * hx), w2 = H2<TH>::bcast(mk * hy * lx);
+              const h2 w3 = H2<TH>::bcast(mk * ly * hx), w4 = H2<TH>::bcast(mk * ly * lx);
+              h2 lo = H2<TH>::mul(w1, *reinterpret_cast<const h2*>(&u1.x));
+              h2 hi = H2<TH>::mul(w1, *reinterpret_cast<const h2*>(&u1.y));
+              lo = H2<TH>::fma(w2, *reinterpret_cast<const h2*>(&u2.x), lo);
+              hi = H2<TH>::fma(w2, *reinterpret_cast<const h2*>(&u2.y), hi);
+              lo = H2<TH>::fma(w3, *reinterpret_cast<const h2*>(&u3.x), lo);
+              hi = H2<TH>::fma(w3, *reinterpret_cast<const h2*>(&u3.y), hi);
+              lo = H2<TH>::fma(w4, *reinterpret_cast<const h2*>(&u4.x), lo);
+              hi = H2<TH>::fma(w4, *reinterpret_cast<const h2*>(&u4.y), hi);
+              pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            } else {
+              // large offset: sample lies outside the staged window -> bounds-checked global corners (fp32 blend)
+              const float py = (float)(y0 + (r >> 3) - p.d + fr * p.d) + c_dy[j];
+              const float px = (float)(x0 + (r & 7) - p.d + fs * p.d) + c_dx[j];
+              if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
+                const int iy0 = (int)floorf(py), ix0 = (int)floorf(px);
+                const float ly = py - (float)iy0, lx = px - (float)ix0, hy = 1.f - ly, hx = 1.f - lx;
+                const TH* xb = xg + (int64_t)b * p.H * p.W * p.x_pitch + g * 4;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool y0ok = iy0 >= 0, y1ok = iy0 + 1 <= p.H - 1, x0ok = ix0 >= 0, x1ok = ix0 + 1 <= p.W - 1;
+                const float4 v1 = (y0ok && x0ok) ? ld4h<TH>(xb + ((int64_t)iy0 * p.W + ix0) * p.x_pitch) : z;
+                const float4 v2 = (y0ok && x1ok) ? ld4h<TH>(xb + ((int64_t)iy0 * p.W + ix0 + 1) * p.x_pitch) : z;
+                const float4 v3 = (y1ok && x0ok) ? ld4h<TH>(xb + ((int64_t)(iy0 + 1) * p.W + ix0) * p.x_pitch) : z;
+                const float4 v4 = (y1ok && x1ok) ? ld4h<TH>(xb + ((int64_t)(iy0 + 1) * p.W + ix0 + 1) * p.x_pitch) : z;
+                const float mk = c_mk[j];
+                const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+                pk.x = f2_to_h2<TH>(mk * (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x),
+                                    mk * (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y));
+                pk.y = f2_to_h2<TH>(mk * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z),
+                                    mk * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w));
+              }
             }
           }
-          uint2 pk;
-          pk.x = f2_to_h2<TH>(val.x, val.y);
-          pk.y = f2_to_h2<TH>(val.z, val.w);
           *reinterpret_cast<uint2*>(a_st + r * 128 + ((((uint32_t)(g >> 1)) ^ (uint32_t)(r & 7)) << 4) + ((g & 1) << 3)) = pk;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
-        mbar_arrive(a_full(stage));
+#pragma unroll
+        for (int j = 0; j < kPairs; ++j) { c_dy[j] = n_dy[j]; c_dx[j] = n_dx[j]; c_mk[j] = n_mk[j]; }
+        if (!(p.trace & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full(stage));   // one arrival per warp: 512 same-address arrivals would serialise
+        if (threadIdx.x == 0) dtrace(p.trace, git, 2 + tap);
         if (++stage == kAStages) { stage = 0; aph ^= 1u; }
       }
-      mbar_arrive(win_free);   // this thread no longer reads the window of this tile
+      __syncwarp();
+      if (lane == 0) mbar_arrive(win_free);   // this warp no longer reads the window of this tile
     }
   } else if (warp == kGatherWarps) {
     // ===================== TMA + MMA issuer (warp-uniform control flow, elected lane issues) =====
@@ -187,6 +268,19 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t idesc = (1u << 4) | (p.ab_format << 7) | (p.ab_format << 10) | ((uint32_t)(p.BN >> 3) << 17) |
                            ((uint32_t)(128 >> 4) << 24);
+    // pull a tile's offsets|masks (16 row segments of 8 pixels x 27G floats, the dominant HBM stream) into
+    // L2 one tile ahead, so the gather warps' dependent loads see L2 rather than HBM latency
+    auto prefetch_om = [&](int b, int y0, int x0) {
+      const int row = lane >> 1, half = lane & 1;          // 32 lanes: 16 rows x 2 halves of the 8-pixel segment
+      const int y = y0 + row, x = x0 + half * 4;
+      if (y < p.H && x < p.W) {
+        const int npx = (p.W - x < 4) ? (p.W - x) : 4;
+        const float* ptr = p.om + ((int64_t)(b * p.H + y) * p.W + x) * p.om_pitch;
+        const uint32_t bytes = (uint32_t)(npx * p.om_pitch * 4) & ~15u;
+        if (bytes >= 16 && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0))
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+      }
+    };
     if (leader) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
@@ -201,6 +295,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           mbar_arrive_expect_tx(win_full, p.win_bytes);
           tma_tiled_4d(smem_u32(s_win), &tmX, win_full, 0, x0 - p.R, y0 - p.R, b);
         }
+        prefetch_om(b, y0, x0);
       }
     }
     mbar_wait(w_full, 0);
@@ -237,6 +332,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           mbar_arrive_expect_tx(win_full, p.win_bytes);
           tma_tiled_4d(smem_u32(s_win), &tmX, win_full, 0, x0 - p.R, y0 - p.R, b);
         }
+        prefetch_om(b, y0, x0);
       }
     }
   } else {
@@ -264,7 +360,8 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       const uint32_t t_addr = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(quarter * 32) << 16);
       epilogue_rows<TH>(ea, t_addr, 0, p.BN, valid, pix, stage, lane, false, no_pre);
       tc_fence_before();
-      mbar_arrive(tempty(acc));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(acc));
     }
   }
 
@@ -306,6 +403,8 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
   p.w_tile_bytes = (uint32_t)p.BN * 128u;
   p.ab_format = d->dtype == FAMI_F16 ? 0u : 1u;
   p.om = om; p.x = x; p.bias = bias; p.out = out;
+  static const bool trace_on = getenv("FAMI_DCN_TRACE") != nullptr;
+  p.trace = trace_on ? atoi(getenv("FAMI_DCN_TRACE")) : 0;
 
   const CUtensorMapDataType tm_dtype = d->dtype == FAMI_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap tmX, tmW;
@@ -349,6 +448,12 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
     dcn_tc_kernel<__nv_bfloat16><<<grid, kDcnThreads, smem, st>>>(tmX, tmW, p);
   FAMI_CHECK_LAUNCH("dcn_tc_kernel");
   return 0;
+}
+
+int debug_read_dcn_trace(unsigned long long* host_out, int n) {
+  if (n > 4096) n = 4096;
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host_out, g_dcn_trace, (size_t)n * sizeof(unsigned long long)) == cudaSuccess ? 0 : 1;
 }
 
 }  // namespace fami

@@ -107,6 +107,12 @@ __device__ __forceinline__ void umma_ksteps_n(int nk, bool leader, uint32_t tmem
   }
 }
 
+// whole-warp wait with a single polling lane (32 lanes polling one mbarrier add contention for nothing)
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane) {
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+
 // true in exactly one lane of a fully converged warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -40,11 +40,16 @@ if which in ("all", "dcn"):
     msk = ops.empty_nhwc(B, 9 * G, H, W, torch.float32, dev).normal_()
     dcn = fp.DeformConv2d(C, C, 3, padding=3, dilation=3).to(dev)
     out = ops.empty_nhwc(B, C, H, W, dt, dev)
+    om = ops.empty_nhwc(B, 27 * G, H, W, torch.float32, dev).normal_() * 2
+    fused = dt != torch.float32
     ts = []
     for i in range(6):
         e0, e1 = ev(), ev()
         e0.record()
-        dcn(x, off, msk, out=out)
+        if fused:
+            dcn(x, None, None, out=out, fused_om=om)
+        else:
+            dcn(x, off, msk, out=out)
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
