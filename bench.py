@@ -155,6 +155,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     fp.set_precision(args.precision)
@@ -323,9 +324,15 @@ def dcn_roofline(fp, ops, dev, stream, B, pk):
     sx = 2 if half else 4
     alg = B * H * W * (sx * (C + C) + 4 * 27 * G) + sx * 9 * C * C + 4 * C
     ach = alg / t / 1e9
+    traffic = None
+    try:   # DRAM bytes of the same launch from the committed ncu --set full capture (16-bit arm, B=32)
+        if half and B == 32:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["dcn_tc_kernel_fp16_B32"]
+    except Exception:
+        traffic = None
     return {"kernel": "fami_dcn_fwd (modulated deformable conv, C=48 G=12 96x72 B=%d, x/out %s, offsets fp32)" % (B, str(dt).replace("torch.", "")),
             "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-            "traffic": None, "algorithmic_bytes": alg, "us_per_launch": t * 1e6}
+            "traffic": traffic, "algorithmic_bytes": alg, "us_per_launch": t * 1e6}
 
 
 def conv_roofline(fp, ops, dev, stream, B, pk, precision):
