@@ -237,7 +237,7 @@ int fami_warp_translate_fwd(const void* src, int src_pitch, const float* txy, vo
 int fami_warp_translate_bwd(const float* src, int src_pitch, const float* txy, const float* grad_out, int go_pitch,
                             float* grad_src, int gs_pitch, float* grad_txy, int B, int H, int W, int C,
                             void* stream) {
-  FAMI_CHECK_ARG(src && txy && grad_out, "fami_warp_translate_bwd: null pointer");
+  FAMI_CHECK_ARG(src && txy && grad_out && (grad_src || grad_txy), "fami_warp_translate_bwd: null pointer");
   FAMI_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0, "fami_warp_translate_bwd: bad shape");
   return warp_translate_bwd_launch(src, src_pitch, txy, grad_out, go_pitch, grad_src, gs_pitch, grad_txy, B, H, W, C,
                                    (cudaStream_t)stream);

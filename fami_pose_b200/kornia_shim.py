@@ -10,4 +10,8 @@ def warp_affine(src, M, dsize, mode='bilinear', padding_mode='zeros', align_corn
         raise NotImplementedError("dsize must equal the input size")
     x = ops.to_nhwc(src)
     txy = M[:, :, 2]  # (tx, ty); the linear part must be the identity (not checked: would sync the host)
+    import torch
+    if torch.is_grad_enabled() and (x.requires_grad or txy.requires_grad):
+        from .autograd import WarpTranslateFunction   # differentiable path (fp32 arm): fami_warp_translate_bwd
+        return WarpTranslateFunction.apply(x, txy.float().contiguous())
     return ops.warp_translate(x, txy)

@@ -196,5 +196,8 @@ class DeformConv2d(nn.Module):
         if mask is None:
             raise NotImplementedError("FAMI-Pose always passes a modulation mask (DCNv2)")
         msk = ops.to_nhwc(mask, torch.float32)
+        if torch.is_grad_enabled() and out is None and any(t.requires_grad for t in (x, off, msk, self.weight)):
+            from .autograd import DeformConvFunction   # differentiable path (fp32 arm): fami_dcn_bwd
+            return DeformConvFunction.apply(x, off, msk, self.weight, self.bias, self, self.padding[0], self.dilation[0])
         return ops.dcn_fwd(x, off, msk, self.weight, self.bias, self, pad=self.padding[0], dil=self.dilation[0],
                            out=out)

@@ -124,8 +124,10 @@ typedef struct fami_dcn_desc {
 
 int fami_dcn_fwd(const fami_dcn_desc* d, const void* x, const void* offset, const void* mask,
                  const void* w_packed, const float* bias, void* out, void* stream);
-/* backward (fp32 storage): grad wrt input (scatter), offset+mask, weight+bias.
- * torchvision: deformable_col2im / deformable_col2im_coord + GEMMs.              */
+/* backward (fp32 storage, om_layout 0): grad wrt input (atomic scatter), offset+mask, weight+bias.
+ * torchvision: deformable_col2im / deformable_col2im_coord + GEMMs.  Gradient buffers
+ * are DENSE (grad_x [B,H,W,C], grad_offset [B,H,W,18G], grad_mask [B,H,W,9G], grad_w_packed in the
+ * fp32 packed layout [9*C][CoutPad], grad_bias [Cout] or NULL) and are zero-filled by the call.   */
 int fami_dcn_bwd(const fami_dcn_desc* d, const float* x, const float* offset, const float* mask,
                  const float* w_packed, const float* grad_out, float* grad_x, float* grad_offset,
                  float* grad_mask, float* grad_w_packed, float* grad_bias, void* stream);
@@ -136,6 +138,7 @@ int fami_dcn_bwd(const fami_dcn_desc* d, const float* x, const float* offset, co
  * txy [B,2] = (tx, ty).  out may be a channel slice of the 4-frame concat buffer (:139).        */
 int fami_warp_translate_fwd(const void* src, int src_pitch, const float* txy, void* out, int out_pitch,
                             int dtype, int B, int H, int W, int C, void* stream);
+/* grad_src [B,H,W,C] dense (gs_pitch == C) and grad_txy [B,2] are zero-filled by the call; either may be NULL. */
 int fami_warp_translate_bwd(const float* src, int src_pitch, const float* txy, const float* grad_out,
                             int go_pitch, float* grad_src, int gs_pitch, float* grad_txy, int B, int H,
                             int W, int C, void* stream);

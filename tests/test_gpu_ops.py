@@ -457,3 +457,53 @@ def test_dcn_tc_zero_offset_equals_dilated_conv_full_size():
         assert float((a - b).abs().max()) <= 4e-3 * float(b.abs().max()) + 1e-3
     finally:
         m.set_precision("fp32")
+
+
+# ---------------------------------------------------------------------------------------------
+# backward kernels (fp32 arm)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c48g12", "c32g8", "c16g1_oob", "c64g16"])
+def test_dcn_bwd_vs_torchvision_autograd_golden(name, golden_dir):
+    """fami_dcn_bwd vs torchvision's autograd (committed fp64 golden: grads wrt input, offset, mask,
+    weight, bias, incl. out-of-bounds offsets and G=1); tolerance 2e-4 * max|ref| (fp32, atomics)."""
+    fp()
+    from fami_pose_b200 import layers
+    gold = np.load(os.path.join(golden_dir, "dcn_torchvision.npz"))
+    case, (x, off, msk, w, b, go) = _golden_inputs(name)
+    _, B, C, Cout, G, H, W, sig = case
+    mod = layers.DeformConv2d(C, Cout, 3, padding=3, dilation=3).to(DEV)
+    with torch.no_grad():
+        mod.weight.copy_(w.to(DEV))
+        mod.bias.copy_(b.to(DEV))
+    xd, od, md = nhwc(x).requires_grad_(True), nhwc(off).requires_grad_(True), nhwc(msk).requires_grad_(True)
+    out = mod(xd, od, md)
+    out.backward(nhwc(go))
+    got = {"gx": back(xd.grad), "goff": back(od.grad), "gmask": back(md.grad), "gw": mod.weight.grad.cpu(),
+           "gb": mod.bias.grad.cpu()}
+    for key, g in got.items():
+        ref = torch.from_numpy(gold["%s_f64_%s" % (name, key)]).float()
+        err = float((g - ref).abs().max())
+        assert err <= 2e-4 * max(1.0, float(ref.abs().max())), (key, err)
+
+
+def test_warp_translate_bwd_vs_torch_autograd():
+    """fami_warp_translate_bwd vs torch autograd through the kornia restatement (CPU fp64); tol 1e-4 rel."""
+    fp()
+    from fami_pose_b200 import kornia_shim
+    g = torch.Generator().manual_seed(31)
+    B, C, H, W = 3, 16, 12, 9
+    src = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    txy = torch.tensor([[0.3, -1.7], [2.25, 0.5], [-0.6, 3.4]], dtype=torch.float64)
+    go = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    s_ref, t_ref = src.clone().requires_grad_(True), txy.clone().requires_grad_(True)
+    M = torch.eye(3, dtype=torch.float64)[0:2].view(1, 2, 3).repeat(B, 1, 1)
+    M = torch.cat([M[:, :, :2], t_ref.unsqueeze(2)], 2)
+    fo.warp_affine_kornia(s_ref, M, (H, W)).backward(go)
+    sd = nhwc(src.float()).requires_grad_(True)
+    td = txy.float().to(DEV).requires_grad_(True)
+    Md = torch.cat([torch.eye(3, device=DEV)[0:2].view(1, 2, 3).repeat(B, 1, 1)[:, :, :2], td.unsqueeze(2)], 2)
+    out = kornia_shim.warp_affine(sd, Md, (H, W))
+    out.backward(nhwc(go.float()))
+    e1 = float((back(sd.grad).double() - s_ref.grad).abs().max())
+    e2 = float((td.grad.cpu().double() - t_ref.grad).abs().max())
+    assert e1 <= 1e-5 and e2 <= 1e-4 * max(1.0, float(t_ref.grad.abs().max())), (e1, e2)
