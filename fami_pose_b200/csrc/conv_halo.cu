@@ -224,8 +224,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     epi_col_range(p.BN, (warp - kEpiWarp0) >> 2, col_begin, col_end);
     EpiArgs ea;
     ea.spitch = epi_stage_pitch(p.BN, p.out_f32);
-    uint8_t* stage = stage_base + (warp - kEpiWarp0) * 32 * ea.spitch;
-    ea.s_scale = s_scale; ea.s_shift = s_shift; ea.res = p.res; ea.y = p.y;
+    const uint32_t stage = smem_u32(stage_base) + (uint32_t)((warp - kEpiWarp0) * 32 * ea.spitch);
+    ea.s_scale = smem_u32(s_scale); ea.s_shift = smem_u32(s_shift); ea.res = p.res; ea.y = p.y;
     ea.Cout = p.Cout; ea.BN = p.BN; ea.out_pitch = p.out_pitch; ea.res_pitch = p.res_pitch;
     ea.out_f32 = p.out_f32; ea.relu = p.relu; ea.vec_ok = p.vec_ok; ea.up = 1; ea.Wout = p.W;
     int it = 0;

@@ -303,6 +303,84 @@ static int launch_cfg(const ConvParams& p, cudaStream_t st) {
   return 0;
 }
 
+// ---- stem convolution (HRNet conv1: 3 -> 64, 3x3 stride 2; hrnet.py:651) ------------------------------
+// K = 27 is too short for the implicit-GEMM machinery.  One thread computes 16 output channels of 4
+// horizontally adjacent output pixels (64 accumulators): the 27 x 64 weights are read from shared
+// memory once per 4 pixels, which keeps the kernel FMA-bound instead of LDS-bound; 4 threads cover the 64
+// channels of a pixel so a warp writes 128-byte runs.
+template <typename TO>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const ConvParams p) {
+  __shared__ __align__(16) float sw[27 * 64];
+  __shared__ float ssc[64], ssh[64];
+  const float* __restrict__ x = reinterpret_cast<const float*>(p.x);
+  TO* __restrict__ y = reinterpret_cast<TO*>(p.y);
+  for (int i = threadIdx.x; i < 27 * 64; i += 256) sw[i] = p.w[i];
+  if (threadIdx.x < 64) {
+    ssc[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
+    ssh[threadIdx.x] = p.shift ? p.shift[threadIdx.x] : 0.f;
+  }
+  __syncthreads();
+  const int q = threadIdx.x & 3;
+  const int m0 = (blockIdx.x * 64 + (threadIdx.x >> 2)) * 4;   // first of 4 output pixels (same row: Wo % 4 == 0)
+  if (m0 >= p.M) return;
+  const int HoWo = p.Ho * p.Wo;
+  const int n = m0 / HoWo, r = m0 - n * HoWo;
+  const int yo = r / p.Wo, xo = r - yo * p.Wo;
+  float acc[4][16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+#pragma unroll
+  for (int fr = 0; fr < 3; ++fr) {
+    const int iy = yo * 2 - 1 + fr;
+    const bool yok = (unsigned)iy < (unsigned)p.H;
+    const float* row = x + (int64_t)(n * p.H + (yok ? iy : 0)) * p.W * p.in_pitch;
+#pragma unroll
+    for (int fs = 0; fs < 3; ++fs) {
+      float in[4][3];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ix = (xo + i) * 2 - 1 + fs;
+        const bool ok = yok && (unsigned)ix < (unsigned)p.W;
+        const float* px = row + (int64_t)(ok ? ix : 0) * p.in_pitch;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) in[i][c] = ok ? __ldg(px + c) : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int k = (fr * 3 + fs) * 3 + c;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 w = *reinterpret_cast<const float4*>(sw + k * 64 + q * 16 + j4 * 4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float a = in[i][c];
+            acc[i][j4 * 4 + 0] = fmaf(a, w.x, acc[i][j4 * 4 + 0]);
+            acc[i][j4 * 4 + 1] = fmaf(a, w.y, acc[i][j4 * 4 + 1]);
+            acc[i][j4 * 4 + 2] = fmaf(a, w.z, acc[i][j4 * 4 + 2]);
+            acc[i][j4 * 4 + 3] = fmaf(a, w.w, acc[i][j4 * 4 + 3]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    TO* yp = y + (int64_t)(m0 + i) * p.out_pitch + q * 16;
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      float4 o;
+      o.x = fmaf(acc[i][j4 * 4 + 0], ssc[q * 16 + j4 * 4 + 0], ssh[q * 16 + j4 * 4 + 0]);
+      o.y = fmaf(acc[i][j4 * 4 + 1], ssc[q * 16 + j4 * 4 + 1], ssh[q * 16 + j4 * 4 + 1]);
+      o.z = fmaf(acc[i][j4 * 4 + 2], ssc[q * 16 + j4 * 4 + 2], ssh[q * 16 + j4 * 4 + 2]);
+      o.w = fmaf(acc[i][j4 * 4 + 3], ssc[q * 16 + j4 * 4 + 3], ssh[q * 16 + j4 * 4 + 3]);
+      if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      st4<TO>(yp + j4 * 4, o);
+    }
+  }
+}
+
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int MODE, typename TX, typename TO>
@@ -334,6 +412,16 @@ int conv_f32_launch(const fami_conv_desc* d, const float* x, const float* w, con
   p.vec_store = (reinterpret_cast<uintptr_t>(y) % va == 0) && (d->out_pitch % 4 == 0) &&
                 (!res || ((reinterpret_cast<uintptr_t>(res) % va == 0) && d->res_pitch % 4 == 0));
   const bool vec = (d->Cin % 16 == 0) && (d->in_pitch % 4 == 0) && al16(x);
+  // HRNet stem: 3 -> 64, 3x3 stride 2 pad 1, no residual / statistics / upsample
+  if (d->Cin == 3 && d->Cout == 64 && d->kh == 3 && d->stride == 2 && d->pad == 1 && d->dil == 1 && !res && !p.stats &&
+      d->up == 1 && p.vec_store && d->out_pitch % 16 == 0 && d->Wo % 4 == 0) {
+    const int grid = cdiv(p.M, 256);
+    if (d->out_dtype == FAMI_F16) stem_conv_kernel<__half><<<grid, 256, 0, st>>>(p);
+    else if (d->out_dtype == FAMI_BF16) stem_conv_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
+    else stem_conv_kernel<float><<<grid, 256, 0, st>>>(p);
+    FAMI_CHECK_LAUNCH("stem_conv_kernel");
+    return 0;
+  }
   if (d->out_dtype == FAMI_BF16) return dispatch_tile<MODE_SCALAR, float, __nv_bfloat16>(p, st);
   if (d->out_dtype == FAMI_F16) return dispatch_tile<MODE_SCALAR, float, __half>(p, st);
   return vec ? dispatch_tile<MODE_VEC, float, float>(p, st) : dispatch_tile<MODE_SCALAR, float, float>(p, st);

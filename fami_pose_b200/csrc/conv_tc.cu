@@ -152,8 +152,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int Hout = p.Ho * p.up, Wout = p.Wo * p.up;
     EpiArgs ea;
     ea.spitch = epi_stage_pitch(p.BN, p.out_f32);
-    uint8_t* stage = stage_base + (warp - 2) * 32 * ea.spitch;
-    ea.s_scale = s_scale; ea.s_shift = s_shift; ea.res = p.res; ea.y = p.y;
+    const uint32_t stage = smem_u32(stage_base) + (uint32_t)((warp - 2) * 32 * ea.spitch);
+    ea.s_scale = smem_u32(s_scale); ea.s_shift = smem_u32(s_shift); ea.res = p.res; ea.y = p.y;
     ea.Cout = p.Cout; ea.BN = p.BN; ea.out_pitch = p.out_pitch; ea.res_pitch = p.res_pitch;
     ea.out_f32 = p.out_f32; ea.relu = p.relu; ea.vec_ok = p.vec_ok; ea.up = p.up; ea.Wout = Wout;
     int it = 0;
@@ -430,7 +430,7 @@ int debug_umma_rowshift_launch(const void* x, const void* w, float* out, int R, 
 // the halo conv does); 2: as 0 but 4 different accumulator column offsets round-robin.
 // ------------------------------------------------------------------------------------------------
 namespace {
-__global__ void __launch_bounds__(128, 1) umma_rate_probe(long long* out, int N, int iters, int variant) {
+__global__ void __launch_bounds__(512, 1) umma_rate_probe(long long* out, int N, int iters, int variant) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                  // 1024 rows x 128 B
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(128, 1) umma_rate_probe(long long* out, int N,
     __syncwarp();
     mbar_wait(bar_mma, 0);
     long long t2 = clock64();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
       out[0] = t2 - t0;
       out[1] = t1 - t0;
     }
@@ -519,7 +519,9 @@ int debug_umma_rate_launch(long long* out, int N, int iters, int variant, cudaSt
   FAMI_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && iters > 0, "bad N/iters");
   size_t smem = (size_t)(1024 + 256) * 128 + 1024 + 64;
   cudaFuncSetAttribute(umma_rate_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  umma_rate_probe<<<1, 128, smem, st>>>(out, N, iters, variant);
+  const int grid = (variant % 200) >= 100 ? 148 : 1;   // variant + 100: all SMs run the probe concurrently (CTA 0 reports)
+  const int threads = variant >= 200 ? 512 : 128;      // variant + 200: 15 more warps spinning on the completion barrier
+  umma_rate_probe<<<grid, threads, smem, st>>>(out, N, iters, variant % 100);
   FAMI_CHECK_LAUNCH("umma_rate_probe");
   return 0;
 }

@@ -141,6 +141,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const int G = p.G;
     const int npairs = 128 * G;
     typedef typename H2<TH>::t h2;
+    const uint32_t win_u32 = smem_u32(s_win);
     constexpr int kPairs = (128 * 16 + kGatherThreads - 1) / kGatherThreads;   // (pixel, group) pairs per thread, G <= 16
     int stage = 0;
     uint32_t aph = 0, wph = 0;
@@ -187,7 +188,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           }
         }
         mbar_wait(a_empty(stage), aph ^ 1u);
-        uint8_t* a_st = s_a + stage * kATile;
+        const uint32_t a_st = smem_u32(s_a) + (uint32_t)(stage * kATile);
         const float tap_y = (float)(fr * p.d + p.R - p.d), tap_x = (float)(fs * p.d + p.R - p.d);
 #pragma unroll
         for (int j = 0; j < kPairs; ++j) {
@@ -209,10 +210,10 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
               const int row00 = (int)fy * p.WW + (int)fx;
               const int row10 = row00 + p.WW;
               const uint32_t gsel = (uint32_t)(g >> 1), gofs = (uint32_t)(g & 1) << 3;
-              const uint2 u1 = *reinterpret_cast<const uint2*>(s_win + row00 * 128 + ((gsel ^ (uint32_t)(row00 & 7)) << 4) + gofs);
-              const uint2 u2 = *reinterpret_cast<const uint2*>(s_win + (row00 + 1) * 128 + ((gsel ^ (uint32_t)((row00 + 1) & 7)) << 4) + gofs);
-              const uint2 u3 = *reinterpret_cast<const uint2*>(s_win + row10 * 128 + ((gsel ^ (uint32_t)(row10 & 7)) << 4) + gofs);
-              const uint2 u4 = *reinterpret_cast<const uint2*>(s_win + (row10 + 1) * 128 + ((gsel ^ (uint32_t)((row10 + 1) & 7)) << 4) + gofs);
+              const uint2 u1 = lds64(win_u32 + (uint32_t)(row00 * 128) + ((gsel ^ (uint32_t)(row00 & 7)) << 4) + gofs);
+              const uint2 u2 = lds64(win_u32 + (uint32_t)((row00 + 1) * 128) + ((gsel ^ (uint32_t)((row00 + 1) & 7)) << 4) + gofs);
+              const uint2 u3 = lds64(win_u32 + (uint32_t)(row10 * 128) + ((gsel ^ (uint32_t)(row10 & 7)) << 4) + gofs);
+              const uint2 u4 = lds64(win_u32 + (uint32_t)((row10 + 1) * 128) + ((gsel ^ (uint32_t)((row10 + 1) & 7)) << 4) + gofs);
               const float mk = c_mk[j];
               const h2 w1 = H2<TH>::bcast(mk * hy * hx), w2 = H2<TH>::bcast(mk * hy * lx);
               const h2 w3 = H2<TH>::bcast(mk * ly * hx), w4 = H2<TH>::bcast(mk * ly * lx);
@@ -249,7 +250,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
               }
             }
           }
-          *reinterpret_cast<uint2*>(a_st + r * 128 + ((((uint32_t)(g >> 1)) ^ (uint32_t)(r & 7)) << 4) + ((g & 1) << 3)) = pk;
+          sts64(a_st + (uint32_t)(r * 128) + ((((uint32_t)(g >> 1)) ^ (uint32_t)(r & 7)) << 4) + (uint32_t)((g & 1) << 3), pk);
         }
 #pragma unroll
         for (int j = 0; j < kPairs; ++j) { c_dy[j] = n_dy[j]; c_dx[j] = n_dx[j]; c_mk[j] = n_mk[j]; }
@@ -340,11 +341,11 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     EpiArgs ea;
-    ea.s_scale = s_scale; ea.s_shift = s_shift; ea.res = nullptr; ea.y = p.out;
+    ea.s_scale = smem_u32(s_scale); ea.s_shift = smem_u32(s_shift); ea.res = nullptr; ea.y = p.out;
     ea.Cout = p.Cout; ea.BN = p.BN; ea.ch_base = 0; ea.out_pitch = p.out_pitch; ea.res_pitch = 0;
     ea.out_f32 = 0; ea.relu = 0; ea.vec_ok = p.vec_ok; ea.up = 1; ea.Wout = p.W;
     ea.spitch = 128 + 16;
-    uint8_t* stage = stage_base + (warp - kGatherWarps - 1) * 32 * ea.spitch;
+    const uint32_t stage = smem_u32(stage_base) + (uint32_t)((warp - kGatherWarps - 1) * 32 * ea.spitch);
     uint4 no_pre[kPre];
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {

@@ -107,6 +107,33 @@ __device__ __forceinline__ void umma_ksteps_n(int nk, bool leader, uint32_t tmem
   }
 }
 
+// explicit shared-space accesses with 32-bit addresses: pointers derived from the manually aligned dynamic
+// shared-memory base lose their address space and compile to generic LD/ST (slower than LDS/STS)
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint2 v) {
+  asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
+}
+
 // whole-warp wait with a single polling lane (32 lanes polling one mbarrier add contention for nothing)
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane) {
   if (lane == 0) mbar_wait(bar, parity);
@@ -203,8 +230,8 @@ __device__ __forceinline__ void epi_col_range(int BN, int g, int& begin, int& en
 }
 
 struct EpiArgs {
-  const float* s_scale;   // shared memory, indexed by output channel (CoutPad entries; 1/0 defaults)
-  const float* s_shift;
+  uint32_t s_scale;       // shared-memory address of float[CoutPad] (1/0 defaults beyond Cout)
+  uint32_t s_shift;
   const void* res;        // TH, may be null
   void* y;                // TH or float
   int Cout, BN, ch_base;  // ch_base = first output channel of this N tile
@@ -251,12 +278,12 @@ __device__ __forceinline__ bool epi_prefetch(const EpiArgs& a, int col_begin, in
 
 template <typename TH>
 __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr, int col_begin, int col_end, bool valid,
-                                              int pix0, uint8_t* stage, int lane, bool have_pre, uint4 (&pre)[kPre]) {
+                                              int pix0, uint32_t stage, int lane, bool have_pre, uint4 (&pre)[kPre]) {
   if (col_begin >= col_end) return;   // warp-uniform
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
   const int esz = a.out_f32 ? 4 : 2;
   const int gmax = a.out_f32 ? 32 : 64;   // columns per staged group (128 B per row)
-  uint8_t* my_row = stage + lane * a.spitch;
+  const uint32_t my_row = stage + (uint32_t)(lane * a.spitch);
   for (int g0 = col_begin; g0 < col_end; g0 += gmax) {
     const int gc = (col_end - g0 < gmax) ? (col_end - g0) : gmax;
     const int chg = a.ch_base + g0;
@@ -292,7 +319,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
           for (int it = 0; it < 8; ++it) {
             if (it < lpr) {
               const int r = it * rpi + sub_r;
-              if (lane_on) *reinterpret_cast<uint4*>(stage + r * a.spitch + sub_c * 16) = (use_pre && it < kPre) ? pre[it < kPre ? it : 0] : rreg[it];
+              if (lane_on) sts128(stage + (uint32_t)(r * a.spitch + sub_c * 16), (use_pre && it < kPre) ? pre[it < kPre ? it : 0] : rreg[it]);
             }
           }
           __syncwarp();
@@ -306,8 +333,8 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
           float o[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 sc = *reinterpret_cast<const float4*>(a.s_scale + ch0 + 4 * j);
-            const float4 sh = *reinterpret_cast<const float4*>(a.s_shift + ch0 + 4 * j);
+            const float4 sc = lds128f(a.s_scale + (uint32_t)(ch0 + 4 * j) * 4u);
+            const float4 sh = lds128f(a.s_shift + (uint32_t)(ch0 + 4 * j) * 4u);
             o[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
             o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
             o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
@@ -315,8 +342,8 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
           }
           if (grp_vec) {
             if (a.res) {
-              const uint4 r0 = *reinterpret_cast<const uint4*>(my_row + c0 * 2);
-              const uint4 r1 = *reinterpret_cast<const uint4*>(my_row + c0 * 2 + 16);
+              const uint4 r0 = lds128(my_row + (uint32_t)(c0 * 2));
+              const uint4 r1 = lds128(my_row + (uint32_t)(c0 * 2 + 16));
               const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -332,13 +359,13 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
             if (a.out_f32) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<float4*>(my_row + c0 * 4 + 16 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                sts128f(my_row + (uint32_t)(c0 * 4 + 16 * j), make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
             } else {
               uint32_t w[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) w[j] = f2_to_h2<TH>(o[2 * j], o[2 * j + 1]);
-              *reinterpret_cast<uint4*>(my_row + c0 * 2) = make_uint4(w[0], w[1], w[2], w[3]);
-              *reinterpret_cast<uint4*>(my_row + c0 * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+              sts128(my_row + (uint32_t)(c0 * 2), make_uint4(w[0], w[1], w[2], w[3]));
+              sts128(my_row + (uint32_t)(c0 * 2 + 16), make_uint4(w[4], w[5], w[6], w[7]));
             }
           } else if (valid) {
             // ragged tail (Cout not a multiple of the vector width, odd pitches): per-lane scalar path
@@ -364,7 +391,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
               const int r = it * rpi + sub_r;
               const int pr = __shfl_sync(0xffffffffu, pix, r);
               if (lane_on && ((vmask >> r) & 1u)) {
-                const uint4 val = *reinterpret_cast<const uint4*>(stage + r * a.spitch + sub_c * 16);
+                const uint4 val = lds128(stage + (uint32_t)(r * a.spitch + sub_c * 16));
                 uint8_t* dst = reinterpret_cast<uint8_t*>(a.y) + ((int64_t)pr * a.out_pitch + chg) * esz + sub_c * 16;
                 *reinterpret_cast<uint4*>(dst) = val;
               }

@@ -3,9 +3,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from fami_pose_b200 import _lib, ops
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
-for variant in (3, 4, 6, 7, 8):
-    for N in (48, 96):
-        for iters in (81, 810):
+for variant in (3, 203, 4, 204):
+    for N in (48, 192):
+        for iters in (810,):
             _lib.call("fami_debug_umma_rate", ops._ptr(out), N, iters, variant, ops._stream())
             torch.cuda.synchronize()
             tot, iss = out.tolist()
