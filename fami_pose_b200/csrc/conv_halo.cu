@@ -196,8 +196,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 b_lo = sw128_desc_lo(smem_u32(smemB + (size_t)sb * p.b_tile_bytes));
               }
               const bool acc_first = (cc | tap) != 0;
-              uint32_t a_lo = a_tap + (uint32_t)issuer * 1024u, dcol = d_tmem + (uint32_t)(issuer * p.BN);
+              uint32_t a_lo = ((p.trace & 4) ? a_lo0 : a_tap) + (uint32_t)issuer * 1024u, dcol = d_tmem + (uint32_t)(issuer * p.BN);
               const uint32_t a_inc = (uint32_t)p.n_iss * 1024u, d_inc = (uint32_t)(p.n_iss * p.BN);
+              if (p.trace & 8) b_lo = sw128_desc_lo(smem_u32(smemB));
               for (int m = issuer; m < p.NM; m += p.n_iss, a_lo += a_inc, dcol += d_inc)
                 umma_ksteps_n(nk, leader, dcol, a_lo, b_lo, idesc, acc_first);
               if (leader && tap < 8 && issuer == 0) trace(p.trace, 3, it, tap);
@@ -400,6 +401,7 @@ int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, cons
   p.out_pitch = d->out_pitch; p.res_pitch = d->res_pitch;
   p.sA = c.sA; p.sB = c.sB; p.b_resident = c.b_resident; p.acc_bufs = c.acc_bufs;
   p.n_iss = c.NM < kMmaWarps ? c.NM : kMmaWarps;
+  if (getenv("FAMI_HALO_ISS")) { int v = atoi(getenv("FAMI_HALO_ISS")); if (v >= 1 && v <= p.n_iss) p.n_iss = v; }
   p.a_stage_bytes = (uint32_t)c.HR * 128u;
   p.b_tile_bytes = (uint32_t)c.BN * 128u;
   p.a_box_bytes = (uint32_t)((c.BH + 2 * dl) * Wp) * 128u;
