@@ -1,15 +1,17 @@
 // Modulated deformable convolution v2 on B200 -- the north-star kernel (fami_dcn_fwd, 16-bit arm).
 // Replaces torchvision.ops.deform_conv2d as called at posetimation/zoo/Alignment/Alignment_V15.py:146-158.
 //
-// Structure (persistent CTAs, one 16x8-pixel tile at a time, 672 threads):
+// Structure (persistent CTAs, one 16x8-pixel tile at a time, 544 threads):
 //   * the x neighbourhood of the tile ((16+2R) x (8+2R) pixels x 64 channel slots) is brought ONCE into
 //     shared memory by a TMA tiled box load (128B-swizzled rows; out-of-image pixels zero-filled, which
 //     is exactly torchvision's "corner outside the image contributes 0" rule);
-//   * 16 gather warps walk the taps: thread (pixel, offset group) reads its (dy, dx, mask) -- streamed
-//     from HBM exactly once, in the tap-major layout the fused offset|mask conv writes -- forms the four
-//     bilinear corners from shared memory (8-byte loads, swizzle keeps them nearly conflict free), and
-//     stores 4 modulated fp16 columns into the UMMA A tile of that tap (128B-swizzled K-major);
-//     samples that fall outside the staged window take a bounds-checked global path;
+//   * 12 gather warps in three groups; group q owns UMMA A stage q and taps q, q+3, q+6. A thread is one
+//     output pixel: per tap it reads the pixel's 3*G (dy | dx | mask) floats as 16-byte loads -- streamed
+//     from HBM exactly once, in the tap-major layout the fused offset|mask conv writes -- and for each
+//     offset group forms the four bilinear corners from shared memory (8-byte loads), blends them in
+//     packed 16-bit arithmetic and stores the modulated columns into the A tile (128B-swizzled K-major,
+//     16-byte stores). Samples outside the staged window are collected in a bit mask and resolved
+//     afterwards through a bounds-checked global path;
 //   * one warp issues tcgen05.mma (M=128, N=Cout, K=C per tap) against the weights resident in shared
 //     memory, accumulating the nine taps in TMEM (double buffered across tiles);
 //   * 4 epilogue warps add the bias and store the tile (coalesced, through shared-memory staging).
@@ -34,10 +36,10 @@ __device__ __forceinline__ void dtrace(int on, int it, int ev) {
 }
 
 constexpr int kTH = 16, kTW = 8;            // output tile (pixels): 128 = one UMMA M tile
-constexpr int kGatherWarps = 16;
+constexpr int kGatherWarps = 12;          // 3 groups x 4 warps: group q <-> A stage q <-> taps q, q+3, q+6
 constexpr int kGatherThreads = 32 * kGatherWarps;
 constexpr int kDcnEpiWarps = 4;
-constexpr int kDcnThreads = kGatherThreads + 32 + 32 * kDcnEpiWarps;   // 672
+constexpr int kDcnThreads = kGatherThreads + 32 + 32 * kDcnEpiWarps;   // 544
 constexpr int kAStages = 3;
 constexpr int kATile = 128 * 128;          // bytes per A stage
 
@@ -84,7 +86,7 @@ template <> struct H2<__nv_bfloat16> {
   static __device__ __forceinline__ t mul(t a, t b) { return __hmul2(a, b); }
 };
 
-template <typename TH>
+template <typename TH, int kG>
 __global__ void __launch_bounds__(kDcnThreads, 1)
 dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const DcnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -111,7 +113,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     mbar_init(win_full, 1);
     mbar_init(win_free, kGatherWarps);
     mbar_init(w_full, 1);
-    for (int s = 0; s < kAStages; ++s) { mbar_init(a_full(s), kGatherWarps); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < kAStages; ++s) { mbar_init(a_full(s), kGatherWarps / kAStages); mbar_init(a_empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), kDcnEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
@@ -137,131 +139,151 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 
   if (warp < kGatherWarps) {
     // ===================== gather warps =====================
-    const TH* xg = reinterpret_cast<const TH*>(p.x);
-    const int G = p.G;
-    const int npairs = 128 * G;
+    // Three groups of four warps; group q owns A stage q and the taps q, q+3, q+6 (kernel column q).
+    // A thread is one output pixel of the tile and walks all kG offset groups of a (pixel, tap) unit:
+    // the 3*kG floats of the unit are one contiguous 16-byte-aligned run in the tap-major layout.
+    constexpr int kQ = kG / 4;
     typedef typename H2<TH>::t h2;
+    const TH* xg = reinterpret_cast<const TH*>(p.x);
     const uint32_t win_u32 = smem_u32(s_win);
-    constexpr int kPairs = (128 * 16 + kGatherThreads - 1) / kGatherThreads;   // (pixel, group) pairs per thread, G <= 16
-    int stage = 0;
-    uint32_t aph = 0, wph = 0;
+    const int q = warp >> 2;
+    const int r = threadIdx.x & 127;
+    const int ry = r >> 3, rx = r & 7;
+    const uint32_t a_row = smem_u32(s_a) + (uint32_t)(q * kATile + r * 128);
+    const uint32_t rsw = (uint32_t)(r & 7) << 4;
+    const int WW = p.WW;
+    const unsigned ylim = (unsigned)(p.WH - 1), xlim = (unsigned)(WW - 1);
+    const float base_x = (float)(rx + q * p.d + p.R - p.d);
+    uint32_t use = 0, wph = 0, fph = 0;
     int git = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++git) {
       int b, y0, x0;
       tile_origin(tile, b, y0, x0);
       if (threadIdx.x == 0) dtrace(p.trace, git, 0);
-      // this thread's pairs are the same for all nine taps: resolve them once per tile
-      int pr_rg[kPairs];                    // r | g << 8, or -1
-      const float* pr_o[kPairs];            // &om[pixel][tap 0][dy][g]; nullptr if the pixel is outside the image
+      const int y = y0 + ry, x = x0 + rx;
+      const bool valid = y < p.H && x < p.W;
+      const float* po = p.om + ((int64_t)(b * p.H + y) * p.W + x) * p.om_pitch;
+      float4 vdy[kQ], vdx[kQ], vmk[kQ];
+      auto load_unit = [&](int tap) {
+        const float4* o = reinterpret_cast<const float4*>(po + tap * 3 * kG);
 #pragma unroll
-      for (int j = 0; j < kPairs; ++j) {
-        const int pair = threadIdx.x + j * kGatherThreads;
-        pr_o[j] = nullptr;
-        pr_rg[j] = -1;
-        if (pair < npairs) {
-          const int r = pair / G, g = pair - r * G;
-          const int y = y0 + (r >> 3), x = x0 + (r & 7);
-          pr_rg[j] = r | (g << 8);
-          if (y < p.H && x < p.W) pr_o[j] = p.om + ((int64_t)(b * p.H + y) * p.W + x) * p.om_pitch + g;
-        }
-      }
-      // software pipeline: the (dy, dx, mask) triples of tap t+1 are in flight while tap t is gathered
-      float c_dy[kPairs], c_dx[kPairs], c_mk[kPairs], n_dy[kPairs], n_dx[kPairs], n_mk[kPairs];
-#pragma unroll
-      for (int j = 0; j < kPairs; ++j) {
-        c_dy[j] = c_dx[j] = c_mk[j] = 0.f;
-        if (pr_o[j]) { c_dy[j] = __ldg(pr_o[j]); c_dx[j] = __ldg(pr_o[j] + G); c_mk[j] = __ldg(pr_o[j] + 2 * G); }
-      }
+        for (int i = 0; i < kQ; ++i) { vdy[i] = __ldg(o + i); vdx[i] = __ldg(o + kQ + i); vmk[i] = __ldg(o + 2 * kQ + i); }
+      };
+      if (valid) load_unit(q);
       mbar_wait(win_full, wph);
       wph ^= 1u;
       if (threadIdx.x == 0) dtrace(p.trace, git, 1);
-      for (int tap = 0; tap < 9; ++tap) {
-        const int fr = tap / 3, fs = tap - fr * 3;
-        if (tap + 1 < 9) {
+#pragma unroll 1
+      for (int k = 0; k < 3; ++k) {
+        const int tap = q + 3 * k;          // kernel row k, kernel column q
+        mbar_wait(a_empty(q), (use & 1u) ^ 1u);
+        ++use;
+        if (threadIdx.x == 0) dtrace(p.trace, git, 5 + k);
+        if (!valid) {
 #pragma unroll
-          for (int j = 0; j < kPairs; ++j) {
-            n_dy[j] = n_dx[j] = n_mk[j] = 0.f;
-            if (pr_o[j] && !(p.trace & 2)) {
-              const float* o = pr_o[j] + (tap + 1) * 3 * G;
-              n_dy[j] = __ldg(o); n_dx[j] = __ldg(o + G); n_mk[j] = __ldg(o + 2 * G);
-            }
-          }
-        }
-        mbar_wait(a_empty(stage), aph ^ 1u);
-        const uint32_t a_st = smem_u32(s_a) + (uint32_t)(stage * kATile);
-        const float tap_y = (float)(fr * p.d + p.R - p.d), tap_x = (float)(fs * p.d + p.R - p.d);
+          for (int c = 0; c < kG / 2; ++c) sts128(a_row + (((uint32_t)c << 4) ^ rsw), make_uint4(0u, 0u, 0u, 0u));
+        } else {
+          const float base_y = (float)(ry + k * p.d + p.R - p.d);
+          uint32_t slow = 0;
 #pragma unroll
-        for (int j = 0; j < kPairs; ++j) {
-          if (pr_rg[j] < 0) continue;
-          const int r = pr_rg[j] & 255, g = pr_rg[j] >> 8;
-          uint2 pk = make_uint2(0u, 0u);
-          if (pr_o[j]) {
-            // window coordinates: integer shifts of the image-space sample position, so the fractional
-            // parts are exactly those of py / px
-            const float wy = (float)(r >> 3) + tap_y + c_dy[j];
-            const float wx = (float)(r & 7) + tap_x + c_dx[j];
-            if (p.trace & 8) {
-              pk.x = __float_as_uint(wy); pk.y = __float_as_uint(wx);   // experiment: no window loads / blend
-            } else if (wy >= 0.f && wy < (float)(p.WH - 1) && wx >= 0.f && wx < (float)(p.WW - 1)) {
-              // all four corners inside the staged (zero-padded) window: 8-byte shared-memory loads,
-              // blend in packed 16-bit arithmetic (the column is rounded to 16 bit for the MMA anyway)
+          for (int i = 0; i < kQ; ++i) {
+            const float dy4[4] = {vdy[i].x, vdy[i].y, vdy[i].z, vdy[i].w};
+            const float dx4[4] = {vdx[i].x, vdx[i].y, vdx[i].z, vdx[i].w};
+            const float mk4[4] = {vmk[i].x, vmk[i].y, vmk[i].z, vmk[i].w};
+            uint32_t pk[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int g = 4 * i + e;
+              // window coordinates: integer shifts of the image-space sample position, so the fractional
+              // parts are exactly those of py / px
+              const float wy = base_y + dy4[e], wx = base_x + dx4[e];
               const float fy = floorf(wy), fx = floorf(wx);
-              const float ly = wy - fy, lx = wx - fx, hy = 1.f - ly, hx = 1.f - lx;
-              const int row00 = (int)fy * p.WW + (int)fx;
-              const int row10 = row00 + p.WW;
-              const uint32_t gsel = (uint32_t)(g >> 1), gofs = (uint32_t)(g & 1) << 3;
-              const uint2 u1 = lds64(win_u32 + (uint32_t)(row00 * 128) + ((gsel ^ (uint32_t)(row00 & 7)) << 4) + gofs);
-              const uint2 u2 = lds64(win_u32 + (uint32_t)((row00 + 1) * 128) + ((gsel ^ (uint32_t)((row00 + 1) & 7)) << 4) + gofs);
-              const uint2 u3 = lds64(win_u32 + (uint32_t)(row10 * 128) + ((gsel ^ (uint32_t)(row10 & 7)) << 4) + gofs);
-              const uint2 u4 = lds64(win_u32 + (uint32_t)((row10 + 1) * 128) + ((gsel ^ (uint32_t)((row10 + 1) & 7)) << 4) + gofs);
-              const float mk = c_mk[j];
-              const h2 w1 = H2<TH>::bcast(mk * hy * hx), w2 = H2<TH>::bcast(mk * hy * lx);
-              const h2 w3 = H2<TH>::bcast(mk * ly * hx), w4 = H2<TH>::bcast(mk * ly * lx);
-              h2 lo = H2<TH>::mul(w1, *reinterpret_cast<const h2*>(&u1.x));
-              h2 hi = H2<TH>::mul(w1, *reinterpret_cast<const h2*>(&u1.y));
-              lo = H2<TH>::fma(w2, *reinterpret_cast<const h2*>(&u2.x), lo);
-              hi = H2<TH>::fma(w2, *reinterpret_cast<const h2*>(&u2.y), hi);
-              lo = H2<TH>::fma(w3, *reinterpret_cast<const h2*>(&u3.x), lo);
-              hi = H2<TH>::fma(w3, *reinterpret_cast<const h2*>(&u3.y), hi);
-              lo = H2<TH>::fma(w4, *reinterpret_cast<const h2*>(&u4.x), lo);
-              hi = H2<TH>::fma(w4, *reinterpret_cast<const h2*>(&u4.y), hi);
-              pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-              pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-            } else {
-              // large offset: sample lies outside the staged window -> bounds-checked global corners (fp32 blend)
-              const float py = (float)(y0 + (r >> 3) - p.d + fr * p.d) + c_dy[j];
-              const float px = (float)(x0 + (r & 7) - p.d + fs * p.d) + c_dx[j];
-              if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
-                const int iy0 = (int)floorf(py), ix0 = (int)floorf(px);
-                const float ly = py - (float)iy0, lx = px - (float)ix0, hy = 1.f - ly, hx = 1.f - lx;
-                const TH* xb = xg + (int64_t)b * p.H * p.W * p.x_pitch + g * 4;
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                const bool y0ok = iy0 >= 0, y1ok = iy0 + 1 <= p.H - 1, x0ok = ix0 >= 0, x1ok = ix0 + 1 <= p.W - 1;
-                const float4 v1 = (y0ok && x0ok) ? ld4h<TH>(xb + ((int64_t)iy0 * p.W + ix0) * p.x_pitch) : z;
-                const float4 v2 = (y0ok && x1ok) ? ld4h<TH>(xb + ((int64_t)iy0 * p.W + ix0 + 1) * p.x_pitch) : z;
-                const float4 v3 = (y1ok && x0ok) ? ld4h<TH>(xb + ((int64_t)(iy0 + 1) * p.W + ix0) * p.x_pitch) : z;
-                const float4 v4 = (y1ok && x1ok) ? ld4h<TH>(xb + ((int64_t)(iy0 + 1) * p.W + ix0 + 1) * p.x_pitch) : z;
-                const float mk = c_mk[j];
-                const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-                pk.x = f2_to_h2<TH>(mk * (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x),
-                                    mk * (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y));
-                pk.y = f2_to_h2<TH>(mk * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z),
-                                    mk * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w));
+              const int iy = (int)fy, ix = (int)fx;
+              pk[2 * e] = 0u; pk[2 * e + 1] = 0u;
+              if ((unsigned)iy < ylim && (unsigned)ix < xlim) {
+                // all four corners inside the staged (zero-padded) window: 8-byte shared-memory loads,
+                // blend in packed 16-bit arithmetic (the column is rounded to 16 bit for the MMA anyway)
+                const float ly = wy - fy, lx = wx - fx;
+                const float mk = mk4[e];
+                const float wb = mk * ly, wt = mk - wb;          // mask * (ly | 1 - ly)
+                const float w4f = wb * lx, w3f = wb - w4f, w2f = wt * lx, w1f = wt - w2f;
+                const uint32_t row00 = (uint32_t)(iy * WW + ix);
+                const uint32_t row10 = row00 + (uint32_t)WW;
+                const uint32_t gs = (uint32_t)(g >> 1) << 4, gofs = (uint32_t)(g & 1) << 3;
+                const uint2 u1 = lds64(win_u32 + row00 * 128u + ((gs ^ (row00 << 4)) & 0x70u) + gofs);
+                const uint2 u2 = lds64(win_u32 + (row00 + 1u) * 128u + ((gs ^ ((row00 + 1u) << 4)) & 0x70u) + gofs);
+                const uint2 u3 = lds64(win_u32 + row10 * 128u + ((gs ^ (row10 << 4)) & 0x70u) + gofs);
+                const uint2 u4 = lds64(win_u32 + (row10 + 1u) * 128u + ((gs ^ ((row10 + 1u) << 4)) & 0x70u) + gofs);
+                const h2 w1 = H2<TH>::bcast(w1f), w2 = H2<TH>::bcast(w2f), w3 = H2<TH>::bcast(w3f), w4 = H2<TH>::bcast(w4f);
+                h2 lo = H2<TH>::mul(w1, *reinterpret_cast<const h2*>(&u1.x));
+                h2 hi = H2<TH>::mul(w1, *reinterpret_cast<const h2*>(&u1.y));
+                lo = H2<TH>::fma(w2, *reinterpret_cast<const h2*>(&u2.x), lo);
+                hi = H2<TH>::fma(w2, *reinterpret_cast<const h2*>(&u2.y), hi);
+                lo = H2<TH>::fma(w3, *reinterpret_cast<const h2*>(&u3.x), lo);
+                hi = H2<TH>::fma(w3, *reinterpret_cast<const h2*>(&u3.y), hi);
+                lo = H2<TH>::fma(w4, *reinterpret_cast<const h2*>(&u4.x), lo);
+                hi = H2<TH>::fma(w4, *reinterpret_cast<const h2*>(&u4.y), hi);
+                pk[2 * e] = *reinterpret_cast<const uint32_t*>(&lo);
+                pk[2 * e + 1] = *reinterpret_cast<const uint32_t*>(&hi);
+              } else {
+                slow |= 1u << g;          // outside the staged window: resolved below from global memory
               }
             }
+            sts128(a_row + (((uint32_t)(2 * i) << 4) ^ rsw), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+            sts128(a_row + (((uint32_t)(2 * i + 1) << 4) ^ rsw), make_uint4(pk[4], pk[5], pk[6], pk[7]));
           }
-          sts64(a_st + (uint32_t)(r * 128) + ((((uint32_t)(g >> 1)) ^ (uint32_t)(r & 7)) << 4) + (uint32_t)((g & 1) << 3), pk);
+          // large offsets: bounds-checked global corners, fp32 blend (rare; kept out of the main loop so a
+          // single far sample does not serialise the warp through this path once per group)
+          while (slow) {
+            const int g = __ffs((int)slow) - 1;
+            slow &= slow - 1u;
+            const float* o = po + tap * 3 * kG + g;
+            const float dy = __ldg(o), dx = __ldg(o + kG), mk = __ldg(o + 2 * kG);
+            const float py = (float)(y - p.d + k * p.d) + dy;
+            const float px = (float)(x - p.d + q * p.d) + dx;
+            uint2 pk2 = make_uint2(0u, 0u);
+            if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
+              const int iy0 = (int)floorf(py), ix0 = (int)floorf(px);
+              const float ly = py - (float)iy0, lx = px - (float)ix0, hy = 1.f - ly, hx = 1.f - lx;
+              const TH* xb = xg + (int64_t)b * p.H * p.W * p.x_pitch + g * 4;
+              const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+              const bool y0ok = iy0 >= 0, y1ok = iy0 + 1 <= p.H - 1, x0ok = ix0 >= 0, x1ok = ix0 + 1 <= p.W - 1;
+              const float4 v1 = (y0ok && x0ok) ? ld4h<TH>(xb + ((int64_t)iy0 * p.W + ix0) * p.x_pitch) : z;
+              const float4 v2 = (y0ok && x1ok) ? ld4h<TH>(xb + ((int64_t)iy0 * p.W + ix0 + 1) * p.x_pitch) : z;
+              const float4 v3 = (y1ok && x0ok) ? ld4h<TH>(xb + ((int64_t)(iy0 + 1) * p.W + ix0) * p.x_pitch) : z;
+              const float4 v4 = (y1ok && x1ok) ? ld4h<TH>(xb + ((int64_t)(iy0 + 1) * p.W + ix0 + 1) * p.x_pitch) : z;
+              const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+              pk2.x = f2_to_h2<TH>(mk * (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x),
+                                   mk * (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y));
+              pk2.y = f2_to_h2<TH>(mk * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z),
+                                   mk * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w));
+            }
+            sts64(a_row + ((((uint32_t)(g >> 1)) << 4) ^ rsw) + (uint32_t)((g & 1) << 3), pk2);
+          }
         }
-#pragma unroll
-        for (int j = 0; j < kPairs; ++j) { c_dy[j] = n_dy[j]; c_dx[j] = n_dx[j]; c_mk[j] = n_mk[j]; }
-        if (!(p.trace & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
+        if (threadIdx.x == 0) dtrace(p.trace, git, 8 + k);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_full(stage));   // one arrival per warp: 512 same-address arrivals would serialise
-        if (threadIdx.x == 0) dtrace(p.trace, git, 2 + tap);
-        if (++stage == kAStages) { stage = 0; aph ^= 1u; }
+        if (lane == 0) mbar_arrive(a_full(q));   // one arrival per warp
+        if (threadIdx.x == 0) dtrace(p.trace, git, 2 + k);
+        if (k < 2 && valid) load_unit(tap + 3);   // in flight while the MMA drains this stage
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(win_free);   // this warp no longer reads the window of this tile
+      if (warp == 0) {
+        // refill the window for the next tile as soon as the last gather warp has left it (issued from here,
+        // not from the MMA warp, which is still draining the last taps)
+        mbar_wait(win_free, fph);
+        fph ^= 1u;
+        const int next = tile + gridDim.x;
+        if (lane == 0 && next < p.total_tiles) {
+          int nb, ny0, nx0;
+          tile_origin(next, nb, ny0, nx0);
+          mbar_arrive_expect_tx(win_full, p.win_bytes);
+          tma_tiled_4d(smem_u32(s_win), &tmX, win_full, 0, nx0 - p.R, ny0 - p.R, nb);
+        }
+        __syncwarp();
+      }
     }
   } else if (warp == kGatherWarps) {
     // ===================== TMA + MMA issuer (warp-uniform control flow, elected lane issues) =====
@@ -298,13 +320,17 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         }
         prefetch_om(b, y0, x0);
       }
+      if ((int)(blockIdx.x + gridDim.x) < p.total_tiles) {
+        tile_origin(blockIdx.x + gridDim.x, b, y0, x0);
+        prefetch_om(b, y0, x0);
+      }
     }
     mbar_wait(w_full, 0);
     tc_fence_after();
     const uint32_t w_lo0 = sw128_desc_lo(smem_u32(s_w));
     const uint32_t w_step = p.w_tile_bytes >> 4;
     int stage = 0;
-    uint32_t aph = 0, fph = 0;
+    uint32_t aph = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -322,17 +348,11 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         if (++stage == kAStages) { stage = 0; aph ^= 1u; }
       }
       if (leader) umma_commit(tfull(acc));
-      // all gathers of this tile are done (the last a_full completed): refill the window for the next tile
-      const int next = tile + gridDim.x;
-      mbar_wait(win_free, fph);
-      fph ^= 1u;
+      // pull the offsets|masks of the tile after next towards L2 (the window refill is issued by gather warp 0)
+      const int next = tile + 2 * gridDim.x;
       if (next < p.total_tiles) {
         int b, y0, x0;
         tile_origin(next, b, y0, x0);
-        if (leader) {
-          mbar_arrive_expect_tx(win_full, p.win_bytes);
-          tma_tiled_4d(smem_u32(s_win), &tmX, win_full, 0, x0 - p.R, y0 - p.R, b);
-        }
         prefetch_om(b, y0, x0);
       }
     }
@@ -378,7 +398,8 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 
 int dcn_tc_supported(const fami_dcn_desc* d) {
   if (!is_half_dtype(d->dtype) || d->om_layout != 1) return 0;
-  if (d->C % 16 != 0 || d->C > 64 || d->C / d->G != 4) return 0;
+  if (d->C % 16 != 0 || d->C > 64 || d->G * 4 != d->C) return 0;      // G in {4, 8, 12, 16}
+  if (d->off_pitch % 4 != 0) return 0;                                  // 16-byte loads of the (dy|dx|mask) runs
   if (d->Cout > 256 || d->x_pitch % 8 != 0) return 0;
   if (d->kh != 3 || d->kw != 3 || d->pad != d->dil || d->dil > 4) return 0;
   return 1;
@@ -389,6 +410,7 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
   FAMI_CHECK_ARG(load_driver_fns(), "cuTensorMapEncode* driver entry points unavailable");
   FAMI_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
                  "dcn_tc: x / w must be 16-byte aligned");
+  FAMI_CHECK_ARG((reinterpret_cast<uintptr_t>(om) & 15) == 0, "dcn_tc: offsets|masks must be 16-byte aligned");
   DcnTcParams p;
   memset(&p, 0, sizeof(p));
   p.B = d->B; p.H = d->H; p.W = d->W; p.C = d->C; p.Cout = d->Cout; p.G = d->G; p.d = d->dil;
@@ -410,7 +432,9 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
   const CUtensorMapDataType tm_dtype = d->dtype == FAMI_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap tmX, tmW;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)d->C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    // a pitch of >= 64 slots lets the box read whole 128-byte rows without out-of-bounds fill on the channel axis
+    // (slots C..63 are never consumed: the gather only reads channels < C)
+    cuuint64_t dims[4] = {(cuuint64_t)(d->x_pitch >= 64 ? 64 : d->C), (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
     cuuint64_t strides[3] = {(cuuint64_t)d->x_pitch * 2, (cuuint64_t)d->W * d->x_pitch * 2,
                              (cuuint64_t)d->H * d->W * d->x_pitch * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)p.WW, (cuuint32_t)p.WH, 1};
@@ -434,19 +458,32 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
   const size_t smem = (size_t)p.win_bytes + kAStages * kATile + 9 * (size_t)p.w_tile_bytes + 1024 + 256 +
                       (size_t)p.BN * 8 + (size_t)kDcnEpiWarps * 32 * (128 + 16);
   FAMI_CHECK_ARG(smem <= 227 * 1024, "dcn_tc: shared memory budget exceeded (%zu B)", smem);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(dcn_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(dcn_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_done = true;
-  }
   int grid = p.total_tiles;
   const int sms = num_sms();
   if (grid > sms) grid = sms;
-  if (d->dtype == FAMI_F16)
-    dcn_tc_kernel<__half><<<grid, kDcnThreads, smem, st>>>(tmX, tmW, p);
-  else
-    dcn_tc_kernel<__nv_bfloat16><<<grid, kDcnThreads, smem, st>>>(tmX, tmW, p);
+#define FAMI_DCN_LAUNCH(TH_, G_)                                                                              \
+  {                                                                                                            \
+    static bool attr_done = false;                                                                             \
+    if (!attr_done) {                                                                                          \
+      cudaFuncSetAttribute(dcn_tc_kernel<TH_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   \
+      attr_done = true;                                                                                        \
+    }                                                                                                          \
+    dcn_tc_kernel<TH_, G_><<<grid, kDcnThreads, smem, st>>>(tmX, tmW, p);                                      \
+  }
+#define FAMI_DCN_LAUNCH_G(TH_)                                                  \
+  switch (d->G) {                                                                \
+    case 4: FAMI_DCN_LAUNCH(TH_, 4) break;                                       \
+    case 8: FAMI_DCN_LAUNCH(TH_, 8) break;                                       \
+    case 12: FAMI_DCN_LAUNCH(TH_, 12) break;                                     \
+    default: FAMI_DCN_LAUNCH(TH_, 16) break;                                     \
+  }
+  if (d->dtype == FAMI_F16) {
+    FAMI_DCN_LAUNCH_G(__half)
+  } else {
+    FAMI_DCN_LAUNCH_G(__nv_bfloat16)
+  }
+#undef FAMI_DCN_LAUNCH_G
+#undef FAMI_DCN_LAUNCH
   FAMI_CHECK_LAUNCH("dcn_tc_kernel");
   return 0;
 }
