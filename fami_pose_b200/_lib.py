@@ -59,6 +59,15 @@ SIGNATURES = {
                                        c_int, c_int, c_int, c_int, c_void_p]),
     "fami_softmax_pkl_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                      c_float, c_void_p]),
+    "fami_pack_conv_weight_dgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "fami_conv2d_dgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fami_conv2d_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fami_bn_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64,
+                            c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "fami_softmax_pkl_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                     c_int, c_int, c_int, c_float, c_void_p]),
+    "fami_linear_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                c_void_p]),
     "fami_debug_read_trace": (c_int, [c_void_p, c_int]),
     "fami_debug_umma_rate": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "fami_debug_umma_rowshift": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -44,6 +44,16 @@ int conv_halo_supported(const fami_conv_desc* d);
 int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
                      const void* res, void* y, cudaStream_t st);
 int pack_w_bf16_launch(const float* w, void* out, int Cout, int Cin, int kh, int kw, int dtype, cudaStream_t st);
+int flip_transpose_launch(const float* w, float* wt, int Cout, int Cin, int kh, int kw, cudaStream_t st);
+int conv_dgrad_launch(const fami_conv_desc* d, const float* gy, const float* wt_packed, float* gx, cudaStream_t st);
+int conv_wgrad_launch(const fami_conv_desc* d, const float* x, const float* gy, float* dw, float* dbias, cudaStream_t st);
+int bn_bwd_launch(const float* x, int xp, const float* gy, int gp, const float* y, int yp, const float* mean,
+                  const float* invstd, const float* gamma, int64_t rows, int C, int training, double* sums, float* dx,
+                  int dxp, float* g_res, int grp, float* dgamma, float* dbeta, cudaStream_t st);
+int softmax_pkl_bwd_launch(const float* a, int ap, const float* b, int bp, const float* gout, float* ga, int gap, float* gb,
+                           int gbp, int B, int HW, int C, float temperature, cudaStream_t st);
+int linear_bwd_launch(const float* x, const float* w, const float* gy, float* gx, float* gw, float* gb, int M, int K, int N,
+                      cudaStream_t st);
 int dcn_tc_supported(const fami_dcn_desc* d);
 int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const void* w, const float* bias, void* out,
                   cudaStream_t st);
@@ -151,6 +161,65 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
   }
   return conv_f32_launch(d, (const float*)x, (const float*)w_packed, scale, shift, residual, y, stats_out,
                          (cudaStream_t)stream);
+}
+
+static int check_conv_bwd(const fami_conv_desc* d, const char* who) {
+  FAMI_CHECK_ARG(d, "%s: null desc", who);
+  FAMI_CHECK_ARG(d->dtype == FAMI_F32 && d->out_dtype == FAMI_F32, "%s: fp32 storage only", who);
+  FAMI_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "%s: bad shape", who);
+  FAMI_CHECK_ARG(d->kh == d->kw && (d->kh == 1 || d->kh == 3), "%s: kernel %dx%d unsupported", who, d->kh, d->kw);
+  FAMI_CHECK_ARG(d->stride >= 1 && d->dil >= 1 && d->pad >= 0 && d->up == 1, "%s: bad stride/dil/pad/up", who);
+  int Ho = (d->H + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
+  int Wo = (d->W + 2 * d->pad - d->dil * (d->kw - 1) - 1) / d->stride + 1;
+  FAMI_CHECK_ARG(Ho == d->Ho && Wo == d->Wo, "%s: Ho/Wo (%d,%d) inconsistent, expected (%d,%d)", who, d->Ho, d->Wo, Ho, Wo);
+  FAMI_CHECK_ARG(d->in_pitch >= d->Cin && d->out_pitch >= d->Cout, "%s: pitch < channels", who);
+  return 0;
+}
+
+int fami_pack_conv_weight_dgrad(const float* w_oihw, float* scratch_oihw, void* w_packed_t, int Cout, int Cin, int kh,
+                                int kw, int dtype, void* stream) {
+  FAMI_CHECK_ARG(w_oihw && scratch_oihw && w_packed_t, "fami_pack_conv_weight_dgrad: null pointer");
+  FAMI_CHECK_ARG(dtype == FAMI_F32, "fami_pack_conv_weight_dgrad: fp32 only");
+  if (int e = flip_transpose_launch(w_oihw, scratch_oihw, Cout, Cin, kh, kw, (cudaStream_t)stream)) return e;
+  return fami_pack_conv_weight(scratch_oihw, w_packed_t, Cin, Cout, kh, kw, dtype, stream);
+}
+
+int fami_conv2d_dgrad(const fami_conv_desc* d, const float* grad_y, const float* w_packed_t, float* grad_x, void* stream) {
+  if (int e = check_conv_bwd(d, "fami_conv2d_dgrad")) return e;
+  FAMI_CHECK_ARG(grad_y && w_packed_t && grad_x, "fami_conv2d_dgrad: null pointer");
+  FAMI_CHECK_ARG(d->stride > 1 || d->dil * (d->kh - 1) - d->pad >= 0, "fami_conv2d_dgrad: pad larger than the filter reach");
+  return conv_dgrad_launch(d, grad_y, w_packed_t, grad_x, (cudaStream_t)stream);
+}
+
+int fami_conv2d_wgrad(const fami_conv_desc* d, const float* x, const float* grad_y, float* grad_w_oihw, float* grad_bias,
+                      void* stream) {
+  if (int e = check_conv_bwd(d, "fami_conv2d_wgrad")) return e;
+  FAMI_CHECK_ARG(x && grad_y && grad_w_oihw, "fami_conv2d_wgrad: null pointer");
+  return conv_wgrad_launch(d, x, grad_y, grad_w_oihw, grad_bias, (cudaStream_t)stream);
+}
+
+int fami_bn_bwd(const float* x, int x_pitch, const float* grad_y, int gy_pitch, const float* y, int y_pitch,
+                const float* mean, const float* invstd, const float* gamma, int64_t rows, int C, int training,
+                double* sums, float* grad_x, int gx_pitch, float* grad_res, int gres_pitch, float* grad_gamma,
+                float* grad_beta, void* stream) {
+  FAMI_CHECK_ARG(x && grad_y && mean && invstd && sums, "fami_bn_bwd: null pointer");
+  FAMI_CHECK_ARG(rows > 0 && C > 0 && C <= 1024 && x_pitch >= C && gy_pitch >= C, "fami_bn_bwd: bad shape");
+  return bn_bwd_launch(x, x_pitch, grad_y, gy_pitch, y, y_pitch, mean, invstd, gamma, rows, C, training, sums, grad_x,
+                       gx_pitch, grad_res, gres_pitch, grad_gamma, grad_beta, (cudaStream_t)stream);
+}
+
+int fami_softmax_pkl_bwd(const float* a, int a_pitch, const float* b, int b_pitch, const float* grad_out, float* grad_a,
+                         int ga_pitch, float* grad_b, int gb_pitch, int B, int HW, int C, float temperature, void* stream) {
+  FAMI_CHECK_ARG(a && b && grad_out && (grad_a || grad_b), "fami_softmax_pkl_bwd: null pointer");
+  FAMI_CHECK_ARG(B > 0 && HW > 0 && C > 0 && C <= 1024 && temperature > 0.f, "fami_softmax_pkl_bwd: bad shape");
+  return softmax_pkl_bwd_launch(a, a_pitch, b, b_pitch, grad_out, grad_a, ga_pitch, grad_b, gb_pitch, B, HW, C, temperature,
+                                (cudaStream_t)stream);
+}
+
+int fami_linear_bwd(const float* x, const float* w, const float* grad_y, float* grad_x, float* grad_w, float* grad_b, int M,
+                    int K, int N, void* stream) {
+  FAMI_CHECK_ARG(x && w && grad_y && M > 0 && K > 0 && N > 0, "fami_linear_bwd: bad arguments");
+  return linear_bwd_launch(x, w, grad_y, grad_x, grad_w, grad_b, M, K, N, (cudaStream_t)stream);
 }
 
 int fami_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,

@@ -1,0 +1,403 @@
+// Backward kernels of the dense pieces of the trainable head (fp32, NHWC with pitch):
+//   conv dgrad / wgrad      autograd of nn.Conv2d as used by BasicBlock (basic_model.py:44-63),
+//                           conv_bn_relu (basic_layer.py:55-73) and the offset / mask / heatmap convs
+//                           (Alignment_V15.py:79-106)
+//   train/eval BatchNorm bwd (+ the ReLU mask of the fused activation, + the residual's gradient)
+//   MI pseudo-KL backward   (Alignment_V15.py:250-277)
+//   Linear backward         (feat_global_offset_layers[7..9], Alignment_V15.py:69-71)
+// Stride-1 dgrad is the forward convolution of grad_out with the flipped, transposed filter (pad' =
+// dil*(k-1) - pad): it runs on the forward kernels.  Everything else here is a straightforward SIMT kernel.
+#include "common.cuh"
+
+namespace fami {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// flipped + transposed filter in OIHW order: wt[ci][co][kh-1-r][kw-1-s] = w[co][ci][r][s]
+// ---------------------------------------------------------------------------------------------
+__global__ void flip_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int Cin, int kh, int kw) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t tot = (int64_t)Cout * Cin * kh * kw;
+  if (i >= tot) return;
+  int s = (int)(i % kw);
+  int64_t t = i / kw;
+  int r = (int)(t % kh);
+  t /= kh;
+  int ci = (int)(t % Cin), co = (int)(t / Cin);
+  wt[(((int64_t)ci * Cout + co) * kh + (kh - 1 - r)) * kw + (kw - 1 - s)] = w[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic dgrad (any stride): thread = (input pixel, 4 input channels); wt is the fp32 packing of
+// the flipped/transposed filter: [(tap' * Cout + co)][CinPad]
+// ---------------------------------------------------------------------------------------------
+__global__ void conv_dgrad_gather_kernel(const float* __restrict__ gy, int gy_pitch, const float* __restrict__ wt,
+                                         float* __restrict__ gx, int gx_pitch, int N, int H, int W, int Cin, int Cout,
+                                         int kh, int kw, int stride, int pad, int dil, int Ho, int Wo, int CinPad) {
+  const int cq = (Cin + 3) / 4;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t tot = (int64_t)N * H * W * cq;
+  if (i >= tot) return;
+  const int c0 = (int)(i % cq) * 4;
+  int64_t pix = i / cq;
+  const int xi = (int)(pix % W);
+  int64_t t = pix / W;
+  const int yi = (int)(t % H), n = (int)(t / H);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r = 0; r < kh; ++r) {
+    const int yy = yi + pad - r * dil;
+    if (yy < 0 || yy % stride) continue;
+    const int yo = yy / stride;
+    if (yo >= Ho) continue;
+    for (int s = 0; s < kw; ++s) {
+      const int xx = xi + pad - s * dil;
+      if (xx < 0 || xx % stride) continue;
+      const int xo = xx / stride;
+      if (xo >= Wo) continue;
+      const float* g = gy + ((int64_t)(n * Ho + yo) * Wo + xo) * gy_pitch;
+      const int tapf = (kh - 1 - r) * kw + (kw - 1 - s);
+      const float* wrow = wt + (int64_t)tapf * Cout * CinPad + c0;
+      for (int co = 0; co < Cout; ++co) {
+        const float gv = __ldg(g + co);
+        const float4 wv = *reinterpret_cast<const float4*>(wrow + (int64_t)co * CinPad);   // CinPad % 4 == 0, zero padded
+        acc[0] = fmaf(gv, wv.x, acc[0]); acc[1] = fmaf(gv, wv.y, acc[1]);
+        acc[2] = fmaf(gv, wv.z, acc[2]); acc[3] = fmaf(gv, wv.w, acc[3]);
+      }
+    }
+  }
+  float* o = gx + pix * gx_pitch + c0;
+  for (int j = 0; j < 4; ++j)
+    if (c0 + j < Cin) o[j] = acc[j];
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: dw[co][ci][r][s] += sum_pixels gy[p][co] * x[p @ tap][ci].  Block = one (tap, 64 ci, 64 co) tile
+// over a chunk of output pixels; 256 threads, 4x4 accumulators each; fp32 atomics into dw (caller zeroes).
+// ---------------------------------------------------------------------------------------------
+constexpr int kWgPix = 16;
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ x, int x_pitch,
+                                                         const float* __restrict__ gy, int gy_pitch,
+                                                         float* __restrict__ dw, int N, int H, int W, int Cin, int Cout,
+                                                         int kh, int kw, int stride, int pad, int dil, int Ho, int Wo,
+                                                         int ci_tiles, int co_tiles, int pix_per_block) {
+  __shared__ float xs[kWgPix][64];
+  __shared__ float gs[kWgPix][64];
+  int tile = blockIdx.x;
+  const int cot = tile % co_tiles; tile /= co_tiles;
+  const int cit = tile % ci_tiles; tile /= ci_tiles;
+  const int tap = tile;
+  const int r = tap / kw, s = tap - r * kw;
+  const int tid = threadIdx.x;
+  const int tci = tid & 15, tco = tid >> 4;
+  const int64_t npix = (int64_t)N * Ho * Wo;
+  const int64_t p0 = (int64_t)blockIdx.y * pix_per_block;
+  const int64_t p1 = p0 + pix_per_block < npix ? p0 + pix_per_block : npix;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  for (int64_t pb = p0; pb < p1; pb += kWgPix) {
+    // stage 16 pixels x 64 channels of x (at this tap) and of gy
+    for (int e = tid; e < kWgPix * 64; e += 256) {
+      const int pl = e >> 6, c = e & 63;
+      const int64_t p = pb + pl;
+      float xv = 0.f, gv = 0.f;
+      if (p < p1) {
+        const int xo = (int)(p % Wo);
+        const int64_t t = p / Wo;
+        const int yo = (int)(t % Ho), n = (int)(t / Ho);
+        const int yi = yo * stride - pad + r * dil, xi = xo * stride - pad + s * dil;
+        const int ci = cit * 64 + c, co = cot * 64 + c;
+        if (ci < Cin && yi >= 0 && yi < H && xi >= 0 && xi < W) xv = __ldg(x + ((int64_t)(n * H + yi) * W + xi) * x_pitch + ci);
+        if (co < Cout) gv = __ldg(gy + p * gy_pitch + co);
+      }
+      xs[pl][c] = xv;
+      gs[pl][c] = gv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int pl = 0; pl < kWgPix; ++pl) {
+      const float4 xv = *reinterpret_cast<const float4*>(&xs[pl][tci * 4]);
+      const float4 gv = *reinterpret_cast<const float4*>(&gs[pl][tco * 4]);
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ga[a], xa[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+  const int taps = kh * kw;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int co = cot * 64 + tco * 4 + a;
+    if (co >= Cout) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int ci = cit * 64 + tci * 4 + b;
+      if (ci < Cin) atomicAdd(dw + ((int64_t)co * Cin + ci) * taps + tap, acc[a][b]);
+    }
+  }
+}
+
+// per-channel sum over rows (bias gradient); float atomics into out (caller zeroes)
+__global__ void __launch_bounds__(1024) col_sum_kernel(const float* __restrict__ x, int pitch, int64_t rows, int C,
+                                                       float* __restrict__ out, int rows_per_block) {
+  extern __shared__ float sm[];
+  const int RG = blockDim.x / C;
+  const int tid = threadIdx.x, c = tid % C, rg = tid / C;
+  int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float s = 0.f;
+  if (rg < RG)
+    for (int64_t r = r0 + rg; r < r1; r += RG) s += x[r * pitch + c];
+  if (rg < RG) sm[rg * C + c] = s;
+  __syncthreads();
+  if (tid < C) {
+    float t = 0.f;
+    for (int r = 0; r < RG; ++r) t += sm[r * C + tid];
+    atomicAdd(out + tid, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm backward.  g' = gy * [y > 0] (fused ReLU), xhat = (x - mean) * invstd.
+//   pass 1: sums[c] = sum g', sums[C + c] = sum g' * xhat   (double atomics, caller zeroes)
+//   pass 2: training: dx = gamma*invstd * (g' - sums[c]/M - xhat * sums[C+c]/M)
+//           eval    : dx = gamma*invstd * g'
+//           g_res (optional) = g'  -- the gradient of the residual operand of the fused epilogue
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) bn_bwd_reduce_kernel(const float* __restrict__ x, int x_pitch,
+                                                             const float* __restrict__ gy, int gy_pitch,
+                                                             const float* __restrict__ y, int y_pitch,
+                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                             int64_t rows, int C, double* __restrict__ sums,
+                                                             int rows_per_block) {
+  extern __shared__ float sm[];
+  const int RG = blockDim.x / C;
+  const int tid = threadIdx.x, c = tid % C, rg = tid / C;
+  int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float s = 0.f, q = 0.f;
+  if (rg < RG) {
+    const float mu = mean[c], is = invstd[c];
+    for (int64_t r = r0 + rg; r < r1; r += RG) {
+      float g = gy[r * gy_pitch + c];
+      if (y && !(y[r * y_pitch + c] > 0.f)) g = 0.f;
+      s += g;
+      q = fmaf(g, (x[r * x_pitch + c] - mu) * is, q);
+    }
+    sm[rg * C + c] = s;
+    sm[(RG + rg) * C + c] = q;
+  }
+  __syncthreads();
+  if (tid < C) {
+    double ds = 0, dq = 0;
+    for (int r = 0; r < RG; ++r) { ds += sm[r * C + tid]; dq += sm[(RG + r) * C + tid]; }
+    atomicAdd(sums + tid, ds);
+    atomicAdd(sums + C + tid, dq);
+  }
+}
+
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ gy, int gy_pitch,
+                                    const float* __restrict__ y, int y_pitch, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const double* __restrict__ sums, int64_t rows, int C, int training,
+                                    float* __restrict__ dx, int dx_pitch, float* __restrict__ g_res, int gres_pitch,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) {
+    if (dgamma) dgamma[i] = (float)sums[C + i];
+    if (dbeta) dbeta[i] = (float)sums[i];
+  }
+  if (i >= rows * C) return;
+  const int c = (int)(i % C);
+  const int64_t r = i / C;
+  float g = gy[r * gy_pitch + c];
+  if (y && !(y[r * y_pitch + c] > 0.f)) g = 0.f;
+  if (g_res) g_res[r * gres_pitch + c] = g;
+  if (!dx) return;
+  const float is = invstd[c];
+  const float k = (gamma ? gamma[c] : 1.f) * is;
+  float v = g;
+  if (training) {
+    const double inv_m = 1.0 / (double)rows;
+    const float xhat = (x[r * x_pitch + c] - mean[c]) * is;
+    v = g - (float)(sums[c] * inv_m) - xhat * (float)(sums[C + c] * inv_m);
+  }
+  dx[r * dx_pitch + c] = k * v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MI pseudo-KL backward.  Per row (sample, channel) over l: p = softmax(a/T), t = softmax(b/T),
+// L = sum t (log t - p);  dL/da_j = -(1/T) p_j (t_j - S),  S = sum t p;
+// dL/db_j = (1/T) t_j ((log t_j - p_j) - L).  Both scaled by gout / (B*C*HW).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) softmax_pkl_bwd_kernel(const float* __restrict__ a, int a_pitch,
+                                                               const float* __restrict__ bsrc, int b_pitch,
+                                                               const float* __restrict__ gout, float* __restrict__ ga,
+                                                               int ga_pitch, float* __restrict__ gb, int gb_pitch, int HW,
+                                                               int C, float inv_temp, float inv_count) {
+  extern __shared__ float sm[];  // [4][RG*C]
+  const int RG = blockDim.x / C;
+  const int tid = threadIdx.x;
+  const int c = tid % C, rg = tid / C;
+  const bool active = rg < RG;
+  const float* ab = a + (int64_t)blockIdx.x * HW * a_pitch;
+  const float* bb = bsrc + (int64_t)blockIdx.x * HW * b_pitch;
+  float ma = -INFINITY, mb = -INFINITY;
+  if (active)
+    for (int l = rg; l < HW; l += RG) {
+      ma = fmaxf(ma, ab[(int64_t)l * a_pitch + c] * inv_temp);
+      mb = fmaxf(mb, bb[(int64_t)l * b_pitch + c] * inv_temp);
+    }
+  float* s0 = sm; float* s1 = sm + RG * C; float* s2 = sm + 2 * RG * C; float* s3 = sm + 3 * RG * C;
+  if (active) { s0[rg * C + c] = ma; s1[rg * C + c] = mb; }
+  __syncthreads();
+  if (active)
+    for (int r = 0; r < RG; ++r) { ma = fmaxf(ma, s0[r * C + c]); mb = fmaxf(mb, s1[r * C + c]); }
+  __syncthreads();
+  float za = 0.f, zb = 0.f, sb = 0.f, xab = 0.f;
+  if (active)
+    for (int l = rg; l < HW; l += RG) {
+      const float va = ab[(int64_t)l * a_pitch + c] * inv_temp - ma;
+      const float vb = bb[(int64_t)l * b_pitch + c] * inv_temp - mb;
+      const float ea = expf(va), eb = expf(vb);
+      za += ea; zb += eb; sb = fmaf(eb, vb, sb); xab = fmaf(ea, eb, xab);
+    }
+  if (active) { s0[rg * C + c] = za; s1[rg * C + c] = zb; s2[rg * C + c] = sb; s3[rg * C + c] = xab; }
+  __syncthreads();
+  if (active) {
+    za = zb = sb = xab = 0.f;
+    for (int r = 0; r < RG; ++r) { za += s0[r * C + c]; zb += s1[r * C + c]; sb += s2[r * C + c]; xab += s3[r * C + c]; }
+    const float lzb = logf(zb);
+    const float S = xab / (za * zb);
+    const float Lrow = sb / zb - lzb - S;
+    const float gs = __ldg(gout) * inv_count * inv_temp;
+    const float iza = 1.f / za, izb = 1.f / zb;
+    for (int l = rg; l < HW; l += RG) {
+      const float va = ab[(int64_t)l * a_pitch + c] * inv_temp - ma;
+      const float vb = bb[(int64_t)l * b_pitch + c] * inv_temp - mb;
+      const float p = expf(va) * iza, t = expf(vb) * izb;
+      if (ga) ga[((int64_t)blockIdx.x * HW + l) * ga_pitch + c] = -gs * p * (t - S);
+      if (gb) gb[((int64_t)blockIdx.x * HW + l) * gb_pitch + c] = gs * t * ((vb - lzb - p) - Lrow);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Linear backward: gx = gy W, gW = gy^T x, gb = sum_m gy  (tiny: M = 4B, K <= 144, N <= 64)
+// ---------------------------------------------------------------------------------------------
+__global__ void linear_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ gy,
+                                  float* __restrict__ gx, float* __restrict__ gw, float* __restrict__ gb, int M, int K, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_gx = gx ? M * K : 0, n_gw = gw ? N * K : 0, n_gb = gb ? N : 0;
+  if (i < n_gx) {
+    const int m = i / K, k = i - m * K;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s = fmaf(gy[m * N + n], w[n * K + k], s);
+    gx[i] = s;
+  } else if (i < n_gx + n_gw) {
+    const int j = i - n_gx, n = j / K, k = j - n * K;
+    float s = 0.f;
+    for (int m = 0; m < M; ++m) s = fmaf(gy[m * N + n], x[m * K + k], s);
+    gw[j] = s;
+  } else if (i < n_gx + n_gw + n_gb) {
+    const int n = i - n_gx - n_gw;
+    float s = 0.f;
+    for (int m = 0; m < M; ++m) s += gy[m * N + n];
+    gb[n] = s;
+  }
+}
+
+}  // namespace
+
+int flip_transpose_launch(const float* w, float* wt, int Cout, int Cin, int kh, int kw, cudaStream_t st) {
+  int64_t tot = (int64_t)Cout * Cin * kh * kw;
+  flip_transpose_kernel<<<cdiv(tot, 256), 256, 0, st>>>(w, wt, Cout, Cin, kh, kw);
+  FAMI_CHECK_LAUNCH("flip_transpose_kernel");
+  return 0;
+}
+
+int conv_dgrad_launch(const fami_conv_desc* d, const float* gy, const float* wt_packed, float* gx, cudaStream_t st) {
+  if (d->stride == 1) {
+    // forward convolution of grad_out [N,Ho,Wo,Cout] with the flipped/transposed filter
+    fami_conv_desc f = *d;
+    f.H = d->Ho; f.W = d->Wo; f.Cin = d->Cout; f.Cout = d->Cin;
+    f.pad = d->dil * (d->kh - 1) - d->pad;
+    f.Ho = d->H; f.Wo = d->W;
+    f.up = 1; f.relu = 0; f.stats = 0;
+    f.in_pitch = d->out_pitch; f.out_pitch = d->in_pitch; f.res_pitch = 0;
+    f.dtype = FAMI_F32; f.out_dtype = FAMI_F32;
+    return fami_conv2d_bn_act_fwd(&f, gy, wt_packed, nullptr, nullptr, nullptr, gx, nullptr, (void*)st);
+  }
+  const int CinPad = fami_conv_cout_pad(d->Cin);
+  const int64_t tot = (int64_t)d->N * d->H * d->W * ((d->Cin + 3) / 4);
+  conv_dgrad_gather_kernel<<<cdiv(tot, 128), 128, 0, st>>>(gy, d->out_pitch, wt_packed, gx, d->in_pitch, d->N, d->H, d->W,
+                                                           d->Cin, d->Cout, d->kh, d->kw, d->stride, d->pad, d->dil, d->Ho,
+                                                           d->Wo, CinPad);
+  FAMI_CHECK_LAUNCH("conv_dgrad_gather_kernel");
+  return 0;
+}
+
+int conv_wgrad_launch(const fami_conv_desc* d, const float* x, const float* gy, float* dw, float* dbias, cudaStream_t st) {
+  const int ci_tiles = (d->Cin + 63) / 64, co_tiles = (d->Cout + 63) / 64;
+  const int tiles = d->kh * d->kw * ci_tiles * co_tiles;
+  const int64_t npix = (int64_t)d->N * d->Ho * d->Wo;
+  int splits = (4 * num_sms() + tiles - 1) / tiles;
+  int64_t per = (npix + splits - 1) / splits;
+  per = ((per + kWgPix - 1) / kWgPix) * kWgPix;
+  if (per < kWgPix) per = kWgPix;
+  splits = (int)((npix + per - 1) / per);
+  dim3 grid(tiles, splits);
+  conv_wgrad_kernel<<<grid, 256, 0, st>>>(x, d->in_pitch, gy, d->out_pitch, dw, d->N, d->H, d->W, d->Cin, d->Cout, d->kh,
+                                          d->kw, d->stride, d->pad, d->dil, d->Ho, d->Wo, ci_tiles, co_tiles, (int)per);
+  FAMI_CHECK_LAUNCH("conv_wgrad_kernel");
+  if (dbias) {
+    FAMI_CHECK_ARG(d->Cout <= 1024, "conv wgrad: bias gradient supports Cout <= 1024");
+    int threads = 1024, RG = threads / d->Cout;
+    int rows_per_block = 2048;
+    col_sum_kernel<<<cdiv(npix, rows_per_block), threads, (size_t)RG * d->Cout * sizeof(float), st>>>(gy, d->out_pitch, npix,
+                                                                                                   d->Cout, dbias, rows_per_block);
+    FAMI_CHECK_LAUNCH("col_sum_kernel");
+  }
+  return 0;
+}
+
+int bn_bwd_launch(const float* x, int xp, const float* gy, int gp, const float* y, int yp, const float* mean,
+                  const float* invstd, const float* gamma, int64_t rows, int C, int training, double* sums, float* dx,
+                  int dxp, float* g_res, int grp, float* dgamma, float* dbeta, cudaStream_t st) {
+  FAMI_CHECK_ARG(C <= 1024, "bn bwd: C <= 1024");
+  int threads = 1024, RG = threads / C, rows_per_block = 2048;
+  bn_bwd_reduce_kernel<<<cdiv(rows, rows_per_block), threads, (size_t)2 * RG * C * sizeof(float), st>>>(
+      x, xp, gy, gp, y, yp, mean, invstd, rows, C, sums, rows_per_block);
+  FAMI_CHECK_LAUNCH("bn_bwd_reduce_kernel");
+  int64_t tot = rows * C;
+  bn_bwd_apply_kernel<<<cdiv(tot, 256), 256, 0, st>>>(x, xp, gy, gp, y, yp, mean, invstd, gamma, sums, rows, C, training, dx,
+                                                      dxp, g_res, grp, dgamma, dbeta);
+  FAMI_CHECK_LAUNCH("bn_bwd_apply_kernel");
+  return 0;
+}
+
+int softmax_pkl_bwd_launch(const float* a, int ap, const float* b, int bp, const float* gout, float* ga, int gap, float* gb,
+                           int gbp, int B, int HW, int C, float temperature, cudaStream_t st) {
+  int threads = 1024, RG = threads / C;
+  size_t smem = (size_t)4 * RG * C * sizeof(float);
+  float inv_count = 1.f / ((float)B * (float)C * (float)HW);
+  softmax_pkl_bwd_kernel<<<B, threads, smem, st>>>(a, ap, b, bp, gout, ga, gap, gb, gbp, HW, C, 1.f / temperature, inv_count);
+  FAMI_CHECK_LAUNCH("softmax_pkl_bwd_kernel");
+  return 0;
+}
+
+int linear_bwd_launch(const float* x, const float* w, const float* gy, float* gx, float* gw, float* gb, int M, int K, int N,
+                      cudaStream_t st) {
+  int tot = (gx ? M * K : 0) + (gw ? N * K : 0) + (gb ? N : 0);
+  if (tot == 0) return 0;
+  linear_bwd_kernel<<<cdiv(tot, 128), 128, 0, st>>>(x, w, gy, gx, gw, gb, M, K, N);
+  FAMI_CHECK_LAUNCH("linear_bwd_kernel");
+  return 0;
+}
+
+}  // namespace fami

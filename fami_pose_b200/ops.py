@@ -441,3 +441,101 @@ def argmax_hw(hm):
     mx = torch.empty((B, J), dtype=torch.float32, device=hm.device)
     _lib.call("fami_argmax_hw", _ptr(hm), _code(hm.dtype), p, _ptr(idx), _ptr(mx), B, H * W, J, _stream())
     return idx, mx
+
+
+# ------------------------------------------------------------------------------------------------
+# backward of the dense pieces (fp32 arm) -- autograd of nn.Conv2d / nn.BatchNorm2d / nn.Linear and
+# of the MI estimator as the reference's training step derives them (alignment_mi_function_term6_1.py:104-156)
+# ------------------------------------------------------------------------------------------------
+
+def _conv_desc_f32(x_shape_meta, Cout, k, stride, pad, dil, out_pitch):
+    N, Cin, H, W, ip = x_shape_meta
+    Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    return ConvDesc(N, H, W, Cin, Cout, k, k, stride, pad, dil, Ho, Wo, 1, 0, ip, out_pitch, 0, F32, F32, 0), Ho, Wo
+
+
+def conv_dgrad(grad_y, weight, x_shape, stride=1, pad=0, dil=1, out=None):
+    """d loss / d x of y = conv2d(x, weight): grad_y NHWC fp32 [N,Cout,Ho,Wo], weight OIHW; returns NHWC
+    fp32 [N,Cin,H,W] (x_shape = logical NCHW shape of x)."""
+    _need_cuda(grad_y)
+    if grad_y.dtype != torch.float32 or not is_nhwc(grad_y):
+        raise ValueError("conv_dgrad: grad_y must be an fp32 NHWC activation")
+    N, Cin, H, W = x_shape
+    Cout, k = weight.shape[0], weight.shape[2]
+    gN, gC, gH, gW, gp = meta(grad_y)
+    if out is None:
+        out = empty_nhwc(N, Cin, H, W, torch.float32, grad_y.device)
+    d, Ho, Wo = _conv_desc_f32((N, Cin, H, W, meta(out)[4]), Cout, k, stride, pad, dil, gp)
+    if (gN, gC, gH, gW) != (N, Cout, Ho, Wo):
+        raise ValueError("conv_dgrad: grad_y shape %s, expected %s" % (tuple(grad_y.shape), (N, Cout, Ho, Wo)))
+    w = weight.detach().float().contiguous()
+    scratch = torch.empty_like(w)
+    n = _lib.load().fami_packed_weight_elems(Cin, Cout, k, k, F32)
+    wt = torch.empty(n, dtype=torch.float32, device=grad_y.device)
+    _lib.call("fami_pack_conv_weight_dgrad", _ptr(w), _ptr(scratch), _ptr(wt), Cout, Cin, k, k, F32, _stream())
+    _lib.call("fami_conv2d_dgrad", ctypes.byref(d), _ptr(grad_y), _ptr(wt), _ptr(out), _stream())
+    return out
+
+
+def conv_wgrad(x, grad_y, weight_shape, stride=1, pad=0, dil=1, want_bias=False):
+    """(d loss / d weight [OIHW], d loss / d bias or None) of y = conv2d(x, weight) + bias."""
+    _need_cuda(x, grad_y)
+    if x.dtype != torch.float32 or grad_y.dtype != torch.float32:
+        raise ValueError("conv_wgrad: fp32 activations only")
+    Cout, Cin, k, _ = weight_shape
+    d, Ho, Wo = _conv_desc_f32(meta(x), Cout, k, stride, pad, dil, meta(grad_y)[4])
+    if tuple(grad_y.shape) != (x.shape[0], Cout, Ho, Wo) or x.shape[1] != Cin:
+        raise ValueError("conv_wgrad: shape mismatch")
+    gw = torch.zeros(tuple(weight_shape), dtype=torch.float32, device=x.device)
+    gb = torch.zeros(Cout, dtype=torch.float32, device=x.device) if want_bias else None
+    _lib.call("fami_conv2d_wgrad", ctypes.byref(d), _ptr(x), _ptr(grad_y), _ptr(gw), _ptr(gb), _stream())
+    return gw, gb
+
+
+def bn_bwd(x, grad_y, mean, invstd, gamma, y=None, training=True, want_res=False):
+    """BatchNorm2d backward (+ ReLU mask from the post-activation output y, + the residual's gradient).
+    x: the raw conv output the BN normalised (fp32 NHWC).  Returns (grad_x, grad_gamma, grad_beta, grad_res)."""
+    _need_cuda(x, grad_y)
+    N, C, H, W, xp = meta(x)
+    gp = meta(grad_y)[4]
+    yp = meta(y)[4] if y is not None else 0
+    gx = empty_nhwc(N, C, H, W, torch.float32, x.device)
+    gres = empty_nhwc(N, C, H, W, torch.float32, x.device) if want_res else None
+    dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+    sums = torch.zeros(2 * C, dtype=torch.float64, device=x.device)
+    _lib.call("fami_bn_bwd", _ptr(x), xp, _ptr(grad_y), gp, _ptr(y), yp, _ptr(mean), _ptr(invstd), _ptr(gamma),
+              N * H * W, C, int(bool(training)), _ptr(sums), _ptr(gx), meta(gx)[4], _ptr(gres),
+              meta(gres)[4] if gres is not None else 0, _ptr(dgamma), _ptr(dbeta), _stream())
+    return gx, dgamma, dbeta, gres
+
+
+def softmax_pkl_bwd(a, b, grad_out, temperature=0.05, want_a=True, want_b=True):
+    """Gradients of softmax_pkl(a, b) with respect to a and b (fp32 NHWC), scaled by the device scalar grad_out."""
+    _need_cuda(a, b)
+    B, C, H, W, ap = meta(a)
+    bp = meta(b)[4]
+    if a.dtype != torch.float32 or b.dtype != torch.float32:
+        raise ValueError("softmax_pkl_bwd: fp32 activations only")
+    ga = empty_nhwc(B, C, H, W, torch.float32, a.device) if want_a else None
+    gb = empty_nhwc(B, C, H, W, torch.float32, a.device) if want_b else None
+    go = grad_out.detach().float().reshape(1).contiguous()
+    _lib.call("fami_softmax_pkl_bwd", _ptr(a), ap, _ptr(b), bp, _ptr(go), _ptr(ga), meta(ga)[4] if want_a else 0,
+              _ptr(gb), meta(gb)[4] if want_b else 0, B, H * W, C, float(temperature), _stream())
+    return ga, gb
+
+
+def linear_bwd(x, weight, grad_y, want_x=True):
+    """(grad_x, grad_w, grad_b) of y = x W^T + b on float32 [M,K]."""
+    _need_cuda(x, grad_y)
+    x = x.contiguous().float()
+    grad_y = grad_y.contiguous().float()
+    M, K = x.shape
+    N = weight.shape[0]
+    w = weight.detach().float().contiguous()
+    gx = torch.empty((M, K), dtype=torch.float32, device=x.device) if want_x else None
+    gw = torch.empty((N, K), dtype=torch.float32, device=x.device)
+    gb = torch.empty(N, dtype=torch.float32, device=x.device)
+    _lib.call("fami_linear_bwd", _ptr(x), _ptr(w), _ptr(grad_y), _ptr(gx), _ptr(gw), _ptr(gb), M, K, N, _stream())
+    return gx, gw, gb

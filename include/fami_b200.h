@@ -85,6 +85,31 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
                            const float* scale, const float* shift, const void* residual, void* y,
                            double* stats_out, void* stream);
 
+/* ---- backward of the dense pieces (fp32 storage; autograd of the modules above) --------------
+ * nn.Conv2d backward as autograd derives it for basic_model.py:44-63 / basic_layer.py:55-73 /
+ * Alignment_V15.py:79-106.  `d` is the FORWARD descriptor (up = 1, dtype = out_dtype = FAMI_F32).
+ * dgrad consumes the filter flipped and transposed (fami_pack_conv_weight_dgrad: scratch holds
+ * Cout*Cin*kh*kw floats; the packing has fami_packed_weight_elems(Cin, Cout, kh, kw, FAMI_F32)
+ * elements); stride-1 dgrad runs on the forward kernels, other strides on a gather kernel.
+ * wgrad ACCUMULATES into grad_w_oihw [Cout][Cin][kh][kw] and grad_bias [Cout] (may be NULL):
+ * the caller zeroes them (fp32 atomics over pixel chunks).                                        */
+int fami_pack_conv_weight_dgrad(const float* w_oihw, float* scratch_oihw, void* w_packed_t, int Cout, int Cin,
+                                int kh, int kw, int dtype, void* stream);
+int fami_conv2d_dgrad(const fami_conv_desc* d, const float* grad_y, const float* w_packed_t, float* grad_x,
+                      void* stream);
+int fami_conv2d_wgrad(const fami_conv_desc* d, const float* x, const float* grad_y, float* grad_w_oihw,
+                      float* grad_bias, void* stream);
+/* nn.BatchNorm2d backward fused with the ReLU mask of the block epilogue (basic_model.py:44-63):
+ * g' = grad_y * [y > 0] (y = the block's post-activation output, NULL = no ReLU);
+ * training = 1: batch statistics (mean / invstd saved by fami_bn_finalize), the full three-term
+ * formula; training = 0: running statistics, grad_x = gamma * invstd * g'.
+ * grad_gamma = sum g' * xhat, grad_beta = sum g' (may be NULL); grad_res (may be NULL) receives g',
+ * the gradient of the residual operand.  sums: double[2*C] workspace, zeroed by the caller.       */
+int fami_bn_bwd(const float* x, int x_pitch, const float* grad_y, int gy_pitch, const float* y, int y_pitch,
+                const float* mean, const float* invstd, const float* gamma, int64_t rows, int C, int training,
+                double* sums, float* grad_x, int gx_pitch, float* grad_res, int gres_pitch, float* grad_gamma,
+                float* grad_beta, void* stream);
+
 /* train-mode BatchNorm (batch statistics over N*H*W, biased variance, eps, momentum update):
  * nn.BatchNorm2d(momentum=0.1) as used at basic_model.py:29,39 and hrnet.py:53,106,124,137.
  * fami_bn_finalize turns (sum, sumsq) into scale/shift and updates running stats;
@@ -155,6 +180,10 @@ int fami_copy2d(const void* src, int src_pitch, void* dst, int dst_pitch, int dt
  * x [M,K] float, w [N,K] float (torch layout), y [M,N].                                         */
 int fami_linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int K, int N,
                     void* stream);
+/* backward of the same nn.Linear: grad_x [M,K] = grad_y W, grad_w [N,K] = grad_y^T x, grad_b [N] = column
+ * sums of grad_y; any output may be NULL.                                                          */
+int fami_linear_bwd(const float* x, const float* w, const float* grad_y, float* grad_x, float* grad_w,
+                    float* grad_b, int M, int K, int N, void* stream);
 
 /* ---- losses --------------------------------------------------------------------------------
  * JointMSELoss.forward, posetimation/loss/mse_loss.py:21-40 (use_target_weight, divided by J):
@@ -171,6 +200,12 @@ int fami_joint_mse_fwd_bwd(const void* pred, int pred_dtype, int pred_pitch, con
  * out: single float accumulated with atomics (caller zeroes).                                   */
 int fami_softmax_pkl_fwd(const void* a, int a_pitch, const void* b, int b_pitch, int dtype, float* out,
                          int B, int HW, int C, float temperature, void* stream);
+/* gradient of that scalar with respect to a and b (fp32 NHWC, either output may be NULL), scaled by
+ * the device scalar *grad_out: d/da_j = -(1/T) p_j (t_j - sum t p), d/db_j = (1/T) t_j ((log t_j - p_j) - L_row),
+ * both divided by B*C*HW.                                                                          */
+int fami_softmax_pkl_bwd(const float* a, int a_pitch, const float* b, int b_pitch, const float* grad_out,
+                         float* grad_a, int ga_pitch, float* grad_b, int gb_pitch, int B, int HW, int C,
+                         float temperature, void* stream);
 
 /* ---- keypoint argmax -----------------------------------------------------------------------
  * get_max_preds, datasets/process/heatmaps_process.py:16-44: flat argmax over H*W per (b,j),
