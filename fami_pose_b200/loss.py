@@ -1,5 +1,6 @@
 """Drop-in replacement for posetimation/loss/mse_loss.py and the loss combination of
 engine/core/functions/alignment_mi_function_term6_1.py:119-148."""
+import torch
 import torch.nn as nn
 
 from . import ops
@@ -15,7 +16,12 @@ class JointMSELoss(nn.Module):
         self.divided_num_joints = divided_num_joints
 
     def forward(self, output, target, target_weight):
-        loss = ops.joint_mse(output, target, target_weight if self.use_target_weight else None)
+        tw = target_weight if self.use_target_weight else None
+        if torch.is_grad_enabled() and output.requires_grad:
+            from .autograd import JointMSEFunction
+            loss = JointMSEFunction.apply(output, target, tw)
+        else:
+            loss = ops.joint_mse(output, target, tw)
         if not self.divided_num_joints:
             loss = loss * output.shape[1]
         return loss

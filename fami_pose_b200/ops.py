@@ -163,6 +163,16 @@ def packed_weight(owner, weight, dtype):
     return out
 
 
+def pack_weight(weight, dtype):
+    """Uncached packing of an OIHW weight tensor (training: weights change every step; derived weights)."""
+    Cout, Cin, kh, kw = weight.shape
+    n = _lib.load().fami_packed_weight_elems(Cout, Cin, kh, kw, _code(dtype))
+    out = torch.empty(n, dtype=dtype, device=weight.device)
+    w = weight.detach().contiguous().float()
+    _lib.call("fami_pack_conv_weight", _ptr(w), _ptr(out), Cout, Cin, kh, kw, _code(dtype), _stream())
+    return out
+
+
 def folded_affine(conv_bias, bn):
     """Per-channel (scale, shift) of eval-mode BatchNorm folded with the conv bias."""
     owner = bn if bn is not None else None
@@ -224,6 +234,15 @@ def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None, out
     _need_cuda(x)
     if conv.groups != 1:
         raise NotImplementedError("grouped convolutions are not on the FAMI-Pose hot path")
+    if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad
+                                    or (bn is not None and bn.weight is not None and bn.weight.requires_grad)
+                                    or (residual is not None and residual.requires_grad)):
+        # differentiable path (fp32 arm): autograd.ConvBnActFunction
+        if up != 1 or out is not None:
+            raise NotImplementedError("differentiable conv: upsample-on-write / caller-provided outputs are "
+                                      "inference-only (the reference default trains with HRNet frozen)")
+        from . import autograd as _ag
+        return _ag.conv_bn_act(x, conv, bn, relu, residual)
     k = conv.kernel_size[0]
     stride, pad, dil = conv.stride[0], conv.padding[0], conv.dilation[0]
     w = packed_weight(conv, conv.weight, x.dtype)

@@ -183,6 +183,8 @@ class Alignment_V15(nn.Module):
         feat_all = feats[0]
         kf_bb_hm, kf_feat, sup_feat = hm_all[:B], feat_all[:B], feat_all[B:]
         _, _, H, W, _ = ops.meta(kf_feat)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_graph(B, ns, kf_bb_hm, kf_feat, sup_feat)
 
         # :130-137 global translation per supporting frame (shared weights).  Eval-mode BN: all frames
         # in one batch.  Train-mode BN uses per-call batch statistics, so keep the reference's loop.
@@ -222,11 +224,76 @@ class Alignment_V15(nn.Module):
         mi[5] = mi[1]                                               # :177 identical arguments to mi_2
         return final_out, kf_out, mi
 
+    # -- differentiable forward (training step, fp32 arm) ------------------------------------------
+    def _forward_graph(self, B, ns, kf_bb_hm, kf_feat, sup_feat):
+        """Same computation as forward() with every head op recorded for autograd (autograd.py): the
+        reference's concatenations are torch.cat here so their gradients slice back.  The backbone is
+        expected frozen (FREEZE_HRNET_WEIGHTS, the reference default): its fused upsample-on-write
+        layers have no backward in this round."""
+        from . import autograd as ag
+        C = self.width
+        if kf_feat.dtype != torch.float32:
+            raise NotImplementedError("training runs on the exact-fp32 arm: fami.set_precision('fp32')")
+        L = self.feat_global_offset_layers
+        txys, warped = [], []
+        for i in range(ns):                                                        # :130-137
+            sup_i = sup_feat[i * B:(i + 1) * B]
+            t = L[0](ag.SubFunction.apply(sup_i, kf_feat))
+            for j in range(1, 6):
+                t = L[j](t)
+            v = t.reshape(t.shape[0], -1)                                          # nn.Flatten in C,H,W order
+            for j in (7, 8, 9):
+                v = ag.LinearFunction.apply(v, L[j].weight, L[j].bias)
+            txys.append(v)
+            warped.append(ag.WarpTranslateFunction.apply(sup_i, v))
+        txy = torch.cat(txys, 0)
+        agg_sup_feat = self.sup_agg_block(ag.cat_channels(warped))                 # :139-140
+        combined = self.combined_feat_layers(ag.cat_channels([agg_sup_feat, kf_feat]))   # :143
+        combined = self._dcn_graph(1, combined, combined)                          # :144-146
+        combined = self._dcn_graph(2, combined, combined)                          # :148-150
+        aligned = self._dcn_graph(3, combined, agg_sup_feat)                       # :152-154
+        aligned = self._dcn_graph(4, aligned, aligned)                             # :156-158
+        all_agg = self.init_feature_agg_block(ag.cat_channels([kf_feat, aligned]))  # :160-161
+        final_hm = ops.conv_bn_act(all_agg, self.agg_final_layer, None, relu=False, out_dtype=torch.float32)  # :163
+        final_out, kf_out = final_hm.contiguous(), ops.to_nchw(kf_bb_hm)
+        self._last = {"final_hm_nhwc": final_hm, "txy": txy}
+        if not self.is_train:
+            return final_out, kf_out
+        mi = [self.feat_label_mi_estimation(all_agg, final_hm),
+              self.feat_feat_mi_estimation(kf_feat, all_agg),
+              self.feat_label_mi_estimation(agg_sup_feat, final_hm),
+              self.feat_feat_mi_estimation(agg_sup_feat, all_agg),
+              self.feat_label_mi_estimation(kf_feat, final_hm),
+              None]
+        mi[5] = mi[1]
+        return final_out, kf_out, mi
+
+    def _dcn_graph(self, k, feat_for_offsets, x):
+        """Differentiable _dcn: the offset and mask convolutions still run as one launch over the
+        concatenated (differentiable) parameters; torchvision channel order."""
+        from . import autograd as ag
+        off_m, msk_m = getattr(self, "dcn_offset_%d" % k), getattr(self, "dcn_mask_%d" % k)
+        w = torch.cat([off_m.conv.weight, msk_m.conv.weight], 0)
+        b = torch.cat([off_m.conv.bias, msk_m.conv.bias], 0) if off_m.conv.bias is not None else None
+        buf = ag.conv_bn_act(feat_for_offsets, off_m.conv, None, False, None, weight=w, bias=b)
+        n_off = off_m.conv.out_channels
+        return getattr(self, "dcn_%d" % k)(x, buf[:, :n_off], buf[:, n_off:])
+
     def feat_label_mi_estimation(self, Feat, Y):
         """Alignment_V15.py:250-263."""
+        if torch.is_grad_enabled() and Y.requires_grad:
+            # the reference detaches the prediction branch (:259): only Y receives a gradient
+            from . import autograd as ag
+            with torch.no_grad():
+                pred_Y = ops.conv_bn_act(ops.to_nhwc(Feat.detach()), self.hrnet.final_layer, None, relu=False,
+                                         out_dtype=torch.float32)
+            return ag.SoftmaxPklFunction.apply(pred_Y, ops.to_nhwc(Y), 0.05)
         pred_Y = ops.conv_bn_act(ops.to_nhwc(Feat), self.hrnet.final_layer, None, relu=False, out_dtype=torch.float32)
         return ops.softmax_pkl(pred_Y, ops.to_nhwc(Y), 0.05)
 
     def feat_feat_mi_estimation(self, F1, F2):
         """Alignment_V15.py:265-277."""
+        if torch.is_grad_enabled() and F2.requires_grad:
+            from . import autograd as ag
+            return ag.SoftmaxPklFunction.apply(ops.to_nhwc(F1.detach()), ops.to_nhwc(F2), 0.05)
         return ops.softmax_pkl(ops.to_nhwc(F1), ops.to_nhwc(F2), 0.05)

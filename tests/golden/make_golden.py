@@ -113,7 +113,53 @@ def make_model():
     print("model_reference.npz", {k: v.shape for k, v in out.items()})
 
 
+def grad_digest(g):
+    """Compact pin of one gradient tensor: L2 norm, sum, and 48 evenly strided samples."""
+    f = g.detach().double().flatten()
+    idx = torch.linspace(0, f.numel() - 1, steps=min(48, f.numel())).long()
+    return np.concatenate([[float(f.norm()), float(f.sum())], f[idx].numpy()])
+
+
+def make_train():
+    """One training-step backward of the unmodified reference (train phase, train-mode BatchNorm, HRNet
+    frozen as in configs/Alignment/Base_PoseTrack17.yaml), B=2: the loss of
+    alignment_mi_function_term6_1.py:119-148 and a digest of every trainable parameter's gradient.
+    Run twice: in float64 (the pin) and in the reference's own float32 (stored beside it so the test can
+    state how far fp32 rounding alone moves these heavily cancelling sums)."""
+    ref = rh.load_reference()
+    cfg = rh.make_cfg(48, 17)
+    out = {}
+    for dt, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        m = ref.Alignment_V15(cfg, 'train').train()
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict(fo.seeded_state_dict(shapes, SEED), strict=True)
+        m = m.to(dt)
+        kf, sup, tgt, tw = fo.synthetic_clip(2, seed=SEED + 2)
+        hm, kfhm, mi = m(kf.to(dt), sup.to(dt))
+        mse = ref.JointMSELoss()(hm, tgt.to(dt), tw.to(dt))
+        loss = mse * 1.0 + 0.5 * (-0.1 * mi[0] + 0.1 * mi[1] + mi[2] - mi[3] + mi[4] - mi[5])
+        loss.backward()
+        out.update({tag + "/loss": np.float64(loss.item()), tag + "/mse": np.float64(mse.item()),
+                    tag + "/mi": np.array([float(v) for v in mi], dtype=np.float64)})
+        if tag == "f64":
+            out["final_hm"] = hm.detach().float().numpy()
+        names = []
+        for name, p_ in m.named_parameters():
+            if p_.requires_grad:
+                assert p_.grad is not None, name
+                names.append(name)
+                out[tag + "/grad/" + name] = grad_digest(p_.grad)
+        out["names"] = np.array(names)
+        print(tag, "loss", out[tag + "/loss"], flush=True)
+    np.savez_compressed(os.path.join(OUT, "train_reference.npz"), **out)
+    print("train_reference.npz", len(names), "trainable tensors")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
-    make_dcn()
-    make_model()
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        make_train()
+    else:
+        make_dcn()
+        make_model()
+        make_train()
