@@ -68,6 +68,8 @@ SIGNATURES = {
                                      c_int, c_int, c_int, c_float, c_void_p]),
     "fami_linear_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_void_p]),
+    "fami_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
+                               c_int, c_void_p]),
     "fami_debug_read_trace": (c_int, [c_void_p, c_int]),
     "fami_debug_umma_rate": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "fami_debug_umma_rowshift": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

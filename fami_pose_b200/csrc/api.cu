@@ -1,5 +1,6 @@
 // extern "C" surface of libfami_b200.so (see include/fami_b200.h).  Argument validation lives
 // here; kernels live in conv_simt.cu / conv_tc.cu / dcn.cu / misc.cu.
+#include <math.h>
 #include <atomic>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -54,6 +55,8 @@ int softmax_pkl_bwd_launch(const float* a, int ap, const float* b, int bp, const
                            int gbp, int B, int HW, int C, float temperature, cudaStream_t st);
 int linear_bwd_launch(const float* x, const float* w, const float* gy, float* gx, float* gw, float* gb, int M, int K, int N,
                       cudaStream_t st);
+int adam_step_launch(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                     float bc1, float bc2_sqrt, cudaStream_t st);
 int dcn_tc_supported(const fami_dcn_desc* d);
 int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const void* w, const float* bias, void* out,
                   cudaStream_t st);
@@ -220,6 +223,15 @@ int fami_linear_bwd(const float* x, const float* w, const float* grad_y, float* 
                     int K, int N, void* stream) {
   FAMI_CHECK_ARG(x && w && grad_y && M > 0 && K > 0 && N > 0, "fami_linear_bwd: bad arguments");
   return linear_bwd_launch(x, w, grad_y, grad_x, grad_w, grad_b, M, K, N, (cudaStream_t)stream);
+}
+
+int fami_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                   float beta2, float eps, int step, void* stream) {
+  FAMI_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "fami_adam_step: bad arguments");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  return adam_step_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2),
+                          (cudaStream_t)stream);
 }
 
 int fami_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,

@@ -312,7 +312,32 @@ __global__ void linear_bwd_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Adam over one flat parameter bucket (torch.optim.Adam semantics: no weight decay, no amsgrad), as built by
+// posetimation/optimizer/optimizer.py:66-72.  bias corrections are passed in (host computes 1 - beta^t).
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
+                                 float bc1, float bc2_sqrt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+  const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
 }  // namespace
+
+int adam_step_launch(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                     float bc1, float bc2_sqrt, cudaStream_t st) {
+  adam_step_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2_sqrt);
+  FAMI_CHECK_LAUNCH("adam_step_kernel");
+  return 0;
+}
 
 int flip_transpose_launch(const float* w, float* wt, int Cout, int Cin, int kh, int kw, cudaStream_t st) {
   int64_t tot = (int64_t)Cout * Cin * kh * kw;

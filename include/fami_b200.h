@@ -184,6 +184,10 @@ int fami_linear_fwd(const float* x, const float* w, const float* b, float* y, in
  * sums of grad_y; any output may be NULL.                                                          */
 int fami_linear_bwd(const float* x, const float* w, const float* grad_y, float* grad_x, float* grad_w,
                     float* grad_b, int M, int K, int N, void* stream);
+/* One Adam update over a flat fp32 parameter bucket (torch.optim.Adam as built by
+ * posetimation/optimizer/optimizer.py:66-72: betas, eps, no weight decay / amsgrad); `step` counts from 1. */
+int fami_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, int step, void* stream);
 
 /* ---- losses --------------------------------------------------------------------------------
  * JointMSELoss.forward, posetimation/loss/mse_loss.py:21-40 (use_target_weight, divided by J):

@@ -73,3 +73,64 @@ def test_training_step_gradients_vs_reference_golden(golden_dir):
     for r in rows[:8]:
         print("grad dev %.3e (norm rel %.3e, samples %.3e; reference fp32 vs fp64 %.3e; |g| %.3e)  %s" % r)
     assert not bad, "gradients deviate from the reference: %s" % ", ".join("%s (%.2e)" % (b[5], b[0]) for b in bad)
+
+
+def test_adam_step_vs_torch_optim():
+    """fami_adam_step == torch.optim.Adam (the optimizer of posetimation/optimizer/optimizer.py:66-72)."""
+    import fami_pose_b200 as fp
+    from fami_pose_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    n = 10007
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone().double())
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    p = p0.clone().to(DEV)
+    m = torch.zeros(n, device=DEV)
+    v = torch.zeros(n, device=DEV)
+    for step in range(1, 6):
+        grad = torch.randn(n, generator=g) * (0.1 if step % 2 else 3.0)
+        ref.grad = grad.double()
+        opt.step()
+        gd = grad.to(DEV)
+        fp._lib.call("fami_adam_step", ops._ptr(p), ops._ptr(gd), ops._ptr(m), ops._ptr(v), n, 1e-3, 0.9, 0.999, 1e-8, step,
+                     ops._stream())
+        assert float((p.double().cpu() - ref.detach()).abs().max()) < 2e-6
+
+
+def test_train_step_updates_parameters_like_adam_and_keeps_backbone_frozen():
+    """One TrainStep: loss is a device scalar, every trainable tensor moves by exactly the Adam update of its own
+    gradient (|delta| = lr at step 1 wherever the gradient is non-zero), frozen HRNet weights do not move, and
+    a following inference forward sees the updated weights (cache invalidation)."""
+    import fami_pose_b200 as fp
+    from fami_pose_b200.train import TrainStep
+    fp.set_precision("fp32")
+    cfg = rh.make_cfg(48, 17)
+    m = fp.Alignment_V15(cfg, "train")
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(fo.seeded_state_dict(shapes, SEED), strict=True)
+    m = m.to(DEV).train()
+    kf, sup, tgt, tw = (t.to(DEV) for t in fo.synthetic_clip(1, seed=SEED + 3))
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    m.eval()
+    with torch.no_grad():
+        hm_before = m(kf, sup)[0].clone()
+    m.train()
+    step = TrainStep(m, lr=1e-3)
+    loss, hm = step(kf, sup, tgt, tw)
+    assert loss.is_cuda and loss.dim() == 0 and torch.isfinite(loss)
+    lr = 1e-3
+    for n, p in m.named_parameters():
+        d = (p.detach() - before[n])
+        if not p.requires_grad:
+            assert float(d.abs().max()) == 0.0, n
+            continue
+        g = p.grad
+        nz = g.abs() > 1e-12
+        if nz.any():
+            # Adam step 1: delta = -lr * g / (|g| + eps)
+            expect = -lr * g / (g.abs() + 1e-8)
+            assert float((d - expect).abs().max()) < 1e-7, n
+    m.eval()
+    with torch.no_grad():
+        hm_after = m(kf, sup)[0]
+    assert float((hm_after - hm_before).abs().max()) > 1e-6
