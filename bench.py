@@ -136,7 +136,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager step between cudaProfilerStart/Stop (ncu --profile-from-start off) and exit")
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+                    help="forward (default, the headline metric) | train: fwd + loss + bwd + gradient all-reduce + Adam "
+                         "with the backbone frozen (reference default), fp32 head, --precision arm for the backbone")
     args = ap.parse_args()
+    if args.mode == "train" and args.impl == "fami":
+        return run_train(args)
     if args.impl == "reference":
         if args.steps > 5:
             args.steps = 5
@@ -313,6 +318,97 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(fo, sd)
         print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_train(args):
+    """Training step at config 2 / 3 shape: one process per GPU, per-replica BatchNorm, ONE bucketed NCCL
+    all-reduce of the 1.06 M trainable gradients per step, fused Adam.  Eager launches."""
+    import torch
+    import torch.distributed as dist
+    import fami_pose_b200 as fp
+    from fami_pose_b200.train import TrainStep
+    from oracle import fami_oracle as fo   # synthetic inputs + seeded weights only
+    from oracle import ref_harness as rh
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ["NCCL_DEBUG"] = "WARN"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    fp.set_precision("fp32")
+    B = args.batch
+    model = fp.Alignment_V15(rh.make_cfg(WIDTH, J), "train")
+    sd = fo.seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()})
+    model.load_state_dict(sd)
+    model = model.to(dev).train()
+    if args.precision != "fp32":
+        model.backbone_precision = args.precision
+    host = tuple(t.pin_memory() for t in fo.synthetic_clip(B, seed=19970808 + rank))
+    devs = tuple(t.to(dev) for t in host)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    step = TrainStep(model)
+    n_train = sum(p.numel() for p in step.buckets.params)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    def e2e():
+        for d_, h_ in zip(devs, host):
+            d_.copy_(h_, non_blocking=True)
+        loss, _ = step(*devs)
+        loss_host.copy_(loss, non_blocking=True)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = fp._lib.launch_count()
+    step(*devs)
+    torch.cuda.synchronize()
+    launches = fp._lib.launch_count() - l0
+    ms = timed(lambda: step(*devs), args.steps, max(args.warmup, 3))
+    ms_e2e = timed(e2e, args.steps, 1)
+    sampler.stop_flag = True
+    clips = B * world * args.steps
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "mode": "train", "value": clips / (ms / 1000.0), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 head / %s backbone" % args.precision, "data": "synthetic",
+            "config": {"workload": "BASELINE config 2/3: Alignment_V15 HRNet-W48 384x288, 5-frame window, 17 joints, batch 32 "
+                                   "per GPU; TRAIN step = forward (train-mode BN) + JointsMSE + MI losses + backward of the "
+                                   "head (HRNet frozen, reference default) + gradient all-reduce + Adam",
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d, one all-reduce of %d fp32 "
+                       "gradients per step" % (world, n_train), "cuda_graph": False,
+                       "l2": "working set exceeds the 126 MB L2; no flush"},
+            "e2e": {"value": clips / (ms_e2e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches * args.steps, "launches_per_step": launches, "clocks": sampler.summary()}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

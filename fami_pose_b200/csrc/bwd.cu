@@ -25,75 +25,105 @@ struct BwdP {
   float* gb;           // [Cout], zeroed by the launcher
 };
 
-// one thread per (pixel, tap, 4-channel quad): grad wrt input (scatter), offset and mask
-__global__ void __launch_bounds__(256) dcn_bwd_data_kernel(const BwdP p) {
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  // 16-byte vector reduction (sm_90+): one L2 atomic transaction for the 4 channels of a corner
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// one thread per (pixel, tap, 4-channel quad): grad wrt input (scatter), offset and mask.
+// Persistent CTAs; kSmemW: the filter is staged once per CTA in shared memory, transposed to
+// [tap][o][C] so that the quads of a pixel read consecutive 16-byte words (g_col = W^T g_out).
+template <bool kSmemW>
+__global__ void __launch_bounds__(512, 2) dcn_bwd_data_kernel(const BwdP p) {
+  extern __shared__ float s_wt[];
   const int quads = p.C >> 2;
   const int64_t total = (int64_t)p.B * p.H * p.W * 9 * quads;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int q = (int)(i % quads);
-  const int tap = (int)((i / quads) % 9);
-  const int64_t pix = i / (9 * quads);
-  const int x = (int)(pix % p.W);
-  const int y = (int)((pix / p.W) % p.H);
-  const int b = (int)(pix / ((int64_t)p.W * p.H));
-  const int ch = q << 2, g = ch / p.cpg;
-  const int fr = tap / 3, fs = tap - fr * 3;
-
-  // g_col[c] = sum_o W[o,c,tap] * g_out[pix,o]
-  float gc[4] = {0.f, 0.f, 0.f, 0.f};
-  const float* gop = p.go + pix * p.gop;
-  const float* wr = p.w + (int64_t)(tap * p.C + ch) * p.CoutPad;
-  for (int o = 0; o < p.Cout; ++o) {
-    const float gv = __ldg(gop + o);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) gc[c] = fmaf(__ldg(wr + (int64_t)c * p.CoutPad + o), gv, gc[c]);
-  }
-  const float ody = __ldg(p.off + pix * p.offp + g * 18 + 2 * tap);
-  const float odx = __ldg(p.off + pix * p.offp + g * 18 + 2 * tap + 1);
-  const float mk = __ldg(p.mask + pix * p.mp + g * 9 + tap);
-  const float py = (float)(y - p.d + fr * p.d) + ody;
-  const float px = (float)(x - p.d + fs * p.d) + odx;
-  float g_m = 0.f, g_dy = 0.f, g_dx = 0.f;
-  if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
-    const int y0 = (int)floorf(py), x0 = (int)floorf(px);
-    const float ly = py - (float)y0, lx = px - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
-    const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= p.H - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= p.W - 1;
-    const int64_t img = (int64_t)b * p.H * p.W;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* xb = p.x + ch;
-    const float4 v1 = (y0ok && x0ok) ? ld4<float>(xb + (img + (int64_t)y0 * p.W + x0) * p.xp) : z;
-    const float4 v2 = (y0ok && x1ok) ? ld4<float>(xb + (img + (int64_t)y0 * p.W + x0 + 1) * p.xp) : z;
-    const float4 v3 = (y1ok && x0ok) ? ld4<float>(xb + (img + (int64_t)(y0 + 1) * p.W + x0) * p.xp) : z;
-    const float4 v4 = (y1ok && x1ok) ? ld4<float>(xb + (img + (int64_t)(y0 + 1) * p.W + x0 + 1) * p.xp) : z;
-    const float a1[4] = {v1.x, v1.y, v1.z, v1.w}, a2[4] = {v2.x, v2.y, v2.z, v2.w};
-    const float a3[4] = {v3.x, v3.y, v3.z, v3.w}, a4[4] = {v4.x, v4.y, v4.z, v4.w};
-    const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float val = w1 * a1[c] + w2 * a2[c] + w3 * a3[c] + w4 * a4[c];
-      g_m = fmaf(gc[c], val, g_m);
-      g_dy = fmaf(gc[c], hx * (a3[c] - a1[c]) + lx * (a4[c] - a2[c]), g_dy);
-      g_dx = fmaf(gc[c], hy * (a2[c] - a1[c]) + ly * (a4[c] - a3[c]), g_dx);
-      const float gm = gc[c] * mk;
-      float* gxb = p.gx + ch + c;
-      if (y0ok && x0ok) atomicAdd(gxb + (img + (int64_t)y0 * p.W + x0) * p.C, gm * w1);
-      if (y0ok && x1ok) atomicAdd(gxb + (img + (int64_t)y0 * p.W + x0 + 1) * p.C, gm * w2);
-      if (y1ok && x0ok) atomicAdd(gxb + (img + (int64_t)(y0 + 1) * p.W + x0) * p.C, gm * w3);
-      if (y1ok && x1ok) atomicAdd(gxb + (img + (int64_t)(y0 + 1) * p.W + x0 + 1) * p.C, gm * w4);
+  if (kSmemW) {
+    const int n = 9 * p.C * p.Cout;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      const int c = e % p.C;
+      const int t = e / p.C;
+      const int o = t % p.Cout, tap = t / p.Cout;
+      s_wt[e] = __ldg(p.w + (int64_t)(tap * p.C + c) * p.CoutPad + o);
     }
-    g_dy *= mk;
-    g_dx *= mk;
+    __syncthreads();
   }
-  // the cpg/4 quads of one offset group contribute to the same (offset, mask) entries
-  if (p.cpg == 4) {
-    p.goff[pix * (18 * p.G) + g * 18 + 2 * tap] = g_dy;
-    p.goff[pix * (18 * p.G) + g * 18 + 2 * tap + 1] = g_dx;
-    p.gmask[pix * (9 * p.G) + g * 9 + tap] = g_m;
-  } else {
-    atomicAdd(p.goff + pix * (18 * p.G) + g * 18 + 2 * tap, g_dy);
-    atomicAdd(p.goff + pix * (18 * p.G) + g * 18 + 2 * tap + 1, g_dx);
-    atomicAdd(p.gmask + pix * (9 * p.G) + g * 9 + tap, g_m);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % quads);
+    const int tap = (int)((i / quads) % 9);
+    const int64_t pix = i / (9 * quads);
+    const int x = (int)(pix % p.W);
+    const int y = (int)((pix / p.W) % p.H);
+    const int b = (int)(pix / ((int64_t)p.W * p.H));
+    const int ch = q << 2, g = ch / p.cpg;
+    const int fr = tap / 3, fs = tap - fr * 3;
+
+    // g_col[c] = sum_o W[o,c,tap] * g_out[pix,o]
+    float gc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* gop = p.go + pix * p.gop;
+    if (kSmemW) {
+      const float* wr = s_wt + (int64_t)tap * p.Cout * p.C + ch;
+      for (int o = 0; o < p.Cout; ++o) {
+        const float gv = __ldg(gop + o);
+        const float4 wv = *reinterpret_cast<const float4*>(wr + o * p.C);
+        gc[0] = fmaf(wv.x, gv, gc[0]); gc[1] = fmaf(wv.y, gv, gc[1]);
+        gc[2] = fmaf(wv.z, gv, gc[2]); gc[3] = fmaf(wv.w, gv, gc[3]);
+      }
+    } else {
+      const float* wr = p.w + (int64_t)(tap * p.C + ch) * p.CoutPad;
+      for (int o = 0; o < p.Cout; ++o) {
+        const float gv = __ldg(gop + o);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) gc[c] = fmaf(__ldg(wr + (int64_t)c * p.CoutPad + o), gv, gc[c]);
+      }
+    }
+    const float ody = __ldg(p.off + pix * p.offp + g * 18 + 2 * tap);
+    const float odx = __ldg(p.off + pix * p.offp + g * 18 + 2 * tap + 1);
+    const float mk = __ldg(p.mask + pix * p.mp + g * 9 + tap);
+    const float py = (float)(y - p.d + fr * p.d) + ody;
+    const float px = (float)(x - p.d + fs * p.d) + odx;
+    float g_m = 0.f, g_dy = 0.f, g_dx = 0.f;
+    if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
+      const int y0 = (int)floorf(py), x0 = (int)floorf(px);
+      const float ly = py - (float)y0, lx = px - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+      const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= p.H - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= p.W - 1;
+      const int64_t img = (int64_t)b * p.H * p.W;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* xb = p.x + ch;
+      const float4 v1 = (y0ok && x0ok) ? ld4<float>(xb + (img + (int64_t)y0 * p.W + x0) * p.xp) : z;
+      const float4 v2 = (y0ok && x1ok) ? ld4<float>(xb + (img + (int64_t)y0 * p.W + x0 + 1) * p.xp) : z;
+      const float4 v3 = (y1ok && x0ok) ? ld4<float>(xb + (img + (int64_t)(y0 + 1) * p.W + x0) * p.xp) : z;
+      const float4 v4 = (y1ok && x1ok) ? ld4<float>(xb + (img + (int64_t)(y0 + 1) * p.W + x0 + 1) * p.xp) : z;
+      const float a1[4] = {v1.x, v1.y, v1.z, v1.w}, a2[4] = {v2.x, v2.y, v2.z, v2.w};
+      const float a3[4] = {v3.x, v3.y, v3.z, v3.w}, a4[4] = {v4.x, v4.y, v4.z, v4.w};
+      const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+      float gm[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float val = w1 * a1[c] + w2 * a2[c] + w3 * a3[c] + w4 * a4[c];
+        g_m = fmaf(gc[c], val, g_m);
+        g_dy = fmaf(gc[c], hx * (a3[c] - a1[c]) + lx * (a4[c] - a2[c]), g_dy);
+        g_dx = fmaf(gc[c], hy * (a2[c] - a1[c]) + ly * (a4[c] - a3[c]), g_dx);
+        gm[c] = gc[c] * mk;
+      }
+      float* gxb = p.gx + ch;      // gx is dense (pitch C, C % 4 == 0): 16-byte aligned quads
+      if (y0ok && x0ok) red_add_v4(gxb + (img + (int64_t)y0 * p.W + x0) * p.C, gm[0] * w1, gm[1] * w1, gm[2] * w1, gm[3] * w1);
+      if (y0ok && x1ok) red_add_v4(gxb + (img + (int64_t)y0 * p.W + x0 + 1) * p.C, gm[0] * w2, gm[1] * w2, gm[2] * w2, gm[3] * w2);
+      if (y1ok && x0ok) red_add_v4(gxb + (img + (int64_t)(y0 + 1) * p.W + x0) * p.C, gm[0] * w3, gm[1] * w3, gm[2] * w3, gm[3] * w3);
+      if (y1ok && x1ok) red_add_v4(gxb + (img + (int64_t)(y0 + 1) * p.W + x0 + 1) * p.C, gm[0] * w4, gm[1] * w4, gm[2] * w4, gm[3] * w4);
+      g_dy *= mk;
+      g_dx *= mk;
+    }
+    // the cpg/4 quads of one offset group contribute to the same (offset, mask) entries
+    if (p.cpg == 4) {
+      p.goff[pix * (18 * p.G) + g * 18 + 2 * tap] = g_dy;
+      p.goff[pix * (18 * p.G) + g * 18 + 2 * tap + 1] = g_dx;
+      p.gmask[pix * (9 * p.G) + g * 9 + tap] = g_m;
+    } else {
+      atomicAdd(p.goff + pix * (18 * p.G) + g * 18 + 2 * tap, g_dy);
+      atomicAdd(p.goff + pix * (18 * p.G) + g * 18 + 2 * tap + 1, g_dx);
+      atomicAdd(p.gmask + pix * (9 * p.G) + g * 9 + tap, g_m);
+    }
   }
 }
 
@@ -255,7 +285,17 @@ int dcn_bwd_launch(const fami_dcn_desc* d, const float* x, const float* off, con
     cudaMemsetAsync(gmask, 0, sizeof(float) * npix * 9 * d->G, st);
   }
   const int64_t items = npix * 9 * (d->C / 4);
-  dcn_bwd_data_kernel<<<cdiv(items, 256), 256, 0, st>>>(p);
+  FAMI_CHECK_ARG((reinterpret_cast<uintptr_t>(gx) & 15) == 0, "fami_dcn_bwd: grad_x must be 16-byte aligned");
+  const size_t wsm = (size_t)9 * d->C * d->Cout * sizeof(float);
+  int64_t blocks = cdiv(items, 512);
+  if (wsm <= 200 * 1024) {
+    const int64_t cap = (int64_t)num_sms() * 2;        // persistent: the transposed filter is staged once per CTA
+    if (blocks > cap) blocks = cap;
+    cudaFuncSetAttribute(dcn_bwd_data_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm);
+    dcn_bwd_data_kernel<true><<<(unsigned)blocks, 512, wsm, st>>>(p);
+  } else {
+    dcn_bwd_data_kernel<false><<<(unsigned)blocks, 512, 0, st>>>(p);
+  }
   FAMI_CHECK_LAUNCH("dcn_bwd_data_kernel");
   const size_t smem = (size_t)kWChunk * (d->C + d->Cout) * sizeof(float);
   FAMI_CHECK_ARG(smem <= 200 * 1024, "fami_dcn_bwd: C + Cout too large for the weight-gradient kernel");

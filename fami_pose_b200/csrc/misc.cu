@@ -160,6 +160,45 @@ __global__ void __launch_bounds__(1024) bn_stats_kernel(const T* __restrict__ x,
   }
 }
 
+// fp32 input, 4 channels per thread, two independent row streams per thread
+__global__ void __launch_bounds__(1024) bn_stats_vec4_kernel(const float* __restrict__ x, int pitch, int64_t rows, int C,
+                                                             double* __restrict__ stats, int rows_per_block) {
+  extern __shared__ float sm[];
+  const int cq = C >> 2;
+  const int RG = blockDim.x / cq;
+  const int tid = threadIdx.x, q = tid % cq, rg = tid / cq;
+  int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), t = s, s2 = s, t2 = s;
+  if (rg < RG) {
+    int64_t r = r0 + rg;
+    for (; r + RG < r1; r += 2 * RG) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * pitch) + q);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(x + (r + RG) * pitch) + q);
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      t.x = fmaf(a.x, a.x, t.x); t.y = fmaf(a.y, a.y, t.y); t.z = fmaf(a.z, a.z, t.z); t.w = fmaf(a.w, a.w, t.w);
+      s2.x += b.x; s2.y += b.y; s2.z += b.z; s2.w += b.w;
+      t2.x = fmaf(b.x, b.x, t2.x); t2.y = fmaf(b.y, b.y, t2.y); t2.z = fmaf(b.z, b.z, t2.z); t2.w = fmaf(b.w, b.w, t2.w);
+    }
+    if (r < r1) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * pitch) + q);
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      t.x = fmaf(a.x, a.x, t.x); t.y = fmaf(a.y, a.y, t.y); t.z = fmaf(a.z, a.z, t.z); t.w = fmaf(a.w, a.w, t.w);
+    }
+    float* ps = sm + (rg * C + 4 * q);
+    float* pq = sm + ((RG + rg) * C + 4 * q);
+    ps[0] = s.x + s2.x; ps[1] = s.y + s2.y; ps[2] = s.z + s2.z; ps[3] = s.w + s2.w;
+    pq[0] = t.x + t2.x; pq[1] = t.y + t2.y; pq[2] = t.z + t2.z; pq[3] = t.w + t2.w;
+  }
+  __syncthreads();
+  if (tid < C) {
+    double ds = 0, dq = 0;
+    for (int r = 0; r < RG; ++r) { ds += sm[r * C + tid]; dq += sm[(RG + r) * C + tid]; }
+    atomicAdd(stats + tid, ds);
+    atomicAdd(stats + C + tid, dq);
+  }
+}
+
 template <typename TI, typename T>
 __global__ void bn_apply_act_kernel(const TI* __restrict__ x, int x_pitch, const float* __restrict__ scale,
                                     const float* __restrict__ shift, const T* __restrict__ res, int res_pitch,
@@ -182,6 +221,50 @@ __global__ void bn_apply_act_kernel(const TI* __restrict__ x, int x_pitch, const
       if (res) o += to_f<T>(res[op * res_pitch + c]);
       if (relu) o = fmaxf(o, 0.f);
       y[op * y_pitch + c] = from_f<T>(o);
+    }
+}
+
+// 4 channels per thread (C, pitches multiples of 4, 16-byte-aligned bases): 16-byte loads of the raw conv
+// output, 8/16-byte residual loads and stores
+template <typename TI, typename T>
+__global__ void bn_apply_act_vec4_kernel(const TI* __restrict__ x, int x_pitch, const float* __restrict__ scale,
+                                         const float* __restrict__ shift, const T* __restrict__ res, int res_pitch,
+                                         T* __restrict__ y, int y_pitch, int N, int Ho, int Wo, int C, int up, int relu) {
+  const int cq = C >> 2;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t tot = (int64_t)N * Ho * Wo * cq;
+  if (i >= tot) return;
+  const int c = (int)(i % cq) << 2;
+  const int64_t pix = i / cq;
+  const float4 xv = ld4<TI>(x + pix * x_pitch + c);
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+  const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+  const float4 v = make_float4(fmaf(xv.x, sc.x, sh.x), fmaf(xv.y, sc.y, sh.y), fmaf(xv.z, sc.z, sh.z), fmaf(xv.w, sc.w, sh.w));
+  if (up == 1) {
+    float4 o = v;
+    if (res) {
+      const float4 r = ld4<T>(res + pix * res_pitch + c);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    st4<T>(y + pix * y_pitch + c, o);
+    return;
+  }
+  const int xo = (int)(pix % Wo);
+  const int64_t t = pix / Wo;
+  const int yo = (int)(t % Ho);
+  const int n = (int)(t / Ho);
+  const int Hout = Ho * up, Wout = Wo * up;
+  for (int dy = 0; dy < up; ++dy)
+    for (int dx = 0; dx < up; ++dx) {
+      const int64_t op = ((int64_t)n * Hout + yo * up + dy) * Wout + xo * up + dx;
+      float4 o = v;
+      if (res) {
+        const float4 r = ld4<T>(res + op * res_pitch + c);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      st4<T>(y + op * y_pitch + c, o);
     }
 }
 
@@ -375,7 +458,15 @@ int bn_finalize_launch(const double* stats, const float* gamma, const float* bet
 int bn_apply_act_launch(const void* x, int xdt, int xp, const float* scale, const float* shift, const void* res, int rp,
                         void* y, int yp, int dt, int N, int Ho, int Wo, int C, int up, int relu, cudaStream_t st) {
   int64_t tot = (int64_t)N * Ho * Wo * C;
-  if (xdt == FAMI_F32) {
+  const int esz = dt == FAMI_F32 ? 4 : 2;
+  const bool vec = xdt == FAMI_F32 && C % 4 == 0 && xp % 4 == 0 && yp % 4 == 0 && (!res || rp % 4 == 0) &&
+                   (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & (4 * esz - 1)) == 0 &&
+                   (!res || (reinterpret_cast<uintptr_t>(res) & (4 * esz - 1)) == 0) &&
+                   (reinterpret_cast<uintptr_t>(scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(shift) & 15) == 0;
+  if (vec) {
+    DISPATCH_T(dt, bn_apply_act_vec4_kernel<float, T><<<cdiv(tot / 4, 256), 256, 0, st>>>(
+                       (const float*)x, xp, scale, shift, (const T*)res, rp, (T*)y, yp, N, Ho, Wo, C, up, relu);)
+  } else if (xdt == FAMI_F32) {
     DISPATCH_T(dt, bn_apply_act_kernel<float, T><<<cdiv(tot, 256), 256, 0, st>>>(
                        (const float*)x, xp, scale, shift, (const T*)res, rp, (T*)y, yp, N, Ho, Wo, C, up, relu);)
   } else if (xdt == FAMI_F16) {
@@ -389,6 +480,18 @@ int bn_apply_act_launch(const void* x, int xdt, int xp, const float* scale, cons
   return 0;
 }
 int bn_stats_launch(const void* x, int dt, int pitch, int64_t rows, int C, double* stats, cudaStream_t st) {
+  if (dt == FAMI_F32 && C % 4 == 0 && pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && C <= 1024) {
+    const int cq = C / 4;
+    int threads = 512;
+    if (cq > threads) threads = ((cq + 31) / 32) * 32;
+    const int RG = threads / cq;
+    const int rows_per_block = 1024;
+    const size_t smem = (size_t)2 * RG * C * sizeof(float);
+    bn_stats_vec4_kernel<<<cdiv(rows, rows_per_block), threads, smem, st>>>((const float*)x, pitch, rows, C, stats,
+                                                                           rows_per_block);
+    FAMI_CHECK_LAUNCH("bn_stats_vec4");
+    return 0;
+  }
   int threads = 256;
   if (C > threads) threads = ((C + 31) / 32) * 32;
   int RG = threads / C;

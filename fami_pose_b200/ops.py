@@ -234,10 +234,12 @@ def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None, out
     _need_cuda(x)
     if conv.groups != 1:
         raise NotImplementedError("grouped convolutions are not on the FAMI-Pose hot path")
-    if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad
-                                    or (bn is not None and bn.weight is not None and bn.weight.requires_grad)
-                                    or (residual is not None and residual.requires_grad)):
-        # differentiable path (fp32 arm): autograd.ConvBnActFunction
+    if x.dtype == torch.float32 and torch.is_grad_enabled() and (
+            x.requires_grad or conv.weight.requires_grad
+            or (bn is not None and bn.weight is not None and bn.weight.requires_grad)
+            or (residual is not None and residual.requires_grad)):
+        # differentiable path (fp32 arm): autograd.ConvBnActFunction.  The 16-bit arms are inference arms:
+        # their outputs never carry a grad_fn.
         if up != 1 or out is not None:
             raise NotImplementedError("differentiable conv: upsample-on-write / caller-provided outputs are "
                                       "inference-only (the reference default trains with HRNet frozen)")

@@ -179,11 +179,27 @@ class Alignment_V15(nn.Module):
             raise ValueError("model was built for %d supporting frames, got %d" % (self.num_sup, ns))
         C = self.width
         x = ops.frames_to_nhwc(kf_x, sup_x)                       # :117-119, frame-major batch
-        hm_all, feats = self.hrnet(x)                             # :120
-        feat_all = feats[0]
+        graph = (torch.is_grad_enabled() and ops.get_precision() == "fp32"
+                 and any(p.requires_grad for p in self.parameters()))
+        bp = getattr(self, "backbone_precision", None)
+        if graph and bp is not None and bp != ops.get_precision() and not any(
+                p.requires_grad for p in self.hrnet.parameters()):
+            # opt-in for training: the frozen backbone (96 % of the FLOPs) runs on the tensor-core arm, its
+            # outputs are widened to fp32 for the differentiable head
+            prev = ops.get_precision()
+            ops.set_precision(bp)
+            try:
+                with torch.no_grad():
+                    hm_all, feats = self.hrnet(x)
+            finally:
+                ops.set_precision(prev)
+            hm_all, feat_all = hm_all.float(), feats[0].float()
+        else:
+            hm_all, feats = self.hrnet(x)                         # :120
+            feat_all = feats[0]
         kf_bb_hm, kf_feat, sup_feat = hm_all[:B], feat_all[:B], feat_all[B:]
         _, _, H, W, _ = ops.meta(kf_feat)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if graph:
             return self._forward_graph(B, ns, kf_bb_hm, kf_feat, sup_feat)
 
         # :130-137 global translation per supporting frame (shared weights).  Eval-mode BN: all frames

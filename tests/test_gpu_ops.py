@@ -94,10 +94,16 @@ def test_conv_bn_act_eval(case):
             y = F.relu(y)
     conv_d = conv.to(DEV)
     bn_d = bnm.to(DEV) if bn else None
-    out = ops.conv_bn_act(nhwc(x), conv_d, bn_d, relu=relu, residual=nhwc(r) if res else None, up=up)
+    with torch.no_grad():      # the fused inference kernel (with grad enabled the fp32 arm records the unfused graph)
+        out = ops.conv_bn_act(nhwc(x), conv_d, bn_d, relu=relu, residual=nhwc(r) if res else None, up=up)
     got = back(out)
     tol = 2e-5 * float(y.abs().max()) + 1e-5
     assert float((got - y).abs().max()) <= tol
+    if up == 1:
+        # same values through the differentiable (unfused) path
+        out_g = ops.conv_bn_act(nhwc(x), conv_d, bn_d, relu=relu, residual=nhwc(r) if res else None, up=up)
+        assert out_g.requires_grad
+        assert float((back(out_g.detach()) - y).abs().max()) <= tol
 
 
 def test_conv_bn_train_mode():
