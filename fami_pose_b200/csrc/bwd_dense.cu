@@ -75,14 +75,15 @@ __global__ void conv_dgrad_gather_kernel(const float* __restrict__ gy, int gy_pi
 // wgrad: dw[co][ci][r][s] += sum_pixels gy[p][co] * x[p @ tap][ci].  Block = one (tap, 64 ci, 64 co) tile
 // over a chunk of output pixels; 256 threads, 4x4 accumulators each; fp32 atomics into dw (caller zeroes).
 // ---------------------------------------------------------------------------------------------
-constexpr int kWgPix = 16;
+constexpr int kWgPix = 32;
+template <bool kVec>
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ x, int x_pitch,
                                                          const float* __restrict__ gy, int gy_pitch,
                                                          float* __restrict__ dw, int N, int H, int W, int Cin, int Cout,
                                                          int kh, int kw, int stride, int pad, int dil, int Ho, int Wo,
                                                          int ci_tiles, int co_tiles, int pix_per_block) {
-  __shared__ float xs[kWgPix][64];
-  __shared__ float gs[kWgPix][64];
+  __shared__ __align__(16) float xs[kWgPix][64];
+  __shared__ __align__(16) float gs[kWgPix][64];
   int tile = blockIdx.x;
   const int cot = tile % co_tiles; tile /= co_tiles;
   const int cit = tile % ci_tiles; tile /= ci_tiles;
@@ -99,22 +100,43 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
   for (int64_t pb = p0; pb < p1; pb += kWgPix) {
-    // stage 16 pixels x 64 channels of x (at this tap) and of gy
-    for (int e = tid; e < kWgPix * 64; e += 256) {
-      const int pl = e >> 6, c = e & 63;
-      const int64_t p = pb + pl;
-      float xv = 0.f, gv = 0.f;
-      if (p < p1) {
-        const int xo = (int)(p % Wo);
-        const int64_t t = p / Wo;
-        const int yo = (int)(t % Ho), n = (int)(t / Ho);
-        const int yi = yo * stride - pad + r * dil, xi = xo * stride - pad + s * dil;
-        const int ci = cit * 64 + c, co = cot * 64 + c;
-        if (ci < Cin && yi >= 0 && yi < H && xi >= 0 && xi < W) xv = __ldg(x + ((int64_t)(n * H + yi) * W + xi) * x_pitch + ci);
-        if (co < Cout) gv = __ldg(gy + p * gy_pitch + co);
+    // stage kWgPix pixels x 64 channels of x (at this tap) and of gy
+    if (kVec) {
+      // 16-byte loads: thread -> (pixel, 4 channels); Cin, Cout and both pitches are multiples of 4
+      for (int e = tid; e < kWgPix * 16; e += 256) {
+        const int pl = e >> 4, c = (e & 15) << 2;
+        const int64_t p = pb + pl;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
+        if (p < p1) {
+          const int xo = (int)(p % Wo);
+          const int64_t t = p / Wo;
+          const int yo = (int)(t % Ho), n = (int)(t / Ho);
+          const int yi = yo * stride - pad + r * dil, xi = xo * stride - pad + s * dil;
+          const int ci = cit * 64 + c, co = cot * 64 + c;
+          if (ci < Cin && yi >= 0 && yi < H && xi >= 0 && xi < W)
+            xv = __ldg(reinterpret_cast<const float4*>(x + ((int64_t)(n * H + yi) * W + xi) * x_pitch + ci));
+          if (co < Cout) gv = __ldg(reinterpret_cast<const float4*>(gy + p * gy_pitch + co));
+        }
+        *reinterpret_cast<float4*>(&xs[pl][c]) = xv;
+        *reinterpret_cast<float4*>(&gs[pl][c]) = gv;
       }
-      xs[pl][c] = xv;
-      gs[pl][c] = gv;
+    } else {
+      for (int e = tid; e < kWgPix * 64; e += 256) {
+        const int pl = e >> 6, c = e & 63;
+        const int64_t p = pb + pl;
+        float xv = 0.f, gv = 0.f;
+        if (p < p1) {
+          const int xo = (int)(p % Wo);
+          const int64_t t = p / Wo;
+          const int yo = (int)(t % Ho), n = (int)(t / Ho);
+          const int yi = yo * stride - pad + r * dil, xi = xo * stride - pad + s * dil;
+          const int ci = cit * 64 + c, co = cot * 64 + c;
+          if (ci < Cin && yi >= 0 && yi < H && xi >= 0 && xi < W) xv = __ldg(x + ((int64_t)(n * H + yi) * W + xi) * x_pitch + ci);
+          if (co < Cout) gv = __ldg(gy + p * gy_pitch + co);
+        }
+        xs[pl][c] = xv;
+        gs[pl][c] = gv;
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -371,14 +393,22 @@ int conv_wgrad_launch(const fami_conv_desc* d, const float* x, const float* gy, 
   const int ci_tiles = (d->Cin + 63) / 64, co_tiles = (d->Cout + 63) / 64;
   const int tiles = d->kh * d->kw * ci_tiles * co_tiles;
   const int64_t npix = (int64_t)d->N * d->Ho * d->Wo;
-  int splits = (4 * num_sms() + tiles - 1) / tiles;
+  int splits = (8 * num_sms() + tiles - 1) / tiles;
   int64_t per = (npix + splits - 1) / splits;
   per = ((per + kWgPix - 1) / kWgPix) * kWgPix;
   if (per < kWgPix) per = kWgPix;
   splits = (int)((npix + per - 1) / per);
   dim3 grid(tiles, splits);
-  conv_wgrad_kernel<<<grid, 256, 0, st>>>(x, d->in_pitch, gy, d->out_pitch, dw, d->N, d->H, d->W, d->Cin, d->Cout, d->kh,
-                                          d->kw, d->stride, d->pad, d->dil, d->Ho, d->Wo, ci_tiles, co_tiles, (int)per);
+  const bool vec = d->Cin % 4 == 0 && d->Cout % 4 == 0 && d->in_pitch % 4 == 0 && d->out_pitch % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(gy) & 15) == 0;
+  if (vec)
+    conv_wgrad_kernel<true><<<grid, 256, 0, st>>>(x, d->in_pitch, gy, d->out_pitch, dw, d->N, d->H, d->W, d->Cin, d->Cout,
+                                                  d->kh, d->kw, d->stride, d->pad, d->dil, d->Ho, d->Wo, ci_tiles, co_tiles,
+                                                  (int)per);
+  else
+    conv_wgrad_kernel<false><<<grid, 256, 0, st>>>(x, d->in_pitch, gy, d->out_pitch, dw, d->N, d->H, d->W, d->Cin, d->Cout,
+                                                   d->kh, d->kw, d->stride, d->pad, d->dil, d->Ho, d->Wo, ci_tiles, co_tiles,
+                                                   (int)per);
   FAMI_CHECK_LAUNCH("conv_wgrad_kernel");
   if (dbias) {
     FAMI_CHECK_ARG(d->Cout <= 1024, "conv wgrad: bias gradient supports Cout <= 1024");
