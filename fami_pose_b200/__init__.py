@@ -7,7 +7,7 @@ is missing or if they are given CPU tensors.
 """
 from . import _lib, ops  # noqa: F401
 from .backbones import HighResolutionModule, HRNet, HRNetPlus  # noqa: F401
-from .decode import argmax_indices, get_max_preds  # noqa: F401
+from .decode import accuracy, argmax_indices, generate_heatmaps, get_final_preds, get_max_preds  # noqa: F401
 from .layers import (BasicBlock, Bottleneck, ChainOfBasicBlocks, DeformConv2d, Interpolate,  # noqa: F401
                      conv_bn_relu)
 from .loss import JointMSELoss, combine_losses  # noqa: F401

@@ -70,6 +70,12 @@ SIGNATURES = {
                                 c_void_p]),
     "fami_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                                c_int, c_void_p]),
+    "fami_final_preds": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                 c_int, c_int, c_void_p]),
+    "fami_pck_accuracy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                  c_void_p]),
+    "fami_gaussian_targets": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, c_void_p]),
     "fami_debug_read_trace": (c_int, [c_void_p, c_int]),
     "fami_debug_umma_rate": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "fami_debug_umma_rowshift": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

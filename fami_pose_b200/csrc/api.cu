@@ -57,6 +57,12 @@ int linear_bwd_launch(const float* x, const float* w, const float* gy, float* gx
                       cudaStream_t st);
 int adam_step_launch(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                      float bc1, float bc2_sqrt, cudaStream_t st);
+int final_preds_launch(const void* hm, int dt, int pitch, const int32_t* idx, const float* maxv, const float* center,
+                       const float* scale, float* preds, int B, int H, int W, int J, cudaStream_t st);
+int pck_accuracy_launch(const int32_t* pidx, const float* pmax, const int32_t* tidx, const float* tmax, double* out, int B,
+                        int H, int W, int J, float thr, cudaStream_t st);
+int gaussian_targets_launch(const float* joints, const float* vis, float* target, float* weight, int B, int J, int sigma,
+                            int img_w, int img_h, int hm_w, int hm_h, cudaStream_t st);
 int dcn_tc_supported(const fami_dcn_desc* d);
 int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const void* w, const float* bias, void* out,
                   cudaStream_t st);
@@ -232,6 +238,29 @@ int fami_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   return adam_step_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2),
                           (cudaStream_t)stream);
+}
+
+int fami_final_preds(const void* hm, int dtype, int pitch, const int32_t* idx, const float* maxvals, const float* center,
+                     const float* scale, float* preds, int B, int H, int W, int J, void* stream) {
+  FAMI_CHECK_ARG(hm && idx && maxvals && center && scale && preds, "fami_final_preds: null pointer");
+  FAMI_CHECK_ARG(valid_dtype(dtype) && B > 0 && H > 0 && W > 0 && J > 0 && pitch >= J, "fami_final_preds: bad arguments");
+  return final_preds_launch(hm, dtype, pitch, idx, maxvals, center, scale, preds, B, H, W, J, (cudaStream_t)stream);
+}
+
+int fami_pck_accuracy(const int32_t* pred_idx, const float* pred_max, const int32_t* target_idx, const float* target_max,
+                      double* out, int B, int H, int W, int J, float thr, void* stream) {
+  FAMI_CHECK_ARG(pred_idx && pred_max && target_idx && target_max && out, "fami_pck_accuracy: null pointer");
+  FAMI_CHECK_ARG(B > 0 && H > 0 && W > 0 && J > 0 && J <= 1024, "fami_pck_accuracy: bad shape");
+  return pck_accuracy_launch(pred_idx, pred_max, target_idx, target_max, out, B, H, W, J, thr, (cudaStream_t)stream);
+}
+
+int fami_gaussian_targets(const float* joints, const float* joints_vis, float* target, float* target_weight, int B, int J,
+                          int sigma, int img_w, int img_h, int hm_w, int hm_h, void* stream) {
+  FAMI_CHECK_ARG(joints && joints_vis && target && target_weight, "fami_gaussian_targets: null pointer");
+  FAMI_CHECK_ARG(B > 0 && J > 0 && sigma > 0 && img_w > 0 && img_h > 0 && hm_w > 0 && hm_h > 0,
+                 "fami_gaussian_targets: bad arguments");
+  return gaussian_targets_launch(joints, joints_vis, target, target_weight, B, J, sigma, img_w, img_h, hm_w, hm_h,
+                                 (cudaStream_t)stream);
 }
 
 int fami_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,

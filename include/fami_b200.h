@@ -216,6 +216,24 @@ int fami_softmax_pkl_bwd(const float* a, int a_pitch, const float* b, int b_pitc
  * first maximum wins; idx_out [B,J] int32, maxval_out [B,J] float.  hm NHWC.                    */
 int fami_argmax_hw(const void* hm, int dtype, int pitch, int32_t* idx_out, float* maxval_out, int B,
                    int HW, int J, void* stream);
+/* get_final_preds, datasets/process/heatmaps_process.py:47-81: from the flat argmax (idx, maxvals of
+ * fami_argmax_hw) -> (x, y), zeroed where maxval <= 0, moved +-0.25 px toward the higher neighbour when the
+ * peak is at least 2 px inside the map, then mapped back to image coordinates by the inverse of
+ * get_affine_transform(center, scale, rot = 0, [W, H]) (affine_transform.py:13-45; scale in units of 200 px).
+ * hm NHWC [B,H,W,J] (pitch); center, scale [B,2] float; preds [B,J,2] float.                        */
+int fami_final_preds(const void* hm, int dtype, int pitch, const int32_t* idx, const float* maxvals,
+                     const float* center, const float* scale, float* preds, int B, int H, int W, int J,
+                     void* stream);
+/* accuracy(output, target, hm_type='gaussian', thr), engine/core/utils/evaluate.py:13-75, from the argmaxes of
+ * the predicted and the ground-truth heat maps.  out: double[J+3] = acc[0..J] (acc[0] = average over joints
+ * with at least one valid sample, -1 marks joints without), avg_acc, cnt.                            */
+int fami_pck_accuracy(const int32_t* pred_idx, const float* pred_max, const int32_t* target_idx,
+                      const float* target_max, double* out, int B, int H, int W, int J, float thr, void* stream);
+/* generate_heatmaps, datasets/process/heatmaps_process.py:146-203, batched: joints / joints_vis [B,J,3]
+ * (image pixels; visibility in column 0) -> target [B,J,hm_h,hm_w] (NCHW float, as the loader produces it)
+ * and target_weight [B,J].                                                                           */
+int fami_gaussian_targets(const float* joints, const float* joints_vis, float* target, float* target_weight,
+                          int B, int J, int sigma, int img_w, int img_h, int hm_w, int hm_h, void* stream);
 
 /* ---- hardware probe (test infrastructure, tools/probe_umma.py) -------------------------------
  * out[128][16] = x[shift:shift+128][64] @ w[16][64]^T through one tcgen05 tile whose A descriptor

@@ -297,6 +297,114 @@ def refine_quarter_pixel(batch_heatmaps, coords):
     return coords
 
 
+def affine_from_points(src_pts, dst_pts):
+    """cv2.getAffineTransform(src, dst) (called at datasets/process/affine_transform.py:40-43): the 2x3
+    matrix mapping three float32 points src -> dst, solved in float64."""
+    A = np.zeros((6, 6), np.float64)
+    b = np.zeros(6, np.float64)
+    for i in range(3):
+        x, y = float(src_pts[i][0]), float(src_pts[i][1])
+        A[2 * i] = [x, y, 1, 0, 0, 0]
+        A[2 * i + 1] = [0, 0, 0, x, y, 1]
+        b[2 * i], b[2 * i + 1] = float(dst_pts[i][0]), float(dst_pts[i][1])
+    return np.linalg.solve(A, b).reshape(2, 3)
+
+
+def get_affine_transform(center, scale, output_size, inv=0):
+    """datasets/process/affine_transform.py:13-45 for rot = 0, shift = 0 (the only values the decode path
+    passes, heatmaps_process.py:76): three float32 point pairs, then cv2.getAffineTransform."""
+    scale_tmp = np.asarray(scale, np.float64) * 200.0
+    src_w = scale_tmp[0]
+    dst_w, dst_h = output_size[0], output_size[1]
+    src = np.zeros((3, 2), np.float32)
+    dst = np.zeros((3, 2), np.float32)
+    src[0, :] = np.asarray(center)
+    src[1, :] = np.asarray(center) + np.array([0.0, src_w * -0.5])
+    dst[0, :] = [dst_w * 0.5, dst_h * 0.5]
+    dst[1, :] = np.array([dst_w * 0.5, dst_h * 0.5]) + np.array([0, dst_w * -0.5], np.float32)
+
+    def third(a, b):
+        d = a - b
+        return b + np.array([-d[1], d[0]], np.float32)
+    src[2, :] = third(src[0], src[1])
+    dst[2, :] = third(dst[0], dst[1])
+    return affine_from_points(dst, src) if inv else affine_from_points(src, dst)
+
+
+def get_final_preds(batch_heatmaps, center, scale):
+    """datasets/process/heatmaps_process.py:47-73: argmax, +-0.25 px refinement, inverse affine back to image
+    coordinates (transform_preds :76-81).  Returns (preds [B,J,2] float32, maxvals [B,J,1])."""
+    hm = np.asarray(batch_heatmaps)
+    coords, maxvals, _ = get_max_preds(hm)
+    coords = refine_quarter_pixel(hm, coords)
+    B, J, H, W = hm.shape
+    preds = coords.copy()
+    for i in range(B):
+        t = get_affine_transform(center[i], scale[i], [W, H], inv=1)
+        for p in range(J):
+            v = t @ np.array([coords[i, p, 0], coords[i, p, 1], 1.0])
+            preds[i, p] = v[:2]
+    return preds, maxvals
+
+
+def accuracy(output, target, thr=0.5):
+    """engine/core/utils/evaluate.py:13-75 (hm_type='gaussian'): PCK on heatmap argmaxes, distances
+    normalised by (h, w)/10 -- in that order against (x, y), as the reference does -- ignoring joints whose
+    target argmax has x <= 1 or y <= 1.  Returns (acc [J+1], avg_acc, cnt, pred)."""
+    pred, _, _ = get_max_preds(output)
+    tgt, _, _ = get_max_preds(target)
+    B, J = pred.shape[:2]
+    h, w = output.shape[2], output.shape[3]
+    norm = np.ones((B, 2)) * np.array([h, w]) / 10
+    dists = np.zeros((J, B))
+    for n in range(B):
+        for c in range(J):
+            if tgt[n, c, 0] > 1 and tgt[n, c, 1] > 1:
+                dists[c, n] = np.linalg.norm(pred[n, c, :] / norm[n] - tgt[n, c, :] / norm[n])
+            else:
+                dists[c, n] = -1
+    acc = np.zeros(J + 1)
+    avg, cnt = 0.0, 0
+    for i in range(J):
+        valid = dists[i] != -1
+        acc[i + 1] = (dists[i][valid] < thr).sum() * 1.0 / valid.sum() if valid.sum() > 0 else -1
+        if acc[i + 1] >= 0:
+            avg += acc[i + 1]
+            cnt += 1
+    avg = avg / cnt if cnt != 0 else 0
+    if cnt != 0:
+        acc[0] = avg
+    return acc, avg, cnt, pred
+
+
+def generate_heatmaps(joints, joints_vis, sigma, image_size, heatmap_size, num_joints):
+    """datasets/process/heatmaps_process.py:146-203: unnormalised gaussian (centre value 1) of radius 3*sigma
+    pasted at round(joint / stride); weight 0 for joints whose patch misses the map entirely."""
+    target_weight = np.ones((num_joints, 1), np.float32)
+    target_weight[:, 0] = joints_vis[:, 0]
+    target = np.zeros((num_joints, heatmap_size[1], heatmap_size[0]), np.float32)
+    tmp = sigma * 3
+    stride = np.asarray(image_size, np.float64) / np.asarray(heatmap_size, np.float64)
+    size = 2 * tmp + 1
+    ax = np.arange(0, size, 1, np.float32)
+    g = np.exp(-((ax - size // 2) ** 2 + (ax[:, None] - size // 2) ** 2) / (2 * sigma ** 2))
+    for j in range(num_joints):
+        mu_x = int(joints[j][0] / stride[0] + 0.5)
+        mu_y = int(joints[j][1] / stride[1] + 0.5)
+        ul = [int(mu_x - tmp), int(mu_y - tmp)]
+        br = [int(mu_x + tmp + 1), int(mu_y + tmp + 1)]
+        if ul[0] >= heatmap_size[0] or ul[1] >= heatmap_size[1] or br[0] < 0 or br[1] < 0:
+            target_weight[j] = 0
+            continue
+        gx = max(0, -ul[0]), min(br[0], heatmap_size[0]) - ul[0]
+        gy = max(0, -ul[1]), min(br[1], heatmap_size[1]) - ul[1]
+        ix = max(0, ul[0]), min(br[0], heatmap_size[0])
+        iy = max(0, ul[1]), min(br[1], heatmap_size[1])
+        if target_weight[j] > 0.5:
+            target[j][iy[0]:iy[1], ix[0]:ix[1]] = g[gy[0]:gy[1], gx[0]:gx[1]]
+    return target, target_weight
+
+
 # --------------------------------------------------------------------------------------------
 # Whole-model functional restatement over a state_dict (torch CPU fp32/fp64).
 # Keys are the reference's state_dict keys (SURVEY.md section 5 "Checkpoint").
@@ -592,3 +700,31 @@ def synthetic_clip(B, H=384, W=288, num_sup=4, J=17, seed=19970808):
     tgt = torch.exp(-((xs - cx.round().view(B, J, 1, 1)) ** 2 + (ys - cy.round().view(B, J, 1, 1)) ** 2) / (2 * 3.0 ** 2))
     tw = (torch.rand(B, J, 1, generator=g) < 0.85).float()
     return kf, sup, tgt, tw
+
+
+def synthetic_decode_case(seed=19970808):
+    """Seeded inputs of the decode / accuracy / target-generation pins (regenerated by the tests)."""
+    rng = np.random.default_rng(seed)
+    B, J, H, W = 4, 17, 96, 72
+    hm = rng.standard_normal((B, J, H, W)).astype(np.float32)
+    hm[0, 0] = -1.0                                   # no positive value: coordinates are zeroed
+    hm[0, 1, 0, 0] = 6; hm[0, 2, H - 1, W - 1] = 6    # peaks on the border: no refinement
+    hm[0, 3, 1, 1] = 6; hm[0, 4, 2, 2] = 6            # first positions outside / inside the refinement band
+    hm[0, 5, H - 2, W - 2] = 6; hm[0, 6, H - 3, W - 3] = 6
+    hm[1, 0, 40, 30] = 6; hm[1, 0, 40, 31] = 6        # tie: first maximum wins; equal neighbours -> sign 0
+    tgt = np.zeros((B, J, H, W), np.float32)
+    for b in range(B):
+        for j in range(J):
+            if (b + j) % 5 == 0:
+                continue                              # all-zero target: argmax (0,0) -> ignored by accuracy
+            y, x = rng.integers(0, H), rng.integers(0, W)
+            tgt[b, j, y, x] = 1.0
+            if (b * J + j) % 3 == 0:
+                hm[b, j, y, min(x + int(rng.integers(0, 6)), W - 1)] = 7   # prediction close to the target
+    center = rng.uniform(80, 400, (B, 2)).astype(np.float32)
+    scale = rng.uniform(0.4, 2.6, (B, 2)).astype(np.float32)
+    joints = rng.uniform(-60, 440, (B, J, 3)).astype(np.float32)
+    joints[0, 0, :2] = [0, 0]; joints[0, 1, :2] = [287.9, 383.9]; joints[0, 2, :2] = [-11.9, 100]; joints[0, 3, :2] = [330, 100]
+    vis = (rng.random((B, J, 3)) > 0.2).astype(np.float32)
+    vis[..., 1] = vis[..., 0]; vis[..., 2] = 0
+    return hm, tgt, center, scale, joints, vis

@@ -111,3 +111,40 @@ def load_reference():
                    ChainOfBasicBlocks=ChainOfBasicBlocks, Interpolate=Interpolate,
                    conv_bn_relu=conv_bn_relu)
     return types.SimpleNamespace(**_loaded)
+
+
+_decode = {}
+
+
+def load_reference_decode():
+    """The unmodified reference post-/pre-processing functions (numpy + cv2; build container only):
+    datasets/process/heatmaps_process.py (get_max_preds, get_final_preds, generate_heatmaps) and
+    engine/core/utils/evaluate.py (accuracy).  The packages' __init__ files pull in the whole dataset /
+    engine stack, so the modules are loaded under bare package stubs whose __path__ points at the
+    reference directories (same recipe as load_reference)."""
+    if _decode:
+        return types.SimpleNamespace(**_decode)
+    if not reference_available():
+        raise RuntimeError("reference tree not present at %s" % REF)
+    import importlib
+    import importlib.util
+
+    def pkg(name, path):
+        m = sys.modules.get(name)
+        if m is None or not hasattr(m, "__path__"):
+            m = types.ModuleType(name)
+            m.__path__ = [path]
+            sys.modules[name] = m
+        return m
+
+    pkg("datasets", REF + "/datasets")
+    pkg("datasets.process", REF + "/datasets/process")
+    hp = importlib.import_module("datasets.process.heatmaps_process")
+    # evaluate.py does `from datasets.process.heatmaps_process import get_max_preds`; load it by path so the
+    # faked `engine` package of load_reference() does not matter
+    spec = importlib.util.spec_from_file_location("_fami_ref_evaluate", REF + "/engine/core/utils/evaluate.py")
+    ev = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ev)
+    _decode.update(get_max_preds=hp.get_max_preds, get_final_preds=hp.get_final_preds,
+                   generate_heatmaps=hp.generate_heatmaps, accuracy=ev.accuracy)
+    return types.SimpleNamespace(**_decode)

@@ -113,6 +113,25 @@ def make_model():
     print("model_reference.npz", {k: v.shape for k, v in out.items()})
 
 
+def make_decode():
+    """get_final_preds / accuracy / generate_heatmaps of the UNMODIFIED reference (numpy + cv2)."""
+    r = rh.load_reference_decode()
+    hm, tgt, center, scale, joints, vis = fo.synthetic_decode_case(SEED)
+    preds, maxvals = r.get_final_preds(hm.copy(), center, scale)
+    acc, avg, cnt, pred = r.accuracy(hm, tgt)
+    out = {"final_preds": preds, "maxvals": maxvals, "acc": acc, "avg_acc": np.float64(avg), "cnt": np.int64(cnt),
+           "acc_pred": pred}
+    acc2, avg2, cnt2, _ = r.accuracy(hm, tgt, thr=0.2)
+    out.update({"acc_thr02": acc2, "avg_acc_thr02": np.float64(avg2)})
+    T, Wt = [], []
+    for b in range(joints.shape[0]):
+        t, w = r.generate_heatmaps(joints[b], vis[b], 3, np.array([288, 384]), np.array([72, 96]), joints.shape[1])
+        T.append(t); Wt.append(w)
+    out["targets"] = np.stack(T); out["target_weight"] = np.stack(Wt)
+    np.savez_compressed(os.path.join(OUT, "decode_reference.npz"), **out)
+    print("decode_reference.npz", {k: np.shape(v) for k, v in out.items()})
+
+
 def grad_digest(g):
     """Compact pin of one gradient tensor: L2 norm, sum, and 48 evenly strided samples."""
     f = g.detach().double().flatten()
@@ -159,7 +178,10 @@ if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     if len(sys.argv) > 1 and sys.argv[1] == "train":
         make_train()
+    elif len(sys.argv) > 1 and sys.argv[1] == "decode":
+        make_decode()
     else:
+        make_decode()
         make_dcn()
         make_model()
         make_train()
