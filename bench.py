@@ -112,7 +112,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     v = Bs * args.steps / dt
     sample = "B=%d clips/step (bounded sample of the B=32 workload), %d steps" % (Bs, args.steps)
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -123,7 +123,22 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
+_OUT = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the process's original stdout; everything else any library prints on fd 1
+    (NCCL's version banner, torchrun chatter) has been diverted to stderr by main()."""
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -160,7 +175,6 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     fp.set_precision(args.precision)
@@ -317,7 +331,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(fo, sd)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -338,7 +352,6 @@ def run_train(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    os.environ["NCCL_DEBUG"] = "WARN"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     fp.set_precision("fp32")
@@ -396,7 +409,7 @@ def run_train(args):
     sampler.stop_flag = True
     clips = B * world * args.steps
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": METRIC, "mode": "train", "value": clips / (ms / 1000.0), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 head / %s backbone" % args.precision, "data": "synthetic",
