@@ -396,12 +396,26 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 
 }  // namespace
 
+// shared-memory footprint for a window radius R; the launcher takes the largest R <= dil + 5 that fits
+static size_t dcn_tc_smem(const fami_dcn_desc* d, int R) {
+  const int BN = ((d->Cout + 15) / 16) * 16;
+  const size_t win = (size_t)(kTH + 2 * R) * (kTW + 2 * R) * 128;
+  return win + kAStages * kATile + 9 * (size_t)BN * 128 + 1024 + 256 + (size_t)BN * 8 +
+         (size_t)kDcnEpiWarps * 32 * (128 + 16);
+}
+static int dcn_tc_radius(const fami_dcn_desc* d) {
+  for (int R = d->dil + 5; R >= d->dil + 2; --R)
+    if (dcn_tc_smem(d, R) <= 227 * 1024) return R;
+  return -1;
+}
+
 int dcn_tc_supported(const fami_dcn_desc* d) {
   if (!is_half_dtype(d->dtype) || d->om_layout != 1) return 0;
   if (d->C % 16 != 0 || d->C > 64 || d->G * 4 != d->C) return 0;      // G in {4, 8, 12, 16}
   if (d->off_pitch % 4 != 0) return 0;                                  // 16-byte loads of the (dy|dx|mask) runs
   if (d->Cout > 256 || d->x_pitch % 8 != 0) return 0;
   if (d->kh != 3 || d->kw != 3 || d->pad != d->dil || d->dil > 4) return 0;
+  if (dcn_tc_radius(d) < 0) return 0;                                   // filter + window do not fit in shared memory
   return 1;
 }
 
@@ -414,7 +428,8 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
   DcnTcParams p;
   memset(&p, 0, sizeof(p));
   p.B = d->B; p.H = d->H; p.W = d->W; p.C = d->C; p.Cout = d->Cout; p.G = d->G; p.d = d->dil;
-  p.R = d->dil + 5;   // dilation reach + 5 px of offset (2.5 sigma of the sigma = 2 px regime); beyond -> global path
+  p.R = dcn_tc_radius(d);   // dilation reach + up to 5 px of offset (2.5 sigma of the sigma = 2 px regime); beyond -> global path
+  FAMI_CHECK_ARG(p.R > 0, "dcn_tc: filter and window do not fit in shared memory");
   p.WH = kTH + 2 * p.R; p.WW = kTW + 2 * p.R;
   p.tiles_x = (d->W + kTW - 1) / kTW; p.tiles_y = (d->H + kTH - 1) / kTH;
   p.total_tiles = d->B * p.tiles_x * p.tiles_y;
@@ -455,8 +470,7 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FAMI_CHECK_ARG(r == CUDA_SUCCESS, "dcn_tc: cuTensorMapEncodeTiled(w) failed (%d)", (int)r);
   }
-  const size_t smem = (size_t)p.win_bytes + kAStages * kATile + 9 * (size_t)p.w_tile_bytes + 1024 + 256 +
-                      (size_t)p.BN * 8 + (size_t)kDcnEpiWarps * 32 * (128 + 16);
+  const size_t smem = dcn_tc_smem(d, p.R);
   FAMI_CHECK_ARG(smem <= 227 * 1024, "dcn_tc: shared memory budget exceeded (%zu B)", smem);
   int grid = p.total_tiles;
   const int sms = num_sms();

@@ -264,3 +264,39 @@ def test_fp16_batchnorm_train_mode(golden_dir):
         assert e1 <= 1e-1 and e2 <= 1e-1
     finally:
         fp.set_precision("fp32")
+
+
+def _build_config4(phase="validate"):
+    """BASELINE config 4 variant: HRNet-W32, 3-frame window (2 supporting frames), 15 joints (Sub-JHMDB shape).
+    The reference hard-codes 48 / 17 / 4 / 144 (Alignment_V15.py:62-106); the oracle for this configuration is
+    the reference computation with exactly those literals substituted.  Input 320x256, not
+    320x240: the reference's HRNet fuse layers (hrnet.py:99-112, x8 nearest upsample of the 1/32 branch) need
+    H and W divisible by 32 -- at 240 the stride-2 chain gives 8 columns and the upsampled 64 do not add to 60."""
+    import fami_pose_b200 as fp
+    cfg = rh.make_cfg(32, 15)
+    m = fp.Alignment_V15(cfg, phase, width=32, num_sup=2, offset_groups=8, feat_hw=(80, 64))
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = fo.seeded_state_dict(shapes, SEED + 4)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).eval(), sd
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("fp16", 1e-2), ("bf16", 3e-2)])
+def test_config4_w32_3frames_15joints_vs_oracle(prec, tol):
+    import fami_pose_b200 as fp
+    fp.set_precision("fp32")
+    m, sd = _build_config4()
+    kf, sup, _, _ = fo.synthetic_clip(2, H=320, W=256, num_sup=2, J=15, seed=SEED + 4)
+    rhm, rkf = fo.FunctionalFami(sd, width=32, num_joints=15, num_sup=2, offset_groups=8).alignment(kf, sup)
+    fp.set_precision(prec)
+    try:
+        with torch.no_grad():
+            hm, kfhm = m(kf.to(DEV), sup.to(DEV))
+    finally:
+        fp.set_precision("fp32")
+    assert hm.shape == (2, 15, 80, 64)
+    e1 = float((hm.cpu() - rhm).abs().max())
+    e2 = float((kfhm.cpu() - rkf).abs().max())
+    print("config 4 (%s): max-abs err final %.3e kf %.3e" % (prec, e1, e2))
+    assert e1 <= tol and e2 <= tol
+    _argmax_check(hm.cpu().numpy(), rhm.numpy(), tol)
