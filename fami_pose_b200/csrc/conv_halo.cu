@@ -226,6 +226,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     EpiArgs ea;
     ea.spitch = epi_stage_pitch(p.BN, p.out_f32);
     const uint32_t stage = smem_u32(stage_base) + (uint32_t)((warp - kEpiWarp0) * 32 * ea.spitch);
+    // two residual prefetch buffers per warp behind the staging buffers, when the allocation has room for them
+    const uint32_t rb0 = smem_u32(stage_base) + (uint32_t)(kEpiWarps * 32 * ea.spitch);
+    const uint32_t rbuf[2] = {rb0 + (uint32_t)((2 * (warp - kEpiWarp0)) * 32 * ea.spitch),
+                              rb0 + (uint32_t)((2 * (warp - kEpiWarp0) + 1) * 32 * ea.spitch)};
+    const bool pf_on = p.res != nullptr && 3 * ea.spitch <= (128 + 16) && !(p.trace & 16);
+    int pf_have = 0, pf_sel = 0;
     ea.s_scale = smem_u32(s_scale); ea.s_shift = smem_u32(s_shift); ea.res = p.res; ea.y = p.y;
     ea.Cout = p.Cout; ea.BN = p.BN; ea.out_pitch = p.out_pitch; ea.res_pitch = p.res_pitch;
     ea.out_f32 = p.out_f32; ea.relu = p.relu; ea.vec_ok = p.vec_ok; ea.up = 1; ea.Wout = p.W;
@@ -246,8 +252,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         valid = (yy < p.BH) && (xx < p.W) && (y0 + yy < p.H);
         return valid ? (img * p.H + (y0 + yy)) * p.W + xx : 0;
       };
-      // (a register prefetch of the residual one M-tile ahead was tried and measured SLOWER -- 207 vs
-      //  173 us on the 48->48 conv -- because of the extra live registers; kept simple.)
+      // The residual of the NEXT M-tile (or of the first M-tile of this CTA's next tile) is copied into one of
+      // two per-warp shared-memory buffers with cp.async while the current M-tile is drained: its global-load
+      // latency, which used to be exposed once per M-tile, is off the critical path and costs no registers.
+      // (A register prefetch was tried first and measured slower: 207 vs 173 us on the 48->48 conv.)
       uint4 no_pre[kPre];
       mbar_wait(tfull(acc), acc_phase);
       tc_fence_after();
@@ -255,8 +263,38 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int m = 0; m < p.NM; ++m) {
         bool valid;
         const int pix = row_pix(m, valid);
+        int ready = pf_have;            // was the residual of (tile, m) prefetched?
+        pf_have = 0;
+        if (pf_on) {
+          // next unit of this warp
+          bool nvalid = false;
+          int npix = 0;
+          bool have_next = true;
+          const int save_chb = ea.ch_base;
+          if (m + 1 < p.NM) {
+            npix = row_pix(m + 1, nvalid);
+          } else if (tile + (int)gridDim.x < p.total_tiles) {
+            const int ntile = tile + gridDim.x;
+            const int nnt = ntile % p.n_tiles;
+            const int nt2 = ntile / p.n_tiles;
+            const int nty = nt2 % p.tiles_per_img, nimg = nt2 / p.tiles_per_img;
+            const int ny0 = nty * p.BH;
+            const int yy = row / p.Wp, xx = row - yy * p.Wp;
+            nvalid = (yy < p.BH) && (xx < p.W) && (ny0 + yy < p.H);
+            npix = nvalid ? (nimg * p.H + (ny0 + yy)) * p.W + xx : 0;
+            ea.ch_base = nnt * p.BN;
+          } else {
+            have_next = false;
+          }
+          if (have_next) {
+            pf_have = epi_prefetch_async<TH>(ea, col_begin, col_end, nvalid, npix, rbuf[pf_sel ^ 1], lane) ? 1 : 0;
+            ea.ch_base = save_chb;
+          }
+          if (ready && pf_have) ready = 2;   // one newer cp.async group is in flight behind the one we need
+        }
         const uint32_t t_addr = tmem_base + (uint32_t)(acc * acc_cols + m * p.BN) + ((uint32_t)(quarter * 32) << 16);
-        if (!(p.trace & 2)) epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix, stage, lane, false, no_pre);
+        if (!(p.trace & 2)) epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix, stage, lane, false, no_pre, rbuf[pf_sel], ready);
+        pf_sel ^= 1;
       }
       tc_fence_before();
       __syncwarp();

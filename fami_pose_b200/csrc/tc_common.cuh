@@ -276,9 +276,45 @@ __device__ __forceinline__ bool epi_prefetch(const EpiArgs& a, int col_begin, in
   return true;
 }
 
+// Asynchronous residual prefetch (cp.async, no registers held): the residual of the FIRST column group of a
+// FUTURE epilogue_rows call is copied into the per-warp shared-memory buffer `rbuf` (same row pitch as the
+// staging buffer) and committed as one cp.async group.  Returns false (warp-uniform) if that call will not use
+// the vector path; epilogue_rows then loads the residual itself.
+template <typename TH>
+__device__ __forceinline__ bool epi_prefetch_async(const EpiArgs& a, int col_begin, int col_end, bool valid, int pix0,
+                                                   uint32_t rbuf, int lane) {
+  if (col_begin >= col_end || !a.res || a.up != 1 || a.out_f32) return false;
+  const int gc = (col_end - col_begin < 64) ? (col_end - col_begin) : 64;
+  const int chg = a.ch_base + col_begin;
+  if (!(a.vec_ok && (chg + gc <= a.Cout))) return false;
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  const int ppr = (gc * 2) >> 4;
+  const int lg = ppr <= 2 ? 1 : (ppr <= 4 ? 2 : 3);
+  const int lpr = 1 << lg, rpi = 32 >> lg;
+  const int sub_r = lane >> lg, sub_c = lane & (lpr - 1);
+  const bool lane_on = sub_c < ppr;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    if (it < lpr) {
+      const int r = it * rpi + sub_r;
+      const int pr = __shfl_sync(0xffffffffu, pix0, r);
+      if (lane_on && ((vmask >> r) & 1u)) {
+        const void* g = reinterpret_cast<const uint4*>(reinterpret_cast<const TH*>(a.res) + (int64_t)pr * a.res_pitch + chg) + sub_c;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rbuf + (uint32_t)(r * a.spitch + sub_c * 16)), "l"(g)
+                     : "memory");
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  return true;
+}
+
 template <typename TH>
 __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr, int col_begin, int col_end, bool valid,
-                                              int pix0, uint32_t stage, int lane, bool have_pre, uint4 (&pre)[kPre]) {
+                                              int pix0, uint32_t stage, int lane, bool have_pre, uint4 (&pre)[kPre],
+                                              uint32_t rbuf = 0, int r_ready = 0) {
+  // r_ready: 0 = load the residual here; 1 / 2 = the residual of the first column group was prefetched into
+  // `rbuf` by epi_prefetch_async and is the last (1) / second-to-last (2) cp.async group this thread committed
   if (col_begin >= col_end) return;   // warp-uniform
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
   const int esz = a.out_f32 ? 4 : 2;
@@ -300,7 +336,13 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
       for (int dx = 0; dx < a.up; ++dx) {
         const int pix = pix0 + dy * a.Wout + dx;
         // ---- 1. residual: coalesced global -> staging ------------------------------------------
-        if (a.res && grp_vec) {
+        uint32_t res_row = my_row;
+        if (a.res && grp_vec && r_ready && g0 == col_begin && a.up == 1) {
+          if (r_ready == 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
+          else asm volatile("cp.async.wait_group 1;" ::: "memory");
+          __syncwarp();
+          res_row = rbuf + (uint32_t)(lane * a.spitch);
+        } else if (a.res && grp_vec) {
           uint4 rreg[8];
           const bool use_pre = have_pre && g0 == col_begin && dy == 0 && dx == 0;   // warp-uniform
           if (!use_pre) {
@@ -342,8 +384,8 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
           }
           if (grp_vec) {
             if (a.res) {
-              const uint4 r0 = lds128(my_row + (uint32_t)(c0 * 2));
-              const uint4 r1 = lds128(my_row + (uint32_t)(c0 * 2 + 16));
+              const uint4 r0 = lds128(res_row + (uint32_t)(c0 * 2));
+              const uint4 r1 = lds128(res_row + (uint32_t)(c0 * 2 + 16));
               const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
