@@ -153,6 +153,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     EpiArgs ea;
     ea.spitch = epi_stage_pitch(p.BN, p.out_f32);
     const uint32_t stage = smem_u32(stage_base) + (uint32_t)((warp - 2) * 32 * ea.spitch);
+    // replicate-on-write epilogue with pipelined residual: two extra per-warp buffers behind the staging buffers
+    // (they fit in the allocation when the staging pitch is <= 48 B, i.e. 16 columns per warp)
+    const uint32_t rbuf = smem_u32(stage_base) + (uint32_t)(kEpiWarps * 32 * ea.spitch) + (uint32_t)((warp - 2) * 64 * ea.spitch);
+    const int up_fast = (p.up > 1 && p.res != nullptr && 3 * ea.spitch <= (128 + 16)) ? -1 : 0;
     ea.s_scale = smem_u32(s_scale); ea.s_shift = smem_u32(s_shift); ea.res = p.res; ea.y = p.y;
     ea.Cout = p.Cout; ea.BN = p.BN; ea.out_pitch = p.out_pitch; ea.res_pitch = p.res_pitch;
     ea.out_f32 = p.out_f32; ea.relu = p.relu; ea.vec_ok = p.vec_ok; ea.up = p.up; ea.Wout = Wout;
@@ -179,7 +183,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)(quarter * 32) << 16);
-      epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix0, stage, lane, have_pre, pre);
+      epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix0, stage, lane, have_pre, pre, rbuf, up_fast);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));   // one arrival per warp

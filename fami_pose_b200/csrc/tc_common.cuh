@@ -317,6 +317,86 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
   // `rbuf` by epi_prefetch_async and is the last (1) / second-to-last (2) cp.async group this thread committed
   if (col_begin >= col_end) return;   // warp-uniform
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  // ---- replicate-on-write fast path (fuse layers: 1x1 conv + BN + nearest x`up` + running sum + ReLU, hrnet.py:99-112)
+  // for a single 16-column chunk: the accumulator is read and scaled ONCE, then each of the up*up replicas adds its
+  // own residual and is stored; the residual of replica i+1 is in flight (cp.async into the other of two buffers
+  // `rbuf`, `rbuf + 32*spitch`) while replica i is processed.  r_ready == -1 selects it (the caller guarantees the
+  // two buffers exist).
+  if (r_ready == -1 && a.up > 1 && a.res && !a.out_f32 && col_end - col_begin == 16 && a.vec_ok &&
+      a.ch_base + col_end <= a.Cout) {
+    const int chg = a.ch_base + col_begin;
+    const uint32_t my_row = stage + (uint32_t)(lane * a.spitch);
+    const int sub_r = lane >> 1, sub_c = lane & 1;     // 2 x 16-byte pieces per row, 16 rows per iteration
+    auto fetch = [&](int rep, uint32_t buf) {
+      const int dy = rep / a.up, dx = rep - dy * a.up;
+      const int pix = pix0 + dy * a.Wout + dx;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int r = it * 16 + sub_r;
+        const int pr = __shfl_sync(0xffffffffu, pix, r);
+        if ((vmask >> r) & 1u) {
+          const void* g = reinterpret_cast<const uint4*>(reinterpret_cast<const TH*>(a.res) + (int64_t)pr * a.res_pitch + chg) + sub_c;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(buf + (uint32_t)(r * a.spitch + sub_c * 16)), "l"(g)
+                       : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch(0, rbuf);
+    uint32_t v[16];
+    tmem_ld16(t_addr + (uint32_t)col_begin, v);
+    tmem_ld_wait();
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 sc = lds128f(a.s_scale + (uint32_t)(chg + 4 * j) * 4u);
+      const float4 sh = lds128f(a.s_shift + (uint32_t)(chg + 4 * j) * 4u);
+      o[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
+      o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
+      o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
+      o[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
+    }
+    const int nrep = a.up * a.up;
+    for (int rep = 0; rep < nrep; ++rep) {
+      const uint32_t cur = rbuf + (uint32_t)((rep & 1) * 32 * a.spitch);
+      if (rep + 1 < nrep) {
+        fetch(rep + 1, rbuf + (uint32_t)(((rep + 1) & 1) * 32 * a.spitch));
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncwarp();
+      const uint4 r0 = lds128(cur + (uint32_t)(lane * a.spitch));
+      const uint4 r1 = lds128(cur + (uint32_t)(lane * a.spitch + 16));
+      const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 t = h2_to_f2<TH>(rw[j]);
+        float x0 = o[2 * j] + t.x, x1 = o[2 * j + 1] + t.y;
+        if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+        w[j] = f2_to_h2<TH>(x0, x1);
+      }
+      sts128(my_row, make_uint4(w[0], w[1], w[2], w[3]));
+      sts128(my_row + 16, make_uint4(w[4], w[5], w[6], w[7]));
+      __syncwarp();
+      const int dy = rep / a.up, dx = rep - dy * a.up;
+      const int pix = pix0 + dy * a.Wout + dx;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int r = it * 16 + sub_r;
+        const int pr = __shfl_sync(0xffffffffu, pix, r);
+        if ((vmask >> r) & 1u) {
+          const uint4 val = lds128(stage + (uint32_t)(r * a.spitch + sub_c * 16));
+          uint8_t* dst = reinterpret_cast<uint8_t*>(a.y) + ((int64_t)pr * a.out_pitch + chg) * 2 + sub_c * 16;
+          *reinterpret_cast<uint4*>(dst) = val;
+        }
+      }
+      __syncwarp();
+    }
+    return;
+  }
+  if (r_ready < 0) r_ready = 0;
   const int esz = a.out_f32 ? 4 : 2;
   const int gmax = a.out_f32 ? 32 : 64;   // columns per staged group (128 B per row)
   const uint32_t my_row = stage + (uint32_t)(lane * a.spitch);
