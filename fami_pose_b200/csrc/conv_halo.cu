@@ -52,7 +52,7 @@ struct HaloParams {
   int Cout, BN;
   int relu, out_f32, vec_ok;
   int out_pitch, res_pitch;
-  int sA, sB, b_resident, acc_bufs, n_iss;
+  int sA, sB, b_resident, acc_bufs, n_iss, acc_stride;
   uint32_t a_stage_bytes, b_tile_bytes, a_box_bytes;
   uint32_t ab_format;
   int trace;
@@ -104,7 +104,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int acc_cols = p.NM * p.BN;     // TMEM columns of one accumulator set
+  const int acc_cols = p.NM * p.acc_stride;     // TMEM columns of one accumulator set
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====
@@ -196,8 +196,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 b_lo = sw128_desc_lo(smem_u32(smemB + (size_t)sb * p.b_tile_bytes));
               }
               const bool acc_first = (cc | tap) != 0;
-              uint32_t a_lo = ((p.trace & 4) ? a_lo0 : a_tap) + (uint32_t)issuer * 1024u, dcol = d_tmem + (uint32_t)(issuer * p.BN);
-              const uint32_t a_inc = (uint32_t)p.n_iss * 1024u, d_inc = (uint32_t)(p.n_iss * p.BN);
+              uint32_t a_lo = ((p.trace & 4) ? a_lo0 : a_tap) + (uint32_t)issuer * 1024u, dcol = d_tmem + (uint32_t)(issuer * p.acc_stride);
+              const uint32_t a_inc = (uint32_t)p.n_iss * 1024u, d_inc = (uint32_t)(p.n_iss * p.acc_stride);
               if (p.trace & 8) b_lo = sw128_desc_lo(smem_u32(smemB));
               for (int m = issuer; m < p.NM; m += p.n_iss, a_lo += a_inc, dcol += d_inc)
                 umma_ksteps_n(nk, leader, dcol, a_lo, b_lo, idesc, acc_first);
@@ -292,7 +292,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (ready && pf_have) ready = 2;   // one newer cp.async group is in flight behind the one we need
         }
-        const uint32_t t_addr = tmem_base + (uint32_t)(acc * acc_cols + m * p.BN) + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t t_addr = tmem_base + (uint32_t)(acc * acc_cols + m * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
         if (!(p.trace & 2)) epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix, stage, lane, false, no_pre, rbuf[pf_sel], ready);
         pf_sel ^= 1;
       }
@@ -313,7 +313,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 struct HaloCfg {
   int BN, n_tiles, CoutPad, cchunks;
-  int BH, NM, HR, sA, sB, b_resident, acc_bufs;
+  int BH, NM, HR, sA, sB, b_resident, acc_bufs, acc_stride;
   size_t smem;
   bool ok;
 };
@@ -333,14 +333,16 @@ HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d) {
   const int cchunks = (Cin + 63) / 64;
   const int ksteps = 9 * cchunks;
   double best_score = -1;
+  static const int ast_env = getenv("FAMI_HALO_ACCSTRIDE") ? atoi(getenv("FAMI_HALO_ACCSTRIDE")) : 0;
+  const int ast = ast_env > 0 ? ((BN + ast_env - 1) / ast_env) * ast_env : BN;   // TMEM column stride between M-tile accumulators
   for (int NM = 1; NM <= 8; ++NM) {
-    if (NM * BN > 512) break;
+    if (NM * ast > 512) break;
     int BH = (NM * 128) / Wp;
     if (BH < 1) continue;
     if (BH > H) BH = H;
     if (BH + 2 * d > 256) continue;
     const int nm = (BH * Wp + 127) / 128;   // actual M-tiles needed for BH rows
-    const int acc_bufs = (2 * nm * BN <= 512) ? 2 : 1;
+    const int acc_bufs = (2 * nm * ast <= 512) ? 2 : 1;
     int HR = nm * 128 + (2 * Wp + 2) * d;
     const int box_rows = (BH + 2 * d) * Wp;
     if (HR < box_rows) HR = box_rows;
@@ -370,7 +372,7 @@ HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d) {
           best.ok = true;
           best.BN = BN; best.n_tiles = n_tiles; best.CoutPad = BN * n_tiles; best.cchunks = cchunks;
           best.BH = BH; best.NM = nm; best.HR = HR; best.sA = sA; best.sB = resident ? 1 : sB;
-          best.b_resident = resident; best.acc_bufs = acc_bufs; best.smem = smem;
+          best.b_resident = resident; best.acc_bufs = acc_bufs; best.smem = smem; best.acc_stride = ast;
         }
         break;  // largest sA that fits for this (NM, resident)
       }
@@ -437,7 +439,7 @@ int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, cons
   p.vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((d->out_pitch * osz) % 16 == 0) &&
              (!res || (((reinterpret_cast<uintptr_t>(res) & 15) == 0) && (d->res_pitch % 8 == 0)));
   p.out_pitch = d->out_pitch; p.res_pitch = d->res_pitch;
-  p.sA = c.sA; p.sB = c.sB; p.b_resident = c.b_resident; p.acc_bufs = c.acc_bufs;
+  p.sA = c.sA; p.sB = c.sB; p.b_resident = c.b_resident; p.acc_bufs = c.acc_bufs; p.acc_stride = c.acc_stride;
   p.n_iss = c.NM < kMmaWarps ? c.NM : kMmaWarps;
   if (getenv("FAMI_HALO_ISS")) { int v = atoi(getenv("FAMI_HALO_ISS")); if (v >= 1 && v <= p.n_iss) p.n_iss = v; }
   p.a_stage_bytes = (uint32_t)c.HR * 128u;

@@ -32,7 +32,7 @@ struct TcParams {
   int up, relu;
   int out_pitch, res_pitch;
   int out_f32, vec_ok;
-  int stages;
+  int stages, pipe;   // pipe: pipelined residual epilogue (epilogue_rows_pipelined)
   const float* scale;
   const float* shift;
   const void* res;   // TH
@@ -157,6 +157,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // (they fit in the allocation when the staging pitch is <= 48 B, i.e. 16 columns per warp)
     const uint32_t rbuf = smem_u32(stage_base) + (uint32_t)(kEpiWarps * 32 * ea.spitch) + (uint32_t)((warp - 2) * 64 * ea.spitch);
     const int up_fast = (p.up > 1 && p.res != nullptr && 3 * ea.spitch <= (128 + 16)) ? -1 : 0;
+    // pipelined residual epilogue: staging + two residual buffers per warp at the 32-column pitch
+    const uint32_t pp = (uint32_t)epi_pipe_pitch();
+    const uint32_t pstage = smem_u32(stage_base) + (uint32_t)(warp - 2) * 96u * pp;
+    int psel = 0, pprimed = 0;
     ea.s_scale = smem_u32(s_scale); ea.s_shift = smem_u32(s_shift); ea.res = p.res; ea.y = p.y;
     ea.Cout = p.Cout; ea.BN = p.BN; ea.out_pitch = p.out_pitch; ea.res_pitch = p.res_pitch;
     ea.out_f32 = p.out_f32; ea.relu = p.relu; ea.vec_ok = p.vec_ok; ea.up = p.up; ea.Wout = Wout;
@@ -183,7 +187,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)(quarter * 32) << 16);
-      epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix0, stage, lane, have_pre, pre, rbuf, up_fast);
+      if (p.pipe) {
+        const int ntile = tile + gridDim.x;
+        const bool have_next = ntile < total_tiles;
+        const int nmt = ntile / p.n_tiles, nnt = ntile - nmt * p.n_tiles;
+        const int nm = nmt * kBM + row;
+        const bool nvalid = have_next && nm < p.M;
+        epilogue_rows_pipelined<TH>(ea, t_addr, col_begin, col_end, valid, pix0, pstage, pstage + 32u * pp, pstage + 64u * pp, lane,
+                                    psel, pprimed, have_next, nvalid, nvalid ? nm : 0, nnt * p.BN);
+      } else {
+        epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix0, stage, lane, have_pre, pre, rbuf, up_fast);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));   // one arrival per warp
@@ -308,12 +322,15 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   p.ab_format = d->dtype == FAMI_F16 ? 0u : 1u;
 
   const int stage_bytes = kABytes + t.BN * 128;
-  int stages = (150 * 1024) / stage_bytes;
+  p.pipe = (epi_pipe_ok(t.BN, d->Cout, p.vec_ok, out_f32, d->up, res != nullptr) && d->Cout == t.BN * t.n_tiles &&
+            getenv("FAMI_NO_EPI_PIPE") == nullptr) ? 1 : 0;
+  const size_t epi_bytes = p.pipe ? (size_t)kEpiWarps * 32 * 3 * epi_pipe_pitch() : (size_t)kEpiWarps * 32 * (128 + 16);
+  int stages = p.pipe ? (int)((228000 - (size_t)t.CoutPad * 8 - epi_bytes) / stage_bytes) : (150 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 4) * 8 + 64 +
-                      (size_t)t.CoutPad * 8 + (size_t)kEpiWarps * 32 * (128 + 16);
+                      (size_t)t.CoutPad * 8 + epi_bytes;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -525,6 +525,123 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
   }
 }
 
+// Pipelined residual epilogue (up == 1, 16-bit output, vector path): the warp's column range is drained in groups of
+// 32 columns; while group g is processed, the residual of the next unit -- group g+1 of this tile, or group 0 of the
+// warp's next tile -- is already in flight (cp.async into the other of two per-warp buffers).  Only the very first
+// unit of a warp pays the global-load latency.  `sel` (buffer parity) and `primed` (the first group of this call has
+// been prefetched by the previous call) carry the state across calls.
+constexpr int kPipeCols = 32;
+__host__ __device__ inline int epi_pipe_pitch() { return kPipeCols * 2 + 16; }
+__host__ __device__ inline bool epi_pipe_ok(int BN, int Cout_total, int vec_ok, int out_f32, int up, bool has_res) {
+  return has_res && up == 1 && !out_f32 && vec_ok && (Cout_total % 16 == 0) && BN % 16 == 0;
+}
+template <typename TH>
+__device__ __forceinline__ void epi_pipe_fetch(const EpiArgs& a, int chg, int gc, unsigned vmask, int pix, uint32_t buf, int lane) {
+  const int ppr = (gc * 2) >> 4;                 // 16-byte pieces per row: 2 or 4
+  const int lg = ppr <= 2 ? 1 : 2;
+  const int lpr = 1 << lg, rpi = 32 >> lg;
+  const int sub_r = lane >> lg, sub_c = lane & (lpr - 1);
+  const int pitch = epi_pipe_pitch();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    if (it < lpr) {
+      const int r = it * rpi + sub_r;
+      const int pr = __shfl_sync(0xffffffffu, pix, r);
+      if ((vmask >> r) & 1u) {
+        const void* g = reinterpret_cast<const uint4*>(reinterpret_cast<const TH*>(a.res) + (int64_t)pr * a.res_pitch + chg) + sub_c;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(buf + (uint32_t)(r * pitch + sub_c * 16)), "l"(g) : "memory");
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <typename TH>
+__device__ __forceinline__ void epilogue_rows_pipelined(const EpiArgs& a, uint32_t t_addr, int col_begin, int col_end, bool valid,
+                                                        int pix0, uint32_t stage, uint32_t rb0, uint32_t rb1, int lane, int& sel,
+                                                        int& primed, bool have_next, bool next_valid, int next_pix,
+                                                        int next_ch_base) {
+  if (col_begin >= col_end) return;   // warp-uniform
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  const unsigned nmask = __ballot_sync(0xffffffffu, next_valid);
+  const int pitch = epi_pipe_pitch();
+  const uint32_t my_row = stage + (uint32_t)(lane * pitch);
+  if (!primed) {   // very first unit of this warp: nobody prefetched it
+    const int gc0 = (col_end - col_begin < kPipeCols) ? (col_end - col_begin) : kPipeCols;
+    epi_pipe_fetch<TH>(a, a.ch_base + col_begin, gc0, vmask, pix0, sel ? rb1 : rb0, lane);
+  }
+  for (int g0 = col_begin; g0 < col_end; g0 += kPipeCols) {
+    const int gc = (col_end - g0 < kPipeCols) ? (col_end - g0) : kPipeCols;
+    const int chg = a.ch_base + g0;
+    const uint32_t cur = sel ? rb1 : rb0, nxt = sel ? rb0 : rb1;
+    // next unit in flight
+    bool pending = false;
+    if (g0 + kPipeCols < col_end) {
+      const int ngc = (col_end - (g0 + kPipeCols) < kPipeCols) ? (col_end - (g0 + kPipeCols)) : kPipeCols;
+      epi_pipe_fetch<TH>(a, chg + kPipeCols, ngc, vmask, pix0, nxt, lane);
+      pending = true;
+    } else if (have_next) {
+      const int ngc = (col_end - col_begin < kPipeCols) ? (col_end - col_begin) : kPipeCols;
+      epi_pipe_fetch<TH>(a, next_ch_base + col_begin, ngc, nmask, next_pix, nxt, lane);
+      pending = true;
+    }
+    if (pending) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const uint32_t res_row = cur + (uint32_t)(lane * pitch);
+    for (int c0 = 0; c0 < gc; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(t_addr + (uint32_t)(g0 + c0), v);
+      tmem_ld_wait();
+      const int ch0 = chg + c0;
+      float o[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 sc = lds128f(a.s_scale + (uint32_t)(ch0 + 4 * j) * 4u);
+        const float4 sh = lds128f(a.s_shift + (uint32_t)(ch0 + 4 * j) * 4u);
+        o[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
+        o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
+        o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
+        o[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
+      }
+      const uint4 r0 = lds128(res_row + (uint32_t)(c0 * 2));
+      const uint4 r1 = lds128(res_row + (uint32_t)(c0 * 2 + 16));
+      const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 t = h2_to_f2<TH>(rw[j]);
+        float x0 = o[2 * j] + t.x, x1 = o[2 * j + 1] + t.y;
+        if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+        w[j] = f2_to_h2<TH>(x0, x1);
+      }
+      sts128(my_row + (uint32_t)(c0 * 2), make_uint4(w[0], w[1], w[2], w[3]));
+      sts128(my_row + (uint32_t)(c0 * 2 + 16), make_uint4(w[4], w[5], w[6], w[7]));
+    }
+    __syncwarp();
+    {
+      const int ppr = (gc * 2) >> 4;
+      const int lg = ppr <= 2 ? 1 : 2;
+      const int lpr = 1 << lg, rpi = 32 >> lg;
+      const int sub_r = lane >> lg, sub_c = lane & (lpr - 1);
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        if (it < lpr) {
+          const int r = it * rpi + sub_r;
+          const int pr = __shfl_sync(0xffffffffu, pix0, r);
+          if ((vmask >> r) & 1u) {
+            const uint4 val = lds128(stage + (uint32_t)(r * pitch + sub_c * 16));
+            uint8_t* dst = reinterpret_cast<uint8_t*>(a.y) + ((int64_t)pr * a.out_pitch + chg) * 2 + sub_c * 16;
+            *reinterpret_cast<uint4*>(dst) = val;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    sel ^= 1;
+    primed = pending ? 1 : 0;
+  }
+}
+
 // ---- driver entry points for tensor-map encoding (resolved at run time, no -lcuda) ------------
 typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
