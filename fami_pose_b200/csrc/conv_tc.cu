@@ -124,21 +124,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      const uint32_t a_lo0 = sw128_desc_lo(smem_u32(smem));           // stage 0, A tile (descriptor low word: addr >> 4)
+      const uint32_t stage_step = stage_bytes >> 4, b_off = (uint32_t)kABytes >> 4;
+      const uint32_t empty_off = 8u * (uint32_t)stages;               // empty_bar(s) = full_bar(s) + empty_off
+      uint32_t a_lo = a_lo0, full_cur = bar0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_u + (uint32_t)acc * kAccCols;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const int cc = ks % p.cchunks;
-          const int nk = (cc == p.cchunks - 1) ? p.last_kk : 4;
-          umma_ksteps_n(nk, leader, d_tmem, sw128_desc_lo(a_addr), sw128_desc_lo(a_addr + kABytes), idesc, ks != 0);
-          if (leader) umma_commit(empty_bar(stage));   // frees the smem slot once the MMAs above have read it
-          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        // The issuing thread's own instruction stream is the bottleneck of this kernel when it is long (a k-step of
+        // four N=96 MMAs is ~220 clk of tensor pipe): no divisions, descriptors and barrier addresses advanced
+        // incrementally, the channel-chunk loop nested inside the tap loop.
+        bool accum = false;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          for (int cc = 0; cc < p.cchunks; ++cc) {
+            mbar_wait(full_cur, phase);
+            tc_fence_after();
+            const int nk = (cc == p.cchunks - 1) ? p.last_kk : 4;
+            umma_ksteps_n(nk, leader, d_tmem, a_lo, a_lo + b_off, idesc, accum);
+            accum = true;
+            if (leader) umma_commit(full_cur + empty_off);   // frees the smem slot once the MMAs above have read it
+            a_lo += stage_step;
+            full_cur += 8u;
+            if (++stage == stages) { stage = 0; phase ^= 1u; a_lo = a_lo0; full_cur = bar0; }
+          }
         }
         if (leader) umma_commit(tfull_bar(acc));       // accumulator complete -> epilogue
       }
@@ -325,7 +336,7 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   p.pipe = (epi_pipe_ok(t.BN, d->Cout, p.vec_ok, out_f32, d->up, res != nullptr) && d->Cout == t.BN * t.n_tiles &&
             getenv("FAMI_NO_EPI_PIPE") == nullptr) ? 1 : 0;
   const size_t epi_bytes = p.pipe ? (size_t)kEpiWarps * 32 * 3 * epi_pipe_pitch() : (size_t)kEpiWarps * 32 * (128 + 16);
-  int stages = p.pipe ? (int)((228000 - (size_t)t.CoutPad * 8 - epi_bytes) / stage_bytes) : (150 * 1024) / stage_bytes;
+  int stages = (int)((228000 - (size_t)t.CoutPad * 8 - epi_bytes) / stage_bytes);   // all the shared memory there is: the kernel is bound by bytes in flight
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
