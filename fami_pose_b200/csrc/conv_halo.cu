@@ -62,6 +62,26 @@ struct HaloParams {
   void* y;
 };
 
+// The nine taps of one resident-weights channel chunk, issued by one warp for its M-tiles m = issuer, issuer + n_iss, ...
+// NK = 16-channel MMA steps per tap.  Everything but the descriptor increments is hoisted: at N <= 96 the issuing
+// thread's instruction stream, not the tensor pipe, sets the MMA rate.
+template <int NK>
+__device__ __forceinline__ void halo_issue_taps(bool leader, uint32_t a_base, uint32_t b_lo, uint32_t b_step, uint32_t wp8,
+                                                uint32_t d8, uint32_t a_inc, uint32_t d_inc, uint32_t d0, uint32_t idesc,
+                                                int issuer, int NM, int n_iss) {
+  uint32_t a_row = a_base;
+#pragma unroll 1
+  for (int fr = 0; fr < 3; ++fr, a_row += wp8) {
+    uint32_t a_tap = a_row;
+#pragma unroll
+    for (int fs = 0; fs < 3; ++fs, a_tap += d8, b_lo += b_step) {
+      uint32_t a_lo = a_tap, dcol = d0;
+      for (int m = issuer; m < NM; m += n_iss, a_lo += a_inc, dcol += d_inc)
+        umma_ksteps<NK>(leader, dcol, a_lo, b_lo, idesc, (fr | fs) != 0);
+    }
+  }
+}
+
 template <typename TH>
 __global__ void __launch_bounds__(kHThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
@@ -172,6 +192,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         if (leader && issuer == 0) trace(p.trace, 1, it, 0);
         const uint32_t d_tmem = tmem_u + (uint32_t)(acc * acc_cols);
+        if (p.b_resident && p.cchunks == 1 && !p.trace) {
+          // Hot path (Cin <= 64, weights resident): the issuing thread's own instruction stream bounds the MMA rate
+          // at small N, so this loop carries nothing but the descriptor increments.
+          mbar_wait(fullA(sa), pa);
+          tc_fence_after();
+          const uint32_t a_base = sw128_desc_lo(smem_u32(smemA + (size_t)sa * p.a_stage_bytes)) + (uint32_t)issuer * 1024u;
+          const uint32_t b_step = p.b_tile_bytes >> 4;
+          const uint32_t wp8 = (uint32_t)(p.Wp * p.d) * 8u, d8 = (uint32_t)p.d * 8u;
+          const uint32_t a_inc = (uint32_t)p.n_iss * 1024u, d_inc = (uint32_t)(p.n_iss * p.acc_stride);
+          const uint32_t d0 = d_tmem + (uint32_t)(issuer * p.acc_stride);
+          const uint32_t b_lo0 = sw128_desc_lo(smem_u32(smemB));
+          switch (p.last_kk) {
+            case 1: halo_issue_taps<1>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
+            case 2: halo_issue_taps<2>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
+            case 3: halo_issue_taps<3>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
+            default: halo_issue_taps<4>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
+          }
+          if (leader) umma_commit(emptyA(sa));
+          if (++sa == p.sA) { sa = 0; pa ^= 1u; }
+        } else
         for (int cc = 0; cc < p.cchunks; ++cc) {
           mbar_wait(fullA(sa), pa);
           tc_fence_after();
