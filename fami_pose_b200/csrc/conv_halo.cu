@@ -270,7 +270,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t rb0 = smem_u32(stage_base) + (uint32_t)(kEpiWarps * 32 * ea.spitch);
     const uint32_t rbuf[2] = {rb0 + (uint32_t)((2 * (warp - kEpiWarp0)) * 32 * ea.spitch),
                               rb0 + (uint32_t)((2 * (warp - kEpiWarp0) + 1) * 32 * ea.spitch)};
-    const bool pf_on = p.res != nullptr && 3 * ea.spitch <= (128 + 16) && !(p.trace & 16);
+    // pipelined residual epilogue (16-column groups: staging pitch 48 B, three buffers per warp fit the allocation)
+    const bool pf_on = p.res != nullptr && ea.spitch == epi_pipe_pitch(16) && col_end - col_begin == 16 &&
+                       epi_pipe_ok(p.BN, p.Cout, p.vec_ok, p.out_f32, 1, true) && p.Cout == p.BN * p.n_tiles && !(p.trace & 16);
     int pf_have = 0, pf_sel = 0;
     ea.s_scale = smem_u32(s_scale); ea.s_shift = smem_u32(s_shift); ea.res = p.res; ea.y = p.y;
     ea.Cout = p.Cout; ea.BN = p.BN; ea.out_pitch = p.out_pitch; ea.res_pitch = p.res_pitch;
@@ -303,14 +305,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int m = 0; m < p.NM; ++m) {
         bool valid;
         const int pix = row_pix(m, valid);
-        int ready = pf_have;            // was the residual of (tile, m) prefetched?
-        pf_have = 0;
+        const uint32_t t_addr = tmem_base + (uint32_t)(acc * acc_cols + m * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
         if (pf_on) {
-          // next unit of this warp
-          bool nvalid = false;
-          int npix = 0;
-          bool have_next = true;
-          const int save_chb = ea.ch_base;
+          // next unit of this warp: the next M-tile, or the first M-tile of this CTA's next tile
+          bool nvalid = false, have_next = true;
+          int npix = 0, nchb = ea.ch_base;
           if (m + 1 < p.NM) {
             npix = row_pix(m + 1, nvalid);
           } else if (tile + (int)gridDim.x < p.total_tiles) {
@@ -322,19 +321,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int yy = row / p.Wp, xx = row - yy * p.Wp;
             nvalid = (yy < p.BH) && (xx < p.W) && (ny0 + yy < p.H);
             npix = nvalid ? (nimg * p.H + (ny0 + yy)) * p.W + xx : 0;
-            ea.ch_base = nnt * p.BN;
+            nchb = nnt * p.BN;
           } else {
             have_next = false;
           }
-          if (have_next) {
-            pf_have = epi_prefetch_async<TH>(ea, col_begin, col_end, nvalid, npix, rbuf[pf_sel ^ 1], lane) ? 1 : 0;
-            ea.ch_base = save_chb;
-          }
-          if (ready && pf_have) ready = 2;   // one newer cp.async group is in flight behind the one we need
+          if (!(p.trace & 2))
+            epilogue_rows_pipelined<TH>(ea, t_addr, col_begin, col_end, valid, pix, stage, rbuf[0], rbuf[1], lane, pf_sel, pf_have,
+                                        have_next, nvalid, npix, nchb, 16);
+        } else if (!(p.trace & 2)) {
+          epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix, stage, lane, false, no_pre);
         }
-        const uint32_t t_addr = tmem_base + (uint32_t)(acc * acc_cols + m * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
-        if (!(p.trace & 2)) epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix, stage, lane, false, no_pre, rbuf[pf_sel], ready);
-        pf_sel ^= 1;
       }
       tc_fence_before();
       __syncwarp();

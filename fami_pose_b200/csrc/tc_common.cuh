@@ -531,17 +531,17 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
 // unit of a warp pays the global-load latency.  `sel` (buffer parity) and `primed` (the first group of this call has
 // been prefetched by the previous call) carry the state across calls.
 constexpr int kPipeCols = 32;
-__host__ __device__ inline int epi_pipe_pitch() { return kPipeCols * 2 + 16; }
+__host__ __device__ inline int epi_pipe_pitch(int gcols = kPipeCols) { return gcols * 2 + 16; }
 __host__ __device__ inline bool epi_pipe_ok(int BN, int Cout_total, int vec_ok, int out_f32, int up, bool has_res) {
   return has_res && up == 1 && !out_f32 && vec_ok && (Cout_total % 16 == 0) && BN % 16 == 0;
 }
 template <typename TH>
-__device__ __forceinline__ void epi_pipe_fetch(const EpiArgs& a, int chg, int gc, unsigned vmask, int pix, uint32_t buf, int lane) {
+__device__ __forceinline__ void epi_pipe_fetch(const EpiArgs& a, int chg, int gc, unsigned vmask, int pix, uint32_t buf, int lane,
+                                               int pitch) {
   const int ppr = (gc * 2) >> 4;                 // 16-byte pieces per row: 2 or 4
   const int lg = ppr <= 2 ? 1 : 2;
   const int lpr = 1 << lg, rpi = 32 >> lg;
   const int sub_r = lane >> lg, sub_c = lane & (lpr - 1);
-  const int pitch = epi_pipe_pitch();
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     if (it < lpr) {
@@ -559,29 +559,29 @@ template <typename TH>
 __device__ __forceinline__ void epilogue_rows_pipelined(const EpiArgs& a, uint32_t t_addr, int col_begin, int col_end, bool valid,
                                                         int pix0, uint32_t stage, uint32_t rb0, uint32_t rb1, int lane, int& sel,
                                                         int& primed, bool have_next, bool next_valid, int next_pix,
-                                                        int next_ch_base) {
+                                                        int next_ch_base, int gcols = kPipeCols) {
   if (col_begin >= col_end) return;   // warp-uniform
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
   const unsigned nmask = __ballot_sync(0xffffffffu, next_valid);
-  const int pitch = epi_pipe_pitch();
+  const int pitch = epi_pipe_pitch(gcols);
   const uint32_t my_row = stage + (uint32_t)(lane * pitch);
   if (!primed) {   // very first unit of this warp: nobody prefetched it
-    const int gc0 = (col_end - col_begin < kPipeCols) ? (col_end - col_begin) : kPipeCols;
-    epi_pipe_fetch<TH>(a, a.ch_base + col_begin, gc0, vmask, pix0, sel ? rb1 : rb0, lane);
+    const int gc0 = (col_end - col_begin < gcols) ? (col_end - col_begin) : gcols;
+    epi_pipe_fetch<TH>(a, a.ch_base + col_begin, gc0, vmask, pix0, sel ? rb1 : rb0, lane, pitch);
   }
-  for (int g0 = col_begin; g0 < col_end; g0 += kPipeCols) {
-    const int gc = (col_end - g0 < kPipeCols) ? (col_end - g0) : kPipeCols;
+  for (int g0 = col_begin; g0 < col_end; g0 += gcols) {
+    const int gc = (col_end - g0 < gcols) ? (col_end - g0) : gcols;
     const int chg = a.ch_base + g0;
     const uint32_t cur = sel ? rb1 : rb0, nxt = sel ? rb0 : rb1;
     // next unit in flight
     bool pending = false;
-    if (g0 + kPipeCols < col_end) {
-      const int ngc = (col_end - (g0 + kPipeCols) < kPipeCols) ? (col_end - (g0 + kPipeCols)) : kPipeCols;
-      epi_pipe_fetch<TH>(a, chg + kPipeCols, ngc, vmask, pix0, nxt, lane);
+    if (g0 + gcols < col_end) {
+      const int ngc = (col_end - (g0 + gcols) < gcols) ? (col_end - (g0 + gcols)) : gcols;
+      epi_pipe_fetch<TH>(a, chg + gcols, ngc, vmask, pix0, nxt, lane, pitch);
       pending = true;
     } else if (have_next) {
-      const int ngc = (col_end - col_begin < kPipeCols) ? (col_end - col_begin) : kPipeCols;
-      epi_pipe_fetch<TH>(a, next_ch_base + col_begin, ngc, nmask, next_pix, nxt, lane);
+      const int ngc = (col_end - col_begin < gcols) ? (col_end - col_begin) : gcols;
+      epi_pipe_fetch<TH>(a, next_ch_base + col_begin, ngc, nmask, next_pix, nxt, lane, pitch);
       pending = true;
     }
     if (pending) asm volatile("cp.async.wait_group 1;" ::: "memory");
