@@ -273,6 +273,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // pipelined residual epilogue (16-column groups: staging pitch 48 B, three buffers per warp fit the allocation)
     const bool pf_on = p.res != nullptr && ea.spitch == epi_pipe_pitch(16) && col_end - col_begin == 16 &&
                        epi_pipe_ok(p.BN, p.Cout, p.vec_ok, p.out_f32, 1, true) && p.Cout == p.BN * p.n_tiles && !(p.trace & 16);
+    const bool lean_nores = p.res == nullptr && ea.spitch == epi_pipe_pitch(16) && col_end - col_begin == 16 &&
+                            epi_pipe_ok(p.BN, p.Cout, p.vec_ok, p.out_f32, 1, false) && p.Cout == p.BN * p.n_tiles;
     int pf_have = 0, pf_sel = 0;
     ea.s_scale = smem_u32(s_scale); ea.s_shift = smem_u32(s_shift); ea.res = p.res; ea.y = p.y;
     ea.Cout = p.Cout; ea.BN = p.BN; ea.out_pitch = p.out_pitch; ea.res_pitch = p.res_pitch;
@@ -328,6 +330,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!(p.trace & 2))
             epilogue_rows_pipelined<TH>(ea, t_addr, col_begin, col_end, valid, pix, stage, rbuf[0], rbuf[1], lane, pf_sel, pf_have,
                                         have_next, nvalid, npix, nchb, 16);
+        } else if (lean_nores) {
+          if (!(p.trace & 2))
+            epilogue_rows_pipelined<TH, false>(ea, t_addr, col_begin, col_end, valid, pix, stage, 0u, 0u, lane, pf_sel, pf_have, false,
+                                               false, 0, 0, 16);
         } else if (!(p.trace & 2)) {
           epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix, stage, lane, false, no_pre);
         }

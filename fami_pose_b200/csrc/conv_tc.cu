@@ -170,7 +170,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int up_fast = (p.up > 1 && p.res != nullptr && 3 * ea.spitch <= (128 + 16)) ? -1 : 0;
     // pipelined residual epilogue: staging + two residual buffers per warp at the 32-column pitch
     const uint32_t pp = (uint32_t)epi_pipe_pitch();
-    const uint32_t pstage = smem_u32(stage_base) + (uint32_t)(warp - 2) * 96u * pp;
+    const uint32_t pstage = smem_u32(stage_base) + (uint32_t)(warp - 2) * (p.res ? 96u : 32u) * pp;
     int psel = 0, pprimed = 0;
     ea.s_scale = smem_u32(s_scale); ea.s_shift = smem_u32(s_shift); ea.res = p.res; ea.y = p.y;
     ea.Cout = p.Cout; ea.BN = p.BN; ea.out_pitch = p.out_pitch; ea.res_pitch = p.res_pitch;
@@ -204,8 +204,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nmt = ntile / p.n_tiles, nnt = ntile - nmt * p.n_tiles;
         const int nm = nmt * kBM + row;
         const bool nvalid = have_next && nm < p.M;
-        epilogue_rows_pipelined<TH>(ea, t_addr, col_begin, col_end, valid, pix0, pstage, pstage + 32u * pp, pstage + 64u * pp, lane,
-                                    psel, pprimed, have_next, nvalid, nvalid ? nm : 0, nnt * p.BN);
+        if (p.res)
+          epilogue_rows_pipelined<TH, true>(ea, t_addr, col_begin, col_end, valid, pix0, pstage, pstage + 32u * pp, pstage + 64u * pp,
+                                            lane, psel, pprimed, have_next, nvalid, nvalid ? nm : 0, nnt * p.BN);
+        else
+          epilogue_rows_pipelined<TH, false>(ea, t_addr, col_begin, col_end, valid, pix0, pstage, 0u, 0u, lane, psel, pprimed, false,
+                                             false, 0, 0);
       } else {
         epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix0, stage, lane, have_pre, pre, rbuf, up_fast);
       }
@@ -335,7 +339,7 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   const int stage_bytes = kABytes + t.BN * 128;
   p.pipe = (epi_pipe_ok(t.BN, d->Cout, p.vec_ok, out_f32, d->up, res != nullptr) && d->Cout == t.BN * t.n_tiles &&
             getenv("FAMI_NO_EPI_PIPE") == nullptr) ? 1 : 0;
-  const size_t epi_bytes = p.pipe ? (size_t)kEpiWarps * 32 * 3 * epi_pipe_pitch() : (size_t)kEpiWarps * 32 * (128 + 16);
+  const size_t epi_bytes = p.pipe ? (size_t)kEpiWarps * 32 * (res ? 3 : 1) * epi_pipe_pitch() : (size_t)kEpiWarps * 32 * (128 + 16);
   int stages = (int)((228000 - (size_t)t.CoutPad * 8 - epi_bytes) / stage_bytes);   // all the shared memory there is: the kernel is bound by bytes in flight
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;

@@ -533,7 +533,8 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
 constexpr int kPipeCols = 32;
 __host__ __device__ inline int epi_pipe_pitch(int gcols = kPipeCols) { return gcols * 2 + 16; }
 __host__ __device__ inline bool epi_pipe_ok(int BN, int Cout_total, int vec_ok, int out_f32, int up, bool has_res) {
-  return has_res && up == 1 && !out_f32 && vec_ok && (Cout_total % 16 == 0) && BN % 16 == 0;
+  (void)has_res;   // with and without residual (kRes)
+  return up == 1 && !out_f32 && vec_ok && (Cout_total % 16 == 0) && BN % 16 == 0;
 }
 template <typename TH>
 __device__ __forceinline__ void epi_pipe_fetch(const EpiArgs& a, int chg, int gc, unsigned vmask, int pix, uint32_t buf, int lane,
@@ -555,7 +556,7 @@ __device__ __forceinline__ void epi_pipe_fetch(const EpiArgs& a, int chg, int gc
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
-template <typename TH>
+template <typename TH, bool kRes = true>
 __device__ __forceinline__ void epilogue_rows_pipelined(const EpiArgs& a, uint32_t t_addr, int col_begin, int col_end, bool valid,
                                                         int pix0, uint32_t stage, uint32_t rb0, uint32_t rb1, int lane, int& sel,
                                                         int& primed, bool have_next, bool next_valid, int next_pix,
@@ -565,7 +566,7 @@ __device__ __forceinline__ void epilogue_rows_pipelined(const EpiArgs& a, uint32
   const unsigned nmask = __ballot_sync(0xffffffffu, next_valid);
   const int pitch = epi_pipe_pitch(gcols);
   const uint32_t my_row = stage + (uint32_t)(lane * pitch);
-  if (!primed) {   // very first unit of this warp: nobody prefetched it
+  if (kRes && !primed) {   // very first unit of this warp: nobody prefetched it
     const int gc0 = (col_end - col_begin < gcols) ? (col_end - col_begin) : gcols;
     epi_pipe_fetch<TH>(a, a.ch_base + col_begin, gc0, vmask, pix0, sel ? rb1 : rb0, lane, pitch);
   }
@@ -575,7 +576,9 @@ __device__ __forceinline__ void epilogue_rows_pipelined(const EpiArgs& a, uint32
     const uint32_t cur = sel ? rb1 : rb0, nxt = sel ? rb0 : rb1;
     // next unit in flight
     bool pending = false;
-    if (g0 + gcols < col_end) {
+    if (!kRes) {
+      // no residual: nothing to fetch
+    } else if (g0 + gcols < col_end) {
       const int ngc = (col_end - (g0 + gcols) < gcols) ? (col_end - (g0 + gcols)) : gcols;
       epi_pipe_fetch<TH>(a, chg + gcols, ngc, vmask, pix0, nxt, lane, pitch);
       pending = true;
@@ -584,9 +587,11 @@ __device__ __forceinline__ void epilogue_rows_pipelined(const EpiArgs& a, uint32
       epi_pipe_fetch<TH>(a, next_ch_base + col_begin, ngc, nmask, next_pix, nxt, lane, pitch);
       pending = true;
     }
-    if (pending) asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
+    if (kRes) {
+      if (pending) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+    }
     const uint32_t res_row = cur + (uint32_t)(lane * pitch);
     for (int c0 = 0; c0 < gc; c0 += 16) {
       uint32_t v[16];
@@ -603,14 +608,20 @@ __device__ __forceinline__ void epilogue_rows_pipelined(const EpiArgs& a, uint32
         o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
         o[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
       }
-      const uint4 r0 = lds128(res_row + (uint32_t)(c0 * 2));
-      const uint4 r1 = lds128(res_row + (uint32_t)(c0 * 2 + 16));
-      const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      uint32_t rw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      if (kRes) {
+        const uint4 r0 = lds128(res_row + (uint32_t)(c0 * 2));
+        const uint4 r1 = lds128(res_row + (uint32_t)(c0 * 2 + 16));
+        rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w; rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
+      }
       uint32_t w[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float2 t = h2_to_f2<TH>(rw[j]);
-        float x0 = o[2 * j] + t.x, x1 = o[2 * j + 1] + t.y;
+        float x0 = o[2 * j], x1 = o[2 * j + 1];
+        if (kRes) {
+          const float2 t = h2_to_f2<TH>(rw[j]);
+          x0 += t.x; x1 += t.y;
+        }
         if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
         w[j] = f2_to_h2<TH>(x0, x1);
       }
