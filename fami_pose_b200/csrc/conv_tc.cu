@@ -193,8 +193,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       ea.ch_base = nt * p.BN;
-      uint4 pre[kPre];
-      const bool have_pre = false;   // register prefetch of the residual measured slower (register pressure)
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)(quarter * 32) << 16);
@@ -211,7 +209,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           epilogue_rows_pipelined<TH, false>(ea, t_addr, col_begin, col_end, valid, pix0, pstage, 0u, 0u, lane, psel, pprimed, false,
                                              false, 0, 0);
       } else {
-        epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix0, stage, lane, have_pre, pre, rbuf, up_fast);
+        epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix0, stage, lane, rbuf, up_fast);
       }
       tc_fence_before();
       __syncwarp();

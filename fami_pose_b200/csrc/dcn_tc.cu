@@ -366,7 +366,6 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     ea.out_f32 = 0; ea.relu = 0; ea.vec_ok = p.vec_ok; ea.up = 1; ea.Wout = p.W;
     ea.spitch = 128 + 16;
     const uint32_t stage = smem_u32(stage_base) + (uint32_t)((warp - kGatherWarps - 1) * 32 * ea.spitch);
-    uint4 no_pre[kPre];
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -379,7 +378,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       mbar_wait(tfull(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(quarter * 32) << 16);
-      epilogue_rows<TH>(ea, t_addr, 0, p.BN, valid, pix, stage, lane, false, no_pre);
+      epilogue_rows<TH>(ea, t_addr, 0, p.BN, valid, pix, stage, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(acc));

@@ -243,39 +243,6 @@ struct EpiArgs {
 
 // One warp drains columns [col_begin, col_end) of its 32 accumulator rows.  pix0 = pixel index of this
 // lane's row (first replica); valid = row maps to a real output pixel.
-// Residual prefetch for the FIRST column group of a warp's range (replica 0): issues the coalesced
-// 16-byte loads into registers so their latency overlaps whatever the caller does next (waiting for
-// the accumulator, draining the previous M-tile).  Returns false if this (range, args) combination
-// does not use the vector path -- epilogue_rows then loads the residual itself.
-constexpr int kPre = 4;   // prefetch registers (uint4) per lane: column ranges up to 32 x 16-bit columns
-template <typename TH>
-__device__ __forceinline__ bool epi_prefetch(const EpiArgs& a, int col_begin, int col_end, bool valid, int pix0, int lane,
-                                             uint4 (&rreg)[kPre]) {
-  if (col_begin >= col_end || !a.res) return false;
-  const int gmax = a.out_f32 ? 32 : 64;
-  const int gc = (col_end - col_begin < gmax) ? (col_end - col_begin) : gmax;
-  const int chg = a.ch_base + col_begin;
-  if (!(a.vec_ok && (chg + gc <= a.Cout) && !a.out_f32)) return false;
-  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-  const int ppr = (gc * 2) >> 4;
-  const int lg = ppr <= 2 ? 1 : (ppr <= 4 ? 2 : 3);
-  const int lpr = 1 << lg, rpi = 32 >> lg;
-  if (lpr > kPre) return false;   // wide ranges: no register prefetch
-  const int sub_r = lane >> lg, sub_c = lane & (lpr - 1);
-  const bool lane_on = sub_c < ppr;
-#pragma unroll
-  for (int it = 0; it < kPre; ++it) {
-    if (it < lpr) {
-      const int r = it * rpi + sub_r;
-      const int pr = __shfl_sync(0xffffffffu, pix0, r);
-      rreg[it] = make_uint4(0, 0, 0, 0);
-      if (lane_on && ((vmask >> r) & 1u))
-        rreg[it] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const TH*>(a.res) + (int64_t)pr * a.res_pitch + chg) + sub_c);
-    }
-  }
-  return true;
-}
-
 // Asynchronous residual prefetch (cp.async, no registers held): the residual of the FIRST column group of a
 // FUTURE epilogue_rows call is copied into the per-warp shared-memory buffer `rbuf` (same row pitch as the
 // staging buffer) and committed as one cp.async group.  Returns false (warp-uniform) if that call will not use
@@ -311,8 +278,7 @@ __device__ __forceinline__ bool epi_prefetch_async(const EpiArgs& a, int col_beg
 
 template <typename TH>
 __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr, int col_begin, int col_end, bool valid,
-                                              int pix0, uint32_t stage, int lane, bool have_pre, uint4 (&pre)[kPre],
-                                              uint32_t rbuf = 0, int r_ready = 0) {
+                                              int pix0, uint32_t stage, int lane, uint32_t rbuf = 0, int r_ready = 0) {
   // r_ready: 0 = load the residual here; 1 / 2 = the residual of the first column group was prefetched into
   // `rbuf` by epi_prefetch_async and is the last (1) / second-to-last (2) cp.async group this thread committed
   if (col_begin >= col_end) return;   // warp-uniform
@@ -424,24 +390,21 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
           res_row = rbuf + (uint32_t)(lane * a.spitch);
         } else if (a.res && grp_vec) {
           uint4 rreg[8];
-          const bool use_pre = have_pre && g0 == col_begin && dy == 0 && dx == 0;   // warp-uniform
-          if (!use_pre) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              if (it < lpr) {
-                const int r = it * rpi + sub_r;
-                const int pr = __shfl_sync(0xffffffffu, pix, r);
-                rreg[it] = make_uint4(0, 0, 0, 0);
-                if (lane_on && ((vmask >> r) & 1u))
-                  rreg[it] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const TH*>(a.res) + (int64_t)pr * a.res_pitch + chg) + sub_c);
-              }
+          for (int it = 0; it < 8; ++it) {
+            if (it < lpr) {
+              const int r = it * rpi + sub_r;
+              const int pr = __shfl_sync(0xffffffffu, pix, r);
+              rreg[it] = make_uint4(0, 0, 0, 0);
+              if (lane_on && ((vmask >> r) & 1u))
+                rreg[it] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const TH*>(a.res) + (int64_t)pr * a.res_pitch + chg) + sub_c);
             }
           }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             if (it < lpr) {
               const int r = it * rpi + sub_r;
-              if (lane_on) sts128(stage + (uint32_t)(r * a.spitch + sub_c * 16), (use_pre && it < kPre) ? pre[it < kPre ? it : 0] : rreg[it]);
+              if (lane_on) sts128(stage + (uint32_t)(r * a.spitch + sub_c * 16), rreg[it]);
             }
           }
           __syncwarp();
