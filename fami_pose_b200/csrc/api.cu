@@ -298,9 +298,9 @@ static int check_dcn(const fami_dcn_desc* d, const char* who) {
   FAMI_CHECK_ARG((d->C / d->G) % 4 == 0 && d->C % 16 == 0,
                  "%s: channels per offset group must be a multiple of 4 and C a multiple of 16 (C=%d G=%d)", who,
                  d->C, d->G);
-  FAMI_CHECK_ARG(d->om_layout == 0 || d->om_layout == 1, "%s: bad om_layout %d", who, d->om_layout);
+  FAMI_CHECK_ARG(d->om_layout >= 0 && d->om_layout <= 2, "%s: bad om_layout %d", who, d->om_layout);
   FAMI_CHECK_ARG(d->x_pitch >= d->C && d->out_pitch >= d->Cout, "%s: pitch too small", who);
-  FAMI_CHECK_ARG(d->om_layout == 1 ? d->off_pitch >= 27 * d->G : (d->off_pitch >= 18 * d->G && d->mask_pitch >= 9 * d->G),
+  FAMI_CHECK_ARG(d->om_layout == 2 || (d->om_layout == 1 ? d->off_pitch >= 27 * d->G : (d->off_pitch >= 18 * d->G && d->mask_pitch >= 9 * d->G)),
                  "%s: offset/mask pitch too small", who);
   FAMI_CHECK_ARG((int64_t)d->B * d->H * d->W < (1ll << 31), "%s: too many pixels", who);
   return 0;
@@ -309,9 +309,9 @@ static int check_dcn(const fami_dcn_desc* d, const char* who) {
 int fami_dcn_fwd(const fami_dcn_desc* d, const void* x, const void* offset, const void* mask, const void* w_packed,
                  const float* bias, void* out, void* stream) {
   if (int e = check_dcn(d, "fami_dcn_fwd")) return e;
-  FAMI_CHECK_ARG(x && offset && (mask || d->om_layout == 1) && w_packed && out, "fami_dcn_fwd: null pointer");
+  FAMI_CHECK_ARG(x && offset && (mask || d->om_layout >= 1) && w_packed && out, "fami_dcn_fwd: null pointer");
   FAMI_CHECK_ARG(valid_dtype(d->dtype), "fami_dcn_fwd: bad dtype %d", d->dtype);
-  if (d->om_layout == 1) {
+  if (d->om_layout >= 1) {
     FAMI_CHECK_ARG(dcn_tc_supported(d), "fami_dcn_fwd: fused tap-major offsets need the 16-bit tensor-core kernel "
                                         "(C <= 64, 4 channels per offset group, 3x3, pad == dil)");
     return dcn_tc_launch(d, x, (const float*)offset, w_packed, bias, out, (cudaStream_t)stream);

@@ -49,6 +49,8 @@ struct DcnTcParams {
   int tiles_x, tiles_y, total_tiles;
   int nk, BN;
   int om_pitch, x_pitch, out_pitch, vec_ok;
+  int om_blocked;                   // 1: offsets|masks in the warp-blocked layout (om_layout 2)
+  int64_t om_tap_stride;            // floats between taps in the blocked layout = nblk * (3G/4) * 128
   uint32_t win_bytes, w_tile_bytes, ab_format;
   int trace;
   const float* om;                  // [B*H*W][om_pitch], per pixel [9 taps][dy(G) | dx(G) | mask(G)]
@@ -162,12 +164,27 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       if (threadIdx.x == 0) dtrace(p.trace, git, 0);
       const int y = y0 + ry, x = x0 + rx;
       const bool valid = y < p.H && x < p.W;
-      const float* po = p.om + ((int64_t)(b * p.H + y) * p.W + x) * p.om_pitch;
+      // tap-major NHWC (om_layout 1): the 3*kG floats of a (pixel, tap) are one contiguous run, but the 32 lanes of a
+      // warp are 1296 B apart, so every 16-byte load instruction touches 32 cache lines.  Warp-blocked (om_layout 2):
+      // [tap][tile*4 + warp quarter][q < 3kG/4][lane][4 floats] -- each load instruction reads 512 contiguous bytes.
+      const float* po = p.om_blocked
+                            ? p.om + ((int64_t)tile * 4 + (r >> 5)) * (3 * kQ * 128) + lane * 4
+                            : p.om + ((int64_t)(b * p.H + y) * p.W + x) * p.om_pitch;
       float4 vdy[kQ], vdx[kQ], vmk[kQ];
       auto load_unit = [&](int tap) {
-        const float4* o = reinterpret_cast<const float4*>(po + tap * 3 * kG);
+        if (p.om_blocked) {
+          const float* o = po + tap * p.om_tap_stride;
 #pragma unroll
-        for (int i = 0; i < kQ; ++i) { vdy[i] = __ldg(o + i); vdx[i] = __ldg(o + kQ + i); vmk[i] = __ldg(o + 2 * kQ + i); }
+          for (int i = 0; i < kQ; ++i) {
+            vdy[i] = __ldg(reinterpret_cast<const float4*>(o + i * 128));
+            vdx[i] = __ldg(reinterpret_cast<const float4*>(o + (kQ + i) * 128));
+            vmk[i] = __ldg(reinterpret_cast<const float4*>(o + (2 * kQ + i) * 128));
+          }
+        } else {
+          const float4* o = reinterpret_cast<const float4*>(po + tap * 3 * kG);
+#pragma unroll
+          for (int i = 0; i < kQ; ++i) { vdy[i] = __ldg(o + i); vdx[i] = __ldg(o + kQ + i); vmk[i] = __ldg(o + 2 * kQ + i); }
+        }
       };
       if (valid) load_unit(q);
       mbar_wait(win_full, wph);
@@ -237,8 +254,16 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           while (slow) {
             const int g = __ffs((int)slow) - 1;
             slow &= slow - 1u;
-            const float* o = po + tap * 3 * kG + g;
-            const float dy = __ldg(o), dx = __ldg(o + kG), mk = __ldg(o + 2 * kG);
+            float dy, dx, mk;
+            if (p.om_blocked) {
+              const float* o = po + tap * p.om_tap_stride;
+              dy = __ldg(o + (g >> 2) * 128 + (g & 3));
+              dx = __ldg(o + ((kG + g) >> 2) * 128 + ((kG + g) & 3));
+              mk = __ldg(o + ((2 * kG + g) >> 2) * 128 + ((2 * kG + g) & 3));
+            } else {
+              const float* o = po + tap * 3 * kG + g;
+              dy = __ldg(o); dx = __ldg(o + kG); mk = __ldg(o + 2 * kG);
+            }
             const float py = (float)(y - p.d + k * p.d) + dy;
             const float px = (float)(x - p.d + q * p.d) + dx;
             uint2 pk2 = make_uint2(0u, 0u);
@@ -294,6 +319,16 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     // pull a tile's offsets|masks (16 row segments of 8 pixels x 27G floats, the dominant HBM stream) into
     // L2 one tile ahead, so the gather warps' dependent loads see L2 rather than HBM latency
     auto prefetch_om = [&](int b, int y0, int x0) {
+      if (p.om_blocked) {
+        // 9 taps x (4 blocks x 3G/4 x 512 B) contiguous per tile
+        const int tile_id = (b * p.tiles_y + y0 / kTH) * p.tiles_x + x0 / kTW;
+        const uint32_t bytes = (uint32_t)(4 * 3 * (p.G / 4) * 512);
+        if (lane < 9) {
+          const float* ptr = p.om + (int64_t)lane * p.om_tap_stride + (int64_t)tile_id * (bytes / 4);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+        }
+        return;
+      }
       const int row = lane >> 1, half = lane & 1;          // 32 lanes: 16 rows x 2 halves of the 8-pixel segment
       const int y = y0 + row, x = x0 + half * 4;
       if (y < p.H && x < p.W) {
@@ -409,9 +444,9 @@ static int dcn_tc_radius(const fami_dcn_desc* d) {
 }
 
 int dcn_tc_supported(const fami_dcn_desc* d) {
-  if (!is_half_dtype(d->dtype) || d->om_layout != 1) return 0;
+  if (!is_half_dtype(d->dtype) || (d->om_layout != 1 && d->om_layout != 2)) return 0;
   if (d->C % 16 != 0 || d->C > 64 || d->G * 4 != d->C) return 0;      // G in {4, 8, 12, 16}
-  if (d->off_pitch % 4 != 0) return 0;                                  // 16-byte loads of the (dy|dx|mask) runs
+  if (d->om_layout == 1 && d->off_pitch % 4 != 0) return 0;             // 16-byte loads of the (dy|dx|mask) runs
   if (d->Cout > 256 || d->x_pitch % 8 != 0) return 0;
   if (d->kh != 3 || d->kw != 3 || d->pad != d->dil || d->dil > 4) return 0;
   if (dcn_tc_radius(d) < 0) return 0;                                   // filter + window do not fit in shared memory
@@ -440,6 +475,8 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
   p.w_tile_bytes = (uint32_t)p.BN * 128u;
   p.ab_format = d->dtype == FAMI_F16 ? 0u : 1u;
   p.om = om; p.x = x; p.bias = bias; p.out = out;
+  p.om_blocked = d->om_layout == 2;
+  p.om_tap_stride = (int64_t)p.total_tiles * 4 * (3 * (d->G / 4)) * 128;
   static const bool trace_on = getenv("FAMI_DCN_TRACE") != nullptr;
   p.trace = trace_on ? atoi(getenv("FAMI_DCN_TRACE")) : 0;
 

@@ -317,7 +317,34 @@ def tap_major_perm(G, k=3):
     return perm
 
 
-def dcn_fwd(x, offset, mask, weight, bias, owner, pad=3, dil=3, out=None, fused_om=None):
+DCN_TILE_H, DCN_TILE_W = 16, 8      # pixel tile of the tensor-core DCN kernel (csrc/dcn_tc.cu)
+
+
+def om_blocked_numel(B, H, W, G, k=3):
+    """Elements of the warp-blocked offset|mask buffer (fami_dcn_desc.om_layout = 2)."""
+    ty, tx = (H + DCN_TILE_H - 1) // DCN_TILE_H, (W + DCN_TILE_W - 1) // DCN_TILE_W
+    return k * k * B * ty * tx * 4 * (3 * G // 4) * 128
+
+
+def om_to_blocked(om, G, k=3):
+    """tap-major NHWC [B, 27G, H, W] (tap_major_perm order) -> warp-blocked layout
+    [tap][image tile * 4 + warp quarter][q < 3G/4][lane < 32][4 floats]: the 32 pixels of a 4-row x 8-column
+    quarter of a 16x8 tile are the 32 lanes, so one 16-byte load per lane reads 512 contiguous bytes.
+    Host-side converter for tests and tools; in the model the producer convolution writes this layout directly."""
+    B, FC, H, W = om.shape
+    K, Q = k * k, 3 * G // 4
+    ty, tx = (H + DCN_TILE_H - 1) // DCN_TILE_H, (W + DCN_TILE_W - 1) // DCN_TILE_W
+    t = om.permute(0, 2, 3, 1).reshape(B, H, W, K, Q, 4).float()
+    if ty * DCN_TILE_H != H or tx * DCN_TILE_W != W:
+        pad = torch.zeros((B, ty * DCN_TILE_H, tx * DCN_TILE_W, K, Q, 4), dtype=torch.float32, device=om.device)
+        pad[:, :H, :W] = t
+        t = pad
+    t = t.reshape(B, ty, DCN_TILE_H, tx, DCN_TILE_W, K, Q, 4).permute(5, 0, 1, 3, 2, 4, 6, 7)   # K,B,ty,tx,yy,xx,Q,4
+    t = t.reshape(K, B, ty, tx, 4, 32, Q, 4).permute(0, 1, 2, 3, 4, 6, 5, 7)                     # K,B,ty,tx,w,Q,lane,4
+    return t.contiguous().reshape(-1)
+
+
+def dcn_fwd(x, offset, mask, weight, bias, owner, pad=3, dil=3, out=None, fused_om=None, blocked_om=None, groups=None):
     """torchvision.ops.deform_conv2d(x, offset, weight, bias, stride=1, padding=pad, dilation=dil, mask=mask)
     on NHWC operands (Alignment_V15.py:146,150,154,158).  fused_om: ONE float32 buffer [B, 27G, H, W]
     in tap-major layout (see tap_major_perm) instead of (offset, mask) -- the 16-bit tensor-core kernel."""
@@ -328,6 +355,16 @@ def dcn_fwd(x, offset, mask, weight, bias, owner, pad=3, dil=3, out=None, fused_
         out = empty_nhwc(B, Cout, H, W, x.dtype, x.device)
     outp = meta(out)[4]
     b = bias.detach().float() if bias is not None else None
+    if blocked_om is not None:
+        G = groups
+        if Cin != C or not dcn_fused_supported(C, G, x.dtype) or blocked_om.dtype != torch.float32 \
+                or blocked_om.numel() != om_blocked_numel(B, H, W, G, kh):
+            raise ValueError("warp-blocked DCN offsets need 16-bit x, C <= 64, 4 channels per offset group and a "
+                             "float32 buffer of om_blocked_numel elements")
+        w = packed_weight(owner, weight, x.dtype)
+        d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, 0, 0, outp, 2, _code(x.dtype))
+        _lib.call("fami_dcn_fwd", ctypes.byref(d), _ptr(x), _ptr(blocked_om), None, _ptr(w), _ptr(b), _ptr(out), _stream())
+        return out
     if fused_om is not None:
         fB, FC, fH, fW, fp_ = meta(fused_om)
         if FC % (3 * kh * kw) != 0 or (fB, fH, fW) != (B, H, W) or fused_om.dtype != torch.float32:

@@ -13,13 +13,19 @@ out = ops.empty_nhwc(B, C, H, W, torch.float16, "cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for sigma in (0.5, 2.0, 4.0):
     om = ops.empty_nhwc(B, 27 * G, H, W, torch.float32, "cuda").normal_() * sigma
+    blk = ops.om_to_blocked(om, G) if os.environ.get("BLOCKED") else None
+    run = (lambda: dcn(x, None, None, out=out, blocked_om=blk, groups=G)) if blk is not None else (lambda: dcn(x, None, None, out=out, fused_om=om))
+    if blk is not None:
+        ref = ops.empty_nhwc(B, C, H, W, torch.float16, "cuda")
+        dcn(x, None, None, out=ref, fused_om=om); run()
+        print("blocked vs tap-major max diff", float((ref.float() - out.float()).abs().max()))
     for _ in range(3):
-        dcn(x, None, None, out=out, fused_om=om)
+        run()
     ts = []
     for _ in range(10):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); dcn(x, None, None, out=out, fused_om=om); e1.record()
+        e0.record(); run(); e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
     ts.sort()
