@@ -19,7 +19,7 @@ F16 = 2
 class ConvDesc(Structure):
     _fields_ = [(n, c_int32) for n in (
         "N", "H", "W", "Cin", "Cout", "kh", "kw", "stride", "pad", "dil", "Ho", "Wo", "up", "relu",
-        "in_pitch", "out_pitch", "res_pitch", "dtype", "out_dtype", "stats")]
+        "in_pitch", "out_pitch", "res_pitch", "dtype", "out_dtype", "stats", "om_groups")]
 
 
 class DcnDesc(Structure):

@@ -150,7 +150,7 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
   FAMI_CHECK_ARG(Ho == d->Ho && Wo == d->Wo, "fami_conv2d_bn_act_fwd: Ho/Wo (%d,%d) inconsistent, expected (%d,%d)",
                  d->Ho, d->Wo, Ho, Wo);
   FAMI_CHECK_ARG(d->up == 1 || d->up == 2 || d->up == 4 || d->up == 8, "fami_conv2d_bn_act_fwd: up=%d", d->up);
-  FAMI_CHECK_ARG(d->in_pitch >= d->Cin && d->out_pitch >= d->Cout, "fami_conv2d_bn_act_fwd: pitch < channels");
+  FAMI_CHECK_ARG(d->in_pitch >= d->Cin && (d->om_groups != 0 || d->out_pitch >= d->Cout), "fami_conv2d_bn_act_fwd: pitch < channels");
   FAMI_CHECK_ARG(!residual || d->res_pitch >= d->Cout, "fami_conv2d_bn_act_fwd: res_pitch < Cout");
   FAMI_CHECK_ARG(!d->stats || stats_out, "fami_conv2d_bn_act_fwd: stats requested without stats_out");
   FAMI_CHECK_ARG((int64_t)d->N * d->Ho * d->Wo * d->up * d->up < (1ll << 31),
@@ -159,6 +159,19 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
   /* fp32 input with bf16 output: only the stem (Cin not a multiple of 16), which runs the SIMT kernel */
   FAMI_CHECK_ARG(!(d->dtype == FAMI_F32 && is_half_dtype(d->out_dtype)) || (d->Cin % 16 != 0 && !d->stats),
                  "fami_conv2d_bn_act_fwd: fp32-in/bf16-out is only supported for the stem convolution");
+  if (d->om_groups != 0) {
+    FAMI_CHECK_ARG(d->om_groups > 0 && d->om_groups % 4 == 0 && d->Cout == 27 * d->om_groups && d->out_dtype == FAMI_F32 &&
+                       is_half_dtype(d->dtype) && d->up == 1 && !residual && !d->stats && d->kh == 3 && d->stride == 1 &&
+                       d->pad == d->dil,
+                   "fami_conv2d_bn_act_fwd: om_groups needs a 16-bit 3x3 stride-1 same conv with Cout = 27*G, fp32 output, "
+                   "no residual / upsample / statistics");
+    FAMI_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "fami_conv2d_bn_act_fwd: om_groups: y must be 16-byte aligned");
+    static const bool halo_off_om = getenv("FAMI_DISABLE_HALO") != nullptr;
+    if (!halo_off_om && conv_halo_supported(d))
+      return conv_halo_launch(d, x, w_packed, scale, shift, residual, y, (cudaStream_t)stream);
+    FAMI_CHECK_ARG(conv_bf16_tc_supported(d), "fami_conv2d_bn_act_fwd: om_groups: shape not supported by the tensor path");
+    return conv_bf16_tc_launch(d, x, w_packed, scale, shift, residual, y, stats_out, (cudaStream_t)stream);
+  }
   if (is_half_dtype(d->dtype)) {
     FAMI_CHECK_ARG(d->out_dtype == d->dtype || d->out_dtype == FAMI_F32,
                    "fami_conv2d_bn_act_fwd: half-precision conv output must be the same half type or fp32");

@@ -375,7 +375,7 @@ int conv_dgrad_launch(const fami_conv_desc* d, const float* gy, const float* wt_
     f.H = d->Ho; f.W = d->Wo; f.Cin = d->Cout; f.Cout = d->Cin;
     f.pad = d->dil * (d->kh - 1) - d->pad;
     f.Ho = d->H; f.Wo = d->W;
-    f.up = 1; f.relu = 0; f.stats = 0;
+    f.up = 1; f.relu = 0; f.stats = 0; f.om_groups = 0;
     f.in_pitch = d->out_pitch; f.out_pitch = d->in_pitch; f.res_pitch = 0;
     f.dtype = FAMI_F32; f.out_dtype = FAMI_F32;
     return fami_conv2d_bn_act_fwd(&f, gy, wt_packed, nullptr, nullptr, nullptr, gx, nullptr, (void*)st);

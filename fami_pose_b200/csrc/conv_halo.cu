@@ -56,6 +56,8 @@ struct HaloParams {
   uint32_t a_stage_bytes, b_tile_bytes, a_box_bytes;
   uint32_t ab_format;
   int trace;
+  int om_groups, om_tiles_x, om_tiles_y;   // > 0: y is the warp-blocked DCN offset|mask buffer
+  int64_t om_tap_stride;
   const float* scale;
   const float* shift;
   const void* res;
@@ -307,7 +309,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         bool valid;
         const int pix = row_pix(m, valid);
         const uint32_t t_addr = tmem_base + (uint32_t)(acc * acc_cols + m * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
-        if (pf_on) {
+        if (p.om_groups > 0) {
+          const int q = m * 128 + row;
+          const int yy = q / p.Wp, xx = q - yy * p.Wp;
+          OmBlocked ob;
+          ob.base = reinterpret_cast<float*>(p.y); ob.tiles_x = p.om_tiles_x; ob.tiles_y = p.om_tiles_y;
+          ob.G3 = 3 * p.om_groups; ob.tap_stride = p.om_tap_stride;
+          if (!(p.trace & 2)) epilogue_rows_om_blocked(ea, t_addr, col_begin, col_end, valid, img, y0 + yy, xx, ob);
+        } else if (pf_on) {
           // next unit of this warp: the next M-tile, or the first M-tile of this CTA's next tile
           bool nvalid = false, have_next = true;
           int npix = 0, nchb = ea.ch_base;
@@ -489,6 +498,9 @@ int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, cons
   p.a_box_bytes = (uint32_t)((c.BH + 2 * dl) * Wp) * 128u;
   p.ab_format = d->dtype == FAMI_F16 ? 0u : 1u;
   p.scale = scale; p.shift = shift; p.res = res; p.y = y;
+  p.om_groups = d->om_groups;
+  p.om_tiles_x = (d->W + 7) / 8; p.om_tiles_y = (d->H + 15) / 16;
+  p.om_tap_stride = (int64_t)d->N * p.om_tiles_x * p.om_tiles_y * 4 * (3 * (d->om_groups / 4)) * 128;
   static const bool trace_on = getenv("FAMI_HALO_TRACE") != nullptr;
   p.trace = trace_on ? atoi(getenv("FAMI_HALO_TRACE")) : 0;
 

@@ -33,6 +33,8 @@ struct TcParams {
   int out_pitch, res_pitch;
   int out_f32, vec_ok;
   int stages, pipe;   // pipe: pipelined residual epilogue (epilogue_rows_pipelined)
+  int om_groups, om_tiles_x, om_tiles_y;   // > 0: y is the warp-blocked DCN offset|mask buffer (fami_conv_desc.om_groups)
+  int64_t om_tap_stride;
   const float* scale;
   const float* shift;
   const void* res;   // TH
@@ -196,7 +198,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)(quarter * 32) << 16);
-      if (p.pipe) {
+      if (p.om_groups > 0) {
+        const int n = m / p.HoWo, r = m - n * p.HoWo;
+        const int yo = r / p.Wo, xo = r - yo * p.Wo;
+        OmBlocked ob;
+        ob.base = reinterpret_cast<float*>(p.y); ob.tiles_x = p.om_tiles_x; ob.tiles_y = p.om_tiles_y;
+        ob.G3 = 3 * p.om_groups; ob.tap_stride = p.om_tap_stride;
+        epilogue_rows_om_blocked(ea, t_addr, col_begin, col_end, valid, n, yo, xo, ob);
+      } else if (p.pipe) {
         const int ntile = tile + gridDim.x;
         const bool have_next = ntile < total_tiles;
         const int nmt = ntile / p.n_tiles, nnt = ntile - nmt * p.n_tiles;
@@ -332,10 +341,13 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   p.vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((d->out_pitch * osz) % 16 == 0) &&
              (!res || (((reinterpret_cast<uintptr_t>(res) & 15) == 0) && (d->res_pitch % 8 == 0)));
   p.scale = scale; p.shift = shift; p.res = res; p.y = y;
+  p.om_groups = d->om_groups;
+  p.om_tiles_x = (d->Wo + 7) / 8; p.om_tiles_y = (d->Ho + 15) / 16;
+  p.om_tap_stride = (int64_t)d->N * p.om_tiles_x * p.om_tiles_y * 4 * (3 * (d->om_groups / 4)) * 128;
   p.ab_format = d->dtype == FAMI_F16 ? 0u : 1u;
 
   const int stage_bytes = kABytes + t.BN * 128;
-  p.pipe = (epi_pipe_ok(t.BN, d->Cout, p.vec_ok, out_f32, d->up, res != nullptr) && d->Cout == t.BN * t.n_tiles &&
+  p.pipe = (d->om_groups == 0 && epi_pipe_ok(t.BN, d->Cout, p.vec_ok, out_f32, d->up, res != nullptr) && d->Cout == t.BN * t.n_tiles &&
             getenv("FAMI_NO_EPI_PIPE") == nullptr) ? 1 : 0;
   const size_t epi_bytes = p.pipe ? (size_t)kEpiWarps * 32 * (res ? 3 : 1) * epi_pipe_pitch() : (size_t)kEpiWarps * 32 * (128 + 16);
   int stages = (int)((228000 - (size_t)t.CoutPad * 8 - epi_bytes) / stage_bytes);   // all the shared memory there is: the kernel is bound by bytes in flight

@@ -218,9 +218,29 @@ def _conv_raw(x, w_packed, Cout, k, stride, pad, dil, scale, shift, residual, re
             raise ValueError("residual shape %s does not match conv output %s"
                              % (tuple(residual.shape), (N, Cout, Ho * up, Wo * up)))
     d = ConvDesc(N, H, W, Cin, Cout, k, k, stride, pad, dil, Ho, Wo, up, int(bool(relu)), ip, op, rp,
-                 _code(x.dtype), _code(out_dtype), int(stats is not None))
+                 _code(x.dtype), _code(out_dtype), int(stats is not None), 0)
     _lib.call("fami_conv2d_bn_act_fwd", ctypes.byref(d), _ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift),
               _ptr(residual), _ptr(out), _ptr(stats), _stream())
+    return out
+
+
+def conv_offsets_blocked(x, conv, G, out=None):
+    """The fused dcn_offset_k | dcn_mask_k convolution (Alignment_V15.py:144-145; `conv` holds the concatenated,
+    tap-major-permuted parameters) writing the warp-blocked buffer the tensor-core deformable kernel reads
+    (om_to_blocked layout).  Returns the flat float32 buffer."""
+    _need_cuda(x)
+    N, Cin, H, W, ip = meta(x)
+    k, pad, dil = conv.kernel_size[0], conv.padding[0], conv.dilation[0]
+    Cout = conv.out_channels
+    if Cout != 27 * G or k != 3 or conv.stride[0] != 1 or pad != dil:
+        raise ValueError("conv_offsets_blocked: 3x3 stride-1 same conv with 27*G output channels expected")
+    if out is None:
+        out = torch.empty(om_blocked_numel(N, H, W, G), dtype=torch.float32, device=x.device)
+    w = packed_weight(conv, conv.weight, x.dtype)
+    _, shift = folded_affine(conv.bias, None)
+    d = ConvDesc(N, H, W, Cin, Cout, k, k, 1, pad, dil, H, W, 1, 0, ip, 0, 0, _code(x.dtype), F32, 0, G)
+    _lib.call("fami_conv2d_bn_act_fwd", ctypes.byref(d), _ptr(x), _ptr(w), None, _ptr(shift), None, _ptr(out), None,
+              _stream())
     return out
 
 
@@ -510,7 +530,7 @@ def _conv_desc_f32(x_shape_meta, Cout, k, stride, pad, dil, out_pitch):
     N, Cin, H, W, ip = x_shape_meta
     Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
     Wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
-    return ConvDesc(N, H, W, Cin, Cout, k, k, stride, pad, dil, Ho, Wo, 1, 0, ip, out_pitch, 0, F32, F32, 0), Ho, Wo
+    return ConvDesc(N, H, W, Cin, Cout, k, k, stride, pad, dil, Ho, Wo, 1, 0, ip, out_pitch, 0, F32, F32, 0, 0), Ho, Wo
 
 
 def conv_dgrad(grad_y, weight, x_shape, stride=1, pad=0, dil=1, out=None):

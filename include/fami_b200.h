@@ -75,6 +75,11 @@ typedef struct fami_conv_desc {
   int32_t stats;                 /* 1: also accumulate per-channel sum / sum-of-squares of the RAW
                                     (post scale/shift, pre residual/act) output into the double
                                     array stats_out[2*Cout], which the caller zeroes (train-mode BN) */
+  int32_t om_groups;             /* 0: y is an NHWC activation (out_pitch).  G > 0: y is the warp-blocked offset|mask
+                                    buffer of the tensor-core deformable kernel (fami_dcn_desc.om_layout = 2) for G
+                                    offset groups: Cout = 27*G channels in tap-major order, out_dtype FAMI_F32, up = 1,
+                                    no residual, 3x3 stride-1 "same" convolution (the fused dcn_offset_k | dcn_mask_k
+                                    producer, Alignment_V15.py:144-145)                                              */
 } fami_conv_desc;
 
 int fami_conv_cout_pad(int Cout);
@@ -137,7 +142,7 @@ typedef struct fami_dcn_desc {
   int32_t B, H, W, C, Cout, G;
   int32_t kh, kw, stride, pad, dil; /* 3,3,1,3,3 in the reference; stride must be 1 */
   int32_t x_pitch, off_pitch, mask_pitch, out_pitch;
-  int32_t om_layout;                /* 0: torchvision layout -- `offset` [.,18G] (channel g*18+2t = dy, +1 = dx)
+  int32_t om_layout;                /* (2: warp-blocked, see below) 0: torchvision layout -- `offset` [.,18G] (channel g*18+2t = dy, +1 = dx)
                                        and `mask` [.,9G] (channel g*9+t) are separate operands;
                                        1: fused tap-major -- `offset` points at ONE buffer holding, per pixel,
                                        [9 taps][dy(G) | dx(G) | mask(G)] (off_pitch >= 27G), `mask` is ignored.

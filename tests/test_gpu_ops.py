@@ -513,3 +513,38 @@ def test_warp_translate_bwd_vs_torch_autograd():
     e1 = float((back(sd.grad).double() - s_ref.grad).abs().max())
     e2 = float((td.grad.cpu().double() - t_ref.grad).abs().max())
     assert e1 <= 1e-5 and e2 <= 1e-4 * max(1.0, float(t_ref.grad.abs().max())), (e1, e2)
+
+
+@pytest.mark.parametrize("shape", [(2, 48, 12, 33, 21), (1, 32, 8, 16, 8), (3, 64, 16, 20, 30)])
+def test_offset_conv_blocked_layout_and_dcn(shape):
+    """The fused offset|mask producer writing the warp-blocked layout (fami_conv_desc.om_groups) equals the same conv
+    written as an NHWC activation and converted on the host (ops.om_to_blocked), bit for bit -- incl. maps that are not a
+    multiple of the 16x8 DCN tile -- and the deformable kernel gives identical outputs from both layouts."""
+    m = fp()
+    from fami_pose_b200 import ops
+    B, C, G, H, W = shape
+    m.set_precision("fp16")
+    try:
+        g = torch.Generator().manual_seed(31 + C)
+        x = ops.to_nhwc(torch.randn(B, C, H, W, generator=g).to(DEV), torch.float16)
+        conv = torch.nn.Conv2d(C, 27 * G, 3, 1, 3, 3).to(DEV)
+        with torch.no_grad():
+            conv.weight.copy_(torch.randn(conv.weight.shape, generator=g).to(DEV) * 0.05)
+            conv.bias.copy_(torch.randn(27 * G, generator=g).to(DEV))
+            nhwc = ops.conv_bn_act(x, conv, None, relu=False, out_dtype=torch.float32)
+            blk = ops.conv_offsets_blocked(x, conv, G)
+            ref = ops.om_to_blocked(nhwc, G)
+            # slots of pixels outside the image are never written by the producer nor read by the consumer
+            Q = 3 * G // 4
+            ty, tx = (H + 15) // 16, (W + 7) // 8
+            inside = torch.zeros((B, ty * 16, tx * 8), dtype=torch.bool, device=DEV)
+            inside[:, :H, :W] = True
+            msk = inside.reshape(B, ty, 16, tx, 8).permute(0, 1, 3, 2, 4).reshape(B, ty, tx, 4, 1, 32, 1)
+            msk = msk.expand(9, B, ty, tx, 4, Q, 32, 4).reshape(-1)
+            assert torch.equal(blk[msk], ref[msk])
+            dcn = m.DeformConv2d(C, C, 3, padding=3, dilation=3).to(DEV)
+            o1 = dcn(x, None, None, fused_om=nhwc)
+            o2 = dcn(x, None, None, blocked_om=blk, groups=G)
+            assert torch.equal(o1, o2)
+    finally:
+        m.set_precision("fp32")
