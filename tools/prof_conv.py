@@ -42,12 +42,13 @@ if which in ("all", "dcn"):
     out = ops.empty_nhwc(B, C, H, W, dt, dev)
     om = ops.empty_nhwc(B, 27 * G, H, W, torch.float32, dev).normal_() * 2
     fused = dt != torch.float32
+    blk = ops.om_to_blocked(om, G) if fused else None
     ts = []
     for i in range(6):
         e0, e1 = ev(), ev()
         e0.record()
         if fused:
-            dcn(x, None, None, out=out, fused_om=om)
+            dcn(x, None, None, out=out, blocked_om=blk, groups=G)
         else:
             dcn(x, off, msk, out=out)
         e1.record()
