@@ -142,12 +142,18 @@ typedef struct fami_dcn_desc {
   int32_t B, H, W, C, Cout, G;
   int32_t kh, kw, stride, pad, dil; /* 3,3,1,3,3 in the reference; stride must be 1 */
   int32_t x_pitch, off_pitch, mask_pitch, out_pitch;
-  int32_t om_layout;                /* (2: warp-blocked, see below) 0: torchvision layout -- `offset` [.,18G] (channel g*18+2t = dy, +1 = dx)
+  int32_t om_layout;                /* 0: torchvision layout -- `offset` [.,18G] (channel g*18+2t = dy, +1 = dx)
                                        and `mask` [.,9G] (channel g*9+t) are separate operands;
-                                       1: fused tap-major -- `offset` points at ONE buffer holding, per pixel,
-                                       [9 taps][dy(G) | dx(G) | mask(G)] (off_pitch >= 27G), `mask` is ignored.
-                                       The alignment head's fused offset|mask convolution writes layout 1 so the
-                                       16-bit tensor-core kernel streams each tap's 3G floats contiguously.      */
+                                       1: fused tap-major -- `offset` points at ONE NHWC buffer holding, per pixel,
+                                       [9 taps][dy(G) | dx(G) | mask(G)] (off_pitch >= 27G), `mask` is ignored;
+                                       2: fused warp-blocked -- `offset` points at ONE dense buffer
+                                       [9 taps][image tile * 4 + quarter][q < 3G/4][32 lanes][4 floats] over 16x8-pixel
+                                       tiles (tile = (b * ceil(H/16) + y/16) * ceil(W/8) + x/8, quarter and lane from
+                                       r = (y%16)*8 + x%8: quarter = r/32, lane = r%32), where the 4 floats are channels
+                                       4q..4q+3 of the tap's [dy(G) | dx(G) | mask(G)] run; pitches and `mask` ignored.
+                                       Layouts 1 and 2 are the 16-bit tensor-core kernel's; the alignment head's fused
+                                       offset|mask convolution writes layout 2 (fami_conv_desc.om_groups) so that every
+                                       offset load instruction of the deformable kernel reads 512 contiguous bytes.  */
   int32_t dtype;                    /* storage of x/out: FAMI_F32 or FAMI_BF16; offset, mask, packed
                                        weights and bias are always float (sub-pixel precision)        */
 } fami_dcn_desc;
