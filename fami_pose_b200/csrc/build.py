@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu", "dcn_tc.cu", "misc.cu", "bwd.cu", "bwd_dense.cu", "decode.cu"]
+SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu", "dcn_tc.cu", "misc.cu", "bwd.cu", "bwd_dense.cu", "decode.cu", "stem_tc.cu"]
 OUT = os.path.join(os.path.dirname(HERE), "libfami_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -9,6 +9,8 @@
 // (pixel, tap) a contiguous run of Cin floats, so the A tile is gathered with 16-byte cp.async
 // (zero-filled at the padding halo) straight into shared memory; weights are pre-packed
 // [K][CoutPad] so the B tile is a plain 2-D copy.  3-stage cp.async pipeline, 8x4 register tile.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fami {
@@ -393,8 +395,15 @@ static int dispatch_tile(const ConvParams& p, cudaStream_t st) {
 }
 
 // x: float NHWC.  y/residual: float (out_bf16 = 0) or bf16 (out_bf16 = 1, scalar-gather stem path only).
+int stem_tc_supported(const fami_conv_desc* d, const void* y);
+int stem_tc_launch(const fami_conv_desc* d, const float* x, const float* w, const float* scale, const float* shift, void* y,
+                   cudaStream_t st);
+
 int conv_f32_launch(const fami_conv_desc* d, const float* x, const float* w, const float* scale,
                     const float* shift, const void* res, void* y, double* stats, cudaStream_t st) {
+  // HRNet stem (fp32 pixels -> 16-bit activations): tensor-core kernel with an in-CTA im2col (csrc/stem_tc.cu)
+  static const bool stem_tc_off = getenv("FAMI_DISABLE_STEM_TC") != nullptr;
+  if (!stem_tc_off && !res && stem_tc_supported(d, y)) return stem_tc_launch(d, x, w, scale, shift, y, st);
   ConvParams p;
   memset(&p, 0, sizeof(p));
   const bool out_half = is_half_dtype(d->out_dtype);

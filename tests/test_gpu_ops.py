@@ -548,3 +548,35 @@ def test_offset_conv_blocked_layout_and_dcn(shape):
             assert torch.equal(o1, o2)
     finally:
         m.set_precision("fp32")
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 64, 48), (3, 33, 47), (1, 384, 288)])
+def test_stem_conv_tensor_core(shape, prec):
+    """HRNet stem (3 -> 64, 3x3, stride 2, pad 1, fp32 pixels -> 16-bit activations, BN + ReLU; hrnet.py conv1/bn1) on
+    the tensor-core kernel with its in-CTA im2col (csrc/stem_tc.cu) vs torch fp32, incl. odd sizes (image borders,
+    ragged last tile).  Tolerance: 16-bit rounding of inputs, weights and outputs (fp16 2e-3, bf16 1.6e-2 relative)."""
+    m = fp()
+    from fami_pose_b200 import ops
+    N, H, W = shape
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(N, 3, H, W, generator=g)
+    conv = torch.nn.Conv2d(3, 64, 3, 2, 1, bias=False)
+    bn = torch.nn.BatchNorm2d(64).eval()
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * 0.2)
+        bn.weight.copy_(torch.rand(64, generator=g) + 0.5); bn.bias.copy_(torch.randn(64, generator=g) * 0.2)
+        bn.running_mean.copy_(torch.randn(64, generator=g) * 0.2); bn.running_var.copy_(torch.rand(64, generator=g) + 0.5)
+        ref = F.relu(bn(conv(x)))
+    m.set_precision(prec)
+    try:
+        dt = ops.act_dtype()
+        xn = ops.to_nhwc(x.to(DEV), torch.float32)
+        with torch.no_grad():
+            y = ops.conv_bn_act(xn, conv.to(DEV), bn.to(DEV), relu=True, out_dtype=dt)
+        assert y.dtype == dt
+        got = ops.to_nchw(y).float().cpu()
+    finally:
+        m.set_precision("fp32")
+    tol = (2e-3 if prec == "fp16" else 1.6e-2) * float(ref.abs().max()) + 1e-3
+    assert float((got - ref).abs().max()) <= tol
