@@ -385,7 +385,8 @@ HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d) {
   double best_score = -1;
   static const int ast_env = getenv("FAMI_HALO_ACCSTRIDE") ? atoi(getenv("FAMI_HALO_ACCSTRIDE")) : 0;
   const int ast = ast_env > 0 ? ((BN + ast_env - 1) / ast_env) * ast_env : BN;   // TMEM column stride between M-tile accumulators
-  for (int NM = 1; NM <= 8; ++NM) {
+  static const int nm_max = getenv("FAMI_HALO_NMMAX") ? atoi(getenv("FAMI_HALO_NMMAX")) : 8;   // experiment knob
+  for (int NM = 1; NM <= nm_max; ++NM) {
     if (NM * ast > 512) break;
     int BH = (NM * 128) / Wp;
     if (BH < 1) continue;
