@@ -76,6 +76,7 @@ SIGNATURES = {
                                   c_void_p]),
     "fami_gaussian_targets": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_void_p]),
+    "fami_frames_u8_normalize": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "fami_debug_read_trace": (c_int, [c_void_p, c_int]),
     "fami_debug_umma_rate": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "fami_debug_umma_rowshift": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

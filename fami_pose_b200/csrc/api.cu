@@ -63,6 +63,8 @@ int pck_accuracy_launch(const int32_t* pidx, const float* pmax, const int32_t* t
                         int H, int W, int J, float thr, cudaStream_t st);
 int gaussian_targets_launch(const float* joints, const float* vis, float* target, float* weight, int B, int J, int sigma,
                             int img_w, int img_h, int hm_w, int hm_h, cudaStream_t st);
+int frames_u8_normalize_launch(const uint8_t* src, int64_t src_frame_stride, float* dst, int nframes, int64_t px_per_frame,
+                               const float* mean, const float* std, cudaStream_t st);
 int dcn_tc_supported(const fami_dcn_desc* d);
 int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const void* w, const float* bias, void* out,
                   cudaStream_t st);
@@ -251,6 +253,13 @@ int fami_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   return adam_step_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2),
                           (cudaStream_t)stream);
+}
+
+int fami_frames_u8_normalize(const uint8_t* frames, int64_t src_frame_stride, float* out, int nframes, int H, int W,
+                             const float* mean3, const float* std3, void* stream) {
+  FAMI_CHECK_ARG(frames && out && mean3 && std3 && nframes > 0 && H > 0 && W > 0, "fami_frames_u8_normalize: bad arguments");
+  FAMI_CHECK_ARG(src_frame_stride >= (int64_t)H * W * 3, "fami_frames_u8_normalize: frame stride smaller than a frame");
+  return frames_u8_normalize_launch(frames, src_frame_stride, out, nframes, (int64_t)H * W, mean3, std3, (cudaStream_t)stream);
 }
 
 int fami_final_preds(const void* hm, int dtype, int pitch, const int32_t* idx, const float* maxvals, const float* center,

@@ -122,7 +122,33 @@ __global__ void gaussian_targets_kernel(const float* __restrict__ joints, const 
   }
 }
 
+// uint8 HWC frames -> normalised fp32 NHWC (torchvision ToTensor + Normalize, datasets/transforms/build.py:13-22):
+// ((u8 / 255) - mean[c]) / std[c], in that order of IEEE operations.  Frames are gathered with a source frame stride so
+// the (batch, window) order of a loader becomes the frame-major order of Alignment_V15.py:115-119.
+__global__ void frames_u8_normalize_kernel(const uint8_t* __restrict__ src, int64_t src_frame_stride, float* __restrict__ dst,
+                                           int nframes, int64_t px_per_frame, float m0, float m1, float m2, float s0,
+                                           float s1, float s2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)nframes * px_per_frame) return;
+  const int f = (int)(i / px_per_frame);
+  const int64_t pix = i - (int64_t)f * px_per_frame;
+  const uint8_t* s = src + (int64_t)f * src_frame_stride + pix * 3;
+  float* d = dst + i * 3;
+  d[0] = ((float)s[0] / 255.f - m0) / s0;
+  d[1] = ((float)s[1] / 255.f - m1) / s1;
+  d[2] = ((float)s[2] / 255.f - m2) / s2;
+}
+
 }  // namespace
+
+int frames_u8_normalize_launch(const uint8_t* src, int64_t src_frame_stride, float* dst, int nframes, int64_t px_per_frame,
+                               const float* mean, const float* std, cudaStream_t st) {
+  const int64_t tot = (int64_t)nframes * px_per_frame;
+  frames_u8_normalize_kernel<<<cdiv(tot, 256), 256, 0, st>>>(src, src_frame_stride, dst, nframes, px_per_frame, mean[0], mean[1],
+                                                             mean[2], std[0], std[1], std[2]);
+  FAMI_CHECK_LAUNCH("frames_u8_normalize_kernel");
+  return 0;
+}
 
 #define DISPATCH_T(dtype, ...)                                                 \
   if ((dtype) == FAMI_F32) { using T = float; __VA_ARGS__ }                    \

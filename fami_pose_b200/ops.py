@@ -129,6 +129,34 @@ def frames_to_nhwc(kf_x, sup_x, dtype=torch.float32):
     return out
 
 
+IMAGENET_MEAN = (0.485, 0.456, 0.406)     # datasets/transforms/build.py:13-14 (RGB)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def frames_u8_to_nhwc(kf_u8, sup_u8, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """uint8 RGB frames as a loader holds them -- key frames [B,H,W,3], supporting frames [B,ns,H,W,3] -- to the
+    normalised frame-major fp32 NHWC batch [(1+ns)*B, H, W, 3] the backbone consumes: ToTensor + Normalize
+    (datasets/transforms/build.py:13-22) fused with the re-batching of Alignment_V15.py:115-119.  A quarter of the
+    host->device bytes of the float path."""
+    _need_cuda(kf_u8, sup_u8)
+    if kf_u8.dtype != torch.uint8 or sup_u8.dtype != torch.uint8:
+        raise TypeError("frames_u8_to_nhwc expects uint8 frames")
+    kf_u8, sup_u8 = kf_u8.contiguous(), sup_u8.contiguous()
+    B, H, W, _ = kf_u8.shape
+    ns = sup_u8.shape[1]
+    if tuple(sup_u8.shape) != (B, ns, H, W, 3) or kf_u8.shape[3] != 3:
+        raise ValueError("expected key frames [B,H,W,3] and supporting frames [B,ns,H,W,3]")
+    out = empty_nhwc((1 + ns) * B, 3, H, W, torch.float32, kf_u8.device)
+    m = (ctypes.c_float * 3)(*mean)
+    s = (ctypes.c_float * 3)(*std)
+    fb = H * W * 3
+    _lib.call("fami_frames_u8_normalize", _ptr(kf_u8), fb, _ptr(out[:B]), B, H, W, m, s, _stream())
+    for i in range(ns):
+        src = ctypes.c_void_p(sup_u8.data_ptr() + i * fb)
+        _lib.call("fami_frames_u8_normalize", src, ns * fb, _ptr(out[(1 + i) * B:(2 + i) * B]), B, H, W, m, s, _stream())
+    return out
+
+
 def to_nchw(t):
     """NHWC(+pitch) activation -> contiguous float32 NCHW (fami_nhwc_to_nchw)."""
     _need_cuda(t)

@@ -179,8 +179,20 @@ class Alignment_V15(nn.Module):
         B, ns = kf_x.shape[0], sup_x.shape[1] // 3
         if ns != self.num_sup:
             raise ValueError("model was built for %d supporting frames, got %d" % (self.num_sup, ns))
-        C = self.width
         x = ops.frames_to_nhwc(kf_x, sup_x)                       # :117-119, frame-major batch
+        return self._forward_frames(x, B, ns)
+
+    def forward_u8(self, kf_u8, sup_u8, **kwargs):
+        """fami extension: the same forward from uint8 RGB frames as a loader holds them (key frames [B,H,W,3],
+        supporting frames [B,ns,H,W,3]); ToTensor + Normalize of datasets/transforms/build.py:13-22 run on the
+        device (ops.frames_u8_to_nhwc).  Bit-identical to forward() on the normalised float tensors."""
+        B, ns = kf_u8.shape[0], sup_u8.shape[1]
+        if ns != self.num_sup:
+            raise ValueError("model was built for %d supporting frames, got %d" % (self.num_sup, ns))
+        return self._forward_frames(ops.frames_u8_to_nhwc(kf_u8, sup_u8), B, ns)
+
+    def _forward_frames(self, x, B, ns):
+        C = self.width
         graph = (torch.is_grad_enabled() and ops.get_precision() == "fp32"
                  and any(p.requires_grad for p in self.parameters()))
         bp = getattr(self, "backbone_precision", None)

@@ -245,6 +245,11 @@ int fami_pck_accuracy(const int32_t* pred_idx, const float* pred_max, const int3
  * and target_weight [B,J].                                                                           */
 int fami_gaussian_targets(const float* joints, const float* joints_vis, float* target, float* target_weight,
                           int B, int J, int sigma, int img_w, int img_h, int hm_w, int hm_h, void* stream);
+/* torchvision ToTensor + Normalize(mean, std) of datasets/transforms/build.py:13-22 on the device, fused with the
+ * frame re-batching of Alignment_V15.py:115-119: `nframes` uint8 HWC (RGB) frames, `src_frame_stride` BYTES apart,
+ * -> dense fp32 NHWC frames out[f][y][x][c] = ((u8/255) - mean[c]) / std[c].  mean3 / std3 are HOST pointers.   */
+int fami_frames_u8_normalize(const uint8_t* frames, int64_t src_frame_stride, float* out, int nframes, int H, int W,
+                             const float* mean3, const float* std3, void* stream);
 
 /* ---- hardware probe (test infrastructure, tools/probe_umma.py) -------------------------------
  * out[128][16] = x[shift:shift+128][64] @ w[16][64]^T through one tcgen05 tile whose A descriptor

@@ -78,3 +78,38 @@ def test_gaussian_targets_cuda_vs_reference_golden(gold):
     assert np.array_equal(got != 0, ref != 0)                            # identical support (patch placement, clipping)
     assert np.abs(got - ref).max() <= 2e-7                               # expf vs numpy's float32 exp: <= 2 ulp at 1.0
     assert np.array_equal(got.reshape(4, 17, -1).argmax(2), ref.reshape(4, 17, -1).argmax(2))
+
+
+@pytest.mark.gpu
+def test_frames_u8_normalize_bit_exact_and_forward_u8():
+    """uint8 frames -> normalised fp32 NHWC on the device == torchvision's ToTensor + Normalize
+    (datasets/transforms/build.py:13-22: x/255, then (x - mean)/std) bit for bit, in the frame-major order of
+    Alignment_V15.py:115-119; and the model's forward_u8 equals forward() on the normalised float tensors."""
+    import fami_pose_b200 as fp
+    from fami_pose_b200 import ops
+    from oracle import ref_harness as rh
+    g = torch.Generator().manual_seed(5)
+    B, ns, H, W = 2, 4, 64, 64
+    kf = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
+    sup = torch.randint(0, 256, (B, ns, H, W, 3), generator=g, dtype=torch.uint8)
+    mean = torch.tensor(ops.IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(ops.IMAGENET_STD).view(1, 3, 1, 1)
+
+    def tv(x_hwc):                                         # ToTensor + Normalize on [N,H,W,3] uint8
+        t = x_hwc.permute(0, 3, 1, 2).float().div(255)
+        return t.sub(mean).div(std)
+    kf_f = tv(kf)                                           # [B,3,H,W]
+    sup_f = torch.cat([tv(sup[:, i]) for i in range(ns)], 1)  # [B,3*ns,H,W] as the loader stacks the window
+    x = ops.frames_u8_to_nhwc(kf.cuda(), sup.cuda())
+    ref = ops.frames_to_nhwc(kf_f.cuda(), sup_f.cuda())
+    assert x.shape == ref.shape == ((1 + ns) * B, 3, H, W)
+    assert torch.equal(x, ref)
+    fp.set_precision("fp32")
+    m = fp.Alignment_V15(rh.make_cfg(48, 17), "validate", feat_hw=(16, 16))
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(fo.seeded_state_dict(shapes, SEED), strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        a = m(kf_f.cuda(), sup_f.cuda())
+        b = m.forward_u8(kf.cuda(), sup.cuda())
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
