@@ -438,12 +438,14 @@ int conv_halo_supported(const fami_conv_desc* d) {
   if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != d->dil || d->up != 1) return 0;
   if (d->Cin % 16 != 0 || d->in_pitch % 8 != 0) return 0;
   if (d->dil < 1 || d->dil > 8) return 0;
-  // Measured (tools/prof_conv.py, N=160 fp16): the halo form wins when the weights stay resident in
-  // shared memory (Cin <= 64: 48->48 160 us vs 225 us im2col) and loses when they must be re-streamed
-  // per CTA tile (96->96: 146 vs 110 us, 192->192: 109 vs 74 us), so only resident-B shapes come here.
+  // Measured (tools/prof_conv.py, tools/time_conv_shape.py, N=160 fp16): the halo form wins when the weights stay
+  // resident in shared memory (Cin <= 64: 48->48 90 us vs 225 us im2col) and when many input channels feed few
+  // output channels (256->48: 395 vs 590 us, 192->48: 85 vs 91 us: each streamed 6 KB weight tile serves NM M-tiles);
+  // it loses for the square wide classes whose weights must be re-streamed per CTA tile (96->96: 128 vs 111 us,
+  // 192->192: 105 vs 74 us).
   HaloCfg c = halo_cfg(d->H, d->W, d->Cin, d->Cout, d->dil);
   static const bool force = getenv("FAMI_HALO_FORCE") != nullptr;   // experiment: also take streamed-weights shapes
-  return (c.ok && (force || c.b_resident || c.n_tiles > 1)) ? 1 : 0;
+  return (c.ok && (force || c.b_resident || c.n_tiles > 1 || (c.BN <= 64 && c.cchunks >= 3))) ? 1 : 0;
 }
 
 int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
