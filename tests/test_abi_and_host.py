@@ -166,3 +166,42 @@ def test_patch_reference_rebinds_names():
         pytest.skip("reference tree only exists in the build container")
     r = subprocess.run([sys.executable, "-c", _PATCH_SCRIPT % (ROOT, GOLD)], capture_output=True, text=True, timeout=600)
     assert "PATCH_OK" in r.stdout, r.stderr[-2000:]
+
+
+def test_multistep_lr_matches_torch_scheduler():
+    """train.multistep_lr == torch.optim.lr_scheduler.MultiStepLR(LR_STEP, LR_FACTOR) (scheduler.py:14-26)."""
+    import torch
+    from fami_pose_b200.train import multistep_lr
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.Adam([p], lr=1e-4)
+    sch = torch.optim.lr_scheduler.MultiStepLR(opt, [4, 8, 12], 0.1)
+    for epoch in range(15):
+        assert abs(multistep_lr(1e-4, epoch, [4, 8, 12], 0.1) - opt.param_groups[0]["lr"]) < 1e-18
+        opt.step()
+        sch.step()
+
+
+def test_offset_layout_host_logic():
+    """tap_major_perm is a permutation mapping torchvision's [offset(18G) | mask(9G)] order to [tap][dy|dx|mask];
+    om_to_blocked is a bijection onto the warp-blocked buffer for tile-aligned maps (CPU tensors: pure indexing)."""
+    import torch
+    from fami_pose_b200 import ops
+    G = 12
+    perm = ops.tap_major_perm(G)
+    assert sorted(perm) == list(range(27 * G))
+    # tap 2, group 5: dy = offset channel 5*18 + 4, dx = +1, mask = 216 + 5*9 + 2
+    t = 2
+    assert perm[t * 3 * G + 5] == 5 * 18 + 2 * t
+    assert perm[t * 3 * G + G + 5] == 5 * 18 + 2 * t + 1
+    assert perm[t * 3 * G + 2 * G + 5] == 18 * G + 5 * 9 + t
+    B, H, W = 2, 32, 16
+    om = torch.arange(B * 27 * G * H * W, dtype=torch.float32).reshape(B, 27 * G, H, W)
+    blk = ops.om_to_blocked(om, G)
+    assert blk.numel() == ops.om_blocked_numel(B, H, W, G) == om.numel()
+    assert torch.equal(torch.sort(blk).values, torch.sort(om.reshape(-1)).values)
+    # element (b=1, y=17, x=9, tap=3, channel-in-tap f=7): tile (1,1) of image 1, r = 1*8+1 = 9 -> quarter 0, lane 9
+    Q = 3 * G // 4
+    tiles = (H // 16) * (W // 8)
+    tile = 1 * tiles + 1 * (W // 8) + 1
+    idx = ((((3 * (B * tiles) + tile) * 4 + 0) * Q + 7 // 4) * 32 + 9) * 4 + 7 % 4
+    assert float(blk[idx]) == float(om[1, 3 * 3 * G + 7, 17, 9])
