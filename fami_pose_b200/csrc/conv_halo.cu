@@ -213,6 +213,36 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (leader) umma_commit(emptyA(sa));
           if (++sa == p.sA) { sa = 0; pa ^= 1u; }
+        } else if (!p.b_resident && !p.trace) {
+          // Streamed weights (Cin > 64 or several N tiles): one B tile per (tap, channel chunk) through the ring, each
+          // serving this issuer's M-tiles.  Same discipline as the hot path: nothing in the loop but increments.
+          const uint32_t wp8 = (uint32_t)(p.Wp * p.d) * 8u, d8 = (uint32_t)p.d * 8u;
+          const uint32_t a_inc = (uint32_t)p.n_iss * 1024u, d_inc = (uint32_t)(p.n_iss * p.acc_stride);
+          const uint32_t d0 = d_tmem + (uint32_t)(issuer * p.acc_stride);
+          const uint32_t b_ring0 = sw128_desc_lo(smem_u32(smemB)), b_step = p.b_tile_bytes >> 4;
+          bool accum = false;
+          for (int cc = 0; cc < p.cchunks; ++cc) {
+            mbar_wait(fullA(sa), pa);
+            tc_fence_after();
+            const int nk = (cc == p.cchunks - 1) ? p.last_kk : 4;
+            uint32_t a_row = sw128_desc_lo(smem_u32(smemA + (size_t)sa * p.a_stage_bytes)) + (uint32_t)issuer * 1024u;
+            for (int fr = 0; fr < 3; ++fr, a_row += wp8) {
+              uint32_t a_tap = a_row;
+              for (int fs = 0; fs < 3; ++fs, a_tap += d8) {
+                mbar_wait(fullB(sb), pb);
+                tc_fence_after();
+                const uint32_t b_lo = b_ring0 + (uint32_t)sb * b_step;
+                uint32_t a_lo = a_tap, dcol = d0;
+                for (int m = issuer; m < p.NM; m += p.n_iss, a_lo += a_inc, dcol += d_inc)
+                  umma_ksteps_n(nk, leader, dcol, a_lo, b_lo, idesc, accum);
+                accum = true;
+                if (leader) umma_commit(emptyB(sb));
+                if (++sb == p.sB) { sb = 0; pb ^= 1u; }
+              }
+            }
+            if (leader) umma_commit(emptyA(sa));
+            if (++sa == p.sA) { sa = 0; pa ^= 1u; }
+          }
         } else
         for (int cc = 0; cc < p.cchunks; ++cc) {
           mbar_wait(fullA(sa), pa);
@@ -266,17 +296,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int col_begin, col_end;
     epi_col_range(p.BN, (warp - kEpiWarp0) >> 2, col_begin, col_end);
     EpiArgs ea;
-    ea.spitch = epi_stage_pitch(p.BN, p.out_f32);
+    // Lean pipelined epilogue (16-column groups, pitch 48 B: staging + two residual buffers per warp fill exactly the
+    // 12 x 32 x 144 B allocation) whenever the output is a plain 16-bit NHWC tile; the generic routine otherwise.
+    const bool lean = epi_pipe_ok(p.BN, p.Cout, p.vec_ok, p.out_f32, 1, p.res != nullptr) && p.Cout == p.BN * p.n_tiles &&
+                      p.om_groups == 0 && !(p.trace & 16);
+    const bool pf_on = lean && p.res != nullptr;
+    const bool lean_nores = lean && p.res == nullptr;
+    ea.spitch = lean ? epi_pipe_pitch(16) : epi_stage_pitch(p.BN, p.out_f32);
     const uint32_t stage = smem_u32(stage_base) + (uint32_t)((warp - kEpiWarp0) * 32 * ea.spitch);
-    // two residual prefetch buffers per warp behind the staging buffers, when the allocation has room for them
     const uint32_t rb0 = smem_u32(stage_base) + (uint32_t)(kEpiWarps * 32 * ea.spitch);
     const uint32_t rbuf[2] = {rb0 + (uint32_t)((2 * (warp - kEpiWarp0)) * 32 * ea.spitch),
                               rb0 + (uint32_t)((2 * (warp - kEpiWarp0) + 1) * 32 * ea.spitch)};
-    // pipelined residual epilogue (16-column groups: staging pitch 48 B, three buffers per warp fit the allocation)
-    const bool pf_on = p.res != nullptr && ea.spitch == epi_pipe_pitch(16) && col_end - col_begin == 16 &&
-                       epi_pipe_ok(p.BN, p.Cout, p.vec_ok, p.out_f32, 1, true) && p.Cout == p.BN * p.n_tiles && !(p.trace & 16);
-    const bool lean_nores = p.res == nullptr && ea.spitch == epi_pipe_pitch(16) && col_end - col_begin == 16 &&
-                            epi_pipe_ok(p.BN, p.Cout, p.vec_ok, p.out_f32, 1, false) && p.Cout == p.BN * p.n_tiles;
     int pf_have = 0, pf_sel = 0;
     ea.s_scale = smem_u32(s_scale); ea.s_shift = smem_u32(s_shift); ea.res = p.res; ea.y = p.y;
     ea.Cout = p.Cout; ea.BN = p.BN; ea.out_pitch = p.out_pitch; ea.res_pitch = p.res_pitch;
@@ -417,7 +447,11 @@ HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d) {
         const double a_bytes = (double)box_rows * 128.0 * cchunks;
         const double b_bytes = resident ? 0.0 : (double)b_all;
         const double feed = (a_bytes + b_bytes) / ((double)BH * W);
-        double score = eff / feed * (acc_bufs == 2 ? 1.0 : 0.8) * (sA == 2 ? 1.0 : 0.85);
+        // resident weights: big tiles win even single-buffered (48->48: NM=5, sA=1 measured best).  Streamed weights:
+        // the accumulator and the A stage must be double-buffered or the tile loses to the im2col kernel
+        // (96->96: NM=2/sA=2/acc=2 72 us, NM=5/sA=1/acc=1 92 us, im2col 81 us).
+        double score = resident ? eff / feed * (acc_bufs == 2 ? 1.0 : 0.8) * (sA == 2 ? 1.0 : 0.85)
+                                : eff / feed * (acc_bufs == 2 ? 1.0 : 0.4) * (sA == 2 ? 1.0 : 0.5);
         if (score > best_score) {
           best_score = score;
           best.ok = true;
@@ -441,11 +475,12 @@ int conv_halo_supported(const fami_conv_desc* d) {
   // Measured (tools/prof_conv.py, tools/time_conv_shape.py, N=160 fp16): the halo form wins when the weights stay
   // resident in shared memory (Cin <= 64: 48->48 90 us vs 225 us im2col) and when many input channels feed few
   // output channels (256->48: 395 vs 590 us, 192->48: 85 vs 91 us: each streamed 6 KB weight tile serves NM M-tiles);
-  // it loses for the square wide classes whose weights must be re-streamed per CTA tile (96->96: 128 vs 111 us,
-  // 192->192: 105 vs 74 us).
+  // 96->96 wins with double-buffered accumulators and A stages (72 vs 81 us); it loses for the wider square
+  // classes whose weights must be re-streamed per CTA tile (192->192: 75 vs 51 us).
   HaloCfg c = halo_cfg(d->H, d->W, d->Cin, d->Cout, d->dil);
   static const bool force = getenv("FAMI_HALO_FORCE") != nullptr;   // experiment: also take streamed-weights shapes
-  return (c.ok && (force || c.b_resident || c.n_tiles > 1 || (c.BN <= 64 && c.cchunks >= 3))) ? 1 : 0;
+  return (c.ok && (force || c.b_resident || c.n_tiles > 1 || (c.BN <= 64 && c.cchunks >= 3) ||
+                   (c.BN <= 96 && c.acc_bufs == 2 && c.sA == 2))) ? 1 : 0;
 }
 
 int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
