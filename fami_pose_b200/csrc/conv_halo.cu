@@ -436,7 +436,7 @@ HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d) {
       size_t bbytes;
       int sB;
       if (resident) { bbytes = b_all; sB = 0; }
-      else { sB = 4; bbytes = b_tile * sB; }
+      else { static const int sb_env = getenv("FAMI_HALO_SB") ? atoi(getenv("FAMI_HALO_SB")) : 4; sB = sb_env; bbytes = b_tile * sB; }
       for (int sA = 2; sA >= 1; --sA) {
         size_t smem = a_stage * sA + bbytes + 1024 + 256 + (size_t)kEpiWarps * 32 * (128 + 16) + (size_t)BN * n_tiles * 8;
         if (smem > kSmemBudget) continue;
