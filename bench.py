@@ -145,7 +145,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fami", choices=["fami", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
-    ap.add_argument("--precision", default=os.environ.get("FAMI_PRECISION", "fp16"), choices=["fp32", "fp16", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("FAMI_PRECISION", "fp16"), choices=["fp32", "tf32", "fp16", "bf16"])
     ap.add_argument("--ref-batch", type=int, default=2)
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -316,7 +316,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.precision], "data": "synthetic",
+            "dtype": {"fp32": "f32", "tf32": "tf32 (f32 storage)", "fp16": "f16", "bf16": "bf16"}[args.precision], "data": "synthetic",
             "config": {"workload": "BASELINE config 2: Alignment_V15 HRNet-W48 384x288, 5-frame window, 17 joints, "
                                    "batch 32 per GPU; forward (eval-mode BN) + JointsMSE + keypoint argmax",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d (clips shard by batch)" % world,

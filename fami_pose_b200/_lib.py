@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libfami_b200.so")
 F32 = 0
 BF16 = 1
 F16 = 2
+TF32 = 3   # conv / dcn descriptors only: float storage, tcgen05 kind::tf32 arithmetic
 
 
 class ConvDesc(Structure):
@@ -77,11 +78,20 @@ SIGNATURES = {
     "fami_gaussian_targets": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_void_p]),
     "fami_frames_u8_normalize": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "fami_argmax_hw": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+}
+
+# hardware probes / kernel timelines: exported only by libfami_b200_probes.so (csrc/build.py --probes), which the
+# scripts under tools/ select with FAMI_PROBES=1 in the environment before importing the package
+PROBE_SIGNATURES = {
     "fami_debug_read_trace": (c_int, [c_void_p, c_int]),
     "fami_debug_umma_rate": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "fami_debug_umma_rowshift": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "fami_argmax_hw": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "fami_debug_tma_tf32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
+PROBES = os.environ.get("FAMI_PROBES", "0") not in ("", "0")
+if PROBES:
+    LIB_PATH = os.path.join(_HERE, "libfami_b200_probes.so")
 
 _lib = None
 
@@ -100,11 +110,14 @@ def load():
             "libfami_b200.so not found at %s -- run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(or python fami_pose_b200/csrc/build.py).  There is no CPU fallback." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+    sigs = dict(SIGNATURES)
+    if PROBES:
+        sigs.update(PROBE_SIGNATURES)
+    for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.fami_abi_version() != 1:
+    if lib.fami_abi_version() != 2:
         raise FamiLibraryError("libfami_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -118,8 +118,10 @@ class ConvBnActFunction(torch.autograd.Function):
                           ops._ptr(bn.running_mean if track else None), ops._ptr(bn.running_var if track else None),
                           ops._ptr(scale), ops._ptr(shift), ops._ptr(mean), ops._ptr(invstd), Cout, N * Ho * Wo,
                           float(bn.eps), float(mom), ops._stream())
-                if track and bn.num_batches_tracked is not None:
-                    bn.num_batches_tracked += 1
+                if track:
+                    torch.autograd.graph.increment_version((bn.running_mean, bn.running_var))   # see ops.conv_bn_act
+                    if bn.num_batches_tracked is not None:
+                        bn.num_batches_tracked += 1
             else:
                 with torch.no_grad():
                     mean = bn.running_mean.float().clone()

@@ -21,14 +21,16 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static std::atomic<int> sms[64];   // per device (zero-initialised)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int v = sms[dev & 63].load(std::memory_order_relaxed);
+  if (!v) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    sms[dev & 63].store(v, std::memory_order_relaxed);
   }
-  return sms;
+  return v;
 }
 
 // kernels implemented in other translation units
@@ -40,7 +42,7 @@ int dcn_simt_launch(const fami_dcn_desc* d, const void* x, const float* off, con
 int conv_bf16_tc_supported(const fami_conv_desc* d);
 int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale,
                         const float* shift, const void* res, void* y, double* stats, cudaStream_t st);
-int64_t pack_w_bf16_elems(int Cout, int Cin, int kh, int kw);
+int64_t pack_w_bf16_elems(int Cout, int Cin, int kh, int kw, int dtype);
 int conv_halo_supported(const fami_conv_desc* d);
 int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
                      const void* res, void* y, cudaStream_t st);
@@ -91,13 +93,14 @@ int debug_read_trace(unsigned long long* host_out, int n);
 int debug_read_dcn_trace(unsigned long long* host_out, int n);
 int debug_umma_rate_launch(long long* out, int N, int iters, int variant, cudaStream_t st);
 int debug_umma_rowshift_launch(const void*, const void*, float*, int, int, int, cudaStream_t);
+int debug_tma_tf32_launch(const float* x, uint32_t* out, int rows, int mode, cudaStream_t st);
 
 }  // namespace fami
 
 using namespace fami;
 
-static inline bool valid_dtype(int dt) { return dt == FAMI_F32 || dt == FAMI_BF16 || dt == FAMI_F16; }
-static inline size_t esize(int dt) { return dt == FAMI_F32 ? 4 : 2; }
+static inline bool valid_dtype(int dt) { return dt == FAMI_F32 || dt == FAMI_BF16 || dt == FAMI_F16; }   /* storage types */
+static inline size_t esize(int dt) { return (dt == FAMI_F32 || dt == FAMI_TF32) ? 4 : 2; }
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 extern "C" {
@@ -125,7 +128,7 @@ int fami_nhwc_to_nchw(const void* src, int src_dtype, int src_pitch, float* dst,
 int fami_conv_cout_pad(int Cout) { return ((Cout + 15) / 16) * 16; }
 
 int64_t fami_packed_weight_elems(int Cout, int Cin, int kh, int kw, int dtype) {
-  if (is_half_dtype(dtype)) return pack_w_bf16_elems(Cout, Cin, kh, kw);
+  if (is_tc_dtype(dtype)) return pack_w_bf16_elems(Cout, Cin, kh, kw, dtype);
   int64_t kpad = ((int64_t)kh * kw * Cin + 15) / 16 * 16;
   return kpad * fami_conv_cout_pad(Cout);
 }
@@ -133,16 +136,16 @@ int64_t fami_packed_weight_elems(int Cout, int Cin, int kh, int kw, int dtype) {
 int fami_pack_conv_weight(const float* w_oihw, void* w_packed, int Cout, int Cin, int kh, int kw, int dtype,
                           void* stream) {
   FAMI_CHECK_ARG(w_oihw && w_packed, "fami_pack_conv_weight: null pointer");
-  FAMI_CHECK_ARG(valid_dtype(dtype), "fami_pack_conv_weight: bad dtype %d", dtype);
+  FAMI_CHECK_ARG(valid_dtype(dtype) || dtype == FAMI_TF32, "fami_pack_conv_weight: bad dtype %d", dtype);
   FAMI_CHECK_ARG(Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "fami_pack_conv_weight: bad shape");
-  if (is_half_dtype(dtype)) return pack_w_bf16_launch(w_oihw, w_packed, Cout, Cin, kh, kw, dtype, (cudaStream_t)stream);
+  if (is_tc_dtype(dtype)) return pack_w_bf16_launch(w_oihw, w_packed, Cout, Cin, kh, kw, dtype, (cudaStream_t)stream);
   return pack_w_f32_launch(w_oihw, (float*)w_packed, Cout, Cin, kh, kw, (cudaStream_t)stream);
 }
 
 int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w_packed, const float* scale,
                            const float* shift, const void* residual, void* y, double* stats_out, void* stream) {
   FAMI_CHECK_ARG(d && x && w_packed && y, "fami_conv2d_bn_act_fwd: null pointer");
-  FAMI_CHECK_ARG(valid_dtype(d->dtype), "fami_conv2d_bn_act_fwd: bad dtype %d", d->dtype);
+  FAMI_CHECK_ARG(valid_dtype(d->dtype) || d->dtype == FAMI_TF32, "fami_conv2d_bn_act_fwd: bad dtype %d", d->dtype);
   FAMI_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "fami_conv2d_bn_act_fwd: bad shape");
   FAMI_CHECK_ARG(d->kh == d->kw && (d->kh == 1 || d->kh == 3), "fami_conv2d_bn_act_fwd: kernel %dx%d unsupported",
                  d->kh, d->kw);
@@ -163,7 +166,7 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
                  "fami_conv2d_bn_act_fwd: fp32-in/bf16-out is only supported for the stem convolution");
   if (d->om_groups != 0) {
     FAMI_CHECK_ARG(d->om_groups > 0 && d->om_groups % 4 == 0 && d->Cout == 27 * d->om_groups && d->out_dtype == FAMI_F32 &&
-                       is_half_dtype(d->dtype) && d->up == 1 && !residual && !d->stats && d->kh == 3 && d->stride == 1 &&
+                       is_tc_dtype(d->dtype) && d->up == 1 && !residual && !d->stats && d->kh == 3 && d->stride == 1 &&
                        d->pad == d->dil,
                    "fami_conv2d_bn_act_fwd: om_groups needs a 16-bit 3x3 stride-1 same conv with Cout = 27*G, fp32 output, "
                    "no residual / upsample / statistics");
@@ -174,10 +177,11 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
     FAMI_CHECK_ARG(conv_bf16_tc_supported(d), "fami_conv2d_bn_act_fwd: om_groups: shape not supported by the tensor path");
     return conv_bf16_tc_launch(d, x, w_packed, scale, shift, residual, y, stats_out, (cudaStream_t)stream);
   }
-  if (is_half_dtype(d->dtype)) {
+  if (is_tc_dtype(d->dtype)) {
     FAMI_CHECK_ARG(d->out_dtype == d->dtype || d->out_dtype == FAMI_F32,
-                   "fami_conv2d_bn_act_fwd: half-precision conv output must be the same half type or fp32");
-    FAMI_CHECK_ARG(conv_bf16_tc_supported(d), "fami_conv2d_bn_act_fwd: shape not supported by the bf16 tensor path");
+                   "fami_conv2d_bn_act_fwd: tensor-core conv output must be the input's storage type or fp32");
+    FAMI_CHECK_ARG(conv_bf16_tc_supported(d), "fami_conv2d_bn_act_fwd: shape not supported by the tensor-core path "
+                                              "(Cin multiple of 16 (16-bit) / 8 (tf32), 16-byte aligned pixel pitch)");
     static const bool halo_off = getenv("FAMI_DISABLE_HALO") != nullptr;
     if (!halo_off && !d->stats && conv_halo_supported(d))
       return conv_halo_launch(d, x, w_packed, scale, shift, residual, y, (cudaStream_t)stream);
@@ -428,6 +432,7 @@ int fami_argmax_hw(const void* hm, int dtype, int pitch, int32_t* idx_out, float
   return argmax_hw_launch(hm, dtype, pitch, idx_out, maxval_out, B, HW, J, (cudaStream_t)stream);
 }
 
+#ifdef FAMI_DEBUG_PROBES
 /* per-role timeline of CTA 0 of the last halo conv launched with FAMI_HALO_TRACE=1 (tools/trace_halo.py) */
 int fami_debug_read_trace(uint64_t* host_out, int n) {
   FAMI_CHECK_ARG(host_out && n != 0, "fami_debug_read_trace: bad arguments");
@@ -447,5 +452,12 @@ int fami_debug_umma_rowshift(const void* x_f16, const void* w_f16, float* out, i
   FAMI_CHECK_ARG(x_f16 && w_f16 && out, "fami_debug_umma_rowshift: null pointer");
   return debug_umma_rowshift_launch(x_f16, w_f16, out, R, shift, mode, (cudaStream_t)stream);
 }
+
+/* hardware probe: element conversion performed by a TMA load with a TFLOAT32 tensor map (tools/probe_tma_tf32.py) */
+int fami_debug_tma_tf32(const float* x, uint32_t* out_bits, int rows, int mode, void* stream) {
+  FAMI_CHECK_ARG(x && out_bits, "fami_debug_tma_tf32: null pointer");
+  return debug_tma_tf32_launch(x, out_bits, rows, mode, (cudaStream_t)stream);
+}
+#endif  /* FAMI_DEBUG_PROBES */
 
 }  // extern "C"

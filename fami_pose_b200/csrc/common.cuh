@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <atomic>
 #include <stdio.h>
 #include <string.h>
 
@@ -103,9 +104,24 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
-int num_sms();
+int num_sms();   // SM count of the CURRENT device (cached per device)
+
+// cudaFuncSetAttribute applies to the current device only: opt a kernel in to large dynamic shared memory once per
+// DEVICE (not once per process), so a single process driving several GPUs (nn.DataParallel, which the reference's
+// trainer uses) launches correctly on every one of them.  `mask` is a per-kernel static; racing callers at worst
+// repeat the (idempotent) driver call.
+template <typename K>
+static inline void set_max_smem_once(std::atomic<uint64_t>& mask, K kernel, int bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  if (mask.load(std::memory_order_acquire) & bit) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  mask.fetch_or(bit, std::memory_order_release);
+}
 
 static inline bool is_half_dtype(int dt) { return dt == FAMI_BF16 || dt == FAMI_F16; }
-static inline size_t dtype_size(int dt) { return dt == FAMI_F32 ? 4 : 2; }
+static inline bool is_tc_dtype(int dt) { return dt == FAMI_BF16 || dt == FAMI_F16 || dt == FAMI_TF32; }
+static inline size_t dtype_size(int dt) { return (dt == FAMI_F32 || dt == FAMI_TF32) ? 4 : 2; }
 
 }  // namespace fami

@@ -54,7 +54,6 @@ struct HaloParams {
   int out_pitch, res_pitch;
   int sA, sB, b_resident, acc_bufs, n_iss, acc_stride;
   uint32_t a_stage_bytes, b_tile_bytes, a_box_bytes;
-  uint32_t ab_format;
   int trace;
   int om_groups, om_tiles_x, om_tiles_y;   // > 0: y is the warp-blocked DCN offset|mask buffer
   int64_t om_tap_stride;
@@ -67,7 +66,7 @@ struct HaloParams {
 // The nine taps of one resident-weights channel chunk, issued by one warp for its M-tiles m = issuer, issuer + n_iss, ...
 // NK = 16-channel MMA steps per tap.  Everything but the descriptor increments is hoisted: at N <= 96 the issuing
 // thread's instruction stream, not the tensor pipe, sets the MMA rate.
-template <int NK>
+template <int NK, bool kTf32>
 __device__ __forceinline__ void halo_issue_taps(bool leader, uint32_t a_base, uint32_t b_lo, uint32_t b_step, uint32_t wp8,
                                                 uint32_t d8, uint32_t a_inc, uint32_t d_inc, uint32_t d0, uint32_t idesc,
                                                 int issuer, int NM, int n_iss) {
@@ -79,7 +78,7 @@ __device__ __forceinline__ void halo_issue_taps(bool leader, uint32_t a_base, ui
     for (int fs = 0; fs < 3; ++fs, a_tap += d8, b_lo += b_step) {
       uint32_t a_lo = a_tap, dcol = d0;
       for (int m = issuer; m < NM; m += n_iss, a_lo += a_inc, dcol += d_inc)
-        umma_ksteps<NK>(leader, dcol, a_lo, b_lo, idesc, (fr | fs) != 0);
+        umma_ksteps<NK, kTf32>(leader, dcol, a_lo, b_lo, idesc, (fr | fs) != 0);
     }
   }
 }
@@ -88,6 +87,8 @@ template <typename TH>
 __global__ void __launch_bounds__(kHThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int kKC = TcTraits<TH>::kKC;       // channels per 128-byte row: 64 (16-bit) / 32 (tf32)
+  constexpr bool kTf32 = TcTraits<TH>::kTf32;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int ksteps = 9 * p.cchunks;
   const int nB = p.b_resident ? ksteps : p.sB;
@@ -140,7 +141,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // all weights of this conv (single N tile) stay in shared memory for the whole kernel
         if (leader) mbar_arrive_expect_tx(fullB(0), (uint32_t)ksteps * p.b_tile_bytes);
         for (int ks = 0; ks < ksteps; ++ks)
-          if (leader) tma_tiled_2d(smem_u32(smemB + (size_t)ks * p.b_tile_bytes), &tmB, fullB(0), ks * 64, 0);
+          if (leader) tma_tiled_2d(smem_u32(smemB + (size_t)ks * p.b_tile_bytes), &tmB, fullB(0), ks * kKC, 0);
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
@@ -154,7 +155,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (leader) {
             trace(p.trace, 0, (tile - blockIdx.x) / gridDim.x, 0);
             mbar_arrive_expect_tx(fullA(sa), p.a_box_bytes);
-            tma_tiled_4d(smem_u32(smemA + (size_t)sa * p.a_stage_bytes), &tmA, fullA(sa), cc * 64, -p.d, y0 - p.d, img);
+            tma_tiled_4d(smem_u32(smemA + (size_t)sa * p.a_stage_bytes), &tmA, fullA(sa), cc * kKC, -p.d, y0 - p.d, img);
           }
           if (++sa == p.sA) { sa = 0; pa ^= 1u; }
           if (!p.b_resident) {
@@ -162,7 +163,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               mbar_wait(emptyB(sb), pb ^ 1u);
               if (leader) {
                 mbar_arrive_expect_tx(fullB(sb), p.b_tile_bytes);
-                tma_tiled_2d(smem_u32(smemB + (size_t)sb * p.b_tile_bytes), &tmB, fullB(sb), (tap * p.cchunks + cc) * 64,
+                tma_tiled_2d(smem_u32(smemB + (size_t)sb * p.b_tile_bytes), &tmB, fullB(sb), (tap * p.cchunks + cc) * kKC,
                              nt * p.BN);
               }
               if (++sb == p.sB) { sb = 0; pb ^= 1u; }
@@ -180,8 +181,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     {
       const bool leader = elect_one();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t idesc = (1u << 4) | (p.ab_format << 7) | (p.ab_format << 10) | ((uint32_t)(p.BN >> 3) << 17) |
-                             ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc = umma_idesc<TH>(p.BN);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -206,10 +206,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t d0 = d_tmem + (uint32_t)(issuer * p.acc_stride);
           const uint32_t b_lo0 = sw128_desc_lo(smem_u32(smemB));
           switch (p.last_kk) {
-            case 1: halo_issue_taps<1>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
-            case 2: halo_issue_taps<2>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
-            case 3: halo_issue_taps<3>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
-            default: halo_issue_taps<4>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
+            case 1: halo_issue_taps<1, kTf32>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
+            case 2: halo_issue_taps<2, kTf32>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
+            case 3: halo_issue_taps<3, kTf32>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
+            default: halo_issue_taps<4, kTf32>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
           }
           if (leader) umma_commit(emptyA(sa));
           if (++sa == p.sA) { sa = 0; pa ^= 1u; }
@@ -234,7 +234,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t b_lo = b_ring0 + (uint32_t)sb * b_step;
                 uint32_t a_lo = a_tap, dcol = d0;
                 for (int m = issuer; m < p.NM; m += p.n_iss, a_lo += a_inc, dcol += d_inc)
-                  umma_ksteps_n(nk, leader, dcol, a_lo, b_lo, idesc, accum);
+                  umma_ksteps_n<kTf32>(nk, leader, dcol, a_lo, b_lo, idesc, accum);
                 accum = true;
                 if (leader) umma_commit(emptyB(sb));
                 if (++sb == p.sB) { sb = 0; pb ^= 1u; }
@@ -272,7 +272,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint32_t a_inc = (uint32_t)p.n_iss * 1024u, d_inc = (uint32_t)(p.n_iss * p.acc_stride);
               if (p.trace & 8) b_lo = sw128_desc_lo(smem_u32(smemB));
               for (int m = issuer; m < p.NM; m += p.n_iss, a_lo += a_inc, dcol += d_inc)
-                umma_ksteps_n(nk, leader, dcol, a_lo, b_lo, idesc, acc_first);
+                umma_ksteps_n<kTf32>(nk, leader, dcol, a_lo, b_lo, idesc, acc_first);
               if (leader && tap < 8 && issuer == 0) trace(p.trace, 3, it, tap);
               if (!p.b_resident) {
                 if (leader) umma_commit(emptyB(sb));
@@ -298,8 +298,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     EpiArgs ea;
     // Lean pipelined epilogue (16-column groups, pitch 48 B: staging + two residual buffers per warp fill exactly the
     // 12 x 32 x 144 B allocation) whenever the output is a plain 16-bit NHWC tile; the generic routine otherwise.
-    const bool lean = epi_pipe_ok(p.BN, p.Cout, p.vec_ok, p.out_f32, 1, p.res != nullptr) && p.Cout == p.BN * p.n_tiles &&
-                      p.om_groups == 0 && !(p.trace & 16);
+    const bool lean = sizeof(TH) == 2 && epi_pipe_ok(p.BN, p.Cout, p.vec_ok, p.out_f32, 1, p.res != nullptr) &&
+                      p.Cout == p.BN * p.n_tiles && p.om_groups == 0 && !(p.trace & 16);
     const bool pf_on = lean && p.res != nullptr;
     const bool lean_nores = lean && p.res == nullptr;
     ea.spitch = lean ? epi_pipe_pitch(16) : epi_stage_pitch(p.BN, p.out_f32);
@@ -347,6 +347,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ob.G3 = 3 * p.om_groups; ob.tap_stride = p.om_tap_stride;
           if (!(p.trace & 2)) epilogue_rows_om_blocked(ea, t_addr, col_begin, col_end, valid, img, y0 + yy, xx, ob);
         } else if (pf_on) {
+         if constexpr (sizeof(TH) == 2) {
           // next unit of this warp: the next M-tile, or the first M-tile of this CTA's next tile
           bool nvalid = false, have_next = true;
           int npix = 0, nchb = ea.ch_base;
@@ -368,10 +369,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!(p.trace & 2))
             epilogue_rows_pipelined<TH>(ea, t_addr, col_begin, col_end, valid, pix, stage, rbuf[0], rbuf[1], lane, pf_sel, pf_have,
                                         have_next, nvalid, npix, nchb, 16);
+         }
         } else if (lean_nores) {
+         if constexpr (sizeof(TH) == 2) {
           if (!(p.trace & 2))
             epilogue_rows_pipelined<TH, false>(ea, t_addr, col_begin, col_end, valid, pix, stage, 0u, 0u, lane, pf_sel, pf_have, false,
                                                false, 0, 0, 16);
+         }
         } else if (!(p.trace & 2)) {
           epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix, stage, lane);
         }
@@ -402,7 +406,7 @@ constexpr size_t kSmemBudget = 220 * 1024;
 
 // Chooses the CTA tile: BH image rows (NM = ceil(BH*Wp/128) M-tiles).  Preference: double-buffered
 // accumulators, high fraction of useful MMA rows, weights resident if they fit.
-HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d) {
+HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d, int kKC) {
   HaloCfg best;
   best.ok = false;
   const int Wp = W + 2 * d;
@@ -410,7 +414,7 @@ HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d) {
   int n_tiles = (Cout + 255) / 256;
   int per = (Cout + n_tiles - 1) / n_tiles;
   int BN = ((per + 15) / 16) * 16;
-  const int cchunks = (Cin + 63) / 64;
+  const int cchunks = (Cin + kKC - 1) / kKC;
   const int ksteps = 9 * cchunks;
   double best_score = -1;
   static const int ast_env = getenv("FAMI_HALO_ACCSTRIDE") ? atoi(getenv("FAMI_HALO_ACCSTRIDE")) : 0;
@@ -470,14 +474,15 @@ HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d) {
 
 int conv_halo_supported(const fami_conv_desc* d) {
   if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != d->dil || d->up != 1) return 0;
-  if (d->Cin % 16 != 0 || d->in_pitch % 8 != 0) return 0;
+  const bool tf32 = d->dtype == FAMI_TF32;
+  if (tf32 ? (d->Cin % 8 != 0 || d->in_pitch % 4 != 0) : (d->Cin % 16 != 0 || d->in_pitch % 8 != 0)) return 0;
   if (d->dil < 1 || d->dil > 8) return 0;
   // Measured (tools/prof_conv.py, tools/time_conv_shape.py, N=160 fp16): the halo form wins when the weights stay
   // resident in shared memory (Cin <= 64: 48->48 90 us vs 225 us im2col) and when many input channels feed few
   // output channels (256->48: 395 vs 590 us, 192->48: 85 vs 91 us: each streamed 6 KB weight tile serves NM M-tiles);
   // 96->96 wins with double-buffered accumulators and A stages (72 vs 81 us); it loses for the wider square
   // classes whose weights must be re-streamed per CTA tile (192->192: 75 vs 51 us).
-  HaloCfg c = halo_cfg(d->H, d->W, d->Cin, d->Cout, d->dil);
+  HaloCfg c = halo_cfg(d->H, d->W, d->Cin, d->Cout, d->dil, tf32 ? 32 : 64);
   static const bool force = getenv("FAMI_HALO_FORCE") != nullptr;   // experiment: also take streamed-weights shapes
   return (c.ok && (force || c.b_resident || c.n_tiles > 1 || (c.BN <= 64 && c.cchunks >= 3) ||
                    (c.BN <= 96 && c.acc_bufs == 2 && c.sA == 2))) ? 1 : 0;
@@ -486,29 +491,34 @@ int conv_halo_supported(const fami_conv_desc* d) {
 int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
                      const void* res, void* y, cudaStream_t st) {
   FAMI_CHECK_ARG(load_driver_fns(), "cuTensorMapEncode* driver entry points unavailable");
-  HaloCfg c = halo_cfg(d->H, d->W, d->Cin, d->Cout, d->dil);
+  const bool tf32 = d->dtype == FAMI_TF32;
+  const int kKC = tf32 ? 32 : 64;
+  const cuuint64_t es = tf32 ? 4 : 2;
+  FAMI_CHECK_ARG(!tf32 || d->out_dtype == FAMI_F32 || d->out_dtype == FAMI_TF32, "conv_halo: tf32 convolutions write float");
+  HaloCfg c = halo_cfg(d->H, d->W, d->Cin, d->Cout, d->dil, kKC);
   FAMI_CHECK_ARG(c.ok, "conv_halo: no tile configuration fits");
-  const CUtensorMapDataType tm_dtype = d->dtype == FAMI_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType tm_dtype = tm_dtype_of(d->dtype);
+  const CUtensorMapDataType tm_wdtype = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : tm_dtype;   // weights are pre-rounded
   const int dl = d->dil, Wp = d->W + 2 * dl;
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-    cuuint64_t strides[3] = {(cuuint64_t)d->in_pitch * 2, (cuuint64_t)d->W * d->in_pitch * 2,
-                             (cuuint64_t)d->H * d->W * d->in_pitch * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)Wp, (cuuint32_t)(c.BH + 2 * dl), 1};
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_pitch * es, (cuuint64_t)d->W * d->in_pitch * es,
+                             (cuuint64_t)d->H * d->W * d->in_pitch * es};
+    cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)Wp, (cuuint32_t)(c.BH + 2 * dl), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = g_encode_tiled(&tmA, tm_dtype, 4, const_cast<void*>(x), dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FAMI_CHECK_ARG(r == CUDA_SUCCESS, "conv_halo: cuTensorMapEncodeTiled(A) failed (%d)", (int)r);
   }
-  const int Kp = 9 * c.cchunks * 64;
+  const int Kp = 9 * c.cchunks * kKC;
   {
     cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)c.CoutPad};
-    cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)c.BN};
+    cuuint64_t strides[1] = {(cuuint64_t)Kp * es};
+    cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)c.BN};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(&tmB, tm_dtype, 2, const_cast<void*>(w), dims, strides, box, estr,
+    CUresult r = g_encode_tiled(&tmB, tm_wdtype, 2, const_cast<void*>(w), dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FAMI_CHECK_ARG(r == CUDA_SUCCESS, "conv_halo: cuTensorMapEncodeTiled(B) failed (%d)", (int)r);
@@ -521,12 +531,12 @@ int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, cons
   p.n_tiles = c.n_tiles;
   p.total_tiles = d->N * p.tiles_per_img * c.n_tiles;
   p.cchunks = c.cchunks;
-  p.last_kk = (d->Cin - (c.cchunks - 1) * 64) / 16;
+  p.last_kk = (d->Cin - (c.cchunks - 1) * kKC) / (kKC / 4);
   p.Cout = d->Cout; p.BN = c.BN;
-  p.relu = d->relu; p.out_f32 = d->out_dtype == FAMI_F32;
+  p.relu = d->relu; p.out_f32 = d->out_dtype == FAMI_F32 || d->out_dtype == FAMI_TF32;
   const size_t osz = p.out_f32 ? 4 : 2;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((d->out_pitch * osz) % 16 == 0) &&
-             (!res || (((reinterpret_cast<uintptr_t>(res) & 15) == 0) && (d->res_pitch % 8 == 0)));
+             (!res || (((reinterpret_cast<uintptr_t>(res) & 15) == 0) && ((d->res_pitch * es) % 16 == 0)));
   p.out_pitch = d->out_pitch; p.res_pitch = d->res_pitch;
   p.sA = c.sA; p.sB = c.sB; p.b_resident = c.b_resident; p.acc_bufs = c.acc_bufs; p.acc_stride = c.acc_stride;
   p.n_iss = c.NM < kMmaWarps ? c.NM : kMmaWarps;
@@ -534,7 +544,6 @@ int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, cons
   p.a_stage_bytes = (uint32_t)c.HR * 128u;
   p.b_tile_bytes = (uint32_t)c.BN * 128u;
   p.a_box_bytes = (uint32_t)((c.BH + 2 * dl) * Wp) * 128u;
-  p.ab_format = d->dtype == FAMI_F16 ? 0u : 1u;
   p.scale = scale; p.shift = shift; p.res = res; p.y = y;
   p.om_groups = d->om_groups;
   p.om_tiles_x = (d->W + 7) / 8; p.om_tiles_y = (d->H + 15) / 16;
@@ -542,19 +551,20 @@ int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, cons
   static const bool trace_on = getenv("FAMI_HALO_TRACE") != nullptr;
   p.trace = trace_on ? atoi(getenv("FAMI_HALO_TRACE")) : 0;
 
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(conv_halo_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_h{0}, attr_b{0}, attr_t{0};
   int grid = p.total_tiles;
   const int sms = num_sms();
   if (grid > sms) grid = sms;
-  if (d->dtype == FAMI_F16)
+  if (tf32) {
+    set_max_smem_once(attr_t, conv_halo_kernel<float>, 227 * 1024);
+    conv_halo_kernel<float><<<grid, kHThreads, c.smem, st>>>(tmA, tmB, p);
+  } else if (d->dtype == FAMI_F16) {
+    set_max_smem_once(attr_h, conv_halo_kernel<__half>, 227 * 1024);
     conv_halo_kernel<__half><<<grid, kHThreads, c.smem, st>>>(tmA, tmB, p);
-  else
+  } else {
+    set_max_smem_once(attr_b, conv_halo_kernel<__nv_bfloat16>, 227 * 1024);
     conv_halo_kernel<__nv_bfloat16><<<grid, kHThreads, c.smem, st>>>(tmA, tmB, p);
+  }
   FAMI_CHECK_LAUNCH("conv_halo_kernel");
   return 0;
 }

@@ -19,8 +19,7 @@ namespace fami {
 namespace {
 
 constexpr int kBM = 128;
-constexpr int kKC = 64;                 // channels per K chunk (128 B of bf16 = one swizzle row)
-constexpr int kABytes = kBM * kKC * 2;  // 16 KB
+constexpr int kABytes = kBM * 128;      // 16 KB: 128 pixels x one 128-byte swizzle row (TcTraits<TH>::kKC channels)
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kAccCols = 256;           // TMEM columns per accumulator buffer
 
@@ -39,13 +38,14 @@ struct TcParams {
   const float* shift;
   const void* res;   // TH
   void* y;
-  uint32_t ab_format;  // instruction-descriptor operand format: 0 = F16, 1 = BF16
 };
 
 template <typename TH>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int kKC = TcTraits<TH>::kKC;
+  constexpr bool kTf32 = TcTraits<TH>::kTf32;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int stages = p.stages;
   const uint32_t b_bytes = (uint32_t)p.BN * 128u;
@@ -122,7 +122,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool leader = elect_one();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       // instruction descriptor: D=f32, A=B=f16|bf16, both K-major, M=128, N=BN
-      const uint32_t idesc = (1u << 4) | (p.ab_format << 7) | (p.ab_format << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+      const uint32_t idesc = umma_idesc<TH>(p.BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -145,7 +145,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(full_cur, phase);
             tc_fence_after();
             const int nk = (cc == p.cchunks - 1) ? p.last_kk : 4;
-            umma_ksteps_n(nk, leader, d_tmem, a_lo, a_lo + b_off, idesc, accum);
+            umma_ksteps_n<kTf32>(nk, leader, d_tmem, a_lo, a_lo + b_off, idesc, accum);
             accum = true;
             if (leader) umma_commit(full_cur + empty_off);   // frees the smem slot once the MMAs above have read it
             a_lo += stage_step;
@@ -205,7 +205,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ob.base = reinterpret_cast<float*>(p.y); ob.tiles_x = p.om_tiles_x; ob.tiles_y = p.om_tiles_y;
         ob.G3 = 3 * p.om_groups; ob.tap_stride = p.om_tap_stride;
         epilogue_rows_om_blocked(ea, t_addr, col_begin, col_end, valid, n, yo, xo, ob);
-      } else if (p.pipe) {
+      } else if (sizeof(TH) == 2 && p.pipe) {
+       if constexpr (sizeof(TH) == 2) {
         const int ntile = tile + gridDim.x;
         const bool have_next = ntile < total_tiles;
         const int nmt = ntile / p.n_tiles, nnt = ntile - nmt * p.n_tiles;
@@ -217,6 +218,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else
           epilogue_rows_pipelined<TH, false>(ea, t_addr, col_begin, col_end, valid, pix0, pstage, 0u, 0u, lane, psel, pprimed, false,
                                              false, 0, 0);
+       }
       } else {
         epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix0, stage, lane, rbuf, up_fast);
       }
@@ -239,7 +241,7 @@ struct TileCfg {
   int BN, n_tiles, CoutPad, cchunks, Kp;
 };
 
-TileCfg tile_cfg(int Cout, int Cin, int kh, int kw) {
+TileCfg tile_cfg(int Cout, int Cin, int kh, int kw, int kKC) {
   TileCfg t;
   t.n_tiles = (Cout + 255) / 256;
   int per = (Cout + t.n_tiles - 1) / t.n_tiles;
@@ -252,16 +254,19 @@ TileCfg tile_cfg(int Cout, int Cin, int kh, int kw) {
 
 }  // namespace
 
+static inline int kc_of(int dtype) { return dtype == FAMI_TF32 ? 32 : 64; }
+
 int conv_bf16_tc_supported(const fami_conv_desc* d) {
-  if (d->Cin % 16 != 0 || d->in_pitch % 8 != 0) return 0;
+  // K-steps of 32 bytes (16 halves / 8 floats); TMA needs 16-byte pixel strides
+  if (d->dtype == FAMI_TF32 ? (d->Cin % 8 != 0 || d->in_pitch % 4 != 0) : (d->Cin % 16 != 0 || d->in_pitch % 8 != 0)) return 0;
   if (d->kh != d->kw || (d->kh != 1 && d->kh != 3)) return 0;
   if (d->stride < 1 || d->stride > 8) return 0;
   if (d->pad > 127 || (d->kh - 1) * d->dil - d->pad > 128) return 0;
   return 1;
 }
 
-int64_t pack_w_bf16_elems(int Cout, int Cin, int kh, int kw) {
-  TileCfg t = tile_cfg(Cout, Cin, kh, kw);
+int64_t pack_w_bf16_elems(int Cout, int Cin, int kh, int kw, int dtype) {
+  TileCfg t = tile_cfg(Cout, Cin, kh, kw, kc_of(dtype));
   return (int64_t)t.CoutPad * t.Kp;
 }
 
@@ -269,6 +274,7 @@ int64_t pack_w_bf16_elems(int Cout, int Cin, int kh, int kw) {
 template <typename TH>
 __global__ void pack_w_bf16_kernel(const float* __restrict__ w, TH* __restrict__ out, int Cout, int Cin,
                                    int taps, int cchunks, int CoutPad) {
+  constexpr int kKC = TcTraits<TH>::kKC;
   const int Kp = taps * cchunks * kKC;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)CoutPad * Kp) return;
@@ -276,13 +282,16 @@ __global__ void pack_w_bf16_kernel(const float* __restrict__ w, TH* __restrict__
   int tap = k / (cchunks * kKC), c = k - tap * cchunks * kKC;
   float v = 0.f;
   if (o < Cout && c < Cin) v = w[((int64_t)o * Cin + c) * taps + tap];
-  out[i] = from_f<TH>(v);
+  if constexpr (TcTraits<TH>::kTf32) out[i] = f32_to_tf32_rna(v);   // the tensor core would truncate: round here instead
+  else out[i] = from_f<TH>(v);
 }
 
 int pack_w_bf16_launch(const float* w, void* out, int Cout, int Cin, int kh, int kw, int dtype, cudaStream_t st) {
-  TileCfg t = tile_cfg(Cout, Cin, kh, kw);
+  TileCfg t = tile_cfg(Cout, Cin, kh, kw, kc_of(dtype));
   int64_t tot = (int64_t)t.CoutPad * t.Kp;
-  if (dtype == FAMI_F16)
+  if (dtype == FAMI_TF32)
+    pack_w_bf16_kernel<float><<<cdiv(tot, 256), 256, 0, st>>>(w, (float*)out, Cout, Cin, kh * kw, t.cchunks, t.CoutPad);
+  else if (dtype == FAMI_F16)
     pack_w_bf16_kernel<__half><<<cdiv(tot, 256), 256, 0, st>>>(w, (__half*)out, Cout, Cin, kh * kw, t.cchunks, t.CoutPad);
   else
     pack_w_bf16_kernel<__nv_bfloat16><<<cdiv(tot, 256), 256, 0, st>>>(w, (__nv_bfloat16*)out, Cout, Cin, kh * kw, t.cchunks, t.CoutPad);
@@ -298,15 +307,20 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   FAMI_CHECK_ARG(load_driver_fns(), "cuTensorMapEncode* driver entry points unavailable");
   FAMI_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
                  "bf16 tensor-core conv: x / w must be 16-byte aligned");
-  const int out_f32 = d->out_dtype == FAMI_F32;
-  TileCfg t = tile_cfg(d->Cout, d->Cin, d->kh, d->kw);
+  const int out_f32 = d->out_dtype == FAMI_F32 || d->out_dtype == FAMI_TF32;
+  const bool tf32 = d->dtype == FAMI_TF32;
+  FAMI_CHECK_ARG(!tf32 || out_f32, "tf32 tensor-core conv: the output is float");
+  const int kKC = kc_of(d->dtype);
+  const cuuint64_t es = tf32 ? 4 : 2;     // element size
+  TileCfg t = tile_cfg(d->Cout, d->Cin, d->kh, d->kw, kKC);
 
   CUtensorMap tmA, tmB;
-  const CUtensorMapDataType tm_dtype = d->dtype == FAMI_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType tm_dtype = tm_dtype_of(d->dtype);
+  const CUtensorMapDataType tm_wdtype = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : tm_dtype;   // weights are pre-rounded
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-    cuuint64_t strides[3] = {(cuuint64_t)d->in_pitch * 2, (cuuint64_t)d->W * d->in_pitch * 2,
-                             (cuuint64_t)d->H * d->W * d->in_pitch * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_pitch * es, (cuuint64_t)d->W * d->in_pitch * es,
+                             (cuuint64_t)d->H * d->W * d->in_pitch * es};
     int lower[2] = {-d->pad, -d->pad};
     int upper[2] = {d->pad - (d->kw - 1) * d->dil, d->pad - (d->kh - 1) * d->dil};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
@@ -317,10 +331,10 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)t.Kp, (cuuint64_t)t.CoutPad};
-    cuuint64_t strides[1] = {(cuuint64_t)t.Kp * 2};
-    cuuint32_t box[2] = {kKC, (cuuint32_t)t.BN};
+    cuuint64_t strides[1] = {(cuuint64_t)t.Kp * es};
+    cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)t.BN};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(&tmB, tm_dtype, 2, const_cast<void*>(w), dims, strides, box,
+    CUresult r = g_encode_tiled(&tmB, tm_wdtype, 2, const_cast<void*>(w), dims, strides, box,
                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FAMI_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -332,22 +346,21 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   p.Ho = d->Ho; p.Wo = d->Wo; p.HoWo = d->Ho * d->Wo;
   p.stride = d->stride; p.pad = d->pad; p.dil = d->dil; p.kw = d->kw; p.taps = d->kh * d->kw;
   p.cchunks = t.cchunks;
-  p.last_kk = (d->Cin - (t.cchunks - 1) * kKC) / 16;
+  p.last_kk = (d->Cin - (t.cchunks - 1) * kKC) / (kKC / 4);   // 32-byte K-steps in the last channel chunk
   p.Cout = d->Cout; p.BN = t.BN; p.n_tiles = t.n_tiles; p.m_tiles = (p.M + kBM - 1) / kBM;
   p.up = d->up; p.relu = d->relu;
   p.out_pitch = d->out_pitch; p.res_pitch = d->res_pitch;
   p.out_f32 = out_f32;
   const size_t osz = out_f32 ? 4 : 2;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((d->out_pitch * osz) % 16 == 0) &&
-             (!res || (((reinterpret_cast<uintptr_t>(res) & 15) == 0) && (d->res_pitch % 8 == 0)));
+             (!res || (((reinterpret_cast<uintptr_t>(res) & 15) == 0) && ((d->res_pitch * es) % 16 == 0)));
   p.scale = scale; p.shift = shift; p.res = res; p.y = y;
   p.om_groups = d->om_groups;
   p.om_tiles_x = (d->Wo + 7) / 8; p.om_tiles_y = (d->Ho + 15) / 16;
   p.om_tap_stride = (int64_t)d->N * p.om_tiles_x * p.om_tiles_y * 4 * (3 * (d->om_groups / 4)) * 128;
-  p.ab_format = d->dtype == FAMI_F16 ? 0u : 1u;
 
   const int stage_bytes = kABytes + t.BN * 128;
-  p.pipe = (d->om_groups == 0 && epi_pipe_ok(t.BN, d->Cout, p.vec_ok, out_f32, d->up, res != nullptr) && d->Cout == t.BN * t.n_tiles &&
+  p.pipe = (!tf32 && d->om_groups == 0 && epi_pipe_ok(t.BN, d->Cout, p.vec_ok, out_f32, d->up, res != nullptr) && d->Cout == t.BN * t.n_tiles &&
             getenv("FAMI_NO_EPI_PIPE") == nullptr) ? 1 : 0;
   const size_t epi_bytes = p.pipe ? (size_t)kEpiWarps * 32 * (res ? 3 : 1) * epi_pipe_pitch() : (size_t)kEpiWarps * 32 * (128 + 16);
   int stages = (int)((228000 - (size_t)t.CoutPad * 8 - epi_bytes) / stage_bytes);   // all the shared memory there is: the kernel is bound by bytes in flight
@@ -356,219 +369,21 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 4) * 8 + 64 +
                       (size_t)t.CoutPad * 8 + epi_bytes;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_h{0}, attr_b{0}, attr_t{0};
   int grid = p.m_tiles * p.n_tiles;
   const int sms = num_sms();
   if (grid > sms) grid = sms;
-  if (d->dtype == FAMI_F16)
+  if (tf32) {
+    set_max_smem_once(attr_t, conv_tc_kernel<float>, 227 * 1024);
+    conv_tc_kernel<float><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  } else if (d->dtype == FAMI_F16) {
+    set_max_smem_once(attr_h, conv_tc_kernel<__half>, 227 * 1024);
     conv_tc_kernel<__half><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
-  else
+  } else {
+    set_max_smem_once(attr_b, conv_tc_kernel<__nv_bfloat16>, 227 * 1024);
     conv_tc_kernel<__nv_bfloat16><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  }
   FAMI_CHECK_LAUNCH("conv_tc_kernel");
-  return 0;
-}
-
-
-// ------------------------------------------------------------------------------------------------
-// Hardware probe (test infrastructure): does a K-major SWIZZLE_128B UMMA descriptor whose start
-// address is shifted by `shift` 128-byte rows inside a TMA-written tile address rows
-// [shift, shift+128)?  mode 0: base_offset field = 0; mode 1: base_offset = (addr >> 7) & 7.
-// x: f16 [R][64], w: f16 [16][64], out: f32 [128][16] = x[shift:shift+128] @ w^T.
-// ------------------------------------------------------------------------------------------------
-namespace {
-__global__ void __launch_bounds__(128, 1)
-umma_rowshift_probe(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, float* out,
-                    int R, int shift, int mode) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sX = smem;                    // R rows x 128 B (R multiple of 8)
-  uint8_t* sW = smem + (size_t)R * 128;  // 16 rows x 128 B
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 16 * 128);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  const uint32_t bar_load = smem_u32(bars), bar_mma = smem_u32(bars + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    mbar_init(bar_load, 1);
-    mbar_init(bar_mma, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(bar_load, (uint32_t)(R * 128 + 16 * 128));
-    for (int r0 = 0; r0 < R; r0 += 8) tma_tiled_2d(smem_u32(sX + (size_t)r0 * 128), &tmX, bar_load, 0, r0);
-    tma_tiled_2d(smem_u32(sW), &tmW, bar_load, 0, 0);
-    mbar_wait(bar_load, 0);
-    tc_fence_after();
-    const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t a_addr = smem_u32(sX) + (uint32_t)shift * 128u;
-    uint64_t adesc = make_sw128_desc(a_addr);
-    if (mode == 1) adesc |= (uint64_t)((a_addr >> 7) & 7u) << 49;
-    const uint64_t bdesc = make_sw128_desc(smem_u32(sW));
-    for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k ? 1u : 0u);
-    umma_commit(bar_mma);
-  }
-  mbar_wait(bar_mma, 0);
-  tc_fence_after();
-  uint32_t v[16];
-  tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16), v);
-  tmem_ld_wait();
-  const int row = warp * 32 + lane;
-  for (int j = 0; j < 16; ++j) out[row * 16 + j] = __uint_as_float(v[j]);
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");
-  }
-}
-}  // namespace
-
-int debug_umma_rowshift_launch(const void* x, const void* w, float* out, int R, int shift, int mode, cudaStream_t st) {
-  FAMI_CHECK_ARG(load_driver_fns(), "driver entry points unavailable");
-  FAMI_CHECK_ARG(R % 8 == 0 && R >= 128 + shift + 8 && R <= 1024, "bad R");
-  CUtensorMap tmX, tmW;
-  {
-    cuuint64_t dims[2] = {64, (cuuint64_t)R};
-    cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, 8};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    FAMI_CHECK_ARG(r == CUDA_SUCCESS, "encode X failed %d", (int)r);
-  }
-  {
-    cuuint64_t dims[2] = {64, 16};
-    cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, 16};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    FAMI_CHECK_ARG(r == CUDA_SUCCESS, "encode W failed %d", (int)r);
-  }
-  size_t smem = (size_t)R * 128 + 16 * 128 + 1024 + 64;
-  cudaFuncSetAttribute(umma_rowshift_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  umma_rowshift_probe<<<1, 128, smem, st>>>(tmX, tmW, out, R, shift, mode);
-  FAMI_CHECK_LAUNCH("umma_rowshift_probe");
-  return 0;
-}
-
-
-// ------------------------------------------------------------------------------------------------
-// Hardware probe: back-to-back tcgen05.mma throughput (M=128, K=16, f16) as a function of N and of
-// how the issuing thread builds its descriptors.  out[0] = clock cycles for `iters` MMAs (clock64 around
-// issue + final commit wait), out[1] = cycles for the issue loop alone.
-// variant 0: constant descriptors; 1: descriptors recomputed per MMA from a rotating row shift (as
-// the halo conv does); 2: as 0 but 4 different accumulator column offsets round-robin.
-// ------------------------------------------------------------------------------------------------
-namespace {
-__global__ void __launch_bounds__(512, 1) umma_rate_probe(long long* out, int N, int iters, int variant) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                  // 1024 rows x 128 B
-  uint8_t* sB = smem + 1024 * 128;     // 256 rows x 128 B
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 256 * 128);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  const uint32_t bar_mma = smem_u32(bars);
-  for (int i = threadIdx.x; i < (1024 + 256) * 128 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // 1.0h
-  const int warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
-    mbar_init(bar_mma, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  asm volatile("fence.proxy.async;" ::: "memory");
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (warp == 0) {
-    // warp-uniform control flow; a single elected lane issues (variant >= 3) or lane 0 in divergent code
-    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-    const uint64_t adesc0 = make_sw128_desc(a0), bdesc0 = make_sw128_desc(b0);
-    long long t0 = clock64(), t1 = 0;
-    if (variant >= 3) {
-      const bool leader = elect_one();
-      for (int i = 0; i < iters; ++i) {
-        uint64_t ad = adesc0, bd = bdesc0;
-        uint32_t dt = tm;
-        if (variant >= 6) {
-          // mimic the halo conv issue pattern: tap -> m (3 accumulators) -> k (3 K-steps)
-          const int k = i % 3, m = (i / 3) % 3, tap = (i / 9) % 9;
-          const int fr = tap / 3, fs = tap - fr * 3;
-          ad = make_sw128_desc(a0 + (uint32_t)(m * 128 + fr * 74 + fs) * 128u) + (uint64_t)(2 * k);
-          bd = make_sw128_desc(b0 + (uint32_t)(variant == 8 ? 0 : tap) * (uint32_t)N * 128u % (256u * 128u)) + (uint64_t)(2 * k);
-          dt = tm + (uint32_t)(m * (variant == 7 ? 64 : N));
-        }
-        if (variant == 4) {
-          const uint32_t shift = (uint32_t)((i * 37) & 511);
-          ad = make_sw128_desc(a0 + shift * 128u) + (uint64_t)(2 * (i & 3));
-          bd = bdesc0 + (uint64_t)(2 * (i & 3));
-        }
-        if (variant == 5) dt = tm + (uint32_t)((i & 1) * 256);
-        if (leader) umma_bf16(dt, ad, bd, idesc, i > 1 ? 1u : 0u);
-      }
-      t1 = clock64();
-      if (leader) umma_commit(bar_mma);
-    } else if (threadIdx.x == 0) {
-      for (int i = 0; i < iters; ++i) {
-        if (variant == 1) {
-          const uint32_t shift = (uint32_t)((i * 37) & 511);
-          const uint64_t ad = make_sw128_desc(a0 + shift * 128u) + (uint64_t)(2 * (i & 3));
-          umma_bf16(tmem_base, ad, bdesc0 + (uint64_t)(2 * (i & 3)), idesc, i ? 1u : 0u);
-        } else if (variant == 2) {
-          umma_bf16(tmem_base + (uint32_t)((i & 1) * 256), adesc0, bdesc0, idesc, i > 1 ? 1u : 0u);
-        } else {
-          umma_bf16(tmem_base, adesc0, bdesc0, idesc, i ? 1u : 0u);
-        }
-      }
-      t1 = clock64();
-      umma_commit(bar_mma);
-    }
-    __syncwarp();
-    mbar_wait(bar_mma, 0);
-    long long t2 = clock64();
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-      out[0] = t2 - t0;
-      out[1] = t1 - t0;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
-}
-}  // namespace
-
-int debug_umma_rate_launch(long long* out, int N, int iters, int variant, cudaStream_t st) {
-  FAMI_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && iters > 0, "bad N/iters");
-  size_t smem = (size_t)(1024 + 256) * 128 + 1024 + 64;
-  cudaFuncSetAttribute(umma_rate_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  const int grid = (variant % 200) >= 100 ? 148 : 1;   // variant + 100: all SMs run the probe concurrently (CTA 0 reports)
-  const int threads = variant >= 200 ? 512 : 128;      // variant + 200: 15 more warps spinning on the completion barrier
-  umma_rate_probe<<<grid, threads, smem, st>>>(out, N, iters, variant % 100);
-  FAMI_CHECK_LAUNCH("umma_rate_probe");
   return 0;
 }
 

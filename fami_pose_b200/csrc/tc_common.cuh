@@ -1,6 +1,7 @@
 // Shared tcgen05 / TMA / mbarrier helpers for the tensor-core kernels (sm_100a inline PTX).
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -75,36 +76,69 @@ __device__ __forceinline__ void tma_tiled_4d(uint32_t dst, const CUtensorMap* tm
 constexpr uint32_t kSw128DescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO=1024, version 1, SWIZZLE_128B
 __device__ __forceinline__ uint32_t sw128_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 
+// Operand traits of the tensor-core kernels, keyed on the STORAGE type of the activations:
+//   __half / __nv_bfloat16 -> tcgen05.mma.kind::f16 (K = 16 per instruction, 64 channels per 128-byte swizzle row)
+//   float                  -> tcgen05.mma.kind::tf32 (K = 8 per instruction, 32 channels per 128-byte row; the tensor
+//                             core reads the upper 19 bits of each fp32 operand: the "tf32" arm = fp32 storage, TF32
+//                             multiplicands, fp32 accumulation -- what cuDNN does for the reference's fp32 convs on a GPU)
+// A K-step is 32 bytes of the row in both cases, so descriptor arithmetic is identical.
+template <typename TH> struct TcTraits;
+template <> struct TcTraits<__half> { static constexpr int kKC = 64; static constexpr uint32_t kFmt = 0u; static constexpr bool kTf32 = false; };
+template <> struct TcTraits<__nv_bfloat16> { static constexpr int kKC = 64; static constexpr uint32_t kFmt = 1u; static constexpr bool kTf32 = false; };
+template <> struct TcTraits<float> { static constexpr int kKC = 32; static constexpr uint32_t kFmt = 2u; static constexpr bool kTf32 = true; };
+// instruction descriptor: D = f32, A / B formats from the traits, both K-major, M = 128, N = BN
+template <typename TH> __device__ __forceinline__ uint32_t umma_idesc(int BN) {
+  return (1u << 4) | (TcTraits<TH>::kFmt << 7) | (TcTraits<TH>::kFmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+template <bool kTf32 = false>
 __device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool accumulate) {
   const uint64_t ad = ((uint64_t)kSw128DescHi << 32) | a_lo;
   const uint64_t bd = ((uint64_t)kSw128DescHi << 32) | b_lo;
-  if (accumulate) {
-    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                 ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc) : "memory");
+  if constexpr (kTf32) {
+    if (accumulate) {
+      asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                   ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc) : "memory");
+    } else {
+      asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                   ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc) : "memory");
+    }
   } else {
-    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                 ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc) : "memory");
+    if (accumulate) {
+      asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                   ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc) : "memory");
+    } else {
+      asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                   ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc) : "memory");
+    }
   }
 }
-// NK K-steps (16 elements = 32 B = +2 in the descriptor address field each) of one (A rows, B tile) pair
-template <int NK>
+// NK K-steps (32 B of the 128-byte row = +2 in the descriptor address field each) of one (A rows, B tile) pair
+template <int NK, bool kTf32 = false>
 __device__ __forceinline__ void umma_ksteps(bool leader, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
                                             bool first_accumulates) {
   if (leader) {
-    if (first_accumulates) umma_f16_lo(tmem_d, a_lo, b_lo, idesc, true);
-    else umma_f16_lo(tmem_d, a_lo, b_lo, idesc, false);
+    if (first_accumulates) umma_f16_lo<kTf32>(tmem_d, a_lo, b_lo, idesc, true);
+    else umma_f16_lo<kTf32>(tmem_d, a_lo, b_lo, idesc, false);
 #pragma unroll
-    for (int k = 1; k < NK; ++k) umma_f16_lo(tmem_d, a_lo + 2u * k, b_lo + 2u * k, idesc, true);
+    for (int k = 1; k < NK; ++k) umma_f16_lo<kTf32>(tmem_d, a_lo + 2u * k, b_lo + 2u * k, idesc, true);
   }
 }
+template <bool kTf32 = false>
 __device__ __forceinline__ void umma_ksteps_n(int nk, bool leader, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
                                               uint32_t idesc, bool first_accumulates) {
   switch (nk) {
-    case 1: umma_ksteps<1>(leader, tmem_d, a_lo, b_lo, idesc, first_accumulates); break;
-    case 2: umma_ksteps<2>(leader, tmem_d, a_lo, b_lo, idesc, first_accumulates); break;
-    case 3: umma_ksteps<3>(leader, tmem_d, a_lo, b_lo, idesc, first_accumulates); break;
-    default: umma_ksteps<4>(leader, tmem_d, a_lo, b_lo, idesc, first_accumulates); break;
+    case 1: umma_ksteps<1, kTf32>(leader, tmem_d, a_lo, b_lo, idesc, first_accumulates); break;
+    case 2: umma_ksteps<2, kTf32>(leader, tmem_d, a_lo, b_lo, idesc, first_accumulates); break;
+    case 3: umma_ksteps<3, kTf32>(leader, tmem_d, a_lo, b_lo, idesc, first_accumulates); break;
+    default: umma_ksteps<4, kTf32>(leader, tmem_d, a_lo, b_lo, idesc, first_accumulates); break;
   }
+}
+// round-to-nearest (ties away) fp32 -> tf32, result as an fp32 bit pattern with the low 13 mantissa bits zero
+__device__ __forceinline__ float f32_to_tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
 }
 
 // explicit shared-space accesses with 32-bit addresses: pointers derived from the manually aligned dynamic
@@ -288,6 +322,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
   // own residual and is stored; the residual of replica i+1 is in flight (cp.async into the other of two buffers
   // `rbuf`, `rbuf + 32*spitch`) while replica i is processed.  r_ready == -1 selects it (the caller guarantees the
   // two buffers exist).
+  if constexpr (sizeof(TH) == 2)
   if (r_ready == -1 && a.up > 1 && a.res && !a.out_f32 && col_end - col_begin == 16 && a.vec_ok &&
       a.ch_base + col_end <= a.Cout) {
     const int chg = a.ch_base + col_begin;
@@ -370,7 +405,9 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
     const int gc = (col_end - g0 < gmax) ? (col_end - g0) : gmax;
     const int chg = a.ch_base + g0;
     if (chg >= a.Cout) break;   // warp-uniform
-    const bool grp_vec = a.vec_ok && (chg + gc <= a.Cout) && !(a.res && a.out_f32);
+    // 16-bit residual with fp32 output has no common staging geometry (heatmap convs never carry a residual);
+    // fp32 storage (TH = float, the tf32 arm) stages residual and output with the same 4-byte elements
+    const bool grp_vec = a.vec_ok && (chg + gc <= a.Cout) && !(a.res && a.out_f32 && sizeof(TH) == 2);
     // 16-byte pieces per row, mapped with power-of-two lanes per row (no divisions)
     const int ppr = (gc * esz) >> 4;
     const int lg = ppr <= 2 ? 1 : (ppr <= 4 ? 2 : 3);
@@ -427,14 +464,22 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
           }
           if (grp_vec) {
             if (a.res) {
-              const uint4 r0 = lds128(res_row + (uint32_t)(c0 * 2));
-              const uint4 r1 = lds128(res_row + (uint32_t)(c0 * 2 + 16));
-              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+              if constexpr (sizeof(TH) == 4) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 t = h2_to_f2<TH>(rw[j]);
-                o[2 * j] += t.x;
-                o[2 * j + 1] += t.y;
+                for (int j = 0; j < 4; ++j) {
+                  const float4 t = lds128f(res_row + (uint32_t)(c0 * 4 + 16 * j));
+                  o[4 * j] += t.x; o[4 * j + 1] += t.y; o[4 * j + 2] += t.z; o[4 * j + 3] += t.w;
+                }
+              } else {
+                const uint4 r0 = lds128(res_row + (uint32_t)(c0 * 2));
+                const uint4 r1 = lds128(res_row + (uint32_t)(c0 * 2 + 16));
+                const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float2 t = h2_to_f2<TH>(rw[j]);
+                  o[2 * j] += t.x;
+                  o[2 * j + 1] += t.y;
+                }
               }
             }
             if (a.relu) {
@@ -445,7 +490,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 sts128f(my_row + (uint32_t)(c0 * 4 + 16 * j), make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
-            } else {
+            } else if constexpr (sizeof(TH) == 2) {
               uint32_t w[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) w[j] = f2_to_h2<TH>(o[2 * j], o[2 * j + 1]);
@@ -665,6 +710,18 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// tensor-map element type of an activation operand.  FAMI_TF32: the TMA unit converts fp32 -> tf32 while it copies
+// (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32; round-to-nearest measured by tools/probe_tma_tf32.py), so activations stay
+// full fp32 in HBM -- the residual stream keeps all 24 bits -- and only the multiplicand is rounded, as cuDNN's
+// TF32 convolutions do.  FAMI_TMA_TF32=0 selects a plain FLOAT32 copy (the tensor core then truncates).
+inline CUtensorMapDataType tm_dtype_of(int dtype) {
+  if (dtype == FAMI_TF32) {
+    static const bool plain = getenv("FAMI_TMA_TF32") != nullptr && atoi(getenv("FAMI_TMA_TF32")) == 0;
+    return plain ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+  }
+  return dtype == FAMI_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+}
 
 inline EncodeIm2colFn g_encode_im2col = nullptr;
 inline EncodeTiledFn g_encode_tiled = nullptr;

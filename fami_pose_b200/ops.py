@@ -11,18 +11,22 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import BF16, F16, F32, ConvDesc, DcnDesc
+from ._lib import BF16, F16, F32, TF32, ConvDesc, DcnDesc
 
 _PRECISION = "fp32"
 
 
-_DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
+_DTYPES = {"fp32": torch.float32, "tf32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
 
 
 def set_precision(p):
-    """'fp32': exact-fp32 SIMT kernels (1e-3 parity arm).  'fp16' / 'bf16': tcgen05 tensor-core arm
-    with 16-bit activations (fp32 accumulation, fp32 offsets/masks/heatmaps); fp16 carries 3 more
-    mantissa bits than bf16 at the same tensor-core rate and is the default tensor arm."""
+    """'fp32': exact-fp32 SIMT kernels (bit-for-bit fp32 FMA arithmetic).
+    'tf32': fp32 STORAGE everywhere (activations, residual stream, offsets, heatmaps) with every convolution on
+    tcgen05.mma.kind::tf32 -- multiplicands rounded to TF32 (10-bit mantissa; weights at pack time, activations by
+    the TMA load), fp32 accumulation.  This is the arithmetic the reference's fp32 nn.Conv2d gets from cuDNN on a
+    GPU (torch.backends.cudnn.allow_tf32 = True by default); it meets the fp32 tier's 1e-3 tolerance.
+    'fp16' / 'bf16': tcgen05 tensor-core arm with 16-bit activations (fp32 accumulation, fp32
+    offsets/masks/heatmaps); fp16 carries 3 more mantissa bits than bf16 at the same tensor-core rate."""
     global _PRECISION
     if p not in _DTYPES:
         raise ValueError("precision must be one of %s" % sorted(_DTYPES))
@@ -45,6 +49,17 @@ def _code(dtype):
     if dtype == torch.float16:
         return F16
     raise TypeError("unsupported activation dtype %s" % dtype)
+
+
+def conv_code(x, Cin=None):
+    """Descriptor dtype of a convolution / deformable convolution over activation x: the storage code of x, or
+    TF32 when the 'tf32' arm is active and the shape fits the tensor-core path (Cin multiple of 8, 16-byte pixel
+    pitch; the 3-channel stem stays on the exact-fp32 kernel)."""
+    if _PRECISION == "tf32" and x.dtype == torch.float32:
+        N, C, H, W, p = meta(x)
+        if (Cin or C) % 8 == 0 and p % 4 == 0:
+            return TF32
+    return _code(x.dtype)
 
 
 def _stream():
@@ -174,30 +189,36 @@ def _ver(*ts):
     return tuple((t._version, t.data_ptr()) if t is not None else None for t in ts)
 
 
+_CODE_STORAGE = {F32: torch.float32, TF32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
+
+
+def _as_code(dtype):
+    return dtype if isinstance(dtype, int) else _code(dtype)
+
+
 def packed_weight(owner, weight, dtype):
-    """[kh*kw*Cin][CoutPad] packing of an OIHW weight (fami_pack_conv_weight), cached per version."""
-    key = ("w", _code(dtype))
+    """Kernel-ready packing of an OIHW weight (fami_pack_conv_weight), cached per parameter version.  `dtype`: a
+    torch dtype or a descriptor code (TF32: fp32 storage rounded to tf32, K-major 32-channel rows)."""
+    code = _as_code(dtype)
+    key = ("w", code)
     cache = owner.__dict__.setdefault("_fami_cache", {})
     ver = _ver(weight)
     hit = cache.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1]
-    Cout, Cin, kh, kw = weight.shape
-    n = _lib.load().fami_packed_weight_elems(Cout, Cin, kh, kw, _code(dtype))
-    out = torch.empty(n, dtype=dtype, device=weight.device)
-    w = weight.detach().contiguous().float()
-    _lib.call("fami_pack_conv_weight", _ptr(w), _ptr(out), Cout, Cin, kh, kw, _code(dtype), _stream())
+    out = pack_weight(weight, code)
     cache[key] = (ver, out)
     return out
 
 
 def pack_weight(weight, dtype):
     """Uncached packing of an OIHW weight tensor (training: weights change every step; derived weights)."""
+    code = _as_code(dtype)
     Cout, Cin, kh, kw = weight.shape
-    n = _lib.load().fami_packed_weight_elems(Cout, Cin, kh, kw, _code(dtype))
-    out = torch.empty(n, dtype=dtype, device=weight.device)
+    n = _lib.load().fami_packed_weight_elems(Cout, Cin, kh, kw, code)
+    out = torch.empty(n, dtype=_CODE_STORAGE[code], device=weight.device)
     w = weight.detach().contiguous().float()
-    _lib.call("fami_pack_conv_weight", _ptr(w), _ptr(out), Cout, Cin, kh, kw, _code(dtype), _stream())
+    _lib.call("fami_pack_conv_weight", _ptr(w), _ptr(out), Cout, Cin, kh, kw, code, _stream())
     return out
 
 
@@ -229,7 +250,8 @@ def folded_affine(conv_bias, bn):
 # convolution (+BN +residual +ReLU +upsample-on-write)
 # ------------------------------------------------------------------------------------------------
 
-def _conv_raw(x, w_packed, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, out, stats, out_dtype=None):
+def _conv_raw(x, w_packed, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, out, stats, out_dtype=None,
+              code=None):
     N, Cin, H, W, ip = meta(x)
     Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
     Wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
@@ -246,7 +268,7 @@ def _conv_raw(x, w_packed, Cout, k, stride, pad, dil, scale, shift, residual, re
             raise ValueError("residual shape %s does not match conv output %s"
                              % (tuple(residual.shape), (N, Cout, Ho * up, Wo * up)))
     d = ConvDesc(N, H, W, Cin, Cout, k, k, stride, pad, dil, Ho, Wo, up, int(bool(relu)), ip, op, rp,
-                 _code(x.dtype), _code(out_dtype), int(stats is not None), 0)
+                 code if code is not None else _code(x.dtype), _code(out_dtype), int(stats is not None), 0)
     _lib.call("fami_conv2d_bn_act_fwd", ctypes.byref(d), _ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift),
               _ptr(residual), _ptr(out), _ptr(stats), _stream())
     return out
@@ -295,18 +317,20 @@ def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None, out
         return _ag.conv_bn_act(x, conv, bn, relu, residual)
     k = conv.kernel_size[0]
     stride, pad, dil = conv.stride[0], conv.padding[0], conv.dilation[0]
-    w = packed_weight(conv, conv.weight, x.dtype)
+    code = conv_code(x, conv.in_channels)
+    w = packed_weight(conv, conv.weight, code)
     Cout = conv.out_channels
     if bn is not None and bn.training:
         # batch statistics: raw conv (+bias) with fused per-channel sum / sum-of-squares
         bias = conv.bias.detach().float() if conv.bias is not None else None
         stats = torch.zeros(2 * Cout, dtype=torch.float64, device=x.device)
-        if x.dtype == torch.float32:
+        if code == F32:
             raw = _conv_raw(x, w, Cout, k, stride, pad, dil, None, bias, None, False, 1, None, stats, torch.float32)
             N, _, Ho, Wo, rawp = meta(raw)
         else:
-            # tensor-core arm: raw conv output kept in fp32, statistics by a separate column reduction
-            raw = _conv_raw(x, w, Cout, k, stride, pad, dil, None, bias, None, False, 1, None, None, torch.float32)
+            # tensor-core arms: raw conv output kept in fp32, statistics by a separate column reduction
+            raw = _conv_raw(x, w, Cout, k, stride, pad, dil, None, bias, None, False, 1, None, None, torch.float32,
+                            code=code)
             N, _, Ho, Wo, rawp = meta(raw)
             _lib.call("fami_bn_stats", _ptr(raw), F32, rawp, N * Ho * Wo, Cout, _ptr(stats), _stream())
         scale = torch.empty(Cout, dtype=torch.float32, device=x.device)
@@ -316,8 +340,12 @@ def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None, out
         _lib.call("fami_bn_finalize", _ptr(stats), _ptr(bn.weight), _ptr(bn.bias),
                   _ptr(bn.running_mean if track else None), _ptr(bn.running_var if track else None),
                   _ptr(scale), _ptr(shift), None, None, Cout, N * Ho * Wo, float(bn.eps), float(mom), _stream())
-        if track and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked += 1
+        if track:
+            # the running statistics were updated through raw pointers: bump their version counters so the
+            # folded eval-mode affine cached by folded_affine() is rebuilt on the next eval forward
+            torch.autograd.graph.increment_version((bn.running_mean, bn.running_var))
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
         if out is None:
             out = empty_nhwc(N, Cout, Ho * up, Wo * up, out_dtype or act_dtype(), x.device)
         op = meta(out)[4]
@@ -326,7 +354,7 @@ def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None, out
                   _ptr(out), op, _code(out.dtype), N, Ho, Wo, Cout, up, int(bool(relu)), _stream())
         return out
     scale, shift = folded_affine(conv.bias, bn)
-    return _conv_raw(x, w, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, out, None, out_dtype)
+    return _conv_raw(x, w, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, out, None, out_dtype, code=code)
 
 
 def upsample_nearest(x, factor):

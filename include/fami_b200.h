@@ -19,6 +19,10 @@
  *     reference's torch.cat along dim=1) can be read/written in place.
  *   - dtype: FAMI_F32 activations are float (exact-fp32 SIMT arm); FAMI_F16 / FAMI_BF16 activations
  *     are __half / __nv_bfloat16 (tcgen05 tensor-core arm; "half" below means either 16-bit type).
+ *     FAMI_TF32 (convolution / deformable descriptors only) = float STORAGE of x, residual and y with
+ *     the contraction on tcgen05.mma.kind::tf32: multiplicands rounded to TF32 (weights at pack time,
+ *     activations by the TMA load), fp32 accumulation -- the arithmetic cuDNN applies to the
+ *     reference's fp32 nn.Conv2d on a GPU (torch.backends.cudnn.allow_tf32 defaults to True).
  *     Per-channel scale/shift vectors, biases, loss outputs are always float.
  */
 #ifndef FAMI_B200_H_
@@ -30,9 +34,9 @@
 extern "C" {
 #endif
 
-#define FAMI_ABI_VERSION 1
+#define FAMI_ABI_VERSION 2
 
-enum { FAMI_F32 = 0, FAMI_BF16 = 1, FAMI_F16 = 2 };
+enum { FAMI_F32 = 0, FAMI_BF16 = 1, FAMI_F16 = 2, FAMI_TF32 = 3 };
 
 /* error text of the last failing call on this thread ("" if none) */
 const char* fami_last_error(void);
@@ -251,18 +255,26 @@ int fami_gaussian_targets(const float* joints, const float* joints_vis, float* t
 int fami_frames_u8_normalize(const uint8_t* frames, int64_t src_frame_stride, float* out, int nframes, int H, int W,
                              const float* mean3, const float* std3, void* stream);
 
-/* ---- hardware probe (test infrastructure, tools/probe_umma.py) -------------------------------
- * out[128][16] = x[shift:shift+128][64] @ w[16][64]^T through one tcgen05 tile whose A descriptor
+/* ---- hardware probes (tooling only) ------------------------------------------------------------
+ * NOT exported by the product library: compiled only with -DFAMI_DEBUG_PROBES into
+ * libfami_b200_probes.so (python fami_pose_b200/csrc/build.py --probes), which tools/probe_*.py and
+ * tools/trace_*.py load instead of libfami_b200.so.                                                */
+#ifdef FAMI_DEBUG_PROBES
+/* out[128][16] = x[shift:shift+128][64] @ w[16][64]^T through one tcgen05 tile whose A descriptor
  * starts `shift` 128-byte rows into a TMA-written SWIZZLE_128B tile (mode 0: base_offset 0,
  * mode 1: base_offset = (addr >> 7) & 7).  Establishes the row-shift rule the halo conv relies on. */
+int fami_debug_umma_rowshift(const void* x_f16, const void* w_f16, float* out, int R, int shift, int mode,
+                             void* stream);
 /* globaltimer timeline (ns) of CTA 0 of the last halo conv launched with FAMI_HALO_TRACE=1:
  * [role 0..2][tile iteration 0..63][event 0..7] (tools/trace_halo.py).  Synchronises the device.   */
 int fami_debug_read_trace(uint64_t* host_out, int n);
 /* out[0] = SM clocks for `iters` back-to-back M=128,K=16 f16 tcgen05.mma of width N (issue + drain),
  * out[1] = clocks of the issue loop alone (tools/probe_umma.py).                                   */
 int fami_debug_umma_rate(int64_t* out, int N, int iters, int variant, void* stream);
-int fami_debug_umma_rowshift(const void* x_f16, const void* w_f16, float* out, int R, int shift, int mode,
-                             void* stream);
+/* bit patterns that land in shared memory when [rows][32] floats are TMA-loaded through a tensor map of
+ * element type FLOAT32 (mode 0), TFLOAT32 (1) or TFLOAT32_FTZ (2) (tools/probe_tma_tf32.py).           */
+int fami_debug_tma_tf32(const float* x, uint32_t* out_bits, int rows, int mode, void* stream);
+#endif
 
 #ifdef __cplusplus
 }

@@ -14,9 +14,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-def _header_functions():
+def _header_functions(probes=False):
+    """Functions declared by include/fami_b200.h: the product section, or the #ifdef FAMI_DEBUG_PROBES section."""
     src = open(os.path.join(ROOT, "include", "fami_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    m = re.search(r"#ifdef FAMI_DEBUG_PROBES(.*?)#endif", src, re.S)
+    probe_src = m.group(1) if m else ""
+    if probes:
+        src = probe_src
+    elif m:
+        src = src.replace(m.group(0), "")
     return sorted(set(re.findall(r"\b(fami_[a-z0-9_]+)\s*\(", src)))
 
 
@@ -24,16 +31,23 @@ def test_library_exports_every_declared_symbol():
     from fami_pose_b200 import _lib
     names = _header_functions()
     assert len(names) >= 20
-    lib = ctypes.CDLL(_lib.LIB_PATH)
+    lib = ctypes.CDLL(os.path.join(ROOT, "fami_pose_b200", "libfami_b200.so"))
     for n in names:
         assert hasattr(lib, n), "missing export %s" % n
+    # the hardware probes are NOT part of the product library (build flag FAMI_DEBUG_PROBES)
+    probes = _header_functions(probes=True)
+    assert probes and sorted(_lib.PROBE_SIGNATURES) == probes
+    for n in probes:
+        assert not hasattr(lib, n), "debug export %s leaked into the product library" % n
     # the ctypes signature table covers exactly the header
     assert sorted(_lib.SIGNATURES) == names
     l = _lib.load()
-    assert l.fami_abi_version() == 1
+    assert l.fami_abi_version() == 2
     assert l.fami_conv_cout_pad(17) == 32 and l.fami_conv_cout_pad(48) == 48
     assert l.fami_packed_weight_elems(48, 48, 3, 3, _lib.F32) == 432 * 48
     assert l.fami_packed_weight_elems(48, 48, 3, 3, _lib.F16) == 48 * 9 * 64
+    assert l.fami_packed_weight_elems(48, 48, 3, 3, _lib.TF32) == 48 * 9 * 64     # two 32-channel rows per tap
+    assert l.fami_packed_weight_elems(96, 96, 3, 3, _lib.TF32) == 96 * 9 * 96
     assert l.fami_last_error() is not None
 
 

@@ -183,6 +183,29 @@ def test_full_size_properties_config2(prec):
 HALF_ARMS = [("fp16", 1e-2), ("bf16", 3e-2)]
 
 
+def test_alignment_v15_tf32_vs_reference_golden(golden_dir):
+    """The 'tf32' arm -- fp32 storage, every convolution on tcgen05.mma.kind::tf32 with round-to-nearest TF32
+    multiplicands and fp32 accumulation, i.e. what cuDNN gives the reference's fp32 convs on a GPU -- against the
+    reference's CPU fp32 golden at the FP32 tier's tolerance: 1e-3 max-abs, argmax identical where the margin > 1e-3."""
+    import fami_pose_b200 as fp
+    gold = np.load(os.path.join(golden_dir, "model_reference.npz"))
+    m, sd = _build("validate")
+    m.eval()
+    fp.set_precision("tf32")
+    try:
+        kf, sup, tgt, tw = fo.synthetic_clip(1, seed=SEED)
+        with torch.no_grad():
+            hm, kfhm = m(kf.to(DEV), sup.to(DEV))
+        e1 = float(np.abs(hm.cpu().numpy() - gold["v15_eval_final_hm"]).max())
+        e2 = float(np.abs(kfhm.cpu().numpy() - gold["v15_eval_kf_hm"]).max())
+        print("tf32 max-abs err final %.3e kf %.3e" % (e1, e2))
+        assert e1 <= TOL and e2 <= TOL
+        _argmax_check(hm.cpu().numpy(), gold["v15_eval_final_hm"])
+        _argmax_check(kfhm.cpu().numpy(), gold["v15_eval_kf_hm"])
+    finally:
+        fp.set_precision("fp32")
+
+
 @pytest.mark.parametrize("prec,tol", HALF_ARMS)
 def test_alignment_v15_half_vs_reference_golden(golden_dir, prec, tol):
     import fami_pose_b200 as fp

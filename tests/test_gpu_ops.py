@@ -397,6 +397,90 @@ def test_conv_tc_half(case, prec):
         m.set_precision("fp32")
 
 
+def _tf32_rna(t):
+    """cvt.rna.tf32.f32 on a float32 tensor: round the 23-bit mantissa to 10 bits, ties away from zero."""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("case", TC_CASES + HALO_CASES)
+def test_conv_tc_tf32(case):
+    """tcgen05 kind::tf32 conv (fp32 storage, TF32 multiplicands, fp32 accumulate; the 'tf32' arm) vs torch CPU fp32
+    conv on operands ALREADY rounded to tf32, so only the accumulation order differs: tol 2e-5*max|ref| + 1e-5.
+    Output, residual and the BN/ReLU/upsample epilogue are fp32."""
+    import fami_pose_b200 as m
+    from fami_pose_b200 import ops
+    m.set_precision("tf32")
+    try:
+        Cin, Cout, k, s, p, d, H, W, N, bias, bn, relu, res, up, out_f32 = case
+        g = torch.Generator().manual_seed(abs(hash(case)) % (2 ** 31))
+        x = _tf32_rna(torch.randn(N, Cin, H, W, generator=g))
+        conv = torch.nn.Conv2d(Cin, Cout, k, s, p, d, bias=bias)
+        with torch.no_grad():
+            conv.weight.copy_(_tf32_rna(torch.randn(conv.weight.shape, generator=g) / (Cin * k * k) ** 0.5))
+            if bias:
+                conv.bias.copy_(torch.randn(Cout, generator=g))
+        bnm = None
+        if bn:
+            bnm = torch.nn.BatchNorm2d(Cout).eval()
+            with torch.no_grad():
+                bnm.weight.copy_(torch.rand(Cout, generator=g) + 0.5)
+                bnm.bias.copy_(torch.randn(Cout, generator=g) * 0.2)
+                bnm.running_mean.copy_(torch.randn(Cout, generator=g) * 0.2)
+                bnm.running_var.copy_(torch.rand(Cout, generator=g) + 0.5)
+        with torch.no_grad():
+            y = torch.nn.functional.conv2d(x.double(), conv.weight.double(), conv.bias.double() if bias else None, s, p, d).float()
+            if bn:
+                y = bnm(y)
+            if up > 1:
+                y = F.interpolate(y, scale_factor=up, mode="nearest")
+            r = torch.randn(y.shape, generator=g) if res else None      # the residual stream keeps full fp32
+            if res:
+                y = y + r
+            if relu:
+                y = F.relu(y)
+        xd = ops.to_nhwc(x.to(DEV), torch.float32)
+        assert ops.conv_code(xd, Cin) == m._lib.TF32
+        rd = ops.to_nhwc(r.to(DEV), torch.float32) if res else None
+        with torch.no_grad():
+            out = ops.conv_bn_act(xd, conv.to(DEV), bnm.to(DEV) if bn else None, relu=relu, residual=rd, up=up)
+        assert out.dtype == torch.float32
+        got = ops.to_nchw(out).cpu()
+        tol = 2e-5 * float(y.abs().max()) + 1e-5
+        err = float((got - y).abs().max())
+        print("tf32 conv", case, "err", err, "tol", tol)
+        assert err <= tol
+    finally:
+        m.set_precision("fp32")
+
+
+def test_conv_tf32_rounds_activations_to_nearest():
+    """The tf32 arm keeps activations as full fp32 in HBM; the multiplicand is rounded to TF32 (to nearest even, measured
+    by tools/probe_tma_tf32.py) on its way into shared memory (TFLOAT32 tensor map), not truncated by the tensor core.
+    Un-rounded inputs: the result must match the conv of nearest-rounded inputs (2e-5; ties are measure-zero for random
+    data, so rna and rne agree) and differ measurably from the conv of truncated inputs."""
+    import fami_pose_b200 as m
+    from fami_pose_b200 import ops
+    m.set_precision("tf32")
+    try:
+        g = torch.Generator().manual_seed(7)
+        x = torch.rand(2, 64, 24, 18, generator=g) + 0.5            # positive: truncation bias is coherent
+        conv = torch.nn.Conv2d(64, 64, 3, 1, 1, bias=False)
+        with torch.no_grad():
+            conv.weight.copy_(_tf32_rna(torch.rand(conv.weight.shape, generator=g) / 576))
+        xt = (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
+        with torch.no_grad():
+            y_rna = F.conv2d(_tf32_rna(x).double(), conv.weight.double(), None, 1, 1).float()
+            y_trunc = F.conv2d(xt.double(), conv.weight.double(), None, 1, 1).float()
+        with torch.no_grad():
+            got = ops.to_nchw(ops.conv_bn_act(ops.to_nhwc(x.to(DEV), torch.float32), conv.to(DEV), None)).cpu()
+        e_rna, e_trunc = float((got - y_rna).abs().max()), float((got - y_trunc).abs().max())
+        print("tf32 activation rounding: err vs rna %.3e, vs truncation %.3e" % (e_rna, e_trunc))
+        assert e_rna <= 2e-5 * float(y_rna.abs().max()) and e_trunc > 5 * e_rna
+    finally:
+        m.set_precision("fp32")
+
+
 # ---------------------------------------------------------------------------------------------
 # 16-bit tensor-core DCN (fused tap-major offsets)
 # ---------------------------------------------------------------------------------------------

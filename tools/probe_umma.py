@@ -1,4 +1,6 @@
 """Probe: row-shifted SWIZZLE_128B UMMA descriptors (see fami_debug_umma_rowshift)."""
+import os
+os.environ["FAMI_PROBES"] = "1"   # fami_debug_* live in libfami_b200_probes.so (csrc/build.py --probes)
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -1,4 +1,6 @@
 """Timeline of CTA 0 of the tensor-core DCN kernel (FAMI_DCN_TRACE=1)."""
+import os
+os.environ["FAMI_PROBES"] = "1"   # fami_debug_* live in libfami_b200_probes.so (csrc/build.py --probes)
 import os, sys, ctypes
 os.environ.setdefault("FAMI_DCN_TRACE", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,4 +1,6 @@
 """Per-role timeline of CTA 0 of a halo conv (FAMI_HALO_TRACE=1)."""
+import os
+os.environ["FAMI_PROBES"] = "1"   # fami_debug_* live in libfami_b200_probes.so (csrc/build.py --probes)
 import os, sys, ctypes
 os.environ.setdefault("FAMI_HALO_TRACE", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
