@@ -34,6 +34,7 @@ SIGNATURES = {
     "fami_last_error": (c_char_p, []),
     "fami_abi_version": (c_int, []),
     "fami_launch_count": (c_int64, []),
+    "fami_workspace_bytes": (c_int64, [c_int, c_void_p]),
     "fami_nchw_to_nhwc": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "fami_nhwc_to_nchw": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "fami_conv_cout_pad": (c_int, [c_int]),

@@ -109,6 +109,22 @@ const char* fami_last_error(void) { return g_err; }
 int fami_abi_version(void) { return FAMI_ABI_VERSION; }
 int64_t fami_launch_count(void) { return g_launches.load(); }
 
+int64_t fami_workspace_bytes(int op, const void* desc) {
+  if (!desc) return -1;
+  const fami_conv_desc* c = static_cast<const fami_conv_desc*>(desc);
+  const fami_dcn_desc* d = static_cast<const fami_dcn_desc*>(desc);
+  switch (op) {
+    case FAMI_OP_CONV_FWD: return c->stats ? 16ll * c->Cout : 0;
+    case FAMI_OP_CONV_DGRAD:
+      return 4ll * c->Cout * c->Cin * c->kh * c->kw + 4ll * fami_packed_weight_elems(c->Cin, c->Cout, c->kh, c->kw, FAMI_F32);
+    case FAMI_OP_CONV_WGRAD: return 0;
+    case FAMI_OP_BN_BWD: return 16ll * c->Cout;
+    case FAMI_OP_DCN_FWD: return 0;
+    case FAMI_OP_DCN_BWD: return 4ll * d->kh * d->kw * d->C * fami_conv_cout_pad(d->Cout);
+    default: return -1;
+  }
+}
+
 int fami_nchw_to_nhwc(const float* src, int64_t src_n_stride, void* dst, int dst_dtype, int N, int C, int H, int W,
                       int dst_pitch, void* stream) {
   FAMI_CHECK_ARG(src && dst, "fami_nchw_to_nhwc: null pointer");

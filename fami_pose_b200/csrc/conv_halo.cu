@@ -435,8 +435,9 @@ HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d, int kKC) {
     const size_t a_stage = (size_t)HR * 128;
     const size_t b_tile = (size_t)BN * 128;
     const size_t b_all = b_tile * ksteps;
+    static const bool no_resident = getenv("FAMI_HALO_NORES") != nullptr;   // experiment knob: streamed weights only
     for (int resident = 1; resident >= 0; --resident) {
-      if (resident && n_tiles != 1) continue;
+      if (resident && (n_tiles != 1 || no_resident)) continue;
       size_t bbytes;
       int sB;
       if (resident) { bbytes = b_all; sB = 0; }

@@ -38,6 +38,20 @@ extern "C" {
 
 enum { FAMI_F32 = 0, FAMI_BF16 = 1, FAMI_F16 = 2, FAMI_TF32 = 3 };
 
+/* Caller-provided scratch.  No entry point allocates device memory: where an operation needs scratch beyond its
+ * inputs and outputs, the caller passes it (stats_out / sums / scratch_oihw / w_packed_t / grad_w_packed arguments
+ * below) and sizes it with fami_workspace_bytes(op, desc), desc = the operation's fami_conv_desc / fami_dcn_desc.
+ *   FAMI_OP_CONV_FWD    : 16*Cout if desc->stats (double stats_out[2*Cout], zeroed by the caller), else 0
+ *   FAMI_OP_CONV_DGRAD  : scratch_oihw (4*Cout*Cin*kh*kw) + w_packed_t (fami_packed_weight_elems(Cin,Cout,..) floats)
+ *   FAMI_OP_CONV_WGRAD  : 0 (accumulates into grad_w_oihw / grad_bias, which the caller zeroes)
+ *   FAMI_OP_BN_BWD      : 16*Cout (double sums[2*C], zeroed by the caller)
+ *   FAMI_OP_DCN_FWD     : 0
+ *   FAMI_OP_DCN_BWD     : grad_w_packed, 4 * kh*kw * C * fami_conv_cout_pad(Cout)
+ * Returns -1 for an unknown op or a null descriptor.                                                           */
+enum { FAMI_OP_CONV_FWD = 0, FAMI_OP_CONV_DGRAD = 1, FAMI_OP_CONV_WGRAD = 2, FAMI_OP_BN_BWD = 3, FAMI_OP_DCN_FWD = 4,
+       FAMI_OP_DCN_BWD = 5 };
+int64_t fami_workspace_bytes(int op, const void* desc);
+
 /* error text of the last failing call on this thread ("" if none) */
 const char* fami_last_error(void);
 int fami_abi_version(void);

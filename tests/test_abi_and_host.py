@@ -49,6 +49,14 @@ def test_library_exports_every_declared_symbol():
     assert l.fami_packed_weight_elems(48, 48, 3, 3, _lib.TF32) == 48 * 9 * 64     # two 32-channel rows per tap
     assert l.fami_packed_weight_elems(96, 96, 3, 3, _lib.TF32) == 96 * 9 * 96
     assert l.fami_last_error() is not None
+    # caller-provided scratch sizes: no entry point allocates
+    c = _lib.ConvDesc(1, 8, 8, 48, 324, 3, 3, 1, 3, 3, 8, 8, 1, 0, 48, 324, 0, 0, 0, 1, 0)
+    assert l.fami_workspace_bytes(0, ctypes.byref(c)) == 16 * 324          # FAMI_OP_CONV_FWD with stats
+    assert l.fami_workspace_bytes(1, ctypes.byref(c)) == 4 * 324 * 48 * 9 + 4 * l.fami_packed_weight_elems(48, 324, 3, 3, _lib.F32)
+    assert l.fami_workspace_bytes(2, ctypes.byref(c)) == 0
+    d = _lib.DcnDesc(1, 8, 8, 48, 48, 12, 3, 3, 1, 3, 3, 48, 216, 108, 48, 0, 0)
+    assert l.fami_workspace_bytes(5, ctypes.byref(d)) == 4 * 9 * 48 * 48   # FAMI_OP_DCN_BWD: packed grad_w
+    assert l.fami_workspace_bytes(99, ctypes.byref(d)) == -1
 
 
 def test_desc_struct_layout_matches_header():

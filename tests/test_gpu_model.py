@@ -144,19 +144,25 @@ def test_alignment_v15_vs_oracle_other_seed_and_batch():
     assert float((kfhm.cpu() - rkf).abs().max()) <= TOL
 
 
-@pytest.mark.parametrize("prec", ["fp32", "fp16"])
-def test_full_size_properties_config2(prec):
-    """Size-independent properties at BASELINE config 2's full size (B=32, 160 HRNet images), where the
-    CPU oracle would take minutes: (i) clips are independent -> the first clips of a B=32 batch equal
-    the same clips run at B=2 (same kernels, same per-pixel arithmetic: bit-exact on the fp32 arm; on the
-    16-bit arm the persistent kernels tile the two batch sizes identically per pixel as well); (ii) outputs
-    finite; (iii) device argmax == numpy argmax of the output.  The fp16 case is also the only test that
-    drives every tensor-core kernel through many tiles per CTA (multi-wave barrier phases)."""
+FULL_SIZE_ARMS = [("fp32", 1e-3), ("tf32", 1e-3), ("fp16", 1e-2)]
+
+
+@pytest.mark.parametrize("prec,tol", FULL_SIZE_ARMS)
+def test_full_size_config2_vs_oracle_and_properties(prec, tol):
+    """BASELINE config 2 at full size (B=32, 160 HRNet images -- the shape bench.py times, the only one that drives every
+    tensor-core kernel through many tiles per CTA and multi-wave barrier phases):
+    (i) the first two clips of the B=32 batch against the CPU ORACLE run on those same two clips (seed 99; clips are
+        independent in eval mode): north_star tolerance of the arm (1e-3 fp32 / tf32, 1e-2 fp16) and argmax indices
+        identical wherever the oracle's top-1/top-2 margin exceeds it;
+    (ii) clip independence: the same clips run at B=2 through the same kernels agree to 1e-6;
+    (iii) outputs finite; (iv) device argmax == numpy argmax of the device heatmaps for all 32x17 joints."""
     import fami_pose_b200 as fp
     m, sd = _build("validate")
     m.eval()
-    kf, sup, _, _ = fo.synthetic_clip(32, seed=99)
-    kf, sup = kf.to(DEV), sup.to(DEV)
+    kf_h, sup_h, _, _ = fo.synthetic_clip(32, seed=99)
+    with torch.no_grad():
+        rhm, rkf = fo.FunctionalFami(sd).alignment(kf_h[:2], sup_h[:2])
+    kf, sup = kf_h.to(DEV), sup_h.to(DEV)
     fp.set_precision(prec)
     try:
         with torch.no_grad():
@@ -166,6 +172,13 @@ def test_full_size_properties_config2(prec):
     finally:
         fp.set_precision("fp32")
     assert torch.isfinite(hm).all() and torch.isfinite(kfhm).all()
+    e1 = float((hm[:2].cpu() - rhm).abs().max())
+    e2 = float((kfhm[:2].cpu() - rkf).abs().max())
+    print("config 2 full size (%s): clips 0-1 of B=32 vs oracle: final %.3e kf %.3e" % (prec, e1, e2))
+    assert e1 <= tol and e2 <= tol
+    n_strict, n_all = _argmax_check(hm[:2].cpu().numpy(), rhm.numpy(), tol)
+    _argmax_check(kfhm[:2].cpu().numpy(), rkf.numpy(), tol)
+    assert n_strict > 0
     assert float((hm[:2] - hm2).abs().max()) <= 1e-6
     assert float((kfhm[:2] - kfhm2).abs().max()) <= 1e-6
     idx = fp.argmax_indices(hm).cpu().numpy()
