@@ -298,7 +298,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     EpiArgs ea;
     // Lean pipelined epilogue (16-column groups, pitch 48 B: staging + two residual buffers per warp fill exactly the
     // 12 x 32 x 144 B allocation) whenever the output is a plain 16-bit NHWC tile; the generic routine otherwise.
-    const bool lean = sizeof(TH) == 2 && epi_pipe_ok(p.BN, p.Cout, p.vec_ok, p.out_f32, 1, p.res != nullptr) &&
+    const bool lean = epi_pipe_ok(p.BN, p.Cout, p.vec_ok, p.out_f32, 1, p.res != nullptr, sizeof(TH) == 4) &&
                       p.Cout == p.BN * p.n_tiles && p.om_groups == 0 && !(p.trace & 16);
     const bool pf_on = lean && p.res != nullptr;
     const bool lean_nores = lean && p.res == nullptr;
@@ -369,12 +369,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!(p.trace & 2))
             epilogue_rows_pipelined<TH>(ea, t_addr, col_begin, col_end, valid, pix, stage, rbuf[0], rbuf[1], lane, pf_sel, pf_have,
                                         have_next, nvalid, npix, nchb, 16);
+         } else {
+          bool nvalid = false, have_next = true;
+          int npix = 0, nchb = ea.ch_base;
+          if (m + 1 < p.NM) {
+            npix = row_pix(m + 1, nvalid);
+          } else if (tile + (int)gridDim.x < p.total_tiles) {
+            const int ntile = tile + gridDim.x;
+            const int nnt = ntile % p.n_tiles;
+            const int nt2 = ntile / p.n_tiles;
+            const int nty = nt2 % p.tiles_per_img, nimg = nt2 / p.tiles_per_img;
+            const int ny0 = nty * p.BH;
+            const int yy = row / p.Wp, xx = row - yy * p.Wp;
+            nvalid = (yy < p.BH) && (xx < p.W) && (ny0 + yy < p.H);
+            npix = nvalid ? (nimg * p.H + (ny0 + yy)) * p.W + xx : 0;
+            nchb = nnt * p.BN;
+          } else {
+            have_next = false;
+          }
+          epilogue_rows_pipelined_f32<true>(ea, t_addr, col_begin, col_end, valid, pix, stage, rbuf[0], rbuf[1], lane, pf_sel, pf_have,
+                                            have_next, nvalid, npix, nchb);
          }
         } else if (lean_nores) {
          if constexpr (sizeof(TH) == 2) {
           if (!(p.trace & 2))
             epilogue_rows_pipelined<TH, false>(ea, t_addr, col_begin, col_end, valid, pix, stage, 0u, 0u, lane, pf_sel, pf_have, false,
                                                false, 0, 0, 16);
+         } else {
+          epilogue_rows_pipelined_f32<false>(ea, t_addr, col_begin, col_end, valid, pix, stage, 0u, 0u, lane, pf_sel, pf_have, false,
+                                             false, 0, 0);
          }
         } else if (!(p.trace & 2)) {
           epilogue_rows<TH>(ea, t_addr, col_begin, col_end, valid, pix, stage, lane);
@@ -455,7 +478,10 @@ HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d, int kKC) {
         // resident weights: big tiles win even single-buffered (48->48: NM=5, sA=1 measured best).  Streamed weights:
         // the accumulator and the A stage must be double-buffered or the tile loses to the im2col kernel
         // (96->96: NM=2/sA=2/acc=2 72 us, NM=5/sA=1/acc=1 92 us, im2col 81 us).
-        double score = resident ? eff / feed * (acc_bufs == 2 ? 1.0 : 0.8) * (sA == 2 ? 1.0 : 0.85)
+        // tf32 (32-channel rows): a single A stage with several channel chunks serialises load and MMA per chunk
+        // (48->48 tf32: resident NM=2 sA=1 291 us, streamed NM=3 sA=2 160 us)
+        const double sa1 = (kKC == 32 && cchunks > 1) ? 0.35 : 0.85;
+        double score = resident ? eff / feed * (acc_bufs == 2 ? 1.0 : 0.8) * (sA == 2 ? 1.0 : sa1)
                                 : eff / feed * (acc_bufs == 2 ? 1.0 : 0.4) * (sA == 2 ? 1.0 : 0.5);
         if (score > best_score) {
           best_score = score;

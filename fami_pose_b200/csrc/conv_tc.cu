@@ -171,7 +171,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t rbuf = smem_u32(stage_base) + (uint32_t)(kEpiWarps * 32 * ea.spitch) + (uint32_t)((warp - 2) * 64 * ea.spitch);
     const int up_fast = (p.up > 1 && p.res != nullptr && 3 * ea.spitch <= (128 + 16)) ? -1 : 0;
     // pipelined residual epilogue: staging + two residual buffers per warp at the 32-column pitch
-    const uint32_t pp = (uint32_t)epi_pipe_pitch();
+    const uint32_t pp = (uint32_t)(sizeof(TH) == 4 ? epi_pipe_pitch(kPipeColsF32 * 2) : epi_pipe_pitch());   // 48 B (fp32, 8 cols) / 80 B
     const uint32_t pstage = smem_u32(stage_base) + (uint32_t)(warp - 2) * (p.res ? 96u : 32u) * pp;
     int psel = 0, pprimed = 0;
     ea.s_scale = smem_u32(s_scale); ea.s_shift = smem_u32(s_shift); ea.res = p.res; ea.y = p.y;
@@ -205,13 +205,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ob.base = reinterpret_cast<float*>(p.y); ob.tiles_x = p.om_tiles_x; ob.tiles_y = p.om_tiles_y;
         ob.G3 = 3 * p.om_groups; ob.tap_stride = p.om_tap_stride;
         epilogue_rows_om_blocked(ea, t_addr, col_begin, col_end, valid, n, yo, xo, ob);
-      } else if (sizeof(TH) == 2 && p.pipe) {
-       if constexpr (sizeof(TH) == 2) {
+      } else if (p.pipe) {
         const int ntile = tile + gridDim.x;
         const bool have_next = ntile < total_tiles;
         const int nmt = ntile / p.n_tiles, nnt = ntile - nmt * p.n_tiles;
         const int nm = nmt * kBM + row;
         const bool nvalid = have_next && nm < p.M;
+       if constexpr (sizeof(TH) == 4) {
+        if (p.res)
+          epilogue_rows_pipelined_f32<true>(ea, t_addr, col_begin, col_end, valid, pix0, pstage, pstage + 32u * pp, pstage + 64u * pp,
+                                            lane, psel, pprimed, have_next, nvalid, nvalid ? nm : 0, nnt * p.BN);
+        else
+          epilogue_rows_pipelined_f32<false>(ea, t_addr, col_begin, col_end, valid, pix0, pstage, 0u, 0u, lane, psel, pprimed, false,
+                                             false, 0, 0);
+       } else {
         if (p.res)
           epilogue_rows_pipelined<TH, true>(ea, t_addr, col_begin, col_end, valid, pix0, pstage, pstage + 32u * pp, pstage + 64u * pp,
                                             lane, psel, pprimed, have_next, nvalid, nvalid ? nm : 0, nnt * p.BN);
@@ -360,9 +367,10 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   p.om_tap_stride = (int64_t)d->N * p.om_tiles_x * p.om_tiles_y * 4 * (3 * (d->om_groups / 4)) * 128;
 
   const int stage_bytes = kABytes + t.BN * 128;
-  p.pipe = (!tf32 && d->om_groups == 0 && epi_pipe_ok(t.BN, d->Cout, p.vec_ok, out_f32, d->up, res != nullptr) && d->Cout == t.BN * t.n_tiles &&
+  p.pipe = (d->om_groups == 0 && epi_pipe_ok(t.BN, d->Cout, p.vec_ok, out_f32, d->up, res != nullptr, tf32) && d->Cout == t.BN * t.n_tiles &&
             getenv("FAMI_NO_EPI_PIPE") == nullptr) ? 1 : 0;
-  const size_t epi_bytes = p.pipe ? (size_t)kEpiWarps * 32 * (res ? 3 : 1) * epi_pipe_pitch() : (size_t)kEpiWarps * 32 * (128 + 16);
+  const size_t pipe_pitch = tf32 ? epi_pipe_pitch(kPipeColsF32 * 2) : epi_pipe_pitch();
+  const size_t epi_bytes = p.pipe ? (size_t)kEpiWarps * 32 * (res ? 3 : 1) * pipe_pitch : (size_t)kEpiWarps * 32 * (128 + 16);
   int stages = (int)((228000 - (size_t)t.CoutPad * 8 - epi_bytes) / stage_bytes);   // all the shared memory there is: the kernel is bound by bytes in flight
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;

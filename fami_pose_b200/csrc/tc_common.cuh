@@ -540,14 +540,17 @@ __device__ __forceinline__ void epilogue_rows(const EpiArgs& a, uint32_t t_addr,
 // been prefetched by the previous call) carry the state across calls.
 constexpr int kPipeCols = 32;
 __host__ __device__ inline int epi_pipe_pitch(int gcols = kPipeCols) { return gcols * 2 + 16; }
-__host__ __device__ inline bool epi_pipe_ok(int BN, int Cout_total, int vec_ok, int out_f32, int up, bool has_res) {
+__host__ __device__ inline bool epi_pipe_ok(int BN, int Cout_total, int vec_ok, int out_f32, int up, bool has_res,
+                                            bool f32_storage = false) {
   (void)has_res;   // with and without residual (kRes)
-  return up == 1 && !out_f32 && vec_ok && (Cout_total % 16 == 0) && BN % 16 == 0;
+  // out_f32 with 16-bit storage (heatmap / offset convs) takes the generic routine; with fp32 storage (tf32 arm) the
+  // fp32 twin epilogue_rows_pipelined_f32
+  return up == 1 && (f32_storage ? out_f32 != 0 : !out_f32) && vec_ok && (Cout_total % 16 == 0) && BN % 16 == 0;
 }
 template <typename TH>
 __device__ __forceinline__ void epi_pipe_fetch(const EpiArgs& a, int chg, int gc, unsigned vmask, int pix, uint32_t buf, int lane,
                                                int pitch) {
-  const int ppr = (gc * 2) >> 4;                 // 16-byte pieces per row: 2 or 4
+  const int ppr = (gc * (int)sizeof(TH)) >> 4;   // 16-byte pieces per row: 2 or 4
   const int lg = ppr <= 2 ? 1 : 2;
   const int lpr = 1 << lg, rpi = 32 >> lg;
   const int sub_r = lane >> lg, sub_c = lane & (lpr - 1);
@@ -563,6 +566,86 @@ __device__ __forceinline__ void epi_pipe_fetch(const EpiArgs& a, int chg, int gc
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// fp32-storage twin of epilogue_rows_pipelined (the tf32 arm: float residual, float output): groups of 8 columns =
+// 32 bytes per row, row pitch 48 B -- the same per-warp footprint (staging + two residual buffers = 3 x 32 x 48 B) as
+// the 16-bit routine at 16 columns, so both share one shared-memory allocation.  While group g is drained the residual
+// of the next unit (next group / next M-tile / next CTA tile) is in flight (cp.async).
+constexpr int kPipeColsF32 = 8;
+template <bool kRes>
+__device__ __forceinline__ void epilogue_rows_pipelined_f32(const EpiArgs& a, uint32_t t_addr, int col_begin, int col_end, bool valid,
+                                                            int pix0, uint32_t stage, uint32_t rb0, uint32_t rb1, int lane, int& sel,
+                                                            int& primed, bool have_next, bool next_valid, int next_pix,
+                                                            int next_ch_base) {
+  if (col_begin >= col_end) return;   // warp-uniform
+  constexpr int gcols = kPipeColsF32;
+  constexpr int pitch = gcols * 4 + 16;   // 48
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  const unsigned nmask = __ballot_sync(0xffffffffu, next_valid);
+  const uint32_t my_row = stage + (uint32_t)(lane * pitch);
+  const int sub_r = lane >> 1, sub_c = lane & 1;   // 2 x 16-byte pieces per row, 16 rows per iteration
+  if (kRes && !primed) epi_pipe_fetch<float>(a, a.ch_base + col_begin, gcols, vmask, pix0, sel ? rb1 : rb0, lane, pitch);
+  for (int g0 = col_begin; g0 < col_end; g0 += gcols) {
+    const int chg = a.ch_base + g0;
+    const uint32_t cur = sel ? rb1 : rb0, nxt = sel ? rb0 : rb1;
+    bool pending = false;
+    if (kRes) {
+      if (g0 + gcols < col_end) {
+        epi_pipe_fetch<float>(a, chg + gcols, gcols, vmask, pix0, nxt, lane, pitch);
+        pending = true;
+      } else if (have_next) {
+        epi_pipe_fetch<float>(a, next_ch_base + col_begin, gcols, nmask, next_pix, nxt, lane, pitch);
+        pending = true;
+      }
+      if (pending) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+    }
+    uint32_t v[8];
+    tmem_ld8(t_addr + (uint32_t)g0, v);
+    tmem_ld_wait();
+    const float4 sc0 = lds128f(a.s_scale + (uint32_t)chg * 4u), sc1 = lds128f(a.s_scale + (uint32_t)(chg + 4) * 4u);
+    const float4 sh0 = lds128f(a.s_shift + (uint32_t)chg * 4u), sh1 = lds128f(a.s_shift + (uint32_t)(chg + 4) * 4u);
+    float4 o0, o1;
+    o0.x = fmaf(__uint_as_float(v[0]), sc0.x, sh0.x); o0.y = fmaf(__uint_as_float(v[1]), sc0.y, sh0.y);
+    o0.z = fmaf(__uint_as_float(v[2]), sc0.z, sh0.z); o0.w = fmaf(__uint_as_float(v[3]), sc0.w, sh0.w);
+    o1.x = fmaf(__uint_as_float(v[4]), sc1.x, sh1.x); o1.y = fmaf(__uint_as_float(v[5]), sc1.y, sh1.y);
+    o1.z = fmaf(__uint_as_float(v[6]), sc1.z, sh1.z); o1.w = fmaf(__uint_as_float(v[7]), sc1.w, sh1.w);
+    if (kRes) {
+      const uint32_t res_row = cur + (uint32_t)(lane * pitch);
+      const float4 r0 = lds128f(res_row), r1 = lds128f(res_row + 16);
+      o0.x += r0.x; o0.y += r0.y; o0.z += r0.z; o0.w += r0.w;
+      o1.x += r1.x; o1.y += r1.y; o1.z += r1.z; o1.w += r1.w;
+    }
+    if (a.relu) {
+      o0.x = fmaxf(o0.x, 0.f); o0.y = fmaxf(o0.y, 0.f); o0.z = fmaxf(o0.z, 0.f); o0.w = fmaxf(o0.w, 0.f);
+      o1.x = fmaxf(o1.x, 0.f); o1.y = fmaxf(o1.y, 0.f); o1.z = fmaxf(o1.z, 0.f); o1.w = fmaxf(o1.w, 0.f);
+    }
+    sts128f(my_row, o0);
+    sts128f(my_row + 16, o1);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int r = it * 16 + sub_r;
+      const int pr = __shfl_sync(0xffffffffu, pix0, r);
+      if ((vmask >> r) & 1u) {
+        const uint4 val = lds128(stage + (uint32_t)(r * pitch + sub_c * 16));
+        uint8_t* dst = reinterpret_cast<uint8_t*>(a.y) + ((int64_t)pr * a.out_pitch + chg) * 4 + sub_c * 16;
+        *reinterpret_cast<uint4*>(dst) = val;
+      }
+    }
+    __syncwarp();
+    sel ^= 1;
+    primed = pending ? 1 : 0;
+  }
 }
 template <typename TH, bool kRes = true>
 __device__ __forceinline__ void epilogue_rows_pipelined(const EpiArgs& a, uint32_t t_addr, int col_begin, int col_end, bool valid,
