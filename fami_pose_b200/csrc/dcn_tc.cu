@@ -36,11 +36,13 @@ __device__ __forceinline__ void dtrace(int on, int it, int ev) {
 }
 
 constexpr int kTH = 16, kTW = 8;            // output tile (pixels): 128 = one UMMA M tile
-constexpr int kGatherWarps = 12;          // 3 groups x 4 warps: group q <-> A stage q <-> taps q, q+3, q+6
+constexpr int kGatherSets = 2;            // two sets of 8 warps; set s gathers taps s, s+2, s+4, ... of every tile
+constexpr int kSetWarps = 8;              // 256 threads = 128 pixels x 2 offset-group parities
+constexpr int kGatherWarps = kGatherSets * kSetWarps;
 constexpr int kGatherThreads = 32 * kGatherWarps;
 constexpr int kDcnEpiWarps = 4;
-constexpr int kDcnThreads = kGatherThreads + 32 + 32 * kDcnEpiWarps;   // 544
-constexpr int kAStages = 3;
+constexpr int kDcnThreads = kGatherThreads + 32 + 32 * kDcnEpiWarps;   // 672
+constexpr int kAStages = 3;               // tap t -> A stage t % 3
 constexpr int kATile = 128 * 128;          // bytes per A stage
 
 struct DcnTcParams {
@@ -78,12 +80,18 @@ template <typename TH> struct H2;
 template <> struct H2<__half> {
   typedef __half2 t;
   static __device__ __forceinline__ t bcast(float w) { return __float2half2_rn(w); }
+  static __device__ __forceinline__ t pack(float a, float b) { return __floats2half2_rn(a, b); }
+  static __device__ __forceinline__ t lo(t v) { return __low2half2(v); }
+  static __device__ __forceinline__ t hi(t v) { return __high2half2(v); }
   static __device__ __forceinline__ t fma(t a, t b, t c) { return __hfma2(a, b, c); }
   static __device__ __forceinline__ t mul(t a, t b) { return __hmul2(a, b); }
 };
 template <> struct H2<__nv_bfloat16> {
   typedef __nv_bfloat162 t;
   static __device__ __forceinline__ t bcast(float w) { return __float2bfloat162_rn(w); }
+  static __device__ __forceinline__ t pack(float a, float b) { return __floats2bfloat162_rn(a, b); }
+  static __device__ __forceinline__ t lo(t v) { return __low2bfloat162(v); }
+  static __device__ __forceinline__ t hi(t v) { return __high2bfloat162(v); }
   static __device__ __forceinline__ t fma(t a, t b, t c) { return __hfma2(a, b, c); }
   static __device__ __forceinline__ t mul(t a, t b) { return __hmul2(a, b); }
 };
@@ -115,7 +123,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     mbar_init(win_full, 1);
     mbar_init(win_free, kGatherWarps);
     mbar_init(w_full, 1);
-    for (int s = 0; s < kAStages; ++s) { mbar_init(a_full(s), kGatherWarps / kAStages); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < kAStages; ++s) { mbar_init(a_full(s), kSetWarps); mbar_init(a_empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), kDcnEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
@@ -141,22 +149,28 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 
   if (warp < kGatherWarps) {
     // ===================== gather warps =====================
-    // Three groups of four warps; group q owns A stage q and the taps q, q+3, q+6 (kernel column q).
-    // A thread is one output pixel of the tile and walks all kG offset groups of a (pixel, tap) unit:
-    // the 3*kG floats of the unit are one contiguous 16-byte-aligned run in the tap-major layout.
+    // Two sets of eight warps; set s owns the taps s, s+2, s+4, ... of every tile (tap t lands in A stage t % 3, the MMA
+    // warp consumes the taps in order).  A thread is (output pixel, offset-group parity): it walks the kG/2 groups
+    // g = 2j + parity of its pixel for one tap.  Lane layout: 16 lanes = 8 consecutive pixels of an image row x 2 parities.
+    // Bank picture of a corner load (8 bytes at window row r, 16-byte chunk (g>>1) ^ (r&7), half g&1): eight consecutive
+    // pixels hit eight different chunks and the two parities the two halves, so a half-warp covers all 32 banks when the
+    // offsets are smooth (one wavefront instead of the 2-4 of a one-thread-per-pixel mapping, where g&1 was warp-uniform
+    // and only half the banks were reachable), and random offsets spread over 16 bank pairs instead of 8.
     constexpr int kQ = kG / 4;
+    constexpr int kJ = kG / 2;             // groups per thread
     typedef typename H2<TH>::t h2;
     const TH* xg = reinterpret_cast<const TH*>(p.x);
     const uint32_t win_u32 = smem_u32(s_win);
-    const int q = warp >> 2;
-    const int r = threadIdx.x & 127;
-    const int ry = r >> 3, rx = r & 7;
-    const uint32_t a_row = smem_u32(s_a) + (uint32_t)(q * kATile + r * 128);
+    const int set = warp / kSetWarps;
+    const int wset = warp - set * kSetWarps;                      // warp within the set: image rows 2*wset, 2*wset+1 of the tile
+    const int par = lane & 1;
+    const int ry = 2 * wset + (lane >> 4), rx = (lane >> 1) & 7;
+    const int r = ry * kTW + rx;                                   // A-tile row = pixel of the tile
     const uint32_t rsw = (uint32_t)(r & 7) << 4;
+    const uint32_t a_row0 = smem_u32(s_a) + (uint32_t)(r * 128) + ((uint32_t)par << 3);
     const int WW = p.WW;
     const unsigned ylim = (unsigned)(p.WH - 1), xlim = (unsigned)(WW - 1);
-    const float base_x = (float)(rx + q * p.d + p.R - p.d);
-    uint32_t use = 0, wph = 0, fph = 0;
+    uint32_t wph = 0, fph = 0;
     int git = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++git) {
       int b, y0, x0;
@@ -164,108 +178,114 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       if (threadIdx.x == 0) dtrace(p.trace, git, 0);
       const int y = y0 + ry, x = x0 + rx;
       const bool valid = y < p.H && x < p.W;
-      // tap-major NHWC (om_layout 1): the 3*kG floats of a (pixel, tap) are one contiguous run, but the 32 lanes of a
-      // warp are 1296 B apart, so every 16-byte load instruction touches 32 cache lines.  Warp-blocked (om_layout 2):
-      // [tap][tile*4 + warp quarter][q < 3kG/4][lane][4 floats] -- each load instruction reads 512 contiguous bytes.
+      // tap-major NHWC (om_layout 1): the 3*kG floats of a (pixel, tap) are one contiguous run.  Warp-blocked (om_layout 2):
+      // [tap][tile*8 + warp block][q < 3kG/4][16 pixels][e0 e2 | e1 e3]: this lane's float2 = its two groups of quad q, the
+      // warp's 32 lanes read 256 contiguous bytes per instruction.
       const float* po = p.om_blocked
-                            ? p.om + ((int64_t)tile * 4 + (r >> 5)) * (3 * kQ * 128) + lane * 4
+                            ? p.om + ((int64_t)tile * 8 + wset) * (3 * kQ * 64) + (lane & 31) * 2
                             : p.om + ((int64_t)(b * p.H + y) * p.W + x) * p.om_pitch;
-      float4 vdy[kQ], vdx[kQ], vmk[kQ];
+      float2 vdy[kQ], vdx[kQ], vmk[kQ];      // groups g = 4i + par (x) and 4i + 2 + par (y)
       auto load_unit = [&](int tap) {
         if (p.om_blocked) {
           const float* o = po + tap * p.om_tap_stride;
 #pragma unroll
           for (int i = 0; i < kQ; ++i) {
-            vdy[i] = __ldg(reinterpret_cast<const float4*>(o + i * 128));
-            vdx[i] = __ldg(reinterpret_cast<const float4*>(o + (kQ + i) * 128));
-            vmk[i] = __ldg(reinterpret_cast<const float4*>(o + (2 * kQ + i) * 128));
+            vdy[i] = __ldg(reinterpret_cast<const float2*>(o + i * 64));
+            vdx[i] = __ldg(reinterpret_cast<const float2*>(o + (kQ + i) * 64));
+            vmk[i] = __ldg(reinterpret_cast<const float2*>(o + (2 * kQ + i) * 64));
           }
         } else {
-          const float4* o = reinterpret_cast<const float4*>(po + tap * 3 * kG);
+          const float* o = po + tap * 3 * kG + par;
 #pragma unroll
-          for (int i = 0; i < kQ; ++i) { vdy[i] = __ldg(o + i); vdx[i] = __ldg(o + kQ + i); vmk[i] = __ldg(o + 2 * kQ + i); }
+          for (int i = 0; i < kQ; ++i) {
+            vdy[i] = make_float2(__ldg(o + 4 * i), __ldg(o + 4 * i + 2));
+            vdx[i] = make_float2(__ldg(o + kG + 4 * i), __ldg(o + kG + 4 * i + 2));
+            vmk[i] = make_float2(__ldg(o + 2 * kG + 4 * i), __ldg(o + 2 * kG + 4 * i + 2));
+          }
         }
       };
-      if (valid) load_unit(q);
+      if (valid) load_unit(set);
       mbar_wait(win_full, wph);
       wph ^= 1u;
       if (threadIdx.x == 0) dtrace(p.trace, git, 1);
 #pragma unroll 1
-      for (int k = 0; k < 3; ++k) {
-        const int tap = q + 3 * k;          // kernel row k, kernel column q
-        mbar_wait(a_empty(q), (use & 1u) ^ 1u);
-        ++use;
-        if (threadIdx.x == 0) dtrace(p.trace, git, 5 + k);
+      for (int tap = set; tap < 9; tap += kGatherSets) {
+        const int kr = tap / 3, kc = tap - kr * 3;      // kernel row / column
+        const int stage = tap - kr * 3;                 // tap % 3
+        const uint32_t u = (uint32_t)(git * 3 + kr);    // use index of this stage
+        mbar_wait(a_empty(stage), (u & 1u) ^ 1u);
+        const uint32_t a_row = a_row0 + (uint32_t)(stage * kATile);
         if (!valid) {
 #pragma unroll
-          for (int c = 0; c < kG / 2; ++c) sts128(a_row + (((uint32_t)c << 4) ^ rsw), make_uint4(0u, 0u, 0u, 0u));
+          for (int j = 0; j < kJ; ++j) sts64(a_row + (((uint32_t)j << 4) ^ rsw), make_uint2(0u, 0u));
         } else {
-          const float base_y = (float)(ry + k * p.d + p.R - p.d);
+          const float base_y = (float)(ry + kr * p.d + p.R - p.d);
+          const float base_x = (float)(rx + kc * p.d + p.R - p.d);
           uint32_t slow = 0;
 #pragma unroll
-          for (int i = 0; i < kQ; ++i) {
-            const float dy4[4] = {vdy[i].x, vdy[i].y, vdy[i].z, vdy[i].w};
-            const float dx4[4] = {vdx[i].x, vdx[i].y, vdx[i].z, vdx[i].w};
-            const float mk4[4] = {vmk[i].x, vmk[i].y, vmk[i].z, vmk[i].w};
-            uint32_t pk[8];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int g = 4 * i + e;
-              // window coordinates: integer shifts of the image-space sample position, so the fractional
-              // parts are exactly those of py / px
-              const float wy = base_y + dy4[e], wx = base_x + dx4[e];
-              const float fy = floorf(wy), fx = floorf(wx);
-              const int iy = (int)fy, ix = (int)fx;
-              pk[2 * e] = 0u; pk[2 * e + 1] = 0u;
-              if ((unsigned)iy < ylim && (unsigned)ix < xlim) {
-                // all four corners inside the staged (zero-padded) window: 8-byte shared-memory loads,
-                // blend in packed 16-bit arithmetic (the column is rounded to 16 bit for the MMA anyway)
-                const float ly = wy - fy, lx = wx - fx;
-                const float mk = mk4[e];
-                const float wb = mk * ly, wt = mk - wb;          // mask * (ly | 1 - ly)
-                const float w4f = wb * lx, w3f = wb - w4f, w2f = wt * lx, w1f = wt - w2f;
-                const uint32_t row00 = (uint32_t)(iy * WW + ix);
-                const uint32_t row10 = row00 + (uint32_t)WW;
-                const uint32_t gs = (uint32_t)(g >> 1) << 4, gofs = (uint32_t)(g & 1) << 3;
-                const uint2 u1 = lds64(win_u32 + row00 * 128u + ((gs ^ (row00 << 4)) & 0x70u) + gofs);
-                const uint2 u2 = lds64(win_u32 + (row00 + 1u) * 128u + ((gs ^ ((row00 + 1u) << 4)) & 0x70u) + gofs);
-                const uint2 u3 = lds64(win_u32 + row10 * 128u + ((gs ^ (row10 << 4)) & 0x70u) + gofs);
-                const uint2 u4 = lds64(win_u32 + (row10 + 1u) * 128u + ((gs ^ ((row10 + 1u) << 4)) & 0x70u) + gofs);
-                const h2 w1 = H2<TH>::bcast(w1f), w2 = H2<TH>::bcast(w2f), w3 = H2<TH>::bcast(w3f), w4 = H2<TH>::bcast(w4f);
-                h2 lo = H2<TH>::mul(w1, *reinterpret_cast<const h2*>(&u1.x));
-                h2 hi = H2<TH>::mul(w1, *reinterpret_cast<const h2*>(&u1.y));
-                lo = H2<TH>::fma(w2, *reinterpret_cast<const h2*>(&u2.x), lo);
-                hi = H2<TH>::fma(w2, *reinterpret_cast<const h2*>(&u2.y), hi);
-                lo = H2<TH>::fma(w3, *reinterpret_cast<const h2*>(&u3.x), lo);
-                hi = H2<TH>::fma(w3, *reinterpret_cast<const h2*>(&u3.y), hi);
-                lo = H2<TH>::fma(w4, *reinterpret_cast<const h2*>(&u4.x), lo);
-                hi = H2<TH>::fma(w4, *reinterpret_cast<const h2*>(&u4.y), hi);
-                pk[2 * e] = *reinterpret_cast<const uint32_t*>(&lo);
-                pk[2 * e + 1] = *reinterpret_cast<const uint32_t*>(&hi);
-              } else {
-                slow |= 1u << g;          // outside the staged window: resolved below from global memory
-              }
+          for (int j = 0; j < kJ; ++j) {
+            // group g = 2j + par: quad j >> 1, element (j & 1) of this lane's float2
+            const float dy = (j & 1) ? vdy[j >> 1].y : vdy[j >> 1].x;
+            const float dx = (j & 1) ? vdx[j >> 1].y : vdx[j >> 1].x;
+            const float mk = (j & 1) ? vmk[j >> 1].y : vmk[j >> 1].x;
+            // window coordinates: integer shifts of the image-space sample position, so the fractional
+            // parts are exactly those of py / px.  floor() without the conversion unit (FRND / F2I run at 16 lanes
+            // per clock and were 2/3 busy): adding 1.5 * 2^23 with round-down leaves floor(w) in the low mantissa bits
+            // for |w| < 2^22; a sample further out than that is far outside the window either way.
+            const float wy = base_y + dy, wx = base_x + dx;
+            const float ty = __fadd_rd(wy, 12582912.f), tx = __fadd_rd(wx, 12582912.f);
+            const float fy = ty - 12582912.f, fx = tx - 12582912.f;
+            const int iy = __float_as_int(ty) - 0x4B400000, ix = __float_as_int(tx) - 0x4B400000;
+            uint2 pk = make_uint2(0u, 0u);
+            if ((unsigned)iy < ylim && (unsigned)ix < xlim) {
+              // all four corners inside the staged (zero-padded) window: 8-byte shared-memory loads,
+              // blend in packed 16-bit arithmetic (the column is rounded to 16 bit for the MMA anyway)
+              const float ly = wy - fy, lx = wx - fx;
+              const float wb = mk * ly, wt = mk - wb;          // mask * (ly | 1 - ly)
+              const float w4f = wb * lx, w3f = wb - w4f, w2f = wt * lx, w1f = wt - w2f;
+              const uint32_t row00 = (uint32_t)(iy * WW + ix);
+              const uint32_t row10 = row00 + (uint32_t)WW;
+              const uint32_t gs = (uint32_t)j << 4, gofs = (uint32_t)par << 3;
+              const uint2 u1 = lds64(win_u32 + row00 * 128u + ((gs ^ (row00 << 4)) & 0x70u) + gofs);
+              const uint2 u2 = lds64(win_u32 + (row00 + 1u) * 128u + ((gs ^ ((row00 + 1u) << 4)) & 0x70u) + gofs);
+              const uint2 u3 = lds64(win_u32 + row10 * 128u + ((gs ^ (row10 << 4)) & 0x70u) + gofs);
+              const uint2 u4 = lds64(win_u32 + (row10 + 1u) * 128u + ((gs ^ ((row10 + 1u) << 4)) & 0x70u) + gofs);
+              // two packed conversions + four lane broadcasts (PRMT) instead of four conversions
+              const h2 w12 = H2<TH>::pack(w1f, w2f), w34 = H2<TH>::pack(w3f, w4f);
+              const h2 w1 = H2<TH>::lo(w12), w2 = H2<TH>::hi(w12), w3 = H2<TH>::lo(w34), w4 = H2<TH>::hi(w34);
+              h2 lo = H2<TH>::mul(w1, *reinterpret_cast<const h2*>(&u1.x));
+              h2 hi = H2<TH>::mul(w1, *reinterpret_cast<const h2*>(&u1.y));
+              lo = H2<TH>::fma(w2, *reinterpret_cast<const h2*>(&u2.x), lo);
+              hi = H2<TH>::fma(w2, *reinterpret_cast<const h2*>(&u2.y), hi);
+              lo = H2<TH>::fma(w3, *reinterpret_cast<const h2*>(&u3.x), lo);
+              hi = H2<TH>::fma(w3, *reinterpret_cast<const h2*>(&u3.y), hi);
+              lo = H2<TH>::fma(w4, *reinterpret_cast<const h2*>(&u4.x), lo);
+              hi = H2<TH>::fma(w4, *reinterpret_cast<const h2*>(&u4.y), hi);
+              pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            } else {
+              slow |= 1u << j;          // outside the staged window: resolved below from global memory
             }
-            sts128(a_row + (((uint32_t)(2 * i) << 4) ^ rsw), make_uint4(pk[0], pk[1], pk[2], pk[3]));
-            sts128(a_row + (((uint32_t)(2 * i + 1) << 4) ^ rsw), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+            sts64(a_row + (((uint32_t)j << 4) ^ rsw), pk);
           }
           // large offsets: bounds-checked global corners, fp32 blend (rare; kept out of the main loop so a
           // single far sample does not serialise the warp through this path once per group)
           while (slow) {
-            const int g = __ffs((int)slow) - 1;
+            const int j = __ffs((int)slow) - 1;
             slow &= slow - 1u;
+            const int g = 2 * j + par;
             float dy, dx, mk;
             if (p.om_blocked) {
               const float* o = po + tap * p.om_tap_stride;
-              dy = __ldg(o + (g >> 2) * 128 + (g & 3));
-              dx = __ldg(o + ((kG + g) >> 2) * 128 + ((kG + g) & 3));
-              mk = __ldg(o + ((2 * kG + g) >> 2) * 128 + ((2 * kG + g) & 3));
+              dy = __ldg(o + (j >> 1) * 64 + (j & 1));
+              dx = __ldg(o + (kQ + (j >> 1)) * 64 + (j & 1));
+              mk = __ldg(o + (2 * kQ + (j >> 1)) * 64 + (j & 1));
             } else {
               const float* o = po + tap * 3 * kG + g;
               dy = __ldg(o); dx = __ldg(o + kG); mk = __ldg(o + 2 * kG);
             }
-            const float py = (float)(y - p.d + k * p.d) + dy;
-            const float px = (float)(x - p.d + q * p.d) + dx;
+            const float py = (float)(y - p.d + kr * p.d) + dy;
+            const float px = (float)(x - p.d + kc * p.d) + dx;
             uint2 pk2 = make_uint2(0u, 0u);
             if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
               const int iy0 = (int)floorf(py), ix0 = (int)floorf(px);
@@ -283,15 +303,13 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
               pk2.y = f2_to_h2<TH>(mk * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z),
                                    mk * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w));
             }
-            sts64(a_row + ((((uint32_t)(g >> 1)) << 4) ^ rsw) + (uint32_t)((g & 1) << 3), pk2);
+            sts64(a_row + (((uint32_t)j << 4) ^ rsw), pk2);
           }
         }
-        if (threadIdx.x == 0) dtrace(p.trace, git, 8 + k);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_full(q));   // one arrival per warp
-        if (threadIdx.x == 0) dtrace(p.trace, git, 2 + k);
-        if (k < 2 && valid) load_unit(tap + 3);   // in flight while the MMA drains this stage
+        if (lane == 0) mbar_arrive(a_full(stage));   // one arrival per warp
+        if (tap + kGatherSets < 9 && valid) load_unit(tap + kGatherSets);   // in flight while the MMA drains this stage
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(win_free);   // this warp no longer reads the window of this tile
@@ -320,7 +338,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     // L2 one tile ahead, so the gather warps' dependent loads see L2 rather than HBM latency
     auto prefetch_om = [&](int b, int y0, int x0) {
       if (p.om_blocked) {
-        // 9 taps x (4 blocks x 3G/4 x 512 B) contiguous per tile
+        // 9 taps x (8 blocks x 3G/4 x 256 B) contiguous per tile
         const int tile_id = (b * p.tiles_y + y0 / kTH) * p.tiles_x + x0 / kTW;
         const uint32_t bytes = (uint32_t)(4 * 3 * (p.G / 4) * 512);
         if (lane < 9) {

@@ -745,9 +745,12 @@ __device__ __forceinline__ void epilogue_rows_pipelined(const EpiArgs& a, uint32
 }
 
 // Epilogue of the fused offset|mask producer convolution writing the warp-blocked layout the deformable kernel reads
-// (fami_dcn_desc.om_layout = 2): [tap][tile*4 + quarter][q < 3G/4][lane < 32][4 floats], tile = 16x8 pixels, quarter =
-// 4 rows x 8 columns.  Channel n = tap*3G + 4q + e, so a float4 of four consecutive channels never straddles a tap; the
-// 8 lanes of an 8-pixel row segment store 128 contiguous bytes.  Straight from registers, no staging.
+// (fami_dcn_desc.om_layout = 2): [tap][tile*8 + block][q < 3G/4][16 pixels][4 floats], tile = 16x8 pixels, block = 2 rows x
+// 8 columns (the 16 pixels one gather warp of the deformable kernel owns).  Channel n = tap*3G + 4q + e, so the four
+// channels of a float4 never straddle a tap or a (dy | dx | mask) run; they are stored in the order (e0, e2, e1, e3): the
+// deformable kernel's two lanes of a pixel (offset-group parity 0 / 1) each read ONE float2 = their two groups of the
+// quad, and a warp's load instruction reads 256 contiguous bytes.  The 8 lanes of an 8-pixel row segment store 128
+// contiguous bytes, straight from registers, no staging.
 struct OmBlocked {
   float* base;
   int tiles_x, tiles_y, G3;     // DCN tiles per image, 3*G
@@ -757,8 +760,8 @@ __device__ __forceinline__ void epilogue_rows_om_blocked(const EpiArgs& a, uint3
                                                          int img, int y, int x, const OmBlocked& ob) {
   if (col_begin >= col_end) return;   // warp-uniform
   const int r = ((y & 15) << 3) | (x & 7);
-  const int64_t blk = ((int64_t)(img * ob.tiles_y + (y >> 4)) * ob.tiles_x + (x >> 3)) * 4 + (r >> 5);
-  float* lane_base = ob.base + blk * (int64_t)(ob.G3 * 32) + (r & 31) * 4;     // (3G/4) * 128 floats per block
+  const int64_t blk = ((int64_t)(img * ob.tiles_y + (y >> 4)) * ob.tiles_x + (x >> 3)) * 8 + (r >> 4);
+  float* lane_base = ob.base + blk * (int64_t)(ob.G3 * 16) + (r & 15) * 4;     // (3G/4) * 64 floats per block
   for (int c0 = col_begin; c0 < col_end; c0 += 16) {
     const int ch0 = a.ch_base + c0;
     if (ch0 >= a.Cout) break;   // warp-uniform
@@ -773,12 +776,12 @@ __device__ __forceinline__ void epilogue_rows_om_blocked(const EpiArgs& a, uint3
         const float4 sh = lds128f(a.s_shift + (uint32_t)c4 * 4u);
         const int tap = c4 / ob.G3, f = c4 - tap * ob.G3;
         if (valid) {
-          float4 o;
+          float4 o;   // (e0, e2, e1, e3)
           o.x = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
-          o.y = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
-          o.z = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
+          o.z = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
+          o.y = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
           o.w = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
-          *reinterpret_cast<float4*>(lane_base + (int64_t)tap * ob.tap_stride + (f >> 2) * 128) = o;
+          *reinterpret_cast<float4*>(lane_base + (int64_t)tap * ob.tap_stride + (f >> 2) * 64) = o;
         }
       }
     }

@@ -399,24 +399,27 @@ DCN_TILE_H, DCN_TILE_W = 16, 8      # pixel tile of the tensor-core DCN kernel (
 def om_blocked_numel(B, H, W, G, k=3):
     """Elements of the warp-blocked offset|mask buffer (fami_dcn_desc.om_layout = 2)."""
     ty, tx = (H + DCN_TILE_H - 1) // DCN_TILE_H, (W + DCN_TILE_W - 1) // DCN_TILE_W
-    return k * k * B * ty * tx * 4 * (3 * G // 4) * 128
+    return k * k * B * ty * tx * 8 * (3 * G // 4) * 64
 
 
 def om_to_blocked(om, G, k=3):
     """tap-major NHWC [B, 27G, H, W] (tap_major_perm order) -> warp-blocked layout
-    [tap][image tile * 4 + warp quarter][q < 3G/4][lane < 32][4 floats]: the 32 pixels of a 4-row x 8-column
-    quarter of a 16x8 tile are the 32 lanes, so one 16-byte load per lane reads 512 contiguous bytes.
-    Host-side converter for tests and tools; in the model the producer convolution writes this layout directly."""
+    [tap][image tile * 8 + block][q < 3G/4][16 pixels][4 floats]: a block is 2 rows x 8 columns of a 16x8 tile (the 16
+    pixels of one gather warp of the deformable kernel); the four floats are channels 4q + (0, 2, 1, 3) of the tap's
+    [dy(G) | dx(G) | mask(G)] run, so each of a pixel's two lanes (offset-group parity) reads one float2 and a warp's
+    load reads 256 contiguous bytes.  Host-side converter for tests and tools; in the model the producer convolution
+    writes this layout directly."""
     B, FC, H, W = om.shape
     K, Q = k * k, 3 * G // 4
     ty, tx = (H + DCN_TILE_H - 1) // DCN_TILE_H, (W + DCN_TILE_W - 1) // DCN_TILE_W
     t = om.permute(0, 2, 3, 1).reshape(B, H, W, K, Q, 4).float()
+    t = t[..., [0, 2, 1, 3]]
     if ty * DCN_TILE_H != H or tx * DCN_TILE_W != W:
         pad = torch.zeros((B, ty * DCN_TILE_H, tx * DCN_TILE_W, K, Q, 4), dtype=torch.float32, device=om.device)
         pad[:, :H, :W] = t
         t = pad
     t = t.reshape(B, ty, DCN_TILE_H, tx, DCN_TILE_W, K, Q, 4).permute(5, 0, 1, 3, 2, 4, 6, 7)   # K,B,ty,tx,yy,xx,Q,4
-    t = t.reshape(K, B, ty, tx, 4, 32, Q, 4).permute(0, 1, 2, 3, 4, 6, 5, 7)                     # K,B,ty,tx,w,Q,lane,4
+    t = t.reshape(K, B, ty, tx, 8, 16, Q, 4).permute(0, 1, 2, 3, 4, 6, 5, 7)                     # K,B,ty,tx,blk,Q,px16,4
     return t.contiguous().reshape(-1)
 
 

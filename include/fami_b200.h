@@ -165,13 +165,16 @@ typedef struct fami_dcn_desc {
                                        1: fused tap-major -- `offset` points at ONE NHWC buffer holding, per pixel,
                                        [9 taps][dy(G) | dx(G) | mask(G)] (off_pitch >= 27G), `mask` is ignored;
                                        2: fused warp-blocked -- `offset` points at ONE dense buffer
-                                       [9 taps][image tile * 4 + quarter][q < 3G/4][32 lanes][4 floats] over 16x8-pixel
-                                       tiles (tile = (b * ceil(H/16) + y/16) * ceil(W/8) + x/8, quarter and lane from
-                                       r = (y%16)*8 + x%8: quarter = r/32, lane = r%32), where the 4 floats are channels
-                                       4q..4q+3 of the tap's [dy(G) | dx(G) | mask(G)] run; pitches and `mask` ignored.
+                                       [9 taps][image tile * 8 + block][q < 3G/4][16 pixels][4 floats] over 16x8-pixel
+                                       tiles (tile = (b * ceil(H/16) + y/16) * ceil(W/8) + x/8; block and pixel from
+                                       r = (y%16)*8 + x%8: block = r/16 (2 rows x 8 columns), pixel = r%16), where the
+                                       4 floats are channels 4q + (0, 2, 1, 3) of the tap's [dy(G) | dx(G) | mask(G)]
+                                       run; pitches and `mask` ignored.
                                        Layouts 1 and 2 are the 16-bit tensor-core kernel's; the alignment head's fused
-                                       offset|mask convolution writes layout 2 (fami_conv_desc.om_groups) so that every
-                                       offset load instruction of the deformable kernel reads 512 contiguous bytes.  */
+                                       offset|mask convolution writes layout 2 (fami_conv_desc.om_groups): a gather warp
+                                       of the deformable kernel is 16 pixels x 2 offset-group parities, each lane reads
+                                       one float2 (its two groups of quad q) and every load instruction of the warp
+                                       256 contiguous bytes.  */
   int32_t dtype;                    /* storage of x/out: FAMI_F32 or FAMI_BF16; offset, mask, packed
                                        weights and bias are always float (sub-pixel precision)        */
 } fami_dcn_desc;

@@ -221,9 +221,12 @@ def test_offset_layout_host_logic():
     blk = ops.om_to_blocked(om, G)
     assert blk.numel() == ops.om_blocked_numel(B, H, W, G) == om.numel()
     assert torch.equal(torch.sort(blk).values, torch.sort(om.reshape(-1)).values)
-    # element (b=1, y=17, x=9, tap=3, channel-in-tap f=7): tile (1,1) of image 1, r = 1*8+1 = 9 -> quarter 0, lane 9
+    # element (b=1, y=17, x=9, tap=3, channel-in-tap f=7): tile (1,1) of image 1, r = 1*8+1 = 9 -> block 0, pixel 9;
+    # f = 7 -> quad 1, element 3 -> stored at position 3 of the (0, 2, 1, 3) order
     Q = 3 * G // 4
     tiles = (H // 16) * (W // 8)
     tile = 1 * tiles + 1 * (W // 8) + 1
-    idx = ((((3 * (B * tiles) + tile) * 4 + 0) * Q + 7 // 4) * 32 + 9) * 4 + 7 % 4
+    idx = ((((3 * (B * tiles) + tile) * 8 + 0) * Q + 7 // 4) * 16 + 9) * 4 + 3
     assert float(blk[idx]) == float(om[1, 3 * 3 * G + 7, 17, 9])
+    # f = 5 (quad 1, element 1) sits at position 2 of its float4
+    assert float(blk[idx - 1]) == float(om[1, 3 * 3 * G + 5, 17, 9])

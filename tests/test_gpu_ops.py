@@ -623,8 +623,8 @@ def test_offset_conv_blocked_layout_and_dcn(shape):
             ty, tx = (H + 15) // 16, (W + 7) // 8
             inside = torch.zeros((B, ty * 16, tx * 8), dtype=torch.bool, device=DEV)
             inside[:, :H, :W] = True
-            msk = inside.reshape(B, ty, 16, tx, 8).permute(0, 1, 3, 2, 4).reshape(B, ty, tx, 4, 1, 32, 1)
-            msk = msk.expand(9, B, ty, tx, 4, Q, 32, 4).reshape(-1)
+            msk = inside.reshape(B, ty, 16, tx, 8).permute(0, 1, 3, 2, 4).reshape(B, ty, tx, 8, 1, 16, 1)
+            msk = msk.expand(9, B, ty, tx, 8, Q, 16, 4).reshape(-1)
             assert torch.equal(blk[msk], ref[msk])
             dcn = m.DeformConv2d(C, C, 3, padding=3, dilation=3).to(DEV)
             o1 = dcn(x, None, None, fused_om=nhwc)
