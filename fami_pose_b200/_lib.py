@@ -26,7 +26,7 @@ class ConvDesc(Structure):
 class DcnDesc(Structure):
     _fields_ = [(n, c_int32) for n in (
         "B", "H", "W", "C", "Cout", "G", "kh", "kw", "stride", "pad", "dil",
-        "x_pitch", "off_pitch", "mask_pitch", "out_pitch", "om_layout", "dtype")]
+        "x_pitch", "off_pitch", "mask_pitch", "out_pitch", "om_layout", "dtype", "out_f32")]
 
 
 # name -> (restype, argtypes); mirrors include/fami_b200.h exactly (tests check every symbol)

@@ -353,6 +353,8 @@ int fami_dcn_fwd(const fami_dcn_desc* d, const void* x, const void* offset, cons
   if (int e = check_dcn(d, "fami_dcn_fwd")) return e;
   FAMI_CHECK_ARG(x && offset && (mask || d->om_layout >= 1) && w_packed && out, "fami_dcn_fwd: null pointer");
   FAMI_CHECK_ARG(valid_dtype(d->dtype), "fami_dcn_fwd: bad dtype %d", d->dtype);
+  FAMI_CHECK_ARG(!d->out_f32 || (d->om_layout >= 1 && is_half_dtype(d->dtype)),
+                 "fami_dcn_fwd: out_f32 applies to the 16-bit tensor-core kernel (om_layout 1 / 2)");
   if (d->om_layout >= 1) {
     FAMI_CHECK_ARG(dcn_tc_supported(d), "fami_dcn_fwd: fused tap-major offsets need the 16-bit tensor-core kernel "
                                         "(C <= 64, 4 channels per offset group, 3x3, pad == dil)");

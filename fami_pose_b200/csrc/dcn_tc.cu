@@ -50,7 +50,7 @@ struct DcnTcParams {
   int WH, WW;                       // staged window (pixels)
   int tiles_x, tiles_y, total_tiles;
   int nk, BN;
-  int om_pitch, x_pitch, out_pitch, vec_ok;
+  int om_pitch, x_pitch, out_pitch, vec_ok, out_f32;
   int om_blocked;                   // 1: offsets|masks in the warp-blocked layout (om_layout 2)
   int64_t om_tap_stride;            // floats between taps in the blocked layout = nblk * (3G/4) * 128
   uint32_t win_bytes, w_tile_bytes, ab_format;
@@ -416,7 +416,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     EpiArgs ea;
     ea.s_scale = smem_u32(s_scale); ea.s_shift = smem_u32(s_shift); ea.res = nullptr; ea.y = p.out;
     ea.Cout = p.Cout; ea.BN = p.BN; ea.ch_base = 0; ea.out_pitch = p.out_pitch; ea.res_pitch = 0;
-    ea.out_f32 = 0; ea.relu = 0; ea.vec_ok = p.vec_ok; ea.up = 1; ea.Wout = p.W;
+    ea.out_f32 = p.out_f32; ea.relu = 0; ea.vec_ok = p.vec_ok; ea.up = 1; ea.Wout = p.W;
     ea.spitch = 128 + 16;
     const uint32_t stage = smem_u32(stage_base) + (uint32_t)((warp - kGatherWarps - 1) * 32 * ea.spitch);
     int it = 0;
@@ -488,7 +488,8 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
   p.nk = d->C / 16;
   p.BN = ((d->Cout + 15) / 16) * 16;
   p.om_pitch = d->off_pitch; p.x_pitch = d->x_pitch; p.out_pitch = d->out_pitch;
-  p.vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (d->out_pitch % 8 == 0);
+  p.out_f32 = d->out_f32 ? 1 : 0;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (d->out_pitch % (d->out_f32 ? 4 : 8) == 0);
   p.win_bytes = (uint32_t)(p.WH * p.WW) * 128u;
   p.w_tile_bytes = (uint32_t)p.BN * 128u;
   p.ab_format = d->dtype == FAMI_F16 ? 0u : 1u;

@@ -286,9 +286,10 @@ def conv_offsets_blocked(x, conv, G, out=None):
         raise ValueError("conv_offsets_blocked: 3x3 stride-1 same conv with 27*G output channels expected")
     if out is None:
         out = torch.empty(om_blocked_numel(N, H, W, G), dtype=torch.float32, device=x.device)
-    w = packed_weight(conv, conv.weight, x.dtype)
+    code = conv_code(x, Cin)
+    w = packed_weight(conv, conv.weight, code)
     _, shift = folded_affine(conv.bias, None)
-    d = ConvDesc(N, H, W, Cin, Cout, k, k, 1, pad, dil, H, W, 1, 0, ip, 0, 0, _code(x.dtype), F32, 0, G)
+    d = ConvDesc(N, H, W, Cin, Cout, k, k, 1, pad, dil, H, W, 1, 0, ip, 0, 0, code, F32, 0, G)
     _lib.call("fami_conv2d_bn_act_fwd", ctypes.byref(d), _ptr(x), _ptr(w), None, _ptr(shift), None, _ptr(out), None,
               _stream())
     return out
@@ -377,8 +378,29 @@ def upsample_nearest(x, factor):
 # ------------------------------------------------------------------------------------------------
 
 def dcn_fused_supported(C, G, dtype):
-    """True if the 16-bit tensor-core DCN kernel (fused tap-major offsets) takes this shape."""
-    return dtype in (torch.float16, torch.bfloat16) and C % 16 == 0 and C <= 64 and C % G == 0 and C // G == 4
+    """True if the tensor-core DCN kernel (fused tap-major offsets) takes this shape: 16-bit activations, or the fp32
+    activations of the 'tf32' arm (cast to fp16 -- the same 11-bit significand as TF32 -- on the way in, fp32 out)."""
+    half = dtype in (torch.float16, torch.bfloat16) or (dtype == torch.float32 and _PRECISION == "tf32")
+    return half and C % 16 == 0 and C <= 64 and C % G == 0 and C // G == 4
+
+
+def cast_nhwc(x, dtype, out=None):
+    """Elementwise storage cast of an NHWC(+pitch) activation (fami_bn_apply_act with an identity affine)."""
+    _need_cuda(x)
+    N, C, H, W, p = meta(x)
+    if out is None:
+        out = empty_nhwc(N, C, H, W, dtype, x.device)
+    key = (C, x.device)
+    ident = _IDENT.get(key)
+    if ident is None:
+        ident = _IDENT[key] = (torch.ones(C, dtype=torch.float32, device=x.device),
+                               torch.zeros(C, dtype=torch.float32, device=x.device))
+    _lib.call("fami_bn_apply_act", _ptr(x), _code(x.dtype), p, _ptr(ident[0]), _ptr(ident[1]), None, 0, _ptr(out),
+              meta(out)[4], _code(dtype), N, H, W, C, 1, 0, _stream())
+    return out
+
+
+_IDENT = {}
 
 
 def tap_major_perm(G, k=3):
@@ -430,8 +452,14 @@ def dcn_fwd(x, offset, mask, weight, bias, owner, pad=3, dil=3, out=None, fused_
     _need_cuda(x, offset, mask, fused_om)
     B, C, H, W, xp = meta(x)
     Cout, Cin, kh, kw = weight.shape
+    out_f32 = 0
+    if x.dtype == torch.float32 and (blocked_om is not None or fused_om is not None):
+        # tf32 arm: the gather and the contraction run on fp16 multiplicands (11-bit significand, as TF32), fp32 out
+        x = cast_nhwc(x, torch.float16)
+        xp = meta(x)[4]
+        out_f32 = 1
     if out is None:
-        out = empty_nhwc(B, Cout, H, W, x.dtype, x.device)
+        out = empty_nhwc(B, Cout, H, W, torch.float32 if out_f32 else x.dtype, x.device)
     outp = meta(out)[4]
     b = bias.detach().float() if bias is not None else None
     if blocked_om is not None:
@@ -441,7 +469,7 @@ def dcn_fwd(x, offset, mask, weight, bias, owner, pad=3, dil=3, out=None, fused_
             raise ValueError("warp-blocked DCN offsets need 16-bit x, C <= 64, 4 channels per offset group and a "
                              "float32 buffer of om_blocked_numel elements")
         w = packed_weight(owner, weight, x.dtype)
-        d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, 0, 0, outp, 2, _code(x.dtype))
+        d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, 0, 0, outp, 2, _code(x.dtype), out_f32)
         _lib.call("fami_dcn_fwd", ctypes.byref(d), _ptr(x), _ptr(blocked_om), None, _ptr(w), _ptr(b), _ptr(out), _stream())
         return out
     if fused_om is not None:
@@ -452,7 +480,7 @@ def dcn_fwd(x, offset, mask, weight, bias, owner, pad=3, dil=3, out=None, fused_
         if Cin != C or not dcn_fused_supported(C, G, x.dtype):
             raise ValueError("fused tap-major DCN needs 16-bit x, C <= 64 and 4 channels per offset group")
         w = packed_weight(owner, weight, x.dtype)      # UMMA B operand: [CoutPad][9][64] half
-        d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, fp_, 0, outp, 1, _code(x.dtype))
+        d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, fp_, 0, outp, 1, _code(x.dtype), out_f32)
         _lib.call("fami_dcn_fwd", ctypes.byref(d), _ptr(x), _ptr(fused_om), None, _ptr(w), _ptr(b), _ptr(out), _stream())
         return out
     oB, OC, oH, oW, offp = meta(offset)

@@ -175,8 +175,12 @@ typedef struct fami_dcn_desc {
                                        of the deformable kernel is 16 pixels x 2 offset-group parities, each lane reads
                                        one float2 (its two groups of quad q) and every load instruction of the warp
                                        256 contiguous bytes.  */
-  int32_t dtype;                    /* storage of x/out: FAMI_F32 or FAMI_BF16; offset, mask, packed
+  int32_t dtype;                    /* storage of x/out: FAMI_F32 or FAMI_F16 / FAMI_BF16; offset, mask, packed
                                        weights and bias are always float (sub-pixel precision)        */
+  int32_t out_f32;                  /* 1 (16-bit dtype, layouts 1 / 2 only): `out` is float while x stays 16-bit -- the
+                                       tf32 arm's deformable convolutions: x is cast to fp16 (same 11-bit significand as
+                                       TF32), the contraction runs on kind::f16 with fp32 accumulation, the result
+                                       returns to the fp32 activation stream.  0: out has the storage type of x.       */
 } fami_dcn_desc;
 
 int fami_dcn_fwd(const fami_dcn_desc* d, const void* x, const void* offset, const void* mask,

@@ -526,6 +526,44 @@ def test_dcn_tc_fused_vs_oracle(shape, prec):
         m.set_precision("fp32")
 
 
+@pytest.mark.parametrize("shape", [(2, 48, 48, 12, 33, 21, 2.0), (1, 32, 32, 8, 16, 8, 1.0), (1, 48, 48, 12, 40, 30, 14.0)])
+def test_dcn_tf32_arm_vs_oracle(shape):
+    """The 'tf32' arm's deformable convolution: fp32 x in, fp32 out, the gather and the contraction on fp16 multiplicands
+    (x cast on the way in: the same 11-bit significand as TF32), fp32 accumulation, fp32 offsets -- vs the numpy oracle on
+    the UNROUNDED fp32 operands.  Tolerance 3e-3*max|ref| (three 2^-11 roundings of the sampled column per term)."""
+    import fami_pose_b200 as m
+    from fami_pose_b200 import layers, ops
+    B, C, Cout, G, H, W, sig = shape
+    m.set_precision("tf32")
+    try:
+        g = torch.Generator().manual_seed(B * 1000 + C + H)
+        x = torch.randn(B, C, H, W, generator=g)
+        off = sig * torch.randn(B, 18 * G, H, W, generator=g)
+        msk = torch.randn(B, 9 * G, H, W, generator=g)
+        w = 0.05 * torch.randn(Cout, C, 3, 3, generator=g)
+        b = 0.1 * torch.randn(Cout, generator=g)
+        ref = torch.from_numpy(fo.dcn_fwd(x.numpy(), off.numpy(), msk.numpy(), w.numpy(), b.numpy()))
+        mod = layers.DeformConv2d(C, Cout, 3, padding=3, dilation=3).to(DEV)
+        with torch.no_grad():
+            mod.weight.copy_(w.to(DEV))
+            mod.bias.copy_(b.to(DEV))
+            om = ops.to_nhwc(_to_tap_major(off, msk, G).to(DEV), torch.float32)
+            blk = ops.om_to_blocked(om, G)
+            xd = ops.to_nhwc(x.to(DEV), torch.float32)
+            out = mod(xd, None, None, blocked_om=blk, groups=G)
+            wide = ops.empty_nhwc(B, 2 * Cout, H, W, torch.float32, DEV)          # output slice of a wider buffer
+            mod(xd, None, None, out=wide[:, Cout:], blocked_om=blk, groups=G)
+        assert out.dtype == torch.float32
+        got = ops.to_nchw(out).cpu()
+        assert torch.equal(ops.to_nchw(wide[:, Cout:]).cpu(), got)
+        tol = 3e-3 * float(ref.abs().max()) + 1e-3
+        err = float((got - ref).abs().max())
+        print("dcn tf32 arm", shape, "err", err, "tol", tol)
+        assert err <= tol
+    finally:
+        m.set_precision("fp32")
+
+
 def test_dcn_tc_zero_offset_equals_dilated_conv_full_size():
     """Property at config-2 size (B=32): zero offsets + unit mask == the tensor-core dilated conv."""
     import fami_pose_b200 as m
