@@ -408,14 +408,16 @@ def train_record(ctx, steps, warmup):
     world, rank, dev, args = ctx["world"], ctx["rank"], ctx["dev"], ctx["args"]
     from fami_pose_b200.train import TrainStep
     B = args.batch
-    backbone = "fp16" if args.precision in ("tf32", "fp32") else args.precision
-    backbone = os.environ.get("FAMI_TRAIN_BACKBONE", backbone)
-    fp.set_precision("fp32")
+    # the frozen backbone runs on the headline arm (tf32 by default: the configuration tests/test_gpu_train.py pins against
+    # the reference's float64 autograd); FAMI_TRAIN_BACKBONE=fp16 puts it on the 16-bit arm
+    backbone = os.environ.get("FAMI_TRAIN_BACKBONE", "tf32" if args.precision == "fp32" else args.precision)
+    head = os.environ.get("FAMI_TRAIN_HEAD", "tf32")      # 'tf32': tensor-core forward + dgrad of the trainable head; 'fp32': SIMT
+    fp.set_precision(head)
     model = fp.Alignment_V15(synth.make_cfg(WIDTH, J), "train")
     sd = synth.seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()})
     model.load_state_dict(sd)
     model = model.to(dev).train()
-    if backbone != "fp32":
+    if backbone != head:
         model.backbone_precision = backbone
     host = tuple(t.pin_memory() for t in synth.synthetic_clip(B, seed=synth.SEED + rank))
     devs = tuple(t.to(dev) for t in host)
@@ -424,28 +426,37 @@ def train_record(ctx, steps, warmup):
     step = TrainStep(model)
     n_train = sum(p.numel() for p in step.buckets.params)
     stream = torch.cuda.current_stream()
-
-    def e2e(_k):
-        for d_, h_ in zip(devs, host):
-            d_.copy_(h_, non_blocking=True)
-        loss, _ = step(*devs)
-        loss_host.copy_(loss, non_blocking=True)
-
     l0 = fp._lib.launch_count()
     step(*devs)
     torch.cuda.synchronize()
     launches = fp._lib.launch_count() - l0
-    ms = timed_region(ctx, stream, lambda k: step(*devs), steps, warmup)
+    graphed, graph_note = False, ""
+    if not args.no_graph and os.environ.get("FAMI_TRAIN_GRAPH", "1") != "0":
+        try:      # the whole step (forward, loss, backward, gradient all-reduce, Adam) as ONE CUDA graph
+            step.capture(*devs)
+            graphed = True
+        except Exception as e:   # e.g. a collective that cannot be captured on this NCCL build: time the eager step
+            graph_note = "capture failed, eager step timed: " + repr(e)[:160]
+            torch.cuda.synchronize()
+    run = (lambda: step.replay()) if graphed else (lambda: step(*devs))
+
+    def e2e(_k):
+        for d_, h_ in zip(devs, host):
+            d_.copy_(h_, non_blocking=True)
+        loss, _ = run()
+        loss_host.copy_(loss, non_blocking=True)
+
+    ms = timed_region(ctx, stream, lambda k: run(), steps, warmup)
     ms_e2e = timed_region(ctx, stream, e2e, steps, 1)
     clips = B * world * steps
     rec = {"value": clips / (ms / 1000.0), "unit": UNIT, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
-           "dtype": "f32 head / %s frozen backbone" % backbone,
+           "dtype": "%s head (f32 storage) / %s frozen backbone" % (head, backbone),
            "config": {"workload": "BASELINE config 2/3 TRAIN step: forward (train-mode BN) + JointsMSE + MI losses + backward of "
                                   "the head (HRNet frozen, reference default) + gradient all-reduce + Adam; batch 32 per GPU",
                       "batch_per_gpu": B, "global_batch": B * world,
                       "collective": "one bucketed NCCL all-reduce of %d fp32 gradients per step over %d rank(s), inside the "
                                     "timed region" % (n_train, world),
-                      "cuda_graph": False},
+                      "cuda_graph": graphed, "note": graph_note},
            "e2e": {"value": clips / (ms_e2e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                    "ms_per_step": ms_e2e / steps},
            "gpu_launches": launches * steps, "launches_per_step": launches}

@@ -57,4 +57,17 @@ def patch_reference():
     patched.append("kornia.geometry.warp_affine")
     rebind("posetimation.zoo.Alignment.Alignment_V15", conv_bn_relu=conv_bn_relu,
            ChainOfBasicBlocks=ChainOfBasicBlocks, HRNetPlus=HRNetPlus, DeformConv2d=DeformConv2d)
+    # engine plug-in registries (engine/defaults/constant.py:9-11; looked up by cfg.CORE_FUNCTION, engine/core/base.py:65,
+    # and cfg.MODEL.NAME, posetimation/zoo/build.py:65): the entries are REPLACED under the reference's own names, so a
+    # config naming AlignmentMIFunction_Term6_V1 / Alignment_V15 runs the fami versions with no config change
+    try:
+        const = importlib.import_module("engine.defaults.constant")
+        from .train import AlignmentMIFunction_Term6_V1
+        for reg_name, obj in (("CORE_FUNCTION_REGISTRY", AlignmentMIFunction_Term6_V1), ("MODEL_REGISTRY", Alignment_V15)):
+            reg = getattr(const, reg_name, None)
+            if reg is not None and hasattr(reg, "_obj_map"):
+                reg._obj_map[obj.__name__] = obj
+                patched.append("engine.defaults.constant.%s[%s]" % (reg_name, obj.__name__))
+    except Exception:
+        pass
     return patched

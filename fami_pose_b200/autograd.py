@@ -97,16 +97,21 @@ class ConvBnActFunction(torch.autograd.Function):
         k, stride, pad, dil = geom
         Cout = weight.shape[0]
         dev = x.device
-        wp = ops.pack_weight(weight, torch.float32)
+        code = ops.conv_code(x, weight.shape[1])      # F32: exact SIMT kernels; TF32 ('tf32' arm): tcgen05 kind::tf32
+        wp = ops.pack_weight(weight, code)
         b = bias.detach().float().contiguous() if bias is not None else None
         raw = mean = invstd = None
         if bn is None:
-            y = ops._conv_raw(x, wp, Cout, k, stride, pad, dil, None, b, residual, relu, 1, None, None, torch.float32)
+            y = ops._conv_raw(x, wp, Cout, k, stride, pad, dil, None, b, residual, relu, 1, None, None, torch.float32, code=code)
         else:
             training = bn.training or bn.running_mean is None
+            fused_stats = training and code == F32      # the tensor-core kernels take the statistics in a separate pass
             stats = torch.zeros(2 * Cout, dtype=torch.float64, device=dev) if training else None
-            raw = ops._conv_raw(x, wp, Cout, k, stride, pad, dil, None, b, None, False, 1, None, stats, torch.float32)
+            raw = ops._conv_raw(x, wp, Cout, k, stride, pad, dil, None, b, None, False, 1, None, stats if fused_stats else None,
+                                torch.float32, code=code)
             N, _, Ho, Wo, rawp = ops.meta(raw)
+            if training and not fused_stats:
+                _lib.call("fami_bn_stats", ops._ptr(raw), F32, rawp, N * Ho * Wo, Cout, ops._ptr(stats), ops._stream())
             scale = torch.empty(Cout, dtype=torch.float32, device=dev)
             shift = torch.empty_like(scale)
             if training:
@@ -171,13 +176,48 @@ class ConvBnActFunction(torch.autograd.Function):
 def conv_bn_act(x, conv, bn, relu, residual, weight=None, bias=None):
     """Differentiable ops.conv_bn_act (fp32 arm, no upsample-on-write, freshly allocated output)."""
     if x.dtype != torch.float32:
-        raise NotImplementedError("the differentiable path runs on the exact-fp32 arm: fami.set_precision('fp32')")
+        raise NotImplementedError("the differentiable path runs on fp32 storage: fami.set_precision('fp32' | 'tf32')")
     weight = conv.weight if weight is None else weight
     bias = conv.bias if bias is None else bias
     geom = (conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0])
     gamma = bn.weight if bn is not None else None
     beta = bn.bias if bn is not None else None
     return ConvBnActFunction.apply(x, weight, bias, gamma, beta, residual, geom, bn, relu)
+
+
+class UpsampleAddReluFunction(torch.autograd.Function):
+    """y = [ReLU](residual + nearest_upsample(t, up)): the tail of an HRNet fuse-layer term (hrnet.py:99-112 Interpolate +
+    the running sum / final ReLU of :151-172).  Inference fuses this into the 1x1 conv's store; the differentiable path
+    runs it as its own launch (fami_bn_apply_act with an identity affine) so that autograd can see it, with
+    fami_upsample_add_bwd as the backward (replica sum + ReLU mask + residual gradient in one pass)."""
+
+    @staticmethod
+    def forward(ctx, t, residual, up, relu):
+        N, C, H, W, tp = ops.meta(t)
+        dev = t.device
+        one = torch.ones(C, dtype=torch.float32, device=dev)
+        zero = torch.zeros(C, dtype=torch.float32, device=dev)
+        y = ops.empty_nhwc(N, C, H * up, W * up, torch.float32, dev)
+        rp = ops.meta(residual)[4] if residual is not None else 0
+        _lib.call("fami_bn_apply_act", ops._ptr(t), F32, tp, ops._ptr(one), ops._ptr(zero), ops._ptr(residual), rp, ops._ptr(y),
+                  ops.meta(y)[4], F32, N, H, W, C, up, int(bool(relu)), ops._stream())
+        ctx.up, ctx.relu, ctx.has_res = up, bool(relu), residual is not None
+        ctx.small = (N, C, H, W)
+        ctx.save_for_backward(y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        N, C, H, W = ctx.small
+        g = _nhwc_f32(gy)
+        need_res = ctx.has_res and ctx.needs_input_grad[1]
+        gt = ops.empty_nhwc(N, C, H, W, torch.float32, g.device)
+        gres = ops.empty_nhwc(N, C, H * ctx.up, W * ctx.up, torch.float32, g.device) if need_res else None
+        _lib.call("fami_upsample_add_bwd", ops._ptr(g), ops.meta(g)[4], ops._ptr(y), ops.meta(y)[4] if y is not None else 0,
+                  ops._ptr(gt), ops.meta(gt)[4], ops._ptr(gres), ops.meta(gres)[4] if gres is not None else 0, N, H, W, C,
+                  ctx.up, ops._stream())
+        return gt, gres, None, None
 
 
 class LinearFunction(torch.autograd.Function):

@@ -59,6 +59,10 @@ int linear_bwd_launch(const float* x, const float* w, const float* gy, float* gx
                       cudaStream_t st);
 int adam_step_launch(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                      float bc1, float bc2_sqrt, cudaStream_t st);
+int adam_step_dev_launch(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1, float beta2,
+                         float eps, cudaStream_t st);
+int upsample_add_bwd_launch(const float* gy, int gp, const float* y, int yp, float* gsmall, int sp, float* gres, int rp, int N,
+                            int Ho, int Wo, int C, int up, cudaStream_t st);
 int final_preds_launch(const void* hm, int dt, int pitch, const int32_t* idx, const float* maxv, const float* center,
                        const float* scale, float* preds, int B, int H, int W, int J, cudaStream_t st);
 int pck_accuracy_launch(const int32_t* pidx, const float* pmax, const int32_t* tidx, const float* tmax, double* out, int B,
@@ -209,7 +213,7 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
 
 static int check_conv_bwd(const fami_conv_desc* d, const char* who) {
   FAMI_CHECK_ARG(d, "%s: null desc", who);
-  FAMI_CHECK_ARG(d->dtype == FAMI_F32 && d->out_dtype == FAMI_F32, "%s: fp32 storage only", who);
+  FAMI_CHECK_ARG((d->dtype == FAMI_F32 || d->dtype == FAMI_TF32) && d->out_dtype == FAMI_F32, "%s: fp32 storage only", who);
   FAMI_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "%s: bad shape", who);
   FAMI_CHECK_ARG(d->kh == d->kw && (d->kh == 1 || d->kh == 3), "%s: kernel %dx%d unsupported", who, d->kh, d->kw);
   FAMI_CHECK_ARG(d->stride >= 1 && d->dil >= 1 && d->pad >= 0 && d->up == 1, "%s: bad stride/dil/pad/up", who);
@@ -223,7 +227,7 @@ static int check_conv_bwd(const fami_conv_desc* d, const char* who) {
 int fami_pack_conv_weight_dgrad(const float* w_oihw, float* scratch_oihw, void* w_packed_t, int Cout, int Cin, int kh,
                                 int kw, int dtype, void* stream) {
   FAMI_CHECK_ARG(w_oihw && scratch_oihw && w_packed_t, "fami_pack_conv_weight_dgrad: null pointer");
-  FAMI_CHECK_ARG(dtype == FAMI_F32, "fami_pack_conv_weight_dgrad: fp32 only");
+  FAMI_CHECK_ARG(dtype == FAMI_F32 || dtype == FAMI_TF32, "fami_pack_conv_weight_dgrad: fp32 storage only (FAMI_F32 / FAMI_TF32)");
   if (int e = flip_transpose_launch(w_oihw, scratch_oihw, Cout, Cin, kh, kw, (cudaStream_t)stream)) return e;
   return fami_pack_conv_weight(scratch_oihw, w_packed_t, Cin, Cout, kh, kw, dtype, stream);
 }
@@ -232,6 +236,8 @@ int fami_conv2d_dgrad(const fami_conv_desc* d, const float* grad_y, const float*
   if (int e = check_conv_bwd(d, "fami_conv2d_dgrad")) return e;
   FAMI_CHECK_ARG(grad_y && w_packed_t && grad_x, "fami_conv2d_dgrad: null pointer");
   FAMI_CHECK_ARG(d->stride > 1 || d->dil * (d->kh - 1) - d->pad >= 0, "fami_conv2d_dgrad: pad larger than the filter reach");
+  FAMI_CHECK_ARG(d->dtype == FAMI_F32 || d->stride == 1, "fami_conv2d_dgrad: the tf32 tensor-core path takes stride-1 convolutions "
+                                                         "(strided dgrad runs the fp32 gather kernel: pass FAMI_F32)");
   return conv_dgrad_launch(d, grad_y, w_packed_t, grad_x, (cudaStream_t)stream);
 }
 
@@ -239,6 +245,7 @@ int fami_conv2d_wgrad(const fami_conv_desc* d, const float* x, const float* grad
                       void* stream) {
   if (int e = check_conv_bwd(d, "fami_conv2d_wgrad")) return e;
   FAMI_CHECK_ARG(x && grad_y && grad_w_oihw, "fami_conv2d_wgrad: null pointer");
+  FAMI_CHECK_ARG(d->dtype == FAMI_F32, "fami_conv2d_wgrad: fp32 arithmetic (pass FAMI_F32)");
   return conv_wgrad_launch(d, x, grad_y, grad_w_oihw, grad_bias, (cudaStream_t)stream);
 }
 
@@ -273,6 +280,24 @@ int fami_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   return adam_step_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2),
                           (cudaStream_t)stream);
+}
+
+int fami_adam_step_graph(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* hyper_dev,
+                         float beta1, float beta2, float eps, void* stream) {
+  FAMI_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && hyper_dev && n > 0, "fami_adam_step_graph: bad arguments");
+  return adam_step_dev_launch(param, grad, exp_avg, exp_avg_sq, n, hyper_dev, beta1, beta2, eps, (cudaStream_t)stream);
+}
+
+int fami_upsample_add_bwd(const float* grad_y, int gy_pitch, const float* y, int y_pitch, float* grad_small, int gs_pitch,
+                          float* grad_res, int gr_pitch, int N, int Ho, int Wo, int C, int up, void* stream) {
+  FAMI_CHECK_ARG(grad_y && grad_small, "fami_upsample_add_bwd: null pointer");
+  FAMI_CHECK_ARG(N > 0 && Ho > 0 && Wo > 0 && C > 0 && C % 4 == 0 && (up == 1 || up == 2 || up == 4 || up == 8),
+                 "fami_upsample_add_bwd: bad shape (C multiple of 4, up in 1/2/4/8)");
+  FAMI_CHECK_ARG(gy_pitch % 4 == 0 && gs_pitch % 4 == 0 && (!y || y_pitch % 4 == 0) && (!grad_res || gr_pitch % 4 == 0) &&
+                     aligned(grad_y, 16) && aligned(grad_small, 16) && (!y || aligned(y, 16)) && (!grad_res || aligned(grad_res, 16)),
+                 "fami_upsample_add_bwd: 16-byte aligned operands with pitches multiple of 4");
+  return upsample_add_bwd_launch(grad_y, gy_pitch, y, y_pitch, grad_small, gs_pitch, grad_res, gr_pitch, N, Ho, Wo, C, up,
+                                 (cudaStream_t)stream);
 }
 
 int fami_frames_u8_normalize(const uint8_t* frames, int64_t src_frame_stride, float* out, int nframes, int H, int W,

@@ -352,7 +352,70 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
   p[i] -= (lr / bc1) * (mi / denom);
 }
 
+// CUDA-graph form: learning rate and bias corrections come from device memory (hyper = {lr, 1 - beta1^t, sqrt(1 - beta2^t)}),
+// so a captured training step replays with the current step count / MultiStepLR value.
+__global__ void adam_step_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                     float* __restrict__ v, int64_t n, const float* __restrict__ hyper, float beta1, float beta2,
+                                     float eps) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lr = hyper[0], bc1 = hyper[1], bc2_sqrt = hyper[2];
+  const float gi = g[i];
+  const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+  const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
+// sum of the up x up replicas of a nearest-upsampled gradient (+ optional ReLU mask from the block output y):
+// backward of Interpolate(scale_factor=up, mode='nearest') fused with the `+ residual -> ReLU` of the HRNet fuse layers
+// (hrnet.py:99-112,151-172).  g' = grad_y * [y > 0]; grad_small[n,yo,xo,c] = sum_{dy,dx} g'[n,yo*up+dy,xo*up+dx,c];
+// grad_res = g' (may be null).  One thread per (low-resolution pixel, 4 channels).
+__global__ void upsample_add_bwd_kernel(const float* __restrict__ gy, int gp, const float* __restrict__ y, int yp,
+                                        float* __restrict__ gsmall, int sp, float* __restrict__ gres, int rp, int N, int Ho,
+                                        int Wo, int C, int up) {
+  const int c4n = C >> 2;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)N * Ho * Wo * c4n) return;
+  const int c = (int)(i % c4n) * 4;
+  int64_t pix = i / c4n;
+  const int xo = (int)(pix % Wo);
+  const int yo = (int)((pix / Wo) % Ho);
+  const int n = (int)(pix / ((int64_t)Wo * Ho));
+  const int Wb = Wo * up, Hb = Ho * up;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int dy = 0; dy < up; ++dy)
+    for (int dx = 0; dx < up; ++dx) {
+      const int64_t q = ((int64_t)n * Hb + yo * up + dy) * Wb + xo * up + dx;
+      float4 g = *reinterpret_cast<const float4*>(gy + q * gp + c);
+      if (y) {
+        const float4 o = *reinterpret_cast<const float4*>(y + q * yp + c);
+        g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+      }
+      if (gres) *reinterpret_cast<float4*>(gres + q * rp + c) = g;
+      acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+    }
+  *reinterpret_cast<float4*>(gsmall + pix * sp + c) = acc;
+}
+
 }  // namespace
+
+int adam_step_dev_launch(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1, float beta2,
+                         float eps, cudaStream_t st) {
+  adam_step_dev_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, g, m, v, n, hyper, beta1, beta2, eps);
+  FAMI_CHECK_LAUNCH("adam_step_dev_kernel");
+  return 0;
+}
+
+int upsample_add_bwd_launch(const float* gy, int gp, const float* y, int yp, float* gsmall, int sp, float* gres, int rp, int N,
+                            int Ho, int Wo, int C, int up, cudaStream_t st) {
+  const int64_t tot = (int64_t)N * Ho * Wo * (C / 4);
+  upsample_add_bwd_kernel<<<cdiv(tot, 256), 256, 0, st>>>(gy, gp, y, yp, gsmall, sp, gres, rp, N, Ho, Wo, C, up);
+  FAMI_CHECK_LAUNCH("upsample_add_bwd_kernel");
+  return 0;
+}
 
 int adam_step_launch(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                      float bc1, float bc2_sqrt, cudaStream_t st) {
@@ -377,7 +440,7 @@ int conv_dgrad_launch(const fami_conv_desc* d, const float* gy, const float* wt_
     f.Ho = d->H; f.Wo = d->W;
     f.up = 1; f.relu = 0; f.stats = 0; f.om_groups = 0;
     f.in_pitch = d->out_pitch; f.out_pitch = d->in_pitch; f.res_pitch = 0;
-    f.dtype = FAMI_F32; f.out_dtype = FAMI_F32;
+    f.out_dtype = FAMI_F32;      // f.dtype stays FAMI_F32 (exact SIMT) or FAMI_TF32 (tcgen05 kind::tf32, same kernels as forward)
     return fami_conv2d_bn_act_fwd(&f, gy, wt_packed, nullptr, nullptr, nullptr, gx, nullptr, (void*)st);
   }
   const int CinPad = fami_conv_cout_pad(d->Cin);

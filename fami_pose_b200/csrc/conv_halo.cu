@@ -502,7 +502,7 @@ HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d, int kKC) {
 int conv_halo_supported(const fami_conv_desc* d) {
   if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != d->dil || d->up != 1) return 0;
   const bool tf32 = d->dtype == FAMI_TF32;
-  if (tf32 ? (d->Cin % 8 != 0 || d->in_pitch % 4 != 0) : (d->Cin % 16 != 0 || d->in_pitch % 8 != 0)) return 0;
+  if (tf32 ? (d->Cin % 4 != 0 || d->in_pitch % 4 != 0) : (d->Cin % 16 != 0 || d->in_pitch % 8 != 0)) return 0;
   if (d->dil < 1 || d->dil > 8) return 0;
   // Measured (tools/prof_conv.py, tools/time_conv_shape.py, N=160 fp16): the halo form wins when the weights stay
   // resident in shared memory (Cin <= 64: 48->48 90 us vs 225 us im2col) and when many input channels feed few
@@ -558,7 +558,7 @@ int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, cons
   p.n_tiles = c.n_tiles;
   p.total_tiles = d->N * p.tiles_per_img * c.n_tiles;
   p.cchunks = c.cchunks;
-  p.last_kk = (d->Cin - (c.cchunks - 1) * kKC) / (kKC / 4);
+  p.last_kk = (d->Cin - (c.cchunks - 1) * kKC + kKC / 4 - 1) / (kKC / 4);
   p.Cout = d->Cout; p.BN = c.BN;
   p.relu = d->relu; p.out_f32 = d->out_dtype == FAMI_F32 || d->out_dtype == FAMI_TF32;
   const size_t osz = p.out_f32 ? 4 : 2;

@@ -265,7 +265,9 @@ static inline int kc_of(int dtype) { return dtype == FAMI_TF32 ? 32 : 64; }
 
 int conv_bf16_tc_supported(const fami_conv_desc* d) {
   // K-steps of 32 bytes (16 halves / 8 floats); TMA needs 16-byte pixel strides
-  if (d->dtype == FAMI_TF32 ? (d->Cin % 8 != 0 || d->in_pitch % 4 != 0) : (d->Cin % 16 != 0 || d->in_pitch % 8 != 0)) return 0;
+  // (tf32: Cin a multiple of 4 is enough -- the last 8-channel K-step reads TMA zero fill against zero-padded weights;
+  //  the 324-channel offset|mask gradient of the alignment head needs it)
+  if (d->dtype == FAMI_TF32 ? (d->Cin % 4 != 0 || d->in_pitch % 4 != 0) : (d->Cin % 16 != 0 || d->in_pitch % 8 != 0)) return 0;
   if (d->kh != d->kw || (d->kh != 1 && d->kh != 3)) return 0;
   if (d->stride < 1 || d->stride > 8) return 0;
   if (d->pad > 127 || (d->kh - 1) * d->dil - d->pad > 128) return 0;
@@ -353,7 +355,7 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   p.Ho = d->Ho; p.Wo = d->Wo; p.HoWo = d->Ho * d->Wo;
   p.stride = d->stride; p.pad = d->pad; p.dil = d->dil; p.kw = d->kw; p.taps = d->kh * d->kw;
   p.cchunks = t.cchunks;
-  p.last_kk = (d->Cin - (t.cchunks - 1) * kKC) / (kKC / 4);   // 32-byte K-steps in the last channel chunk
+  p.last_kk = (d->Cin - (t.cchunks - 1) * kKC + kKC / 4 - 1) / (kKC / 4);   // 32-byte K-steps in the last channel chunk
   p.Cout = d->Cout; p.BN = t.BN; p.n_tiles = t.n_tiles; p.m_tiles = (p.M + kBM - 1) / kBM;
   p.up = d->up; p.relu = d->relu;
   p.out_pitch = d->out_pitch; p.res_pitch = d->res_pitch;

@@ -57,7 +57,7 @@ def conv_code(x, Cin=None):
     pitch; the 3-channel stem stays on the exact-fp32 kernel)."""
     if _PRECISION == "tf32" and x.dtype == torch.float32:
         N, C, H, W, p = meta(x)
-        if (Cin or C) % 8 == 0 and p % 4 == 0:
+        if (Cin or C) % 4 == 0 and p % 4 == 0:
             return TF32
     return _code(x.dtype)
 
@@ -309,12 +309,16 @@ def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None, out
             x.requires_grad or conv.weight.requires_grad
             or (bn is not None and bn.weight is not None and bn.weight.requires_grad)
             or (residual is not None and residual.requires_grad)):
-        # differentiable path (fp32 arm): autograd.ConvBnActFunction.  The 16-bit arms are inference arms:
-        # their outputs never carry a grad_fn.
-        if up != 1 or out is not None:
-            raise NotImplementedError("differentiable conv: upsample-on-write / caller-provided outputs are "
-                                      "inference-only (the reference default trains with HRNet frozen)")
+        # differentiable path (fp32 storage: 'fp32' / 'tf32' arms): autograd.ConvBnActFunction.  The 16-bit arms are
+        # inference arms: their outputs never carry a grad_fn.
+        if out is not None:
+            raise NotImplementedError("differentiable conv: caller-provided output slices are inference-only")
         from . import autograd as _ag
+        if up != 1:
+            # fuse-layer term of an un-frozen backbone (hrnet.py:99-112): conv + BN, then upsample + running sum + ReLU as
+            # its own differentiable launch (the inference path replicates on write inside the conv's epilogue)
+            t = _ag.conv_bn_act(x, conv, bn, False, None)
+            return _ag.UpsampleAddReluFunction.apply(t, residual, up, relu)
         return _ag.conv_bn_act(x, conv, bn, relu, residual)
     k = conv.kernel_size[0]
     stride, pad, dil = conv.stride[0], conv.padding[0], conv.dilation[0]
@@ -622,7 +626,8 @@ def _conv_desc_f32(x_shape_meta, Cout, k, stride, pad, dil, out_pitch):
 
 def conv_dgrad(grad_y, weight, x_shape, stride=1, pad=0, dil=1, out=None):
     """d loss / d x of y = conv2d(x, weight): grad_y NHWC fp32 [N,Cout,Ho,Wo], weight OIHW; returns NHWC
-    fp32 [N,Cin,H,W] (x_shape = logical NCHW shape of x)."""
+    fp32 [N,Cin,H,W] (x_shape = logical NCHW shape of x).  On the 'tf32' arm stride-1 dgrad runs on the tensor cores
+    (the forward kernels over the flipped / transposed filter)."""
     _need_cuda(grad_y)
     if grad_y.dtype != torch.float32 or not is_nhwc(grad_y):
         raise ValueError("conv_dgrad: grad_y must be an fp32 NHWC activation")
@@ -634,11 +639,13 @@ def conv_dgrad(grad_y, weight, x_shape, stride=1, pad=0, dil=1, out=None):
     d, Ho, Wo = _conv_desc_f32((N, Cin, H, W, meta(out)[4]), Cout, k, stride, pad, dil, gp)
     if (gN, gC, gH, gW) != (N, Cout, Ho, Wo):
         raise ValueError("conv_dgrad: grad_y shape %s, expected %s" % (tuple(grad_y.shape), (N, Cout, Ho, Wo)))
+    code = conv_code(grad_y, Cout) if stride == 1 else F32
+    d.dtype = code
     w = weight.detach().float().contiguous()
     scratch = torch.empty_like(w)
-    n = _lib.load().fami_packed_weight_elems(Cin, Cout, k, k, F32)
+    n = _lib.load().fami_packed_weight_elems(Cin, Cout, k, k, code)
     wt = torch.empty(n, dtype=torch.float32, device=grad_y.device)
-    _lib.call("fami_pack_conv_weight_dgrad", _ptr(w), _ptr(scratch), _ptr(wt), Cout, Cin, k, k, F32, _stream())
+    _lib.call("fami_pack_conv_weight_dgrad", _ptr(w), _ptr(scratch), _ptr(wt), Cout, Cin, k, k, code, _stream())
     _lib.call("fami_conv2d_dgrad", ctypes.byref(d), _ptr(grad_y), _ptr(wt), _ptr(out), _stream())
     return out
 

@@ -193,7 +193,7 @@ class Alignment_V15(nn.Module):
 
     def _forward_frames(self, x, B, ns):
         C = self.width
-        graph = (torch.is_grad_enabled() and ops.get_precision() == "fp32"
+        graph = (torch.is_grad_enabled() and ops.get_precision() in ("fp32", "tf32")
                  and any(p.requires_grad for p in self.parameters()))
         bp = getattr(self, "backbone_precision", None)
         if graph and bp is not None and bp != ops.get_precision() and not any(
@@ -263,7 +263,7 @@ class Alignment_V15(nn.Module):
         from . import autograd as ag
         C = self.width
         if kf_feat.dtype != torch.float32:
-            raise NotImplementedError("training runs on the exact-fp32 arm: fami.set_precision('fp32')")
+            raise NotImplementedError("training runs on fp32 storage: fami.set_precision('fp32' | 'tf32')")
         L = self.feat_global_offset_layers
         txys, warped = [], []
         for i in range(ns):                                                        # :130-137
@@ -286,7 +286,9 @@ class Alignment_V15(nn.Module):
         all_agg = self.init_feature_agg_block(ag.cat_channels([kf_feat, aligned]))  # :160-161
         final_hm = ops.conv_bn_act(all_agg, self.agg_final_layer, None, relu=False, out_dtype=torch.float32)  # :163
         final_out, kf_out = final_hm.contiguous(), ops.to_nchw(kf_bb_hm)
-        self._last = {"final_hm_nhwc": final_hm, "txy": txy}
+        # detached: a live grad_fn here would keep the whole autograd graph (and its AccumulateGrad nodes) alive until the
+        # next forward, which breaks CUDA-graph capture of the training step on another stream
+        self._last = {"final_hm_nhwc": final_hm.detach(), "txy": txy.detach()}
         if not self.is_train:
             return final_out, kf_out
         mi = [self.feat_label_mi_estimation(all_agg, final_hm),

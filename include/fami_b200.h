@@ -112,8 +112,9 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
  * nn.Conv2d backward as autograd derives it for basic_model.py:44-63 / basic_layer.py:55-73 /
  * Alignment_V15.py:79-106.  `d` is the FORWARD descriptor (up = 1, dtype = out_dtype = FAMI_F32).
  * dgrad consumes the filter flipped and transposed (fami_pack_conv_weight_dgrad: scratch holds
- * Cout*Cin*kh*kw floats; the packing has fami_packed_weight_elems(Cin, Cout, kh, kw, FAMI_F32)
- * elements); stride-1 dgrad runs on the forward kernels, other strides on a gather kernel.
+ * Cout*Cin*kh*kw floats; the packing has fami_packed_weight_elems(Cin, Cout, kh, kw, dtype)
+ * elements); stride-1 dgrad runs on the forward kernels -- d->dtype = FAMI_F32: exact SIMT,
+ * FAMI_TF32: tcgen05 kind::tf32 with a FAMI_TF32 packing -- other strides on an fp32 gather kernel.
  * wgrad ACCUMULATES into grad_w_oihw [Cout][Cin][kh][kw] and grad_bias [Cout] (may be NULL):
  * the caller zeroes them (fp32 atomics over pixel chunks).                                        */
 int fami_pack_conv_weight_dgrad(const float* w_oihw, float* scratch_oihw, void* w_packed_t, int Cout, int Cin,
@@ -220,6 +221,15 @@ int fami_linear_fwd(const float* x, const float* w, const float* b, float* y, in
  * sums of grad_y; any output may be NULL.                                                          */
 int fami_linear_bwd(const float* x, const float* w, const float* grad_y, float* grad_x, float* grad_w,
                     float* grad_b, int M, int K, int N, void* stream);
+/* Backward of the HRNet fuse-layer tail `y = ReLU(residual + nearest_up(t))` (Interpolate, basic_model.py:116-125, inside
+ * hrnet.py:99-112,151-172): g' = grad_y * [y > 0] (y NULL = no ReLU); grad_small [N,Ho,Wo,C] = sum of g' over the up x up
+ * replicas; grad_res (may be NULL) = g'.  grad_y / y / grad_res are [N, Ho*up, Wo*up, C] (pitches in elements).            */
+int fami_upsample_add_bwd(const float* grad_y, int gy_pitch, const float* y, int y_pitch, float* grad_small, int gs_pitch,
+                          float* grad_res, int gr_pitch, int N, int Ho, int Wo, int C, int up, void* stream);
+/* fami_adam_step for a CUDA-graph-captured training step: hyper_dev = device float[3] {lr, 1 - beta1^t, sqrt(1 - beta2^t)},
+ * refreshed by the host before every replay (MultiStepLR, scheduler.py:14-26, and the step count stay live).               */
+int fami_adam_step_graph(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                         const float* hyper_dev, float beta1, float beta2, float eps, void* stream);
 /* One Adam update over a flat fp32 parameter bucket (torch.optim.Adam as built by
  * posetimation/optimizer/optimizer.py:66-72: betas, eps, no weight decay / amsgrad); `step` counts from 1. */
 int fami_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,

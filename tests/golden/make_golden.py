@@ -174,9 +174,46 @@ def make_train():
     print("train_reference.npz", len(names), "trainable tensors")
 
 
+def make_train_unfrozen():
+    """The same training-step backward with the backbone UN-frozen (FREEZE_HRNET_WEIGHTS: false,
+    Alignment_V15.py:110-111 / hrnet.py:686-690): a digest of the gradient of every one of the model's parameters
+    (HRNet-W48 included: the 258.6 MB all-reduce case of SURVEY.md 8e).  B=1 (5 frames through train-mode BatchNorm),
+    float64 pin + the reference's own float32 run."""
+    ref = rh.load_reference()
+    cfg = rh.make_cfg(48, 17, freeze_hrnet=False)
+    out = {}
+    for dt, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        m = ref.Alignment_V15(cfg, 'train').train()
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict(fo.seeded_state_dict(shapes, SEED), strict=True)
+        m = m.to(dt)
+        kf, sup, tgt, tw = fo.synthetic_clip(1, seed=SEED + 3)
+        hm, kfhm, mi = m(kf.to(dt), sup.to(dt))
+        mse = ref.JointMSELoss()(hm, tgt.to(dt), tw.to(dt))
+        loss = mse * 1.0 + 0.5 * (-0.1 * mi[0] + 0.1 * mi[1] + mi[2] - mi[3] + mi[4] - mi[5])
+        loss.backward()
+        out.update({tag + "/loss": np.float64(loss.item()), tag + "/mse": np.float64(mse.item())})
+        if tag == "f64":
+            out["final_hm"] = hm.detach().float().numpy()
+        names = []
+        for name, p_ in m.named_parameters():
+            assert p_.requires_grad, name
+            if p_.grad is None:        # parameters the loss does not reach (e.g. unused heads)
+                continue
+            names.append(name)
+            out[tag + "/grad/" + name] = grad_digest(p_.grad)
+        out["names"] = np.array(names)
+        out["n_params_total"] = np.int64(sum(1 for _ in m.named_parameters()))
+        print(tag, "loss", out[tag + "/loss"], len(names), "tensors with gradients", flush=True)
+    np.savez_compressed(os.path.join(OUT, "train_unfrozen_reference.npz"), **out)
+    print("train_unfrozen_reference.npz", len(names), "tensors")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
-    if len(sys.argv) > 1 and sys.argv[1] == "train":
+    if len(sys.argv) > 1 and sys.argv[1] == "train_unfrozen":
+        make_train_unfrozen()
+    elif len(sys.argv) > 1 and sys.argv[1] == "train":
         make_train()
     elif len(sys.argv) > 1 and sys.argv[1] == "decode":
         make_decode()

@@ -170,6 +170,13 @@ import posetimation.backbones.hrnet as H
 A = importlib.import_module("posetimation.zoo.Alignment.Alignment_V15")   # the module, not the class
 assert H.BasicBlock is fp.BasicBlock and A.DeformConv2d is fp.DeformConv2d and A.HRNetPlus is fp.HRNetPlus
 assert "kornia.geometry.warp_affine" in names
+# the engine's plug-in registries resolve the reference's own names to the fami classes (engine/core/base.py:65)
+from engine.defaults.constant import CORE_FUNCTION_REGISTRY, MODEL_REGISTRY
+from fami_pose_b200.train import AlignmentMIFunction_Term6_V1
+assert CORE_FUNCTION_REGISTRY.get("AlignmentMIFunction_Term6_V1") is AlignmentMIFunction_Term6_V1
+assert MODEL_REGISTRY.get("Alignment_V15") is fp.Alignment_V15
+cf = CORE_FUNCTION_REGISTRY.get("AlignmentMIFunction_Term6_V1")(None, criterion=None, output_dir="/tmp", PE_Name="x")
+assert hasattr(cf, "train") and hasattr(cf, "predict")
 # the reference's own model class now builds on fami modules with unchanged state_dict keys
 m = A.Alignment_V15(rh.make_cfg(48, 17), "validate")
 assert isinstance(m.hrnet, fp.HRNetPlus) and isinstance(m.dcn_1, fp.DeformConv2d)

@@ -35,6 +35,26 @@ def _worker(rank, world, port, q):
     buckets.allreduce_mean()
     ok = bool(torch.allclose(lin.weight.grad, torch.full_like(lin.weight, 1.5)) and
               torch.allclose(lin.bias.grad, torch.full_like(lin.bias, 15.0)))
+    # overlapped form: each bucket's all-reduce is issued from an autograd hook as soon as its last gradient lands;
+    # buckets are laid out in reverse parameter order (= the order backward produces gradients)
+    torch.manual_seed(1)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 6), torch.nn.Tanh(), torch.nn.Linear(6, 2))
+    ob = parallel.GradBuckets(list(net.parameters()), bucket_bytes=64, overlap=True)
+    assert [len(b) for b in ob.buckets] == [2, 1, 1] and ob.buckets[0][0] is net[2].bias     # last layer first
+    ob.zero()
+    xin = torch.full((3, 4), float(rank + 1))
+    net(xin).sum().backward()
+    first_issued = list(ob.launch_order)
+    ob.finish()
+    ref = torch.nn.Sequential(torch.nn.Linear(4, 6), torch.nn.Tanh(), torch.nn.Linear(6, 2))
+    ref.load_state_dict(net.state_dict())
+    tot = [torch.zeros_like(p) for p in ref.parameters()]
+    for r in range(world):
+        ref.zero_grad()
+        ref(torch.full((3, 4), float(r + 1))).sum().backward()
+        tot = [t + p.grad / world for t, p in zip(tot, ref.parameters())]
+    ok = ok and all(torch.allclose(p.grad, t, atol=1e-6) for p, t in zip(net.parameters(), tot))
+    ok = ok and first_issued[0] == 0 and sorted(first_issued) == [0, 1, 2]                       # head bucket went out first
     mx = parallel.max_over_ranks(float(rank) * 2.0, torch.device("cpu"))
     q.put((rank, ok, mx, parallel.shard_range(65, rank, world), parallel.rank_seed(100, rank)))
     dist.barrier()
