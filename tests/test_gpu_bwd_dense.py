@@ -52,6 +52,35 @@ def test_conv_dgrad_wgrad_vs_autograd(case):
         assert _rel(gb.double().cpu(), b.grad) < 2e-5
 
 
+def _tf32_rna64(t):
+    f = t.float().contiguous()
+    i = f.view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32).double()
+
+
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[6] == 1 and c[2] % 4 == 0],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv_dgrad_tf32_vs_autograd(case):
+    """Stride-1 dgrad on the 'tf32' arm (the forward tensor-core kernels over the flipped / transposed filter, incl. the
+    324-channel offset|mask gradient whose last 8-channel K-step is half zero fill): grad_y and the weights pre-rounded to
+    TF32 so that only the accumulation order differs from float64 autograd."""
+    N, Cin, Cout, H, W, k, stride, pad, dil, bias = case
+    fp.set_precision("tf32")
+    try:
+        g = torch.Generator().manual_seed(200 + Cin + Cout)
+        x = torch.randn(N, Cin, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+        w = _tf32_rna64(torch.randn(Cout, Cin, k, k, generator=g, dtype=torch.float64) * 0.1)
+        y = F.conv2d(x, w, None, stride, pad, dil)
+        gy = _tf32_rna64(torch.randn(y.shape, generator=g, dtype=torch.float64))
+        y.backward(gy)
+        gyn = _nhwc(gy)
+        assert ops.conv_code(gyn, Cout) == fp._lib.TF32
+        gx = ops.conv_dgrad(gyn, w.float().cuda(), (N, Cin, H, W), stride, pad, dil)
+        assert _rel(ops.to_nchw(gx).double().cpu(), x.grad) < 2e-5
+    finally:
+        fp.set_precision("fp32")
+
+
 def test_conv_dgrad_into_channel_slice():
     """grad_x written into a channel slice of a wider buffer (the concat operands of Alignment_V15.py:143,160)."""
     fp.set_precision("fp32")
