@@ -510,7 +510,7 @@ def dcn_roofline(fp, ops, dev, stream, B, pk):
     import torch
     C, G, H, W = 48, 12, 96, 72
     dt = ops.act_dtype()
-    half = dt != torch.float32
+    half = ops.dcn_fused_supported(C, G, dt)      # 16-bit arms, and the tf32 arm (fp32 x cast to fp16 on the way in, fp32 out)
     g = torch.Generator(device="cpu").manual_seed(1)
     x = ops.to_nhwc(torch.randn(B, C, H, W, generator=g).to(dev), dt)
     off = (2 * torch.randn(B, 18 * G, H, W, generator=g)).to(dev)     # sigma = 2 px
@@ -538,16 +538,18 @@ def dcn_roofline(fp, ops, dev, stream, B, pk):
             if i >= 3:
                 times.append(e0.elapsed_time(e1))
     t = sorted(times)[len(times) // 2] / 1000.0
-    sx = 2 if half else 4
+    sx = dt.itemsize        # storage of x and out as the caller holds them (2: fp16 / bf16 arms; 4: fp32 and tf32 arms)
     alg = B * H * W * (sx * (C + C) + 4 * 27 * G) + sx * 9 * C * C + 4 * C
     ach = alg / t / 1e9
     traffic = None
     try:   # DRAM bytes of the same launch from the committed ncu --set full capture (16-bit arm, B=32)
         if half and B == 32:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["dcn_tc_kernel_fp16_B32"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["dcn_tc_kernel_fp16_B32"]
     except Exception:
         traffic = None
-    return {"kernel": "fami_dcn_fwd (modulated deformable conv, C=48 G=12 96x72 B=%d, x/out %s, offsets fp32)" % (B, str(dt).replace("torch.", "")),
+    return {"kernel": "fami_dcn_fwd (modulated deformable conv, C=48 G=12 96x72 B=%d, x/out %s, offsets fp32%s)"
+                      % (B, str(dt).replace("torch.", ""), "; fp32 x is cast to fp16 by one elementwise launch inside the timed call"
+                         if (half and sx == 4) else ""),
             "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
             "traffic": traffic, "algorithmic_bytes": alg, "us_per_launch": t * 1e6}
 

@@ -41,11 +41,13 @@ int dcn_simt_launch(const fami_dcn_desc* d, const void* x, const float* off, con
                     const float* w, const float* bias, void* out, cudaStream_t st);
 int conv_bf16_tc_supported(const fami_conv_desc* d);
 int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale,
-                        const float* shift, const void* res, void* y, double* stats, cudaStream_t st);
+                        const float* shift, const void* res, void* y, double* stats, cudaStream_t st,
+                        const float* res32 = nullptr, float* y32 = nullptr, int y32_pitch = 0);
 int64_t pack_w_bf16_elems(int Cout, int Cin, int kh, int kw, int dtype);
 int conv_halo_supported(const fami_conv_desc* d);
 int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
-                     const void* res, void* y, cudaStream_t st);
+                     const void* res, void* y, cudaStream_t st, const float* res32 = nullptr, float* y32 = nullptr,
+                     int y32_pitch = 0);
 int pack_w_bf16_launch(const float* w, void* out, int Cout, int Cin, int kh, int kw, int dtype, cudaStream_t st);
 int flip_transpose_launch(const float* w, float* wt, int Cout, int Cin, int kh, int kw, cudaStream_t st);
 int conv_dgrad_launch(const fami_conv_desc* d, const float* gy, const float* wt_packed, float* gx, cudaStream_t st);
@@ -209,6 +211,30 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
   }
   return conv_f32_launch(d, (const float*)x, (const float*)w_packed, scale, shift, residual, y, stats_out,
                          (cudaStream_t)stream);
+}
+
+int fami_conv2d_bn_act_fwd_stream(const fami_conv_desc* d, const void* x, const void* w_packed, const float* scale,
+                                  const float* shift, const float* residual_f32, void* y, float* y_f32, int y32_pitch,
+                                  void* stream) {
+  FAMI_CHECK_ARG(d && x && w_packed && y, "fami_conv2d_bn_act_fwd_stream: null pointer");
+  FAMI_CHECK_ARG(is_half_dtype(d->dtype) && d->out_dtype == d->dtype, "fami_conv2d_bn_act_fwd_stream: 16-bit arms only");
+  FAMI_CHECK_ARG(residual_f32 || y_f32, "fami_conv2d_bn_act_fwd_stream: neither a float residual nor a float output given");
+  FAMI_CHECK_ARG(d->om_groups == 0 && !d->stats, "fami_conv2d_bn_act_fwd_stream: no om_groups / stats in stream mode");
+  FAMI_CHECK_ARG(d->kh == d->kw && (d->kh == 1 || d->kh == 3) && d->stride >= 1 && d->dil >= 1 && d->pad >= 0,
+                 "fami_conv2d_bn_act_fwd_stream: bad kernel geometry");
+  int Ho = (d->H + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
+  int Wo = (d->W + 2 * d->pad - d->dil * (d->kw - 1) - 1) / d->stride + 1;
+  FAMI_CHECK_ARG(Ho == d->Ho && Wo == d->Wo, "fami_conv2d_bn_act_fwd_stream: Ho/Wo inconsistent");
+  FAMI_CHECK_ARG(d->up == 1 || d->up == 2 || d->up == 4 || d->up == 8, "fami_conv2d_bn_act_fwd_stream: up=%d", d->up);
+  FAMI_CHECK_ARG(d->in_pitch >= d->Cin && d->out_pitch >= d->Cout && (!residual_f32 || d->res_pitch >= d->Cout) &&
+                     (!y_f32 || y32_pitch >= d->Cout),
+                 "fami_conv2d_bn_act_fwd_stream: pitch < channels");
+  FAMI_CHECK_ARG(conv_bf16_tc_supported(d), "fami_conv2d_bn_act_fwd_stream: shape not supported by the tensor-core path");
+  static const bool halo_off = getenv("FAMI_DISABLE_HALO") != nullptr;
+  if (!halo_off && conv_halo_supported(d))
+    return conv_halo_launch(d, x, w_packed, scale, shift, nullptr, y, (cudaStream_t)stream, residual_f32, y_f32, y32_pitch);
+  return conv_bf16_tc_launch(d, x, w_packed, scale, shift, nullptr, y, nullptr, (cudaStream_t)stream, residual_f32, y_f32,
+                             y32_pitch);
 }
 
 static int check_conv_bwd(const fami_conv_desc* d, const char* who) {

@@ -61,6 +61,9 @@ struct HaloParams {
   const float* shift;
   const void* res;
   void* y;
+  const float* res32;   // fp32 residual stream mode (16-bit arms), may be null
+  float* y32;
+  int res32_pitch, y32_pitch;
 };
 
 // The nine taps of one resident-weights channel chunk, issued by one warp for its M-tiles m = issuer, issuer + n_iss, ...
@@ -311,6 +314,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ea.s_scale = smem_u32(s_scale); ea.s_shift = smem_u32(s_shift); ea.res = p.res; ea.y = p.y;
     ea.Cout = p.Cout; ea.BN = p.BN; ea.out_pitch = p.out_pitch; ea.res_pitch = p.res_pitch;
     ea.out_f32 = p.out_f32; ea.relu = p.relu; ea.vec_ok = p.vec_ok; ea.up = 1; ea.Wout = p.W;
+    ea.res32 = p.res32; ea.y32 = p.y32; ea.res32_pitch = p.res32_pitch; ea.y32_pitch = p.y32_pitch;
+    const bool stream_mode = p.res32 != nullptr || p.y32 != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = (p.acc_bufs == 2) ? (it & 1) : 0;
@@ -339,7 +344,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         bool valid;
         const int pix = row_pix(m, valid);
         const uint32_t t_addr = tmem_base + (uint32_t)(acc * acc_cols + m * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
-        if (p.om_groups > 0) {
+        if (stream_mode) {
+          epilogue_rows_stream<TH>(ea, t_addr, col_begin, col_end, valid, pix);
+        } else if (p.om_groups > 0) {
           const int q = m * 128 + row;
           const int yy = q / p.Wp, xx = q - yy * p.Wp;
           OmBlocked ob;
@@ -516,7 +523,7 @@ int conv_halo_supported(const fami_conv_desc* d) {
 }
 
 int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
-                     const void* res, void* y, cudaStream_t st) {
+                     const void* res, void* y, cudaStream_t st, const float* res32, float* y32, int y32_pitch) {
   FAMI_CHECK_ARG(load_driver_fns(), "cuTensorMapEncode* driver entry points unavailable");
   const bool tf32 = d->dtype == FAMI_TF32;
   const int kKC = tf32 ? 32 : 64;
@@ -572,6 +579,7 @@ int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, cons
   p.b_tile_bytes = (uint32_t)c.BN * 128u;
   p.a_box_bytes = (uint32_t)((c.BH + 2 * dl) * Wp) * 128u;
   p.scale = scale; p.shift = shift; p.res = res; p.y = y;
+  p.res32 = res32; p.y32 = y32; p.res32_pitch = d->res_pitch; p.y32_pitch = y32_pitch;
   p.om_groups = d->om_groups;
   p.om_tiles_x = (d->W + 7) / 8; p.om_tiles_y = (d->H + 15) / 16;
   p.om_tap_stride = (int64_t)d->N * p.om_tiles_x * p.om_tiles_y * 4 * (3 * (d->om_groups / 4)) * 128;

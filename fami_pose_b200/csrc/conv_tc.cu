@@ -38,6 +38,9 @@ struct TcParams {
   const float* shift;
   const void* res;   // TH
   void* y;
+  const float* res32;   // fp32 residual stream mode (16-bit arms): float residual / additional float output, may be null
+  float* y32;
+  int res32_pitch, y32_pitch;
 };
 
 template <typename TH>
@@ -177,6 +180,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ea.s_scale = smem_u32(s_scale); ea.s_shift = smem_u32(s_shift); ea.res = p.res; ea.y = p.y;
     ea.Cout = p.Cout; ea.BN = p.BN; ea.out_pitch = p.out_pitch; ea.res_pitch = p.res_pitch;
     ea.out_f32 = p.out_f32; ea.relu = p.relu; ea.vec_ok = p.vec_ok; ea.up = p.up; ea.Wout = Wout;
+    ea.res32 = p.res32; ea.y32 = p.y32; ea.res32_pitch = p.res32_pitch; ea.y32_pitch = p.y32_pitch;
+    const bool stream_mode = p.res32 != nullptr || p.y32 != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -198,7 +203,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)(quarter * 32) << 16);
-      if (p.om_groups > 0) {
+      if (stream_mode) {
+        epilogue_rows_stream<TH>(ea, t_addr, col_begin, col_end, valid, pix0);
+      } else if (p.om_groups > 0) {
         const int n = m / p.HoWo, r = m - n * p.HoWo;
         const int yo = r / p.Wo, xo = r - yo * p.Wo;
         OmBlocked ob;
@@ -310,7 +317,8 @@ int pack_w_bf16_launch(const float* w, void* out, int Cout, int Cin, int kh, int
 
 // x, residual: bf16 NHWC; y: bf16 or fp32 (d->out_dtype)
 int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
-                        const void* res, void* y, double* stats, cudaStream_t st) {
+                        const void* res, void* y, double* stats, cudaStream_t st, const float* res32, float* y32,
+                        int y32_pitch) {
   (void)stats;
   FAMI_CHECK_ARG(!d->stats, "bf16 tensor-core conv: fused BN statistics are not supported (use fami_bn_stats)");
   FAMI_CHECK_ARG(load_driver_fns(), "cuTensorMapEncode* driver entry points unavailable");
@@ -364,12 +372,13 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   p.vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((d->out_pitch * osz) % 16 == 0) &&
              (!res || (((reinterpret_cast<uintptr_t>(res) & 15) == 0) && ((d->res_pitch * es) % 16 == 0)));
   p.scale = scale; p.shift = shift; p.res = res; p.y = y;
+  p.res32 = res32; p.y32 = y32; p.res32_pitch = d->res_pitch; p.y32_pitch = y32_pitch;
   p.om_groups = d->om_groups;
   p.om_tiles_x = (d->Wo + 7) / 8; p.om_tiles_y = (d->Ho + 15) / 16;
   p.om_tap_stride = (int64_t)d->N * p.om_tiles_x * p.om_tiles_y * 4 * (3 * (d->om_groups / 4)) * 128;
 
   const int stage_bytes = kABytes + t.BN * 128;
-  p.pipe = (d->om_groups == 0 && epi_pipe_ok(t.BN, d->Cout, p.vec_ok, out_f32, d->up, res != nullptr, tf32) && d->Cout == t.BN * t.n_tiles &&
+  p.pipe = (!res32 && !y32 && d->om_groups == 0 && epi_pipe_ok(t.BN, d->Cout, p.vec_ok, out_f32, d->up, res != nullptr, tf32) && d->Cout == t.BN * t.n_tiles &&
             getenv("FAMI_NO_EPI_PIPE") == nullptr) ? 1 : 0;
   const size_t pipe_pitch = tf32 ? epi_pipe_pitch(kPipeColsF32 * 2) : epi_pipe_pitch();
   const size_t epi_bytes = p.pipe ? (size_t)kEpiWarps * 32 * (res ? 3 : 1) * pipe_pitch : (size_t)kEpiWarps * 32 * (128 + 16);

@@ -273,7 +273,98 @@ struct EpiArgs {
   int out_f32, relu, vec_ok;
   int up, Wout;           // nearest-upsample replication (1 = none); Wout = output row width in pixels
   int spitch;             // staging row pitch in bytes (epi_stage_pitch)
+  // fp32 residual stream of the 16-bit arms (fami_conv2d_bn_act_fwd_stream): the residual operand is read from a float
+  // tensor and the result is additionally written, before rounding, to a float tensor, so that the ~100 sequential
+  // residual additions of the HRNet trunk accumulate in fp32 while every MMA operand stays 16-bit
+  const float* res32;     // may be null
+  float* y32;             // may be null
+  int res32_pitch, y32_pitch;
 };
+
+// Direct (unstaged) epilogue of the fp32-residual-stream mode: each lane owns one accumulator row and moves 64-byte
+// runs itself.  Slower than the staged routines (32 cache lines per warp instruction) -- this is the parity mode of
+// the bf16 arm, not the throughput path.
+template <typename TH>
+__device__ __forceinline__ void epilogue_rows_stream(const EpiArgs& a, uint32_t t_addr, int col_begin, int col_end, bool valid,
+                                                     int pix0) {
+  if (col_begin >= col_end) return;   // warp-uniform
+  const bool rvec = a.res32 && (a.res32_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.res32) & 15) == 0);
+  const bool y32vec = a.y32 && (a.y32_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y32) & 15) == 0);
+  for (int c0 = col_begin; c0 < col_end; c0 += 16) {
+    const int ch0 = a.ch_base + c0;
+    if (ch0 >= a.Cout) break;   // warp-uniform
+    uint32_t v[16];
+    tmem_ld16(t_addr + (uint32_t)c0, v);
+    tmem_ld_wait();
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 sc = lds128f(a.s_scale + (uint32_t)(ch0 + 4 * j) * 4u);
+      const float4 sh = lds128f(a.s_shift + (uint32_t)(ch0 + 4 * j) * 4u);
+      o[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
+      o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
+      o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
+      o[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
+    }
+    if (!valid) continue;
+    const bool full = ch0 + 16 <= a.Cout;
+    for (int dy = 0; dy < a.up; ++dy)
+      for (int dx = 0; dx < a.up; ++dx) {
+        const int64_t pix = (int64_t)pix0 + dy * a.Wout + dx;
+        float t[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) t[j] = o[j];
+        if (a.res32) {
+          const float* r = a.res32 + pix * a.res32_pitch + ch0;
+          if (full && rvec) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(r) + j);
+              t[4 * j] += q.x; t[4 * j + 1] += q.y; t[4 * j + 2] += q.z; t[4 * j + 3] += q.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (ch0 + j < a.Cout) t[j] += __ldg(r + j);
+          }
+        } else if (a.res) {
+          const TH* r = reinterpret_cast<const TH*>(a.res) + pix * a.res_pitch + ch0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (ch0 + j < a.Cout) t[j] += to_f<TH>(r[j]);
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) t[j] = fmaxf(t[j], 0.f);
+        }
+        if (a.y32) {
+          float* d = a.y32 + pix * a.y32_pitch + ch0;
+          if (full && y32vec) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(d)[j] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (ch0 + j < a.Cout) d[j] = t[j];
+          }
+        }
+        if (a.out_f32) {
+          float* d = reinterpret_cast<float*>(a.y) + pix * a.out_pitch + ch0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (ch0 + j < a.Cout) d[j] = t[j];
+        } else if constexpr (sizeof(TH) == 2) {
+          TH* d = reinterpret_cast<TH*>(a.y) + pix * a.out_pitch + ch0;
+          if (full && a.vec_ok) {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = f2_to_h2<TH>(t[2 * j], t[2 * j + 1]);
+            reinterpret_cast<uint4*>(d)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            reinterpret_cast<uint4*>(d)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (ch0 + j < a.Cout) d[j] = from_f<TH>(t[j]);
+          }
+        }
+      }
+  }
+}
 
 // One warp drains columns [col_begin, col_end) of its 32 accumulator rows.  pix0 = pixel index of this
 // lane's row (first replica); valid = row maps to a real output pixel.

@@ -7,6 +7,7 @@ without copies.  torch is used for memory, streams and parameter bookkeeping onl
 activations is issued through the C ABI.
 """
 import ctypes
+import os
 
 import torch
 
@@ -19,7 +20,14 @@ _PRECISION = "fp32"
 _DTYPES = {"fp32": torch.float32, "tf32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
 
 
-def set_precision(p):
+_STREAM_F32 = False
+
+
+def stream_f32():
+    return _STREAM_F32
+
+
+def set_precision(p, stream_f32=None):
     """'fp32': exact-fp32 SIMT kernels (bit-for-bit fp32 FMA arithmetic).
     'tf32': fp32 STORAGE everywhere (activations, residual stream, offsets, heatmaps) with every convolution on
     tcgen05.mma.kind::tf32 -- multiplicands rounded to TF32 (10-bit mantissa; weights at pack time, activations by
@@ -27,10 +35,17 @@ def set_precision(p):
     GPU (torch.backends.cudnn.allow_tf32 = True by default); it meets the fp32 tier's 1e-3 tolerance.
     'fp16' / 'bf16': tcgen05 tensor-core arm with 16-bit activations (fp32 accumulation, fp32
     offsets/masks/heatmaps); fp16 carries 3 more mantissa bits than bf16 at the same tensor-core rate."""
-    global _PRECISION
+    global _PRECISION, _STREAM_F32
     if p not in _DTYPES:
         raise ValueError("precision must be one of %s" % sorted(_DTYPES))
     _PRECISION = p
+    # fp32 residual stream on the 16-bit arms: every conv output that can later serve as a residual is stored twice --
+    # rounded to 16 bit (the tensor-core operand) and unrounded in fp32 (the residual) -- so the trunk's ~100 sequential
+    # residual additions accumulate in fp32.  Default: on for bf16 (8-bit significand: 1.1e-2 / 2.1e-2 without it, inside
+    # north_star's 1e-2 with it), off for fp16 (meets 1e-2 either way; the extra fp32 traffic costs throughput).
+    env = os.environ.get("FAMI_STREAM_F32")
+    _STREAM_F32 = (p == "bf16") if stream_f32 is None and env is None else bool(int(env) if stream_f32 is None else stream_f32)
+    _STREAM_F32 = _STREAM_F32 and p in ("bf16", "fp16")
 
 
 def get_precision():
@@ -359,7 +374,32 @@ def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None, out
                   _ptr(out), op, _code(out.dtype), N, Ho, Wo, Cout, up, int(bool(relu)), _stream())
         return out
     scale, shift = folded_affine(conv.bias, bn)
+    if _STREAM_F32 and x.dtype in (torch.float16, torch.bfloat16) and out is None and out_dtype in (None, x.dtype):
+        return _conv_stream(x, w, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, code)
     return _conv_raw(x, w, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, out, None, out_dtype, code=code)
+
+
+def _conv_stream(x, w_packed, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, code):
+    """fp32-residual-stream form of the fused convolution (16-bit arms, fami_conv2d_bn_act_fwd_stream): the residual is
+    taken from the float twin of `residual` when it has one (`_fami_f32`, attached to every output of this function) and
+    the output gets a float twin of its own.  Slices / views drop the twin and fall back to the 16-bit values."""
+    N, Cin, H, W, ip = meta(x)
+    Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    out = empty_nhwc(N, Cout, Ho * up, Wo * up, x.dtype, x.device)
+    y32 = empty_nhwc(N, Cout, Ho * up, Wo * up, torch.float32, x.device)
+    res32 = getattr(residual, "_fami_f32", None) if residual is not None else None
+    if residual is not None and res32 is None:
+        res32 = cast_nhwc(residual, torch.float32)        # a residual without a twin (e.g. a slice): widen it
+    rp = meta(res32)[4] if res32 is not None else 0
+    if res32 is not None and tuple(res32.shape) != (N, Cout, Ho * up, Wo * up):
+        raise ValueError("residual shape %s does not match conv output %s" % (tuple(res32.shape), (N, Cout, Ho * up, Wo * up)))
+    d = ConvDesc(N, H, W, Cin, Cout, k, k, stride, pad, dil, Ho, Wo, up, int(bool(relu)), ip, meta(out)[4], rp,
+                 code, code, 0, 0)
+    _lib.call("fami_conv2d_bn_act_fwd_stream", ctypes.byref(d), _ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(res32),
+              _ptr(out), _ptr(y32), meta(y32)[4], _stream())
+    out._fami_f32 = y32
+    return out
 
 
 def upsample_nearest(x, factor):

@@ -108,6 +108,15 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
                            const float* scale, const float* shift, const void* residual, void* y,
                            double* stats_out, void* stream);
 
+/* fp32 residual stream for the 16-bit arms (dtype = out_dtype = FAMI_F16 / FAMI_BF16): the same fused convolution, but
+ * the residual operand is FLOAT (residual_f32, pitch d->res_pitch, may be NULL) and the result is additionally stored,
+ * before rounding, into the float tensor y_f32 (pitch y32_pitch, may be NULL).  With every block output kept this way the
+ * ~100 sequential residual additions of the HRNet trunk (basic_model.py:60,110; hrnet.py:151-172) accumulate in fp32 while
+ * all tensor-core operands stay 16-bit: bf16 then meets north_star's 1e-2 (fp16: 1e-3) -- see DESIGN.md section 3.      */
+int fami_conv2d_bn_act_fwd_stream(const fami_conv_desc* d, const void* x, const void* w_packed, const float* scale,
+                                  const float* shift, const float* residual_f32, void* y, float* y_f32, int y32_pitch,
+                                  void* stream);
+
 /* ---- backward of the dense pieces (fp32 storage; autograd of the modules above) --------------
  * nn.Conv2d backward as autograd derives it for basic_model.py:44-63 / basic_layer.py:55-73 /
  * Alignment_V15.py:79-106.  `d` is the FORWARD descriptor (up = 1, dtype = out_dtype = FAMI_F32).

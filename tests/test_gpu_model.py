@@ -168,11 +168,14 @@ def _plant_peaks(sd, all_agg, kf_feat, J=17):
     return out, sels[0], sels[1], mins
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("tf32", 1e-3), ("fp16", 1e-2)])
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("tf32", 1e-3), ("fp16+stream", 1e-2), ("bf16", 1e-2)])
 def test_planted_peak_argmax_is_bit_exact_for_every_joint(prec, tol):
     """UNCONDITIONAL argmax equality (no margin escape hatch): with the planted-peak recipe every one of the 2 x 17
-    heatmaps has a top-1 / top-2 margin of at least 4e-3 (final) / 2e-2 (key frame) in the oracle, several times the
-    arm's measured error, so the device argmax indices must equal the oracle's for ALL joints, on every arm."""
+    heatmaps has a top-1 / top-2 margin of at least 4e-3 (final) / 2e-2 (key frame) in the oracle, more than twice the
+    arm's error (asserted), so the device argmax indices must equal the oracle's for ALL joints.  The planted heatmaps
+    are raw feature channels (|max| up to 4.5), so the value tolerance is the arm's tolerance relative to max(1, |ref|).
+    The 16-bit arms run with the fp32 residual stream (bf16's default; fp16 by option): plain fp16 measures 2.9e-3 on the
+    final features here, a hair over half the smallest planted margin (5.7e-3), where equality is no longer guaranteed."""
     import fami_pose_b200 as fp
     m, sd = _build("validate")
     kf, sup, _, _ = fo.synthetic_clip(1, seed=105)
@@ -183,7 +186,10 @@ def test_planted_peak_argmax_is_bit_exact_for_every_joint(prec, tol):
     assert min_f >= 4e-3 and min_k >= 2e-2, (min_f, min_k)
     m.load_state_dict(sd2, strict=True)
     m.eval()
-    fp.set_precision(prec)
+    if prec == "fp16+stream":
+        fp.set_precision("fp16", stream_f32=True)
+    else:
+        fp.set_precision(prec)
     try:
         with torch.no_grad():
             hm, kfhm = m(kf.to(DEV), sup.to(DEV))
@@ -192,8 +198,9 @@ def test_planted_peak_argmax_is_bit_exact_for_every_joint(prec, tol):
     finally:
         fp.set_precision("fp32")
     e1, e2 = float((hm.cpu() - ref_final).abs().max()), float((kfhm.cpu() - ref_kf).abs().max())
-    print("planted peaks (%s): err final %.3e kf %.3e; min margins %.3e / %.3e" % (prec, e1, e2, min_f, min_k))
-    assert e1 <= tol and e2 <= tol
+    print("planted peaks (%s): err final %.3e kf %.3e (|ref| max %.2f / %.2f); min margins %.3e / %.3e"
+          % (prec, e1, e2, float(ref_final.abs().max()), float(ref_kf.abs().max()), min_f, min_k))
+    assert e1 <= tol * max(1.0, float(ref_final.abs().max())) and e2 <= tol * max(1.0, float(ref_kf.abs().max()))
     assert 2 * e1 < min_f and 2 * e2 < min_k          # the margins dominate the arm's error: equality is well posed
     assert np.array_equal(idx, ref_final.reshape(1, 17, -1).argmax(2).numpy().astype(np.int32))
     assert np.array_equal(idx_k, ref_kf.reshape(1, 17, -1).argmax(2).numpy().astype(np.int32))
@@ -241,14 +248,15 @@ def test_full_size_config2_vs_oracle_and_properties(prec, tol):
 
 
 # ---------------------------------------------------------------------------------------------
-# 16-bit tensor-core arm (tcgen05 convs, fp16/bf16 activations, fp32 accumulation and fp32
-# offsets/masks/heatmaps).  north_star tolerance for the reduced-precision arm: 1e-2 max-abs vs the
-# reference's fp32 forward.  fp16 (11-bit significand) meets it with margin and is the default
-# tensor arm.  bf16 (8-bit significand) does NOT on this randomly-initialised 300-layer network:
-# ~100 sequential roundings of the residual stream give ~1e-2 relative noise (measured 1.1e-2 /
-# 2.1e-2 max-abs), so bf16 is checked against a looser, documented 3e-2 band.
+# 16-bit tensor-core arms (tcgen05 convs, fp16/bf16 activations, fp32 accumulation and fp32
+# offsets/masks/heatmaps).  north_star tolerance for the reduced-precision arms: 1e-2 max-abs vs the
+# reference's fp32 forward, for BOTH.  fp16 (11-bit significand) meets it with 16-bit residual
+# sums.  bf16 (8-bit significand) does not that way (~100 sequential roundings of the residual stream:
+# 1.1e-2 / 2.1e-2 measured in round 1), so the bf16 arm keeps the residual stream in fp32
+# (fami_conv2d_bn_act_fwd_stream: bf16 tensor-core operands, float residual operand / float twin of
+# every block output) and is held to the same 1e-2.
 # ---------------------------------------------------------------------------------------------
-HALF_ARMS = [("fp16", 1e-2), ("bf16", 3e-2)]
+HALF_ARMS = [("fp16", 1e-2), ("bf16", 1e-2)]
 
 
 def test_alignment_v15_tf32_vs_reference_golden(golden_dir):
@@ -380,7 +388,10 @@ def _build_config4(phase="validate"):
     return m.to(DEV).eval(), sd
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("fp16", 1e-2), ("bf16", 3e-2)])
+# config 4 is BASELINE's bf16-named configuration: bf16 and fp16 at north_star's 1e-2, fp32 at 1e-3.  The tf32 row is
+# informational for this W32 variant: its final heatmaps measure 7.1e-4, the backbone's rough key-frame heatmaps 1.13e-3
+# (1.5e-3 band); on the headline configuration (config 2) both are inside 1e-3 (test_alignment_v15_tf32_vs_reference_golden).
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("tf32", 1.5e-3), ("fp16", 1e-2), ("bf16", 1e-2)])
 def test_config4_w32_3frames_15joints_vs_oracle(prec, tol):
     import fami_pose_b200 as fp
     fp.set_precision("fp32")
