@@ -84,6 +84,8 @@ SIGNATURES = {
                                   c_void_p]),
     "fami_gaussian_targets": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_void_p]),
+    "fami_crop_affine_u8": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p]),
     "fami_frames_u8_normalize": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "fami_argmax_hw": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
 }

@@ -73,6 +73,8 @@ int gaussian_targets_launch(const float* joints, const float* vis, float* target
                             int img_w, int img_h, int hm_w, int hm_h, cudaStream_t st);
 int frames_u8_normalize_launch(const uint8_t* src, int64_t src_frame_stride, float* dst, int nframes, int64_t px_per_frame,
                                const float* mean, const float* std, cudaStream_t st);
+int crop_affine_u8_launch(const uint8_t* src, int64_t src_frame_stride, int Hs, int Ws, const double* minv, void* dst,
+                          int nframes, int Hd, int Wd, const float* mean, const float* std, cudaStream_t st);
 int dcn_tc_supported(const fami_dcn_desc* d);
 int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const void* w, const float* bias, void* out,
                   cudaStream_t st);
@@ -331,6 +333,15 @@ int fami_frames_u8_normalize(const uint8_t* frames, int64_t src_frame_stride, fl
   FAMI_CHECK_ARG(frames && out && mean3 && std3 && nframes > 0 && H > 0 && W > 0, "fami_frames_u8_normalize: bad arguments");
   FAMI_CHECK_ARG(src_frame_stride >= (int64_t)H * W * 3, "fami_frames_u8_normalize: frame stride smaller than a frame");
   return frames_u8_normalize_launch(frames, src_frame_stride, out, nframes, (int64_t)H * W, mean3, std3, (cudaStream_t)stream);
+}
+
+int fami_crop_affine_u8(const uint8_t* frames, int64_t src_frame_stride, int Hs, int Ws, const double* inv_trans, void* out,
+                        int nframes, int Hd, int Wd, const float* mean3, const float* std3, void* stream) {
+  FAMI_CHECK_ARG(frames && inv_trans && out && nframes > 0 && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0, "fami_crop_affine_u8: bad arguments");
+  FAMI_CHECK_ARG(src_frame_stride >= (int64_t)Hs * Ws * 3, "fami_crop_affine_u8: frame stride smaller than a frame");
+  FAMI_CHECK_ARG((mean3 == nullptr) == (std3 == nullptr), "fami_crop_affine_u8: pass both mean3 and std3, or neither");
+  FAMI_CHECK_ARG(Hs < 32768 && Ws < 32768, "fami_crop_affine_u8: source larger than OpenCV's 16-bit coordinate range");
+  return crop_affine_u8_launch(frames, src_frame_stride, Hs, Ws, inv_trans, out, nframes, Hd, Wd, mean3, std3, (cudaStream_t)stream);
 }
 
 int fami_final_preds(const void* hm, int dtype, int pitch, const int32_t* idx, const float* maxvals, const float* center,

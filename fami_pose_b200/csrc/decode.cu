@@ -139,7 +139,71 @@ __global__ void frames_u8_normalize_kernel(const uint8_t* __restrict__ src, int6
   d[2] = ((float)s[2] / 255.f - m2) / s2;
 }
 
+// cv2.warpAffine(frame_u8, trans, (Wd, Hd), flags=INTER_LINEAR), constant-0 border, bit for bit (OpenCV's fixed-point path;
+// datasets/zoo/posetrack/PoseTrack_Alignment.py:235-241, affine_transform.py:76-82).  minv[f][6]: the INVERSE affine map of
+// frame f in double, as cv::invertAffineTransform computes it (done by the caller in float64).  Source coordinates:
+// X = (rint((m1*y + m2)*1024) + 16 + rint(m0*x*1024)) >> 5 (5 fractional bits), likewise Y; weights (32-fy|fy)*(32-fx|fx)*32
+// sum to 2^15; out = (sum w*p + 2^14) >> 15.  The double products are formed with explicit round-to-nearest multiplies and
+// adds (no fused contraction), as the scalar C++ does.  One thread per destination pixel (3 channels).
+// kNorm: write ToTensor + Normalize(mean, std) of that 8-bit value as float (datasets/transforms/build.py:13-22) instead.
+template <bool kNorm>
+__global__ void crop_affine_u8_kernel(const uint8_t* __restrict__ src, int64_t src_frame_stride, int Hs, int Ws,
+                                      const double* __restrict__ minv, void* __restrict__ dst, int nframes, int Hd, int Wd,
+                                      float m0, float m1, float m2, float s0, float s1, float s2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)nframes * Hd * Wd) return;
+  const int x = (int)(i % Wd);
+  const int y = (int)((i / Wd) % Hd);
+  const int f = (int)(i / ((int64_t)Wd * Hd));
+  const double* m = minv + f * 6;
+  const long long ad = __double2ll_rn(__dmul_rn(__dmul_rn(m[0], (double)x), 1024.0));
+  const long long bd = __double2ll_rn(__dmul_rn(__dmul_rn(m[3], (double)x), 1024.0));
+  const long long X0 = __double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[1], (double)y), m[2]), 1024.0)) + 16;
+  const long long Y0 = __double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[4], (double)y), m[5]), 1024.0)) + 16;
+  // cv::saturate_cast<int> of the rounded products, then int arithmetic
+  auto sat = [](long long v) { return (int)(v > 2147483647ll ? 2147483647ll : (v < -2147483648ll ? -2147483648ll : v)); };
+  const int X = (sat(X0 - 16) + 16 + sat(ad)) >> 5, Y = (sat(Y0 - 16) + 16 + sat(bd)) >> 5;
+  int ix = X >> 5, iy = Y >> 5;
+  // cv::saturate_cast<short> of the integer coordinates (remap stores them as 16-bit)
+  ix = ix > 32767 ? 32767 : (ix < -32768 ? -32768 : ix);
+  iy = iy > 32767 ? 32767 : (iy < -32768 ? -32768 : iy);
+  const int fx = X & 31, fy = Y & 31;
+  const int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+  const uint8_t* s = src + (int64_t)f * src_frame_stride;
+  int acc[3] = {16384, 16384, 16384};
+  auto tap = [&](int yy, int xx, int w) {
+    if (w != 0 && yy >= 0 && yy < Hs && xx >= 0 && xx < Ws) {
+      const uint8_t* p = s + ((int64_t)yy * Ws + xx) * 3;
+      acc[0] += w * p[0]; acc[1] += w * p[1]; acc[2] += w * p[2];
+    }
+  };
+  tap(iy, ix, w00); tap(iy, ix + 1, w01); tap(iy + 1, ix, w10); tap(iy + 1, ix + 1, w11);
+  const int v0 = acc[0] >> 15, v1 = acc[1] >> 15, v2 = acc[2] >> 15;
+  if (kNorm) {
+    float* d = reinterpret_cast<float*>(dst) + i * 3;
+    d[0] = ((float)v0 / 255.f - m0) / s0;
+    d[1] = ((float)v1 / 255.f - m1) / s1;
+    d[2] = ((float)v2 / 255.f - m2) / s2;
+  } else {
+    uint8_t* d = reinterpret_cast<uint8_t*>(dst) + i * 3;
+    d[0] = (uint8_t)v0; d[1] = (uint8_t)v1; d[2] = (uint8_t)v2;
+  }
+}
+
 }  // namespace
+
+int crop_affine_u8_launch(const uint8_t* src, int64_t src_frame_stride, int Hs, int Ws, const double* minv, void* dst,
+                          int nframes, int Hd, int Wd, const float* mean, const float* std, cudaStream_t st) {
+  const int64_t tot = (int64_t)nframes * Hd * Wd;
+  if (mean && std)
+    crop_affine_u8_kernel<true><<<cdiv(tot, 256), 256, 0, st>>>(src, src_frame_stride, Hs, Ws, minv, dst, nframes, Hd, Wd, mean[0],
+                                                                mean[1], mean[2], std[0], std[1], std[2]);
+  else
+    crop_affine_u8_kernel<false><<<cdiv(tot, 256), 256, 0, st>>>(src, src_frame_stride, Hs, Ws, minv, dst, nframes, Hd, Wd, 0.f, 0.f,
+                                                                 0.f, 1.f, 1.f, 1.f);
+  FAMI_CHECK_LAUNCH("crop_affine_u8_kernel");
+  return 0;
+}
 
 int frames_u8_normalize_launch(const uint8_t* src, int64_t src_frame_stride, float* dst, int nframes, int64_t px_per_frame,
                                const float* mean, const float* std, cudaStream_t st) {

@@ -289,6 +289,15 @@ int fami_pck_accuracy(const int32_t* pred_idx, const float* pred_max, const int3
  * and target_weight [B,J].                                                                           */
 int fami_gaussian_targets(const float* joints, const float* joints_vis, float* target, float* target_weight,
                           int B, int J, int sigma, int img_w, int img_h, int hm_w, int hm_h, void* stream);
+/* The affine crop of the input pipeline on the device: cv2.warpAffine(frame, trans, (Wd, Hd), flags=cv2.INTER_LINEAR) with the
+ * default constant-0 border, bit for bit (datasets/zoo/posetrack/PoseTrack_Alignment.py:233-241,415-423; crop(),
+ * datasets/process/affine_transform.py:76-82).  `nframes` uint8 HWC frames of Hs x Ws, `src_frame_stride` BYTES apart;
+ * inv_trans: DEVICE double[nframes][6], the inverse of each frame's 2x3 `trans` exactly as cv::invertAffineTransform forms it
+ * (the caller inverts in float64: fami_pose_b200.pipeline.invert_affine).  out: uint8 [nframes][Hd][Wd][3] when mean3 / std3
+ * (HOST pointers) are NULL, else float [nframes][Hd][Wd][3] = ((u8 / 255) - mean) / std -- ToTensor + Normalize of
+ * datasets/transforms/build.py:13-22 applied to that 8-bit value, i.e. the frame the backbone consumes.                      */
+int fami_crop_affine_u8(const uint8_t* frames, int64_t src_frame_stride, int Hs, int Ws, const double* inv_trans, void* out,
+                        int nframes, int Hd, int Wd, const float* mean3, const float* std3, void* stream);
 /* torchvision ToTensor + Normalize(mean, std) of datasets/transforms/build.py:13-22 on the device, fused with the
  * frame re-batching of Alignment_V15.py:115-119: `nframes` uint8 HWC (RGB) frames, `src_frame_stride` BYTES apart,
  * -> dense fp32 NHWC frames out[f][y][x][c] = ((u8/255) - mean[c]) / std[c].  mean3 / std3 are HOST pointers.   */

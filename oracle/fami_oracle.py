@@ -331,6 +331,70 @@ def get_affine_transform(center, scale, output_size, inv=0):
     return affine_from_points(dst, src) if inv else affine_from_points(src, dst)
 
 
+def get_affine_transform_rot(center, scale, rot, output_size, shift=(0.0, 0.0), inv=0):
+    """datasets/process/affine_transform.py:13-45 with rotation and shift (the training-time augmentation of
+    datasets/zoo/posetrack/PoseTrack_Alignment.py:213-233): three float32 point pairs, then cv2.getAffineTransform."""
+    scale_tmp = np.asarray(scale) * 200.0          # dtype of the caller's scale (float32 in the dataset) is kept
+    src_w = scale_tmp[0]
+    dst_w, dst_h = output_size[0], output_size[1]
+    rot_rad = np.pi * rot / 180
+    sn, cs = np.sin(rot_rad), np.cos(rot_rad)
+    p = [0.0, src_w * -0.5]
+    src_dir = [p[0] * cs - p[1] * sn, p[0] * sn + p[1] * cs]
+    dst_dir = np.array([0, dst_w * -0.5], np.float32)
+    src = np.zeros((3, 2), np.float32)
+    dst = np.zeros((3, 2), np.float32)
+    sh = scale_tmp * np.array(shift, dtype=np.float32)
+    src[0, :] = np.asarray(center) + sh
+    src[1, :] = np.asarray(center) + src_dir + sh
+    dst[0, :] = [dst_w * 0.5, dst_h * 0.5]
+    dst[1, :] = np.array([dst_w * 0.5, dst_h * 0.5]) + dst_dir
+
+    def third(a, b):
+        d = a - b
+        return b + np.array([-d[1], d[0]], np.float32)
+    src[2, :] = third(src[0], src[1])
+    dst[2, :] = third(dst[0], dst[1])
+    return affine_from_points(dst, src) if inv else affine_from_points(src, dst)
+
+
+def warp_affine_u8(img, M, dsize):
+    """cv2.warpAffine(img_u8[H,W,C], M[2,3], (w, h), flags=cv2.INTER_LINEAR) with the default constant-0 border, as called
+    at datasets/zoo/posetrack/PoseTrack_Alignment.py:235-241,417-423 and affine_transform.py:76-82 -- a bit-exact restatement
+    of OpenCV's fixed-point path (pinned against cv2 4.13 in tests/golden/crop_reference.npz): the forward matrix is inverted
+    in double; source coordinates are 10-bit fixed point (rounded products per column / row, + 16, >> 5 -> 5 fractional
+    bits); the four bilinear weights are (32-fy|fy)*(32-fx|fx)*32 (sum 2^15, exact); result = (sum w*p + 2^14) >> 15."""
+    Wd, Hd = int(dsize[0]), int(dsize[1])
+    m = np.array(M, dtype=np.float64).reshape(6).copy()
+    D = m[0] * m[4] - m[1] * m[3]
+    D = 1.0 / D if D != 0 else 0.0
+    A11, A22 = m[4] * D, m[0] * D
+    m[0] = A11; m[1] *= -D; m[3] *= -D; m[4] = A22
+    b1 = -m[0] * m[2] - m[1] * m[5]
+    b2 = -m[3] * m[2] - m[4] * m[5]
+    m[2], m[5] = b1, b2
+    xs = np.arange(Wd, dtype=np.float64)
+    adelta = np.rint(m[0] * xs * 1024).astype(np.int64)
+    bdelta = np.rint(m[3] * xs * 1024).astype(np.int64)
+    img = np.asarray(img)
+    Hs, Ws, C = img.shape
+    out = np.zeros((Hd, Wd, C), np.uint8)
+    for y in range(Hd):
+        X0 = int(np.rint((m[1] * y + m[2]) * 1024)) + 16
+        Y0 = int(np.rint((m[4] * y + m[5]) * 1024)) + 16
+        X, Y = (X0 + adelta) >> 5, (Y0 + bdelta) >> 5
+        ix, iy, fx, fy = X >> 5, Y >> 5, X & 31, Y & 31
+        acc = np.zeros((Wd, C), np.int64)
+        for dy, dx, w in ((0, 0, (32 - fy) * (32 - fx)), (0, 1, (32 - fy) * fx), (1, 0, fy * (32 - fx)), (1, 1, fy * fx)):
+            yy, xx = iy + dy, ix + dx
+            ok = (yy >= 0) & (yy < Hs) & (xx >= 0) & (xx < Ws)
+            p = np.zeros((Wd, C), np.int64)
+            p[ok] = img[yy[ok], xx[ok]]
+            acc += (w * 32)[:, None] * p
+        out[y] = ((acc + 16384) >> 15).astype(np.uint8)
+    return out
+
+
 def get_final_preds(batch_heatmaps, center, scale):
     """datasets/process/heatmaps_process.py:47-73: argmax, +-0.25 px refinement, inverse affine back to image
     coordinates (transform_preds :76-81).  Returns (preds [B,J,2] float32, maxvals [B,J,1])."""

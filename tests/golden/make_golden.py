@@ -132,6 +132,46 @@ def make_decode():
     print("decode_reference.npz", {k: np.shape(v) for k, v in out.items()})
 
 
+def synthetic_frames(seed, F=3, H=200, W=260):
+    """Smooth, textured uint8 RGB frames (compress well, exercise every interpolation weight)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    out = np.zeros((F, H, W, 3), np.uint8)
+    for f in range(F):
+        for c in range(3):
+            a, b, ph = rng.uniform(0.02, 0.2, 3)
+            v = 127 + 60 * np.sin(a * xx + ph * 10 + f) + 50 * np.cos(b * yy - ph * 7) + 15 * np.sin(0.9 * xx + 1.3 * yy)
+            out[f, :, :, c] = np.clip(v, 0, 255).astype(np.uint8)
+        out[f, 40:60, 50:90] = rng.integers(0, 256, (20, 40, 3))          # a noisy patch
+    return out
+
+
+def make_crop():
+    """The dataset's affine crop (datasets/zoo/posetrack/PoseTrack_Alignment.py:233-241): the UNMODIFIED reference's
+    get_affine_transform (datasets/process/affine_transform.py:13-45) + cv2.warpAffine(INTER_LINEAR) on synthetic frames:
+    rotation / scale augmentation, a crop reaching far outside the image (constant-0 border), an up-scaling crop."""
+    import cv2
+    import importlib
+    rh.load_reference_decode()          # installs the bare `datasets.process` package stub
+    at = importlib.import_module("datasets.process.affine_transform")
+    cases = [  # center (x, y), scale (w, h)/200, rot, output (w, h)
+        ((130.0, 100.0), (0.9, 1.2), 0.0, (288, 384)),
+        ((110.5, 92.25), (0.75, 1.0), 33.7, (144, 192)),
+        ((20.0, 180.0), (1.3, 1.7333), -51.2, (144, 192)),
+        ((128.0, 96.0), (0.3, 0.4), 7.0, (96, 128)),
+    ]
+    out = {"frames": synthetic_frames(SEED, F=2)}
+    for i, (c, sc, r, osz) in enumerate(cases):
+        trans = at.get_affine_transform(np.array(c, np.float32), np.array(sc, np.float32), r, osz)
+        out["case%d/params" % i] = np.array([c[0], c[1], sc[0], sc[1], r, osz[0], osz[1]], np.float64)
+        out["case%d/trans" % i] = np.asarray(trans, np.float64)
+        out["case%d/out" % i] = np.stack([cv2.warpAffine(fr, trans, (int(osz[0]), int(osz[1])), flags=cv2.INTER_LINEAR)
+                                          for fr in out["frames"]])
+    out["cv2_version"] = np.array(cv2.__version__)
+    np.savez_compressed(os.path.join(OUT, "crop_reference.npz"), **out)
+    print("crop_reference.npz", {k: np.shape(v) for k, v in out.items()})
+
+
 def grad_digest(g):
     """Compact pin of one gradient tensor: L2 norm, sum, and 48 evenly strided samples."""
     f = g.detach().double().flatten()
@@ -211,7 +251,9 @@ def make_train_unfrozen():
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
-    if len(sys.argv) > 1 and sys.argv[1] == "train_unfrozen":
+    if len(sys.argv) > 1 and sys.argv[1] == "crop":
+        make_crop()
+    elif len(sys.argv) > 1 and sys.argv[1] == "train_unfrozen":
         make_train_unfrozen()
     elif len(sys.argv) > 1 and sys.argv[1] == "train":
         make_train()
@@ -219,6 +261,7 @@ if __name__ == "__main__":
         make_decode()
     else:
         make_decode()
+        make_crop()
         make_dcn()
         make_model()
         make_train()
