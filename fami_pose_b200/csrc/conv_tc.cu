@@ -43,7 +43,13 @@ struct TcParams {
   int res32_pitch, y32_pitch;
 };
 
-template <typename TH>
+// kPair: CTA pairs (cluster of 2, tcgen05 cta_group::2).  A pair processes two adjacent 128-pixel M-tiles as ONE
+// M = 256 MMA per K-step: each CTA loads its own A tile and HALF of the B (weight) tile -- half the weight traffic from
+// L2 and half the shared memory per stage, so deeper rings -- and every stage hand-over (the 1.4 us barrier round trip that
+// bounds the single-CTA form) now covers twice the tensor work.  Only the leader CTA issues MMAs; the
+// peer's TMA loads complete on the leader's full barrier; tcgen05.commit multicasts `empty` / `tfull` to both CTAs; the
+// peer's epilogue warps release the accumulator on the leader's `tempty`.
+template <typename TH, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -51,7 +57,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr bool kTf32 = TcTraits<TH>::kTf32;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int stages = p.stages;
-  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const bool is_leader_cta = cta_rank == 0u;
+  const int bn_cta = kPair ? (p.BN >> 1) : p.BN;              // rows of the B tile held by this CTA
+  const uint32_t b_bytes = (uint32_t)bn_cta * 128u;
   const uint32_t stage_bytes = kABytes + b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
   const uint32_t bar0 = smem_u32(bars);
@@ -69,23 +78,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kPair ? 2 * kEpiWarps : kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();    // barrier inits and TMEM allocation of BOTH CTAs visible before any cross-CTA signal
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
-  const int ksteps = p.taps * p.cchunks;
+  // work units: (M-tile, N-tile); a CTA pair takes two adjacent M-tiles of one N-tile, the CTA of rank r the M-tile 2*u + r
+  // (clamped to the last M-tile when the count is odd: computed twice, stored once)
+  const int m_units = kPair ? (p.m_tiles + 1) >> 1 : p.m_tiles;
+  const int total_tiles = m_units * p.n_tiles;
+  const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto unit_mt = [&](int unit, bool& dup) -> int {
+    if (!kPair) { dup = false; return unit; }
+    const int mt = 2 * unit + (int)cta_rank;
+    dup = mt >= p.m_tiles;
+    return dup ? p.m_tiles - 1 : mt;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====
@@ -97,8 +122,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int unit = tile / p.n_tiles, nt = tile - unit * p.n_tiles;
+        bool dup;
+        const int mt = unit_mt(unit, dup);
         const int m0 = mt * kBM;
         const int n = m0 / p.HoWo, r = m0 - n * p.HoWo;
         const int yo = r / p.Wo, xo = r - yo * p.Wo;
@@ -108,11 +135,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int cc = 0; cc < p.cchunks; ++cc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (leader) {
-              mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
               const uint32_t a_dst = smem_u32(smem + (size_t)stage * stage_bytes);
-              tma_im2col_4d(a_dst, &tmA, full_bar(stage), cc * kKC, cw, ch, n, (uint16_t)(fs * p.dil),
-                            (uint16_t)(fr * p.dil));
-              tma_tiled_2d(a_dst + kABytes, &tmB, full_bar(stage), (tap * p.cchunks + cc) * kKC, nt * p.BN);
+              if constexpr (kPair) {
+                // the leader arms its full barrier for the bytes of BOTH CTAs; the peer's loads complete on it too
+                if (is_leader_cta) mbar_arrive_expect_tx(full_bar(stage), 2u * stage_bytes);
+                tma_im2col_4d_2sm(a_dst, &tmA, full_bar(stage), cc * kKC, cw, ch, n, (uint16_t)(fs * p.dil),
+                                  (uint16_t)(fr * p.dil));
+                tma_tiled_2d_2sm(a_dst + kABytes, &tmB, full_bar(stage), (tap * p.cchunks + cc) * kKC,
+                                 nt * p.BN + (int)cta_rank * bn_cta);
+              } else {
+                mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+                tma_im2col_4d(a_dst, &tmA, full_bar(stage), cc * kKC, cw, ch, n, (uint16_t)(fs * p.dil),
+                              (uint16_t)(fr * p.dil));
+                tma_tiled_2d(a_dst + kABytes, &tmB, full_bar(stage), (tap * p.cchunks + cc) * kKC, nt * p.BN);
+              }
             }
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
@@ -121,11 +157,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =======
-    {
+    if (is_leader_cta) {
       const bool leader = elect_one();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      // instruction descriptor: D=f32, A=B=f16|bf16, both K-major, M=128, N=BN
-      const uint32_t idesc = umma_idesc<TH>(p.BN);
+      // instruction descriptor: D=f32, A=B=f16|bf16|tf32, both K-major, M=128 (256 for a CTA pair), N=BN
+      const uint32_t idesc = kPair ? umma_idesc_pair<TH>(p.BN) : umma_idesc<TH>(p.BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -133,7 +169,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t stage_step = stage_bytes >> 4, b_off = (uint32_t)kABytes >> 4;
       const uint32_t empty_off = 8u * (uint32_t)stages;               // empty_bar(s) = full_bar(s) + empty_off
       uint32_t a_lo = a_lo0, full_cur = bar0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -148,15 +184,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(full_cur, phase);
             tc_fence_after();
             const int nk = (cc == p.cchunks - 1) ? p.last_kk : 4;
-            umma_ksteps_n<kTf32>(nk, leader, d_tmem, a_lo, a_lo + b_off, idesc, accum);
+            if constexpr (kPair) {
+              umma_pair_ksteps_n<kTf32>(nk, leader, d_tmem, a_lo, a_lo + b_off, idesc, accum);
+              if (leader) umma_commit_pair(full_cur + empty_off);   // frees the slot in BOTH CTAs
+            } else {
+              umma_ksteps_n<kTf32>(nk, leader, d_tmem, a_lo, a_lo + b_off, idesc, accum);
+              if (leader) umma_commit(full_cur + empty_off);   // frees the smem slot once the MMAs above have read it
+            }
             accum = true;
-            if (leader) umma_commit(full_cur + empty_off);   // frees the smem slot once the MMAs above have read it
             a_lo += stage_step;
             full_cur += 8u;
             if (++stage == stages) { stage = 0; phase ^= 1u; a_lo = a_lo0; full_cur = bar0; }
           }
         }
-        if (leader) umma_commit(tfull_bar(acc));       // accumulator complete -> epilogue
+        if (leader) {                                  // accumulator complete -> epilogue (of both CTAs)
+          if constexpr (kPair) umma_commit_pair(tfull_bar(acc));
+          else umma_commit(tfull_bar(acc));
+        }
       }
     }
   } else {
@@ -183,12 +227,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ea.res32 = p.res32; ea.y32 = p.y32; ea.res32_pitch = p.res32_pitch; ea.y32_pitch = p.y32_pitch;
     const bool stream_mode = p.res32 != nullptr || p.y32 != nullptr;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int unit = tile / p.n_tiles, nt = tile - unit * p.n_tiles;
+      bool dup;
+      const int mt = unit_mt(unit, dup);
       const int m = mt * kBM + row;
-      const bool valid = m < p.M;
+      const bool valid = m < p.M && !dup;
       int pix0 = 0;
       if (valid) {
         if (p.up == 1) {
@@ -213,11 +259,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ob.G3 = 3 * p.om_groups; ob.tap_stride = p.om_tap_stride;
         epilogue_rows_om_blocked(ea, t_addr, col_begin, col_end, valid, n, yo, xo, ob);
       } else if (p.pipe) {
-        const int ntile = tile + gridDim.x;
+        const int ntile = tile + tile_step;
         const bool have_next = ntile < total_tiles;
-        const int nmt = ntile / p.n_tiles, nnt = ntile - nmt * p.n_tiles;
+        const int nunit = ntile / p.n_tiles, nnt = ntile - nunit * p.n_tiles;
+        bool ndup;
+        const int nmt = unit_mt(nunit, ndup);
         const int nm = nmt * kBM + row;
-        const bool nvalid = have_next && nm < p.M;
+        const bool nvalid = have_next && nm < p.M && !ndup;
        if constexpr (sizeof(TH) == 4) {
         if (p.res)
           epilogue_rows_pipelined_f32<true>(ea, t_addr, col_begin, col_end, valid, pix0, pstage, pstage + 32u * pp, pstage + 64u * pp,
@@ -238,15 +286,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));   // one arrival per warp
+      if (lane == 0) {                               // one arrival per warp, on the issuing (leader) CTA's barrier
+        if constexpr (kPair) mbar_arrive_leader(tempty_bar(acc));
+        else mbar_arrive(tempty_bar(acc));
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();    // no CTA frees its TMEM / exits while the peer's MMAs or signals may still touch it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if constexpr (kPair)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -330,6 +385,14 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   const int kKC = kc_of(d->dtype);
   const cuuint64_t es = tf32 ? 4 : 2;     // element size
   TileCfg t = tile_cfg(d->Cout, d->Cin, d->kh, d->kw, kKC);
+  // CTA pairs (cta_group::2).  Measured on B200 (tools/time_convs.py, N=160, fp16 / tf32): the wide 3x3 stride-1 classes gain
+  // (192->192 +res 60.2 -> 56.2 us / 97.1 -> 90.9 us, 384->384 +res 56.2 -> 52.1 / 88.9 -> 84.8); 1x1, stride-2 and upsampling
+  // convs, whose time is epilogue / HBM bound, LOSE to the extra cross-CTA hand-over (256->64 1x1: 123 -> 172 us), so the pair
+  // form is selected for 3x3 stride-1 convs with Cin >= 128 only.  FAMI_TC_PAIR=0 disables it, =1 takes it wherever legal.
+  static const int pair_env = getenv("FAMI_TC_PAIR") ? atoi(getenv("FAMI_TC_PAIR")) : -1;
+  const int m_tiles_all = (d->N * d->Ho * d->Wo + kBM - 1) / kBM;
+  const bool pair_legal = m_tiles_all >= 2 && d->om_groups == 0;
+  const bool pair = pair_legal && (pair_env == 1 || (pair_env != 0 && d->kh == 3 && d->stride == 1 && d->up == 1 && d->Cin >= 128));
 
   CUtensorMap tmA, tmB;
   const CUtensorMapDataType tm_dtype = tm_dtype_of(d->dtype);
@@ -349,7 +412,7 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   {
     cuuint64_t dims[2] = {(cuuint64_t)t.Kp, (cuuint64_t)t.CoutPad};
     cuuint64_t strides[1] = {(cuuint64_t)t.Kp * es};
-    cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)t.BN};
+    cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)(pair ? t.BN / 2 : t.BN)};   // a CTA of a pair holds half of the N rows
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode_tiled(&tmB, tm_wdtype, 2, const_cast<void*>(w), dims, strides, box,
                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -377,7 +440,7 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   p.om_tiles_x = (d->Wo + 7) / 8; p.om_tiles_y = (d->Ho + 15) / 16;
   p.om_tap_stride = (int64_t)d->N * p.om_tiles_x * p.om_tiles_y * 4 * (3 * (d->om_groups / 4)) * 128;
 
-  const int stage_bytes = kABytes + t.BN * 128;
+  const int stage_bytes = kABytes + (pair ? t.BN / 2 : t.BN) * 128;
   p.pipe = (!res32 && !y32 && d->om_groups == 0 && epi_pipe_ok(t.BN, d->Cout, p.vec_ok, out_f32, d->up, res != nullptr, tf32) && d->Cout == t.BN * t.n_tiles &&
             getenv("FAMI_NO_EPI_PIPE") == nullptr) ? 1 : 0;
   const size_t pipe_pitch = tf32 ? epi_pipe_pitch(kPipeColsF32 * 2) : epi_pipe_pitch();
@@ -388,19 +451,48 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 4) * 8 + 64 +
                       (size_t)t.CoutPad * 8 + epi_bytes;
-  static std::atomic<uint64_t> attr_h{0}, attr_b{0}, attr_t{0};
-  int grid = p.m_tiles * p.n_tiles;
+  static std::atomic<uint64_t> attr_h{0}, attr_b{0}, attr_t{0}, attr_h2{0}, attr_b2{0}, attr_t2{0};
   const int sms = num_sms();
+  if (pair) {
+    int clusters = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    if (clusters > sms / 2) clusters = sms / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    if (tf32) {
+      set_max_smem_once(attr_t2, conv_tc_kernel<float, true>, 227 * 1024);
+      e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<float, true>, tmA, tmB, p);
+    } else if (d->dtype == FAMI_F16) {
+      set_max_smem_once(attr_h2, conv_tc_kernel<__half, true>, 227 * 1024);
+      e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<__half, true>, tmA, tmB, p);
+    } else {
+      set_max_smem_once(attr_b2, conv_tc_kernel<__nv_bfloat16, true>, 227 * 1024);
+      e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<__nv_bfloat16, true>, tmA, tmB, p);
+    }
+    FAMI_CHECK_ARG(e == cudaSuccess, "conv_tc_kernel (pair): launch failed: %s", cudaGetErrorString(e));
+    FAMI_CHECK_LAUNCH("conv_tc_kernel");
+    return 0;
+  }
+  int grid = p.m_tiles * p.n_tiles;
   if (grid > sms) grid = sms;
   if (tf32) {
-    set_max_smem_once(attr_t, conv_tc_kernel<float>, 227 * 1024);
-    conv_tc_kernel<float><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+    set_max_smem_once(attr_t, conv_tc_kernel<float, false>, 227 * 1024);
+    conv_tc_kernel<float, false><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   } else if (d->dtype == FAMI_F16) {
-    set_max_smem_once(attr_h, conv_tc_kernel<__half>, 227 * 1024);
-    conv_tc_kernel<__half><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+    set_max_smem_once(attr_h, conv_tc_kernel<__half, false>, 227 * 1024);
+    conv_tc_kernel<__half, false><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   } else {
-    set_max_smem_once(attr_b, conv_tc_kernel<__nv_bfloat16>, 227 * 1024);
-    conv_tc_kernel<__nv_bfloat16><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+    set_max_smem_once(attr_b, conv_tc_kernel<__nv_bfloat16, false>, 227 * 1024);
+    conv_tc_kernel<__nv_bfloat16, false><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   }
   FAMI_CHECK_LAUNCH("conv_tc_kernel");
   return 0;

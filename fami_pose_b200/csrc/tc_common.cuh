@@ -91,6 +91,97 @@ template <typename TH> __device__ __forceinline__ uint32_t umma_idesc(int BN) {
   return (1u << 4) | (TcTraits<TH>::kFmt << 7) | (TcTraits<TH>::kFmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// ---- CTA pairs (tcgen05 cta_group::2) -----------------------------------------------------------
+// Two CTAs of a cluster (same TPC) execute ONE MMA of M = 256: each CTA's tensor core produces its own 128 accumulator
+// rows from its own A tile and reads N/2 rows of B from its own shared memory and N/2 from the peer's.  Only the leader
+// (cluster rank 0) issues; tcgen05.commit multicasts the completion to the same barrier in both CTAs; TMA loads of the
+// peer signal the LEADER's full barrier (address with the peer bit cleared).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_im2col_4d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w, int h, int n,
+                                                  uint16_t offw, uint16_t offh) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & kPeerBitMask), "r"(c), "r"(w), "r"(h), "r"(n), "h"(offw), "h"(offh)
+      : "memory");
+}
+__device__ __forceinline__ void tma_tiled_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_tiled_4d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// arrive on the LEADER CTA's copy of a barrier (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+// completion of all prior MMAs of this thread -> arrive on the same barrier in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+template <bool kTf32>
+__device__ __forceinline__ void umma_pair_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool accumulate) {
+  const uint64_t ad = ((uint64_t)kSw128DescHi << 32) | a_lo;
+  const uint64_t bd = ((uint64_t)kSw128DescHi << 32) | b_lo;
+  if constexpr (kTf32) {
+    if (accumulate) {
+      asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                   ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc) : "memory");
+    } else {
+      asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                   ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc) : "memory");
+    }
+  } else {
+    if (accumulate) {
+      asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                   ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc) : "memory");
+    } else {
+      asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                   ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc) : "memory");
+    }
+  }
+}
+template <int NK, bool kTf32>
+__device__ __forceinline__ void umma_pair_ksteps(bool leader, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                 bool first_accumulates) {
+  if (leader) {
+    if (first_accumulates) umma_pair_lo<kTf32>(tmem_d, a_lo, b_lo, idesc, true);
+    else umma_pair_lo<kTf32>(tmem_d, a_lo, b_lo, idesc, false);
+#pragma unroll
+    for (int k = 1; k < NK; ++k) umma_pair_lo<kTf32>(tmem_d, a_lo + 2u * k, b_lo + 2u * k, idesc, true);
+  }
+}
+template <bool kTf32>
+__device__ __forceinline__ void umma_pair_ksteps_n(int nk, bool leader, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                                   uint32_t idesc, bool first_accumulates) {
+  switch (nk) {
+    case 1: umma_pair_ksteps<1, kTf32>(leader, tmem_d, a_lo, b_lo, idesc, first_accumulates); break;
+    case 2: umma_pair_ksteps<2, kTf32>(leader, tmem_d, a_lo, b_lo, idesc, first_accumulates); break;
+    case 3: umma_pair_ksteps<3, kTf32>(leader, tmem_d, a_lo, b_lo, idesc, first_accumulates); break;
+    default: umma_pair_ksteps<4, kTf32>(leader, tmem_d, a_lo, b_lo, idesc, first_accumulates); break;
+  }
+}
+// instruction descriptor of a pair MMA: M = 256
+template <typename TH> __device__ __forceinline__ uint32_t umma_idesc_pair(int BN) {
+  return (1u << 4) | (TcTraits<TH>::kFmt << 7) | (TcTraits<TH>::kFmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
 template <bool kTf32 = false>
 __device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool accumulate) {
   const uint64_t ad = ((uint64_t)kSw128DescHi << 32) | a_lo;
