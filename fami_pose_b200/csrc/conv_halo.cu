@@ -69,7 +69,23 @@ struct HaloParams {
 // The nine taps of one resident-weights channel chunk, issued by one warp for its M-tiles m = issuer, issuer + n_iss, ...
 // NK = 16-channel MMA steps per tap.  Everything but the descriptor increments is hoisted: at N <= 96 the issuing
 // thread's instruction stream, not the tensor pipe, sets the MMA rate.
-template <int NK, bool kTf32>
+// one (A rows, B tile) pair of NK K-steps, single CTA or CTA pair (cta_group::2)
+template <int NK, bool kTf32, bool kPair>
+__device__ __forceinline__ void halo_mma(bool leader, uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool acc) {
+  if constexpr (kPair) umma_pair_ksteps<NK, kTf32>(leader, d, a_lo, b_lo, idesc, acc);
+  else umma_ksteps<NK, kTf32>(leader, d, a_lo, b_lo, idesc, acc);
+}
+template <bool kTf32, bool kPair>
+__device__ __forceinline__ void halo_mma_n(int nk, bool leader, uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool acc) {
+  if constexpr (kPair) umma_pair_ksteps_n<kTf32>(nk, leader, d, a_lo, b_lo, idesc, acc);
+  else umma_ksteps_n<kTf32>(nk, leader, d, a_lo, b_lo, idesc, acc);
+}
+template <bool kPair> __device__ __forceinline__ void halo_commit(uint32_t bar) {
+  if constexpr (kPair) umma_commit_pair(bar);
+  else umma_commit(bar);
+}
+
+template <int NK, bool kTf32, bool kPair>
 __device__ __forceinline__ void halo_issue_taps(bool leader, uint32_t a_base, uint32_t b_lo, uint32_t b_step, uint32_t wp8,
                                                 uint32_t d8, uint32_t a_inc, uint32_t d_inc, uint32_t d0, uint32_t idesc,
                                                 int issuer, int NM, int n_iss) {
@@ -81,17 +97,32 @@ __device__ __forceinline__ void halo_issue_taps(bool leader, uint32_t a_base, ui
     for (int fs = 0; fs < 3; ++fs, a_tap += d8, b_lo += b_step) {
       uint32_t a_lo = a_tap, dcol = d0;
       for (int m = issuer; m < NM; m += n_iss, a_lo += a_inc, dcol += d_inc)
-        umma_ksteps<NK, kTf32>(leader, dcol, a_lo, b_lo, idesc, (fr | fs) != 0);
+        halo_mma<NK, kTf32, kPair>(leader, dcol, a_lo, b_lo, idesc, (fr | fs) != 0);
     }
   }
 }
 
-template <typename TH>
+// kPair: CTA pairs (cluster of 2, tcgen05 cta_group::2): the two CTAs take two consecutive CTA tiles; every MMA is M = 256
+// (M-tile m of BOTH tiles), issued by the leader CTA only -- half the MMA instructions per pixel for the issue-bound narrow
+// classes -- and each CTA keeps only HALF of the rows of every weight tile, so resident weights cost half the shared memory
+// (what lets the tf32 48->48 conv keep its weights resident AND double-buffer its A tile).
+template <typename TH, bool kPair>
 __global__ void __launch_bounds__(kHThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int kKC = TcTraits<TH>::kKC;       // channels per 128-byte row: 64 (16-bit) / 32 (tf32)
   constexpr bool kTf32 = TcTraits<TH>::kTf32;
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const bool is_leader_cta = cta_rank == 0u;
+  const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // work units: CTA tiles, or pairs of them
+  const int tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_units = kPair ? (p.total_tiles + 1) >> 1 : p.total_tiles;
+  auto unit_tile = [&](int unit, bool& dup) -> int {
+    if (!kPair) { dup = false; return unit; }
+    const int t = 2 * unit + (int)cta_rank;
+    dup = t >= p.total_tiles;
+    return dup ? p.total_tiles - 1 : t;
+  };
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int ksteps = 9 * p.cchunks;
   const int nB = p.b_resident ? ksteps : p.sB;
@@ -117,17 +148,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.sA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), p.n_iss); }
     for (int s = 0; s < nBbar; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), p.n_iss); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), p.n_iss); mbar_init(tempty(a), kEpiWarps); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), p.n_iss); mbar_init(tempty(a), kPair ? 2 * kEpiWarps : kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int acc_cols = p.NM * p.acc_stride;     // TMEM columns of one accumulator set
@@ -140,15 +178,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
       }
+      // pair mode: b_tile_bytes is this CTA's HALF of a weight tile (rows [rank * BN/2, +BN/2)); every load of either CTA
+      // completes on the LEADER's barrier, which the leader arms for the bytes of both
+      const int b_row0 = kPair ? (int)cta_rank * (p.BN >> 1) : 0;
       if (p.b_resident) {
         // all weights of this conv (single N tile) stay in shared memory for the whole kernel
-        if (leader) mbar_arrive_expect_tx(fullB(0), (uint32_t)ksteps * p.b_tile_bytes);
+        if (leader && is_leader_cta) mbar_arrive_expect_tx(fullB(0), (kPair ? 2u : 1u) * (uint32_t)ksteps * p.b_tile_bytes);
         for (int ks = 0; ks < ksteps; ++ks)
-          if (leader) tma_tiled_2d(smem_u32(smemB + (size_t)ks * p.b_tile_bytes), &tmB, fullB(0), ks * kKC, 0);
+          if (leader) {
+            if constexpr (kPair) tma_tiled_2d_2sm(smem_u32(smemB + (size_t)ks * p.b_tile_bytes), &tmB, fullB(0), ks * kKC, b_row0);
+            else tma_tiled_2d(smem_u32(smemB + (size_t)ks * p.b_tile_bytes), &tmB, fullB(0), ks * kKC, 0);
+          }
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int unit = tile0; unit < n_units; unit += tile_step) {
+        bool dup;
+        const int tile = unit_tile(unit, dup);
         const int nt = tile % p.n_tiles;
         const int t2 = tile / p.n_tiles;
         const int ty = t2 % p.tiles_per_img, img = t2 / p.tiles_per_img;
@@ -156,18 +202,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int cc = 0; cc < p.cchunks; ++cc) {
           mbar_wait(emptyA(sa), pa ^ 1u);
           if (leader) {
-            trace(p.trace, 0, (tile - blockIdx.x) / gridDim.x, 0);
-            mbar_arrive_expect_tx(fullA(sa), p.a_box_bytes);
-            tma_tiled_4d(smem_u32(smemA + (size_t)sa * p.a_stage_bytes), &tmA, fullA(sa), cc * kKC, -p.d, y0 - p.d, img);
+            trace(p.trace, 0, (unit - tile0) / tile_step, 0);
+            if constexpr (kPair) {
+              if (is_leader_cta) mbar_arrive_expect_tx(fullA(sa), 2u * p.a_box_bytes);
+              tma_tiled_4d_2sm(smem_u32(smemA + (size_t)sa * p.a_stage_bytes), &tmA, fullA(sa), cc * kKC, -p.d, y0 - p.d, img);
+            } else {
+              mbar_arrive_expect_tx(fullA(sa), p.a_box_bytes);
+              tma_tiled_4d(smem_u32(smemA + (size_t)sa * p.a_stage_bytes), &tmA, fullA(sa), cc * kKC, -p.d, y0 - p.d, img);
+            }
           }
           if (++sa == p.sA) { sa = 0; pa ^= 1u; }
           if (!p.b_resident) {
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(emptyB(sb), pb ^ 1u);
               if (leader) {
-                mbar_arrive_expect_tx(fullB(sb), p.b_tile_bytes);
-                tma_tiled_2d(smem_u32(smemB + (size_t)sb * p.b_tile_bytes), &tmB, fullB(sb), (tap * p.cchunks + cc) * kKC,
-                             nt * p.BN);
+                if constexpr (kPair) {
+                  if (is_leader_cta) mbar_arrive_expect_tx(fullB(sb), 2u * p.b_tile_bytes);
+                  tma_tiled_2d_2sm(smem_u32(smemB + (size_t)sb * p.b_tile_bytes), &tmB, fullB(sb), (tap * p.cchunks + cc) * kKC,
+                                   nt * p.BN + b_row0);
+                } else {
+                  mbar_arrive_expect_tx(fullB(sb), p.b_tile_bytes);
+                  tma_tiled_2d(smem_u32(smemB + (size_t)sb * p.b_tile_bytes), &tmB, fullB(sb), (tap * p.cchunks + cc) * kKC,
+                               nt * p.BN);
+                }
               }
               if (++sb == p.sB) { sb = 0; pb ^= 1u; }
             }
@@ -176,7 +233,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp <= kMmaWarps) {
-   if (warp - 1 < p.n_iss) {
+   if (warp - 1 < p.n_iss && is_leader_cta) {
     const int issuer = warp - 1;
     // ===================== MMA issuers (warp-uniform control flow, one elected lane issues) ======
     // Operands of tcgen05.mma live in uniform registers: keeping the whole warp converged lets the
@@ -184,12 +241,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     {
       const bool leader = elect_one();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t idesc = umma_idesc<TH>(p.BN);
+      const uint32_t idesc = kPair ? umma_idesc_pair<TH>(p.BN) : umma_idesc<TH>(p.BN);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
       if (p.b_resident) { mbar_wait(fullB(0), 0); tc_fence_after(); }
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int unit = tile0; unit < n_units; unit += tile_step, ++it) {
         const int acc = (p.acc_bufs == 2) ? (it & 1) : 0;
         const uint32_t acc_phase = (p.acc_bufs == 2) ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
         if (leader && issuer == 0) trace(p.trace, 1, it, 3);
@@ -209,12 +266,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t d0 = d_tmem + (uint32_t)(issuer * p.acc_stride);
           const uint32_t b_lo0 = sw128_desc_lo(smem_u32(smemB));
           switch (p.last_kk) {
-            case 1: halo_issue_taps<1, kTf32>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
-            case 2: halo_issue_taps<2, kTf32>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
-            case 3: halo_issue_taps<3, kTf32>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
-            default: halo_issue_taps<4, kTf32>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
+            case 1: halo_issue_taps<1, kTf32, kPair>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
+            case 2: halo_issue_taps<2, kTf32, kPair>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
+            case 3: halo_issue_taps<3, kTf32, kPair>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
+            default: halo_issue_taps<4, kTf32, kPair>(leader, a_base, b_lo0, b_step, wp8, d8, a_inc, d_inc, d0, idesc, issuer, p.NM, p.n_iss); break;
           }
-          if (leader) umma_commit(emptyA(sa));
+          if (leader) halo_commit<kPair>(emptyA(sa));
           if (++sa == p.sA) { sa = 0; pa ^= 1u; }
         } else if (!p.b_resident && !p.trace) {
           // Streamed weights (Cin > 64 or several N tiles): one B tile per (tap, channel chunk) through the ring, each
@@ -237,13 +294,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t b_lo = b_ring0 + (uint32_t)sb * b_step;
                 uint32_t a_lo = a_tap, dcol = d0;
                 for (int m = issuer; m < p.NM; m += p.n_iss, a_lo += a_inc, dcol += d_inc)
-                  umma_ksteps_n<kTf32>(nk, leader, dcol, a_lo, b_lo, idesc, accum);
+                  halo_mma_n<kTf32, kPair>(nk, leader, dcol, a_lo, b_lo, idesc, accum);
                 accum = true;
-                if (leader) umma_commit(emptyB(sb));
+                if (leader) halo_commit<kPair>(emptyB(sb));
                 if (++sb == p.sB) { sb = 0; pb ^= 1u; }
               }
             }
-            if (leader) umma_commit(emptyA(sa));
+            if (leader) halo_commit<kPair>(emptyA(sa));
             if (++sa == p.sA) { sa = 0; pa ^= 1u; }
           }
         } else
@@ -275,18 +332,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint32_t a_inc = (uint32_t)p.n_iss * 1024u, d_inc = (uint32_t)(p.n_iss * p.acc_stride);
               if (p.trace & 8) b_lo = sw128_desc_lo(smem_u32(smemB));
               for (int m = issuer; m < p.NM; m += p.n_iss, a_lo += a_inc, dcol += d_inc)
-                umma_ksteps_n<kTf32>(nk, leader, dcol, a_lo, b_lo, idesc, acc_first);
+                halo_mma_n<kTf32, kPair>(nk, leader, dcol, a_lo, b_lo, idesc, acc_first);
               if (leader && tap < 8 && issuer == 0) trace(p.trace, 3, it, tap);
               if (!p.b_resident) {
-                if (leader) umma_commit(emptyB(sb));
+                if (leader) halo_commit<kPair>(emptyB(sb));
                 if (++sb == p.sB) { sb = 0; pb ^= 1u; }
               }
             }
           }
-          if (leader) umma_commit(emptyA(sa));
+          if (leader) halo_commit<kPair>(emptyA(sa));
           if (++sa == p.sA) { sa = 0; pa ^= 1u; }
         }
-        if (leader) umma_commit(tfull(acc));
+        if (leader) halo_commit<kPair>(tfull(acc));
         if (leader && issuer == 0) trace(p.trace, 1, it, 2);
         if (leader && issuer == 0 && p.trace && blockIdx.x == 0 && it < 64) g_trace[(1 * 64 + it) * 8 + 5] = (unsigned long long)clock64();
       }
@@ -317,7 +374,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ea.res32 = p.res32; ea.y32 = p.y32; ea.res32_pitch = p.res32_pitch; ea.y32_pitch = p.y32_pitch;
     const bool stream_mode = p.res32 != nullptr || p.y32 != nullptr;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int unit = tile0; unit < n_units; unit += tile_step, ++it) {
+      bool dup;
+      const int tile = unit_tile(unit, dup);
       const int acc = (p.acc_bufs == 2) ? (it & 1) : 0;
       const uint32_t acc_phase = (p.acc_bufs == 2) ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
       const int nt = tile % p.n_tiles;
@@ -330,7 +389,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       auto row_pix = [&](int m, bool& valid) -> int {
         const int q = m * 128 + row;
         const int yy = q / p.Wp, xx = q - yy * p.Wp;
-        valid = (yy < p.BH) && (xx < p.W) && (y0 + yy < p.H);
+        valid = (yy < p.BH) && (xx < p.W) && (y0 + yy < p.H) && !dup;
         return valid ? (img * p.H + (y0 + yy)) * p.W + xx : 0;
       };
       // The residual of the NEXT M-tile (or of the first M-tile of this CTA's next tile) is copied into one of
@@ -360,14 +419,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           int npix = 0, nchb = ea.ch_base;
           if (m + 1 < p.NM) {
             npix = row_pix(m + 1, nvalid);
-          } else if (tile + (int)gridDim.x < p.total_tiles) {
-            const int ntile = tile + gridDim.x;
+          } else if (unit + tile_step < n_units) {
+            bool ndup;
+            const int ntile = unit_tile(unit + tile_step, ndup);
             const int nnt = ntile % p.n_tiles;
             const int nt2 = ntile / p.n_tiles;
             const int nty = nt2 % p.tiles_per_img, nimg = nt2 / p.tiles_per_img;
             const int ny0 = nty * p.BH;
             const int yy = row / p.Wp, xx = row - yy * p.Wp;
-            nvalid = (yy < p.BH) && (xx < p.W) && (ny0 + yy < p.H);
+            nvalid = (yy < p.BH) && (xx < p.W) && (ny0 + yy < p.H) && !ndup;
             npix = nvalid ? (nimg * p.H + (ny0 + yy)) * p.W + xx : 0;
             nchb = nnt * p.BN;
           } else {
@@ -381,14 +441,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           int npix = 0, nchb = ea.ch_base;
           if (m + 1 < p.NM) {
             npix = row_pix(m + 1, nvalid);
-          } else if (tile + (int)gridDim.x < p.total_tiles) {
-            const int ntile = tile + gridDim.x;
+          } else if (unit + tile_step < n_units) {
+            bool ndup;
+            const int ntile = unit_tile(unit + tile_step, ndup);
             const int nnt = ntile % p.n_tiles;
             const int nt2 = ntile / p.n_tiles;
             const int nty = nt2 % p.tiles_per_img, nimg = nt2 / p.tiles_per_img;
             const int ny0 = nty * p.BH;
             const int yy = row / p.Wp, xx = row - yy * p.Wp;
-            nvalid = (yy < p.BH) && (xx < p.W) && (ny0 + yy < p.H);
+            nvalid = (yy < p.BH) && (xx < p.W) && (ny0 + yy < p.H) && !ndup;
             npix = nvalid ? (nimg * p.H + (ny0 + yy)) * p.W + xx : 0;
             nchb = nnt * p.BN;
           } else {
@@ -412,16 +473,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty(acc));   // one arrival per warp
+      if (lane == 0) {                             // one arrival per warp, on the issuing (leader) CTA's barrier
+        if constexpr (kPair) mbar_arrive_leader(tempty(acc));
+        else mbar_arrive(tempty(acc));
+      }
       if (warp == kEpiWarp0 && lane == 0) trace(p.trace, 2, it, 1);
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if constexpr (kPair)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -436,7 +504,7 @@ constexpr size_t kSmemBudget = 220 * 1024;
 
 // Chooses the CTA tile: BH image rows (NM = ceil(BH*Wp/128) M-tiles).  Preference: double-buffered
 // accumulators, high fraction of useful MMA rows, weights resident if they fit.
-HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d, int kKC) {
+HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d, int kKC, bool pair = false) {
   HaloCfg best;
   best.ok = false;
   const int Wp = W + 2 * d;
@@ -463,9 +531,10 @@ HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d, int kKC) {
     if (HR < box_rows) HR = box_rows;
     HR = ((HR + 7) / 8) * 8;
     const size_t a_stage = (size_t)HR * 128;
-    const size_t b_tile = (size_t)BN * 128;
+    const size_t b_tile = (size_t)(pair ? BN / 2 : BN) * 128;      // a CTA of a pair holds half of the rows of a weight tile
     const size_t b_all = b_tile * ksteps;
     static const bool no_resident = getenv("FAMI_HALO_NORES") != nullptr;   // experiment knob: streamed weights only
+    if (pair && n_tiles != 1) break;        // the two CTAs of a pair share one N tile
     for (int resident = 1; resident >= 0; --resident) {
       if (resident && (n_tiles != 1 || no_resident)) continue;
       size_t bbytes;
@@ -506,6 +575,18 @@ HaloCfg halo_cfg(int H, int W, int Cin, int Cout, int d, int kKC) {
 
 }  // namespace
 
+// Default policy for the pair form, from tools/time_convs.py on B200 (N = 160, us single -> pair; FAMI_HALO_PAIR=1 forces it):
+//   fp16: 48->48 92 -> 100 (+res 98 -> 121), 96->96 69 -> 87, 64->64 112 -> 133, 192->48 68 -> 81, 96->48 66 -> 54
+//   tf32: 48->48 159 -> 236 (+res 175 -> 248), 96->96 102 -> 97, 64->64 224 -> 173, 96->48 68.5 -> 67.6
+// An M = 256 MMA with N <= 96 is dominated by the cross-SM exchange of the weight halves, and the two CTAs of a pair wait for
+// the slower of two A loads at every hand-over: the narrow classes this kernel exists for lose.  The pair form is therefore
+// taken only where it measured >= 15 % faster: tf32 64->64 (weights become resident) and 16-bit 96->48.
+static bool halo_pair_default(const fami_conv_desc* d, const HaloCfg& single, const HaloCfg& pair) {
+  (void)single; (void)pair;
+  if (d->dtype == FAMI_TF32) return d->Cin == 64 && d->Cout == 64;
+  return d->Cin == 96 && d->Cout == 48;
+}
+
 int conv_halo_supported(const fami_conv_desc* d) {
   if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != d->dil || d->up != 1) return 0;
   const bool tf32 = d->dtype == FAMI_TF32;
@@ -531,6 +612,14 @@ int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, cons
   FAMI_CHECK_ARG(!tf32 || d->out_dtype == FAMI_F32 || d->out_dtype == FAMI_TF32, "conv_halo: tf32 convolutions write float");
   HaloCfg c = halo_cfg(d->H, d->W, d->Cin, d->Cout, d->dil, kKC);
   FAMI_CHECK_ARG(c.ok, "conv_halo: no tile configuration fits");
+  // CTA pairs (cta_group::2): FAMI_HALO_PAIR=1 takes the pair form wherever it is legal (single N tile, no blocked output),
+  // =0 never; default: see halo_pair_default()
+  static const int pair_env = getenv("FAMI_HALO_PAIR") ? atoi(getenv("FAMI_HALO_PAIR")) : -1;
+  bool pair = false;
+  if (pair_env != 0 && c.n_tiles == 1 && d->om_groups == 0 && !res32 && !y32) {
+    HaloCfg cp = halo_cfg(d->H, d->W, d->Cin, d->Cout, d->dil, kKC, true);
+    if (cp.ok && (pair_env == 1 || halo_pair_default(d, c, cp))) { c = cp; pair = true; }
+  }
   const CUtensorMapDataType tm_dtype = tm_dtype_of(d->dtype);
   const CUtensorMapDataType tm_wdtype = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : tm_dtype;   // weights are pre-rounded
   const int dl = d->dil, Wp = d->W + 2 * dl;
@@ -550,7 +639,7 @@ int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, cons
   {
     cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)c.CoutPad};
     cuuint64_t strides[1] = {(cuuint64_t)Kp * es};
-    cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)c.BN};
+    cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)(pair ? c.BN / 2 : c.BN)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode_tiled(&tmB, tm_wdtype, 2, const_cast<void*>(w), dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -576,7 +665,7 @@ int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, cons
   p.n_iss = c.NM < kMmaWarps ? c.NM : kMmaWarps;
   if (getenv("FAMI_HALO_ISS")) { int v = atoi(getenv("FAMI_HALO_ISS")); if (v >= 1 && v <= p.n_iss) p.n_iss = v; }
   p.a_stage_bytes = (uint32_t)c.HR * 128u;
-  p.b_tile_bytes = (uint32_t)c.BN * 128u;
+  p.b_tile_bytes = (uint32_t)(pair ? c.BN / 2 : c.BN) * 128u;
   p.a_box_bytes = (uint32_t)((c.BH + 2 * dl) * Wp) * 128u;
   p.scale = scale; p.shift = shift; p.res = res; p.y = y;
   p.res32 = res32; p.y32 = y32; p.res32_pitch = d->res_pitch; p.y32_pitch = y32_pitch;
@@ -586,19 +675,48 @@ int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, cons
   static const bool trace_on = getenv("FAMI_HALO_TRACE") != nullptr;
   p.trace = trace_on ? atoi(getenv("FAMI_HALO_TRACE")) : 0;
 
-  static std::atomic<uint64_t> attr_h{0}, attr_b{0}, attr_t{0};
-  int grid = p.total_tiles;
+  static std::atomic<uint64_t> attr_h{0}, attr_b{0}, attr_t{0}, attr_h2{0}, attr_b2{0}, attr_t2{0};
   const int sms = num_sms();
+  if (pair) {
+    int clusters = (p.total_tiles + 1) / 2;
+    if (clusters > sms / 2) clusters = sms / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kHThreads);
+    cfg.dynamicSmemBytes = c.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    if (tf32) {
+      set_max_smem_once(attr_t2, conv_halo_kernel<float, true>, 227 * 1024);
+      e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<float, true>, tmA, tmB, p);
+    } else if (d->dtype == FAMI_F16) {
+      set_max_smem_once(attr_h2, conv_halo_kernel<__half, true>, 227 * 1024);
+      e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<__half, true>, tmA, tmB, p);
+    } else {
+      set_max_smem_once(attr_b2, conv_halo_kernel<__nv_bfloat16, true>, 227 * 1024);
+      e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<__nv_bfloat16, true>, tmA, tmB, p);
+    }
+    FAMI_CHECK_ARG(e == cudaSuccess, "conv_halo_kernel (pair): launch failed: %s", cudaGetErrorString(e));
+    FAMI_CHECK_LAUNCH("conv_halo_kernel");
+    return 0;
+  }
+  int grid = p.total_tiles;
   if (grid > sms) grid = sms;
   if (tf32) {
-    set_max_smem_once(attr_t, conv_halo_kernel<float>, 227 * 1024);
-    conv_halo_kernel<float><<<grid, kHThreads, c.smem, st>>>(tmA, tmB, p);
+    set_max_smem_once(attr_t, conv_halo_kernel<float, false>, 227 * 1024);
+    conv_halo_kernel<float, false><<<grid, kHThreads, c.smem, st>>>(tmA, tmB, p);
   } else if (d->dtype == FAMI_F16) {
-    set_max_smem_once(attr_h, conv_halo_kernel<__half>, 227 * 1024);
-    conv_halo_kernel<__half><<<grid, kHThreads, c.smem, st>>>(tmA, tmB, p);
+    set_max_smem_once(attr_h, conv_halo_kernel<__half, false>, 227 * 1024);
+    conv_halo_kernel<__half, false><<<grid, kHThreads, c.smem, st>>>(tmA, tmB, p);
   } else {
-    set_max_smem_once(attr_b, conv_halo_kernel<__nv_bfloat16>, 227 * 1024);
-    conv_halo_kernel<__nv_bfloat16><<<grid, kHThreads, c.smem, st>>>(tmA, tmB, p);
+    set_max_smem_once(attr_b, conv_halo_kernel<__nv_bfloat16, false>, 227 * 1024);
+    conv_halo_kernel<__nv_bfloat16, false><<<grid, kHThreads, c.smem, st>>>(tmA, tmB, p);
   }
   FAMI_CHECK_LAUNCH("conv_halo_kernel");
   return 0;
