@@ -48,15 +48,22 @@ def patch_reference():
            HighResolutionModule=HighResolutionModule, HRNetPlus=HRNetPlus, HRNet=HRNet,
            blocks_dict={'BASIC': BasicBlock, 'BOTTLENECK': Bottleneck})
     rebind("posetimation.loss.mse_loss", JointMSELoss=JointMSELoss)
-    if "kornia" not in sys.modules:
+    # kornia.geometry.warp_affine: the translation-only shim is bound to the name `kornia` INSIDE the Alignment_V15 module
+    # only (its single call site, Alignment_V15.py:133-135, builds a pure translation) -- a real kornia install keeps its own
+    # warp_affine for every other caller (rotation / scale augmentation code).  Without kornia installed a stub module is
+    # registered so that the reference's `import kornia` succeeds; the stub has nothing but the shim.
+    try:
+        importlib.import_module("kornia")
+    except Exception:
         k = types.ModuleType("kornia")
         k.geometry = types.ModuleType("kornia.geometry")
+        k.geometry.warp_affine = kornia_shim.warp_affine
         sys.modules["kornia"] = k
         sys.modules["kornia.geometry"] = k.geometry
-    sys.modules["kornia"].geometry.warp_affine = kornia_shim.warp_affine
-    patched.append("kornia.geometry.warp_affine")
+        patched.append("kornia (stub module)")
+    proxy = types.SimpleNamespace(geometry=types.SimpleNamespace(warp_affine=kornia_shim.warp_affine))
     rebind("posetimation.zoo.Alignment.Alignment_V15", conv_bn_relu=conv_bn_relu,
-           ChainOfBasicBlocks=ChainOfBasicBlocks, HRNetPlus=HRNetPlus, DeformConv2d=DeformConv2d)
+           ChainOfBasicBlocks=ChainOfBasicBlocks, HRNetPlus=HRNetPlus, DeformConv2d=DeformConv2d, kornia=proxy)
     # engine plug-in registries (engine/defaults/constant.py:9-11; looked up by cfg.CORE_FUNCTION, engine/core/base.py:65,
     # and cfg.MODEL.NAME, posetimation/zoo/build.py:65): the entries are REPLACED under the reference's own names, so a
     # config naming AlignmentMIFunction_Term6_V1 / Alignment_V15 runs the fami versions with no config change

@@ -294,11 +294,8 @@ template <int WM, int WN, int MODE, typename TX, typename TO>
 static int launch_cfg(const ConvParams& p, cudaStream_t st) {
   constexpr int BM = WM * 64, BN = WN * 16;
   constexpr size_t smem = (size_t)3 * (BM * 20 + 16 * BN) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(conv_f32_kernel<WM, WN, MODE, TX, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_mask{0};
+  set_max_smem_once(attr_mask, conv_f32_kernel<WM, WN, MODE, TX, TO>, (int)smem);
   dim3 grid(cdiv(p.M, BM), p.CoutPad / BN);
   conv_f32_kernel<WM, WN, MODE, TX, TO><<<grid, WM * WN * 32, smem, st>>>(p);
   FAMI_CHECK_LAUNCH("conv_f32_kernel");

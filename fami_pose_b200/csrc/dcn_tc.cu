@@ -1,18 +1,20 @@
 // Modulated deformable convolution v2 on B200 -- the north-star kernel (fami_dcn_fwd, 16-bit arm).
 // Replaces torchvision.ops.deform_conv2d as called at posetimation/zoo/Alignment/Alignment_V15.py:146-158.
 //
-// Structure (persistent CTAs, one 16x8-pixel tile at a time, 544 threads):
+// Structure (persistent CTAs, one 16x8-pixel tile at a time, 640 threads = 20 warps x 96 registers):
 //   * the x neighbourhood of the tile ((16+2R) x (8+2R) pixels x 64 channel slots) is brought ONCE into
-//     shared memory by a TMA tiled box load (128B-swizzled rows; out-of-image pixels zero-filled, which
-//     is exactly torchvision's "corner outside the image contributes 0" rule);
-//   * 12 gather warps in three groups; group q owns UMMA A stage q and taps q, q+3, q+6. A thread is one
-//     output pixel: per tap it reads the pixel's 3*G (dy | dx | mask) floats as 16-byte loads -- streamed
-//     from HBM exactly once, in the tap-major layout the fused offset|mask conv writes -- and for each
-//     offset group forms the four bilinear corners from shared memory (8-byte loads), blends them in
-//     packed 16-bit arithmetic and stores the modulated columns into the A tile (128B-swizzled K-major,
-//     16-byte stores). Samples outside the staged window are collected in a bit mask and resolved
-//     afterwards through a bounds-checked global path;
-//   * one warp issues tcgen05.mma (M=128, N=Cout, K=C per tap) against the weights resident in shared
+//     shared memory by a TMA tiled box load, UNSWIZZLED with a 128-byte pixel pitch (out-of-image pixels
+//     zero-filled, which is exactly torchvision's "corner outside the image contributes 0" rule);
+//   * 16 gather warps, warp w = image row w of the tile.  A LANE is (pixel, offset group): the 4-channel
+//     (8-byte) corner of group g sits at byte 8g of its pixel's 128-byte row, i.e. in bank pair g WHATEVER the
+//     sampling position is -- the lanes of a half-warp (one pixel's groups) can never conflict, for any offsets
+//     (the one-lane-per-pixel mappings before were 2.9x over the ideal wavefront count at sigma = 2 px).  Per
+//     (pixel, tap) a lane reads its (dy, dx, mask) -- streamed from HBM exactly once, in the lane-blocked layout
+//     the fused offset|mask convolution writes, pulled into L2 two tiles ahead by bulk prefetches and into
+//     registers two taps ahead --, forms the four bilinear corners from shared memory, blends them in packed
+//     16-bit arithmetic and stores the modulated 4 channels into the tap's A tile (128B-swizzled K-major).
+//     Samples outside the staged window are resolved per tap through a bounds-checked global path;
+//   * one warp (also an epilogue warp) issues tcgen05.mma (M=128, N=Cout, K=C per tap) against the weights resident in shared
 //     memory, accumulating the nine taps in TMEM (double buffered across tiles);
 //   * 4 epilogue warps add the bias and store the tile (coalesced, through shared-memory staging).
 // The [C*9, B*H*W] column buffer of the reference never exists; HBM traffic is the algorithmic minimum:
@@ -36,14 +38,23 @@ __device__ __forceinline__ void dtrace(int on, int it, int ev) {
 }
 
 constexpr int kTH = 16, kTW = 8;            // output tile (pixels): 128 = one UMMA M tile
-constexpr int kGatherSets = 2;            // two sets of 8 warps; set s gathers taps s, s+2, s+4, ... of every tile
-constexpr int kSetWarps = 8;              // 256 threads = 128 pixels x 2 offset-group parities
-constexpr int kGatherWarps = kGatherSets * kSetWarps;
+constexpr int kGatherWarps = kTH;         // gather warp w owns image row w of the tile
 constexpr int kGatherThreads = 32 * kGatherWarps;
 constexpr int kDcnEpiWarps = 4;
-constexpr int kDcnThreads = kGatherThreads + 32 + 32 * kDcnEpiWarps;   // 672
+constexpr int kDcnThreads = kGatherThreads + 32 * kDcnEpiWarps;   // 640: 20 warps x 96 registers fill the register file
+                                                                     // (the first epilogue warp is also the TMA + MMA issuer)
 constexpr int kAStages = 3;               // tap t -> A stage t % 3
 constexpr int kATile = 128 * 128;          // bytes per A stage
+constexpr uint32_t kMagicBits = 0x4B400000u;   // 1.5 * 2^23: adding it with round-down leaves floor(v) in the low mantissa bits
+constexpr float kMagic = 12582912.f;
+
+// lane <-> (pixel, offset group) map of a gather warp: LG lanes per pixel (G rounded up to a power of two), PPW pixels
+// per warp iteration, NIT iterations per (tile row, tap).  G = 12 leaves lanes 12..15 of each half-warp idle.
+template <int kG> struct LaneMap {
+  static constexpr int LG = kG > 8 ? 16 : kG;
+  static constexpr int PPW = 32 / LG;
+  static constexpr int NIT = kTW / PPW;
+};
 
 struct DcnTcParams {
   int B, H, W, C, Cout, G, d, R;
@@ -51,11 +62,11 @@ struct DcnTcParams {
   int tiles_x, tiles_y, total_tiles;
   int nk, BN;
   int om_pitch, x_pitch, out_pitch, vec_ok, out_f32;
-  int om_blocked;                   // 1: offsets|masks in the warp-blocked layout (om_layout 2)
-  int64_t om_tap_stride;            // floats between taps in the blocked layout = nblk * (3G/4) * 128
+  int om_blocked;                   // 1: offsets|masks in the lane-blocked layout (om_layout 2)
+  int64_t om_tap_stride;            // floats between taps in the blocked layout = tiles * 128 * 3G
   uint32_t win_bytes, w_tile_bytes, ab_format;
   int trace;
-  const float* om;                  // [B*H*W][om_pitch], per pixel [9 taps][dy(G) | dx(G) | mask(G)]
+  const float* om;                  // layout 1: [B*H*W][om_pitch], per pixel [9 taps][dy(G) | dx(G) | mask(G)]
   const void* x;                    // TH NHWC (global fallback path)
   const float* bias;
   void* out;
@@ -79,7 +90,6 @@ template <> __device__ __forceinline__ float4 ld4h<__nv_bfloat16>(const __nv_bfl
 template <typename TH> struct H2;
 template <> struct H2<__half> {
   typedef __half2 t;
-  static __device__ __forceinline__ t bcast(float w) { return __float2half2_rn(w); }
   static __device__ __forceinline__ t pack(float a, float b) { return __floats2half2_rn(a, b); }
   static __device__ __forceinline__ t lo(t v) { return __low2half2(v); }
   static __device__ __forceinline__ t hi(t v) { return __high2half2(v); }
@@ -88,7 +98,6 @@ template <> struct H2<__half> {
 };
 template <> struct H2<__nv_bfloat16> {
   typedef __nv_bfloat162 t;
-  static __device__ __forceinline__ t bcast(float w) { return __float2bfloat162_rn(w); }
   static __device__ __forceinline__ t pack(float a, float b) { return __floats2bfloat162_rn(a, b); }
   static __device__ __forceinline__ t lo(t v) { return __low2bfloat162(v); }
   static __device__ __forceinline__ t hi(t v) { return __high2bfloat162(v); }
@@ -96,26 +105,39 @@ template <> struct H2<__nv_bfloat16> {
   static __device__ __forceinline__ t mul(t a, t b) { return __hmul2(a, b); }
 };
 
+// streamed once: no L1 allocation (the three loads of an iteration touch disjoint 32-byte sectors)
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float v;
+  asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+// (dy, dx, mask) of one tap for the NIT iterations of a lane
+template <int NIT> struct OmRegs { float dy[NIT], dx[NIT], mk[NIT]; };
+
 template <typename TH, int kG>
 __global__ void __launch_bounds__(kDcnThreads, 1)
 dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const DcnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* s_win = smem;                                   // WH*WW rows x 128 B
-  uint8_t* s_a = s_win + p.win_bytes;                      // kAStages x 16 KB
-  uint8_t* s_w = s_a + kAStages * kATile;                  // 9 x BN x 128 B
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + 9 * p.w_tile_bytes);
-  const uint32_t bar0 = smem_u32(bars);
+  // every address below is a 32-bit shared-space address derived ONCE from the aligned base (generic pointers only for the
+  // few plain C accesses): the compiler otherwise rematerialises the generic -> shared conversion in the inner loops
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t sbase = (raw_u32 + 1023u) & ~1023u;
+  const uint32_t win_u32 = sbase;                                          // WH*WW rows x 128 B
+  const uint32_t a_u32 = win_u32 + ((p.win_bytes + 1023u) & ~1023u);       // kAStages x 16 KB (1 KB-aligned swizzle atoms)
+  const uint32_t w_u32 = a_u32 + kAStages * kATile;                        // 9 x BN x 128 B
+  const uint32_t bar0 = w_u32 + 9 * p.w_tile_bytes;
   // barriers: win_full, win_free, w_full, a_full[3], a_empty[3], tfull[2], tempty[2]
   const uint32_t win_full = bar0, win_free = bar0 + 8, w_full = bar0 + 16;
   auto a_full = [&](int s) { return bar0 + 8u * (3 + s); };
   auto a_empty = [&](int s) { return bar0 + 8u * (3 + kAStages + s); };
   auto tfull = [&](int a) { return bar0 + 8u * (3 + 2 * kAStages + a); };
   auto tempty = [&](int a) { return bar0 + 8u * (5 + 2 * kAStages + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 + 2 * kAStages);
-  float* s_scale = reinterpret_cast<float*>(bars + 10 + 2 * kAStages);   // 16-byte aligned (float4 reads)
+  uint8_t* gen0 = smem_raw + (bar0 - raw_u32);                             // generic pointer to the barrier block
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen0 + 8 * (7 + 2 * kAStages));
+  float* s_scale = reinterpret_cast<float*>(gen0 + 8 * (10 + 2 * kAStages));   // 16-byte aligned (float4 reads)
   float* s_shift = s_scale + p.BN;
-  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_shift + p.BN) + 15) & ~(uintptr_t)15);
+  const uint32_t stage_u32 = (bar0 + 8u * (10 + 2 * kAStages) + (uint32_t)p.BN * 8u + 15u) & ~15u;   // epilogue staging
   fill_scale_shift(s_scale, s_shift, nullptr, p.bias, p.Cout, p.BN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,13 +145,13 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     mbar_init(win_full, 1);
     mbar_init(win_free, kGatherWarps);
     mbar_init(w_full, 1);
-    for (int s = 0; s < kAStages; ++s) { mbar_init(a_full(s), kSetWarps); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < kAStages; ++s) { mbar_init(a_full(s), kGatherWarps); mbar_init(a_empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), kDcnEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
   }
   if (warp == kGatherWarps) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bar0 + 8u * (7 + 2 * kAStages)), "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -149,167 +171,201 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 
   if (warp < kGatherWarps) {
     // ===================== gather warps =====================
-    // Two sets of eight warps; set s owns the taps s, s+2, s+4, ... of every tile (tap t lands in A stage t % 3, the MMA
-    // warp consumes the taps in order).  A thread is (output pixel, offset-group parity): it walks the kG/2 groups
-    // g = 2j + parity of its pixel for one tap.  Lane layout: 16 lanes = 8 consecutive pixels of an image row x 2 parities.
-    // Bank picture of a corner load (8 bytes at window row r, 16-byte chunk (g>>1) ^ (r&7), half g&1): eight consecutive
-    // pixels hit eight different chunks and the two parities the two halves, so a half-warp covers all 32 banks when the
-    // offsets are smooth (one wavefront instead of the 2-4 of a one-thread-per-pixel mapping, where g&1 was warp-uniform
-    // and only half the banks were reachable), and random offsets spread over 16 bank pairs instead of 8.
-    constexpr int kQ = kG / 4;
-    constexpr int kJ = kG / 2;             // groups per thread
+    typedef LaneMap<kG> LM;
+    constexpr int LG = LM::LG, PPW = LM::PPW, NIT = LM::NIT;
     typedef typename H2<TH>::t h2;
+    typedef OmRegs<NIT> Om;
     const TH* xg = reinterpret_cast<const TH*>(p.x);
-    const uint32_t win_u32 = smem_u32(s_win);
-    const int set = warp / kSetWarps;
-    const int wset = warp - set * kSetWarps;                      // warp within the set: image rows 2*wset, 2*wset+1 of the tile
-    const int par = lane & 1;
-    const int ry = 2 * wset + (lane >> 4), rx = (lane >> 1) & 7;
-    const int r = ry * kTW + rx;                                   // A-tile row = pixel of the tile
-    const uint32_t rsw = (uint32_t)(r & 7) << 4;
-    const uint32_t a_row0 = smem_u32(s_a) + (uint32_t)(r * 128) + ((uint32_t)par << 3);
-    const int WW = p.WW;
-    const unsigned ylim = (unsigned)(p.WH - 1), xlim = (unsigned)(WW - 1);
-    uint32_t wph = 0, fph = 0;
-    int git = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++git) {
+    const int ry = warp;                                   // image row of the tile
+    const int pix = lane / LG, g = lane - pix * LG;
+    const bool lane_on = g < kG;
+    const uint32_t rowpitch = (uint32_t)p.WW * 128u;
+    const uint32_t ylim = (uint32_t)(p.WH - 1), xlim = (uint32_t)(p.WW - 1);
+    // window address of the sample = iy_bits * rowpitch + ix_bits * 128 + kaddr (+ iteration * PPW * 128), the bit patterns
+    // of the magic-number floors used directly (32-bit wrap-around arithmetic)
+    const uint32_t kaddr = win_u32 + (uint32_t)g * 8u - kMagicBits * rowpitch - kMagicBits * 128u;
+    const uint32_t win_safe = win_u32;
+    // A-tile byte address of (row r = ry*8 + j*PPW + pix, group g), 128B-swizzled K-major: chunk (g>>1) ^ (r&7).  pix and
+    // j*PPW occupy disjoint bits of r&7, so iteration j is the iteration-0 address with bits 4..6 XORed by j*PPW, plus j*PPW rows.
+    const uint32_t aoff0 = a_u32 + (uint32_t)((ry * kTW + pix) * 128) + ((uint32_t)(((g >> 1) ^ pix) << 4) | ((uint32_t)(g & 1) << 3));
+    auto a_addr = [&](int j, int kc) { return (aoff0 ^ (uint32_t)(j * PPW * 16)) + (uint32_t)(j * PPW * 128 + kc * kATile); };
+    const float fd = (float)p.d;
+    const float my0 = kMagic + (float)(ry + p.R - p.d);     // + kr * d per kernel row
+    const float mx0 = kMagic + (float)(pix + p.R - p.d);    // + kc * d per kernel column
+    const float mx1 = mx0 + fd, mx2 = mx1 + fd;
+
+    // per-tile state of this lane: pointer to its (dy) float of tap 0 / iteration 0, and the valid-iteration mask
+    struct TileRef { const float* po; uint32_t vmask; int tile; };
+    auto tile_ref = [&](int tile) {
+      TileRef t;
+      t.po = p.om; t.vmask = 0; t.tile = tile;
+      if (tile >= p.total_tiles) return t;
       int b, y0, x0;
       tile_origin(tile, b, y0, x0);
-      if (threadIdx.x == 0) dtrace(p.trace, git, 0);
-      const int y = y0 + ry, x = x0 + rx;
-      const bool valid = y < p.H && x < p.W;
-      // tap-major NHWC (om_layout 1): the 3*kG floats of a (pixel, tap) are one contiguous run.  Warp-blocked (om_layout 2):
-      // [tap][tile*8 + warp block][q < 3kG/4][16 pixels][e0 e2 | e1 e3]: this lane's float2 = its two groups of quad q, the
-      // warp's 32 lanes read 256 contiguous bytes per instruction.
-      const float* po = p.om_blocked
-                            ? p.om + ((int64_t)tile * 8 + wset) * (3 * kQ * 64) + (lane & 31) * 2
-                            : p.om + ((int64_t)(b * p.H + y) * p.W + x) * p.om_pitch;
-      float2 vdy[kQ], vdx[kQ], vmk[kQ];      // groups g = 4i + par (x) and 4i + 2 + par (y)
-      auto load_unit = [&](int tap) {
-        if (p.om_blocked) {
-          const float* o = po + tap * p.om_tap_stride;
+      const int y = y0 + ry;
 #pragma unroll
-          for (int i = 0; i < kQ; ++i) {
-            vdy[i] = __ldg(reinterpret_cast<const float2*>(o + i * 64));
-            vdx[i] = __ldg(reinterpret_cast<const float2*>(o + (kQ + i) * 64));
-            vmk[i] = __ldg(reinterpret_cast<const float2*>(o + (2 * kQ + i) * 64));
-          }
-        } else {
-          const float* o = po + tap * 3 * kG + par;
+      for (int j = 0; j < NIT; ++j)
+        if (lane_on && y < p.H && x0 + j * PPW + pix < p.W) t.vmask |= 1u << j;
+      if (p.om_blocked) {
+        // [tap][tile][row 16][iteration NIT][dy | dx | mask][pixel PPW][group G]
+        t.po = p.om + (int64_t)tile * (128 * 3 * kG) + ry * (NIT * 3 * PPW * kG) + pix * kG + g;
+      } else {
+        t.po = p.om + ((int64_t)(b * p.H + (y < p.H ? y : 0)) * p.W + x0 + pix) * p.om_pitch + g;
+      }
+      return t;
+    };
+    auto load_tap = [&](const TileRef& t, int tap, Om& o) {
+      if (p.om_blocked) {
+        const float* q = t.po + tap * p.om_tap_stride;
 #pragma unroll
-          for (int i = 0; i < kQ; ++i) {
-            vdy[i] = make_float2(__ldg(o + 4 * i), __ldg(o + 4 * i + 2));
-            vdx[i] = make_float2(__ldg(o + kG + 4 * i), __ldg(o + kG + 4 * i + 2));
-            vmk[i] = make_float2(__ldg(o + 2 * kG + 4 * i), __ldg(o + 2 * kG + 4 * i + 2));
-          }
+        for (int j = 0; j < NIT; ++j) {
+          const bool v = (t.vmask >> j) & 1u;
+          o.dy[j] = v ? ldg_stream(q + (j * 3 + 0) * (PPW * kG)) : 0.f;
+          o.dx[j] = v ? ldg_stream(q + (j * 3 + 1) * (PPW * kG)) : 0.f;
+          o.mk[j] = v ? ldg_stream(q + (j * 3 + 2) * (PPW * kG)) : 0.f;
         }
-      };
-      if (valid) load_unit(set);
+      } else {
+        const float* q = t.po + tap * 3 * kG;
+#pragma unroll
+        for (int j = 0; j < NIT; ++j) {
+          const bool v = (t.vmask >> j) & 1u;
+          const float* qj = q + (int64_t)(j * PPW) * p.om_pitch;
+          o.dy[j] = v ? __ldg(qj) : 0.f;
+          o.dx[j] = v ? __ldg(qj + kG) : 0.f;
+          o.mk[j] = v ? __ldg(qj + 2 * kG) : 0.f;
+        }
+      }
+    };
+    // load of the tap two positions ahead in the (tile, tap) stream
+    auto load_ahead = [&](const TileRef& cur, const TileRef& nxt, int tap, Om& o) {
+      if (tap + 2 < 9) load_tap(cur, tap + 2, o);
+      else load_tap(nxt, tap + 2 - 9, o);
+    };
+
+    // one tap of one tile: NIT samples of this lane into A stage kc
+    auto do_tap = [&](const TileRef& t, const Om& o, int kr, float my, float mx, int kc, int git) {
+      const uint32_t u = (uint32_t)(git * 3 + kr);            // use index of stage kc
+      mbar_wait(a_empty(kc), (u & 1u) ^ 1u);
+      bool far = false;                          // any sample of this lane outside the staged window
+      constexpr int NB = NIT < 2 ? NIT : 2;      // samples per batch (8 corner loads in flight per lane)
+#pragma unroll
+      for (int j0 = 0; j0 < NIT; j0 += NB) {
+        uint32_t a00[NB], a10[NB];
+        h2 w12[NB], w34[NB];
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) {
+          const int j = j0 + jb;
+          const float dy = o.dy[j], dx = o.dx[j], mk = o.mk[j];
+          // floor() through the magic-number add (round-down): exact for |v| < 2^22, the integer lands in the low mantissa bits
+          const float ty = __fadd_rd(dy, my), tx = __fadd_rd(dx, mx);
+          const float ly = dy - (ty - my), lx = dx - (tx - mx);
+          const uint32_t iyb = __float_as_uint(ty), ixb = __float_as_uint(tx);
+          const bool in = (iyb - kMagicBits) < ylim && (ixb - (kMagicBits - (uint32_t)(j * PPW))) < xlim;
+          const float wb = mk * ly, wt = mk - wb;          // mask * (ly | 1 - ly)
+          const float w4f = wb * lx, w3f = wb - w4f, w2f = wt * lx, w1f = wt - w2f;
+          w12[jb] = H2<TH>::pack(w1f, w2f);
+          w34[jb] = H2<TH>::pack(w3f, w4f);
+          const uint32_t a = iyb * rowpitch + (ixb * 128u + kaddr);
+          a00[jb] = in ? a : win_safe;                      // outside the staged window: harmless address, fixed up below
+          a10[jb] = a00[jb] + rowpitch;
+          far |= !in;      // (idle lanes and pixels outside the image carry zero offsets: always inside)
+        }
+        uint2 u1[NB], u2[NB], u3[NB], u4[NB];
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) {
+          const int j = j0 + jb;
+          u1[jb] = lds64(a00[jb] + (uint32_t)(j * PPW * 128));
+          u2[jb] = lds64(a00[jb] + (uint32_t)(j * PPW * 128 + 128));
+          u3[jb] = lds64(a10[jb] + (uint32_t)(j * PPW * 128));
+          u4[jb] = lds64(a10[jb] + (uint32_t)(j * PPW * 128 + 128));
+        }
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) {
+          const int j = j0 + jb;
+          const h2 w1 = H2<TH>::lo(w12[jb]), w2 = H2<TH>::hi(w12[jb]), w3 = H2<TH>::lo(w34[jb]), w4 = H2<TH>::hi(w34[jb]);
+          h2 lo = H2<TH>::mul(w1, *reinterpret_cast<const h2*>(&u1[jb].x));
+          h2 hi = H2<TH>::mul(w1, *reinterpret_cast<const h2*>(&u1[jb].y));
+          lo = H2<TH>::fma(w2, *reinterpret_cast<const h2*>(&u2[jb].x), lo);
+          hi = H2<TH>::fma(w2, *reinterpret_cast<const h2*>(&u2[jb].y), hi);
+          lo = H2<TH>::fma(w3, *reinterpret_cast<const h2*>(&u3[jb].x), lo);
+          hi = H2<TH>::fma(w3, *reinterpret_cast<const h2*>(&u3[jb].y), hi);
+          lo = H2<TH>::fma(w4, *reinterpret_cast<const h2*>(&u4[jb].x), lo);
+          hi = H2<TH>::fma(w4, *reinterpret_cast<const h2*>(&u4[jb].y), hi);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+          // (a pixel outside the image carries mask 0: all four weights are 0 and the column is 0; idle lanes never store)
+          if (lane_on) sts64(a_addr(j, kc), pk);
+        }
+      }
+      // large offsets: bounds-checked global corners, fp32 blend.  Kept out of the sample loop and entered once per tap
+      // by the whole warp, so the dependent global loads of all far samples of the tap are in flight together.
+      if (__any_sync(0xffffffffu, far)) {
+        uint32_t slow = 0;
+#pragma unroll
+        for (int j = 0; j < NIT; ++j) {
+          const uint32_t iyb = __float_as_uint(__fadd_rd(o.dy[j], my)), ixb = __float_as_uint(__fadd_rd(o.dx[j], mx));
+          if (!((iyb - kMagicBits) < ylim && (ixb - (kMagicBits - (uint32_t)(j * PPW))) < xlim)) slow |= 1u << j;
+        }
+        while (slow) {
+          const int j = __ffs((int)slow) - 1;
+          slow &= slow - 1u;
+          float sdy = 0.f, sdx = 0.f, smk = 0.f;
+#pragma unroll
+          for (int jj = 0; jj < NIT; ++jj)
+            if (jj == j) { sdy = o.dy[jj]; sdx = o.dx[jj]; smk = o.mk[jj]; }
+          int tb, ty0, tx0;
+          tile_origin(t.tile, tb, ty0, tx0);
+          const int y = ty0 + ry, x = tx0 + j * PPW + pix;
+          const float py = (float)(y - p.d + kr * p.d) + sdy;
+          const float px = (float)(x - p.d + kc * p.d) + sdx;
+          uint2 pk2 = make_uint2(0u, 0u);
+          if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
+            const int iy0 = (int)floorf(py), ix0 = (int)floorf(px);
+            const float ly = py - (float)iy0, lx = px - (float)ix0, hy = 1.f - ly, hx = 1.f - lx;
+            const TH* xb = xg + (int64_t)tb * p.H * p.W * p.x_pitch + g * 4;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool y0ok = iy0 >= 0, y1ok = iy0 + 1 <= p.H - 1, x0ok = ix0 >= 0, x1ok = ix0 + 1 <= p.W - 1;
+            const float4 v1 = (y0ok && x0ok) ? ld4h<TH>(xb + ((int64_t)iy0 * p.W + ix0) * p.x_pitch) : z;
+            const float4 v2 = (y0ok && x1ok) ? ld4h<TH>(xb + ((int64_t)iy0 * p.W + ix0 + 1) * p.x_pitch) : z;
+            const float4 v3 = (y1ok && x0ok) ? ld4h<TH>(xb + ((int64_t)(iy0 + 1) * p.W + ix0) * p.x_pitch) : z;
+            const float4 v4 = (y1ok && x1ok) ? ld4h<TH>(xb + ((int64_t)(iy0 + 1) * p.W + ix0 + 1) * p.x_pitch) : z;
+            const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+            pk2.x = f2_to_h2<TH>(smk * (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x),
+                                 smk * (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y));
+            pk2.y = f2_to_h2<TH>(smk * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z),
+                                 smk * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w));
+          }
+          sts64((aoff0 ^ (uint32_t)(j * PPW * 16)) + (uint32_t)(j * PPW * 128 + kc * kATile), pk2);
+        }
+        __syncwarp();
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full(kc));   // one arrival per warp
+    };
+
+    uint32_t wph = 0, fph = 0;
+    int git = 0;
+    TileRef cur = tile_ref(blockIdx.x), nxt = tile_ref(blockIdx.x + gridDim.x);
+    Om o0, o1, o2;                       // taps 3i, 3i+1, 3i+2 of the stream: rotating, two taps in flight
+    load_tap(cur, 0, o0);
+    load_tap(cur, 1, o1);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++git) {
+      if (threadIdx.x == 0) dtrace(p.trace, git, 0);
       mbar_wait(win_full, wph);
       wph ^= 1u;
       if (threadIdx.x == 0) dtrace(p.trace, git, 1);
+      float my = my0;
 #pragma unroll 1
-      for (int tap = set; tap < 9; tap += kGatherSets) {
-        const int kr = tap / 3, kc = tap - kr * 3;      // kernel row / column
-        const int stage = tap - kr * 3;                 // tap % 3
-        const uint32_t u = (uint32_t)(git * 3 + kr);    // use index of this stage
-        mbar_wait(a_empty(stage), (u & 1u) ^ 1u);
-        const uint32_t a_row = a_row0 + (uint32_t)(stage * kATile);
-        if (!valid) {
-#pragma unroll
-          for (int j = 0; j < kJ; ++j) sts64(a_row + (((uint32_t)j << 4) ^ rsw), make_uint2(0u, 0u));
-        } else {
-          const float base_y = (float)(ry + kr * p.d + p.R - p.d);
-          const float base_x = (float)(rx + kc * p.d + p.R - p.d);
-          uint32_t slow = 0;
-#pragma unroll
-          for (int j = 0; j < kJ; ++j) {
-            // group g = 2j + par: quad j >> 1, element (j & 1) of this lane's float2
-            const float dy = (j & 1) ? vdy[j >> 1].y : vdy[j >> 1].x;
-            const float dx = (j & 1) ? vdx[j >> 1].y : vdx[j >> 1].x;
-            const float mk = (j & 1) ? vmk[j >> 1].y : vmk[j >> 1].x;
-            // window coordinates: integer shifts of the image-space sample position, so the fractional
-            // parts are exactly those of py / px.  floor() without the conversion unit (FRND / F2I run at 16 lanes
-            // per clock and were 2/3 busy): adding 1.5 * 2^23 with round-down leaves floor(w) in the low mantissa bits
-            // for |w| < 2^22; a sample further out than that is far outside the window either way.
-            const float wy = base_y + dy, wx = base_x + dx;
-            const float ty = __fadd_rd(wy, 12582912.f), tx = __fadd_rd(wx, 12582912.f);
-            const float fy = ty - 12582912.f, fx = tx - 12582912.f;
-            const int iy = __float_as_int(ty) - 0x4B400000, ix = __float_as_int(tx) - 0x4B400000;
-            uint2 pk = make_uint2(0u, 0u);
-            if ((unsigned)iy < ylim && (unsigned)ix < xlim) {
-              // all four corners inside the staged (zero-padded) window: 8-byte shared-memory loads,
-              // blend in packed 16-bit arithmetic (the column is rounded to 16 bit for the MMA anyway)
-              const float ly = wy - fy, lx = wx - fx;
-              const float wb = mk * ly, wt = mk - wb;          // mask * (ly | 1 - ly)
-              const float w4f = wb * lx, w3f = wb - w4f, w2f = wt * lx, w1f = wt - w2f;
-              const uint32_t row00 = (uint32_t)(iy * WW + ix);
-              const uint32_t row10 = row00 + (uint32_t)WW;
-              const uint32_t gs = (uint32_t)j << 4, gofs = (uint32_t)par << 3;
-              const uint2 u1 = lds64(win_u32 + row00 * 128u + ((gs ^ (row00 << 4)) & 0x70u) + gofs);
-              const uint2 u2 = lds64(win_u32 + (row00 + 1u) * 128u + ((gs ^ ((row00 + 1u) << 4)) & 0x70u) + gofs);
-              const uint2 u3 = lds64(win_u32 + row10 * 128u + ((gs ^ (row10 << 4)) & 0x70u) + gofs);
-              const uint2 u4 = lds64(win_u32 + (row10 + 1u) * 128u + ((gs ^ ((row10 + 1u) << 4)) & 0x70u) + gofs);
-              // two packed conversions + four lane broadcasts (PRMT) instead of four conversions
-              const h2 w12 = H2<TH>::pack(w1f, w2f), w34 = H2<TH>::pack(w3f, w4f);
-              const h2 w1 = H2<TH>::lo(w12), w2 = H2<TH>::hi(w12), w3 = H2<TH>::lo(w34), w4 = H2<TH>::hi(w34);
-              h2 lo = H2<TH>::mul(w1, *reinterpret_cast<const h2*>(&u1.x));
-              h2 hi = H2<TH>::mul(w1, *reinterpret_cast<const h2*>(&u1.y));
-              lo = H2<TH>::fma(w2, *reinterpret_cast<const h2*>(&u2.x), lo);
-              hi = H2<TH>::fma(w2, *reinterpret_cast<const h2*>(&u2.y), hi);
-              lo = H2<TH>::fma(w3, *reinterpret_cast<const h2*>(&u3.x), lo);
-              hi = H2<TH>::fma(w3, *reinterpret_cast<const h2*>(&u3.y), hi);
-              lo = H2<TH>::fma(w4, *reinterpret_cast<const h2*>(&u4.x), lo);
-              hi = H2<TH>::fma(w4, *reinterpret_cast<const h2*>(&u4.y), hi);
-              pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-              pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-            } else {
-              slow |= 1u << j;          // outside the staged window: resolved below from global memory
-            }
-            sts64(a_row + (((uint32_t)j << 4) ^ rsw), pk);
-          }
-          // large offsets: bounds-checked global corners, fp32 blend (rare; kept out of the main loop so a
-          // single far sample does not serialise the warp through this path once per group)
-          while (slow) {
-            const int j = __ffs((int)slow) - 1;
-            slow &= slow - 1u;
-            const int g = 2 * j + par;
-            float dy, dx, mk;
-            if (p.om_blocked) {
-              const float* o = po + tap * p.om_tap_stride;
-              dy = __ldg(o + (j >> 1) * 64 + (j & 1));
-              dx = __ldg(o + (kQ + (j >> 1)) * 64 + (j & 1));
-              mk = __ldg(o + (2 * kQ + (j >> 1)) * 64 + (j & 1));
-            } else {
-              const float* o = po + tap * 3 * kG + g;
-              dy = __ldg(o); dx = __ldg(o + kG); mk = __ldg(o + 2 * kG);
-            }
-            const float py = (float)(y - p.d + kr * p.d) + dy;
-            const float px = (float)(x - p.d + kc * p.d) + dx;
-            uint2 pk2 = make_uint2(0u, 0u);
-            if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
-              const int iy0 = (int)floorf(py), ix0 = (int)floorf(px);
-              const float ly = py - (float)iy0, lx = px - (float)ix0, hy = 1.f - ly, hx = 1.f - lx;
-              const TH* xb = xg + (int64_t)b * p.H * p.W * p.x_pitch + g * 4;
-              const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-              const bool y0ok = iy0 >= 0, y1ok = iy0 + 1 <= p.H - 1, x0ok = ix0 >= 0, x1ok = ix0 + 1 <= p.W - 1;
-              const float4 v1 = (y0ok && x0ok) ? ld4h<TH>(xb + ((int64_t)iy0 * p.W + ix0) * p.x_pitch) : z;
-              const float4 v2 = (y0ok && x1ok) ? ld4h<TH>(xb + ((int64_t)iy0 * p.W + ix0 + 1) * p.x_pitch) : z;
-              const float4 v3 = (y1ok && x0ok) ? ld4h<TH>(xb + ((int64_t)(iy0 + 1) * p.W + ix0) * p.x_pitch) : z;
-              const float4 v4 = (y1ok && x1ok) ? ld4h<TH>(xb + ((int64_t)(iy0 + 1) * p.W + ix0 + 1) * p.x_pitch) : z;
-              const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-              pk2.x = f2_to_h2<TH>(mk * (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x),
-                                   mk * (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y));
-              pk2.y = f2_to_h2<TH>(mk * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z),
-                                   mk * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w));
-            }
-            sts64(a_row + (((uint32_t)j << 4) ^ rsw), pk2);
-          }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_full(stage));   // one arrival per warp
-        if (tap + kGatherSets < 9 && valid) load_unit(tap + kGatherSets);   // in flight while the MMA drains this stage
+      for (int kr = 0; kr < 3; ++kr, my += fd) {
+        load_ahead(cur, nxt, kr * 3 + 0, o2);
+        do_tap(cur, o0, kr, my, mx0, 0, git);
+        load_ahead(cur, nxt, kr * 3 + 1, o0);
+        do_tap(cur, o1, kr, my, mx1, 1, git);
+        load_ahead(cur, nxt, kr * 3 + 2, o1);
+        do_tap(cur, o2, kr, my, mx2, 2, git);
+        if (threadIdx.x == 0) dtrace(p.trace, git, 2 + kr);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(win_free);   // this warp no longer reads the window of this tile
@@ -323,104 +379,24 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           int nb, ny0, nx0;
           tile_origin(next, nb, ny0, nx0);
           mbar_arrive_expect_tx(win_full, p.win_bytes);
-          tma_tiled_4d(smem_u32(s_win), &tmX, win_full, 0, nx0 - p.R, ny0 - p.R, nb);
+          tma_tiled_4d(win_u32, &tmX, win_full, 0, nx0 - p.R, ny0 - p.R, nb);
         }
         __syncwarp();
       }
-    }
-  } else if (warp == kGatherWarps) {
-    // ===================== TMA + MMA issuer (warp-uniform control flow, elected lane issues) =====
-    const bool leader = elect_one();
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t idesc = (1u << 4) | (p.ab_format << 7) | (p.ab_format << 10) | ((uint32_t)(p.BN >> 3) << 17) |
-                           ((uint32_t)(128 >> 4) << 24);
-    // pull a tile's offsets|masks (16 row segments of 8 pixels x 27G floats, the dominant HBM stream) into
-    // L2 one tile ahead, so the gather warps' dependent loads see L2 rather than HBM latency
-    auto prefetch_om = [&](int b, int y0, int x0) {
-      if (p.om_blocked) {
-        // 9 taps x (8 blocks x 3G/4 x 256 B) contiguous per tile
-        const int tile_id = (b * p.tiles_y + y0 / kTH) * p.tiles_x + x0 / kTW;
-        const uint32_t bytes = (uint32_t)(4 * 3 * (p.G / 4) * 512);
-        if (lane < 9) {
-          const float* ptr = p.om + (int64_t)lane * p.om_tap_stride + (int64_t)tile_id * (bytes / 4);
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
-        }
-        return;
-      }
-      const int row = lane >> 1, half = lane & 1;          // 32 lanes: 16 rows x 2 halves of the 8-pixel segment
-      const int y = y0 + row, x = x0 + half * 4;
-      if (y < p.H && x < p.W) {
-        const int npx = (p.W - x < 4) ? (p.W - x) : 4;
-        const float* ptr = p.om + ((int64_t)(b * p.H + y) * p.W + x) * p.om_pitch;
-        const uint32_t bytes = (uint32_t)(npx * p.om_pitch * 4) & ~15u;
-        if (bytes >= 16 && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0))
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
-      }
-    };
-    if (leader) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
-      mbar_arrive_expect_tx(w_full, 9u * p.w_tile_bytes);
-      for (int t = 0; t < 9; ++t) tma_tiled_2d(smem_u32(s_w + t * p.w_tile_bytes), &tmW, w_full, t * 64, 0);
-    }
-    {
-      int b, y0, x0;
-      if ((int)blockIdx.x < p.total_tiles) {
-        tile_origin(blockIdx.x, b, y0, x0);
-        if (leader) {
-          mbar_arrive_expect_tx(win_full, p.win_bytes);
-          tma_tiled_4d(smem_u32(s_win), &tmX, win_full, 0, x0 - p.R, y0 - p.R, b);
-        }
-        prefetch_om(b, y0, x0);
-      }
-      if ((int)(blockIdx.x + gridDim.x) < p.total_tiles) {
-        tile_origin(blockIdx.x + gridDim.x, b, y0, x0);
-        prefetch_om(b, y0, x0);
-      }
-    }
-    mbar_wait(w_full, 0);
-    tc_fence_after();
-    const uint32_t w_lo0 = sw128_desc_lo(smem_u32(s_w));
-    const uint32_t w_step = p.w_tile_bytes >> 4;
-    int stage = 0;
-    uint32_t aph = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(tempty(acc), acc_phase ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_u + (uint32_t)(acc * p.BN);
-      uint32_t w_lo = w_lo0;
-      for (int tap = 0; tap < 9; ++tap, w_lo += w_step) {
-        mbar_wait(a_full(stage), aph);
-        tc_fence_after();
-        const uint32_t a_lo = sw128_desc_lo(smem_u32(s_a + stage * kATile));
-        umma_ksteps_n(p.nk, leader, d_tmem, a_lo, w_lo, idesc, tap != 0);
-        if (leader) umma_commit(a_empty(stage));
-        if (++stage == kAStages) { stage = 0; aph ^= 1u; }
-      }
-      if (leader) umma_commit(tfull(acc));
-      // pull the offsets|masks of the tile after next towards L2 (the window refill is issued by gather warp 0)
-      const int next = tile + 2 * gridDim.x;
-      if (next < p.total_tiles) {
-        int b, y0, x0;
-        tile_origin(next, b, y0, x0);
-        prefetch_om(b, y0, x0);
-      }
+      cur = nxt;
+      nxt = tile_ref(tile + 2 * gridDim.x);
     }
   } else {
-    // ===================== epilogue warps =====================
+    // ===================== epilogue warps (the first one is also the TMA + MMA issuer) =====================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     EpiArgs ea;
-    ea.s_scale = smem_u32(s_scale); ea.s_shift = smem_u32(s_shift); ea.res = nullptr; ea.y = p.out;
+    ea.s_scale = bar0 + 8u * (10 + 2 * kAStages); ea.s_shift = ea.s_scale + (uint32_t)p.BN * 4u; ea.res = nullptr; ea.y = p.out;
     ea.Cout = p.Cout; ea.BN = p.BN; ea.ch_base = 0; ea.out_pitch = p.out_pitch; ea.res_pitch = 0;
     ea.out_f32 = p.out_f32; ea.relu = 0; ea.vec_ok = p.vec_ok; ea.up = 1; ea.Wout = p.W;
     ea.spitch = 128 + 16;
-    const uint32_t stage = smem_u32(stage_base) + (uint32_t)((warp - kGatherWarps - 1) * 32 * ea.spitch);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    const uint32_t epi_stage = stage_u32 + (uint32_t)((warp - kGatherWarps) * 32 * ea.spitch);
+    auto epi_tile = [&](int tile, int it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       int b, y0, x0;
@@ -431,10 +407,98 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       mbar_wait(tfull(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(quarter * 32) << 16);
-      epilogue_rows<TH>(ea, t_addr, 0, p.BN, valid, pix, stage, lane);
+      epilogue_rows<TH>(ea, t_addr, 0, p.BN, valid, pix, epi_stage, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(acc));
+    };
+    if (warp == kGatherWarps) {
+      // ---- TMA + MMA issuer (warp-uniform control flow, elected lane issues), then its quarter of the epilogue ----
+      const bool leader = elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t idesc = (1u << 4) | (p.ab_format << 7) | (p.ab_format << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      // pull a tile's offsets|masks (16 row segments of 8 pixels x 27G floats, the dominant HBM stream) into
+      // L2 one tile ahead, so the gather warps' dependent loads see L2 rather than HBM latency
+      auto prefetch_om = [&](int b, int y0, int x0) {
+        if (p.om_blocked) {
+          // 9 taps x (128 pixels x 3G floats) contiguous per tile
+          const int tile_id = (b * p.tiles_y + y0 / kTH) * p.tiles_x + x0 / kTW;
+          const uint32_t bytes = (uint32_t)(128 * 3 * p.G * 4);
+          if (lane < 9) {
+            const float* ptr = p.om + (int64_t)lane * p.om_tap_stride + (int64_t)tile_id * (bytes / 4);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+          }
+          return;
+        }
+        const int row = lane >> 1, half = lane & 1;          // 32 lanes: 16 rows x 2 halves of the 8-pixel segment
+        const int y = y0 + row, x = x0 + half * 4;
+        if (y < p.H && x < p.W) {
+          const int npx = (p.W - x < 4) ? (p.W - x) : 4;
+          const float* ptr = p.om + ((int64_t)(b * p.H + y) * p.W + x) * p.om_pitch;
+          const uint32_t bytes = (uint32_t)(npx * p.om_pitch * 4) & ~15u;
+          if (bytes >= 16 && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0))
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+        }
+      };
+      if (leader) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+        mbar_arrive_expect_tx(w_full, 9u * p.w_tile_bytes);
+        for (int t = 0; t < 9; ++t) tma_tiled_2d(w_u32 + t * p.w_tile_bytes, &tmW, w_full, t * 64, 0);
+      }
+      {
+        int b, y0, x0;
+        if ((int)blockIdx.x < p.total_tiles) {
+          tile_origin(blockIdx.x, b, y0, x0);
+          if (leader) {
+            mbar_arrive_expect_tx(win_full, p.win_bytes);
+            tma_tiled_4d(win_u32, &tmX, win_full, 0, x0 - p.R, y0 - p.R, b);
+          }
+          prefetch_om(b, y0, x0);
+        }
+        if ((int)(blockIdx.x + gridDim.x) < p.total_tiles) {
+          tile_origin(blockIdx.x + gridDim.x, b, y0, x0);
+          prefetch_om(b, y0, x0);
+        }
+      }
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      const uint32_t w_lo0 = sw128_desc_lo(w_u32);
+      const uint32_t w_step = p.w_tile_bytes >> 4;
+      int stage = 0;
+      uint32_t aph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_u + (uint32_t)(acc * p.BN);
+        uint32_t w_lo = w_lo0;
+        for (int tap = 0; tap < 9; ++tap, w_lo += w_step) {
+          mbar_wait(a_full(stage), aph);
+          tc_fence_after();
+          const uint32_t a_lo = sw128_desc_lo(a_u32 + stage * kATile);
+          umma_ksteps_n(p.nk, leader, d_tmem, a_lo, w_lo, idesc, tap != 0);
+          if (leader) umma_commit(a_empty(stage));
+          if (++stage == kAStages) { stage = 0; aph ^= 1u; }
+        }
+        if (leader) umma_commit(tfull(acc));
+        // pull the offsets|masks of the tile after next towards L2 (the window refill is issued by gather warp 0)
+        const int next = tile + 2 * gridDim.x;
+        if (next < p.total_tiles) {
+          int b, y0, x0;
+          tile_origin(next, b, y0, x0);
+          prefetch_om(b, y0, x0);
+        }
+        // this warp's quarter of the tile's epilogue: by the time it is drained the gather warps are at most three taps
+        // (the A stages) into the next tile
+        epi_tile(tile, it);
+      }
+    } else {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) epi_tile(tile, it);
     }
   }
 
@@ -451,7 +515,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 // shared-memory footprint for a window radius R; the launcher takes the largest R <= dil + 5 that fits
 static size_t dcn_tc_smem(const fami_dcn_desc* d, int R) {
   const int BN = ((d->Cout + 15) / 16) * 16;
-  const size_t win = (size_t)(kTH + 2 * R) * (kTW + 2 * R) * 128;
+  const size_t win = ((size_t)(kTH + 2 * R) * (kTW + 2 * R) * 128 + 1023) & ~(size_t)1023;
   return win + kAStages * kATile + 9 * (size_t)BN * 128 + 1024 + 256 + (size_t)BN * 8 +
          (size_t)kDcnEpiWarps * 32 * (128 + 16);
 }
@@ -495,7 +559,7 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
   p.ab_format = d->dtype == FAMI_F16 ? 0u : 1u;
   p.om = om; p.x = x; p.bias = bias; p.out = out;
   p.om_blocked = d->om_layout == 2;
-  p.om_tap_stride = (int64_t)p.total_tiles * 4 * (3 * (d->G / 4)) * 128;
+  p.om_tap_stride = (int64_t)p.total_tiles * 128 * 3 * d->G;
   static const bool trace_on = getenv("FAMI_DCN_TRACE") != nullptr;
   p.trace = trace_on ? atoi(getenv("FAMI_DCN_TRACE")) : 0;
 
@@ -509,8 +573,9 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
                              (cuuint64_t)d->H * d->W * d->x_pitch * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)p.WW, (cuuint32_t)p.WH, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
+    // unswizzled: pixel pitch 128 B, group g of every pixel in bank pair g
     CUresult r = g_encode_tiled(&tmX, tm_dtype, 4, const_cast<void*>(x), dims, strides, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FAMI_CHECK_ARG(r == CUDA_SUCCESS, "dcn_tc: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
   }
@@ -532,11 +597,8 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
   if (grid > sms) grid = sms;
 #define FAMI_DCN_LAUNCH(TH_, G_)                                                                              \
   {                                                                                                            \
-    static bool attr_done = false;                                                                             \
-    if (!attr_done) {                                                                                          \
-      cudaFuncSetAttribute(dcn_tc_kernel<TH_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   \
-      attr_done = true;                                                                                        \
-    }                                                                                                          \
+    static std::atomic<uint64_t> attr_mask{0};                                                                 \
+    set_max_smem_once(attr_mask, dcn_tc_kernel<TH_, G_>, 227 * 1024);                                          \
     dcn_tc_kernel<TH_, G_><<<grid, kDcnThreads, smem, st>>>(tmX, tmW, p);                                      \
   }
 #define FAMI_DCN_LAUNCH_G(TH_)                                                  \

@@ -143,20 +143,25 @@ __global__ void __launch_bounds__(1024) bn_stats_kernel(const T* __restrict__ x,
   const int tid = threadIdx.x, c = tid % C, rg = tid / C;
   int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  // shifted sums (shift k = the channel's value in row 0, the same in every block): the float partial sums of (v - k) and
+  // (v - k)^2 stay well conditioned when |mean| >> std (post-ReLU features, large conv biases); they are converted back
+  // to sum / sum-of-squares of v in double per block
   float s = 0.f, q = 0.f;
+  const float k = rg < RG ? to_f<T>(x[c]) : 0.f;
   if (rg < RG)
     for (int64_t r = r0 + rg; r < r1; r += RG) {
-      float v = to_f<T>(x[r * pitch + c]);
+      float v = to_f<T>(x[r * pitch + c]) - k;
       s += v;
       q = fmaf(v, v, q);
     }
   if (rg < RG) { sm[rg * C + c] = s; sm[(RG + rg) * C + c] = q; }
   __syncthreads();
-  if (tid < C) {
+  if (tid < C && r1 > r0) {
     double ds = 0, dq = 0;
     for (int r = 0; r < RG; ++r) { ds += sm[r * C + tid]; dq += sm[(RG + r) * C + tid]; }
-    atomicAdd(stats + tid, ds);
-    atomicAdd(stats + C + tid, dq);
+    const double kd = (double)k, n = (double)(r1 - r0);
+    atomicAdd(stats + tid, ds + n * kd);
+    atomicAdd(stats + C + tid, dq + 2.0 * kd * ds + n * kd * kd);
   }
 }
 
@@ -171,17 +176,22 @@ __global__ void __launch_bounds__(1024) bn_stats_vec4_kernel(const float* __rest
   int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), t = s, s2 = s, t2 = s;
   if (rg < RG) {
+    // shifted sums, see bn_stats_kernel
+    const float4 k = __ldg(reinterpret_cast<const float4*>(x) + q);
     int64_t r = r0 + rg;
     for (; r + RG < r1; r += 2 * RG) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * pitch) + q);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(x + (r + RG) * pitch) + q);
+      float4 a = __ldg(reinterpret_cast<const float4*>(x + r * pitch) + q);
+      float4 b = __ldg(reinterpret_cast<const float4*>(x + (r + RG) * pitch) + q);
+      a.x -= k.x; a.y -= k.y; a.z -= k.z; a.w -= k.w;
+      b.x -= k.x; b.y -= k.y; b.z -= k.z; b.w -= k.w;
       s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
       t.x = fmaf(a.x, a.x, t.x); t.y = fmaf(a.y, a.y, t.y); t.z = fmaf(a.z, a.z, t.z); t.w = fmaf(a.w, a.w, t.w);
       s2.x += b.x; s2.y += b.y; s2.z += b.z; s2.w += b.w;
       t2.x = fmaf(b.x, b.x, t2.x); t2.y = fmaf(b.y, b.y, t2.y); t2.z = fmaf(b.z, b.z, t2.z); t2.w = fmaf(b.w, b.w, t2.w);
     }
     if (r < r1) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * pitch) + q);
+      float4 a = __ldg(reinterpret_cast<const float4*>(x + r * pitch) + q);
+      a.x -= k.x; a.y -= k.y; a.z -= k.z; a.w -= k.w;
       s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
       t.x = fmaf(a.x, a.x, t.x); t.y = fmaf(a.y, a.y, t.y); t.z = fmaf(a.z, a.z, t.z); t.w = fmaf(a.w, a.w, t.w);
     }
@@ -191,11 +201,12 @@ __global__ void __launch_bounds__(1024) bn_stats_vec4_kernel(const float* __rest
     pq[0] = t.x + t2.x; pq[1] = t.y + t2.y; pq[2] = t.z + t2.z; pq[3] = t.w + t2.w;
   }
   __syncthreads();
-  if (tid < C) {
+  if (tid < C && r1 > r0) {
     double ds = 0, dq = 0;
     for (int r = 0; r < RG; ++r) { ds += sm[r * C + tid]; dq += sm[(RG + r) * C + tid]; }
-    atomicAdd(stats + tid, ds);
-    atomicAdd(stats + C + tid, dq);
+    const double kd = (double)__ldg(x + tid), n = (double)(r1 - r0);
+    atomicAdd(stats + tid, ds + n * kd);
+    atomicAdd(stats + C + tid, dq + 2.0 * kd * ds + n * kd * kd);
   }
 }
 

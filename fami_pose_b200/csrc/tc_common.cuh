@@ -29,16 +29,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+// suspend-time hint of mbarrier.try_wait: the waiting warp sleeps in hardware (woken by the completing arrival) instead of
+// re-issuing the poll every ~40 clk -- a CTA's spinning epilogue / issuer warps executed 30 % of all warp instructions of the
+// deformable kernel and competed with its gather warps for issue slots
+constexpr uint32_t kMbarSuspendHint = 0x989680u;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity)
+      "}\n" ::"r"(bar), "r"(parity), "r"(kMbarSuspendHint)
       : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -926,13 +930,13 @@ __device__ __forceinline__ void epilogue_rows_pipelined(const EpiArgs& a, uint32
   }
 }
 
-// Epilogue of the fused offset|mask producer convolution writing the warp-blocked layout the deformable kernel reads
-// (fami_dcn_desc.om_layout = 2): [tap][tile*8 + block][q < 3G/4][16 pixels][4 floats], tile = 16x8 pixels, block = 2 rows x
-// 8 columns (the 16 pixels one gather warp of the deformable kernel owns).  Channel n = tap*3G + 4q + e, so the four
-// channels of a float4 never straddle a tap or a (dy | dx | mask) run; they are stored in the order (e0, e2, e1, e3): the
-// deformable kernel's two lanes of a pixel (offset-group parity 0 / 1) each read ONE float2 = their two groups of the
-// quad, and a warp's load instruction reads 256 contiguous bytes.  The 8 lanes of an 8-pixel row segment store 128
-// contiguous bytes, straight from registers, no staging.
+// Epilogue of the fused offset|mask producer convolution writing the lane-blocked layout the deformable kernel reads
+// (fami_dcn_desc.om_layout = 2): [tap][tile][row 16][iteration NIT][dy | dx | mask][pixel PPW][group G] over 16x8-pixel
+// tiles, where a gather warp of the deformable kernel owns one tile row and its lanes are (pixel, group): LG = 16 lanes per
+// pixel for G > 8 (else G), PPW = 32 / LG pixels per warp iteration, NIT = 8 / PPW iterations per row.  Pixel x of a row is
+// (iteration, pixel) = (x / PPW, x % PPW); every load instruction of a gather warp reads PPW*G contiguous floats and the
+// warp's reads of a (row, tap) are one contiguous run of 24*G floats.  Channel n = tap*3G + k*G + g (k = dy, dx, mask), so
+// the four channels of a float4 never straddle a (tap, k) run; stored straight from registers, no staging.
 struct OmBlocked {
   float* base;
   int tiles_x, tiles_y, G3;     // DCN tiles per image, 3*G
@@ -941,9 +945,14 @@ struct OmBlocked {
 __device__ __forceinline__ void epilogue_rows_om_blocked(const EpiArgs& a, uint32_t t_addr, int col_begin, int col_end, bool valid,
                                                          int img, int y, int x, const OmBlocked& ob) {
   if (col_begin >= col_end) return;   // warp-uniform
-  const int r = ((y & 15) << 3) | (x & 7);
-  const int64_t blk = ((int64_t)(img * ob.tiles_y + (y >> 4)) * ob.tiles_x + (x >> 3)) * 8 + (r >> 4);
-  float* lane_base = ob.base + blk * (int64_t)(ob.G3 * 16) + (r & 15) * 4;     // (3G/4) * 64 floats per block
+  const int G = ob.G3 / 3;
+  const int LG = G > 8 ? 16 : G, PPW = 32 / LG, NIT = 8 / PPW;
+  const int ry = y & 15, rx = x & 7;
+  const int j = rx / PPW, pix = rx - j * PPW;
+  const int64_t tile = (int64_t)(img * ob.tiles_y + (y >> 4)) * ob.tiles_x + (x >> 3);
+  // + k * PPW*G + g per (dy | dx | mask) run
+  float* lane_base = ob.base + tile * (int64_t)(128 * ob.G3) + (int64_t)((ry * NIT + j) * 3) * (PPW * G) + pix * G;
+  const int kstride = PPW * G;
   for (int c0 = col_begin; c0 < col_end; c0 += 16) {
     const int ch0 = a.ch_base + c0;
     if (ch0 >= a.Cout) break;   // warp-uniform
@@ -951,19 +960,20 @@ __device__ __forceinline__ void epilogue_rows_om_blocked(const EpiArgs& a, uint3
     tmem_ld16(t_addr + (uint32_t)c0, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c4 = ch0 + 4 * j;
+    for (int q = 0; q < 4; ++q) {
+      const int c4 = ch0 + 4 * q;
       if (c4 < a.Cout) {          // warp-uniform
         const float4 sc = lds128f(a.s_scale + (uint32_t)c4 * 4u);
         const float4 sh = lds128f(a.s_shift + (uint32_t)c4 * 4u);
         const int tap = c4 / ob.G3, f = c4 - tap * ob.G3;
+        const int k = f / G, g0 = f - k * G;
         if (valid) {
-          float4 o;   // (e0, e2, e1, e3)
-          o.x = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
-          o.z = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
-          o.y = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
-          o.w = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
-          *reinterpret_cast<float4*>(lane_base + (int64_t)tap * ob.tap_stride + (f >> 2) * 64) = o;
+          float4 o;
+          o.x = fmaf(__uint_as_float(v[4 * q + 0]), sc.x, sh.x);
+          o.y = fmaf(__uint_as_float(v[4 * q + 1]), sc.y, sh.y);
+          o.z = fmaf(__uint_as_float(v[4 * q + 2]), sc.z, sh.z);
+          o.w = fmaf(__uint_as_float(v[4 * q + 3]), sc.w, sh.w);
+          *reinterpret_cast<float4*>(lane_base + (int64_t)tap * ob.tap_stride + k * kstride + g0) = o;
         }
       }
     }

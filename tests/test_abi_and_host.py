@@ -169,7 +169,7 @@ names = fp.patch_reference()
 import posetimation.backbones.hrnet as H
 A = importlib.import_module("posetimation.zoo.Alignment.Alignment_V15")   # the module, not the class
 assert H.BasicBlock is fp.BasicBlock and A.DeformConv2d is fp.DeformConv2d and A.HRNetPlus is fp.HRNetPlus
-assert "kornia.geometry.warp_affine" in names
+assert "posetimation.zoo.Alignment.Alignment_V15.kornia" in names and A.kornia.geometry.warp_affine is fp.kornia_shim.warp_affine
 # the engine's plug-in registries resolve the reference's own names to the fami classes (engine/core/base.py:65)
 from engine.defaults.constant import CORE_FUNCTION_REGISTRY, MODEL_REGISTRY
 from fami_pose_b200.train import AlignmentMIFunction_Term6_V1
@@ -212,7 +212,7 @@ def test_multistep_lr_matches_torch_scheduler():
 
 def test_offset_layout_host_logic():
     """tap_major_perm is a permutation mapping torchvision's [offset(18G) | mask(9G)] order to [tap][dy|dx|mask];
-    om_to_blocked is a bijection onto the warp-blocked buffer for tile-aligned maps (CPU tensors: pure indexing)."""
+    om_to_blocked is a bijection onto the lane-blocked buffer for tile-aligned maps (CPU tensors: pure indexing)."""
     import torch
     from fami_pose_b200 import ops
     G = 12
@@ -228,12 +228,13 @@ def test_offset_layout_host_logic():
     blk = ops.om_to_blocked(om, G)
     assert blk.numel() == ops.om_blocked_numel(B, H, W, G) == om.numel()
     assert torch.equal(torch.sort(blk).values, torch.sort(om.reshape(-1)).values)
-    # element (b=1, y=17, x=9, tap=3, channel-in-tap f=7): tile (1,1) of image 1, r = 1*8+1 = 9 -> block 0, pixel 9;
-    # f = 7 -> quad 1, element 3 -> stored at position 3 of the (0, 2, 1, 3) order
-    Q = 3 * G // 4
+    # element (b=1, y=17, x=9, tap=3, channel-in-tap f = G + 7 -> dx of group 7): tile (1,1) of image 1, row 1, x%8 = 1 ->
+    # G = 12: 16 lanes per pixel, 2 pixels per warp iteration, 4 iterations: (iteration, pixel) = (0, 1)
+    LG, PPW, NIT = ops.om_lane_map(G)
+    assert (LG, PPW, NIT) == (16, 2, 4) and ops.om_lane_map(8) == (8, 4, 2) and ops.om_lane_map(4) == (4, 8, 1)
     tiles = (H // 16) * (W // 8)
     tile = 1 * tiles + 1 * (W // 8) + 1
-    idx = ((((3 * (B * tiles) + tile) * 8 + 0) * Q + 7 // 4) * 16 + 9) * 4 + 3
-    assert float(blk[idx]) == float(om[1, 3 * 3 * G + 7, 17, 9])
-    # f = 5 (quad 1, element 1) sits at position 2 of its float4
-    assert float(blk[idx - 1]) == float(om[1, 3 * 3 * G + 5, 17, 9])
+    idx = (((((3 * (B * tiles) + tile) * 16 + 1) * NIT + 0) * 3 + 1) * PPW + 1) * G + 7
+    assert float(blk[idx]) == float(om[1, 3 * 3 * G + G + 7, 17, 9])
+    # the same pixel's mask of group 0 is one (dy | dx | mask) run further
+    assert float(blk[idx - 7 + PPW * G]) == float(om[1, 3 * 3 * G + 2 * G, 17, 9])

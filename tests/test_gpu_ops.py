@@ -130,6 +130,30 @@ def test_conv_bn_train_mode():
 
 
 
+@pytest.mark.parametrize("C,dtype", [(48, torch.float32), (17, torch.float32), (48, torch.float16)])
+def test_bn_stats_large_mean(C, dtype):
+    """per-channel sum / sum-of-squares with |mean| / std = 1e3 (post-ReLU-like features, large conv biases): the variance
+    recovered from the statistics must match a float64 computation to 1e-3 relative (E[x^2] - mean^2 from plain float
+    partial sums loses it entirely at this ratio)."""
+    m = fp()
+    from fami_pose_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    rows = 4 * 24 * 18
+    mean = 100.0 if dtype == torch.float16 else 1000.0       # fp16 storage: keep the ulp of the values below the std
+    std = 1.0
+    x = (torch.randn(rows, C, generator=g) * std + mean).to(dtype).to(DEV).contiguous()
+    st = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
+    m._lib.call("fami_bn_stats", ops._ptr(x), ops._code(dtype),
+                C, rows, C, ops._ptr(st), ops._stream())
+    torch.cuda.synchronize()
+    xd = x.double()
+    ref_mean, ref_var = xd.mean(0), xd.var(0, unbiased=False)
+    got_mean = st[:C] / rows
+    got_var = st[C:] / rows - got_mean * got_mean
+    assert float((got_mean - ref_mean).abs().max()) <= 1e-6 * mean
+    assert float(((got_var - ref_var) / ref_var).abs().max()) <= 1e-3
+
+
 def _golden_inputs(name):
     # same generator recipe as tests/golden/make_golden.py::dcn_inputs (kept in sync by test_oracle.py)
     from tests_support import dcn_cases, dcn_inputs
@@ -639,7 +663,7 @@ def test_warp_translate_bwd_vs_torch_autograd():
 
 @pytest.mark.parametrize("shape", [(2, 48, 12, 33, 21), (1, 32, 8, 16, 8), (3, 64, 16, 20, 30)])
 def test_offset_conv_blocked_layout_and_dcn(shape):
-    """The fused offset|mask producer writing the warp-blocked layout (fami_conv_desc.om_groups) equals the same conv
+    """The fused offset|mask producer writing the lane-blocked layout (fami_conv_desc.om_groups) equals the same conv
     written as an NHWC activation and converted on the host (ops.om_to_blocked), bit for bit -- incl. maps that are not a
     multiple of the 16x8 DCN tile -- and the deformable kernel gives identical outputs from both layouts."""
     m = fp()
@@ -657,12 +681,7 @@ def test_offset_conv_blocked_layout_and_dcn(shape):
             blk = ops.conv_offsets_blocked(x, conv, G)
             ref = ops.om_to_blocked(nhwc, G)
             # slots of pixels outside the image are never written by the producer nor read by the consumer
-            Q = 3 * G // 4
-            ty, tx = (H + 15) // 16, (W + 7) // 8
-            inside = torch.zeros((B, ty * 16, tx * 8), dtype=torch.bool, device=DEV)
-            inside[:, :H, :W] = True
-            msk = inside.reshape(B, ty, 16, tx, 8).permute(0, 1, 3, 2, 4).reshape(B, ty, tx, 8, 1, 16, 1)
-            msk = msk.expand(9, B, ty, tx, 8, Q, 16, 4).reshape(-1)
+            msk = ops.om_to_blocked(torch.ones_like(nhwc), G) > 0       # the converter zero-fills the slots outside the image
             assert torch.equal(blk[msk], ref[msk])
             dcn = m.DeformConv2d(C, C, 3, padding=3, dilation=3).to(DEV)
             o1 = dcn(x, None, None, fused_om=nhwc)

@@ -1,5 +1,5 @@
 """Per-call device timing of one training step (CUDA events around every C-ABI call), aggregated by entry point.
-usage: python tools/profile_train.py [batch] [backbone_precision|none]"""
+usage: python tools/profile_train.py [batch] [backbone_precision|none] [head_precision]   (bench.py's train record: 32 tf32 tf32)"""
 import collections, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,12 +8,13 @@ from fami_pose_b200 import _lib, ops, autograd as ag, train as tr
 from oracle import fami_oracle as fo, ref_harness as rh
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-bp = sys.argv[2] if len(sys.argv) > 2 else "fp16"
-fp.set_precision("fp32")
+bp = sys.argv[2] if len(sys.argv) > 2 else "tf32"
+head = sys.argv[3] if len(sys.argv) > 3 else "tf32"
+fp.set_precision(head)
 m = fp.Alignment_V15(rh.make_cfg(48, 17), "train")
 m.load_state_dict(fo.seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 19970808))
 m = m.cuda().train()
-if bp != "none":
+if bp != "none" and bp != head:
     m.backbone_precision = bp
 kf, sup, tgt, tw = (t.cuda() for t in fo.synthetic_clip(B, seed=1))
 step = tr.TrainStep(m)

@@ -12,15 +12,16 @@ B, C, G, H, W = 32, 48, 12, 96, 72
 XP = int(os.environ.get("XPITCH", C))
 x = ops.empty_nhwc(B, XP, H, W, torch.float16, "cuda").normal_()[:, :C]
 om = ops.empty_nhwc(B, 27 * G, H, W, torch.float32, "cuda").normal_() * float(os.environ.get("SIGMA", "2"))
+blk = ops.om_to_blocked(om, G)
 dcn = fp.DeformConv2d(C, C, 3, padding=3, dilation=3).cuda()
 out = ops.empty_nhwc(B, C, H, W, torch.float16, "cuda")
 for _ in range(3):
-    dcn(x, None, None, out=out, fused_om=om)
+    dcn(x, None, None, out=out, blocked_om=blk, groups=G)
 buf = np.zeros(4096, dtype=np.uint64)
 _lib.call("fami_debug_read_trace", buf.ctypes.data_as(ctypes.c_void_p), -4096)
 t = buf[:256].reshape(16, 16).astype(np.int64)
 t0 = t[0, 0]
-print("tile | start win_ok | per unit k of group 0: a_empty ok, blend done, arrived (us after win_ok)")
-for i in range(8):
+print("tile | start   window ready | kernel row 0 / 1 / 2 gathered (us after window ready)   [CTA 0, gather warp 0]")
+for i in range(10):
     print("%3d | %7.2f %7.2f | %s" % (i, (t[i, 0] - t0) / 1e3, (t[i, 1] - t0) / 1e3,
-          "  ".join("%5.2f %5.2f %5.2f" % ((t[i, 5 + k] - t[i, 1]) / 1e3, (t[i, 8 + k] - t[i, 1]) / 1e3, (t[i, 2 + k] - t[i, 1]) / 1e3) for k in range(3))))
+          "  ".join("%5.2f" % ((t[i, 2 + k] - t[i, 1]) / 1e3) for k in range(3))))
