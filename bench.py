@@ -517,7 +517,7 @@ def dcn_roofline(fp, ops, dev, stream, B, pk):
     msk = torch.randn(B, 9 * G, H, W, generator=g).to(dev)
     dcn = fp.DeformConv2d(C, C, 3, padding=3, dilation=3).to(dev)
     out = ops.empty_nhwc(B, C, H, W, dt, dev)
-    if half:   # fused [offset|mask] buffer in the lane-blocked layout, as the alignment head's producer conv writes it
+    if half:   # fused [offset|mask] buffer in the row-blocked layout, as the alignment head's producer conv writes it
         om = ops.to_nhwc(torch.cat([off, msk], 1)[:, ops.tap_major_perm(G)].contiguous(), torch.float32)
         blk = ops.om_to_blocked(om, G)
         del om

@@ -55,7 +55,7 @@ struct HaloParams {
   int sA, sB, b_resident, acc_bufs, n_iss, acc_stride;
   uint32_t a_stage_bytes, b_tile_bytes, a_box_bytes;
   int trace;
-  int om_groups, om_tiles_x, om_tiles_y;   // > 0: y is the lane-blocked DCN offset|mask buffer
+  int om_groups, om_tiles_x, om_tiles_y;   // > 0: y is the row-blocked DCN offset|mask buffer
   int64_t om_tap_stride;
   const float* scale;
   const float* shift;

@@ -32,7 +32,7 @@ struct TcParams {
   int out_pitch, res_pitch;
   int out_f32, vec_ok;
   int stages, pipe;   // pipe: pipelined residual epilogue (epilogue_rows_pipelined)
-  int om_groups, om_tiles_x, om_tiles_y;   // > 0: y is the lane-blocked DCN offset|mask buffer (fami_conv_desc.om_groups)
+  int om_groups, om_tiles_x, om_tiles_y;   // > 0: y is the row-blocked DCN offset|mask buffer (fami_conv_desc.om_groups)
   int64_t om_tap_stride;
   const float* scale;
   const float* shift;

@@ -7,10 +7,11 @@
 //     zero-filled, which is exactly torchvision's "corner outside the image contributes 0" rule);
 //   * 16 gather warps, warp w = image row w of the tile.  A LANE is (pixel, offset group): the 4-channel
 //     (8-byte) corner of group g sits at byte 8g of its pixel's 128-byte row, i.e. in bank pair g WHATEVER the
-//     sampling position is -- the lanes of a half-warp (one pixel's groups) can never conflict, for any offsets
-//     (the one-lane-per-pixel mappings before were 2.9x over the ideal wavefront count at sigma = 2 px).  Per
-//     (pixel, tap) a lane reads its (dy, dx, mask) -- streamed from HBM exactly once, in the lane-blocked layout
-//     the fused offset|mask convolution writes, pulled into L2 two tiles ahead by bulk prefetches and into
+//     sampling position is -- lanes with different groups can never conflict, for any offsets (the
+//     one-lane-per-pixel mappings before were 2.9x over the ideal wavefront count at sigma = 2 px).  The 8*G
+//     samples of a (row, tap) are walked 32 at a time (LaneMap).  Per sample a lane reads its (dy, dx, mask)
+//     -- streamed from HBM exactly once, in the row-blocked layout the fused offset|mask convolution writes
+//     (128 contiguous bytes per load instruction), pulled into L2 two tiles ahead by bulk prefetches and into
 //     registers two taps ahead --, forms the four bilinear corners from shared memory, blends them in packed
 //     16-bit arithmetic and stores the modulated 4 channels into the tap's A tile (128B-swizzled K-major).
 //     Samples outside the staged window are resolved per tap through a bounds-checked global path;
@@ -48,12 +49,13 @@ constexpr int kATile = 128 * 128;          // bytes per A stage
 constexpr uint32_t kMagicBits = 0x4B400000u;   // 1.5 * 2^23: adding it with round-down leaves floor(v) in the low mantissa bits
 constexpr float kMagic = 12582912.f;
 
-// lane <-> (pixel, offset group) map of a gather warp: LG lanes per pixel (G rounded up to a power of two), PPW pixels
-// per warp iteration, NIT iterations per (tile row, tap).  G = 12 leaves lanes 12..15 of each half-warp idle.
+// lane <-> (pixel, offset group) map of a gather warp: the 8*G samples of a (tile row, tap) are numbered s = pixel*G + g and
+// taken 32 at a time, lane = s % 32: NIT = G/4 iterations, every lane busy in every iteration.  For G = 4, 8, 16 a half-warp
+// holds whole pixels (all its groups distinct: one wavefront per 8-byte corner load); for G = 12 sixteen consecutive samples
+// wrap around the groups once, so four lanes share a bank pair with four others (two wavefronts) -- cheaper than leaving a
+// quarter of the lanes idle in every instruction of the sample loop.
 template <int kG> struct LaneMap {
-  static constexpr int LG = kG > 8 ? 16 : kG;
-  static constexpr int PPW = 32 / LG;
-  static constexpr int NIT = kTW / PPW;
+  static constexpr int NIT = kG / 4;
 };
 
 struct DcnTcParams {
@@ -62,7 +64,7 @@ struct DcnTcParams {
   int tiles_x, tiles_y, total_tiles;
   int nk, BN;
   int om_pitch, x_pitch, out_pitch, vec_ok, out_f32;
-  int om_blocked;                   // 1: offsets|masks in the lane-blocked layout (om_layout 2)
+  int om_blocked;                   // 1: offsets|masks in the row-blocked layout (om_layout 2)
   int64_t om_tap_stride;            // floats between taps in the blocked layout = tiles * 128 * 3G
   uint32_t win_bytes, w_tile_bytes, ab_format;
   int trace;
@@ -171,27 +173,33 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 
   if (warp < kGatherWarps) {
     // ===================== gather warps =====================
-    typedef LaneMap<kG> LM;
-    constexpr int LG = LM::LG, PPW = LM::PPW, NIT = LM::NIT;
+    constexpr int NIT = LaneMap<kG>::NIT;
     typedef typename H2<TH>::t h2;
     typedef OmRegs<NIT> Om;
     const TH* xg = reinterpret_cast<const TH*>(p.x);
     const int ry = warp;                                   // image row of the tile
-    const int pix = lane / LG, g = lane - pix * LG;
-    const bool lane_on = g < kG;
     const uint32_t rowpitch = (uint32_t)p.WW * 128u;
     const uint32_t ylim = (uint32_t)(p.WH - 1), xlim = (uint32_t)(p.WW - 1);
-    // window address of the sample = iy_bits * rowpitch + ix_bits * 128 + kaddr (+ iteration * PPW * 128), the bit patterns
-    // of the magic-number floors used directly (32-bit wrap-around arithmetic)
-    const uint32_t kaddr = win_u32 + (uint32_t)g * 8u - kMagicBits * rowpitch - kMagicBits * 128u;
     const uint32_t win_safe = win_u32;
-    // A-tile byte address of (row r = ry*8 + j*PPW + pix, group g), 128B-swizzled K-major: chunk (g>>1) ^ (r&7).  pix and
-    // j*PPW occupy disjoint bits of r&7, so iteration j is the iteration-0 address with bits 4..6 XORed by j*PPW, plus j*PPW rows.
-    const uint32_t aoff0 = a_u32 + (uint32_t)((ry * kTW + pix) * 128) + ((uint32_t)(((g >> 1) ^ pix) << 4) | ((uint32_t)(g & 1) << 3));
-    auto a_addr = [&](int j, int kc) { return (aoff0 ^ (uint32_t)(j * PPW * 16)) + (uint32_t)(j * PPW * 128 + kc * kATile); };
+    // per iteration j of this lane: sample s = 32 j + lane = pixel * G + g.
+    //   kaddr[j]: window address of the sample = iy_bits * rowpitch + ix_bits * 128 + kaddr[j], the bit patterns of the
+    //             magic-number floors used directly (32-bit wrap-around arithmetic; ix is relative to pixel 0 of the row)
+    //   xbias[j]: ix_bits - xbias[j] = window column of the sample (bounds test)
+    //   a_st[j] : A-tile byte address of (row r = ry*8 + pixel, group g), 128B-swizzled K-major: chunk (g>>1) ^ (r&7)
+    uint32_t kaddr[NIT], xbias[NIT], a_st[NIT];
+    int pixj[NIT], gj[NIT];
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {
+      const int sidx = 32 * j + lane;
+      pixj[j] = sidx / kG;
+      gj[j] = sidx - pixj[j] * kG;
+      kaddr[j] = win_u32 + (uint32_t)(gj[j] * 8 + pixj[j] * 128) - kMagicBits * rowpitch - kMagicBits * 128u;
+      xbias[j] = kMagicBits - (uint32_t)pixj[j];
+      a_st[j] = a_u32 + (uint32_t)((ry * kTW + pixj[j]) * 128) + ((uint32_t)(((gj[j] >> 1) ^ pixj[j]) << 4) | ((uint32_t)(gj[j] & 1) << 3));
+    }
     const float fd = (float)p.d;
     const float my0 = kMagic + (float)(ry + p.R - p.d);     // + kr * d per kernel row
-    const float mx0 = kMagic + (float)(pix + p.R - p.d);    // + kc * d per kernel column
+    const float mx0 = kMagic + (float)(p.R - p.d);          // + kc * d per kernel column (pixel 0 of the row)
     const float mx1 = mx0 + fd, mx2 = mx1 + fd;
 
     // per-tile state of this lane: pointer to its (dy) float of tap 0 / iteration 0, and the valid-iteration mask
@@ -205,12 +213,12 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       const int y = y0 + ry;
 #pragma unroll
       for (int j = 0; j < NIT; ++j)
-        if (lane_on && y < p.H && x0 + j * PPW + pix < p.W) t.vmask |= 1u << j;
+        if (y < p.H && x0 + pixj[j] < p.W) t.vmask |= 1u << j;
       if (p.om_blocked) {
-        // [tap][tile][row 16][iteration NIT][dy | dx | mask][pixel PPW][group G]
-        t.po = p.om + (int64_t)tile * (128 * 3 * kG) + ry * (NIT * 3 * PPW * kG) + pix * kG + g;
+        // [tap][tile][row 16][dy | dx | mask][pixel 8][group G]: sample s of iteration j at float 32 j + lane of its run
+        t.po = p.om + (int64_t)tile * (128 * 3 * kG) + ry * (3 * 8 * kG) + lane;
       } else {
-        t.po = p.om + ((int64_t)(b * p.H + (y < p.H ? y : 0)) * p.W + x0 + pix) * p.om_pitch + g;
+        t.po = p.om + ((int64_t)(b * p.H + (y < p.H ? y : 0)) * p.W + x0) * p.om_pitch;
       }
       return t;
     };
@@ -220,16 +228,16 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < NIT; ++j) {
           const bool v = (t.vmask >> j) & 1u;
-          o.dy[j] = v ? ldg_stream(q + (j * 3 + 0) * (PPW * kG)) : 0.f;
-          o.dx[j] = v ? ldg_stream(q + (j * 3 + 1) * (PPW * kG)) : 0.f;
-          o.mk[j] = v ? ldg_stream(q + (j * 3 + 2) * (PPW * kG)) : 0.f;
+          o.dy[j] = v ? ldg_stream(q + 32 * j) : 0.f;
+          o.dx[j] = v ? ldg_stream(q + 8 * kG + 32 * j) : 0.f;
+          o.mk[j] = v ? ldg_stream(q + 16 * kG + 32 * j) : 0.f;
         }
       } else {
         const float* q = t.po + tap * 3 * kG;
 #pragma unroll
         for (int j = 0; j < NIT; ++j) {
           const bool v = (t.vmask >> j) & 1u;
-          const float* qj = q + (int64_t)(j * PPW) * p.om_pitch;
+          const float* qj = q + (int64_t)pixj[j] * p.om_pitch + gj[j];
           o.dy[j] = v ? __ldg(qj) : 0.f;
           o.dx[j] = v ? __ldg(qj + kG) : 0.f;
           o.mk[j] = v ? __ldg(qj + 2 * kG) : 0.f;
@@ -245,9 +253,10 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     // one tap of one tile: NIT samples of this lane into A stage kc
     auto do_tap = [&](const TileRef& t, const Om& o, int kr, float my, float mx, int kc, int git) {
       const uint32_t u = (uint32_t)(git * 3 + kr);            // use index of stage kc
-      mbar_wait(a_empty(kc), (u & 1u) ^ 1u);
       bool far = false;                          // any sample of this lane outside the staged window
-      constexpr int NB = NIT < 2 ? NIT : 2;      // samples per batch (8 corner loads in flight per lane)
+      constexpr int NB = (NIT % 2) ? NIT : 2;    // samples per batch (8 or 12 corner loads in flight per lane); NB divides NIT
+      static_assert(NIT % NB == 0, "batch size must divide the iteration count");
+      uint2 pk[NIT];
 #pragma unroll
       for (int j0 = 0; j0 < NIT; j0 += NB) {
         uint32_t a00[NB], a10[NB];
@@ -260,24 +269,24 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           const float ty = __fadd_rd(dy, my), tx = __fadd_rd(dx, mx);
           const float ly = dy - (ty - my), lx = dx - (tx - mx);
           const uint32_t iyb = __float_as_uint(ty), ixb = __float_as_uint(tx);
-          const bool in = (iyb - kMagicBits) < ylim && (ixb - (kMagicBits - (uint32_t)(j * PPW))) < xlim;
+          const bool in = (iyb - kMagicBits) < ylim && (ixb - xbias[j]) < xlim;
           const float wb = mk * ly, wt = mk - wb;          // mask * (ly | 1 - ly)
           const float w4f = wb * lx, w3f = wb - w4f, w2f = wt * lx, w1f = wt - w2f;
           w12[jb] = H2<TH>::pack(w1f, w2f);
           w34[jb] = H2<TH>::pack(w3f, w4f);
-          const uint32_t a = iyb * rowpitch + (ixb * 128u + kaddr);
+          const uint32_t a = iyb * rowpitch + (ixb * 128u + kaddr[j]);
           a00[jb] = in ? a : win_safe;                      // outside the staged window: harmless address, fixed up below
           a10[jb] = a00[jb] + rowpitch;
-          far |= !in;      // (idle lanes and pixels outside the image carry zero offsets: always inside)
+          far |= !in;      // (pixels outside the image carry zero offsets: always inside)
         }
         uint2 u1[NB], u2[NB], u3[NB], u4[NB];
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) {
           const int j = j0 + jb;
-          u1[jb] = lds64(a00[jb] + (uint32_t)(j * PPW * 128));
-          u2[jb] = lds64(a00[jb] + (uint32_t)(j * PPW * 128 + 128));
-          u3[jb] = lds64(a10[jb] + (uint32_t)(j * PPW * 128));
-          u4[jb] = lds64(a10[jb] + (uint32_t)(j * PPW * 128 + 128));
+          u1[jb] = lds64(a00[jb]);
+          u2[jb] = lds64(a00[jb] + 128u);
+          u3[jb] = lds64(a10[jb]);
+          u4[jb] = lds64(a10[jb] + 128u);
         }
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) {
@@ -291,13 +300,15 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           hi = H2<TH>::fma(w3, *reinterpret_cast<const h2*>(&u3[jb].y), hi);
           lo = H2<TH>::fma(w4, *reinterpret_cast<const h2*>(&u4[jb].x), lo);
           hi = H2<TH>::fma(w4, *reinterpret_cast<const h2*>(&u4[jb].y), hi);
-          uint2 pk;
-          pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-          pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-          // (a pixel outside the image carries mask 0: all four weights are 0 and the column is 0; idle lanes never store)
-          if (lane_on) sts64(a_addr(j, kc), pk);
+          // (a pixel outside the image carries mask 0: all four weights are 0 and the column is 0)
+          pk[j].x = *reinterpret_cast<const uint32_t*>(&lo);
+          pk[j].y = *reinterpret_cast<const uint32_t*>(&hi);
         }
       }
+      // the A stage is needed only now: the wait for the MMA that last read it hides behind the loads and blends above
+      mbar_wait(a_empty(kc), (u & 1u) ^ 1u);
+#pragma unroll
+      for (int j = 0; j < NIT; ++j) sts64(a_st[j] + (uint32_t)(kc * kATile), pk[j]);
       // large offsets: bounds-checked global corners, fp32 blend.  Kept out of the sample loop and entered once per tap
       // by the whole warp, so the dependent global loads of all far samples of the tap are in flight together.
       if (__any_sync(0xffffffffu, far)) {
@@ -305,18 +316,20 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < NIT; ++j) {
           const uint32_t iyb = __float_as_uint(__fadd_rd(o.dy[j], my)), ixb = __float_as_uint(__fadd_rd(o.dx[j], mx));
-          if (!((iyb - kMagicBits) < ylim && (ixb - (kMagicBits - (uint32_t)(j * PPW))) < xlim)) slow |= 1u << j;
+          if (!((iyb - kMagicBits) < ylim && (ixb - xbias[j]) < xlim)) slow |= 1u << j;
         }
         while (slow) {
           const int j = __ffs((int)slow) - 1;
           slow &= slow - 1u;
           float sdy = 0.f, sdx = 0.f, smk = 0.f;
+          int spix = 0, g = 0;
+          uint32_t sa = 0;
 #pragma unroll
           for (int jj = 0; jj < NIT; ++jj)
-            if (jj == j) { sdy = o.dy[jj]; sdx = o.dx[jj]; smk = o.mk[jj]; }
+            if (jj == j) { sdy = o.dy[jj]; sdx = o.dx[jj]; smk = o.mk[jj]; spix = pixj[jj]; g = gj[jj]; sa = a_st[jj]; }
           int tb, ty0, tx0;
           tile_origin(t.tile, tb, ty0, tx0);
-          const int y = ty0 + ry, x = tx0 + j * PPW + pix;
+          const int y = ty0 + ry, x = tx0 + spix;
           const float py = (float)(y - p.d + kr * p.d) + sdy;
           const float px = (float)(x - p.d + kc * p.d) + sdx;
           uint2 pk2 = make_uint2(0u, 0u);
@@ -336,7 +349,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             pk2.y = f2_to_h2<TH>(smk * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z),
                                  smk * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w));
           }
-          sts64((aoff0 ^ (uint32_t)(j * PPW * 16)) + (uint32_t)(j * PPW * 128 + kc * kATile), pk2);
+          sts64(sa + (uint32_t)(kc * kATile), pk2);
         }
         __syncwarp();
       }

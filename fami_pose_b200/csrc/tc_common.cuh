@@ -930,13 +930,12 @@ __device__ __forceinline__ void epilogue_rows_pipelined(const EpiArgs& a, uint32
   }
 }
 
-// Epilogue of the fused offset|mask producer convolution writing the lane-blocked layout the deformable kernel reads
-// (fami_dcn_desc.om_layout = 2): [tap][tile][row 16][iteration NIT][dy | dx | mask][pixel PPW][group G] over 16x8-pixel
-// tiles, where a gather warp of the deformable kernel owns one tile row and its lanes are (pixel, group): LG = 16 lanes per
-// pixel for G > 8 (else G), PPW = 32 / LG pixels per warp iteration, NIT = 8 / PPW iterations per row.  Pixel x of a row is
-// (iteration, pixel) = (x / PPW, x % PPW); every load instruction of a gather warp reads PPW*G contiguous floats and the
-// warp's reads of a (row, tap) are one contiguous run of 24*G floats.  Channel n = tap*3G + k*G + g (k = dy, dx, mask), so
-// the four channels of a float4 never straddle a (tap, k) run; stored straight from registers, no staging.
+// Epilogue of the fused offset|mask producer convolution writing the row-blocked layout the deformable kernel reads
+// (fami_dcn_desc.om_layout = 2): [tap][tile][row 16][dy | dx | mask][pixel 8][group G] over 16x8-pixel tiles.  A gather warp of
+// the deformable kernel owns one tile row; its lanes walk the 8*G samples (pixel, group) of a (row, tap) 32 at a time, so
+// every load instruction of the warp reads 128 contiguous bytes and the warp's reads of a (row, tap) are one contiguous run
+// of 24*G floats.  Channel n = tap*3G + k*G + g (k = dy, dx, mask), so the four channels of a float4 never straddle a
+// (tap, k) run; stored straight from registers, no staging.
 struct OmBlocked {
   float* base;
   int tiles_x, tiles_y, G3;     // DCN tiles per image, 3*G
@@ -946,13 +945,11 @@ __device__ __forceinline__ void epilogue_rows_om_blocked(const EpiArgs& a, uint3
                                                          int img, int y, int x, const OmBlocked& ob) {
   if (col_begin >= col_end) return;   // warp-uniform
   const int G = ob.G3 / 3;
-  const int LG = G > 8 ? 16 : G, PPW = 32 / LG, NIT = 8 / PPW;
   const int ry = y & 15, rx = x & 7;
-  const int j = rx / PPW, pix = rx - j * PPW;
   const int64_t tile = (int64_t)(img * ob.tiles_y + (y >> 4)) * ob.tiles_x + (x >> 3);
-  // + k * PPW*G + g per (dy | dx | mask) run
-  float* lane_base = ob.base + tile * (int64_t)(128 * ob.G3) + (int64_t)((ry * NIT + j) * 3) * (PPW * G) + pix * G;
-  const int kstride = PPW * G;
+  // + k * 8G + g per (dy | dx | mask) run
+  float* lane_base = ob.base + tile * (int64_t)(128 * ob.G3) + (int64_t)(ry * 3) * (8 * G) + rx * G;
+  const int kstride = 8 * G;
   for (int c0 = col_begin; c0 < col_end; c0 += 16) {
     const int ch0 = a.ch_base + c0;
     if (ch0 >= a.Cout) break;   // warp-uniform

@@ -189,7 +189,7 @@ class DeformConv2d(nn.Module):
     def forward(self, input, offset, mask=None, out=None, fused_om=None, blocked_om=None, groups=None):
         x = ops.to_nhwc(input)
         if blocked_om is not None:
-            # fami extension: lane-blocked [offset|mask] buffer written by the fused producer conv (ops.om_to_blocked)
+            # fami extension: row-blocked [offset|mask] buffer written by the fused producer conv (ops.om_to_blocked)
             return ops.dcn_fwd(x, None, None, self.weight, self.bias, self, pad=self.padding[0], dil=self.dilation[0],
                                out=out, blocked_om=blocked_om, groups=groups)
         if fused_om is not None:

@@ -291,7 +291,7 @@ def _conv_raw(x, w_packed, Cout, k, stride, pad, dil, scale, shift, residual, re
 
 def conv_offsets_blocked(x, conv, G, out=None):
     """The fused dcn_offset_k | dcn_mask_k convolution (Alignment_V15.py:144-145; `conv` holds the concatenated,
-    tap-major-permuted parameters) writing the lane-blocked buffer the tensor-core deformable kernel reads
+    tap-major-permuted parameters) writing the row-blocked buffer the tensor-core deformable kernel reads
     (om_to_blocked layout).  Returns the flat float32 buffer."""
     _need_cuda(x)
     N, Cin, H, W, ip = meta(x)
@@ -462,35 +462,27 @@ def tap_major_perm(G, k=3):
 DCN_TILE_H, DCN_TILE_W = 16, 8      # pixel tile of the tensor-core DCN kernel (csrc/dcn_tc.cu)
 
 
-def om_lane_map(G):
-    """(LG, PPW, NIT) of the deformable kernel's gather warps (csrc/dcn_tc.cu LaneMap): lanes per pixel, pixels per warp
-    iteration, iterations per tile row."""
-    LG = 16 if G > 8 else G
-    return LG, 32 // LG, DCN_TILE_W * LG // 32
-
-
 def om_blocked_numel(B, H, W, G, k=3):
-    """Elements of the lane-blocked offset|mask buffer (fami_dcn_desc.om_layout = 2)."""
+    """Elements of the row-blocked offset|mask buffer (fami_dcn_desc.om_layout = 2)."""
     ty, tx = (H + DCN_TILE_H - 1) // DCN_TILE_H, (W + DCN_TILE_W - 1) // DCN_TILE_W
     return k * k * B * ty * tx * DCN_TILE_H * DCN_TILE_W * 3 * G
 
 
 def om_to_blocked(om, G, k=3):
-    """tap-major NHWC [B, 27G, H, W] (tap_major_perm order) -> lane-blocked layout
-    [tap][image tile][row 16][iteration NIT][dy | dx | mask][pixel PPW][group G] over 16x8-pixel tiles: a gather warp of
-    the deformable kernel owns one tile row, its lanes are (pixel, offset group), pixel x of the row is (iteration, pixel) =
-    (x // PPW, x % PPW) -- every load instruction of the warp reads PPW*G contiguous floats.  Host-side converter for tests
-    and tools; in the model the producer convolution writes this layout directly (fami_conv_desc.om_groups)."""
+    """tap-major NHWC [B, 27G, H, W] (tap_major_perm order) -> row-blocked layout
+    [tap][image tile][row 16][dy | dx | mask][pixel 8][group G] over 16x8-pixel tiles: a gather warp of the deformable kernel
+    owns one tile row and walks its 8*G (pixel, group) samples of a tap 32 at a time -- every load instruction of the warp
+    reads 128 contiguous bytes.  Host-side converter for tests and tools; in the model the producer convolution writes this
+    layout directly (fami_conv_desc.om_groups)."""
     B, FC, H, W = om.shape
     K = k * k
-    _, PPW, NIT = om_lane_map(G)
     ty, tx = (H + DCN_TILE_H - 1) // DCN_TILE_H, (W + DCN_TILE_W - 1) // DCN_TILE_W
     t = om.permute(0, 2, 3, 1).reshape(B, H, W, K, 3, G).float()
     if ty * DCN_TILE_H != H or tx * DCN_TILE_W != W:
         pad = torch.zeros((B, ty * DCN_TILE_H, tx * DCN_TILE_W, K, 3, G), dtype=torch.float32, device=om.device)
         pad[:, :H, :W] = t
         t = pad
-    t = t.reshape(B, ty, DCN_TILE_H, tx, NIT, PPW, K, 3, G).permute(6, 0, 1, 3, 2, 4, 7, 5, 8)   # K,B,ty,tx,row,it,k,pix,G
+    t = t.reshape(B, ty, DCN_TILE_H, tx, DCN_TILE_W, K, 3, G).permute(5, 0, 1, 3, 2, 6, 4, 7)   # K,B,ty,tx,row,k,pix,G
     return t.contiguous().reshape(-1)
 
 
@@ -515,7 +507,7 @@ def dcn_fwd(x, offset, mask, weight, bias, owner, pad=3, dil=3, out=None, fused_
         G = groups
         if Cin != C or not dcn_fused_supported(C, G, x.dtype) or blocked_om.dtype != torch.float32 \
                 or blocked_om.numel() != om_blocked_numel(B, H, W, G, kh):
-            raise ValueError("lane-blocked DCN offsets need 16-bit x, C <= 64, 4 channels per offset group and a "
+            raise ValueError("row-blocked DCN offsets need 16-bit x, C <= 64, 4 channels per offset group and a "
                              "float32 buffer of om_blocked_numel elements")
         w = packed_weight(owner, weight, x.dtype)
         d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, 0, 0, outp, 2, _code(x.dtype), out_f32)

@@ -93,7 +93,7 @@ typedef struct fami_conv_desc {
   int32_t stats;                 /* 1: also accumulate per-channel sum / sum-of-squares of the RAW
                                     (post scale/shift, pre residual/act) output into the double
                                     array stats_out[2*Cout], which the caller zeroes (train-mode BN) */
-  int32_t om_groups;             /* 0: y is an NHWC activation (out_pitch).  G > 0: y is the lane-blocked offset|mask
+  int32_t om_groups;             /* 0: y is an NHWC activation (out_pitch).  G > 0: y is the row-blocked offset|mask
                                     buffer of the tensor-core deformable kernel (fami_dcn_desc.om_layout = 2) for G
                                     offset groups: Cout = 27*G channels in tap-major order, out_dtype FAMI_F32, up = 1,
                                     no residual, 3x3 stride-1 "same" convolution (the fused dcn_offset_k | dcn_mask_k
@@ -174,16 +174,16 @@ typedef struct fami_dcn_desc {
                                        and `mask` [.,9G] (channel g*9+t) are separate operands;
                                        1: fused tap-major -- `offset` points at ONE NHWC buffer holding, per pixel,
                                        [9 taps][dy(G) | dx(G) | mask(G)] (off_pitch >= 27G), `mask` is ignored;
-                                       2: fused lane-blocked -- `offset` points at ONE dense buffer
-                                       [9 taps][image tile][row 16][iteration NIT][dy | dx | mask][pixel PPW][group G]
-                                       over 16x8-pixel tiles (tile = (b * ceil(H/16) + y/16) * ceil(W/8) + x/8, row =
-                                       y%16, (iteration, pixel) = ((x%8) / PPW, (x%8) % PPW)), with LG = 16 lanes per pixel
-                                       for G > 8 (else G), PPW = 32 / LG, NIT = 8 / PPW; pitches and `mask` ignored.
+                                       2: fused row-blocked -- `offset` points at ONE dense buffer
+                                       [9 taps][image tile][row 16][dy | dx | mask][pixel 8][group G] over 16x8-pixel
+                                       tiles (tile = (b * ceil(H/16) + y/16) * ceil(W/8) + x/8, row = y%16, pixel = x%8);
+                                       pitches and `mask` ignored.
                                        Layouts 1 and 2 are the 16-bit tensor-core kernel's; the alignment head's fused
                                        offset|mask convolution writes layout 2 (fami_conv_desc.om_groups): a gather warp
-                                       of the deformable kernel owns one tile row, its lanes are (pixel, offset group),
-                                       every load instruction of the warp reads PPW*G contiguous floats and the warp's
-                                       reads of a (row, tap) are one contiguous run of 24*G floats.  */
+                                       of the deformable kernel owns one tile row and walks its 8*G (pixel, group)
+                                       samples of a tap 32 at a time, every load instruction of the warp reads 128
+                                       contiguous bytes and the warp's reads of a (row, tap) are one contiguous run of
+                                       24*G floats.  */
   int32_t dtype;                    /* storage of x/out: FAMI_F32 or FAMI_F16 / FAMI_BF16; offset, mask, packed
                                        weights and bias are always float (sub-pixel precision)        */
   int32_t out_f32;                  /* 1 (16-bit dtype, layouts 1 / 2 only): `out` is float while x stays 16-bit -- the

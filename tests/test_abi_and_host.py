@@ -212,7 +212,7 @@ def test_multistep_lr_matches_torch_scheduler():
 
 def test_offset_layout_host_logic():
     """tap_major_perm is a permutation mapping torchvision's [offset(18G) | mask(9G)] order to [tap][dy|dx|mask];
-    om_to_blocked is a bijection onto the lane-blocked buffer for tile-aligned maps (CPU tensors: pure indexing)."""
+    om_to_blocked is a bijection onto the row-blocked buffer for tile-aligned maps (CPU tensors: pure indexing)."""
     import torch
     from fami_pose_b200 import ops
     G = 12
@@ -228,13 +228,10 @@ def test_offset_layout_host_logic():
     blk = ops.om_to_blocked(om, G)
     assert blk.numel() == ops.om_blocked_numel(B, H, W, G) == om.numel()
     assert torch.equal(torch.sort(blk).values, torch.sort(om.reshape(-1)).values)
-    # element (b=1, y=17, x=9, tap=3, channel-in-tap f = G + 7 -> dx of group 7): tile (1,1) of image 1, row 1, x%8 = 1 ->
-    # G = 12: 16 lanes per pixel, 2 pixels per warp iteration, 4 iterations: (iteration, pixel) = (0, 1)
-    LG, PPW, NIT = ops.om_lane_map(G)
-    assert (LG, PPW, NIT) == (16, 2, 4) and ops.om_lane_map(8) == (8, 4, 2) and ops.om_lane_map(4) == (4, 8, 1)
+    # element (b=1, y=17, x=9, tap=3, channel-in-tap f = G + 7 -> dx of group 7): tile (1,1) of image 1, row 1, pixel x%8 = 1
     tiles = (H // 16) * (W // 8)
     tile = 1 * tiles + 1 * (W // 8) + 1
-    idx = (((((3 * (B * tiles) + tile) * 16 + 1) * NIT + 0) * 3 + 1) * PPW + 1) * G + 7
+    idx = ((((3 * (B * tiles) + tile) * 16 + 1) * 3 + 1) * 8 + 1) * G + 7
     assert float(blk[idx]) == float(om[1, 3 * 3 * G + G + 7, 17, 9])
-    # the same pixel's mask of group 0 is one (dy | dx | mask) run further
-    assert float(blk[idx - 7 + PPW * G]) == float(om[1, 3 * 3 * G + 2 * G, 17, 9])
+    # the same pixel's mask of group 0 is one (dy | dx | mask) run of 8*G floats further
+    assert float(blk[idx - 7 + 8 * G]) == float(om[1, 3 * 3 * G + 2 * G, 17, 9])

@@ -663,7 +663,7 @@ def test_warp_translate_bwd_vs_torch_autograd():
 
 @pytest.mark.parametrize("shape", [(2, 48, 12, 33, 21), (1, 32, 8, 16, 8), (3, 64, 16, 20, 30)])
 def test_offset_conv_blocked_layout_and_dcn(shape):
-    """The fused offset|mask producer writing the lane-blocked layout (fami_conv_desc.om_groups) equals the same conv
+    """The fused offset|mask producer writing the row-blocked layout (fami_conv_desc.om_groups) equals the same conv
     written as an NHWC activation and converted on the host (ops.om_to_blocked), bit for bit -- incl. maps that are not a
     multiple of the 16x8 DCN tile -- and the deformable kernel gives identical outputs from both layouts."""
     m = fp()
