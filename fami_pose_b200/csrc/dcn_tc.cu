@@ -46,6 +46,7 @@ constexpr int kDcnThreads = kGatherThreads + 32 * kDcnEpiWarps;   // 640: 20 war
                                                                      // (the first epilogue warp is also the TMA + MMA issuer)
 constexpr int kAStages = 3;               // tap t -> A stage t % 3
 constexpr int kATile = 128 * 128;          // bytes per A stage
+constexpr int kBarSlots = 13 + 2 * kAStages; // mbarriers of the kernel (8 B each); the TMEM slot and the bias table follow
 constexpr uint32_t kMagicBits = 0x4B400000u;   // 1.5 * 2^23: adding it with round-down leaves floor(v) in the low mantissa bits
 constexpr float kMagic = 12582912.f;
 
@@ -63,6 +64,8 @@ struct DcnTcParams {
   int WH, WW;                       // staged window (pixels)
   int tiles_x, tiles_y, total_tiles;
   int nk, BN;
+  int npass;                        // channel passes of 64 channels (C > 64), else 1
+  int w_stream;                     // 0: the 9 weight tiles are resident; NW > 0: streamed through NW stages per (pass, tap)
   int om_pitch, x_pitch, out_pitch, vec_ok, out_f32;
   int om_blocked;                   // 1: offsets|masks in the row-blocked layout (om_layout 2)
   int64_t om_tap_stride;            // floats between taps in the blocked layout = tiles * 128 * 3G
@@ -127,19 +130,21 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   const uint32_t sbase = (raw_u32 + 1023u) & ~1023u;
   const uint32_t win_u32 = sbase;                                          // WH*WW rows x 128 B
   const uint32_t a_u32 = win_u32 + ((p.win_bytes + 1023u) & ~1023u);       // kAStages x 16 KB (1 KB-aligned swizzle atoms)
-  const uint32_t w_u32 = a_u32 + kAStages * kATile;                        // 9 x BN x 128 B
-  const uint32_t bar0 = w_u32 + 9 * p.w_tile_bytes;
-  // barriers: win_full, win_free, w_full, a_full[3], a_empty[3], tfull[2], tempty[2]
+  const uint32_t w_u32 = a_u32 + kAStages * kATile;                        // 9 (resident) or NW (streamed) x BN x 128 B
+  const uint32_t bar0 = w_u32 + (uint32_t)(p.w_stream ? p.w_stream : 9) * p.w_tile_bytes;
+  // barriers: win_full, win_free, w_full, a_full[3], a_empty[3], tfull[2], tempty[2], ws_full[3], ws_empty[3]
   const uint32_t win_full = bar0, win_free = bar0 + 8, w_full = bar0 + 16;
   auto a_full = [&](int s) { return bar0 + 8u * (3 + s); };
   auto a_empty = [&](int s) { return bar0 + 8u * (3 + kAStages + s); };
   auto tfull = [&](int a) { return bar0 + 8u * (3 + 2 * kAStages + a); };
   auto tempty = [&](int a) { return bar0 + 8u * (5 + 2 * kAStages + a); };
+  auto ws_full = [&](int s) { return bar0 + 8u * (7 + 2 * kAStages + s); };
+  auto ws_empty = [&](int s) { return bar0 + 8u * (10 + 2 * kAStages + s); };
   uint8_t* gen0 = smem_raw + (bar0 - raw_u32);                             // generic pointer to the barrier block
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen0 + 8 * (7 + 2 * kAStages));
-  float* s_scale = reinterpret_cast<float*>(gen0 + 8 * (10 + 2 * kAStages));   // 16-byte aligned (float4 reads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen0 + 8 * kBarSlots);
+  float* s_scale = reinterpret_cast<float*>(gen0 + 8 * (kBarSlots + 3));   // 16-byte aligned (float4 reads)
   float* s_shift = s_scale + p.BN;
-  const uint32_t stage_u32 = (bar0 + 8u * (10 + 2 * kAStages) + (uint32_t)p.BN * 8u + 15u) & ~15u;   // epilogue staging
+  const uint32_t stage_u32 = (bar0 + 8u * (kBarSlots + 3) + (uint32_t)p.BN * 8u + 15u) & ~15u;   // epilogue staging
   fill_scale_shift(s_scale, s_shift, nullptr, p.bias, p.Cout, p.BN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -149,11 +154,12 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     mbar_init(w_full, 1);
     for (int s = 0; s < kAStages; ++s) { mbar_init(a_full(s), kGatherWarps); mbar_init(a_empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), kDcnEpiWarps); }
+    for (int w = 0; w < 3; ++w) { mbar_init(ws_full(w), 1); mbar_init(ws_empty(w), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
   }
   if (warp == kGatherWarps) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bar0 + 8u * (7 + 2 * kAStages)), "r"(512u)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bar0 + 8u * kBarSlots), "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -202,23 +208,30 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const float mx0 = kMagic + (float)(p.R - p.d);          // + kc * d per kernel column (pixel 0 of the row)
     const float mx1 = mx0 + fd, mx2 = mx1 + fd;
 
-    // per-tile state of this lane: pointer to its (dy) float of tap 0 / iteration 0, and the valid-iteration mask
-    struct TileRef { const float* po; uint32_t vmask; int tile; };
-    auto tile_ref = [&](int tile) {
+    // A CTA walks a stream of units = (tile, channel pass of 64 channels); C <= 64 has one pass per tile.
+    // per-unit state of this lane: pointer to its (dy) float of tap 0 / iteration 0, and the valid-iteration mask
+    const int NP = p.npass, Gt = p.G;
+    struct TileRef { const float* po; uint32_t vmask; int tile; int pass; };
+    auto unit_ref = [&](int useq) {
       TileRef t;
-      t.po = p.om; t.vmask = 0; t.tile = tile;
-      if (tile >= p.total_tiles) return t;
+      t.po = p.om; t.vmask = 0;
+      const int ti = useq / NP;
+      t.pass = useq - ti * NP;
+      t.tile = blockIdx.x + ti * gridDim.x;
+      if (t.tile >= p.total_tiles) return t;
       int b, y0, x0;
-      tile_origin(tile, b, y0, x0);
+      tile_origin(t.tile, b, y0, x0);
       const int y = y0 + ry;
 #pragma unroll
       for (int j = 0; j < NIT; ++j)
         if (y < p.H && x0 + pixj[j] < p.W) t.vmask |= 1u << j;
       if (p.om_blocked) {
-        // [tap][tile][row 16][dy | dx | mask][pixel 8][group G]: sample s of iteration j at float 32 j + lane of its run
-        t.po = p.om + (int64_t)tile * (128 * 3 * kG) + ry * (3 * 8 * kG) + lane;
+        // [tap][tile][row 16][dy | dx | mask][pixel 8][group G]; one pass: sample s of iteration j at float 32 j + lane of
+        // its run; passes (16 groups each): lanes 0-15 / 16-31 are pixels 2j / 2j+1, groups 16 pass .. 16 pass + 15
+        const int lane_part = (kG == 16) ? (lane >> 4) * Gt + (lane & 15) + 16 * t.pass : lane;
+        t.po = p.om + (int64_t)t.tile * (128 * 3 * Gt) + ry * (3 * 8 * Gt) + lane_part;
       } else {
-        t.po = p.om + ((int64_t)(b * p.H + (y < p.H ? y : 0)) * p.W + x0) * p.om_pitch;
+        t.po = p.om + ((int64_t)(b * p.H + (y < p.H ? y : 0)) * p.W + x0) * p.om_pitch + 16 * t.pass;
       }
       return t;
     };
@@ -228,31 +241,32 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < NIT; ++j) {
           const bool v = (t.vmask >> j) & 1u;
-          o.dy[j] = v ? ldg_stream(q + 32 * j) : 0.f;
-          o.dx[j] = v ? ldg_stream(q + 8 * kG + 32 * j) : 0.f;
-          o.mk[j] = v ? ldg_stream(q + 16 * kG + 32 * j) : 0.f;
+          const int jo = (kG == 16) ? 2 * j * Gt : 32 * j;
+          o.dy[j] = v ? ldg_stream(q + jo) : 0.f;
+          o.dx[j] = v ? ldg_stream(q + 8 * Gt + jo) : 0.f;
+          o.mk[j] = v ? ldg_stream(q + 16 * Gt + jo) : 0.f;
         }
       } else {
-        const float* q = t.po + tap * 3 * kG;
+        const float* q = t.po + tap * 3 * Gt;
 #pragma unroll
         for (int j = 0; j < NIT; ++j) {
           const bool v = (t.vmask >> j) & 1u;
           const float* qj = q + (int64_t)pixj[j] * p.om_pitch + gj[j];
           o.dy[j] = v ? __ldg(qj) : 0.f;
-          o.dx[j] = v ? __ldg(qj + kG) : 0.f;
-          o.mk[j] = v ? __ldg(qj + 2 * kG) : 0.f;
+          o.dx[j] = v ? __ldg(qj + Gt) : 0.f;
+          o.mk[j] = v ? __ldg(qj + 2 * Gt) : 0.f;
         }
       }
     };
-    // load of the tap two positions ahead in the (tile, tap) stream
+    // load of the tap two positions ahead in the (unit, tap) stream
     auto load_ahead = [&](const TileRef& cur, const TileRef& nxt, int tap, Om& o) {
       if (tap + 2 < 9) load_tap(cur, tap + 2, o);
       else load_tap(nxt, tap + 2 - 9, o);
     };
 
-    // one tap of one tile: NIT samples of this lane into A stage kc
-    auto do_tap = [&](const TileRef& t, const Om& o, int kr, float my, float mx, int kc, int git) {
-      const uint32_t u = (uint32_t)(git * 3 + kr);            // use index of stage kc
+    // one tap of one unit: NIT samples of this lane into A stage kc
+    auto do_tap = [&](const TileRef& t, const Om& o, int kr, float my, float mx, int kc, int useq) {
+      const uint32_t u = (uint32_t)(useq * 3 + kr);           // use index of stage kc
       bool far = false;                          // any sample of this lane outside the staged window
       constexpr int NB = (NIT % 2) ? NIT : 2;    // samples per batch (8 or 12 corner loads in flight per lane); NB divides NIT
       static_assert(NIT % NB == 0, "batch size must divide the iteration count");
@@ -336,7 +350,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
             const int iy0 = (int)floorf(py), ix0 = (int)floorf(px);
             const float ly = py - (float)iy0, lx = px - (float)ix0, hy = 1.f - ly, hx = 1.f - lx;
-            const TH* xb = xg + (int64_t)tb * p.H * p.W * p.x_pitch + g * 4;
+            const TH* xb = xg + (int64_t)tb * p.H * p.W * p.x_pitch + (16 * t.pass + g) * 4;
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             const bool y0ok = iy0 >= 0, y1ok = iy0 + 1 <= p.H - 1, x0ok = ix0 >= 0, x1ok = ix0 + 1 <= p.W - 1;
             const float4 v1 = (y0ok && x0ok) ? ld4h<TH>(xb + ((int64_t)iy0 * p.W + ix0) * p.x_pitch) : z;
@@ -359,52 +373,52 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     };
 
     uint32_t wph = 0, fph = 0;
-    int git = 0;
-    TileRef cur = tile_ref(blockIdx.x), nxt = tile_ref(blockIdx.x + gridDim.x);
+    const int my_tiles = ((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int n_units = my_tiles * NP;
+    TileRef cur = unit_ref(0), nxt = unit_ref(1);
     Om o0, o1, o2;                       // taps 3i, 3i+1, 3i+2 of the stream: rotating, two taps in flight
     load_tap(cur, 0, o0);
     load_tap(cur, 1, o1);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++git) {
-      if (threadIdx.x == 0) dtrace(p.trace, git, 0);
+    for (int useq = 0; useq < n_units; ++useq) {
+      if (threadIdx.x == 0) dtrace(p.trace, useq, 0);
       mbar_wait(win_full, wph);
       wph ^= 1u;
-      if (threadIdx.x == 0) dtrace(p.trace, git, 1);
+      if (threadIdx.x == 0) dtrace(p.trace, useq, 1);
       float my = my0;
 #pragma unroll 1
       for (int kr = 0; kr < 3; ++kr, my += fd) {
         load_ahead(cur, nxt, kr * 3 + 0, o2);
-        do_tap(cur, o0, kr, my, mx0, 0, git);
+        do_tap(cur, o0, kr, my, mx0, 0, useq);
         load_ahead(cur, nxt, kr * 3 + 1, o0);
-        do_tap(cur, o1, kr, my, mx1, 1, git);
+        do_tap(cur, o1, kr, my, mx1, 1, useq);
         load_ahead(cur, nxt, kr * 3 + 2, o1);
-        do_tap(cur, o2, kr, my, mx2, 2, git);
-        if (threadIdx.x == 0) dtrace(p.trace, git, 2 + kr);
+        do_tap(cur, o2, kr, my, mx2, 2, useq);
+        if (threadIdx.x == 0) dtrace(p.trace, useq, 2 + kr);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(win_free);   // this warp no longer reads the window of this tile
+      if (lane == 0) mbar_arrive(win_free);   // this warp no longer reads the window of this unit
       if (warp == 0) {
-        // refill the window for the next tile as soon as the last gather warp has left it (issued from here,
+        // refill the window for the next unit as soon as the last gather warp has left it (issued from here,
         // not from the MMA warp, which is still draining the last taps)
         mbar_wait(win_free, fph);
         fph ^= 1u;
-        const int next = tile + gridDim.x;
-        if (lane == 0 && next < p.total_tiles) {
+        if (lane == 0 && useq + 1 < n_units) {
           int nb, ny0, nx0;
-          tile_origin(next, nb, ny0, nx0);
+          tile_origin(nxt.tile, nb, ny0, nx0);
           mbar_arrive_expect_tx(win_full, p.win_bytes);
-          tma_tiled_4d(win_u32, &tmX, win_full, 0, nx0 - p.R, ny0 - p.R, nb);
+          tma_tiled_4d(win_u32, &tmX, win_full, 64 * nxt.pass, nx0 - p.R, ny0 - p.R, nb);
         }
         __syncwarp();
       }
       cur = nxt;
-      nxt = tile_ref(tile + 2 * gridDim.x);
+      nxt = unit_ref(useq + 2);
     }
   } else {
     // ===================== epilogue warps (the first one is also the TMA + MMA issuer) =====================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     EpiArgs ea;
-    ea.s_scale = bar0 + 8u * (10 + 2 * kAStages); ea.s_shift = ea.s_scale + (uint32_t)p.BN * 4u; ea.res = nullptr; ea.y = p.out;
+    ea.s_scale = bar0 + 8u * (kBarSlots + 3); ea.s_shift = ea.s_scale + (uint32_t)p.BN * 4u; ea.res = nullptr; ea.y = p.out;
     ea.Cout = p.Cout; ea.BN = p.BN; ea.ch_base = 0; ea.out_pitch = p.out_pitch; ea.res_pitch = 0;
     ea.out_f32 = p.out_f32; ea.relu = 0; ea.vec_ok = p.vec_ok; ea.up = 1; ea.Wout = p.W;
     ea.spitch = 128 + 16;
@@ -457,8 +471,10 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       if (leader) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
-        mbar_arrive_expect_tx(w_full, 9u * p.w_tile_bytes);
-        for (int t = 0; t < 9; ++t) tma_tiled_2d(w_u32 + t * p.w_tile_bytes, &tmW, w_full, t * 64, 0);
+        if (!p.w_stream) {
+          mbar_arrive_expect_tx(w_full, 9u * p.w_tile_bytes);
+          for (int t = 0; t < 9; ++t) tma_tiled_2d(w_u32 + t * p.w_tile_bytes, &tmW, w_full, t * 64, 0);
+        }
       }
       {
         int b, y0, x0;
@@ -475,27 +491,61 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           prefetch_om(b, y0, x0);
         }
       }
-      mbar_wait(w_full, 0);
+      // Weights: resident (C <= 64: nine [BN][64] tiles loaded once) or streamed (C > 64: one [BN][64] tile per (pass, tap)
+      // through NW stages; the slot of the MMA issued one step earlier is refilled, so the issuer never waits on its own MMA).
+      const int NP = p.npass, NW = p.w_stream;
+      const int my_tiles = ((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      const int w_total = my_tiles * NP * 9;               // streamed tiles this CTA consumes
+      auto w_issue = [&](int id) {                         // tile id of the stream -> (pass, tap) of its unit
+        const int k = id % (NP * 9);
+        const int pass = k / 9, tap = k - pass * 9;
+        const int slot = id % NW;
+        if (leader) {
+          mbar_arrive_expect_tx(ws_full(slot), p.w_tile_bytes);
+          tma_tiled_2d(w_u32 + slot * p.w_tile_bytes, &tmW, ws_full(slot), (tap * NP + pass) * 64, 0);
+        }
+      };
+      if (NW) {
+        for (int i = 0; i < NW && i < w_total; ++i) w_issue(i);
+      } else {
+        mbar_wait(w_full, 0);
+      }
       tc_fence_after();
       const uint32_t w_lo0 = sw128_desc_lo(w_u32);
       const uint32_t w_step = p.w_tile_bytes >> 4;
       int stage = 0;
       uint32_t aph = 0;
-      int it = 0;
+      int it = 0, wid = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_u + (uint32_t)(acc * p.BN);
-        uint32_t w_lo = w_lo0;
-        for (int tap = 0; tap < 9; ++tap, w_lo += w_step) {
-          mbar_wait(a_full(stage), aph);
-          tc_fence_after();
-          const uint32_t a_lo = sw128_desc_lo(a_u32 + stage * kATile);
-          umma_ksteps_n(p.nk, leader, d_tmem, a_lo, w_lo, idesc, tap != 0);
-          if (leader) umma_commit(a_empty(stage));
-          if (++stage == kAStages) { stage = 0; aph ^= 1u; }
+        for (int pass = 0; pass < NP; ++pass) {
+          uint32_t w_lo = w_lo0;
+          for (int tap = 0; tap < 9; ++tap, w_lo += w_step) {
+            mbar_wait(a_full(stage), aph);
+            int slot = 0;
+            if (NW) {
+              slot = wid % NW;
+              mbar_wait(ws_full(slot), (uint32_t)(wid / NW) & 1u);
+            }
+            tc_fence_after();
+            const uint32_t a_lo = sw128_desc_lo(a_u32 + stage * kATile);
+            umma_ksteps_n(p.nk, leader, d_tmem, a_lo, NW ? w_lo0 + (uint32_t)slot * w_step : w_lo, idesc, (pass | tap) != 0);
+            if (leader) umma_commit(a_empty(stage));
+            if (NW) {
+              if (leader) umma_commit(ws_empty(slot));
+              if (wid >= 1 && wid - 1 + NW < w_total) {
+                const int prev = wid - 1;
+                mbar_wait(ws_empty(prev % NW), (uint32_t)(prev / NW) & 1u);
+                w_issue(prev + NW);
+              }
+              ++wid;
+            }
+            if (++stage == kAStages) { stage = 0; aph ^= 1u; }
+          }
         }
         if (leader) umma_commit(tfull(acc));
         // pull the offsets|masks of the tile after next towards L2 (the window refill is issued by gather warp 0)
@@ -525,11 +575,18 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 
 }  // namespace
 
+// weight stages: 0 = the nine tiles of the single pass are resident (C <= 64), else streamed per (pass, tap)
+static int dcn_tc_wstream(const fami_dcn_desc* d) {
+  if (d->C <= 64) return 0;
+  const int BN = ((d->Cout + 15) / 16) * 16;
+  return BN > 128 ? 2 : 3;
+}
 // shared-memory footprint for a window radius R; the launcher takes the largest R <= dil + 5 that fits
 static size_t dcn_tc_smem(const fami_dcn_desc* d, int R) {
   const int BN = ((d->Cout + 15) / 16) * 16;
+  const int NW = dcn_tc_wstream(d);
   const size_t win = ((size_t)(kTH + 2 * R) * (kTW + 2 * R) * 128 + 1023) & ~(size_t)1023;
-  return win + kAStages * kATile + 9 * (size_t)BN * 128 + 1024 + 256 + (size_t)BN * 8 +
+  return win + kAStages * kATile + (size_t)(NW ? NW : 9) * BN * 128 + 1024 + 8 * (kBarSlots + 3) + 16 + (size_t)BN * 8 +
          (size_t)kDcnEpiWarps * 32 * (128 + 16);
 }
 static int dcn_tc_radius(const fami_dcn_desc* d) {
@@ -540,7 +597,8 @@ static int dcn_tc_radius(const fami_dcn_desc* d) {
 
 int dcn_tc_supported(const fami_dcn_desc* d) {
   if (!is_half_dtype(d->dtype) || (d->om_layout != 1 && d->om_layout != 2)) return 0;
-  if (d->C % 16 != 0 || d->C > 64 || d->G * 4 != d->C) return 0;      // G in {4, 8, 12, 16}
+  // 4 channels per offset group; one pass of C <= 64 channels (G in {4, 8, 12, 16}) or C / 64 passes of 64 channels
+  if (d->C % 16 != 0 || d->G * 4 != d->C || (d->C > 64 && d->C % 64 != 0)) return 0;
   if (d->om_layout == 1 && d->off_pitch % 4 != 0) return 0;             // 16-byte loads of the (dy|dx|mask) runs
   if (d->Cout > 256 || d->x_pitch % 8 != 0) return 0;
   if (d->kh != 3 || d->kw != 3 || d->pad != d->dil || d->dil > 4) return 0;
@@ -562,7 +620,9 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
   p.WH = kTH + 2 * p.R; p.WW = kTW + 2 * p.R;
   p.tiles_x = (d->W + kTW - 1) / kTW; p.tiles_y = (d->H + kTH - 1) / kTH;
   p.total_tiles = d->B * p.tiles_x * p.tiles_y;
-  p.nk = d->C / 16;
+  p.npass = d->C > 64 ? d->C / 64 : 1;
+  p.w_stream = dcn_tc_wstream(d);
+  p.nk = d->C > 64 ? 4 : d->C / 16;
   p.BN = ((d->Cout + 15) / 16) * 16;
   p.om_pitch = d->off_pitch; p.x_pitch = d->x_pitch; p.out_pitch = d->out_pitch;
   p.out_f32 = d->out_f32 ? 1 : 0;
@@ -581,7 +641,7 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
   {
     // a pitch of >= 64 slots lets the box read whole 128-byte rows without out-of-bounds fill on the channel axis
     // (slots C..63 are never consumed: the gather only reads channels < C)
-    cuuint64_t dims[4] = {(cuuint64_t)(d->x_pitch >= 64 ? 64 : d->C), (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t dims[4] = {(cuuint64_t)(d->C > 64 ? d->C : (d->x_pitch >= 64 ? 64 : d->C)), (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
     cuuint64_t strides[3] = {(cuuint64_t)d->x_pitch * 2, (cuuint64_t)d->W * d->x_pitch * 2,
                              (cuuint64_t)d->H * d->W * d->x_pitch * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)p.WW, (cuuint32_t)p.WH, 1};
@@ -593,9 +653,10 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
     FAMI_CHECK_ARG(r == CUDA_SUCCESS, "dcn_tc: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
   }
   {
-    // weights packed by fami_pack_conv_weight(half): [CoutPad][9 taps][64] (Cin <= 64 -> one chunk per tap)
-    cuuint64_t dims[2] = {(cuuint64_t)9 * 64, (cuuint64_t)p.BN};
-    cuuint64_t strides[1] = {(cuuint64_t)9 * 64 * 2};
+    // weights packed by fami_pack_conv_weight(half): [CoutPad][9 taps][ceil(Cin/64) chunks][64]
+    const int chunks = (d->C + 63) / 64;
+    cuuint64_t dims[2] = {(cuuint64_t)9 * chunks * 64, (cuuint64_t)p.BN};
+    cuuint64_t strides[1] = {(cuuint64_t)9 * chunks * 64 * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)p.BN};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode_tiled(&tmW, tm_dtype, 2, const_cast<void*>(w), dims, strides, box, estr,
@@ -615,7 +676,7 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
     dcn_tc_kernel<TH_, G_><<<grid, kDcnThreads, smem, st>>>(tmX, tmW, p);                                      \
   }
 #define FAMI_DCN_LAUNCH_G(TH_)                                                  \
-  switch (d->G) {                                                                \
+  switch (d->C > 64 ? 16 : d->G) {   /* groups per pass */                      \
     case 4: FAMI_DCN_LAUNCH(TH_, 4) break;                                       \
     case 8: FAMI_DCN_LAUNCH(TH_, 8) break;                                       \
     case 12: FAMI_DCN_LAUNCH(TH_, 12) break;                                     \

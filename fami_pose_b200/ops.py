@@ -425,7 +425,7 @@ def dcn_fused_supported(C, G, dtype):
     """True if the tensor-core DCN kernel (fused tap-major offsets) takes this shape: 16-bit activations, or the fp32
     activations of the 'tf32' arm (cast to fp16 -- the same 11-bit significand as TF32 -- on the way in, fp32 out)."""
     half = dtype in (torch.float16, torch.bfloat16) or (dtype == torch.float32 and _PRECISION == "tf32")
-    return half and C % 16 == 0 and C <= 64 and C % G == 0 and C // G == 4
+    return half and C % 16 == 0 and (C <= 64 or C % 64 == 0) and C % G == 0 and C // G == 4
 
 
 def cast_nhwc(x, dtype, out=None):
@@ -507,7 +507,7 @@ def dcn_fwd(x, offset, mask, weight, bias, owner, pad=3, dil=3, out=None, fused_
         G = groups
         if Cin != C or not dcn_fused_supported(C, G, x.dtype) or blocked_om.dtype != torch.float32 \
                 or blocked_om.numel() != om_blocked_numel(B, H, W, G, kh):
-            raise ValueError("row-blocked DCN offsets need 16-bit x, C <= 64, 4 channels per offset group and a "
+            raise ValueError("row-blocked DCN offsets need 16-bit x, C <= 64 or a multiple of 64, 4 channels per offset group and a "
                              "float32 buffer of om_blocked_numel elements")
         w = packed_weight(owner, weight, x.dtype)
         d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, 0, 0, outp, 2, _code(x.dtype), out_f32)
@@ -519,7 +519,7 @@ def dcn_fwd(x, offset, mask, weight, bias, owner, pad=3, dil=3, out=None, fused_
             raise RuntimeError("fused offset|mask buffer %s inconsistent with input %s" % (tuple(fused_om.shape), tuple(x.shape)))
         G = FC // (3 * kh * kw)
         if Cin != C or not dcn_fused_supported(C, G, x.dtype):
-            raise ValueError("fused tap-major DCN needs 16-bit x, C <= 64 and 4 channels per offset group")
+            raise ValueError("fused tap-major DCN needs 16-bit x, C <= 64 or a multiple of 64, and 4 channels per offset group")
         w = packed_weight(owner, weight, x.dtype)      # UMMA B operand: [CoutPad][9][64] half
         d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, fp_, 0, outp, 1, _code(x.dtype), out_f32)
         _lib.call("fami_dcn_fwd", ctypes.byref(d), _ptr(x), _ptr(fused_om), None, _ptr(w), _ptr(b), _ptr(out), _stream())

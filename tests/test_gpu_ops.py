@@ -516,7 +516,10 @@ def _to_tap_major(off, msk, G):
 
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
 @pytest.mark.parametrize("shape", [(2, 48, 48, 12, 12, 9, 3.0), (1, 32, 32, 8, 10, 7, 2.0), (1, 64, 48, 16, 8, 8, 1.0),
-                                   (2, 48, 48, 12, 96, 72, 2.0), (1, 48, 48, 12, 40, 30, 14.0), (1, 48, 17, 12, 33, 21, 2.0)])
+                                   (2, 48, 48, 12, 96, 72, 2.0), (1, 48, 48, 12, 40, 30, 14.0), (1, 48, 17, 12, 33, 21, 2.0),
+                                   # C > 64: channel passes of 64 channels, weights streamed per (pass, tap) (config 5: C = 128, 256)
+                                   (1, 128, 128, 32, 20, 13, 2.0), (1, 256, 64, 64, 17, 9, 2.0), (2, 128, 48, 32, 16, 8, 7.0),
+                                   (1, 256, 256, 64, 16, 8, 2.0)])
 def test_dcn_tc_fused_vs_oracle(shape, prec):
     """tensor-core DCN (x/weights/columns in 16 bit, fp32 accumulate, fp32 offsets) vs the numpy oracle run
     on the SAME 16-bit-rounded x and weights; sigma=14 px exercises the out-of-window global path.
@@ -584,6 +587,27 @@ def test_dcn_tf32_arm_vs_oracle(shape):
         err = float((got - ref).abs().max())
         print("dcn tf32 arm", shape, "err", err, "tol", tol)
         assert err <= tol
+    finally:
+        m.set_precision("fp32")
+
+
+@pytest.mark.parametrize("shape", [(2, 128, 128, 32, 35, 19), (1, 256, 64, 64, 16, 24), (2, 64, 64, 16, 20, 9), (1, 32, 32, 8, 17, 8)])
+def test_dcn_tc_blocked_equals_tap_major(shape):
+    """The row-blocked offset layout (om_layout 2, ops.om_to_blocked) and the tap-major NHWC layout (om_layout 1) give
+    bit-identical outputs, incl. C > 64 (channel passes) and maps that are not a multiple of the 16x8 tile."""
+    import fami_pose_b200 as m
+    from fami_pose_b200 import layers, ops
+    B, C, Cout, G, H, W = shape
+    m.set_precision("fp16")
+    try:
+        g = torch.Generator().manual_seed(C + H)
+        x = ops.to_nhwc(torch.randn(B, C, H, W, generator=g).to(DEV), torch.float16)
+        om = ops.to_nhwc((2.5 * torch.randn(B, 27 * G, H, W, generator=g)).to(DEV), torch.float32)
+        mod = layers.DeformConv2d(C, Cout, 3, padding=3, dilation=3).to(DEV)
+        with torch.no_grad():
+            o1 = mod(x, None, None, fused_om=om)
+            o2 = mod(x, None, None, blocked_om=ops.om_to_blocked(om, G), groups=G)
+        assert torch.isfinite(o1.float()).all() and torch.equal(o1, o2)
     finally:
         m.set_precision("fp32")
 

@@ -10,7 +10,7 @@ from fami_pose_b200 import ops
 dev = "cuda"
 PEAK = 6650.0
 try:
-    PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbps"]
+    PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
     pass
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
