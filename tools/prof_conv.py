@@ -14,6 +14,7 @@ dt = ops.act_dtype()
 N = 160
 shapes = {"c48": (48, 96, 72), "c96": (96, 48, 36), "c192": (192, 24, 18), "c384": (384, 12, 9)}
 ev = lambda: torch.cuda.Event(enable_timing=True)
+_ng = torch.no_grad(); _ng.__enter__()   # inference launches (fp32 / tf32 storage would otherwise take the autograd path)
 for name, (C, H, W) in shapes.items():
     if which not in ("all", name):
         continue
