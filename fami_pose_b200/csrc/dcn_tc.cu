@@ -17,7 +17,7 @@
 //     Samples outside the staged window are resolved per tap through a bounds-checked global path;
 //   * one warp (also an epilogue warp) issues tcgen05.mma (M=128, N=Cout, K=C per tap) against the weights resident in shared
 //     memory, accumulating the nine taps in TMEM (double buffered across tiles);
-//   * 4 epilogue warps add the bias and store the tile (coalesced, through shared-memory staging).
+//   * 4 epilogue warps add the bias and store the tile (a lane owns a pixel row: whole 32-byte sectors per store).
 // The [C*9, B*H*W] column buffer of the reference never exists; HBM traffic is the algorithmic minimum:
 // offsets+masks (4*27*G B/pixel) + x (~once, via L2) + out.
 #include <stdlib.h>
@@ -44,7 +44,10 @@ constexpr int kGatherThreads = 32 * kGatherWarps;
 constexpr int kDcnEpiWarps = 4;
 constexpr int kDcnThreads = kGatherThreads + 32 * kDcnEpiWarps;   // 640: 20 warps x 96 registers fill the register file
                                                                      // (the first epilogue warp is also the TMA + MMA issuer)
-constexpr int kAStages = 3;               // tap t -> A stage t % 3
+#ifndef FAMI_DCN_ASTAGES
+#define FAMI_DCN_ASTAGES 2
+#endif
+constexpr int kAStages = FAMI_DCN_ASTAGES; // A stages (one tap each), walked round-robin by a running tap counter
 constexpr int kATile = 128 * 128;          // bytes per A stage
 constexpr int kBarSlots = 13 + 2 * kAStages; // mbarriers of the kernel (8 B each); the TMEM slot and the bias table follow
 constexpr uint32_t kMagicBits = 0x4B400000u;   // 1.5 * 2^23: adding it with round-down leaves floor(v) in the low mantissa bits
@@ -71,6 +74,8 @@ struct DcnTcParams {
   int64_t om_tap_stride;            // floats between taps in the blocked layout = tiles * 128 * 3G
   uint32_t win_bytes, w_tile_bytes, ab_format;
   int trace;
+  int ablate;                       // FAMI_DCN_ABLATE (timing experiments, results wrong): 1 no epilogue stores, 2 no window
+                                    // reload, 4 no corner loads / blends, 8 no far path, 16 no offset loads; 32 (results right): issuer's epilogue not deferred
   const float* om;                  // layout 1: [B*H*W][om_pitch], per pixel [9 taps][dy(G) | dx(G) | mask(G)]
   const void* x;                    // TH NHWC (global fallback path)
   const float* bias;
@@ -144,7 +149,6 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen0 + 8 * kBarSlots);
   float* s_scale = reinterpret_cast<float*>(gen0 + 8 * (kBarSlots + 3));   // 16-byte aligned (float4 reads)
   float* s_shift = s_scale + p.BN;
-  const uint32_t stage_u32 = (bar0 + 8u * (kBarSlots + 3) + (uint32_t)p.BN * 8u + 15u) & ~15u;   // epilogue staging
   fill_scale_shift(s_scale, s_shift, nullptr, p.bias, p.Cout, p.BN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -236,6 +240,11 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       return t;
     };
     auto load_tap = [&](const TileRef& t, int tap, Om& o) {
+      if (p.ablate & 16) {
+#pragma unroll
+        for (int j = 0; j < NIT; ++j) { o.dy[j] = 0.25f; o.dx[j] = 0.25f; o.mk[j] = 1.f; }
+        return;
+      }
       if (p.om_blocked) {
         const float* q = t.po + tap * p.om_tap_stride;
 #pragma unroll
@@ -265,12 +274,16 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     };
 
     // one tap of one unit: NIT samples of this lane into A stage kc
-    auto do_tap = [&](const TileRef& t, const Om& o, int kr, float my, float mx, int kc, int useq) {
-      const uint32_t u = (uint32_t)(useq * 3 + kr);           // use index of stage kc
+    auto do_tap = [&](const TileRef& t, const Om& o, int kr, float my, float mx, int kc, uint32_t tcount) {
+      const uint32_t stage = tcount % kAStages, u = tcount / kAStages;   // A stage of this tap and its use index
+      const uint32_t st_off = stage * kATile;
       bool far = false;                          // any sample of this lane outside the staged window
       constexpr int NB = (NIT % 2) ? NIT : 2;    // samples per batch (8 or 12 corner loads in flight per lane); NB divides NIT
       static_assert(NIT % NB == 0, "batch size must divide the iteration count");
       uint2 pk[NIT];
+#pragma unroll
+      for (int j = 0; j < NIT; ++j) pk[j] = make_uint2(0u, 0u);
+      if (!(p.ablate & 4))
 #pragma unroll
       for (int j0 = 0; j0 < NIT; j0 += NB) {
         uint32_t a00[NB], a10[NB];
@@ -320,12 +333,12 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         }
       }
       // the A stage is needed only now: the wait for the MMA that last read it hides behind the loads and blends above
-      mbar_wait(a_empty(kc), (u & 1u) ^ 1u);
+      mbar_wait(a_empty(stage), (u & 1u) ^ 1u);
 #pragma unroll
-      for (int j = 0; j < NIT; ++j) sts64(a_st[j] + (uint32_t)(kc * kATile), pk[j]);
+      for (int j = 0; j < NIT; ++j) sts64(a_st[j] + st_off, pk[j]);
       // large offsets: bounds-checked global corners, fp32 blend.  Kept out of the sample loop and entered once per tap
       // by the whole warp, so the dependent global loads of all far samples of the tap are in flight together.
-      if (__any_sync(0xffffffffu, far)) {
+      if (__any_sync(0xffffffffu, far) && !(p.ablate & 8)) {
         uint32_t slow = 0;
 #pragma unroll
         for (int j = 0; j < NIT; ++j) {
@@ -363,16 +376,16 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             pk2.y = f2_to_h2<TH>(smk * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z),
                                  smk * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w));
           }
-          sts64(sa + (uint32_t)(kc * kATile), pk2);
+          sts64(sa + st_off, pk2);
         }
         __syncwarp();
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_full(kc));   // one arrival per warp
+      if (lane == 0) mbar_arrive(a_full(stage));   // one arrival per warp
     };
 
-    uint32_t wph = 0, fph = 0;
+    uint32_t wph = 0, fph = 0, tcount = 0;       // tcount: taps gathered so far (all units)
     const int my_tiles = ((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int n_units = my_tiles * NP;
     TileRef cur = unit_ref(0), nxt = unit_ref(1);
@@ -381,18 +394,21 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     load_tap(cur, 1, o1);
     for (int useq = 0; useq < n_units; ++useq) {
       if (threadIdx.x == 0) dtrace(p.trace, useq, 0);
-      mbar_wait(win_full, wph);
-      wph ^= 1u;
+      if (!(p.ablate & 2) || useq == 0) {
+        mbar_wait(win_full, wph);
+        wph ^= 1u;
+      }
       if (threadIdx.x == 0) dtrace(p.trace, useq, 1);
       float my = my0;
 #pragma unroll 1
       for (int kr = 0; kr < 3; ++kr, my += fd) {
         load_ahead(cur, nxt, kr * 3 + 0, o2);
-        do_tap(cur, o0, kr, my, mx0, 0, useq);
+        do_tap(cur, o0, kr, my, mx0, 0, tcount);
         load_ahead(cur, nxt, kr * 3 + 1, o0);
-        do_tap(cur, o1, kr, my, mx1, 1, useq);
+        do_tap(cur, o1, kr, my, mx1, 1, tcount + 1);
         load_ahead(cur, nxt, kr * 3 + 2, o1);
-        do_tap(cur, o2, kr, my, mx2, 2, useq);
+        do_tap(cur, o2, kr, my, mx2, 2, tcount + 2);
+        tcount += 3;
         if (threadIdx.x == 0) dtrace(p.trace, useq, 2 + kr);
       }
       __syncwarp();
@@ -402,7 +418,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         // not from the MMA warp, which is still draining the last taps)
         mbar_wait(win_free, fph);
         fph ^= 1u;
-        if (lane == 0 && useq + 1 < n_units) {
+        if (lane == 0 && useq + 1 < n_units && !(p.ablate & 2)) {
           int nb, ny0, nx0;
           tile_origin(nxt.tile, nb, ny0, nx0);
           mbar_arrive_expect_tx(win_full, p.win_bytes);
@@ -417,24 +433,63 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     // ===================== epilogue warps (the first one is also the TMA + MMA issuer) =====================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    EpiArgs ea;
-    ea.s_scale = bar0 + 8u * (kBarSlots + 3); ea.s_shift = ea.s_scale + (uint32_t)p.BN * 4u; ea.res = nullptr; ea.y = p.out;
-    ea.Cout = p.Cout; ea.BN = p.BN; ea.ch_base = 0; ea.out_pitch = p.out_pitch; ea.res_pitch = 0;
-    ea.out_f32 = p.out_f32; ea.relu = 0; ea.vec_ok = p.vec_ok; ea.up = 1; ea.Wout = p.W;
-    ea.spitch = 128 + 16;
-    const uint32_t epi_stage = stage_u32 + (uint32_t)((warp - kGatherWarps) * 32 * ea.spitch);
+    // Direct epilogue: a lane owns one accumulator row (pixel) and stores its Cout channels itself, 16 at a time (32 / 64
+    // contiguous bytes per lane and chunk: whole sectors).  The four epilogue warps have a whole tile time to move 12 KB, so
+    // the staged routine of the conv kernels buys nothing here, and its 18 KB of staging pay for a window with 6 px of reach.
+    const uint32_t s_shift_u32 = bar0 + 8u * (kBarSlots + 3) + (uint32_t)p.BN * 4u;
     auto epi_tile = [&](int tile, int it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       int b, y0, x0;
       tile_origin(tile, b, y0, x0);
       const int y = y0 + (row >> 3), x = x0 + (row & 7);
-      const bool valid = y < p.H && x < p.W;
-      const int pix = valid ? (b * p.H + y) * p.W + x : 0;
+      const bool valid = y < p.H && x < p.W && !(p.ablate & 1);
+      const int64_t pix = valid ? ((int64_t)b * p.H + y) * p.W + x : 0;
       mbar_wait(tfull(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(quarter * 32) << 16);
-      epilogue_rows<TH>(ea, t_addr, 0, p.BN, valid, pix, epi_stage, lane);
+      for (int c0 = 0; c0 < p.Cout; c0 += 16) {          // warp-uniform
+        uint32_t v[16];
+        tmem_ld16(t_addr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        float o[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 sh = lds128f(s_shift_u32 + (uint32_t)(c0 + 4 * q) * 4u);     // bias (0 beyond Cout)
+          o[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + sh.x;
+          o[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + sh.y;
+          o[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + sh.z;
+          o[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + sh.w;
+        }
+        const int nc = p.Cout - c0 < 16 ? p.Cout - c0 : 16;
+        if (valid) {          // (no early exit: the TMEM loads above are warp-collective)
+          if (p.out_f32) {
+            float* dst = reinterpret_cast<float*>(p.out) + pix * p.out_pitch + c0;
+            if (p.vec_ok && nc == 16) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(dst)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 16; ++c)
+                if (c < nc) dst[c] = o[c];
+            }
+          } else {
+            TH* dst = reinterpret_cast<TH*>(p.out) + pix * p.out_pitch + c0;
+            if (p.vec_ok && nc == 16) {
+              uint4 w0, w1;
+              w0.x = f2_to_h2<TH>(o[0], o[1]); w0.y = f2_to_h2<TH>(o[2], o[3]); w0.z = f2_to_h2<TH>(o[4], o[5]); w0.w = f2_to_h2<TH>(o[6], o[7]);
+              w1.x = f2_to_h2<TH>(o[8], o[9]); w1.y = f2_to_h2<TH>(o[10], o[11]); w1.z = f2_to_h2<TH>(o[12], o[13]); w1.w = f2_to_h2<TH>(o[14], o[15]);
+              reinterpret_cast<uint4*>(dst)[0] = w0;
+              reinterpret_cast<uint4*>(dst)[1] = w1;
+            } else {
+#pragma unroll
+              for (int c = 0; c < 16; ++c)
+                if (c < nc) dst[c] = from_f<TH>(o[c]);
+            }
+          }
+        }
+        __syncwarp();
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(acc));
@@ -515,8 +570,8 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       const uint32_t w_step = p.w_tile_bytes >> 4;
       int stage = 0;
       uint32_t aph = 0;
-      int it = 0, wid = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      int it = 0, wid = 0, last_tile = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; last_tile = tile, tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty(acc), acc_phase ^ 1u);
@@ -525,6 +580,9 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         for (int pass = 0; pass < NP; ++pass) {
           uint32_t w_lo = w_lo0;
           for (int tap = 0; tap < 9; ++tap, w_lo += w_step) {
+            // this warp's quarter of the PREVIOUS tile's epilogue, once the first two taps of this tile are issued: the wait
+            // for the previous tile's last MMAs and the drain then overlap the gather instead of holding up taps 0 and 1
+            if (pass == 0 && tap == 2 && it > 0 && !(p.ablate & 32)) epi_tile(last_tile, it - 1);
             mbar_wait(a_full(stage), aph);
             int slot = 0;
             if (NW) {
@@ -555,10 +613,10 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           tile_origin(next, b, y0, x0);
           prefetch_om(b, y0, x0);
         }
-        // this warp's quarter of the tile's epilogue: by the time it is drained the gather warps are at most three taps
-        // (the A stages) into the next tile
-        epi_tile(tile, it);
+        if (p.ablate & 32) epi_tile(tile, it);          // A/B: epilogue quarter at the end of its own tile
       }
+      // (this warp's quarter of a tile's epilogue runs after the first taps of the NEXT tile have been issued -- see above)
+      if (it > 0 && !(p.ablate & 32)) epi_tile(last_tile, it - 1);
     } else {
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) epi_tile(tile, it);
@@ -581,16 +639,16 @@ static int dcn_tc_wstream(const fami_dcn_desc* d) {
   const int BN = ((d->Cout + 15) / 16) * 16;
   return BN > 128 ? 2 : 3;
 }
-// shared-memory footprint for a window radius R; the launcher takes the largest R <= dil + 5 that fits
+// shared-memory footprint for a window radius R; the launcher takes the largest R <= dil + 7 that fits
 static size_t dcn_tc_smem(const fami_dcn_desc* d, int R) {
   const int BN = ((d->Cout + 15) / 16) * 16;
   const int NW = dcn_tc_wstream(d);
   const size_t win = ((size_t)(kTH + 2 * R) * (kTW + 2 * R) * 128 + 1023) & ~(size_t)1023;
-  return win + kAStages * kATile + (size_t)(NW ? NW : 9) * BN * 128 + 1024 + 8 * (kBarSlots + 3) + 16 + (size_t)BN * 8 +
-         (size_t)kDcnEpiWarps * 32 * (128 + 16);
+  return win + kAStages * kATile + (size_t)(NW ? NW : 9) * BN * 128 + 1024 + 8 * (kBarSlots + 3) + 16 + (size_t)BN * 8;
 }
 static int dcn_tc_radius(const fami_dcn_desc* d) {
-  for (int R = d->dil + 5; R >= d->dil + 2; --R)
+  static const int reach = getenv("FAMI_DCN_REACH") ? atoi(getenv("FAMI_DCN_REACH")) : 7;   // A/B switch, default 7 px
+  for (int R = d->dil + reach; R >= d->dil + 2; --R)
     if (dcn_tc_smem(d, R) <= 227 * 1024) return R;
   return -1;
 }
@@ -615,7 +673,7 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
   DcnTcParams p;
   memset(&p, 0, sizeof(p));
   p.B = d->B; p.H = d->H; p.W = d->W; p.C = d->C; p.Cout = d->Cout; p.G = d->G; p.d = d->dil;
-  p.R = dcn_tc_radius(d);   // dilation reach + up to 5 px of offset (2.5 sigma of the sigma = 2 px regime); beyond -> global path
+  p.R = dcn_tc_radius(d);   // dilation reach + up to 7 px of offset (3.5 sigma of the sigma = 2 px regime); beyond -> global path
   FAMI_CHECK_ARG(p.R > 0, "dcn_tc: filter and window do not fit in shared memory");
   p.WH = kTH + 2 * p.R; p.WW = kTW + 2 * p.R;
   p.tiles_x = (d->W + kTW - 1) / kTW; p.tiles_y = (d->H + kTH - 1) / kTH;
@@ -635,6 +693,7 @@ int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
   p.om_tap_stride = (int64_t)p.total_tiles * 128 * 3 * d->G;
   static const bool trace_on = getenv("FAMI_DCN_TRACE") != nullptr;
   p.trace = trace_on ? atoi(getenv("FAMI_DCN_TRACE")) : 0;
+  p.ablate = getenv("FAMI_DCN_ABLATE") ? atoi(getenv("FAMI_DCN_ABLATE")) : 0;
 
   const CUtensorMapDataType tm_dtype = d->dtype == FAMI_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap tmX, tmW;

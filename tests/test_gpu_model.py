@@ -353,24 +353,34 @@ def test_hrnet_w32_half(golden_dir, prec, tol):
         fp.set_precision("fp32")
 
 
-def test_fp16_batchnorm_train_mode(golden_dir):
-    """train-mode BN on the tensor-core arm (fp32 raw conv output + fami_bn_stats).  At B=1 the
-    global-offset head normalises with batch statistics over as few as 9 samples (3x3 map), which
-    amplifies operand rounding into the warp translation; heatmaps have magnitude ~3.  Documented
-    band for this ill-conditioned case: 1e-1 max-abs (fp32 arm: 6e-5, see the fp32 test above)."""
+def test_batchnorm_train_mode_tensor_core_arms_conditioning_normalised():
+    """train-mode BatchNorm (batch statistics in every one of the ~300 BN layers) on the tensor-core arms, B=2, against the
+    oracle run with bn_train=True on the same clip.  With batch statistics this randomly initialised network amplifies ANY
+    rounding ~50-100x compared with eval mode -- measured on the exact-fp32 arm itself: 1.3e-6 (eval) -> 6.4e-5 (train);
+    tf32 5.9e-4 -> 5.5e-2; fp16 1.5e-3 -> 5.6e-2; independent of the batch size (B = 1, 2, 4: tools/bn_train_errors.py), so it
+    is the conditioning of the function, not of a small-sample statistic.  The band is therefore stated relative to the
+    fp32 arm's own error on the same clip: the tensor-core arms must stay within the ratio of the eval-mode errors
+    (tf32 / fp32 ~ 450, fp16 / fp32 ~ 1150; bands 1000 and 2500), and inside 1e-1 absolute on heatmaps of magnitude ~2."""
     import fami_pose_b200 as fp
-    gold = np.load(os.path.join(golden_dir, "model_reference.npz"))
     m, sd = _build("train")
     m.train()
-    fp.set_precision("fp16")
+    kf, sup, tgt, tw = fo.synthetic_clip(2, seed=SEED + 5)
+    with torch.no_grad():
+        rhm, rkf, _ = fo.FunctionalFami(sd, bn_train=True).alignment(kf, sup, with_mi=True)
+    errs = {}
     try:
-        kf, sup, tgt, tw = fo.synthetic_clip(1, seed=SEED)
-        with torch.no_grad():
-            hm, kfhm, mi = m(kf.to(DEV), sup.to(DEV))
-        e1 = float(np.abs(hm.cpu().numpy() - gold["v15_bntrain_final_hm"]).max())
-        e2 = float(np.abs(kfhm.cpu().numpy() - gold["v15_bntrain_kf_hm"]).max())
-        print("fp16 bn-train max-abs err final %.3e kf %.3e" % (e1, e2))
-        assert e1 <= 1e-1 and e2 <= 1e-1
+        for arm in ("fp32", "tf32", "fp16"):
+            fp.set_precision(arm)
+            ma, _ = _build("train")          # fresh running statistics per arm
+            ma.train()
+            fp.set_precision(arm)
+            with torch.no_grad():
+                hm, kfhm, mi = ma(kf.to(DEV), sup.to(DEV))
+            errs[arm] = max(float((hm.float().cpu() - rhm).abs().max()), float((kfhm.float().cpu() - rkf).abs().max()))
+        print("bn-train max-abs err", errs)
+        assert errs["fp32"] <= 1e-3                      # north_star's fp32 tier, train mode included
+        assert errs["tf32"] <= 1000 * errs["fp32"] and errs["tf32"] <= 1e-1
+        assert errs["fp16"] <= 2500 * errs["fp32"] and errs["fp16"] <= 1e-1
     finally:
         fp.set_precision("fp32")
 
