@@ -75,7 +75,7 @@ struct DcnTcParams {
   uint32_t win_bytes, w_tile_bytes, ab_format;
   int trace;
   int ablate;                       // FAMI_DCN_ABLATE (timing experiments, results wrong): 1 no epilogue stores, 2 no window
-                                    // reload, 4 no corner loads / blends, 8 no far path, 16 no offset loads; 32 (results right): issuer's epilogue not deferred
+                                    // reload, 4 no corner loads / blends, 8 no far path, 16 no offset loads; 32 (results right): issuer's epilogue not deferred; 64 no fence.proxy.async
   const float* om;                  // layout 1: [B*H*W][om_pitch], per pixel [9 taps][dy(G) | dx(G) | mask(G)]
   const void* x;                    // TH NHWC (global fallback path)
   const float* bias;
@@ -380,7 +380,8 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         }
         __syncwarp();
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
+      if (!(p.ablate & 64))
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full(stage));   // one arrival per warp
     };
