@@ -378,7 +378,7 @@ int fami_bn_finalize(const double* stats, const float* gamma, const float* beta,
 int fami_bn_apply_act(const void* x, int x_dtype, int x_pitch, const float* scale, const float* shift,
                       const void* residual, int res_pitch, void* y, int y_pitch, int dtype, int N, int Ho, int Wo, int C,
                       int up, int relu, void* stream) {
-  FAMI_CHECK_ARG(x && scale && shift && y, "fami_bn_apply_act: null pointer");
+  FAMI_CHECK_ARG(x && y && ((scale && shift) || (!scale && !shift)), "fami_bn_apply_act: null pointer");
   FAMI_CHECK_ARG(valid_dtype(dtype) && valid_dtype(x_dtype), "fami_bn_apply_act: bad dtype");
   FAMI_CHECK_ARG(up == 1 || up == 2 || up == 4 || up == 8, "fami_bn_apply_act: up=%d", up);
   return bn_apply_act_launch(x, x_dtype, x_pitch, scale, shift, residual, res_pitch, y, y_pitch, dtype, N, Ho, Wo, C, up,

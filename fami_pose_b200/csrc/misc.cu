@@ -466,10 +466,43 @@ int bn_finalize_launch(const double* stats, const float* gamma, const float* bet
   FAMI_CHECK_LAUNCH("bn_finalize");
   return 0;
 }
+// plain storage cast fp32 -> 16 bit of a dense or pitched NHWC activation (fami_bn_apply_act with scale == shift == null):
+// 8 channels per thread and iteration (two 16-byte loads in flight, one 16-byte store), grid-stride
+template <typename T>
+__global__ void __launch_bounds__(256) cast_f32_to_half_kernel(const float* __restrict__ x, int xp, T* __restrict__ y, int yp,
+                                                               int64_t rows, int C) {
+  const int c8 = C >> 3;
+  const int64_t tot = rows * c8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c8;
+    const int c = (int)(i - r * c8) << 3;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * xp + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(x + r * xp + c + 4));
+    T o[8] = {from_f<T>(a.x), from_f<T>(a.y), from_f<T>(a.z), from_f<T>(a.w), from_f<T>(b.x), from_f<T>(b.y), from_f<T>(b.z), from_f<T>(b.w)};
+    *reinterpret_cast<uint4*>(y + r * yp + c) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
 int bn_apply_act_launch(const void* x, int xdt, int xp, const float* scale, const float* shift, const void* res, int rp,
                         void* y, int yp, int dt, int N, int Ho, int Wo, int C, int up, int relu, cudaStream_t st) {
   int64_t tot = (int64_t)N * Ho * Wo * C;
   const int esz = dt == FAMI_F32 ? 4 : 2;
+  if (!scale && !shift) {
+    // identity affine = storage cast; the fast path covers what the deformable convolutions of the tf32 arm need
+    FAMI_CHECK_ARG(!res && up == 1 && !relu, "fami_bn_apply_act: null scale / shift means a plain cast (no residual, up, relu)");
+    FAMI_CHECK_ARG(xdt == FAMI_F32 && dt != FAMI_F32 && C % 8 == 0 && xp % 4 == 0 && yp % 8 == 0 &&
+                       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                   "fami_bn_apply_act: the cast path takes fp32 -> 16 bit, C %% 8 == 0, 16-byte aligned rows");
+    const int64_t rows = (int64_t)N * Ho * Wo;
+    const int64_t work = rows * (C >> 3);
+    int grid = (int)((work + 255) / 256);
+    const int cap = num_sms() * 16;
+    if (grid > cap) grid = cap;
+    if (dt == FAMI_F16) cast_f32_to_half_kernel<__half><<<grid, 256, 0, st>>>((const float*)x, xp, (__half*)y, yp, rows, C);
+    else cast_f32_to_half_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const float*)x, xp, (__nv_bfloat16*)y, yp, rows, C);
+    FAMI_CHECK_LAUNCH("cast_f32_to_half");
+    return 0;
+  }
   const bool vec = xdt == FAMI_F32 && C % 4 == 0 && xp % 4 == 0 && yp % 4 == 0 && (!res || rp % 4 == 0) &&
                    (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & (4 * esz - 1)) == 0 &&
                    (!res || (reinterpret_cast<uintptr_t>(res) & (4 * esz - 1)) == 0) &&

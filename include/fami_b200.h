@@ -146,7 +146,8 @@ int fami_bn_bwd(const float* x, int x_pitch, const float* grad_y, int gy_pitch, 
 /* train-mode BatchNorm (batch statistics over N*H*W, biased variance, eps, momentum update):
  * nn.BatchNorm2d(momentum=0.1) as used at basic_model.py:29,39 and hrnet.py:53,106,124,137.
  * fami_bn_finalize turns (sum, sumsq) into scale/shift and updates running stats;
- * fami_bn_apply_act is y = act(scale*x + shift + residual) with the same `up` write semantics.  */
+ * fami_bn_apply_act is y = act(scale*x + shift + residual) with the same `up` write semantics; scale == shift == null
+ * is a plain fp32 -> 16-bit storage cast (no residual, up = 1, no relu).  */
 int fami_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
                      float* running_var, float* scale, float* shift, float* save_mean,
                      float* save_invstd, int C, int64_t count, float eps, float momentum, void* stream);

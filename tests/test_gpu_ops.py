@@ -154,6 +154,26 @@ def test_bn_stats_large_mean(C, dtype):
     assert float(((got_var - ref_var) / ref_var).abs().max()) <= 1e-3
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_cast_nhwc_fast_path_is_round_to_nearest(dtype):
+    """ops.cast_nhwc (fami_bn_apply_act with null scale / shift: the plain-cast kernel the tf32 arm's deformable convolutions
+    use) equals torch's round-to-nearest conversion bit for bit, for a dense tensor, a channel slice of a wider buffer
+    (pitch > C) and a channel count that falls back to the affine kernel (C % 8 != 0)."""
+    fp()
+    from fami_pose_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    for C, wide in ((48, None), (48, 96), (20, None)):
+        x = torch.randn(3, C, 17, 9, generator=g) * 3
+        xd = ops.to_nhwc(x.to(DEV), torch.float32)
+        if wide:
+            buf = ops.empty_nhwc(3, wide, 17, 9, torch.float32, DEV).zero_()
+            buf[:, 24:24 + C].copy_(xd)
+            xd = buf[:, 24:24 + C]
+        out = ops.cast_nhwc(xd, dtype)
+        assert out.dtype == dtype
+        assert torch.equal(ops.to_nchw(out).cpu(), x.to(dtype))
+
+
 def _golden_inputs(name):
     # same generator recipe as tests/golden/make_golden.py::dcn_inputs (kept in sync by test_oracle.py)
     from tests_support import dcn_cases, dcn_inputs
