@@ -30,6 +30,14 @@ __device__ unsigned long long g_dcn_trace[4096];   // [tile it < 16][16 events] 
 
 namespace {
 
+__device__ __forceinline__ void wtrace(int on, uint32_t tcount, int warp, int ev) {
+  // one steady-state pair of taps (taps 3 and 4 of the CTA's 4th tile) seen by every warp of CTA 0
+  if (on && blockIdx.x == 0 && (tcount == 30u || tcount == 31u) && (threadIdx.x & 31) == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_dcn_trace[2048 + (tcount - 30u) * 256 + warp * 8 + ev] = t;
+  }
+}
 __device__ __forceinline__ void dtrace(int on, int it, int ev) {
   if (on && blockIdx.x == 0 && it < 16) {
     unsigned long long t;
@@ -277,6 +285,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     auto do_tap = [&](const TileRef& t, const Om& o, int kr, float my, float mx, int kc, uint32_t tcount) {
       const uint32_t stage = tcount % kAStages, u = tcount / kAStages;   // A stage of this tap and its use index
       const uint32_t st_off = stage * kATile;
+      wtrace(p.trace, tcount, warp, 0);                       // tap starts (offsets of the tap already in registers)
       bool far = false;                          // any sample of this lane outside the staged window
       constexpr int NB = (NIT % 2) ? NIT : 2;    // samples per batch (8 or 12 corner loads in flight per lane); NB divides NIT
       static_assert(NIT % NB == 0, "batch size must divide the iteration count");
@@ -333,7 +342,9 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         }
       }
       // the A stage is needed only now: the wait for the MMA that last read it hides behind the loads and blends above
+      wtrace(p.trace, tcount, warp, 1);                       // loads and blends done
       mbar_wait(a_empty(stage), (u & 1u) ^ 1u);
+      wtrace(p.trace, tcount, warp, 2);                       // A stage free
 #pragma unroll
       for (int j = 0; j < NIT; ++j) sts64(a_st[j] + st_off, pk[j]);
       // large offsets: bounds-checked global corners, fp32 blend.  Kept out of the sample loop and entered once per tap
@@ -380,10 +391,12 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         }
         __syncwarp();
       }
+      wtrace(p.trace, tcount, warp, 3);                       // stores (and far path) done
       if (!(p.ablate & 64))
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full(stage));   // one arrival per warp
+      wtrace(p.trace, tcount, warp, 4);                       // fenced and arrived
     };
 
     uint32_t wph = 0, fph = 0, tcount = 0;       // tcount: taps gathered so far (all units)
@@ -585,6 +598,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             // for the previous tile's last MMAs and the drain then overlap the gather instead of holding up taps 0 and 1
             if (pass == 0 && tap == 2 && it > 0 && !(p.ablate & 32)) epi_tile(last_tile, it - 1);
             mbar_wait(a_full(stage), aph);
+            wtrace(p.trace, (uint32_t)((it * NP + pass) * 9 + tap), 16, 0);    // all sixteen arrivals seen
             int slot = 0;
             if (NW) {
               slot = wid % NW;
@@ -594,6 +608,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             const uint32_t a_lo = sw128_desc_lo(a_u32 + stage * kATile);
             umma_ksteps_n(p.nk, leader, d_tmem, a_lo, NW ? w_lo0 + (uint32_t)slot * w_step : w_lo, idesc, (pass | tap) != 0);
             if (leader) umma_commit(a_empty(stage));
+            wtrace(p.trace, (uint32_t)((it * NP + pass) * 9 + tap), 16, 1);    // MMAs issued, commit issued
             if (NW) {
               if (leader) umma_commit(ws_empty(slot));
               if (wid >= 1 && wid - 1 + NW < w_total) {

@@ -25,3 +25,10 @@ print("tile | start   window ready | kernel row 0 / 1 / 2 gathered (us after win
 for i in range(10):
     print("%3d | %7.2f %7.2f | %s" % (i, (t[i, 0] - t0) / 1e3, (t[i, 1] - t0) / 1e3,
           "  ".join("%5.2f" % ((t[i, 2 + k] - t[i, 1]) / 1e3) for k in range(3))))
+w = buf[2048:2048 + 512].reshape(2, 32, 8).astype(np.int64)
+for k in range(2):
+    base = w[k, :16, 0].min()
+    print("tap %d of tile 3, every gather warp (us after the first warp started the tap): start | loads+blends done | A stage free | stores done | fenced+arrived" % (3 + k))
+    for wp in range(16):
+        print("  warp %2d: %s" % (wp, "  ".join("%6.2f" % ((w[k, wp, e] - base) / 1e3) for e in range(5))))
+    print("  issuer : all arrivals seen %6.2f   MMAs + commit issued %6.2f" % ((w[k, 16, 0] - base) / 1e3, (w[k, 16, 1] - base) / 1e3))
