@@ -31,12 +31,15 @@ __device__ unsigned long long g_dcn_trace[4096];   // [tile it < 16][16 events] 
 namespace {
 
 __device__ __forceinline__ void wtrace(int on, uint32_t tcount, int warp, int ev) {
-  // one steady-state pair of taps (taps 3 and 4 of the CTA's 4th tile) seen by every warp of CTA 0
+  // one steady-state pair of taps (taps 3 and 4 of the CTA's 4th tile) seen by every warp of CTA 0; compiled into the
+  // probes library only (csrc/build.py --probes), the product kernel carries no per-tap instrumentation
+#ifdef FAMI_DEBUG_PROBES
   if (on && blockIdx.x == 0 && (tcount == 30u || tcount == 31u) && (threadIdx.x & 31) == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g_dcn_trace[2048 + (tcount - 30u) * 256 + warp * 8 + ev] = t;
   }
+#endif
 }
 __device__ __forceinline__ void dtrace(int on, int it, int ev) {
   if (on && blockIdx.x == 0 && it < 16) {
