@@ -7,6 +7,8 @@
 //   Linear backward         (feat_global_offset_layers[7..9], Alignment_V15.py:69-71)
 // Stride-1 dgrad is the forward convolution of grad_out with the flipped, transposed filter (pad' =
 // dil*(k-1) - pad): it runs on the forward kernels.  Everything else here is a straightforward SIMT kernel.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fami {
@@ -160,6 +162,97 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
     for (int b = 0; b < 4; ++b) {
       const int ci = cit * 64 + tci * 4 + b;
       if (ci < Cin) atomicAdd(dw + ((int64_t)co * Cin + ci) * taps + tap, acc[a][b]);
+    }
+  }
+}
+
+// Same tile decomposition, double buffered: the (pixels x 64 ci) slab of x at this tap and the (pixels x 64 co) slab of gy
+// of chunk k+1 are in flight (cp.async, 16 bytes per request, zero-filled outside the image / beyond the channel count)
+// while chunk k is multiplied.  The single-buffered kernel above exposed a global round trip per 32 pixels.
+__global__ void __launch_bounds__(256) conv_wgrad_db_kernel(const float* __restrict__ x, int x_pitch,
+                                                            const float* __restrict__ gy, int gy_pitch,
+                                                            float* __restrict__ dw, int N, int H, int W, int Cin, int Cout,
+                                                            int kh, int kw, int stride, int pad, int dil, int Ho, int Wo,
+                                                            int ci_tiles, int co_tiles, int pix_per_block) {
+  __shared__ __align__(16) float xs[2][kWgPix][64];
+  __shared__ __align__(16) float gs[2][kWgPix][64];
+  int tile = blockIdx.x;
+  const int cot = tile % co_tiles; tile /= co_tiles;
+  const int cit = tile % ci_tiles; tile /= ci_tiles;
+  const int tap = tile;
+  const int r = tap / kw, s = tap - r * kw;
+  const int tid = threadIdx.x;
+  const int tci = tid & 15, tco = tid >> 4;
+  const int64_t npix = (int64_t)N * Ho * Wo;
+  const int64_t p0 = (int64_t)blockIdx.y * pix_per_block;
+  const int64_t p1 = p0 + pix_per_block < npix ? p0 + pix_per_block : npix;
+  // this thread stages pixels (tid >> 4) and (tid >> 4) + 16 of a chunk, channels 4 * (tid & 15) .. + 3
+  const int c = (tid & 15) << 2;
+  const int ci = cit * 64 + c, co = cot * 64 + c;
+  auto stage = [&](int buf, int64_t pb) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int pl = (tid >> 4) + 16 * h;
+      const int64_t p = pb + pl;
+      bool okx = false, okg = false;
+      const float* sx = x;
+      const float* sg = gy;
+      if (p < p1) {
+        const int xo = (int)(p % Wo);
+        const int64_t t = p / Wo;
+        const int yo = (int)(t % Ho), n = (int)(t / Ho);
+        const int yi = yo * stride - pad + r * dil, xi = xo * stride - pad + s * dil;
+        if (ci < Cin && yi >= 0 && yi < H && xi >= 0 && xi < W) {
+          okx = true;
+          sx = x + ((int64_t)(n * H + yi) * W + xi) * x_pitch + ci;
+        }
+        if (co < Cout) {
+          okg = true;
+          sg = gy + p * gy_pitch + co;
+        }
+      }
+      cp_async16(&xs[buf][pl][c], sx, okx);
+      cp_async16(&gs[buf][pl][c], sg, okg);
+    }
+    cp_async_commit();
+  };
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  int buf = 0;
+  if (p0 < p1) stage(0, p0);
+  for (int64_t pb = p0; pb < p1; pb += kWgPix) {
+    if (pb + kWgPix < p1) {
+      stage(buf ^ 1, pb + kWgPix);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+#pragma unroll
+    for (int pl = 0; pl < kWgPix; ++pl) {
+      const float4 xv = *reinterpret_cast<const float4*>(&xs[buf][pl][tci * 4]);
+      const float4 gv = *reinterpret_cast<const float4*>(&gs[buf][pl][tco * 4]);
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ga[a], xa[b], acc[a][b]);
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+  const int taps = kh * kw;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int oc = cot * 64 + tco * 4 + a;
+    if (oc >= Cout) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int ic = cit * 64 + tci * 4 + b;
+      if (ic < Cin) atomicAdd(dw + ((int64_t)oc * Cin + ic) * taps + tap, acc[a][b]);
     }
   }
 }
@@ -464,7 +557,11 @@ int conv_wgrad_launch(const fami_conv_desc* d, const float* x, const float* gy, 
   dim3 grid(tiles, splits);
   const bool vec = d->Cin % 4 == 0 && d->Cout % 4 == 0 && d->in_pitch % 4 == 0 && d->out_pitch % 4 == 0 &&
                    (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(gy) & 15) == 0;
-  if (vec)
+  static const bool single = getenv("FAMI_WGRAD_SINGLE") != nullptr;     // A/B: the single-buffered kernel
+  if (vec && !single)
+    conv_wgrad_db_kernel<<<grid, 256, 0, st>>>(x, d->in_pitch, gy, d->out_pitch, dw, d->N, d->H, d->W, d->Cin, d->Cout,
+                                               d->kh, d->kw, d->stride, d->pad, d->dil, d->Ho, d->Wo, ci_tiles, co_tiles, (int)per);
+  else if (vec)
     conv_wgrad_kernel<true><<<grid, 256, 0, st>>>(x, d->in_pitch, gy, d->out_pitch, dw, d->N, d->H, d->W, d->Cin, d->Cout,
                                                   d->kh, d->kw, d->stride, d->pad, d->dil, d->Ho, d->Wo, ci_tiles, co_tiles,
                                                   (int)per);
