@@ -50,7 +50,11 @@ __device__ __forceinline__ void dtrace(int on, int it, int ev) {
 }
 
 constexpr int kTH = 16, kTW = 8;            // output tile (pixels): 128 = one UMMA M tile
-constexpr int kGatherWarps = kTH;         // gather warp w owns image row w of the tile
+#ifndef FAMI_DCN_RPW
+#define FAMI_DCN_RPW 1
+#endif
+constexpr int kRPW = FAMI_DCN_RPW;        // tile rows per gather warp
+constexpr int kGatherWarps = kTH / kRPW;  // gather warp w owns image rows kRPW*w .. kRPW*w + kRPW-1 of the tile
 constexpr int kGatherThreads = 32 * kGatherWarps;
 constexpr int kDcnEpiWarps = 4;
 constexpr int kDcnThreads = kGatherThreads + 32 * kDcnEpiWarps;   // 640: 20 warps x 96 registers fill the register file
@@ -194,11 +198,12 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 
   if (warp < kGatherWarps) {
     // ===================== gather warps =====================
-    constexpr int NIT = LaneMap<kG>::NIT;
+    constexpr int NIR = LaneMap<kG>::NIT;                  // iterations per tile row
+    constexpr int NIT = kRPW * NIR;                        // iterations per tap of this warp: j = row * NIR + jj
     typedef typename H2<TH>::t h2;
     typedef OmRegs<NIT> Om;
     const TH* xg = reinterpret_cast<const TH*>(p.x);
-    const int ry = warp;                                   // image row of the tile
+    const int ry = warp * kRPW;                            // first image row of the tile owned by this warp
     const uint32_t rowpitch = (uint32_t)p.WW * 128u;
     const uint32_t ylim = (uint32_t)(p.WH - 1), xlim = (uint32_t)(p.WW - 1);
     const uint32_t win_safe = win_u32;
@@ -211,12 +216,12 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     int pixj[NIT], gj[NIT];
 #pragma unroll
     for (int j = 0; j < NIT; ++j) {
-      const int sidx = 32 * j + lane;
+      const int rj = j / NIR, sidx = 32 * (j - rj * NIR) + lane;      // row within the warp, sample within the row
       pixj[j] = sidx / kG;
       gj[j] = sidx - pixj[j] * kG;
-      kaddr[j] = win_u32 + (uint32_t)(gj[j] * 8 + pixj[j] * 128) - kMagicBits * rowpitch - kMagicBits * 128u;
+      kaddr[j] = win_u32 + (uint32_t)(gj[j] * 8 + pixj[j] * 128) + (uint32_t)rj * rowpitch - kMagicBits * rowpitch - kMagicBits * 128u;
       xbias[j] = kMagicBits - (uint32_t)pixj[j];
-      a_st[j] = a_u32 + (uint32_t)((ry * kTW + pixj[j]) * 128) + ((uint32_t)(((gj[j] >> 1) ^ pixj[j]) << 4) | ((uint32_t)(gj[j] & 1) << 3));
+      a_st[j] = a_u32 + (uint32_t)(((ry + rj) * kTW + pixj[j]) * 128) + ((uint32_t)(((gj[j] >> 1) ^ pixj[j]) << 4) | ((uint32_t)(gj[j] & 1) << 3));
     }
     const float fd = (float)p.d;
     const float my0 = kMagic + (float)(ry + p.R - p.d);     // + kr * d per kernel row
@@ -239,7 +244,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       const int y = y0 + ry;
 #pragma unroll
       for (int j = 0; j < NIT; ++j)
-        if (y < p.H && x0 + pixj[j] < p.W) t.vmask |= 1u << j;
+        if (y + j / NIR < p.H && x0 + pixj[j] < p.W) t.vmask |= 1u << j;
       if (p.om_blocked) {
         // [tap][tile][row 16][dy | dx | mask][pixel 8][group G]; one pass: sample s of iteration j at float 32 j + lane of
         // its run; passes (16 groups each): lanes 0-15 / 16-31 are pixels 2j / 2j+1, groups 16 pass .. 16 pass + 15
@@ -261,7 +266,8 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < NIT; ++j) {
           const bool v = (t.vmask >> j) & 1u;
-          const int jo = (kG == 16) ? 2 * j * Gt : 32 * j;
+          const int rj = j / NIR, jj = j - rj * NIR;
+          const int jo = rj * (3 * 8 * Gt) + ((kG == 16) ? 2 * jj * Gt : 32 * jj);
           o.dy[j] = v ? ldg_stream(q + jo) : 0.f;
           o.dx[j] = v ? ldg_stream(q + 8 * Gt + jo) : 0.f;
           o.mk[j] = v ? ldg_stream(q + 16 * Gt + jo) : 0.f;
@@ -271,7 +277,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < NIT; ++j) {
           const bool v = (t.vmask >> j) & 1u;
-          const float* qj = q + (int64_t)pixj[j] * p.om_pitch + gj[j];
+          const float* qj = q + ((int64_t)(j / NIR) * p.W + pixj[j]) * p.om_pitch + gj[j];
           o.dy[j] = v ? __ldg(qj) : 0.f;
           o.dx[j] = v ? __ldg(qj + Gt) : 0.f;
           o.mk[j] = v ? __ldg(qj + 2 * Gt) : 0.f;
@@ -290,7 +296,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       const uint32_t st_off = stage * kATile;
       wtrace(p.trace, tcount, warp, 0);                       // tap starts (offsets of the tap already in registers)
       bool far = false;                          // any sample of this lane outside the staged window
-      constexpr int NB = (NIT % 2) ? NIT : 2;    // samples per batch (8 or 12 corner loads in flight per lane); NB divides NIT
+      constexpr int NB = (NIR % 2) ? NIR : 2;    // samples per batch (8 or 12 corner loads in flight per lane); NB divides NIT
       static_assert(NIT % NB == 0, "batch size must divide the iteration count");
       uint2 pk[NIT];
 #pragma unroll
@@ -308,7 +314,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           const float ty = __fadd_rd(dy, my), tx = __fadd_rd(dx, mx);
           const float ly = dy - (ty - my), lx = dx - (tx - mx);
           const uint32_t iyb = __float_as_uint(ty), ixb = __float_as_uint(tx);
-          const bool in = (iyb - kMagicBits) < ylim && (ixb - xbias[j]) < xlim;
+          const bool in = (iyb - (kMagicBits - (uint32_t)(j / NIR))) < ylim && (ixb - xbias[j]) < xlim;
           const float wb = mk * ly, wt = mk - wb;          // mask * (ly | 1 - ly)
           const float w4f = wb * lx, w3f = wb - w4f, w2f = wt * lx, w1f = wt - w2f;
           w12[jb] = H2<TH>::pack(w1f, w2f);
@@ -357,7 +363,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < NIT; ++j) {
           const uint32_t iyb = __float_as_uint(__fadd_rd(o.dy[j], my)), ixb = __float_as_uint(__fadd_rd(o.dx[j], mx));
-          if (!((iyb - kMagicBits) < ylim && (ixb - xbias[j]) < xlim)) slow |= 1u << j;
+          if (!((iyb - (kMagicBits - (uint32_t)(j / NIR))) < ylim && (ixb - xbias[j]) < xlim)) slow |= 1u << j;
         }
         while (slow) {
           const int j = __ffs((int)slow) - 1;
@@ -370,7 +376,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             if (jj == j) { sdy = o.dy[jj]; sdx = o.dx[jj]; smk = o.mk[jj]; spix = pixj[jj]; g = gj[jj]; sa = a_st[jj]; }
           int tb, ty0, tx0;
           tile_origin(t.tile, tb, ty0, tx0);
-          const int y = ty0 + ry, x = tx0 + spix;
+          const int y = ty0 + ry + j / NIR, x = tx0 + spix;
           const float py = (float)(y - p.d + kr * p.d) + sdy;
           const float px = (float)(x - p.d + kc * p.d) + sdx;
           uint2 pk2 = make_uint2(0u, 0u);
