@@ -573,7 +573,8 @@ def test_dcn_tc_fused_vs_oracle(shape, prec):
         m.set_precision("fp32")
 
 
-@pytest.mark.parametrize("shape", [(2, 48, 48, 12, 33, 21, 2.0), (1, 32, 32, 8, 16, 8, 1.0), (1, 48, 48, 12, 40, 30, 14.0)])
+@pytest.mark.parametrize("shape", [(2, 48, 48, 12, 33, 21, 2.0), (1, 32, 32, 8, 16, 8, 1.0), (1, 48, 48, 12, 40, 30, 14.0),
+                                   (1, 128, 64, 32, 18, 11, 2.0)])
 def test_dcn_tf32_arm_vs_oracle(shape):
     """The 'tf32' arm's deformable convolution: fp32 x in, fp32 out, the gather and the contraction on fp16 multiplicands
     (x cast on the way in: the same 11-bit significand as TF32), fp32 accumulation, fp32 offsets -- vs the numpy oracle on
@@ -628,6 +629,37 @@ def test_dcn_tc_blocked_equals_tap_major(shape):
             o1 = mod(x, None, None, fused_om=om)
             o2 = mod(x, None, None, blocked_om=ops.om_to_blocked(om, G), groups=G)
         assert torch.isfinite(o1.float()).all() and torch.equal(o1, o2)
+    finally:
+        m.set_precision("fp32")
+
+
+@pytest.mark.parametrize("dil", [1, 2, 4])
+def test_dcn_tc_other_dilations(dil):
+    """The tensor-core kernel at the dilations the ABI admits besides the reference's 3 (pad == dil; window radius dil + 7),
+    against the numpy oracle on fp16-rounded operands; offsets up to several pixels beyond the window reach."""
+    import fami_pose_b200 as m
+    from fami_pose_b200 import layers, ops
+    B, C, Cout, G, H, W, sig = 2, 48, 48, 12, 21, 13, 3.0
+    m.set_precision("fp16")
+    try:
+        g = torch.Generator().manual_seed(100 + dil)
+        x = torch.randn(B, C, H, W, generator=g).half().float()
+        off = sig * torch.randn(B, 18 * G, H, W, generator=g)
+        msk = torch.randn(B, 9 * G, H, W, generator=g)
+        w = (0.05 * torch.randn(Cout, C, 3, 3, generator=g)).half().float()
+        b = 0.1 * torch.randn(Cout, generator=g)
+        ref = torch.from_numpy(fo.dcn_fwd(x.numpy(), off.numpy(), msk.numpy(), w.numpy(), b.numpy(), pad=dil, dil=dil))
+        mod = layers.DeformConv2d(C, Cout, 3, padding=dil, dilation=dil).to(DEV)
+        with torch.no_grad():
+            mod.weight.copy_(w.to(DEV))
+            mod.bias.copy_(b.to(DEV))
+            om = ops.to_nhwc(_to_tap_major(off, msk, G).to(DEV), torch.float32)
+            o1 = mod(ops.to_nhwc(x.to(DEV), torch.float16), None, None, fused_om=om)
+            o2 = mod(ops.to_nhwc(x.to(DEV), torch.float16), None, None, blocked_om=ops.om_to_blocked(om, G), groups=G)
+        assert torch.equal(o1, o2)
+        got = ops.to_nchw(o1).cpu().float()
+        tol = 4e-3 * float(ref.abs().max()) + 1e-3
+        assert float((got - ref).abs().max()) <= tol
     finally:
         m.set_precision("fp32")
 
