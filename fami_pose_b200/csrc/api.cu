@@ -44,6 +44,9 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
                         const float* shift, const void* res, void* y, double* stats, cudaStream_t st,
                         const float* res32 = nullptr, float* y32 = nullptr, int y32_pitch = 0);
 int64_t pack_w_bf16_elems(int Cout, int Cin, int kh, int kw, int dtype);
+int stem_tc_supported(const fami_conv_desc* d, const void* y);
+int stem_tc_launch(const fami_conv_desc* d, const float* x, const float* w, const float* scale, const float* shift, void* y,
+                   cudaStream_t st);
 int conv_halo_supported(const fami_conv_desc* d);
 int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
                      const void* res, void* y, cudaStream_t st, const float* res32 = nullptr, float* y32 = nullptr,
@@ -200,6 +203,17 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
       return conv_halo_launch(d, x, w_packed, scale, shift, residual, y, (cudaStream_t)stream);
     FAMI_CHECK_ARG(conv_bf16_tc_supported(d), "fami_conv2d_bn_act_fwd: om_groups: shape not supported by the tensor path");
     return conv_bf16_tc_launch(d, x, w_packed, scale, shift, residual, y, stats_out, (cudaStream_t)stream);
+  }
+  if (d->dtype == FAMI_TF32 && d->Cin == 3) {
+    // the 3-channel stem of the tf32 arm: fp32 pixels and fp32 output; on the tensor cores with fp16 multiplicands (the same
+    // 11-bit significand as TF32, formed in the CTA while it builds the im2col tile) when the shape is the HRNet stem's,
+    // else on the exact-fp32 kernel
+    fami_conv_desc e = *d;
+    e.dtype = FAMI_F32;
+    static const bool stem_tc_off = getenv("FAMI_DISABLE_STEM_TC") != nullptr;
+    if (!stem_tc_off && !residual && !d->stats && e.out_dtype == FAMI_F32 && stem_tc_supported(&e, y))
+      return stem_tc_launch(&e, (const float*)x, (const float*)w_packed, scale, shift, y, (cudaStream_t)stream);
+    return conv_f32_launch(&e, (const float*)x, (const float*)w_packed, scale, shift, residual, y, stats_out, (cudaStream_t)stream);
   }
   if (is_tc_dtype(d->dtype)) {
     FAMI_CHECK_ARG(d->out_dtype == d->dtype || d->out_dtype == FAMI_F32,

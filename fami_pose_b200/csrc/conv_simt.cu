@@ -400,7 +400,8 @@ int conv_f32_launch(const fami_conv_desc* d, const float* x, const float* w, con
                     const float* shift, const void* res, void* y, double* stats, cudaStream_t st) {
   // HRNet stem (fp32 pixels -> 16-bit activations): tensor-core kernel with an in-CTA im2col (csrc/stem_tc.cu)
   static const bool stem_tc_off = getenv("FAMI_DISABLE_STEM_TC") != nullptr;
-  if (!stem_tc_off && !res && stem_tc_supported(d, y)) return stem_tc_launch(d, x, w, scale, shift, y, st);
+  // (fp32 output only on request -- the tf32 arm, see fami_conv2d_bn_act_fwd: a plain FAMI_F32 descriptor is the exact-fp32 arm)
+  if (!stem_tc_off && !res && is_half_dtype(d->out_dtype) && stem_tc_supported(d, y)) return stem_tc_launch(d, x, w, scale, shift, y, st);
   ConvParams p;
   memset(&p, 0, sizeof(p));
   const bool out_half = is_half_dtype(d->out_dtype);

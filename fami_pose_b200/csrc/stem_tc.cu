@@ -25,6 +25,7 @@ struct StemParams {
   int N, H, W, Ho, Wo, M;
   int Cout, BN, CoutPad;
   int in_pitch, out_pitch, relu, vec_ok;
+  int out_f32;          // 1: fp32 output (the tf32 arm: fp16 multiplicands -- the TF32 significand --, fp32 accumulate and store)
   int total_tiles;
   uint32_t ab_format;
   const float* x;
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_tc_kernel(const StemParams 
     EpiArgs ea;
     ea.s_scale = smem_u32(s_scale); ea.s_shift = smem_u32(s_shift); ea.res = nullptr; ea.y = p.y;
     ea.Cout = p.Cout; ea.BN = p.BN; ea.ch_base = 0; ea.out_pitch = p.out_pitch; ea.res_pitch = 0;
-    ea.out_f32 = 0; ea.relu = p.relu; ea.vec_ok = p.vec_ok; ea.up = 1; ea.Wout = p.Wo;
+    ea.out_f32 = p.out_f32; ea.relu = p.relu; ea.vec_ok = p.vec_ok; ea.up = 1; ea.Wout = p.Wo;
     ea.spitch = epi_pipe_pitch(32);
     const uint32_t pstage = smem_u32(stage_base) + (uint32_t)(ew * 32 * epi_pipe_pitch(32));
     int sel = 0, primed = 0, it = 0;
@@ -166,8 +167,12 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_tc_kernel(const StemParams 
       mbar_wait(tfull(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(quarter * 32) << 16);
-      epilogue_rows_pipelined<TH, false>(ea, t_addr, col_begin, col_end, valid, valid ? m : 0, pstage, 0u, 0u, lane, sel, primed, false,
-                                         false, 0, 0, 32);
+      if (p.out_f32)
+        epilogue_rows_pipelined_f32<false>(ea, t_addr, col_begin, col_end, valid, valid ? m : 0, pstage, 0u, 0u, lane, sel, primed, false,
+                                           false, 0, 0);
+      else
+        epilogue_rows_pipelined<TH, false>(ea, t_addr, col_begin, col_end, valid, valid ? m : 0, pstage, 0u, 0u, lane, sel, primed, false,
+                                           false, 0, 0, 32);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(acc));
@@ -186,8 +191,12 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_tc_kernel(const StemParams 
 
 int stem_tc_supported(const fami_conv_desc* d, const void* y) {
   if (d->Cin != 3 || d->kh != 3 || d->kw != 3 || d->stride != 2 || d->pad != 1 || d->dil != 1 || d->up != 1 || d->stats) return 0;
-  if (d->dtype != FAMI_F32 || !is_half_dtype(d->out_dtype)) return 0;
-  if (d->Cout % 16 != 0 || d->Cout > 128 || d->out_pitch % 8 != 0 || (reinterpret_cast<uintptr_t>(y) & 15) != 0) return 0;
+  // fp32 pixels in; 16-bit out (fp16 / bf16 arms) or fp32 out (tf32 arm, selected by the caller: fami_conv2d_bn_act_fwd with
+  // dtype FAMI_TF32 and Cin = 3)
+  if (d->dtype != FAMI_F32 || !(is_half_dtype(d->out_dtype) || d->out_dtype == FAMI_F32)) return 0;
+  if (d->Cout % 16 != 0 || d->Cout > 128 || d->out_pitch % (d->out_dtype == FAMI_F32 ? 4 : 8) != 0 ||
+      (reinterpret_cast<uintptr_t>(y) & 15) != 0)
+    return 0;
   if ((int64_t)d->N * d->Ho * d->Wo >= (1ll << 31) - 256) return 0;
   return 1;
 }
@@ -200,18 +209,19 @@ int stem_tc_launch(const fami_conv_desc* d, const float* x, const float* w, cons
   p.Cout = d->Cout; p.BN = d->Cout; p.CoutPad = fami_conv_cout_pad(d->Cout);
   p.in_pitch = d->in_pitch; p.out_pitch = d->out_pitch; p.relu = d->relu; p.vec_ok = 1;
   p.total_tiles = (p.M + 127) / 128;
-  p.ab_format = d->out_dtype == FAMI_F16 ? 0u : 1u;
+  p.ab_format = d->out_dtype == FAMI_BF16 ? 1u : 0u;      // fp16 multiplicands unless the arm is bf16
+  p.out_f32 = d->out_dtype == FAMI_F32 ? 1 : 0;
   p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.y = y;
   const size_t smem = (size_t)kSStages * kSATile + (size_t)p.BN * 128 + 1024 + 256 + (size_t)p.BN * 8 +
                       (size_t)kSEpiWarps * 32 * epi_pipe_pitch(32);
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  if (d->out_dtype == FAMI_F16) {
-    static bool done = false;
-    if (!done) { cudaFuncSetAttribute(stem_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); done = true; }
+  if (d->out_dtype != FAMI_BF16) {
+    static std::atomic<uint64_t> mask{0};
+    set_max_smem_once(mask, stem_tc_kernel<__half>, 227 * 1024);
     stem_tc_kernel<__half><<<grid, kSThreads, smem, st>>>(p);
   } else {
-    static bool done = false;
-    if (!done) { cudaFuncSetAttribute(stem_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); done = true; }
+    static std::atomic<uint64_t> mask{0};
+    set_max_smem_once(mask, stem_tc_kernel<__nv_bfloat16>, 227 * 1024);
     stem_tc_kernel<__nv_bfloat16><<<grid, kSThreads, smem, st>>>(p);
   }
   FAMI_CHECK_LAUNCH("stem_tc_kernel");

@@ -338,7 +338,12 @@ def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None, out
     k = conv.kernel_size[0]
     stride, pad, dil = conv.stride[0], conv.padding[0], conv.dilation[0]
     code = conv_code(x, conv.in_channels)
-    w = packed_weight(conv, conv.weight, code)
+    wcode = code
+    if _PRECISION == "tf32" and x.dtype == torch.float32 and conv.in_channels == 3:
+        # the 3-channel stem of the tf32 arm: descriptor dtype TF32 (the library picks its tensor-core stem kernel when the
+        # shape fits, the exact-fp32 kernel otherwise); the weights keep the fp32 packing both kernels read
+        code, wcode = TF32, F32
+    w = packed_weight(conv, conv.weight, wcode)
     Cout = conv.out_channels
     if bn is not None and bn.training:
         # batch statistics: raw conv (+bias) with fused per-channel sum / sum-of-squares
