@@ -136,7 +136,8 @@ def emit(obj):
     out.flush()
 
 
-ARM_DTYPE = {"fp32": "f32", "tf32": "tf32 (f32 storage, kind::tf32 tensor cores, f32 accumulate)", "fp16": "f16", "bf16": "bf16"}
+ARM_DTYPE = {"fp32": "f32", "tf32": "tf32 (f32 storage, kind::tf32 tensor cores, f32 accumulate)", "fp16": "f16", "bf16": "bf16",
+             "fp16s": "f16s (f16 multiplicands, f32 residual stream, f32 accumulate)"}
 
 
 def main():
@@ -150,7 +151,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fami", choices=["fami", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
-    ap.add_argument("--precision", default=os.environ.get("FAMI_PRECISION", "tf32"), choices=["fp32", "tf32", "fp16", "bf16"],
+    ap.add_argument("--precision", default=os.environ.get("FAMI_PRECISION", "tf32"), choices=["fp32", "tf32", "fp16", "fp16s", "bf16"],
                     help="the arm `value` / `e2e` / `dtype` belong to.  Default tf32: the reference computes in fp32 and its "
                          "convolutions run as TF32 on a GPU, so this is the like-for-like arm (1e-3 tier)")
     ap.add_argument("--arms", default=None,
@@ -195,7 +196,7 @@ def main():
                 emit(rec)
             return
         B = args.batch
-        extra = [a for a in (args.arms.split(",") if args.arms is not None else (["fp16"] if args.precision == "tf32" else []))
+        extra = [a for a in (args.arms.split(",") if args.arms is not None else (["fp16s", "fp16"] if args.precision == "tf32" else []))
                  if a and a != args.precision]
         fb = ForwardBench(ctx, B)
         if args.profile_step:
@@ -254,6 +255,9 @@ ARM_NOTE = {
             "the arithmetic cuDNN applies to the reference's fp32 convs on a GPU; parity tier 1e-3",
     "fp16": "fp16 activations, tcgen05.mma.kind::f16, fp32 accumulate, fp32 offsets / masks / heatmaps; parity tier 1e-2",
     "bf16": "bf16 activations, tcgen05.mma.kind::f16, fp32 accumulate, fp32 offsets / masks / heatmaps; parity tier 1e-2",
+    "fp16s": "fp16 multiplicands (the 11-bit significand of TF32) on tcgen05.mma.kind::f16, every residual / running sum stored "
+             "and added in fp32 (fp32 twin of each block output), fp32 accumulate, fp32 offsets / masks / heatmaps; measured "
+             "5.5e-4 / 8.3e-4 against the reference (the tf32 arm's error), tested at 1e-3",
 }
 
 

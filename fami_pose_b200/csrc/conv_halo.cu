@@ -373,6 +373,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ea.out_f32 = p.out_f32; ea.relu = p.relu; ea.vec_ok = p.vec_ok; ea.up = 1; ea.Wout = p.W;
     ea.res32 = p.res32; ea.y32 = p.y32; ea.res32_pitch = p.res32_pitch; ea.y32_pitch = p.y32_pitch;
     const bool stream_mode = p.res32 != nullptr || p.y32 != nullptr;
+    // stream mode on a plain tile: the pipelined twin (same 48-byte staging / residual-buffer layout as the lean routines)
+    const bool stream_lean = stream_mode && sizeof(TH) == 2 && p.Cout == p.BN * p.n_tiles && p.om_groups == 0 && p.res == nullptr &&
+                             epi_stream_pipe_ok(p.BN, p.Cout, 1, p.out_f32, p.out_pitch, p.y, p.res32, p.res32_pitch, p.y32, p.y32_pitch);
+    uint32_t sstage = 0, srb0 = 0, srb1 = 0;
+    if (stream_lean) {
+      const uint32_t sp = (uint32_t)epi_pipe_pitch(16);      // 48
+      sstage = smem_u32(stage_base) + (uint32_t)(warp - kEpiWarp0) * 32u * sp;
+      const uint32_t b0 = smem_u32(stage_base) + (uint32_t)kEpiWarps * 32u * sp;
+      srb0 = b0 + (uint32_t)(2 * (warp - kEpiWarp0)) * 32u * sp;
+      srb1 = b0 + (uint32_t)(2 * (warp - kEpiWarp0) + 1) * 32u * sp;
+    }
     int it = 0;
     for (int unit = tile0; unit < n_units; unit += tile_step, ++it) {
       bool dup;
@@ -403,7 +414,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         bool valid;
         const int pix = row_pix(m, valid);
         const uint32_t t_addr = tmem_base + (uint32_t)(acc * acc_cols + m * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
-        if (stream_mode) {
+        if (stream_lean) {
+         if constexpr (sizeof(TH) == 2) {
+          // next unit of this warp (residual prefetch): the next M-tile, or the first M-tile of this CTA's next tile
+          bool nvalid = false, have_next = true;
+          int npix = 0, nchb = ea.ch_base;
+          if (m + 1 < p.NM) {
+            npix = row_pix(m + 1, nvalid);
+          } else if (unit + tile_step < n_units) {
+            bool ndup;
+            const int ntile = unit_tile(unit + tile_step, ndup);
+            const int nnt = ntile % p.n_tiles;
+            const int nt2 = ntile / p.n_tiles;
+            const int nty = nt2 % p.tiles_per_img, nimg = nt2 / p.tiles_per_img;
+            const int ny0 = nty * p.BH;
+            const int yy = row / p.Wp, xx = row - yy * p.Wp;
+            nvalid = (yy < p.BH) && (xx < p.W) && (ny0 + yy < p.H) && !ndup;
+            npix = nvalid ? (nimg * p.H + (ny0 + yy)) * p.W + xx : 0;
+            nchb = nnt * p.BN;
+          } else {
+            have_next = false;
+          }
+          if (p.res32)
+            epilogue_rows_pipelined_stream<TH, true>(ea, t_addr, col_begin, col_end, valid, pix, sstage, srb0, srb1, lane, pf_sel,
+                                                     pf_have, have_next, nvalid, npix, nchb);
+          else
+            epilogue_rows_pipelined_stream<TH, false>(ea, t_addr, col_begin, col_end, valid, pix, sstage, 0u, 0u, lane, pf_sel,
+                                                      pf_have, false, false, 0, 0);
+         }
+        } else if (stream_mode) {
           epilogue_rows_stream<TH>(ea, t_addr, col_begin, col_end, valid, pix);
         } else if (p.om_groups > 0) {
           const int q = m * 128 + row;

@@ -226,6 +226,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ea.out_f32 = p.out_f32; ea.relu = p.relu; ea.vec_ok = p.vec_ok; ea.up = p.up; ea.Wout = Wout;
     ea.res32 = p.res32; ea.y32 = p.y32; ea.res32_pitch = p.res32_pitch; ea.y32_pitch = p.y32_pitch;
     const bool stream_mode = p.res32 != nullptr || p.y32 != nullptr;
+    // stream mode on a plain tile: the pipelined twin; staging + two residual buffers per warp at the 48-byte pitch fit the
+    // generic routine's allocation (kEpiWarps x 32 x 144 B)
+    const bool stream_lean = stream_mode && sizeof(TH) == 2 && p.Cout == p.BN * p.n_tiles && p.om_groups == 0 && p.res == nullptr &&
+                             epi_stream_pipe_ok(p.BN, p.Cout, p.up, p.out_f32, p.out_pitch, p.y, p.res32, p.res32_pitch, p.y32, p.y32_pitch);
+    const uint32_t sps = 48u;
+    const uint32_t sstage = smem_u32(stage_base) + (uint32_t)(warp - 2) * 96u * sps;
     int it = 0;
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
@@ -249,7 +255,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)(quarter * 32) << 16);
-      if (stream_mode) {
+      if (stream_lean) {
+       if constexpr (sizeof(TH) == 2) {
+        const int ntile = tile + tile_step;
+        const bool have_next = ntile < total_tiles;
+        const int nunit = ntile / p.n_tiles, nnt = ntile - nunit * p.n_tiles;
+        bool ndup;
+        const int nmt = unit_mt(nunit, ndup);
+        const int nm = nmt * kBM + row;
+        const bool nvalid = have_next && nm < p.M && !ndup;
+        int npix = 0;                       // first replica of the next unit's row
+        if (nvalid) {
+          if (p.up == 1) {
+            npix = nm;
+          } else {
+            const int n2 = nm / p.HoWo, r2 = nm - n2 * p.HoWo;
+            const int yo2 = r2 / p.Wo, xo2 = r2 - yo2 * p.Wo;
+            npix = (n2 * Hout + yo2 * p.up) * Wout + xo2 * p.up;
+          }
+        }
+        if (p.res32)
+          epilogue_rows_pipelined_stream<TH, true>(ea, t_addr, col_begin, col_end, valid, pix0, sstage, sstage + 32u * sps,
+                                                   sstage + 64u * sps, lane, psel, pprimed, have_next, nvalid, npix, nnt * p.BN);
+        else
+          epilogue_rows_pipelined_stream<TH, false>(ea, t_addr, col_begin, col_end, valid, pix0, sstage, 0u, 0u, lane, psel, pprimed,
+                                                    false, false, 0, 0);
+       }
+      } else if (stream_mode) {
         epilogue_rows_stream<TH>(ea, t_addr, col_begin, col_end, valid, pix0);
       } else if (p.om_groups > 0) {
         const int n = m / p.HoWo, r = m - n * p.HoWo;

@@ -833,6 +833,111 @@ __device__ __forceinline__ void epilogue_rows_pipelined_f32(const EpiArgs& a, ui
     primed = pending ? 1 : 0;
   }
 }
+// fp32-residual-stream twin of the pipelined routines (16-bit arms with an fp32 residual stream,
+// fami_conv2d_bn_act_fwd_stream): 8-column groups as in epilogue_rows_pipelined_f32.  The residual comes from the FLOAT
+// tensor a.res32 (cp.async pipeline, kRes), the result goes -- before rounding -- to the float tensor a.y32 when there is
+// one (staged, coalesced 16-byte pieces) and, rounded, to the 16-bit tensor a.y (each lane stores the 16 bytes of its
+// row's group itself).  Replaces the unstaged epilogue_rows_stream wherever the tile has whole 8-column groups and 16-byte
+// aligned rows (incl. the replicate-on-write fuse layers); that routine keeps the ragged cases.
+template <typename TH, bool kRes>
+__device__ __forceinline__ void epilogue_rows_pipelined_stream(const EpiArgs& a0, uint32_t t_addr, int col_begin, int col_end,
+                                                               bool valid, int pix0, uint32_t stage, uint32_t rb0, uint32_t rb1,
+                                                               int lane, int& sel, int& primed, bool have_next, bool next_valid,
+                                                               int next_pix, int next_ch_base) {
+  if (col_begin >= col_end) return;   // warp-uniform
+  constexpr int gcols = kPipeColsF32;
+  constexpr int pitch = gcols * 4 + 16;   // 48
+  EpiArgs a = a0;
+  a.res = a0.res32;                        // epi_pipe_fetch<float> reads a.res / a.res_pitch
+  a.res_pitch = a0.res32_pitch;
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  const unsigned nmask = __ballot_sync(0xffffffffu, next_valid);
+  const uint32_t my_row = stage + (uint32_t)(lane * pitch);
+  const int sub_r = lane >> 1, sub_c = lane & 1;   // 2 x 16-byte pieces per row, 16 rows per iteration
+  // nearest-upsample replication (the HighResolutionModule fuse layers): the accumulator group is read and scaled once,
+  // every one of the up*up replicas adds its own residual and is stored; the pipeline unit is (column group, replica)
+  const int nrep = a.up * a.up;
+  auto rep_pix = [&](int rep) { const int dy = rep / a.up; return pix0 + dy * a.Wout + (rep - dy * a.up); };
+  if (kRes && !primed) epi_pipe_fetch<float>(a, a.ch_base + col_begin, gcols, vmask, pix0, sel ? rb1 : rb0, lane, pitch);
+  for (int g0 = col_begin; g0 < col_end; g0 += gcols) {
+    const int chg = a.ch_base + g0;
+    uint32_t v[8];
+    tmem_ld8(t_addr + (uint32_t)g0, v);
+    tmem_ld_wait();
+    const float4 sc0 = lds128f(a.s_scale + (uint32_t)chg * 4u), sc1 = lds128f(a.s_scale + (uint32_t)(chg + 4) * 4u);
+    const float4 sh0 = lds128f(a.s_shift + (uint32_t)chg * 4u), sh1 = lds128f(a.s_shift + (uint32_t)(chg + 4) * 4u);
+    float4 b0, b1;
+    b0.x = fmaf(__uint_as_float(v[0]), sc0.x, sh0.x); b0.y = fmaf(__uint_as_float(v[1]), sc0.y, sh0.y);
+    b0.z = fmaf(__uint_as_float(v[2]), sc0.z, sh0.z); b0.w = fmaf(__uint_as_float(v[3]), sc0.w, sh0.w);
+    b1.x = fmaf(__uint_as_float(v[4]), sc1.x, sh1.x); b1.y = fmaf(__uint_as_float(v[5]), sc1.y, sh1.y);
+    b1.z = fmaf(__uint_as_float(v[6]), sc1.z, sh1.z); b1.w = fmaf(__uint_as_float(v[7]), sc1.w, sh1.w);
+    for (int rep = 0; rep < nrep; ++rep) {          // warp-uniform
+      const int pix = rep_pix(rep);
+      const uint32_t cur = sel ? rb1 : rb0, nxt = sel ? rb0 : rb1;
+      bool pending = false;
+      if (kRes) {
+        if (rep + 1 < nrep) {
+          epi_pipe_fetch<float>(a, chg, gcols, vmask, rep_pix(rep + 1), nxt, lane, pitch);
+          pending = true;
+        } else if (g0 + gcols < col_end) {
+          epi_pipe_fetch<float>(a, chg + gcols, gcols, vmask, pix0, nxt, lane, pitch);
+          pending = true;
+        } else if (have_next) {
+          epi_pipe_fetch<float>(a, next_ch_base + col_begin, gcols, nmask, next_pix, nxt, lane, pitch);
+          pending = true;
+        }
+        if (pending) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+      }
+      float4 o0 = b0, o1 = b1;
+      if (kRes) {
+        const uint32_t res_row = cur + (uint32_t)(lane * pitch);
+        const float4 r0 = lds128f(res_row), r1 = lds128f(res_row + 16);
+        o0.x += r0.x; o0.y += r0.y; o0.z += r0.z; o0.w += r0.w;
+        o1.x += r1.x; o1.y += r1.y; o1.z += r1.z; o1.w += r1.w;
+      }
+      if (a.relu) {
+        o0.x = fmaxf(o0.x, 0.f); o0.y = fmaxf(o0.y, 0.f); o0.z = fmaxf(o0.z, 0.f); o0.w = fmaxf(o0.w, 0.f);
+        o1.x = fmaxf(o1.x, 0.f); o1.y = fmaxf(o1.y, 0.f); o1.z = fmaxf(o1.z, 0.f); o1.w = fmaxf(o1.w, 0.f);
+      }
+      // the 16-bit operand twin: this lane's 8 channels = 16 bytes of its pixel row
+      if (valid) {
+        uint4 h;
+        h.x = f2_to_h2<TH>(o0.x, o0.y); h.y = f2_to_h2<TH>(o0.z, o0.w); h.z = f2_to_h2<TH>(o1.x, o1.y); h.w = f2_to_h2<TH>(o1.z, o1.w);
+        *reinterpret_cast<uint4*>(reinterpret_cast<TH*>(a.y) + (int64_t)pix * a.out_pitch + chg) = h;
+      }
+      // the fp32 stream: staged, coalesced 16-byte pieces
+      if (a.y32) {
+        sts128f(my_row, o0);
+        sts128f(my_row + 16, o1);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int r = it * 16 + sub_r;
+          const int pr = __shfl_sync(0xffffffffu, pix, r);
+          if ((vmask >> r) & 1u) {
+            const uint4 val = lds128(stage + (uint32_t)(r * pitch + sub_c * 16));
+            uint8_t* dst = reinterpret_cast<uint8_t*>(a.y32) + ((int64_t)pr * a.y32_pitch + chg) * 4 + sub_c * 16;
+            *reinterpret_cast<uint4*>(dst) = val;
+          }
+        }
+        __syncwarp();
+      }
+      if (kRes) {
+        sel ^= 1;
+        primed = pending ? 1 : 0;
+      }
+    }
+  }
+}
+// host / device: may a stream-mode tile take epilogue_rows_pipelined_stream?
+__host__ __device__ inline bool epi_stream_pipe_ok(int BN, int Cout_total, int up, int out_f32, int out_pitch, const void* y,
+                                                   const float* res32, int res32_pitch, const float* y32, int y32_pitch) {
+  return (up == 1 || up == 2 || up == 4 || up == 8) && !out_f32 && BN % 8 == 0 && Cout_total % 8 == 0 && out_pitch % 8 == 0 &&
+         ((uintptr_t)y & 15) == 0 &&
+         (!res32 || (res32_pitch % 4 == 0 && ((uintptr_t)res32 & 15) == 0)) && (!y32 || (y32_pitch % 4 == 0 && ((uintptr_t)y32 & 15) == 0));
+}
 template <typename TH, bool kRes = true>
 __device__ __forceinline__ void epilogue_rows_pipelined(const EpiArgs& a, uint32_t t_addr, int col_begin, int col_end, bool valid,
                                                         int pix0, uint32_t stage, uint32_t rb0, uint32_t rb1, int lane, int& sel,

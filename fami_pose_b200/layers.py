@@ -50,7 +50,7 @@ class BasicBlock(nn.Module):
         x = ops.to_nhwc(x)
         bn1 = None if self.skip_norm else self.bn1
         bn2 = None if self.skip_norm else self.bn2
-        h = ops.conv_bn_act(x, self.conv1, bn1, relu=True)
+        h = ops.conv_bn_act(x, self.conv1, bn1, relu=True, stream_out=False)
         if self.downsample is not None:
             ds = list(self.downsample.children())
             res = ops.conv_bn_act(x, ds[0], ds[1] if len(ds) > 1 else None, relu=False)
@@ -77,8 +77,8 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         x = ops.to_nhwc(x)
-        h = ops.conv_bn_act(x, self.conv1, self.bn1, relu=True)
-        h = ops.conv_bn_act(h, self.conv2, self.bn2, relu=True)
+        h = ops.conv_bn_act(x, self.conv1, self.bn1, relu=True, stream_out=False)
+        h = ops.conv_bn_act(h, self.conv2, self.bn2, relu=True, stream_out=False)
         if self.downsample is not None:
             ds = list(self.downsample.children())
             res = ops.conv_bn_act(x, ds[0], ds[1] if len(ds) > 1 else None, relu=False)

@@ -34,8 +34,13 @@ def set_precision(p, stream_f32=None):
     the TMA load), fp32 accumulation.  This is the arithmetic the reference's fp32 nn.Conv2d gets from cuDNN on a
     GPU (torch.backends.cudnn.allow_tf32 = True by default); it meets the fp32 tier's 1e-3 tolerance.
     'fp16' / 'bf16': tcgen05 tensor-core arm with 16-bit activations (fp32 accumulation, fp32
-    offsets/masks/heatmaps); fp16 carries 3 more mantissa bits than bf16 at the same tensor-core rate."""
+    offsets/masks/heatmaps); fp16 carries 3 more mantissa bits than bf16 at the same tensor-core rate.
+    'fp16s' = 'fp16' with the fp32 residual stream (stream_f32=True): fp16 multiplicands carry the 11-bit significand of
+    TF32, every residual / running sum is kept and added in fp32, accumulation is fp32 -- the TF32 error (5.5e-4 / 8.3e-4
+    against the reference on config 2) at kind::f16 MMA rates."""
     global _PRECISION, _STREAM_F32
+    if p == "fp16s":
+        p, stream_f32 = "fp16", True
     if p not in _DTYPES:
         raise ValueError("precision must be one of %s" % sorted(_DTYPES))
     _PRECISION = p
@@ -310,12 +315,14 @@ def conv_offsets_blocked(x, conv, G, out=None):
     return out
 
 
-def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None, out_dtype=None):
+def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None, out_dtype=None, stream_out=True):
     """conv -> [BatchNorm] -> [+residual] -> [ReLU] -> [nearest x`up`] in one launch (eval-mode BN)
     or conv(+stats) -> finalize -> apply (train-mode BN, batch statistics).
 
     conv: nn.Conv2d used as a parameter container (square kernel 1/3, groups=1); bn: nn.BatchNorm2d.
     Reference chains: basic_model.py:44-63,83-113; basic_layer.py:55-73; hrnet.py:89-172.
+    stream_out=False (fp32-residual-stream mode of the 16-bit arms only): the output is never used as a residual or running
+    sum (the inner convolutions of a block), so no float twin is written for it.
     """
     _need_cuda(x)
     if conv.groups != 1:
@@ -379,12 +386,13 @@ def conv_bn_act(x, conv, bn=None, relu=False, residual=None, up=1, out=None, out
                   _ptr(out), op, _code(out.dtype), N, Ho, Wo, Cout, up, int(bool(relu)), _stream())
         return out
     scale, shift = folded_affine(conv.bias, bn)
-    if _STREAM_F32 and x.dtype in (torch.float16, torch.bfloat16) and out is None and out_dtype in (None, x.dtype):
-        return _conv_stream(x, w, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, code)
+    if _STREAM_F32 and x.dtype in (torch.float16, torch.bfloat16) and out is None and out_dtype in (None, x.dtype) and (
+            stream_out or residual is not None):
+        return _conv_stream(x, w, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, code, need32=stream_out)
     return _conv_raw(x, w, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, out, None, out_dtype, code=code)
 
 
-def _conv_stream(x, w_packed, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, code):
+def _conv_stream(x, w_packed, Cout, k, stride, pad, dil, scale, shift, residual, relu, up, code, need32=True):
     """fp32-residual-stream form of the fused convolution (16-bit arms, fami_conv2d_bn_act_fwd_stream): the residual is
     taken from the float twin of `residual` when it has one (`_fami_f32`, attached to every output of this function) and
     the output gets a float twin of its own.  Slices / views drop the twin and fall back to the 16-bit values."""
@@ -392,7 +400,7 @@ def _conv_stream(x, w_packed, Cout, k, stride, pad, dil, scale, shift, residual,
     Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
     Wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
     out = empty_nhwc(N, Cout, Ho * up, Wo * up, x.dtype, x.device)
-    y32 = empty_nhwc(N, Cout, Ho * up, Wo * up, torch.float32, x.device)
+    y32 = empty_nhwc(N, Cout, Ho * up, Wo * up, torch.float32, x.device) if need32 else None
     res32 = getattr(residual, "_fami_f32", None) if residual is not None else None
     if residual is not None and res32 is None:
         res32 = cast_nhwc(residual, torch.float32)        # a residual without a twin (e.g. a slice): widen it
@@ -402,8 +410,9 @@ def _conv_stream(x, w_packed, Cout, k, stride, pad, dil, scale, shift, residual,
     d = ConvDesc(N, H, W, Cin, Cout, k, k, stride, pad, dil, Ho, Wo, up, int(bool(relu)), ip, meta(out)[4], rp,
                  code, code, 0, 0)
     _lib.call("fami_conv2d_bn_act_fwd_stream", ctypes.byref(d), _ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(res32),
-              _ptr(out), _ptr(y32), meta(y32)[4], _stream())
-    out._fami_f32 = y32
+              _ptr(out), _ptr(y32), meta(y32)[4] if y32 is not None else 0, _stream())
+    if y32 is not None:
+        out._fami_f32 = y32
     return out
 
 

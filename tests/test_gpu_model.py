@@ -284,6 +284,30 @@ def test_alignment_v15_tf32_vs_reference_golden(golden_dir):
         fp.set_precision("fp32")
 
 
+def test_alignment_v15_fp16_stream_arm_meets_the_fp32_tier(golden_dir):
+    """'fp16s': fp16 multiplicands (the 11-bit significand of TF32) + fp32 residual stream + fp32 accumulation, with the
+    pipelined stream epilogue (epilogue_rows_pipelined_stream) -- against the unmodified reference's fp32 golden at
+    north_star's fp32-tier tolerance 1e-3 (measured 5.5e-4 / 8.3e-4, the tf32 arm's figures), argmax as for the other arms."""
+    import fami_pose_b200 as fp
+    gold = np.load(os.path.join(golden_dir, "model_reference.npz"))
+    m, sd = _build("validate")
+    m.eval()
+    fp.set_precision("fp16s")
+    try:
+        kf, sup, tgt, tw = fo.synthetic_clip(1, seed=SEED)
+        with torch.no_grad():
+            hm, kfhm = m(kf.to(DEV), sup.to(DEV))
+        assert hm.dtype == torch.float32
+        e1 = float(np.abs(hm.cpu().numpy() - gold["v15_eval_final_hm"]).max())
+        e2 = float(np.abs(kfhm.cpu().numpy() - gold["v15_eval_kf_hm"]).max())
+        print("fp16s max-abs err final %.3e kf %.3e" % (e1, e2))
+        assert e1 <= TOL and e2 <= TOL
+        _argmax_check(hm.cpu().numpy(), gold["v15_eval_final_hm"])
+        _argmax_check(kfhm.cpu().numpy(), gold["v15_eval_kf_hm"])
+    finally:
+        fp.set_precision("fp32")
+
+
 @pytest.mark.parametrize("prec,tol", HALF_ARMS)
 def test_alignment_v15_half_vs_reference_golden(golden_dir, prec, tol):
     import fami_pose_b200 as fp
