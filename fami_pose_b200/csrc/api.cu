@@ -79,6 +79,9 @@ int frames_u8_normalize_launch(const uint8_t* src, int64_t src_frame_stride, flo
 int crop_affine_u8_launch(const uint8_t* src, int64_t src_frame_stride, int Hs, int Ws, const double* minv, void* dst,
                           int nframes, int Hd, int Wd, const float* mean, const float* std, cudaStream_t st);
 int dcn_tc_supported(const fami_dcn_desc* d);
+int dcn_wp_supported(const fami_dcn_desc* d);
+int dcn_wp_launch(const fami_dcn_desc* d, const void* x, const float* om, const void* w, const float* bias, void* out,
+                  cudaStream_t st);
 int dcn_tc_launch(const fami_dcn_desc* d, const void* x, const float* om, const void* w, const float* bias, void* out,
                   cudaStream_t st);
 int dcn_bwd_launch(const fami_dcn_desc* d, const float* x, const float* off, const float* mask, const float* w,
@@ -432,6 +435,8 @@ int fami_dcn_fwd(const fami_dcn_desc* d, const void* x, const void* offset, cons
   FAMI_CHECK_ARG(!d->out_f32 || (d->om_layout >= 1 && is_half_dtype(d->dtype)),
                  "fami_dcn_fwd: out_f32 applies to the 16-bit tensor-core kernel (om_layout 1 / 2)");
   if (d->om_layout >= 1) {
+    /* C == Cout <= 64: the warp-private kernel (dcn_wp.cu); everything else: the tcgen05 kernel (dcn_tc.cu) */
+    if (dcn_wp_supported(d)) return dcn_wp_launch(d, x, (const float*)offset, w_packed, bias, out, (cudaStream_t)stream);
     FAMI_CHECK_ARG(dcn_tc_supported(d), "fami_dcn_fwd: fused tap-major offsets need the 16-bit tensor-core kernel "
                                         "(C <= 64, 4 channels per offset group, 3x3, pad == dil)");
     return dcn_tc_launch(d, x, (const float*)offset, w_packed, bias, out, (cudaStream_t)stream);

@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu", "dcn_tc.cu", "misc.cu", "bwd.cu", "bwd_dense.cu",
+SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu", "dcn_tc.cu", "dcn_wp.cu", "misc.cu", "bwd.cu", "bwd_dense.cu",
            "decode.cu", "stem_tc.cu", "probes.cu"]
 OUT = os.path.join(os.path.dirname(HERE), "libfami_b200.so")
 OUT_PROBES = os.path.join(os.path.dirname(HERE), "libfami_b200_probes.so")
