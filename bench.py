@@ -523,7 +523,7 @@ def dcn_roofline(fp, ops, dev, stream, B, pk):
     out = ops.empty_nhwc(B, C, H, W, dt, dev)
     if half:   # fused [offset|mask] buffer in the row-blocked layout, as the alignment head's producer conv writes it
         om = ops.to_nhwc(torch.cat([off, msk], 1)[:, ops.tap_major_perm(G)].contiguous(), torch.float32)
-        blk = ops.om_to_blocked(om, G)
+        blk = ops.om_to_blocked(om, G, layout=ops.dcn_blocked_layout(C, C, G))
         del om
         run = lambda: dcn(x, None, None, out=out, blocked_om=blk, groups=G)
     else:

@@ -20,7 +20,7 @@ TF32 = 3   # conv / dcn descriptors only: float storage, tcgen05 kind::tf32 arit
 class ConvDesc(Structure):
     _fields_ = [(n, c_int32) for n in (
         "N", "H", "W", "Cin", "Cout", "kh", "kw", "stride", "pad", "dil", "Ho", "Wo", "up", "relu",
-        "in_pitch", "out_pitch", "res_pitch", "dtype", "out_dtype", "stats", "om_groups")]
+        "in_pitch", "out_pitch", "res_pitch", "dtype", "out_dtype", "stats", "om_groups", "om_layout")]
 
 
 class DcnDesc(Structure):
@@ -126,7 +126,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.fami_abi_version() != 2:
+    if lib.fami_abi_version() != 3:
         raise FamiLibraryError("libfami_b200.so ABI version mismatch")
     _lib = lib
     return lib

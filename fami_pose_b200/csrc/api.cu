@@ -201,6 +201,7 @@ int fami_conv2d_bn_act_fwd(const fami_conv_desc* d, const void* x, const void* w
                    "fami_conv2d_bn_act_fwd: om_groups needs a 16-bit 3x3 stride-1 same conv with Cout = 27*G, fp32 output, "
                    "no residual / upsample / statistics");
     FAMI_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "fami_conv2d_bn_act_fwd: om_groups: y must be 16-byte aligned");
+    FAMI_CHECK_ARG(d->om_layout == 0 || d->om_layout == 2 || d->om_layout == 3, "fami_conv2d_bn_act_fwd: bad om_layout %d", d->om_layout);
     static const bool halo_off_om = getenv("FAMI_DISABLE_HALO") != nullptr;
     if (!halo_off_om && conv_halo_supported(d))
       return conv_halo_launch(d, x, w_packed, scale, shift, residual, y, (cudaStream_t)stream);
@@ -419,9 +420,9 @@ static int check_dcn(const fami_dcn_desc* d, const char* who) {
   FAMI_CHECK_ARG((d->C / d->G) % 4 == 0 && d->C % 16 == 0,
                  "%s: channels per offset group must be a multiple of 4 and C a multiple of 16 (C=%d G=%d)", who,
                  d->C, d->G);
-  FAMI_CHECK_ARG(d->om_layout >= 0 && d->om_layout <= 2, "%s: bad om_layout %d", who, d->om_layout);
+  FAMI_CHECK_ARG(d->om_layout >= 0 && d->om_layout <= 3, "%s: bad om_layout %d", who, d->om_layout);
   FAMI_CHECK_ARG(d->x_pitch >= d->C && d->out_pitch >= d->Cout, "%s: pitch too small", who);
-  FAMI_CHECK_ARG(d->om_layout == 2 || (d->om_layout == 1 ? d->off_pitch >= 27 * d->G : (d->off_pitch >= 18 * d->G && d->mask_pitch >= 9 * d->G)),
+  FAMI_CHECK_ARG(d->om_layout >= 2 || (d->om_layout == 1 ? d->off_pitch >= 27 * d->G : (d->off_pitch >= 18 * d->G && d->mask_pitch >= 9 * d->G)),
                  "%s: offset/mask pitch too small", who);
   FAMI_CHECK_ARG((int64_t)d->B * d->H * d->W < (1ll << 31), "%s: too many pixels", who);
   return 0;
@@ -437,6 +438,8 @@ int fami_dcn_fwd(const fami_dcn_desc* d, const void* x, const void* offset, cons
   if (d->om_layout >= 1) {
     /* C == Cout <= 64: the warp-private kernel (dcn_wp.cu); everything else: the tcgen05 kernel (dcn_tc.cu) */
     if (dcn_wp_supported(d)) return dcn_wp_launch(d, x, (const float*)offset, w_packed, bias, out, (cudaStream_t)stream);
+    FAMI_CHECK_ARG(d->om_layout != 3, "fami_dcn_fwd: the k-step-blocked offset layout (3) needs the warp-private kernel "
+                                      "(16-bit x, C == Cout in {32, 48}, 4 channels per offset group, 3x3, pad == dil <= 4)");
     FAMI_CHECK_ARG(dcn_tc_supported(d), "fami_dcn_fwd: fused tap-major offsets need the 16-bit tensor-core kernel "
                                         "(C <= 64, 4 channels per offset group, 3x3, pad == dil)");
     return dcn_tc_launch(d, x, (const float*)offset, w_packed, bias, out, (cudaStream_t)stream);

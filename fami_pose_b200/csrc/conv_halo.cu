@@ -57,6 +57,7 @@ struct HaloParams {
   int trace;
   int om_groups, om_tiles_x, om_tiles_y;   // > 0: y is the row-blocked DCN offset|mask buffer
   int64_t om_tap_stride;
+  int om_kblocked;                         // fami_conv_desc.om_layout == 3
   const float* scale;
   const float* shift;
   const void* res;
@@ -449,7 +450,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int yy = q / p.Wp, xx = q - yy * p.Wp;
           OmBlocked ob;
           ob.base = reinterpret_cast<float*>(p.y); ob.tiles_x = p.om_tiles_x; ob.tiles_y = p.om_tiles_y;
-          ob.G3 = 3 * p.om_groups; ob.tap_stride = p.om_tap_stride;
+          ob.G3 = 3 * p.om_groups; ob.tap_stride = p.om_tap_stride; ob.kblocked = p.om_kblocked;
           if (!(p.trace & 2)) epilogue_rows_om_blocked(ea, t_addr, col_begin, col_end, valid, img, y0 + yy, xx, ob);
         } else if (pf_on) {
          if constexpr (sizeof(TH) == 2) {
@@ -709,6 +710,7 @@ int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, cons
   p.scale = scale; p.shift = shift; p.res = res; p.y = y;
   p.res32 = res32; p.y32 = y32; p.res32_pitch = d->res_pitch; p.y32_pitch = y32_pitch;
   p.om_groups = d->om_groups;
+  p.om_kblocked = d->om_layout == 3;
   p.om_tiles_x = (d->W + 7) / 8; p.om_tiles_y = (d->H + 15) / 16;
   p.om_tap_stride = (int64_t)d->N * p.om_tiles_x * p.om_tiles_y * 4 * (3 * (d->om_groups / 4)) * 128;
   static const bool trace_on = getenv("FAMI_HALO_TRACE") != nullptr;

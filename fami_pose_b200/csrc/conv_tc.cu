@@ -34,6 +34,7 @@ struct TcParams {
   int stages, pipe;   // pipe: pipelined residual epilogue (epilogue_rows_pipelined)
   int om_groups, om_tiles_x, om_tiles_y;   // > 0: y is the row-blocked DCN offset|mask buffer (fami_conv_desc.om_groups)
   int64_t om_tap_stride;
+  int om_kblocked;                         // fami_conv_desc.om_layout == 3
   const float* scale;
   const float* shift;
   const void* res;   // TH
@@ -288,7 +289,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int yo = r / p.Wo, xo = r - yo * p.Wo;
         OmBlocked ob;
         ob.base = reinterpret_cast<float*>(p.y); ob.tiles_x = p.om_tiles_x; ob.tiles_y = p.om_tiles_y;
-        ob.G3 = 3 * p.om_groups; ob.tap_stride = p.om_tap_stride;
+        ob.G3 = 3 * p.om_groups; ob.tap_stride = p.om_tap_stride; ob.kblocked = p.om_kblocked;
         epilogue_rows_om_blocked(ea, t_addr, col_begin, col_end, valid, n, yo, xo, ob);
       } else if (p.pipe) {
         const int ntile = tile + tile_step;
@@ -469,6 +470,7 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   p.scale = scale; p.shift = shift; p.res = res; p.y = y;
   p.res32 = res32; p.y32 = y32; p.res32_pitch = d->res_pitch; p.y32_pitch = y32_pitch;
   p.om_groups = d->om_groups;
+  p.om_kblocked = d->om_layout == 3;
   p.om_tiles_x = (d->Wo + 7) / 8; p.om_tiles_y = (d->Ho + 15) / 16;
   p.om_tap_stride = (int64_t)d->N * p.om_tiles_x * p.om_tiles_y * 4 * (3 * (d->om_groups / 4)) * 128;
 

@@ -1045,6 +1045,7 @@ struct OmBlocked {
   float* base;
   int tiles_x, tiles_y, G3;     // DCN tiles per image, 3*G
   int64_t tap_stride;           // floats between taps
+  int kblocked;                 // 1: k-step-blocked runs [group / 4][pixel 8][group % 4] (fami_dcn_desc.om_layout 3)
 };
 __device__ __forceinline__ void epilogue_rows_om_blocked(const EpiArgs& a, uint32_t t_addr, int col_begin, int col_end, bool valid,
                                                          int img, int y, int x, const OmBlocked& ob) {
@@ -1053,8 +1054,9 @@ __device__ __forceinline__ void epilogue_rows_om_blocked(const EpiArgs& a, uint3
   const int ry = y & 15, rx = x & 7;
   const int64_t tile = (int64_t)(img * ob.tiles_y + (y >> 4)) * ob.tiles_x + (x >> 3);
   // + k * 8G + g per (dy | dx | mask) run
-  float* lane_base = ob.base + tile * (int64_t)(128 * ob.G3) + (int64_t)(ry * 3) * (8 * G) + rx * G;
-  const int kstride = 8 * G;
+  // + k * 8G + g per (dy | dx | mask) run; k-step-blocked: + k * 8G + (g / 4) * 32 (g is a multiple of 4 here)
+  float* lane_base = ob.base + tile * (int64_t)(128 * ob.G3) + (int64_t)(ry * 3) * (8 * G) + (ob.kblocked ? rx * 4 : rx * G);
+  const int kstride = 8 * G, gmul = ob.kblocked ? 8 : 1;
   for (int c0 = col_begin; c0 < col_end; c0 += 16) {
     const int ch0 = a.ch_base + c0;
     if (ch0 >= a.Cout) break;   // warp-uniform
@@ -1075,7 +1077,7 @@ __device__ __forceinline__ void epilogue_rows_om_blocked(const EpiArgs& a, uint3
           o.y = fmaf(__uint_as_float(v[4 * q + 1]), sc.y, sh.y);
           o.z = fmaf(__uint_as_float(v[4 * q + 2]), sc.z, sh.z);
           o.w = fmaf(__uint_as_float(v[4 * q + 3]), sc.w, sh.w);
-          *reinterpret_cast<float4*>(lane_base + (int64_t)tap * ob.tap_stride + k * kstride + g0) = o;
+          *reinterpret_cast<float4*>(lane_base + (int64_t)tap * ob.tap_stride + k * kstride + g0 * gmul) = o;
         }
       }
     }

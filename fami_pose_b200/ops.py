@@ -294,10 +294,11 @@ def _conv_raw(x, w_packed, Cout, k, stride, pad, dil, scale, shift, residual, re
     return out
 
 
-def conv_offsets_blocked(x, conv, G, out=None):
+def conv_offsets_blocked(x, conv, G, out=None, layout=2):
     """The fused dcn_offset_k | dcn_mask_k convolution (Alignment_V15.py:144-145; `conv` holds the concatenated,
-    tap-major-permuted parameters) writing the row-blocked buffer the tensor-core deformable kernel reads
-    (om_to_blocked layout).  Returns the flat float32 buffer."""
+    tap-major-permuted parameters) writing the blocked buffer the deformable kernel reads (om_to_blocked layout 2 or 3;
+    dcn_blocked_layout names the one the deformable kernel of a shape takes).  Returns the flat float32 buffer, tagged
+    with its layout for dcn_fwd."""
     _need_cuda(x)
     N, Cin, H, W, ip = meta(x)
     k, pad, dil = conv.kernel_size[0], conv.padding[0], conv.dilation[0]
@@ -309,9 +310,10 @@ def conv_offsets_blocked(x, conv, G, out=None):
     code = conv_code(x, Cin)
     w = packed_weight(conv, conv.weight, code)
     _, shift = folded_affine(conv.bias, None)
-    d = ConvDesc(N, H, W, Cin, Cout, k, k, 1, pad, dil, H, W, 1, 0, ip, 0, 0, code, F32, 0, G)
+    d = ConvDesc(N, H, W, Cin, Cout, k, k, 1, pad, dil, H, W, 1, 0, ip, 0, 0, code, F32, 0, G, layout)
     _lib.call("fami_conv2d_bn_act_fwd", ctypes.byref(d), _ptr(x), _ptr(w), None, _ptr(shift), None, _ptr(out), None,
               _stream())
+    out._fami_om_layout = layout
     return out
 
 
@@ -479,7 +481,15 @@ def tap_major_perm(G, k=3):
     return perm
 
 
-DCN_TILE_H, DCN_TILE_W = 16, 8      # pixel tile of the tensor-core DCN kernel (csrc/dcn_tc.cu)
+DCN_TILE_H, DCN_TILE_W = 16, 8      # pixel tile of the blocked offset|mask layouts (fami_dcn_desc.om_layout 2 / 3)
+
+
+def dcn_blocked_layout(C, Cout, G):
+    """The blocked offset|mask layout the deformable kernel of this shape reads: 3 (k-step-blocked) for the warp-private
+    kernel (csrc/dcn_wp.cu: C == Cout in {32, 48}, 4 channels per offset group), else 2 (row-blocked, csrc/dcn_tc.cu)."""
+    import os
+    wp = os.environ.get("FAMI_DCN_WP", "1") != "0"
+    return 3 if wp and C == Cout and C in (32, 48) and 4 * G == C else 2
 
 
 def om_blocked_numel(B, H, W, G, k=3):
@@ -488,8 +498,10 @@ def om_blocked_numel(B, H, W, G, k=3):
     return k * k * B * ty * tx * DCN_TILE_H * DCN_TILE_W * 3 * G
 
 
-def om_to_blocked(om, G, k=3):
-    """tap-major NHWC [B, 27G, H, W] (tap_major_perm order) -> row-blocked layout
+def om_to_blocked(om, G, k=3, layout=2):
+    """layout 3: as below with every (row, dy | dx | mask) run ordered [group / 4][pixel 8][group % 4] (k-step-blocked, the
+    warp-private kernel's).  layout 2:
+    tap-major NHWC [B, 27G, H, W] (tap_major_perm order) -> row-blocked layout
     [tap][image tile][row 16][dy | dx | mask][pixel 8][group G] over 16x8-pixel tiles: a gather warp of the deformable kernel
     owns one tile row and walks its 8*G (pixel, group) samples of a tap 32 at a time -- every load instruction of the warp
     reads 128 contiguous bytes.  Host-side converter for tests and tools; in the model the producer convolution writes this
@@ -502,8 +514,13 @@ def om_to_blocked(om, G, k=3):
         pad = torch.zeros((B, ty * DCN_TILE_H, tx * DCN_TILE_W, K, 3, G), dtype=torch.float32, device=om.device)
         pad[:, :H, :W] = t
         t = pad
-    t = t.reshape(B, ty, DCN_TILE_H, tx, DCN_TILE_W, K, 3, G).permute(5, 0, 1, 3, 2, 6, 4, 7)   # K,B,ty,tx,row,k,pix,G
-    return t.contiguous().reshape(-1)
+    if layout == 3:
+        t = t.reshape(B, ty, DCN_TILE_H, tx, DCN_TILE_W, K, 3, G // 4, 4).permute(5, 0, 1, 3, 2, 6, 7, 4, 8)   # K,B,ty,tx,row,k,G/4,pix,4
+    else:
+        t = t.reshape(B, ty, DCN_TILE_H, tx, DCN_TILE_W, K, 3, G).permute(5, 0, 1, 3, 2, 6, 4, 7)   # K,B,ty,tx,row,k,pix,G
+    out = t.contiguous().reshape(-1)
+    out._fami_om_layout = layout
+    return out
 
 
 def dcn_fwd(x, offset, mask, weight, bias, owner, pad=3, dil=3, out=None, fused_om=None, blocked_om=None, groups=None):
@@ -530,7 +547,8 @@ def dcn_fwd(x, offset, mask, weight, bias, owner, pad=3, dil=3, out=None, fused_
             raise ValueError("row-blocked DCN offsets need 16-bit x, C <= 64 or a multiple of 64, 4 channels per offset group and a "
                              "float32 buffer of om_blocked_numel elements")
         w = packed_weight(owner, weight, x.dtype)
-        d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, 0, 0, outp, 2, _code(x.dtype), out_f32)
+        d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, 0, 0, outp, getattr(blocked_om, "_fami_om_layout", 2),
+                    _code(x.dtype), out_f32)
         _lib.call("fami_dcn_fwd", ctypes.byref(d), _ptr(x), _ptr(blocked_om), None, _ptr(w), _ptr(b), _ptr(out), _stream())
         return out
     if fused_om is not None:

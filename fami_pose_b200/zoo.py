@@ -168,8 +168,9 @@ class Alignment_V15(nn.Module):
         perm = ops.tap_major_perm(self.offset_groups) if fused else None
         conv = self._offmask[k - 1].get(off_m.conv, msk_m.conv, perm)
         if fused:
-            # the producer writes the row-blocked layout the deformable kernel streams (ops.om_to_blocked)
-            buf = ops.conv_offsets_blocked(feat_for_offsets, conv, self.offset_groups)
+            # the producer writes the blocked layout the deformable kernel of this shape streams (ops.om_to_blocked)
+            buf = ops.conv_offsets_blocked(feat_for_offsets, conv, self.offset_groups,
+                                           layout=ops.dcn_blocked_layout(self.width, dcn.out_channels, self.offset_groups))
             return dcn(x, None, None, out=out, blocked_om=buf, groups=self.offset_groups)
         buf = ops.conv_bn_act(feat_for_offsets, conv, None, relu=False, out_dtype=torch.float32)   # sub-pixel offsets stay fp32
         n_off = off_m.conv.out_channels

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define FAMI_ABI_VERSION 2
+#define FAMI_ABI_VERSION 3
 
 enum { FAMI_F32 = 0, FAMI_BF16 = 1, FAMI_F16 = 2, FAMI_TF32 = 3 };
 
@@ -98,6 +98,8 @@ typedef struct fami_conv_desc {
                                     offset groups: Cout = 27*G channels in tap-major order, out_dtype FAMI_F32, up = 1,
                                     no residual, 3x3 stride-1 "same" convolution (the fused dcn_offset_k | dcn_mask_k
                                     producer, Alignment_V15.py:144-145)                                              */
+  int32_t om_layout;             /* with om_groups > 0: 0 or 2 = row-blocked (fami_dcn_desc.om_layout 2); 3 = k-step-blocked
+                                    (fami_dcn_desc.om_layout 3, the warp-private deformable kernel's)                  */
 } fami_conv_desc;
 
 int fami_conv_cout_pad(int Cout);
@@ -184,7 +186,12 @@ typedef struct fami_dcn_desc {
                                        of the deformable kernel owns one tile row and walks its 8*G (pixel, group)
                                        samples of a tap 32 at a time, every load instruction of the warp reads 128
                                        contiguous bytes and the warp's reads of a (row, tap) are one contiguous run of
-                                       24*G floats.  */
+                                       24*G floats.
+                                       3: fused k-step-blocked -- as 2, but a (row, dy | dx | mask) run is ordered
+                                       [group / 4][pixel 8][group % 4]: the warp-private kernel (C == Cout in {32, 48})
+                                       maps lane (pixel, group % 4) of an mma.sync fragment to one sample per k-step
+                                       (= group / 4), so each of its load instructions reads one contiguous 128-byte
+                                       line.  Layout 3 is accepted by that kernel only.  */
   int32_t dtype;                    /* storage of x/out: FAMI_F32 or FAMI_F16 / FAMI_BF16; offset, mask, packed
                                        weights and bias are always float (sub-pixel precision)        */
   int32_t out_f32;                  /* 1 (16-bit dtype, layouts 1 / 2 only): `out` is float while x stays 16-bit -- the

@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol():
     # the ctypes signature table covers exactly the header
     assert sorted(_lib.SIGNATURES) == names
     l = _lib.load()
-    assert l.fami_abi_version() == 2
+    assert l.fami_abi_version() == 3
     assert l.fami_conv_cout_pad(17) == 32 and l.fami_conv_cout_pad(48) == 48
     assert l.fami_packed_weight_elems(48, 48, 3, 3, _lib.F32) == 432 * 48
     assert l.fami_packed_weight_elems(48, 48, 3, 3, _lib.F16) == 48 * 9 * 64
@@ -235,3 +235,9 @@ def test_offset_layout_host_logic():
     assert float(blk[idx]) == float(om[1, 3 * 3 * G + G + 7, 17, 9])
     # the same pixel's mask of group 0 is one (dy | dx | mask) run of 8*G floats further
     assert float(blk[idx - 7 + 8 * G]) == float(om[1, 3 * 3 * G + 2 * G, 17, 9])
+    # layout 3 (k-step-blocked): the same element sits at [group / 4 = 1][pixel 1][group % 4 = 3] of its run
+    blk3 = ops.om_to_blocked(om, G, layout=3)
+    assert torch.equal(torch.sort(blk3).values, torch.sort(om.reshape(-1)).values)
+    run = (((3 * (B * tiles) + tile) * 16 + 1) * 3 + 1) * 8 * G
+    assert float(blk3[run + 1 * 32 + 1 * 4 + 3]) == float(om[1, 3 * 3 * G + G + 7, 17, 9])
+    assert ops.dcn_blocked_layout(48, 48, 12) in (2, 3) and ops.dcn_blocked_layout(128, 128, 32) == 2

@@ -52,7 +52,7 @@ for (H, W) in ((48, 36), (96, 72)):
                 xh = ops.empty_nhwc(B, C, H, W, torch.float16, dev).normal_()
                 om = ops.empty_nhwc(B, 27 * G, H, W, torch.float32, dev).normal_() * 2
                 oh = ops.empty_nhwc(B, C, H, W, torch.float16, dev)
-                blk = ops.om_to_blocked(om, G)      # the layout the model's producer conv writes
+                blk = ops.om_to_blocked(om, G, layout=ops.dcn_blocked_layout(C, C, G))      # the layout the model's producer conv writes
                 t16 = timeit(lambda: dcn(xh, None, None, out=oh, blocked_om=blk, groups=G))
                 del blk
                 alg16 = B * H * W * (2 * 2 * C + 4 * 27 * G) + 2 * (9 * C * C) + 4 * C

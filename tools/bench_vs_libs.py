@@ -80,7 +80,7 @@ fp.set_precision("fp16")
 xh = ops.empty_nhwc(B, C, H, W, torch.float16, dev).normal_()
 om = ops.empty_nhwc(B, 27 * G, H, W, torch.float32, dev).normal_() * 2
 outh = ops.empty_nhwc(B, C, H, W, torch.float16, dev)
-blk = ops.om_to_blocked(om, G)      # the layout the model's producer conv writes
+blk = ops.om_to_blocked(om, G, layout=ops.dcn_blocked_layout(C, C, G))      # the layout the model's producer conv writes
 t_ours16 = timeit(lambda: dcn(xh, None, None, out=outh, blocked_om=blk, groups=G))
 alg32 = 4 * B * H * W * (2 * C + 27 * G)
 alg16 = B * H * W * (2 * 2 * C + 4 * 27 * G)

@@ -13,7 +13,7 @@ out = ops.empty_nhwc(B, C, H, W, torch.float16, "cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for sigma in (0.5, 2.0, 4.0):
     om = ops.empty_nhwc(B, 27 * G, H, W, torch.float32, "cuda").normal_() * sigma
-    blk = ops.om_to_blocked(om, G) if os.environ.get("BLOCKED") else None
+    blk = ops.om_to_blocked(om, G, layout=ops.dcn_blocked_layout(C, C, G)) if os.environ.get("BLOCKED") else None
     run = (lambda: dcn(x, None, None, out=out, blocked_om=blk, groups=G)) if blk is not None else (lambda: dcn(x, None, None, out=out, fused_om=om))
     if blk is not None:
         ref = ops.empty_nhwc(B, C, H, W, torch.float16, "cuda")
