@@ -713,6 +713,7 @@ int conv_halo_launch(const fami_conv_desc* d, const void* x, const void* w, cons
   p.om_kblocked = d->om_layout == 3;
   p.om_tiles_x = (d->W + 7) / 8; p.om_tiles_y = (d->H + 15) / 16;
   p.om_tap_stride = (int64_t)d->N * p.om_tiles_x * p.om_tiles_y * 4 * (3 * (d->om_groups / 4)) * 128;
+  if (p.om_kblocked) p.om_tap_stride = (int64_t)128 * 3 * d->om_groups;   // layout 3 is tile-major: [tile][tap]
   static const bool trace_on = getenv("FAMI_HALO_TRACE") != nullptr;
   p.trace = trace_on ? atoi(getenv("FAMI_HALO_TRACE")) : 0;
 

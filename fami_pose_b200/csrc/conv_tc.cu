@@ -473,6 +473,7 @@ int conv_bf16_tc_launch(const fami_conv_desc* d, const void* x, const void* w, c
   p.om_kblocked = d->om_layout == 3;
   p.om_tiles_x = (d->Wo + 7) / 8; p.om_tiles_y = (d->Ho + 15) / 16;
   p.om_tap_stride = (int64_t)d->N * p.om_tiles_x * p.om_tiles_y * 4 * (3 * (d->om_groups / 4)) * 128;
+  if (p.om_kblocked) p.om_tap_stride = (int64_t)128 * 3 * d->om_groups;   // layout 3 is tile-major: [tile][tap]
 
   const int stage_bytes = kABytes + (pair ? t.BN / 2 : t.BN) * 128;
   p.pipe = (!res32 && !y32 && d->om_groups == 0 && epi_pipe_ok(t.BN, d->Cout, p.vec_ok, out_f32, d->up, res != nullptr, tf32) && d->Cout == t.BN * t.n_tiles &&

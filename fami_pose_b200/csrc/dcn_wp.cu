@@ -20,7 +20,7 @@
 //     while the next tile's three land, so the window refill that dcn_tc.cu exposes per tile is hidden and an image row is
 //     fetched once per strip; zero fill outside the image = torchvision's rule for corners outside;
 //   * offsets|masks are streamed from HBM exactly once: the producer convolution writes them k-step-blocked (om_layout 3:
-//     a (row, dy | dx | mask) run is [group / 4][pixel 8][group % 4], so the 32 lanes (pixel, group % 4) of a load read one
+//     [tile][tap][row 16][dy | dx | mask][group / 4][pixel 8][group % 4], so the 32 lanes (pixel, group % 4) of a load read one
 //     128-byte line; tap-major NHWC is accepted too), prefetched into L2 one tile ahead and into registers two taps ahead;
 //   * samples outside the window (|dy| > 5 px or |dx| > 7 px beyond the dilation) take a bounds-checked global path that
 //     costs the one warp that meets them.
@@ -57,11 +57,10 @@ struct DcnWpParams {
   int tiles_x, tiles_y, ltiles_y;         // compute tiles (kTH x 8) per image; 16-row layout tiles per image column
   int seg_tiles, segs_per_strip, n_segs;  // a segment = up to seg_tiles vertically consecutive tiles of one strip
   int om_pitch, om_hstride;               // tap-major layout: floats per pixel / between image rows
-  int64_t om_tapstride;                   // row-blocked layout: floats between taps
   int x_pitch, out_pitch, vec_ok, out_f32;
   uint32_t chunk_bytes, rowpitch;
   int ablate;                             // FAMI_DCN_ABLATE (timing experiments, results wrong): 1 no stores, 8 no far path,
-                                          // 16 no offset loads
+                                          // 16 no offset loads, 32 offsets loaded but flattened to 0.25 px (no bank conflicts, no far samples)
   const float* om;
   const void* x;
   const void* w;                          // packed [CoutPad][9 taps][64] 16-bit (fami_pack_conv_weight)
@@ -156,7 +155,7 @@ __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {  
 template <int NS> struct OmRegs { float dy[NS], dx[NS], mk[NS]; };
 
 struct SegIt { int seg, k, nt; uint32_t pos0; };       // tile k of segment seg (nt tiles); pos0: ring position of its chunk 0
-struct TileRef { const float* q; uint32_t vmask; int b, y0, x0; };
+struct TileRef { const float* q; uint32_t vmask; int b, y0, x0, wr; };   // wr: the row pair (rows 2 wr, 2 wr + 1) of this warp in the tile
 
 // window pixel pitch (bytes): dense for C = 48, 64 channel slots otherwise
 __host__ __device__ constexpr uint32_t wp_pix_bytes(int KS) { return KS == 3 ? 96u : 128u; }
@@ -267,9 +266,8 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
   for (int i = 0; i < KS; ++i) gofs[i] = kRot ? 4 * ((i + rot) % KS) : 4 * i;
   const int om_hs = BLK ? 3 * kTW * G : p.om_hstride;   // floats between the two rows of the warp
   constexpr int om_cs = BLK ? kTW * G : G;              // floats between dy, dx, mask
-  const int64_t om_ts = BLK ? p.om_tapstride : (int64_t)(3 * G);
+  constexpr int om_ts = BLK ? kLH * kTW * 3 * G : 3 * G;     // floats between taps (layout 3 is tile-major: [tile][tap])
   const float fd = (float)p.d;
-  const float my00 = kMagic + (float)(2 * warp + kRy - p.d);   // window row of the tap's grid point (row h = 0; + kr * d)
   const float mxb = kMagic + (float)(gid + p.Rx - p.d);        // window column of the tap's grid point (+ kc * d)
   // window column address of iteration i = min(column, WW - 2) * pixel pitch + colk[i] (a far sample reads a harmless clamped
   // address and is fixed up afterwards; ring rows are always valid)
@@ -280,16 +278,19 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
 
   auto it_tile = [&](const SegIt& it) {
     TileRef tr;
-    tr.q = p.om; tr.vmask = 0; tr.b = 0; tr.y0 = 0; tr.x0 = 0;
+    tr.q = p.om; tr.vmask = 0; tr.b = 0; tr.y0 = 0; tr.x0 = 0; tr.wr = warp;
     if (it.seg >= p.n_segs) return tr;
     int b, tx, ty0, nt;
     seg_decode(it.seg, b, tx, ty0, nt);
     const int ty = ty0 + it.k;
     tr.b = b; tr.y0 = ty * kTH; tr.x0 = tx * kTW;
-    const int y = tr.y0 + 2 * warp, x = tr.x0 + gid;
+    // the row pairs rotate over the warps from tile to tile: the border rows of a tile meet the window edge (far samples) far
+    // more often than the inner ones, and a warp that is always slower holds up the ring for the other eleven
+    tr.wr = (warp + it.k + it.seg) % kWpWarps;
+    const int y = tr.y0 + 2 * tr.wr, x = tr.x0 + gid;
     if (x < p.W) tr.vmask = (y < p.H ? 1u : 0u) | (y + 1 < p.H ? 2u : 0u);
     if (BLK)
-      tr.q = p.om + (((int64_t)b * p.ltiles_y + (y >> 4)) * p.tiles_x + tx) * (kLH * kTW * 3 * G) + (y & (kLH - 1)) * (3 * kTW * G) + gid * 4 + t;
+      tr.q = p.om + (((int64_t)b * p.ltiles_y + (y >> 4)) * p.tiles_x + tx) * (9 * kLH * kTW * 3 * G) + (y & (kLH - 1)) * (3 * kTW * G) + gid * 4 + t;
     else
       tr.q = p.om + (((int64_t)b * p.H + (y < p.H ? y : 0)) * p.W + (x < p.W ? x : 0)) * p.om_pitch + t;
     if (!tr.vmask) tr.q = p.om;
@@ -344,10 +345,10 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
     const int y1 = y0 + kTH < p.H ? y0 + kTH : p.H;
     for (int y = y0; y < y1;) {                          // per 16-row layout tile: one contiguous run per tap
       const int ye = ((y >> 4) + 1) << 4 < y1 ? ((y >> 4) + 1) << 4 : y1;
-      const float* ptr = p.om + (((int64_t)b * p.ltiles_y + (y >> 4)) * p.tiles_x + tx) * (kLH * kTW * 3 * G) + (y & (kLH - 1)) * (3 * kTW * G);
+      const float* ptr = p.om + (((int64_t)b * p.ltiles_y + (y >> 4)) * p.tiles_x + tx) * (9 * kLH * kTW * 3 * G) + (y & (kLH - 1)) * (3 * kTW * G);
       const uint32_t bytes = (uint32_t)(ye - y) * (3 * kTW * G * 4);
       for (int tap = 0; tap < 9; ++tap)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr + tap * p.om_tapstride), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr + tap * om_ts), "r"(bytes) : "memory");
       y = ye;
     }
   };
@@ -355,7 +356,7 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
   float acc[NT][4];
 
   // one tap: 2*KS samples of this lane -> A fragments -> KS x NT MMAs
-  auto do_tap = [&](const TileRef& tr, const Om& o, int kr, int kc, float my0, float mx, uint32_t base_row) {
+  auto do_tap = [&](const TileRef& tr, const TileRef& trn, const Om& o, Om& oa, int kr, int kc, float my0, float mx, uint32_t base_row) {
     if (is_producer) pr_poll();
     const float my1 = my0 + 1.f;
     uint2 rs[NS];
@@ -366,7 +367,8 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
         const int h = j / KS, i = j - h * KS;
-        const float dy = o.dy[j], dx = o.dx[j], mk = o.mk[j];
+        float dy = o.dy[j], dx = o.dx[j], mk = o.mk[j];
+        if (p.ablate & 32) { dy = fmaf(dy, 1e-30f, 0.25f); dx = fmaf(dx, 1e-30f, 0.25f); }   // loads kept, regular sample positions
         const float my = h ? my1 : my0;
         // floor() through the magic-number add (round-down): exact for |v| < 2^22, the integer lands in the low mantissa bits
         const float ty = __fadd_rd(dy, my), tx = __fadd_rd(dx, mx);
@@ -415,6 +417,10 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
         rs[j].y = *reinterpret_cast<const uint32_t*>(&hi);
       }
     }
+    // (dy, dx, mask) of the tap two ahead: issued here, behind this tap's gather, so that a wait for THIS tap's registers never
+    // covers the fresh loads' scoreboard (issued in front of the tap, the first use of its offsets stalled for a full memory
+    // round trip once per kernel row)
+    load_ahead(tr, trn, kr * 3 + kc, oa);
     // large offsets: entered by the whole warp so that the dependent global loads of all far samples of the tap overlap
     if (__any_sync(0xffffffffu, far) && !(p.ablate & 8)) {
 #pragma unroll
@@ -423,7 +429,7 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
         const float my = h ? my1 : my0;
         const uint32_t v = __float_as_uint(__fadd_rd(o.dy[j], my)) - kMagicBits, u = __float_as_uint(__fadd_rd(o.dx[j], mx)) - kMagicBits;
         if (!(v < kWinRows - 1u && u < xlim)) {
-          const int y = tr.y0 + 2 * warp + h, x = tr.x0 + gid;
+          const int y = tr.y0 + 2 * tr.wr + h, x = tr.x0 + gid;
           rs[j] = dcn_far_sample<TH>(xg + (int64_t)tr.b * p.H * p.W * p.x_pitch + (gofs[i] + t) * 4, p.H, p.W, p.x_pitch,
                                      (float)(y - p.d + kr * p.d) + o.dy[j], (float)(x - p.d + kc * p.d) + o.dx[j], o.mk[j]);
         }
@@ -466,15 +472,12 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
     const uint32_t base_row = (P * kChunk) % (uint32_t)kRingRows;
 #pragma unroll
     for (int n = 0; n < NT; ++n) { acc[n][0] = 0.f; acc[n][1] = 0.f; acc[n][2] = 0.f; acc[n][3] = 0.f; }
-    float my = my00;
+    float my = kMagic + (float)(2 * tc.wr + kRy - p.d);   // window row of the tap's grid point (row h = 0; + kr * d)
 #pragma unroll 1
     for (int kr = 0; kr < 3; ++kr, my += fd) {
-      load_ahead(tc, tn, kr * 3 + 0, o2);
-      do_tap(tc, o0, kr, 0, my, mxb, base_row);
-      load_ahead(tc, tn, kr * 3 + 1, o0);
-      do_tap(tc, o1, kr, 1, my, mxb + fd, base_row);
-      load_ahead(tc, tn, kr * 3 + 2, o1);
-      do_tap(tc, o2, kr, 2, my, mxb + 2.f * fd, base_row);
+      do_tap(tc, tn, o0, o2, kr, 0, my, mxb, base_row);
+      do_tap(tc, tn, o1, o0, kr, 1, my, mxb + fd, base_row);
+      do_tap(tc, tn, o2, o1, kr, 2, my, mxb + 2.f * fd, base_row);
     }
     __syncwarp();
     if (lane == 0) {             // this warp no longer reads the tile's first kADV chunks (all of them at the end of a segment)
@@ -486,7 +489,7 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
       const int x = tc.x0 + gid;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int y = tc.y0 + 2 * warp + h;
+        const int y = tc.y0 + 2 * tc.wr + h;
         const bool valid = y < p.H && x < p.W;                    // (shuffles below are executed by every lane)
         const int64_t pix = valid ? ((int64_t)tc.b * p.H + y) * p.W + x : 0;
         if (p.out_f32) {
@@ -598,7 +601,6 @@ int dcn_wp_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
   const bool blocked = d->om_layout == 3;
   p.om_pitch = d->off_pitch;
   p.om_hstride = d->W * d->off_pitch;
-  p.om_tapstride = (int64_t)d->B * p.tiles_x * p.ltiles_y * kLH * kTW * 3 * d->G;
   p.x_pitch = d->x_pitch; p.out_pitch = d->out_pitch;
   p.out_f32 = d->out_f32 ? 1 : 0;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(out) & 7) == 0) && (d->out_pitch % (d->out_f32 ? 2 : 4) == 0);

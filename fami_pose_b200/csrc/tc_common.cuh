@@ -1055,7 +1055,8 @@ __device__ __forceinline__ void epilogue_rows_om_blocked(const EpiArgs& a, uint3
   const int64_t tile = (int64_t)(img * ob.tiles_y + (y >> 4)) * ob.tiles_x + (x >> 3);
   // + k * 8G + g per (dy | dx | mask) run
   // + k * 8G + g per (dy | dx | mask) run; k-step-blocked: + k * 8G + (g / 4) * 32 (g is a multiple of 4 here)
-  float* lane_base = ob.base + tile * (int64_t)(128 * ob.G3) + (int64_t)(ry * 3) * (8 * G) + (ob.kblocked ? rx * 4 : rx * G);
+  // (layout 3 is tile-major: the nine taps of a tile are contiguous, ob.tap_stride = 128 * 3G)
+  float* lane_base = ob.base + tile * (int64_t)(128 * ob.G3) * (ob.kblocked ? 9 : 1) + (int64_t)(ry * 3) * (8 * G) + (ob.kblocked ? rx * 4 : rx * G);
   const int kstride = 8 * G, gmul = ob.kblocked ? 8 : 1;
   for (int c0 = col_begin; c0 < col_end; c0 += 16) {
     const int ch0 = a.ch_base + c0;

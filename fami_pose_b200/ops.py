@@ -499,8 +499,8 @@ def om_blocked_numel(B, H, W, G, k=3):
 
 
 def om_to_blocked(om, G, k=3, layout=2):
-    """layout 3: as below with every (row, dy | dx | mask) run ordered [group / 4][pixel 8][group % 4] (k-step-blocked, the
-    warp-private kernel's).  layout 2:
+    """layout 3 (k-step-blocked, the warp-private kernel's): [image tile][tap][row 16][dy | dx | mask][group / 4][pixel 8][group % 4]
+    -- tile-major, the nine taps of a tile contiguous.  layout 2:
     tap-major NHWC [B, 27G, H, W] (tap_major_perm order) -> row-blocked layout
     [tap][image tile][row 16][dy | dx | mask][pixel 8][group G] over 16x8-pixel tiles: a gather warp of the deformable kernel
     owns one tile row and walks its 8*G (pixel, group) samples of a tap 32 at a time -- every load instruction of the warp
@@ -515,7 +515,7 @@ def om_to_blocked(om, G, k=3, layout=2):
         pad[:, :H, :W] = t
         t = pad
     if layout == 3:
-        t = t.reshape(B, ty, DCN_TILE_H, tx, DCN_TILE_W, K, 3, G // 4, 4).permute(5, 0, 1, 3, 2, 6, 7, 4, 8)   # K,B,ty,tx,row,k,G/4,pix,4
+        t = t.reshape(B, ty, DCN_TILE_H, tx, DCN_TILE_W, K, 3, G // 4, 4).permute(0, 1, 3, 5, 2, 6, 7, 4, 8)   # B,ty,tx,K,row,k,G/4,pix,4
     else:
         t = t.reshape(B, ty, DCN_TILE_H, tx, DCN_TILE_W, K, 3, G).permute(5, 0, 1, 3, 2, 6, 4, 7)   # K,B,ty,tx,row,k,pix,G
     out = t.contiguous().reshape(-1)

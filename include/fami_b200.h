@@ -187,8 +187,11 @@ typedef struct fami_dcn_desc {
                                        samples of a tap 32 at a time, every load instruction of the warp reads 128
                                        contiguous bytes and the warp's reads of a (row, tap) are one contiguous run of
                                        24*G floats.
-                                       3: fused k-step-blocked -- as 2, but a (row, dy | dx | mask) run is ordered
-                                       [group / 4][pixel 8][group % 4]: the warp-private kernel (C == Cout in {32, 48})
+                                       3: fused k-step-blocked -- ONE dense buffer
+                                       [image tile][9 taps][row 16][dy | dx | mask][group / 4][pixel 8][group % 4] over the
+                                       same 16x8-pixel tiles (tile-major: the 9 * 128 * 3G floats of a tile are one
+                                       contiguous run, a strip of tiles is a handful of sequential DRAM streams instead
+                                       of nine per tile): the warp-private kernel (C == Cout in {32, 48})
                                        maps lane (pixel, group % 4) of an mma.sync fragment to one sample per k-step
                                        (= group / 4), so each of its load instructions reads one contiguous 128-byte
                                        line.  Layout 3 is accepted by that kernel only.  */

@@ -238,6 +238,6 @@ def test_offset_layout_host_logic():
     # layout 3 (k-step-blocked): the same element sits at [group / 4 = 1][pixel 1][group % 4 = 3] of its run
     blk3 = ops.om_to_blocked(om, G, layout=3)
     assert torch.equal(torch.sort(blk3).values, torch.sort(om.reshape(-1)).values)
-    run = (((3 * (B * tiles) + tile) * 16 + 1) * 3 + 1) * 8 * G
+    run = (((tile * 9 + 3) * 16 + 1) * 3 + 1) * 8 * G          # tile-major: [tile][tap][row][dy | dx | mask]
     assert float(blk3[run + 1 * 32 + 1 * 4 + 3]) == float(om[1, 3 * 3 * G + G + 7, 17, 9])
     assert ops.dcn_blocked_layout(48, 48, 12) in (2, 3) and ops.dcn_blocked_layout(128, 128, 32) == 2
