@@ -59,8 +59,9 @@ struct DcnWpParams {
   int om_pitch, om_hstride;               // tap-major layout: floats per pixel / between image rows
   int x_pitch, out_pitch, vec_ok, out_f32;
   uint32_t chunk_bytes, rowpitch;
+  int pf_mode;                            // offsets|masks towards L2: 0 never, 1 a tile at a time, 2 a tap at a time
   int ablate;                             // FAMI_DCN_ABLATE (timing experiments, results wrong): 1 no stores, 8 no far path,
-                                          // 16 no offset loads, 32 offsets loaded but flattened to 0.25 px (no bank conflicts, no far samples)
+                                          // 16 no offset loads
   const float* om;
   const void* x;
   const void* w;                          // packed [CoutPad][9 taps][64] 16-bit (fami_pack_conv_weight)
@@ -184,24 +185,6 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
     asm volatile("fence.proxy.async;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
   }
-  {
-    // filter -> fragment order: lane (gid, t) of (tap, kstep, n-tile) reads W[cout = 8 nt + gid][tap][cin = 16 ks + 4 t .. +3]:
-    // b0 = k-slots 2t, 2t+1, b1 = k-slots 2t+8, 2t+9 of the k order the gather produces
-    const TH* wg = reinterpret_cast<const TH*>(p.w);
-    for (int idx = threadIdx.x; idx < 9 * KS * (NT / 2) * 64; idx += kWpThreads) {
-      const int q = idx & 1, ln = (idx >> 1) & 31, rest = idx >> 6;
-      const int ntp = rest % (NT / 2), tk = rest / (NT / 2);
-      const int ks = tk % KS, tap = tk / KS;
-      const int cout = 8 * (2 * ntp + q) + (ln >> 2);
-      const uint2 v = __ldg(reinterpret_cast<const uint2*>(wg + ((size_t)cout * 9 + tap) * 64 + 16 * ks + 4 * (ln & 3)));
-      sts64(wf_u32 + (uint32_t)idx * 8u, v);
-    }
-    for (int c = threadIdx.x; c < NT * 8; c += kWpThreads) {
-      const float b = (p.bias && c < p.Cout) ? p.bias[c] : 0.f;
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_u32 + 4u * c), "f"(b) : "memory");
-    }
-  }
-  __syncthreads();
 
   const int segs_per_img = p.tiles_x * p.segs_per_strip;
   auto seg_decode = [&](int seg, int& b, int& tx, int& ty0, int& nt) {
@@ -330,14 +313,15 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
       }
     }
   };
+  // the tap three positions ahead in the (tile, tap) stream, into the registers of the tap just gathered
   auto load_ahead = [&](const TileRef& cur, const TileRef& nxt, int tap, Om& o) {
-    if (tap + 2 < 9) load_tap(cur, tap + 2, o);
-    else load_tap(nxt, tap + 2 - 9, o);
+    if (tap + 3 < 9) load_tap(cur, tap + 3, o);
+    else load_tap(nxt, tap + 3 - 9, o);
   };
 
   // offsets|masks of a whole tile (kTH rows x 8 pixels x 9 taps) towards L2, ONE tile ahead of the tile being computed (a
   // longer lead -- it was 3 tiles when the ring producer issued these -- overruns the L2: 31 % hits, 1.3x the DRAM reads)
-  auto prefetch_om = [&](const SegIt& it) {
+  auto prefetch_om = [&](const SegIt& it, int tap0, int tap1) {
     if (!BLK || (p.ablate & 16) || it.seg >= p.n_segs) return;
     int b, tx, ty0, nt;
     seg_decode(it.seg, b, tx, ty0, nt);
@@ -347,17 +331,21 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
       const int ye = ((y >> 4) + 1) << 4 < y1 ? ((y >> 4) + 1) << 4 : y1;
       const float* ptr = p.om + (((int64_t)b * p.ltiles_y + (y >> 4)) * p.tiles_x + tx) * (9 * kLH * kTW * 3 * G) + (y & (kLH - 1)) * (3 * kTW * G);
       const uint32_t bytes = (uint32_t)(ye - y) * (3 * kTW * G * 4);
-      for (int tap = 0; tap < 9; ++tap)
+      for (int tap = tap0; tap < tap1; ++tap)
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr + tap * om_ts), "r"(bytes) : "memory");
       y = ye;
     }
   };
 
   float acc[NT][4];
+  SegIt cur, nxt;
 
   // one tap: 2*KS samples of this lane -> A fragments -> KS x NT MMAs
-  auto do_tap = [&](const TileRef& tr, const TileRef& trn, const Om& o, Om& oa, int kr, int kc, float my0, float mx, uint32_t base_row) {
-    if (is_producer) pr_poll();
+  auto do_tap = [&](const TileRef& tr, const TileRef& trn, Om& o, int kr, int kc, float my0, float mx, uint32_t base_row) {
+    if (is_producer) {
+      pr_poll();
+      if (p.pf_mode == 2) prefetch_om(nxt, kr * 3 + kc, kr * 3 + kc + 1);
+    }
     const float my1 = my0 + 1.f;
     uint2 rs[NS];
     bool far = false;
@@ -367,8 +355,7 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
         const int h = j / KS, i = j - h * KS;
-        float dy = o.dy[j], dx = o.dx[j], mk = o.mk[j];
-        if (p.ablate & 32) { dy = fmaf(dy, 1e-30f, 0.25f); dx = fmaf(dx, 1e-30f, 0.25f); }   // loads kept, regular sample positions
+        const float dy = o.dy[j], dx = o.dx[j], mk = o.mk[j];
         const float my = h ? my1 : my0;
         // floor() through the magic-number add (round-down): exact for |v| < 2^22, the integer lands in the low mantissa bits
         const float ty = __fadd_rd(dy, my), tx = __fadd_rd(dx, mx);
@@ -417,10 +404,6 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
         rs[j].y = *reinterpret_cast<const uint32_t*>(&hi);
       }
     }
-    // (dy, dx, mask) of the tap two ahead: issued here, behind this tap's gather, so that a wait for THIS tap's registers never
-    // covers the fresh loads' scoreboard (issued in front of the tap, the first use of its offsets stalled for a full memory
-    // round trip once per kernel row)
-    load_ahead(tr, trn, kr * 3 + kc, oa);
     // large offsets: entered by the whole warp so that the dependent global loads of all far samples of the tap overlap
     if (__any_sync(0xffffffffu, far) && !(p.ablate & 8)) {
 #pragma unroll
@@ -436,6 +419,10 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
       }
       __syncwarp();
     }
+    // (dy, dx, mask) of the tap THREE ahead, into the registers this tap has just finished with (the far path above was their
+    // last reader): three buffers give 2.4 taps of lead instead of the 1.5 of a load into the previous tap's buffer; issued
+    // behind the gather, so that a wait for this tap's registers never covers the fresh loads' scoreboard
+    load_ahead(tr, trn, kr * 3 + kc, o);
     const uint32_t wtap = wf_u32 + (uint32_t)((kr * 3 + kc) * KS) * (uint32_t)(NT / 2) * 512u + (uint32_t)lane * 16u;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
@@ -456,17 +443,36 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
     }
   };
 
-  SegIt cur, nxt;
   cur.seg = blockIdx.x; cur.k = 0; cur.pos0 = 0; cur.nt = 0;
   if (cur.seg < p.n_segs) { int b, tx, ty0; seg_decode(cur.seg, b, tx, ty0, cur.nt); }
   nxt = it_next(cur);
   TileRef tc = it_tile(cur), tn = it_tile(nxt);
-  Om o0, o1, o2;                       // taps 3i, 3i+1, 3i+2 of the stream: rotating, two taps in flight
-  if (is_producer) prefetch_om(cur);
+  Om o0, o1, o2;                       // taps 3i, 3i+1, 3i+2 of the stream: rotating, three taps in flight
+  if (is_producer && p.pf_mode) prefetch_om(cur, 0, 9);
   load_tap(tc, 0, o0);
   load_tap(tc, 1, o1);
+  load_tap(tc, 2, o2);
+  // (the first window chunks and the first two taps' offsets are already in flight: the repack below hides behind them)
+  {
+    // filter -> fragment order: lane (gid, t) of (tap, kstep, n-tile) reads W[cout = 8 nt + gid][tap][cin = 16 ks + 4 t .. +3]:
+    // b0 = k-slots 2t, 2t+1, b1 = k-slots 2t+8, 2t+9 of the k order the gather produces
+    const TH* wg = reinterpret_cast<const TH*>(p.w);
+    for (int idx = threadIdx.x; idx < 9 * KS * (NT / 2) * 64; idx += kWpThreads) {
+      const int q = idx & 1, ln = (idx >> 1) & 31, rest = idx >> 6;
+      const int ntp = rest % (NT / 2), tk = rest / (NT / 2);
+      const int ks = tk % KS, tap = tk / KS;
+      const int cout = 8 * (2 * ntp + q) + (ln >> 2);
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(wg + ((size_t)cout * 9 + tap) * 64 + 16 * ks + 4 * (ln & 3)));
+      sts64(wf_u32 + (uint32_t)idx * 8u, v);
+    }
+    for (int c = threadIdx.x; c < NT * 8; c += kWpThreads) {
+      const float b = (p.bias && c < p.Cout) ? p.bias[c] : 0.f;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_u32 + 4u * c), "f"(b) : "memory");
+    }
+  }
+  __syncthreads();
   while (cur.seg < p.n_segs) {
-    if (is_producer) prefetch_om(nxt);
+    if (is_producer && p.pf_mode == 1) prefetch_om(nxt, 0, 9);
     const uint32_t P = cur.pos0 + (uint32_t)(kADV * cur.k);       // first chunk of this tile in the stream
     for (uint32_t c = cur.k == 0 ? 0u : (uint32_t)(kNCH - kADV); c < (uint32_t)kNCH; ++c) wait_full(P + c);
     const uint32_t base_row = (P * kChunk) % (uint32_t)kRingRows;
@@ -475,9 +481,9 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
     float my = kMagic + (float)(2 * tc.wr + kRy - p.d);   // window row of the tap's grid point (row h = 0; + kr * d)
 #pragma unroll 1
     for (int kr = 0; kr < 3; ++kr, my += fd) {
-      do_tap(tc, tn, o0, o2, kr, 0, my, mxb, base_row);
-      do_tap(tc, tn, o1, o0, kr, 1, my, mxb + fd, base_row);
-      do_tap(tc, tn, o2, o1, kr, 2, my, mxb + 2.f * fd, base_row);
+      do_tap(tc, tn, o0, kr, 0, my, mxb, base_row);
+      do_tap(tc, tn, o1, kr, 1, my, mxb + fd, base_row);
+      do_tap(tc, tn, o2, kr, 2, my, mxb + 2.f * fd, base_row);
     }
     __syncwarp();
     if (lane == 0) {             // this warp no longer reads the tile's first kADV chunks (all of them at the end of a segment)
@@ -607,6 +613,7 @@ int dcn_wp_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
   p.rowpitch = (uint32_t)p.WW * pixb;
   p.chunk_bytes = (uint32_t)kChunk * p.rowpitch;
   p.ablate = wp_env("FAMI_DCN_ABLATE", 0);
+  p.pf_mode = wp_env("FAMI_DCN_WP_PF", 0);   // measured: 121 / 135 / 137 us for modes 0 / 1 / 2 (the register loads run 2.4 taps ahead)
   p.om = om; p.x = x; p.w = w; p.bias = bias; p.out = out;
 
   const CUtensorMapDataType tm_dtype = d->dtype == FAMI_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
