@@ -21,7 +21,8 @@
 //     fetched once per strip; zero fill outside the image = torchvision's rule for corners outside;
 //   * offsets|masks are streamed from HBM exactly once: the producer convolution writes them k-step-blocked (om_layout 3:
 //     [tile][tap][row 16][dy | dx | mask][group / 4][pixel 8][group % 4], so the 32 lanes (pixel, group % 4) of a load read one
-//     128-byte line; tap-major NHWC is accepted too), prefetched into L2 one tile ahead and into registers two taps ahead;
+//     128-byte line; tap-major NHWC is accepted too), loaded into registers three taps ahead (2.4 taps of lead; bulk L2 prefetches a tile or a tap ahead measured 12-17 %
+//     SLOWER and are gone);
 //   * samples outside the window (|dy| > 5 px or |dx| > 7 px beyond the dilation) take a bounds-checked global path that
 //     costs the one warp that meets them.
 #include <stdlib.h>
@@ -59,7 +60,6 @@ struct DcnWpParams {
   int om_pitch, om_hstride;               // tap-major layout: floats per pixel / between image rows
   int x_pitch, out_pitch, vec_ok, out_f32;
   uint32_t chunk_bytes, rowpitch;
-  int pf_mode;                            // offsets|masks towards L2: 0 never, 1 a tile at a time, 2 a tap at a time
   int ablate;                             // FAMI_DCN_ABLATE (timing experiments, results wrong): 1 no stores, 8 no far path,
                                           // 16 no offset loads
   const float* om;
@@ -161,6 +161,16 @@ struct TileRef { const float* q; uint32_t vmask; int b, y0, x0, wr; };   // wr: 
 // window pixel pitch (bytes): dense for C = 48, 64 channel slots otherwise
 __host__ __device__ constexpr uint32_t wp_pix_bytes(int KS) { return KS == 3 ? 96u : 128u; }
 
+// segment -> (image, strip, first tile row, tiles); out of line: the integer divisions stay out of the tap loop's code
+__device__ __noinline__ void wp_seg_decode(int seg, int segs_per_img, int segs_per_strip, int seg_tiles, int tiles_y, int& b, int& tx,
+                                           int& ty0, int& nt) {
+  b = seg / segs_per_img;
+  const int r = seg - b * segs_per_img;
+  tx = r / segs_per_strip;
+  ty0 = (r - tx * segs_per_strip) * seg_tiles;
+  nt = tiles_y - ty0 < seg_tiles ? tiles_y - ty0 : seg_tiles;
+}
+
 template <typename TH, int KS, int NT, bool BLK>
 __global__ void __launch_bounds__(kWpThreads, 1)
 dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
@@ -188,11 +198,7 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
 
   const int segs_per_img = p.tiles_x * p.segs_per_strip;
   auto seg_decode = [&](int seg, int& b, int& tx, int& ty0, int& nt) {
-    b = seg / segs_per_img;
-    const int r = seg - b * segs_per_img;
-    tx = r / p.segs_per_strip;
-    ty0 = (r - tx * p.segs_per_strip) * p.seg_tiles;
-    nt = p.tiles_y - ty0 < p.seg_tiles ? p.tiles_y - ty0 : p.seg_tiles;
+    wp_seg_decode(seg, segs_per_img, p.segs_per_strip, p.seg_tiles, p.tiles_y, b, tx, ty0, nt);
   };
 
   // ---- producer state (meaningful in lane 0 of warp 0): next chunk of the CTA's chunk stream ----
@@ -319,33 +325,12 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
     else load_tap(nxt, tap + 3 - 9, o);
   };
 
-  // offsets|masks of a whole tile (kTH rows x 8 pixels x 9 taps) towards L2, ONE tile ahead of the tile being computed (a
-  // longer lead -- it was 3 tiles when the ring producer issued these -- overruns the L2: 31 % hits, 1.3x the DRAM reads)
-  auto prefetch_om = [&](const SegIt& it, int tap0, int tap1) {
-    if (!BLK || (p.ablate & 16) || it.seg >= p.n_segs) return;
-    int b, tx, ty0, nt;
-    seg_decode(it.seg, b, tx, ty0, nt);
-    const int y0 = (ty0 + it.k) * kTH;
-    const int y1 = y0 + kTH < p.H ? y0 + kTH : p.H;
-    for (int y = y0; y < y1;) {                          // per 16-row layout tile: one contiguous run per tap
-      const int ye = ((y >> 4) + 1) << 4 < y1 ? ((y >> 4) + 1) << 4 : y1;
-      const float* ptr = p.om + (((int64_t)b * p.ltiles_y + (y >> 4)) * p.tiles_x + tx) * (9 * kLH * kTW * 3 * G) + (y & (kLH - 1)) * (3 * kTW * G);
-      const uint32_t bytes = (uint32_t)(ye - y) * (3 * kTW * G * 4);
-      for (int tap = tap0; tap < tap1; ++tap)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr + tap * om_ts), "r"(bytes) : "memory");
-      y = ye;
-    }
-  };
-
   float acc[NT][4];
   SegIt cur, nxt;
 
   // one tap: 2*KS samples of this lane -> A fragments -> KS x NT MMAs
   auto do_tap = [&](const TileRef& tr, const TileRef& trn, Om& o, int kr, int kc, float my0, float mx, uint32_t base_row) {
-    if (is_producer) {
-      pr_poll();
-      if (p.pf_mode == 2) prefetch_om(nxt, kr * 3 + kc, kr * 3 + kc + 1);
-    }
+    if (kc == 0 && is_producer) pr_poll();      // once per kernel row: three polls per tile, three chunks to issue per tile
     const float my1 = my0 + 1.f;
     uint2 rs[NS];
     bool far = false;
@@ -448,7 +433,6 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
   nxt = it_next(cur);
   TileRef tc = it_tile(cur), tn = it_tile(nxt);
   Om o0, o1, o2;                       // taps 3i, 3i+1, 3i+2 of the stream: rotating, three taps in flight
-  if (is_producer && p.pf_mode) prefetch_om(cur, 0, 9);
   load_tap(tc, 0, o0);
   load_tap(tc, 1, o1);
   load_tap(tc, 2, o2);
@@ -472,7 +456,6 @@ dcn_wp_kernel(const __grid_constant__ CUtensorMap tmX, const DcnWpParams p) {
   }
   __syncthreads();
   while (cur.seg < p.n_segs) {
-    if (is_producer && p.pf_mode == 1) prefetch_om(nxt, 0, 9);
     const uint32_t P = cur.pos0 + (uint32_t)(kADV * cur.k);       // first chunk of this tile in the stream
     for (uint32_t c = cur.k == 0 ? 0u : (uint32_t)(kNCH - kADV); c < (uint32_t)kNCH; ++c) wait_full(P + c);
     const uint32_t base_row = (P * kChunk) % (uint32_t)kRingRows;
@@ -613,7 +596,6 @@ int dcn_wp_launch(const fami_dcn_desc* d, const void* x, const float* om, const 
   p.rowpitch = (uint32_t)p.WW * pixb;
   p.chunk_bytes = (uint32_t)kChunk * p.rowpitch;
   p.ablate = wp_env("FAMI_DCN_ABLATE", 0);
-  p.pf_mode = wp_env("FAMI_DCN_WP_PF", 0);   // measured: 121 / 135 / 137 us for modes 0 / 1 / 2 (the register loads run 2.4 taps ahead)
   p.om = om; p.x = x; p.w = w; p.bias = bias; p.out = out;
 
   const CUtensorMapDataType tm_dtype = d->dtype == FAMI_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
