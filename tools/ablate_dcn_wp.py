@@ -4,8 +4,6 @@ import os, subprocess, sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 for name, env in (("shipped kernel", {}), ("no epilogue stores", {"FAMI_DCN_ABLATE": "1"}), ("no far-sample path", {"FAMI_DCN_ABLATE": "8"}),
                   ("no offset loads (constants: regular sample positions, no far samples)", {"FAMI_DCN_ABLATE": "16"}),
-                  ("offsets|masks bulk-prefetched into L2 a tile ahead", {"FAMI_DCN_WP_PF": "1"}),
-                  ("offsets|masks bulk-prefetched into L2 a tap at a time", {"FAMI_DCN_WP_PF": "2"}),
                   ("segments of one tile (no ring reuse between tiles)", {"FAMI_DCN_WP_SEG": "1"}),
                   ("tcgen05 kernel (dcn_tc.cu, row-blocked offsets)", {"FAMI_DCN_WP": "0"})):
     e = dict(os.environ, BLOCKED="1", **env)
