@@ -548,7 +548,7 @@ def dcn_roofline(fp, ops, dev, stream, B, pk):
     traffic = None
     try:   # DRAM bytes of the same launch from the committed ncu --set full capture (16-bit arm, B=32)
         if half and B == 32:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["dcn_tc_kernel_fp16_B32"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["dcn_wp_kernel_fp16_B32"]
     except Exception:
         traffic = None
     return {"kernel": "fami_dcn_fwd (modulated deformable conv, C=48 G=12 96x72 B=%d, x/out %s, offsets fp32%s)"

@@ -291,7 +291,8 @@ int fami_conv2d_wgrad(const fami_conv_desc* d, const float* x, const float* grad
                       void* stream) {
   if (int e = check_conv_bwd(d, "fami_conv2d_wgrad")) return e;
   FAMI_CHECK_ARG(x && grad_y && grad_w_oihw, "fami_conv2d_wgrad: null pointer");
-  FAMI_CHECK_ARG(d->dtype == FAMI_F32, "fami_conv2d_wgrad: fp32 arithmetic (pass FAMI_F32)");
+  FAMI_CHECK_ARG(d->dtype == FAMI_F32 || d->dtype == FAMI_TF32, "fami_conv2d_wgrad: fp32 storage (FAMI_F32: exact FMAs; FAMI_TF32: "
+                                                                  "TF32 tensor cores, fp32 accumulation)");
   return conv_wgrad_launch(d, x, grad_y, grad_w_oihw, grad_bias, (cudaStream_t)stream);
 }
 

@@ -166,6 +166,171 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// wgrad on the tensor cores ('tf32' arm): the same (tap, 64 ci, 64 co) tile over a slab of pixels, but the products run on
+// mma.sync.m16n8k8 TF32 with fp32 accumulation: D[ci][co] += sum_pixels x[pixel @ tap][ci] * gy[pixel][co], i.e. M = ci,
+// N = co, K = pixels.  Both operands are staged pixel-major (as they lie in HBM) with a 72-float pitch: lane (gid, t) of a
+// fragment reads [k = t (+4)][m or n = gid (+8)], i.e. bank 8 t + gid -- conflict-free scalar loads, no transposition.
+// Operands are rounded to nearest TF32 on their way into shared memory (the tensor core would truncate).  8 warps: four
+// 32 x 32 warp tiles x two K groups (pixels 0-15 / 16-31 of a 32-pixel chunk), register double buffering of the global
+// loads, the K groups reduced through shared memory before the fp32 atomics.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWmPix = 32, kWmPitch = 72;
+__device__ __forceinline__ float tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32_1688(float (&c)[4], float a0, float a1, float a2, float a3, float b0, float b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(a2)), "r"(__float_as_uint(a3)),
+        "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+template <bool kVec>
+__global__ void __launch_bounds__(256) conv_wgrad_tf32_kernel(const float* __restrict__ x, int x_pitch,
+                                                              const float* __restrict__ gy, int gy_pitch,
+                                                              float* __restrict__ dw, int N, int H, int W, int Cin, int Cout,
+                                                              int kh, int kw, int stride, int pad, int dil, int Ho, int Wo,
+                                                              int ci_tiles, int co_tiles, int pix_per_block) {
+  __shared__ __align__(16) float xs[2][kWmPix][kWmPitch];
+  __shared__ __align__(16) float gs[2][kWmPix][kWmPitch];
+  int tile = blockIdx.x;
+  const int cot = tile % co_tiles; tile /= co_tiles;
+  const int cit = tile % ci_tiles; tile /= ci_tiles;
+  const int tap = tile;
+  const int r = tap / kw, s = tap - r * kw;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gid = lane >> 2, t = lane & 3;
+  const int kg = warp >> 2;                     // K group: pixels 16 kg .. 16 kg + 15 of a chunk
+  const int m0 = (warp & 1) * 32, n0 = ((warp >> 1) & 1) * 32;
+  const int npix = N * Ho * Wo;                 // (< 2^31: checked by the entry point)
+  const int p0 = blockIdx.y * pix_per_block;
+  const int p1 = p0 + pix_per_block < npix ? p0 + pix_per_block : npix;
+  // this thread stages pixels (tid >> 4) and (tid >> 4) + 16 of a chunk, channels 4 * (tid & 15) .. + 3
+  const int c = (tid & 15) << 2;
+  const int ci = cit * 64 + c, co = cot * 64 + c;
+  float4 xr[2], gr[2];
+  // (n, yo, xo) of this thread's two pixels of the chunk being fetched, advanced by 32 pixels per chunk without divisions
+  int fn[2], fy[2], fx[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int p = p0 + (tid >> 4) + 16 * h;
+    fx[h] = p % Wo;
+    const int q = p / Wo;
+    fy[h] = q % Ho;
+    fn[h] = q / Ho;
+  }
+  auto fetch = [&](int pb) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int p = pb + (tid >> 4) + 16 * h;
+      xr[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      gr[h] = xr[h];
+      if (p < p1) {
+        const int yi = fy[h] * stride - pad + r * dil, xi = fx[h] * stride - pad + s * dil;
+        if (kVec) {       // 16-byte loads: Cin, Cout and both pitches are multiples of 4
+          if (ci < Cin && yi >= 0 && yi < H && xi >= 0 && xi < W)
+            xr[h] = __ldg(reinterpret_cast<const float4*>(x + ((int64_t)(fn[h] * H + yi) * W + xi) * x_pitch + ci));
+          if (co < Cout) gr[h] = __ldg(reinterpret_cast<const float4*>(gy + (int64_t)p * gy_pitch + co));
+        } else {          // ragged channel counts (the 17-joint heatmap convolution): element-wise
+          if (yi >= 0 && yi < H && xi >= 0 && xi < W) {
+            const float* sx = x + ((int64_t)(fn[h] * H + yi) * W + xi) * x_pitch + ci;
+            if (ci < Cin) xr[h].x = __ldg(sx);
+            if (ci + 1 < Cin) xr[h].y = __ldg(sx + 1);
+            if (ci + 2 < Cin) xr[h].z = __ldg(sx + 2);
+            if (ci + 3 < Cin) xr[h].w = __ldg(sx + 3);
+          }
+          const float* sg = gy + (int64_t)p * gy_pitch + co;
+          if (co < Cout) gr[h].x = __ldg(sg);
+          if (co + 1 < Cout) gr[h].y = __ldg(sg + 1);
+          if (co + 2 < Cout) gr[h].z = __ldg(sg + 2);
+          if (co + 3 < Cout) gr[h].w = __ldg(sg + 3);
+        }
+      }
+      fx[h] += kWmPix;
+      while (fx[h] >= Wo) {
+        fx[h] -= Wo;
+        if (++fy[h] == Ho) { fy[h] = 0; ++fn[h]; }
+      }
+    }
+  };
+  auto store = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int pl = (tid >> 4) + 16 * h;
+      *reinterpret_cast<float4*>(&xs[buf][pl][c]) = make_float4(tf32_rna(xr[h].x), tf32_rna(xr[h].y), tf32_rna(xr[h].z), tf32_rna(xr[h].w));
+      *reinterpret_cast<float4*>(&gs[buf][pl][c]) = make_float4(tf32_rna(gr[h].x), tf32_rna(gr[h].y), tf32_rna(gr[h].z), tf32_rna(gr[h].w));
+    }
+  };
+  float acc[2][4][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
+  int buf = 0;
+  if (p0 < p1) {
+    fetch(p0);
+    store(0);
+  }
+  __syncthreads();
+  for (int pb = p0; pb < p1; pb += kWmPix) {
+    const bool more = pb + kWmPix < p1;
+    if (more) fetch(pb + kWmPix);               // in flight while this chunk is multiplied
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int kb = 16 * kg + 8 * ks;
+      float a[2][4], b[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        a[mt][0] = xs[buf][kb + t][m0 + 16 * mt + gid];
+        a[mt][1] = xs[buf][kb + t][m0 + 16 * mt + gid + 8];
+        a[mt][2] = xs[buf][kb + t + 4][m0 + 16 * mt + gid];
+        a[mt][3] = xs[buf][kb + t + 4][m0 + 16 * mt + gid + 8];
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        b[nt][0] = gs[buf][kb + t][n0 + 8 * nt + gid];
+        b[nt][1] = gs[buf][kb + t + 4][n0 + 8 * nt + gid];
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32_1688(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b[nt][0], b[nt][1]);
+    }
+    if (more) store(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  // K group 1 hands its partial tile to K group 0 through shared memory (the staging buffers are free now)
+  float* red = &xs[0][0][0];                    // 4 warps x 32 values x 32 lanes = 16 KB <= sizeof(xs)
+  if (kg == 1) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) red[(((warp & 3) * 32) + (mt * 4 + nt) * 4 + e) * 32 + lane] = acc[mt][nt][e];
+  }
+  __syncthreads();
+  if (kg == 0) {
+    const int taps = kh * kw;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float v = acc[mt][nt][e] + red[((warp * 32) + (mt * 4 + nt) * 4 + e) * 32 + lane];
+          const int oci = cit * 64 + m0 + 16 * mt + gid + 8 * (e >> 1);
+          const int oco = cot * 64 + n0 + 8 * nt + 2 * t + (e & 1);
+          if (oci < Cin && oco < Cout) atomicAdd(dw + ((int64_t)oco * Cin + oci) * taps + tap, v);
+        }
+  }
+}
+
 // Same tile decomposition, double buffered: the (pixels x 64 ci) slab of x at this tap and the (pixels x 64 co) slab of gy
 // of chunk k+1 are in flight (cp.async, 16 bytes per request, zero-filled outside the image / beyond the channel count)
 // while chunk k is multiplied.  The single-buffered kernel above exposed a global round trip per 32 pixels.
@@ -558,7 +723,14 @@ int conv_wgrad_launch(const fami_conv_desc* d, const float* x, const float* gy, 
   const bool vec = d->Cin % 4 == 0 && d->Cout % 4 == 0 && d->in_pitch % 4 == 0 && d->out_pitch % 4 == 0 &&
                    (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(gy) & 15) == 0;
   static const bool single = getenv("FAMI_WGRAD_SINGLE") != nullptr;     // A/B: the single-buffered kernel
-  if (vec && !single)
+  static const bool no_tc = getenv("FAMI_WGRAD_SIMT") != nullptr;        // A/B: the 'tf32' arm's wgrad on the fp32 FMA kernel
+  if (d->dtype == FAMI_TF32 && !no_tc && vec)
+    conv_wgrad_tf32_kernel<true><<<grid, 256, 0, st>>>(x, d->in_pitch, gy, d->out_pitch, dw, d->N, d->H, d->W, d->Cin, d->Cout,
+                                                       d->kh, d->kw, d->stride, d->pad, d->dil, d->Ho, d->Wo, ci_tiles, co_tiles, (int)per);
+  else if (d->dtype == FAMI_TF32 && !no_tc)
+    conv_wgrad_tf32_kernel<false><<<grid, 256, 0, st>>>(x, d->in_pitch, gy, d->out_pitch, dw, d->N, d->H, d->W, d->Cin, d->Cout,
+                                                        d->kh, d->kw, d->stride, d->pad, d->dil, d->Ho, d->Wo, ci_tiles, co_tiles, (int)per);
+  else if (vec && !single)
     conv_wgrad_db_kernel<<<grid, 256, 0, st>>>(x, d->in_pitch, gy, d->out_pitch, dw, d->N, d->H, d->W, d->Cin, d->Cout,
                                                d->kh, d->kw, d->stride, d->pad, d->dil, d->Ho, d->Wo, ci_tiles, co_tiles, (int)per);
   else if (vec)

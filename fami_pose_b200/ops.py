@@ -726,7 +726,8 @@ def conv_dgrad(grad_y, weight, x_shape, stride=1, pad=0, dil=1, out=None):
 
 
 def conv_wgrad(x, grad_y, weight_shape, stride=1, pad=0, dil=1, want_bias=False):
-    """(d loss / d weight [OIHW], d loss / d bias or None) of y = conv2d(x, weight) + bias."""
+    """(d loss / d weight [OIHW], d loss / d bias or None) of y = conv2d(x, weight) + bias.  Exact fp32 FMAs on the 'fp32'
+    arm, TF32 tensor cores with fp32 accumulation on the 'tf32' arm."""
     _need_cuda(x, grad_y)
     if x.dtype != torch.float32 or grad_y.dtype != torch.float32:
         raise ValueError("conv_wgrad: fp32 activations only")
@@ -734,6 +735,8 @@ def conv_wgrad(x, grad_y, weight_shape, stride=1, pad=0, dil=1, want_bias=False)
     d, Ho, Wo = _conv_desc_f32(meta(x), Cout, k, stride, pad, dil, meta(grad_y)[4])
     if tuple(grad_y.shape) != (x.shape[0], Cout, Ho, Wo) or x.shape[1] != Cin:
         raise ValueError("conv_wgrad: shape mismatch")
+    if _PRECISION == "tf32":
+        d.dtype = TF32          # 'tf32' arm: the products on mma.sync TF32 (operands rounded to nearest), fp32 accumulation
     gw = torch.zeros(tuple(weight_shape), dtype=torch.float32, device=x.device)
     gb = torch.zeros(Cout, dtype=torch.float32, device=x.device) if want_bias else None
     _lib.call("fami_conv2d_wgrad", ctypes.byref(d), _ptr(x), _ptr(grad_y), _ptr(gw), _ptr(gb), _stream())

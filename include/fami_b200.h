@@ -127,7 +127,9 @@ int fami_conv2d_bn_act_fwd_stream(const fami_conv_desc* d, const void* x, const 
  * elements); stride-1 dgrad runs on the forward kernels -- d->dtype = FAMI_F32: exact SIMT,
  * FAMI_TF32: tcgen05 kind::tf32 with a FAMI_TF32 packing -- other strides on an fp32 gather kernel.
  * wgrad ACCUMULATES into grad_w_oihw [Cout][Cin][kh][kw] and grad_bias [Cout] (may be NULL):
- * the caller zeroes them (fp32 atomics over pixel chunks).                                        */
+ * the caller zeroes them (fp32 atomics over pixel chunks).  d->dtype = FAMI_F32: exact fp32 FMAs;
+ * FAMI_TF32: the products on mma.sync TF32 tensor cores (operands rounded to nearest TF32 on their
+ * way into shared memory, fp32 accumulation).                                                        */
 int fami_pack_conv_weight_dgrad(const float* w_oihw, float* scratch_oihw, void* w_packed_t, int Cout, int Cin,
                                 int kh, int kw, int dtype, void* stream);
 int fami_conv2d_dgrad(const fami_conv_desc* d, const float* grad_y, const float* w_packed_t, float* grad_x,

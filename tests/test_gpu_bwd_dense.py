@@ -81,6 +81,38 @@ def test_conv_dgrad_tf32_vs_autograd(case):
         fp.set_precision("fp32")
 
 
+@pytest.mark.parametrize("case", CONV_CASES + [(2, 48, 324, 40, 30, 3, 1, 3, 3, True)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv_wgrad_tf32_vs_autograd(case):
+    """wgrad on the 'tf32' arm (mma.sync TF32, fp32 accumulation, fp32 atomics over pixel slabs; csrc/bwd_dense.cu
+    conv_wgrad_tf32_kernel): x and grad_y pre-rounded to TF32, so that only the accumulation order differs from float64
+    autograd -- incl. strides, dilation 3, two ci tiles, ragged channel counts (element-wise staging) and a map with several
+    pixel slabs per tile."""
+    N, Cin, Cout, H, W, k, stride, pad, dil, bias = case
+    fp.set_precision("tf32")
+    try:
+        g = torch.Generator().manual_seed(300 + Cin + Cout)
+        x = _tf32_rna64(torch.randn(N, Cin, H, W, generator=g, dtype=torch.float64))
+        w = (torch.randn(Cout, Cin, k, k, generator=g, dtype=torch.float64) * 0.1).requires_grad_()
+        b = torch.randn(Cout, generator=g, dtype=torch.float64, requires_grad=True) if bias else None
+        y = F.conv2d(x, w, b, stride, pad, dil)
+        gy = _tf32_rna64(torch.randn(y.shape, generator=g, dtype=torch.float64))
+        y.backward(gy)
+        gw, gb = ops.conv_wgrad(_nhwc(x), _nhwc(gy), (Cout, Cin, k, k), stride, pad, dil, want_bias=bias)
+        assert _rel(gw.double().cpu(), w.grad) < 2e-5
+        if bias:
+            assert _rel(gb.double().cpu(), b.grad) < 2e-5
+        # unrounded operands: the result moves by TF32's rounding of the operands only (2^-11 relative per factor)
+        xu = torch.randn(N, Cin, H, W, generator=g, dtype=torch.float64)
+        gyu = torch.randn(y.shape, generator=g, dtype=torch.float64)
+        w2 = w.detach().clone().requires_grad_()
+        F.conv2d(xu, w2, None, stride, pad, dil).backward(gyu)
+        gw2, _ = ops.conv_wgrad(_nhwc(xu), _nhwc(gyu), (Cout, Cin, k, k), stride, pad, dil)
+        assert _rel(gw2.double().cpu(), w2.grad) < 2e-3
+    finally:
+        fp.set_precision("fp32")
+
+
 def test_conv_dgrad_into_channel_slice():
     """grad_x written into a channel slice of a wider buffer (the concat operands of Alignment_V15.py:143,160)."""
     fp.set_precision("fp32")

@@ -1,3 +1,7 @@
+"""Hot spots of one kernel from an ncu report taken with --set full --import-source on:
+    python tools/ncu_hotspots.py report.ncu-rep [units]
+headline counters, executed warp instructions per opcode (per `units`, default 124416 = the warp-taps of the config-2
+deformable launch), warp-state samples, the instructions with the most samples and the shared-memory wavefront totals."""
 import csv, collections, re, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu","-i",rep,"--page","raw","--csv"],capture_output=True,text=True).stdout
@@ -9,7 +13,7 @@ for i,h in enumerate(hdr):
 src = subprocess.run(["ncu","-i",rep,"--page","source","--csv","--print-source","sass"],capture_output=True,text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 hdr = rows[1]; ix = {h:i for i,h in enumerate(hdr)}; data = rows[2:]
-NWT = 124416.0
+NWT = float(sys.argv[2]) if len(sys.argv) > 2 else 124416.0
 tot_exec = sum(int(r[ix["Instructions Executed"]] or 0) for r in data)
 tot_samp = sum(int(r[ix["# Samples"]] or 0) for r in data)
 print("total exec", tot_exec, "per warp-tap", tot_exec/NWT, "samples", tot_samp)

@@ -1,5 +1,6 @@
 """Timeline of CTA 0 of the tensor-core DCN kernel (FAMI_DCN_TRACE=1)."""
 import os
+os.environ.setdefault("FAMI_DCN_WP", "0")   # the per-tap timeline is the tcgen05 kernel's (csrc/dcn_tc.cu)
 os.environ["FAMI_PROBES"] = "1"   # fami_debug_* live in libfami_b200_probes.so (csrc/build.py --probes)
 import os, sys, ctypes
 os.environ.setdefault("FAMI_DCN_TRACE", "1")
