@@ -6,7 +6,7 @@ import ctypes
 import torch
 
 from . import _lib, ops
-from ._lib import DcnDesc, F32
+from ._lib import DcnDesc, F32, TF32
 
 
 class DeformConvFunction(torch.autograd.Function):
@@ -40,7 +40,8 @@ class DeformConvFunction(torch.autograd.Function):
         gw = torch.empty(kh * kw * C * cpad, dtype=torch.float32, device=dev)
         gb = torch.empty(Cout, dtype=torch.float32, device=dev)
         w = ops.packed_weight(owner, weight, torch.float32)
-        d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, offp, mp, gop, 0, F32)
+        # 'tf32' arm: the weight gradient's products on TF32 tensor cores (everything else of the backward stays exact fp32)
+        d = DcnDesc(B, H, W, C, Cout, G, kh, kw, 1, pad, dil, xp, offp, mp, gop, 0, TF32 if ops._PRECISION == "tf32" else F32)
         _lib.call("fami_dcn_bwd", ctypes.byref(d), ops._ptr(x), ops._ptr(offset), ops._ptr(mask), ops._ptr(w),
                   ops._ptr(go), ops._ptr(gx), ops._ptr(goff), ops._ptr(gmask), ops._ptr(gw), ops._ptr(gb), ops._stream())
         # packed [taps][C][CoutPad] -> OIHW

@@ -456,7 +456,8 @@ int fami_dcn_bwd(const fami_dcn_desc* d, const float* x, const float* offset, co
                  float* grad_w_packed, float* grad_bias, void* stream) {
   if (int e = check_dcn(d, "fami_dcn_bwd")) return e;
   FAMI_CHECK_ARG(x && offset && mask && w_packed && grad_out, "fami_dcn_bwd: null pointer");
-  FAMI_CHECK_ARG(d->dtype == FAMI_F32, "fami_dcn_bwd: fp32 storage only");
+  FAMI_CHECK_ARG(d->dtype == FAMI_F32 || d->dtype == FAMI_TF32, "fami_dcn_bwd: fp32 storage only (FAMI_F32: exact; FAMI_TF32: the "
+                                                                  "weight gradient's products on TF32 tensor cores)");
   return dcn_bwd_launch(d, x, offset, mask, w_packed, grad_out, grad_x, grad_offset, grad_mask, grad_w_packed,
                         grad_bias, (cudaStream_t)stream);
 }

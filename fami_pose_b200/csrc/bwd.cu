@@ -4,6 +4,8 @@
 //   fami_warp_translate_bwd -- backward of kornia warp_affine for pure translations (Alignment_V15.py:133-135)
 // First correct versions: straightforward SIMT with atomics for the scatters; they complete the ABI so the
 // reference's trainable head (1.06 M parameters with the frozen HRNet default) can be differentiated.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fami {
@@ -13,6 +15,9 @@ namespace {
 struct BwdP {
   int B, H, W, C, Cout, CoutPad, G, cpg, d;
   int xp, offp, mp, gop;
+  int tf32;            // weight gradient products on mma.sync TF32 (FAMI_TF32 descriptors), else exact fp32 FMAs
+  int tap_minor;       // weight-gradient grid: (9 taps, chunks) instead of (chunks, 9 taps)
+  int colp, gosp;      // shared-memory row pitches of the weight-gradient kernel's column / grad_out slabs
   const float* x;
   const float* off;
   const float* mask;
@@ -24,6 +29,12 @@ struct BwdP {
   float* gw;           // packed [9*C][CoutPad], zeroed by the launcher
   float* gb;           // [Cout], zeroed by the launcher
 };
+
+__device__ __forceinline__ float tf32_rna_b(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   // 16-byte vector reduction (sm_90+): one L2 atomic transaction for the 4 channels of a corner
@@ -131,10 +142,12 @@ __global__ void __launch_bounds__(512, 2) dcn_bwd_data_kernel(const BwdP p) {
 constexpr int kWChunk = 64;
 __global__ void __launch_bounds__(256) dcn_bwd_weight_kernel(const BwdP p) {
   extern __shared__ float sm[];
-  float* s_col = sm;                        // [kWChunk][C]
-  float* s_go = sm + kWChunk * p.C;         // [kWChunk][Cout]
-  const int tap = blockIdx.y;
-  const int64_t pix0 = (int64_t)blockIdx.x * kWChunk;
+  float* s_col = sm;                        // [kWChunk][colp]
+  float* s_go = sm + kWChunk * p.colp;      // [kWChunk][gosp]  (pitches == 8 | 24 mod 32: conflict-free fragment loads)
+  // the nine taps of a pixel chunk are adjacent blocks (blockIdx.x = tap): the chunk's offsets, masks and grad_out are
+  // read from DRAM once and from the L2 eight times (tap-major block order streamed the 287 MB of offsets nine times)
+  const int tap = p.tap_minor ? blockIdx.x : blockIdx.y;
+  const int64_t pix0 = (int64_t)(p.tap_minor ? blockIdx.y : blockIdx.x) * kWChunk;
   const int64_t npix = (int64_t)p.B * p.H * p.W;
   const int fr = tap / 3, fs = tap - fr * 3;
   const int quads = p.C >> 2;
@@ -170,24 +183,56 @@ __global__ void __launch_bounds__(256) dcn_bwd_weight_kernel(const BwdP p) {
         val.w = mk * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w);
       }
     }
-    *reinterpret_cast<float4*>(s_col + pl * p.C + (q << 2)) = val;
+    if (p.tf32) { val.x = tf32_rna_b(val.x); val.y = tf32_rna_b(val.y); val.z = tf32_rna_b(val.z); val.w = tf32_rna_b(val.w); }
+    *reinterpret_cast<float4*>(s_col + pl * p.colp + (q << 2)) = val;
   }
   for (int e = threadIdx.x; e < kWChunk * p.Cout; e += blockDim.x) {
     const int pl = e / p.Cout, o = e - pl * p.Cout;
     const int64_t pix = pix0 + pl;
-    s_go[e] = pix < npix ? __ldg(p.go + pix * p.gop + o) : 0.f;
+    const float gv = pix < npix ? __ldg(p.go + pix * p.gop + o) : 0.f;
+    s_go[pl * p.gosp + o] = gv;       // (kept unrounded: the bias gradient below sums it exactly; rounded at fragment load)
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < p.C * p.Cout; e += blockDim.x) {
-    const int c = e / p.Cout, o = e - c * p.Cout;
-    float s = 0.f;
-    for (int pl = 0; pl < kWChunk; ++pl) s = fmaf(s_col[pl * p.C + c], s_go[pl * p.Cout + o], s);
-    atomicAdd(p.gw + (int64_t)(tap * p.C + c) * p.CoutPad + o, s);
+  if (p.tf32) {
+    // D[c][o] += sum_pixels col[pixel][c] * g_out[pixel][o] on mma.sync.m16n8k8 TF32 (M = c, N = o, K = the 64 pixels of
+    // the chunk): both slabs are pixel-major, lane (gid, t) of a fragment reads [k = t (+4)][m | n = gid (+8)]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, t = lane & 3;
+    const int mt_n = (p.C + 15) >> 4, nt_n = (p.Cout + 7) >> 3;
+    for (int tile = warp; tile < mt_n * nt_n; tile += 8) {
+      const int mt = tile / nt_n, nt = tile - mt * nt_n;
+      const int c0 = 16 * mt + gid, o0 = 8 * nt + gid;
+      const bool c0ok = c0 < p.C, c1ok = c0 + 8 < p.C, ook = o0 < p.Cout;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kb = 0; kb < kWChunk; kb += 8) {
+        const float* ca = s_col + (kb + t) * p.colp;
+        const float* cb = ca + 4 * p.colp;
+        const float* ga = s_go + (kb + t) * p.gosp;
+        const float a0 = c0ok ? ca[c0] : 0.f, a1 = c1ok ? ca[c0 + 8] : 0.f, a2 = c0ok ? cb[c0] : 0.f, a3 = c1ok ? cb[c0 + 8] : 0.f;
+        const float b0 = ook ? tf32_rna_b(ga[o0]) : 0.f, b1 = ook ? tf32_rna_b(ga[4 * p.gosp + o0]) : 0.f;
+        asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+            : "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(a2)), "r"(__float_as_uint(a3)),
+              "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {      // acc = {(c0, 2t), (c0, 2t+1), (c0+8, 2t), (c0+8, 2t+1)} of the (mt, nt) tile
+        const int c = 16 * mt + gid + 8 * (e >> 1), o = 8 * nt + 2 * t + (e & 1);
+        if (c < p.C && o < p.Cout) atomicAdd(p.gw + (int64_t)(tap * p.C + c) * p.CoutPad + o, acc[e]);
+      }
+    }
+  } else {
+    for (int e = threadIdx.x; e < p.C * p.Cout; e += blockDim.x) {
+      const int c = e / p.Cout, o = e - c * p.Cout;
+      float s = 0.f;
+      for (int pl = 0; pl < kWChunk; ++pl) s = fmaf(s_col[pl * p.colp + c], s_go[pl * p.gosp + o], s);
+      atomicAdd(p.gw + (int64_t)(tap * p.C + c) * p.CoutPad + o, s);
+    }
   }
   if (tap == 0 && p.gb) {
     for (int o = threadIdx.x; o < p.Cout; o += blockDim.x) {
       float s = 0.f;
-      for (int pl = 0; pl < kWChunk; ++pl) s += s_go[pl * p.Cout + o];
+      for (int pl = 0; pl < kWChunk; ++pl) s += s_go[pl * p.gosp + o];
       atomicAdd(p.gb + o, s);
     }
   }
@@ -297,10 +342,18 @@ int dcn_bwd_launch(const fami_dcn_desc* d, const float* x, const float* off, con
     dcn_bwd_data_kernel<false><<<(unsigned)blocks, 512, 0, st>>>(p);
   }
   FAMI_CHECK_LAUNCH("dcn_bwd_data_kernel");
-  const size_t smem = (size_t)kWChunk * (d->C + d->Cout) * sizeof(float);
+  // slab pitches: exact arm dense; tf32 arm == 8 | 24 (mod 32) floats so that the four k rows of a fragment load hit
+  // different banks (and a multiple of 4 for the float4 column stores)
+  auto frag_pitch = [](int n) { int q = (n + 3) & ~3; while (q % 32 != 8 && q % 32 != 24) q += 4; return q; };
+  p.tf32 = d->dtype == FAMI_TF32 && getenv("FAMI_DCN_BWD_SIMT") == nullptr;
+  p.colp = p.tf32 ? frag_pitch(d->C) : d->C;
+  p.gosp = p.tf32 ? frag_pitch(d->Cout) : d->Cout;
+  const size_t smem = (size_t)kWChunk * (p.colp + p.gosp) * sizeof(float);
   FAMI_CHECK_ARG(smem <= 200 * 1024, "fami_dcn_bwd: C + Cout too large for the weight-gradient kernel");
   cudaFuncSetAttribute(dcn_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid(cdiv(npix, kWChunk), 9);
+  const int chunks = cdiv(npix, kWChunk);
+  p.tap_minor = chunks <= 65535 && getenv("FAMI_DCN_BWD_TAPMAJOR") == nullptr;
+  dim3 grid(p.tap_minor ? 9 : chunks, p.tap_minor ? chunks : 9);
   dcn_bwd_weight_kernel<<<grid, 256, smem, st>>>(p);
   FAMI_CHECK_LAUNCH("dcn_bwd_weight_kernel");
   return 0;

@@ -210,7 +210,9 @@ int fami_dcn_fwd(const fami_dcn_desc* d, const void* x, const void* offset, cons
 /* backward (fp32 storage, om_layout 0): grad wrt input (atomic scatter), offset+mask, weight+bias.
  * torchvision: deformable_col2im / deformable_col2im_coord + GEMMs.  Gradient buffers
  * are DENSE (grad_x [B,H,W,C], grad_offset [B,H,W,18G], grad_mask [B,H,W,9G], grad_w_packed in the
- * fp32 packed layout [9*C][CoutPad], grad_bias [Cout] or NULL) and are zero-filled by the call.   */
+ * fp32 packed layout [9*C][CoutPad], grad_bias [Cout] or NULL) and are zero-filled by the call.
+ * d->dtype = FAMI_F32: exact fp32 throughout; FAMI_TF32: the weight gradient's products (sampled columns x
+ * grad_out over 64-pixel chunks) run on mma.sync TF32 with fp32 accumulation, everything else stays exact.  */
 int fami_dcn_bwd(const fami_dcn_desc* d, const float* x, const float* offset, const float* mask,
                  const float* w_packed, const float* grad_out, float* grad_x, float* grad_offset,
                  float* grad_mask, float* grad_w_packed, float* grad_bias, void* stream);
