@@ -757,7 +757,10 @@ int bn_bwd_launch(const float* x, int xp, const float* gy, int gp, const float* 
                   const float* invstd, const float* gamma, int64_t rows, int C, int training, double* sums, float* dx,
                   int dxp, float* g_res, int grp, float* dgamma, float* dbeta, cudaStream_t st) {
   FAMI_CHECK_ARG(C <= 1024, "bn bwd: C <= 1024");
-  int threads = 1024, RG = threads / C, rows_per_block = 2048;
+  int threads = 1024, RG = threads / C;
+  // at least two blocks per SM (the head's maps at N = 32 are 221 K rows: 108 blocks of 2048 rows left a quarter of the SMs idle)
+  int rows_per_block = (int)(rows / (2 * num_sms()));
+  rows_per_block = rows_per_block > 2048 ? 2048 : (rows_per_block < 4 * RG ? 4 * RG : rows_per_block);
   bn_bwd_reduce_kernel<<<cdiv(rows, rows_per_block), threads, (size_t)2 * RG * C * sizeof(float), st>>>(
       x, xp, gy, gp, y, yp, mean, invstd, rows, C, sums, rows_per_block);
   FAMI_CHECK_LAUNCH("bn_bwd_reduce_kernel");
