@@ -205,7 +205,10 @@ __global__ void __launch_bounds__(1024) bn_stats_vec4_kernel(const float* __rest
   const int tid = threadIdx.x, q = tid % cq, rg = tid / cq;
   int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), t = s, s2 = s, t2 = s;
+  // per-thread sums of the shifted values in DOUBLE: the result does not depend on how the rows are cut into blocks and
+  // row groups (to ~1e-16), so the grid can follow the SM count; the shared-memory hand-over stays double as well
+  double s[4] = {0., 0., 0., 0.}, t[4] = {0., 0., 0., 0.};
+  double* smd = reinterpret_cast<double*>(sm);
   if (rg < RG) {
     // shifted sums, see bn_stats_kernel
     const float4 k = __ldg(reinterpret_cast<const float4*>(x) + q);
@@ -215,26 +218,25 @@ __global__ void __launch_bounds__(1024) bn_stats_vec4_kernel(const float* __rest
       float4 b = __ldg(reinterpret_cast<const float4*>(x + (r + RG) * pitch) + q);
       a.x -= k.x; a.y -= k.y; a.z -= k.z; a.w -= k.w;
       b.x -= k.x; b.y -= k.y; b.z -= k.z; b.w -= k.w;
-      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-      t.x = fmaf(a.x, a.x, t.x); t.y = fmaf(a.y, a.y, t.y); t.z = fmaf(a.z, a.z, t.z); t.w = fmaf(a.w, a.w, t.w);
-      s2.x += b.x; s2.y += b.y; s2.z += b.z; s2.w += b.w;
-      t2.x = fmaf(b.x, b.x, t2.x); t2.y = fmaf(b.y, b.y, t2.y); t2.z = fmaf(b.z, b.z, t2.z); t2.w = fmaf(b.w, b.w, t2.w);
+      s[0] += (double)a.x + (double)b.x; s[1] += (double)a.y + (double)b.y; s[2] += (double)a.z + (double)b.z; s[3] += (double)a.w + (double)b.w;
+      t[0] += (double)a.x * a.x + (double)b.x * b.x; t[1] += (double)a.y * a.y + (double)b.y * b.y;
+      t[2] += (double)a.z * a.z + (double)b.z * b.z; t[3] += (double)a.w * a.w + (double)b.w * b.w;
     }
     if (r < r1) {
       float4 a = __ldg(reinterpret_cast<const float4*>(x + r * pitch) + q);
       a.x -= k.x; a.y -= k.y; a.z -= k.z; a.w -= k.w;
-      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-      t.x = fmaf(a.x, a.x, t.x); t.y = fmaf(a.y, a.y, t.y); t.z = fmaf(a.z, a.z, t.z); t.w = fmaf(a.w, a.w, t.w);
+      s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w;
+      t[0] += (double)a.x * a.x; t[1] += (double)a.y * a.y; t[2] += (double)a.z * a.z; t[3] += (double)a.w * a.w;
     }
-    float* ps = sm + (rg * C + 4 * q);
-    float* pq = sm + ((RG + rg) * C + 4 * q);
-    ps[0] = s.x + s2.x; ps[1] = s.y + s2.y; ps[2] = s.z + s2.z; ps[3] = s.w + s2.w;
-    pq[0] = t.x + t2.x; pq[1] = t.y + t2.y; pq[2] = t.z + t2.z; pq[3] = t.w + t2.w;
+    double* ps = smd + (rg * C + 4 * q);
+    double* pq = smd + ((RG + rg) * C + 4 * q);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { ps[e] = s[e]; pq[e] = t[e]; }
   }
   __syncthreads();
   if (tid < C && r1 > r0) {
     double ds = 0, dq = 0;
-    for (int r = 0; r < RG; ++r) { ds += sm[r * C + tid]; dq += sm[(RG + r) * C + tid]; }
+    for (int r = 0; r < RG; ++r) { ds += smd[r * C + tid]; dq += smd[(RG + r) * C + tid]; }
     const double kd = (double)__ldg(x + tid), n = (double)(r1 - r0);
     atomicAdd(stats + tid, ds + n * kd);
     atomicAdd(stats + C + tid, dq + 2.0 * kd * ds + n * kd * kd);
@@ -564,8 +566,10 @@ int bn_stats_launch(const void* x, int dt, int pitch, int64_t rows, int C, doubl
     int threads = 512;
     if (cq > threads) threads = ((cq + 31) / 32) * 32;
     const int RG = threads / cq;
-    const int rows_per_block = 1024;
-    const size_t smem = (size_t)2 * RG * C * sizeof(float);
+    // at least two blocks per SM: the low-resolution branches (12x9x384 at N = 160: 17 K rows) ran on 17 blocks of 1024 rows
+    int rows_per_block = (int)(rows / (2 * num_sms()));
+    rows_per_block = rows_per_block > 1024 ? 1024 : (rows_per_block < 4 * RG ? 4 * RG : rows_per_block);
+    const size_t smem = (size_t)2 * RG * C * sizeof(double);
     bn_stats_vec4_kernel<<<cdiv(rows, rows_per_block), threads, smem, st>>>((const float*)x, pitch, rows, C, stats,
                                                                            rows_per_block);
     FAMI_CHECK_LAUNCH("bn_stats_vec4");
