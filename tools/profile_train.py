@@ -28,6 +28,11 @@ def timed(name, *args):
     if name in ("fami_conv2d_bn_act_fwd", "fami_conv2d_dgrad", "fami_conv2d_wgrad"):
         d = args[0]._obj
         key = "%s Cin=%d Cout=%d k=%d s=%d d=%d %dx%d N=%d dt=%d" % (name[5:], d.Cin, d.Cout, d.kh, d.stride, d.dil, d.H, d.W, d.N, d.dtype)
+    if name == "fami_bn_apply_act" and os.environ.get("BN_BY_SHAPE"):
+        # (x, x_dtype, x_pitch, scale, shift, res, res_pitch, y, y_pitch, y_dtype, N, Ho, Wo, C, up, relu, stream)
+        key = "bn_apply_act N=%d %dx%d C=%d res=%d" % (args[10], args[11], args[12], args[13], int(args[5] is not None and bool(args[5])))
+    if name == "fami_bn_stats" and os.environ.get("BN_BY_SHAPE"):
+        key = "bn_stats rows=%d C=%d" % (args[3], args[4])
     e0.record(); orig(name, *args); e1.record()
     records.append((key, e0, e1))
 for mod in (_lib, ops, ag, tr):
@@ -41,5 +46,5 @@ for k, e0, e1 in records:
     agg[k][0] += 1; agg[k][1] += e0.elapsed_time(e1)
 tot = sum(v[1] for v in agg.values())
 print("step %.1f ms wall on device; %.2f ms inside %d C-ABI calls (eager, event-timed)" % (w0.elapsed_time(w1), tot, len(records)))
-for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(os.environ.get('TOPN', 40))]:
     print("%8.3f ms %5.1f%% n=%3d avg %7.1f us  %s" % (t, 100 * t / tot, n, 1000 * t / n, k))
