@@ -510,6 +510,71 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, int x_pitch, co
   dx[r * dx_pitch + c] = k * v;
 }
 
+// 16-byte form of bn_bwd_apply_kernel (C, pitches multiples of 4, 16-byte aligned tensors): two pieces per thread, the loads of
+// both issued before the first use (the element-per-thread kernel keeps 4 bytes per tensor in flight per thread)
+__global__ void __launch_bounds__(256) bn_bwd_apply_vec4_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ gy,
+                                                                int gy_pitch, const float* __restrict__ y, int y_pitch,
+                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                const float* __restrict__ gamma, const double* __restrict__ sums,
+                                                                int64_t rows, int C, int training, float* __restrict__ dx,
+                                                                int dx_pitch, float* __restrict__ g_res, int gres_pitch,
+                                                                float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int cq = C >> 2;
+  const int64_t base = (int64_t)blockIdx.x * 512 + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int64_t ch = base + 256 * k;
+    if (ch < C) {
+      if (dgamma) dgamma[ch] = (float)sums[C + ch];
+      if (dbeta) dbeta[ch] = (float)sums[ch];
+    }
+  }
+  const int64_t tot = rows * cq;
+  float4 g[2], yv[2], xv[2];
+  int c[2];
+  int64_t r[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int64_t i = base + 256 * k;
+    r[k] = i / cq;
+    c[k] = (int)(i - r[k] * cq) << 2;
+    if (i < tot) {
+      g[k] = __ldg(reinterpret_cast<const float4*>(gy + r[k] * gy_pitch + c[k]));
+      if (y) yv[k] = __ldg(reinterpret_cast<const float4*>(y + r[k] * y_pitch + c[k]));
+      if (dx && training) xv[k] = __ldg(reinterpret_cast<const float4*>(x + r[k] * x_pitch + c[k]));
+    }
+  }
+  const double inv_m = 1.0 / (double)rows;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (base + 256 * k >= tot) continue;
+    float ga[4] = {g[k].x, g[k].y, g[k].z, g[k].w};
+    if (y) {
+      const float ya[4] = {yv[k].x, yv[k].y, yv[k].z, yv[k].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (!(ya[e] > 0.f)) ga[e] = 0.f;
+    }
+    if (g_res) *reinterpret_cast<float4*>(g_res + r[k] * gres_pitch + c[k]) = make_float4(ga[0], ga[1], ga[2], ga[3]);
+    if (!dx) continue;
+    const float xa[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w};
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int ch = c[k] + e;
+      const float is = invstd[ch];
+      const float kk = (gamma ? gamma[ch] : 1.f) * is;
+      float v = ga[e];
+      if (training) {
+        const float xhat = (xa[e] - mean[ch]) * is;
+        v = ga[e] - (float)(sums[ch] * inv_m) - xhat * (float)(sums[C + ch] * inv_m);
+      }
+      o[e] = kk * v;
+    }
+    *reinterpret_cast<float4*>(dx + r[k] * dx_pitch + c[k]) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // MI pseudo-KL backward.  Per row (sample, channel) over l: p = softmax(a/T), t = softmax(b/T),
 // L = sum t (log t - p);  dL/da_j = -(1/T) p_j (t_j - S),  S = sum t p;
@@ -765,8 +830,15 @@ int bn_bwd_launch(const float* x, int xp, const float* gy, int gp, const float* 
       x, xp, gy, gp, y, yp, mean, invstd, rows, C, sums, rows_per_block);
   FAMI_CHECK_LAUNCH("bn_bwd_reduce_kernel");
   int64_t tot = rows * C;
-  bn_bwd_apply_kernel<<<cdiv(tot, 256), 256, 0, st>>>(x, xp, gy, gp, y, yp, mean, invstd, gamma, sums, rows, C, training, dx,
-                                                      dxp, g_res, grp, dgamma, dbeta);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool vec = C % 4 == 0 && C >= 4 && xp % 4 == 0 && gp % 4 == 0 && (!y || yp % 4 == 0) && (!dx || dxp % 4 == 0) &&
+                   (!g_res || grp % 4 == 0) && al16(x) && al16(gy) && al16(y) && al16(dx) && al16(g_res);
+  if (vec)
+    bn_bwd_apply_vec4_kernel<<<cdiv(tot / 4 > C ? tot / 4 : C, 512), 256, 0, st>>>(x, xp, gy, gp, y, yp, mean, invstd, gamma, sums, rows, C, training,
+                                                                 dx, dxp, g_res, grp, dgamma, dbeta);
+  else
+    bn_bwd_apply_kernel<<<cdiv(tot, 256), 256, 0, st>>>(x, xp, gy, gp, y, yp, mean, invstd, gamma, sums, rows, C, training, dx,
+                                                        dxp, g_res, grp, dgamma, dbeta);
   FAMI_CHECK_LAUNCH("bn_bwd_apply_kernel");
   return 0;
 }
