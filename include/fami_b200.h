@@ -183,9 +183,10 @@ typedef struct fami_dcn_desc {
                                        [9 taps][image tile][row 16][dy | dx | mask][pixel 8][group G] over 16x8-pixel
                                        tiles (tile = (b * ceil(H/16) + y/16) * ceil(W/8) + x/8, row = y%16, pixel = x%8);
                                        pitches and `mask` ignored.
-                                       Layouts 1 and 2 are the 16-bit tensor-core kernel's; the alignment head's fused
-                                       offset|mask convolution writes layout 2 (fami_conv_desc.om_groups): a gather warp
-                                       of the deformable kernel owns one tile row and walks its 8*G (pixel, group)
+                                       Layouts 1 - 3 are the 16-bit tensor-core kernels' (1: both; 2: the tcgen05 kernel,
+                                       csrc/dcn_tc.cu; 3: the warp-private kernel, csrc/dcn_wp.cu); the alignment head's
+                                       fused offset|mask convolution writes layout 2 or 3 (fami_conv_desc.om_groups /
+                                       om_layout).  Layout 2: a gather warp of the tcgen05 kernel owns one tile row and walks its 8*G (pixel, group)
                                        samples of a tap 32 at a time, every load instruction of the warp reads 128
                                        contiguous bytes and the warp's reads of a (row, tap) are one contiguous run of
                                        24*G floats.
@@ -199,9 +200,9 @@ typedef struct fami_dcn_desc {
                                        line.  Layout 3 is accepted by that kernel only.  */
   int32_t dtype;                    /* storage of x/out: FAMI_F32 or FAMI_F16 / FAMI_BF16; offset, mask, packed
                                        weights and bias are always float (sub-pixel precision)        */
-  int32_t out_f32;                  /* 1 (16-bit dtype, layouts 1 / 2 only): `out` is float while x stays 16-bit -- the
+  int32_t out_f32;                  /* 1 (16-bit dtype, layouts 1 - 3 only): `out` is float while x stays 16-bit -- the
                                        tf32 arm's deformable convolutions: x is cast to fp16 (same 11-bit significand as
-                                       TF32), the contraction runs on kind::f16 with fp32 accumulation, the result
+                                       TF32), the contraction runs on 16-bit tensor-core MMAs with fp32 accumulation, the result
                                        returns to the fp32 activation stream.  0: out has the storage type of x.       */
 } fami_dcn_desc;
 
