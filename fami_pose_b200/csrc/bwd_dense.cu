@@ -787,6 +787,7 @@ int conv_wgrad_launch(const fami_conv_desc* d, const float* x, const float* gy, 
   dim3 grid(tiles, splits);
   const bool vec = d->Cin % 4 == 0 && d->Cout % 4 == 0 && d->in_pitch % 4 == 0 && d->out_pitch % 4 == 0 &&
                    (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(gy) & 15) == 0;
+  FAMI_CHECK_ARG(npix < (1ll << 31) - 2 * per, "conv wgrad: too many output pixels");
   static const bool single = getenv("FAMI_WGRAD_SINGLE") != nullptr;     // A/B: the single-buffered kernel
   static const bool no_tc = getenv("FAMI_WGRAD_SIMT") != nullptr;        // A/B: the 'tf32' arm's wgrad on the fp32 FMA kernel
   if (d->dtype == FAMI_TF32 && !no_tc && vec)
